@@ -1,0 +1,345 @@
+/*
+ * hx_oracle.c — CPU restatement of dft-efe's H.X / Chebyshev / Rayleigh-Ritz
+ * hot path.  TEST INFRASTRUCTURE ONLY: this file is the checker the CUDA path
+ * is compared against (tests/, __graft_entry__.smoke(), bench.py's
+ * cpu_baseline / --impl reference legs).  Nothing under dft_efe_b200/ may
+ * import, link or call it.
+ *
+ * Parity status: the H.X composite is UNPINNED by the reference's own tests
+ * (test/ksdft/src/TestHXOrthoEFE.cpp only prints norms and is
+ * disabled).  The leaf routines below are pinned against (a) the reference's
+ * own compiled sources where they build without deal.II/MPI (oracle/_ref, see
+ * oracle/Makefile: ConstraintsInternal.cpp, DiscontiguousDataOperations.cpp,
+ * BlasLapackKernels.cpp, ChebyshevFilter.t.cpp) and (b) the golden vectors in
+ * the reference's tests (tests/golden/).
+ *
+ * Every routine cites the reference file:line it restates (paths relative to
+ * /root/reference/src).  All data FP64; size_type = uint32_t.
+ */
+#include <stddef.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+
+typedef uint32_t u32;
+
+/* ---------------------------------------------------------------- BLAS --- */
+/* Fortran-ABI dgemm as the reference calls it (linearAlgebra/BlasAPIWrapperHost.cpp:97-137,
+ * linearAlgebra/BlasLapackTemplates.h:188).  An optimised BLAS can be plugged in
+ * at run time (orc_set_dgemm, e.g. SciPy's OpenBLAS dgemm pointer) so that the
+ * CPU baseline does "one dgemm_ per cell through an optimised BLAS" like the
+ * reference; otherwise the built-in loops below are used. */
+typedef void (*dgemm_fn)(const char *, const char *, const int *, const int *, const int *,
+                         const double *, const double *, const int *, const double *, const int *,
+                         const double *, double *, const int *);
+static dgemm_fn g_dgemm = NULL;
+void orc_set_dgemm(void *fn) { g_dgemm = (dgemm_fn)fn; }
+
+static int is_trans(char t) { return t == 'T' || t == 't' || t == 'C' || t == 'c'; }
+
+/* column-major C(m x n) = alpha*op(A)(m x k)*op(B)(k x n) + beta*C */
+static void builtin_dgemm(char ta, char tb, int m, int n, int k, double alpha, const double *A,
+                          int lda, const double *Bm, int ldb, double beta, double *C, int ldc)
+{
+    const int tA = is_trans(ta), tB = is_trans(tb);
+    for (int j = 0; j < n; ++j) {
+        double *c = C + (size_t)j * ldc;
+        if (beta == 0.0)
+            for (int i = 0; i < m; ++i) c[i] = 0.0;
+        else if (beta != 1.0)
+            for (int i = 0; i < m; ++i) c[i] *= beta;
+        for (int l = 0; l < k; ++l) {
+            const double b = alpha * (tB ? Bm[j + (size_t)l * ldb] : Bm[l + (size_t)j * ldb]);
+            if (!tA) {
+                const double *a = A + (size_t)l * lda;
+                for (int i = 0; i < m; ++i) c[i] += a[i] * b;
+            } else {
+                for (int i = 0; i < m; ++i) c[i] += A[l + (size_t)i * lda] * b;
+            }
+        }
+    }
+}
+
+void orc_dgemm(char ta, char tb, u32 m, u32 n, u32 k, double alpha, const double *A, u32 lda,
+               const double *Bm, u32 ldb, double beta, double *C, u32 ldc)
+{
+    if (g_dgemm) {
+        int mi = (int)m, ni = (int)n, ki = (int)k, la = (int)lda, lb = (int)ldb, lc = (int)ldc;
+        g_dgemm(&ta, &tb, &mi, &ni, &ki, &alpha, A, &la, Bm, &lb, &beta, C, &lc);
+    } else {
+        builtin_dgemm(ta, tb, (int)m, (int)n, (int)k, alpha, A, (int)lda, Bm, (int)ldb, beta, C, (int)ldc);
+    }
+}
+
+/* long-double referee: same contraction accumulated in extended precision */
+static void dgemm_nn_ld(u32 m, u32 n, u32 k, const double *A, u32 lda, const double *Bm, u32 ldb,
+                        double *C, u32 ldc)
+{
+    for (u32 j = 0; j < n; ++j)
+        for (u32 i = 0; i < m; ++i) {
+            long double s = 0.0L;
+            for (u32 l = 0; l < k; ++l)
+                s += (long double)A[i + (size_t)l * lda] * (long double)Bm[l + (size_t)j * ldb];
+            C[i + (size_t)j * ldc] = (double)s;
+        }
+}
+
+/* linearAlgebra/BlasLapack.t.cpp:388-436 (host gemmStridedVarBatched: one gemm per matrix,
+ * operands advanced by the per-matrix strides, skipped when any of m,n,k is 0) */
+void orc_gemm_strided_var_batched(u32 numMats, const char *transA, const char *transB,
+                                  const u32 *stridea, const u32 *strideb, const u32 *stridec,
+                                  const u32 *m, const u32 *n, const u32 *k, double alpha,
+                                  const double *dA, const u32 *ldda, const double *dB, const u32 *lddb,
+                                  double beta, double *dC, const u32 *lddc)
+{
+    size_t ca = 0, cb = 0, cc = 0;
+    for (u32 i = 0; i < numMats; ++i) {
+        if (m[i] > 0 && n[i] > 0 && k[i] > 0)
+            orc_dgemm(transA[i], transB[i], m[i], n[i], k[i], alpha, dA + ca, ldda[i], dB + cb, lddb[i],
+                      beta, dC + cc, lddc[i]);
+        ca += stridea[i];
+        cb += strideb[i];
+        cc += stridec[i];
+    }
+}
+
+/* ------------------------------------------------------- constraints --- */
+/* basis/ConstraintsInternal.cpp:35-108: sequential over rows, in place;
+ * newValues = inhomogeneity; axpy per column; copy into the row. */
+void orc_p2c(double *x, u32 B, u32 nR, const u32 *rowIds, const u32 *rowSizes, const u32 *rowOffsets,
+             const u32 *colIds, const double *colVals, const double *inhom)
+{
+    double *nv = (double *)malloc(sizeof(double) * (B ? B : 1));
+    for (u32 i = 0; i < nR; ++i) {
+        for (u32 v = 0; v < B; ++v) nv[v] = inhom[i];
+        const size_t rs = (size_t)rowIds[i] * B;
+        const u32 cs = rowOffsets[i];
+        for (u32 j = 0; j < rowSizes[i]; ++j) {
+            const size_t col = (size_t)colIds[cs + j] * B;
+            const double a = colVals[cs + j];
+            for (u32 v = 0; v < B; ++v) nv[v] += a * x[col + v];
+        }
+        memcpy(x + rs, nv, sizeof(double) * B);
+    }
+    free(nv);
+}
+
+/* basis/ConstraintsInternal.cpp:110-170: y[col] += w*y[row] per entry, then row = 0. */
+void orc_c2p(double *y, u32 B, u32 nR, const u32 *rowIds, const u32 *rowSizes, const u32 *rowOffsets,
+             const u32 *colIds, const double *colVals)
+{
+    for (u32 i = 0; i < nR; ++i) {
+        const size_t rs = (size_t)rowIds[i] * B;
+        const u32 cs = rowOffsets[i];
+        for (u32 j = 0; j < rowSizes[i]; ++j) {
+            const size_t col = (size_t)colIds[cs + j] * B;
+            const double a = colVals[cs + j];
+            for (u32 v = 0; v < B; ++v) y[col + v] += a * y[rs + v];
+        }
+        for (u32 v = 0; v < B; ++v) y[rs + v] = 0.0;
+    }
+}
+
+/* basis/ConstraintsInternal.cpp:172-196 */
+void orc_set_constrained_zero(double *y, u32 B, u32 nR, const u32 *rowIds)
+{
+    for (u32 i = 0; i < nR; ++i)
+        for (u32 v = 0; v < B; ++v) y[(size_t)rowIds[i] * B + v] = 0.0;
+}
+
+/* ---------------------------------------------------- gather/scatter --- */
+/* basis/FECellWiseDataOperations.t.cpp:58-86 */
+void orc_gather(const double *x, u32 B, const u32 *cellLocalIds, const u32 *numCellDofs, u32 C,
+                double *cellWise)
+{
+    size_t cum = 0;
+    for (u32 c = 0; c < C; ++c) {
+        for (u32 i = 0; i < numCellDofs[c]; ++i)
+            memcpy(cellWise + (cum + i) * B, x + (size_t)cellLocalIds[cum + i] * B, sizeof(double) * B);
+        cum += numCellDofs[c];
+    }
+}
+
+/* basis/FECellWiseDataOperations.t.cpp:87-153: cells ascending, dofs ascending */
+void orc_scatter_add(const double *cellWise, u32 B, const u32 *cellLocalIds, const u32 *numCellDofs,
+                     u32 C, double *y)
+{
+    size_t cum = 0;
+    for (u32 c = 0; c < C; ++c) {
+        for (u32 i = 0; i < numCellDofs[c]; ++i) {
+            const double *s = cellWise + (cum + i) * B;
+            double *d = y + (size_t)cellLocalIds[cum + i] * B;
+            for (u32 v = 0; v < B; ++v) d[v] += s[v];
+        }
+        cum += numCellDofs[c];
+    }
+}
+
+/* ------------------------------------------------------------- halo --- */
+/* utils/DiscontiguousDataOperations.cpp:36-52 (pack) */
+void orc_pack(const double *x, u32 B, const u32 *ids, u32 n, double *buf)
+{
+    for (u32 i = 0; i < n; ++i) memcpy(buf + (size_t)i * B, x + (size_t)ids[i] * B, sizeof(double) * B);
+}
+/* utils/DiscontiguousDataOperations.cpp:54-70 (unpack into the ghost section) */
+void orc_unpack(const double *buf, u32 B, const u32 *ids, u32 n, double *xGhostBase)
+{
+    for (u32 i = 0; i < n; ++i)
+        memcpy(xGhostBase + (size_t)ids[i] * B, buf + (size_t)i * B, sizeof(double) * B);
+}
+/* utils/DiscontiguousDataOperations.cpp:73-88 (accumulate into owned rows) */
+void orc_add_from_buf(const double *buf, u32 B, const u32 *ids, u32 n, double *x)
+{
+    for (u32 i = 0; i < n; ++i)
+        for (u32 v = 0; v < B; ++v) x[(size_t)ids[i] * B + v] += buf[(size_t)i * B + v];
+}
+
+/* -------------------------------------------------------- BLAS-1-ish --- */
+/* linearAlgebra/BlasLapackKernels.cpp:456-474 */
+void orc_axpby(size_t n, double alpha, const double *x, double beta, const double *y, double *z)
+{
+    for (size_t i = 0; i < n; ++i) z[i] = alpha * x[i] + beta * y[i];
+}
+/* linearAlgebra/BlasLapackKernels.cpp:477-502 */
+void orc_axpby_blocked(size_t size, u32 blockSize, double alpha1, const double *alpha, const double *x,
+                       double beta1, const double *beta, const double *y, double *z)
+{
+    for (size_t i = 0; i < size; ++i)
+        for (u32 j = 0; j < blockSize; ++j)
+            z[i * blockSize + j] = alpha1 * alpha[j] * x[i * blockSize + j] + beta1 * beta[j] * y[i * blockSize + j];
+}
+/* linearAlgebra/BlasLapackKernels.cpp:91-123 */
+void orc_ascale(size_t n, double alpha, const double *x, double *z)
+{
+    for (size_t i = 0; i < n; ++i) z[i] = alpha * x[i];
+}
+/* khatriRaoProduct(ColMajor, sizeI=1, sizeJ=B, sizeK=n): Z[k*B+j] = A[k]*X[k*B+j]
+ * linearAlgebra/BlasLapackKernels.cpp:356-372 as called by
+ * basis/CFEOverlapInverseOpContextGLL.t.cpp:538-546 */
+void orc_row_scale(const double *d, const double *x, double *z, u32 B, size_t n)
+{
+    for (size_t k = 0; k < n; ++k)
+        for (u32 j = 0; j < B; ++j) z[k * B + j] = d[k] * x[k * B + j];
+}
+/* linearAlgebra/MultiVector.t.cpp:553-578 (local part of l2Norms: sum of squares per column) */
+void orc_col_sumsq(const double *x, u32 B, size_t nOwned, double *out)
+{
+    for (u32 j = 0; j < B; ++j) out[j] = 0.0;
+    for (size_t i = 0; i < nOwned; ++i)
+        for (u32 j = 0; j < B; ++j) out[j] += x[i * B + j] * x[i * B + j];
+}
+
+/* ------------------------------------------------------------- H.X ----- */
+/* ksdft/KohnShamOperatorContextFE.t.cpp:1030-1071 (LOOP A of computeAxCellWiseOptimized):
+ * gather every cell into the whole-rank xCell buffer and, with projectors,
+ * CX += C_c^H x_c via basis/AtomCenterNonLocalOpContextFE.t.cpp:889-942
+ * (cellWiseGEMM with transB='C', ldb = nProj_c, beta = 0; then scatter-add of
+ * the cell result into the projector vector).  cellBlockSize = 1 (Defaults). */
+void orc_hx_loop_a(const double *x, u32 B, u32 C, const u32 *numCellDofs, const u32 *cellLocalIds,
+                   double *xCell, const u32 *numCellProj, const u32 *cellProjIds, const double *cellC,
+                   double *CX)
+{
+    size_t off = 0, poff = 0, coff = 0;
+    u32 maxp = 0;
+    if (numCellProj)
+        for (u32 c = 0; c < C; ++c) maxp = numCellProj[c] > maxp ? numCellProj[c] : maxp;
+    double *cxCell = numCellProj ? (double *)malloc(sizeof(double) * (size_t)(maxp ? maxp : 1) * B) : NULL;
+    for (u32 c = 0; c < C; ++c) {
+        const u32 n = numCellDofs[c];
+        orc_gather(x, B, cellLocalIds + off, &n, 1, xCell + off * B);
+        if (numCellProj) {
+            const u32 np = numCellProj[c];
+            if (np) {
+                orc_dgemm('N', 'C', B, np, n, 1.0, xCell + off * B, B, cellC + coff, np, 0.0, cxCell, B);
+                orc_scatter_add(cxCell, B, cellProjIds + poff, &np, 1, CX);
+            }
+            poff += np;
+            coff += (size_t)np * n;
+        }
+        off += n;
+    }
+    free(cxCell);
+}
+
+/* ksdft/KohnShamOperatorContextFE.t.cpp:1088-1198 (LOOP B): per cell
+ * yCell = xCell * H_c (col-major m=B, n=k=n_c, lda=ldc=B, ldb=n_c; :713-760,1155-1175),
+ * with projectors yCell += CXcell * C_c (beta = 1,
+ * basis/AtomCenterNonLocalOpContextFE.t.cpp:998-1036), then scatter-add. */
+void orc_hx_loop_b(const double *xCell, double *y, u32 B, u32 C, const u32 *numCellDofs,
+                   const u32 *cellLocalIds, const double *hCell, const u32 *numCellProj,
+                   const u32 *cellProjIds, const double *cellC, const double *CX, int longDouble)
+{
+    u32 maxn = 0, maxp = 0;
+    for (u32 c = 0; c < C; ++c) {
+        maxn = numCellDofs[c] > maxn ? numCellDofs[c] : maxn;
+        if (numCellProj) maxp = numCellProj[c] > maxp ? numCellProj[c] : maxp;
+    }
+    double *yCell = (double *)malloc(sizeof(double) * (size_t)(maxn ? maxn : 1) * B);
+    double *cxCell = (double *)malloc(sizeof(double) * (size_t)(maxp ? maxp : 1) * B);
+    size_t off = 0, hoff = 0, poff = 0, coff = 0;
+    for (u32 c = 0; c < C; ++c) {
+        const u32 n = numCellDofs[c];
+        if (longDouble)
+            dgemm_nn_ld(B, n, n, xCell + off * B, B, hCell + hoff, n, yCell, B);
+        else
+            orc_dgemm('N', 'N', B, n, n, 1.0, xCell + off * B, B, hCell + hoff, n, 0.0, yCell, B);
+        if (numCellProj) {
+            const u32 np = numCellProj[c];
+            if (np) {
+                orc_gather(CX, B, cellProjIds + poff, &np, 1, cxCell);
+                orc_dgemm('N', 'N', B, n, np, 1.0, cxCell, B, cellC + coff, np, 1.0, yCell, B);
+            }
+            poff += np;
+            coff += (size_t)np * n;
+        }
+        orc_scatter_add(yCell, B, cellLocalIds + off, &n, 1, y);
+        off += n;
+        hoff += (size_t)n * n;
+    }
+    free(yCell);
+    free(cxCell);
+}
+
+/* ------------------------------------------------------ subspace ops --- */
+/* linearAlgebra/RayleighRitzEigenSolver.t.cpp:782-796: gemm('N','C', m=B-j0, n=b, k=nOwned,
+ * X+j0 (ld B), OpXb (ld b)) -> SBlock (ld B-j0).  S[j + i*(B-j0)] = sum_dof X[dof,j0+j]*OpX[dof,i] */
+void orc_gram_block(const double *X, u32 B, u32 j0, const double *OpXb, u32 b, size_t nOwned, double *S)
+{
+    orc_dgemm('N', 'C', B - j0, b, (u32)nOwned, 1.0, X + j0, B, OpXb, b, 0.0, S, B - j0);
+}
+
+/* linearAlgebra/ElpaScalapackOperations.t.cpp:230-330 (subspaceRotation), single dof block /
+ * vector blocks of wfcBlock: Xnew[dof, j] = sum_{i<D} Qblk[j-jvec + i*BVec] X[dof,i],
+ * Qblk[i*BVec + j] = Q(i, jvec+j) if transpose else Q(jvec+j, i); Q given column-major B x B. */
+void orc_subspace_rotation(double *X, size_t M, u32 N, const double *Q, u32 dofBlock, u32 vecBlock,
+                           int rotationMatTranspose, int lowerTri)
+{
+    const u32 vbs = vecBlock < N ? vecBlock : N;
+    const size_t dbs = dofBlock < M ? dofBlock : M;
+    double *qb = (double *)calloc((size_t)vbs * N, sizeof(double));
+    double *tmp = (double *)calloc((size_t)N * (dbs ? dbs : 1), sizeof(double));
+    for (size_t idof = 0; idof < M; idof += dbs) {
+        const size_t BDof = (M - idof) < dbs ? (M - idof) : dbs;
+        for (u32 jvec = 0; jvec < N; jvec += vbs) {
+            const u32 BVec = (N - jvec) < vbs ? (N - jvec) : vbs;
+            const u32 D = lowerTri ? (jvec + BVec) : N;
+            memset(qb, 0, sizeof(double) * (size_t)BVec * N);
+            for (u32 i = 0; i < D; ++i)
+                for (u32 j = 0; j < BVec; ++j)
+                    qb[(size_t)i * BVec + j] = rotationMatTranspose ? Q[i + (size_t)(j + jvec) * N]
+                                                                    : Q[(j + jvec) + (size_t)i * N];
+            orc_dgemm('N', 'N', BVec, (u32)BDof, D, 1.0, qb, BVec, X + idof * N, N, 0.0, tmp + jvec, N);
+        }
+        memcpy(X + idof * N, tmp, sizeof(double) * N * BDof);
+    }
+    free(qb);
+    free(tmp);
+}
+
+/* basis/OEFEAtomBlockOverlapInvOpContextGLL.t.cpp:989-1090: enrichment rows
+ * Y_enr (B x nE) = X_enr (B x nE) * Blk (nE x nE), col-major 'N','N', ld nE. */
+void orc_enr_block_apply(const double *Xenr, double *Yenr, u32 B, u32 nE, const double *blk)
+{
+    if (nE) orc_dgemm('N', 'N', B, nE, nE, 1.0, Xenr, B, blk, nE, 0.0, Yenr, B);
+}
