@@ -31,7 +31,7 @@ def build(force: bool = False) -> str:
     src = os.path.join(_HERE, "hx_oracle.c")
     out = os.path.join(_HERE, "liborc.so")
     if force or not os.path.exists(out) or os.path.getmtime(out) < os.path.getmtime(src):
-        subprocess.check_call(["gcc", "-O3", "-march=native", "-fPIC", "-shared", "-std=c11",
+        subprocess.check_call(["gcc", "-O3", "-march=native", "-ffp-contract=off", "-fPIC", "-shared", "-std=c11",
                                "-o", out, src, "-lm"])
     return out
 

@@ -1,0 +1,76 @@
+"""ctypes access to oracle/_ref/libdftefe_ref.so — the REFERENCE's own sources compiled by
+oracle/Makefile (`make ref`).  TEST INFRASTRUCTURE ONLY.  `available()` is False when the
+library has not been built (it needs /root/reference at build time; the built .so travels)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_PATH = os.path.join(_HERE, "_ref", "libdftefe_ref.so")
+_LIB = None
+
+c_u32p = C.POINTER(C.c_uint32)
+c_f64p = C.POINTER(C.c_double)
+APPLY_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_int, c_f64p, c_f64p, C.c_uint32, C.c_uint32, C.c_int, C.c_int)
+
+
+def build() -> bool:
+    """Build _ref if the reference tree is present; return availability."""
+    if os.path.isdir("/root/reference/src"):
+        subprocess.check_call(["make", "-s", "-C", _HERE, "ref"])
+    return available()
+
+
+def available() -> bool:
+    return os.path.exists(_PATH)
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(_PATH)
+    return _LIB
+
+
+def f64(a):
+    assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(c_f64p)
+
+
+def u32(a):
+    a = np.ascontiguousarray(a, dtype=np.uint32)
+    return a, a.ctypes.data_as(c_u32p)
+
+
+def p2c(X, prob):
+    r, rp = u32(prob.row_ids); s, sp = u32(prob.row_sizes); o, op = u32(prob.row_offsets); c, cp = u32(prob.col_ids)
+    v = np.ascontiguousarray(prob.col_vals); ih = np.ascontiguousarray(prob.inhom)
+    lib().ref_p2c(f64(X), C.c_uint32(X.shape[0]), C.c_uint32(X.shape[1]), C.c_uint32(len(r)), rp, sp, op, cp,
+                  C.c_uint32(len(c)), f64(v), f64(ih))
+
+
+def c2p(Y, prob):
+    r, rp = u32(prob.row_ids); s, sp = u32(prob.row_sizes); o, op = u32(prob.row_offsets); c, cp = u32(prob.col_ids)
+    v = np.ascontiguousarray(prob.col_vals)
+    lib().ref_c2p(f64(Y), C.c_uint32(Y.shape[0]), C.c_uint32(Y.shape[1]), C.c_uint32(len(r)), rp, sp, op, cp,
+                  C.c_uint32(len(c)), f64(v))
+
+
+def cell_gemm_batched(xcell, h_cell, ncd, B):
+    """The gemmStridedVarBatched call of KohnShamOperatorContextFE.t.cpp:1155-1175 with the sizes of
+    storeSizes (:713-760), all cells in one batch.  Returns yCell [S, B]."""
+    n = np.ascontiguousarray(ncd, dtype=np.uint32)
+    nm = len(n)
+    m = np.full(nm, B, np.uint32)
+    sa = (m * n).astype(np.uint32); sb = (n * n).astype(np.uint32); sc = sa.copy()
+    ta = (C.c_char * nm)(*([b"N"] * nm)); tb = (C.c_char * nm)(*([b"N"] * nm))
+    y = np.zeros_like(xcell)
+    p = lambda a: a.ctypes.data_as(c_u32p)
+    lib().ref_gemm_strided_var_batched(C.c_uint32(nm), ta, tb, p(sa), p(sb), p(sc), p(m), p(n), p(n),
+                                       C.c_double(1.0), f64(xcell), p(m), f64(h_cell), p(n), C.c_double(0.0),
+                                       f64(y), p(m))
+    return y

@@ -1,0 +1,294 @@
+// ref_shim.cpp — C entry points over the REFERENCE's own compiled sources.
+//
+// TEST INFRASTRUCTURE ONLY.  This translation unit is ours; everything it calls
+// lives in /root/reference/src and is compiled where it lies by oracle/Makefile
+// into oracle/_ref/libdftefe_ref.so (git-ignored; nothing is copied).  Only the
+// parts of the hot path that build without deal.II / MPI / ELPA are reachable:
+//   basis/ConstraintsInternal.cpp            (hanging-node distribute, a3/a7)
+//   utils/DiscontiguousDataOperations.cpp    (halo pack / unpack / add, a2/a8)
+//   linearAlgebra/BlasLapack*.cpp            (gemmStridedVarBatched, axpby, axpbyBlocked,
+//                                             khatriRaoProduct, scaleStridedVarBatched, ascale)
+//   linearAlgebra/ChebyshevFilter.t.cpp      (both filters, templated on OperatorContext)
+//   linearAlgebra/MultiVector.t.cpp          (serial MultiVector)
+// The Fortran BLAS the reference links (dgemm_, daxpy_, ...) is third-party and
+// absent here; oracle/fortran_blas.c supplies netlib-semantics versions.
+//
+// It is used to validate oracle/hx_oracle.c (tests/test_oracle_vs_ref.py) and to
+// generate tests/golden/*.npz (tests/golden/make_golden.py).
+#include <utils/TypeConfig.h>
+#include <utils/MemoryStorage.h>
+#include <utils/DiscontiguousDataOperations.h>
+#include <linearAlgebra/MultiVector.h>
+#include <linearAlgebra/OperatorContext.h>
+#include <linearAlgebra/ChebyshevFilter.h>
+#include <linearAlgebra/BlasLapack.h>
+#include <linearAlgebra/LinAlgOpContext.h>
+#include <basis/ConstraintsInternal.h>
+#include <cstring>
+#include <memory>
+#include <vector>
+
+using namespace dftefe;
+constexpr auto HOST = utils::MemorySpace::HOST;
+using MV            = linearAlgebra::MultiVector<double, HOST>;
+using Ctx           = linearAlgebra::LinAlgOpContext<HOST>;
+template <typename T>
+using Store = utils::MemoryStorage<T, HOST>;
+
+static std::shared_ptr<Ctx>
+ctx()
+{
+  static auto bq = std::make_shared<linearAlgebra::blasLapack::BlasQueue<HOST>>();
+  static auto lq = std::make_shared<linearAlgebra::blasLapack::LapackQueue<HOST>>();
+  static auto c  = std::make_shared<Ctx>(bq, lq);
+  return c;
+}
+
+template <typename T>
+static Store<T>
+mk(const T *p, size_t n)
+{
+  Store<T> s(n);
+  if (n)
+    std::memcpy(s.data(), p, n * sizeof(T));
+  return s;
+}
+
+extern "C"
+{
+  void
+  ref_p2c(double *        x,
+          unsigned        nLocal,
+          unsigned        B,
+          unsigned        nR,
+          const unsigned *rowIds,
+          const unsigned *rowSizes,
+          const unsigned *rowOffsets,
+          const unsigned *colIds,
+          unsigned        nnz,
+          const double *  colVals,
+          const double *  inhom)
+  {
+    MV X((size_type)nLocal, (size_type)B, ctx(), 0.0);
+    std::memcpy(X.data(), x, sizeof(double) * (size_t)nLocal * B);
+    auto r = mk(rowIds, nR), s = mk(rowSizes, nR), o = mk(rowOffsets, nR), c = mk(colIds, nnz);
+    auto v = mk(colVals, nnz), ih = mk(inhom, nR);
+    basis::ConstraintsInternal<double, HOST>::constraintsDistributeParentToChild(
+      X, B, r, s, c, o, v, ih, *ctx());
+    std::memcpy(x, X.data(), sizeof(double) * (size_t)nLocal * B);
+  }
+
+  void
+  ref_c2p(double *        y,
+          unsigned        nLocal,
+          unsigned        B,
+          unsigned        nR,
+          const unsigned *rowIds,
+          const unsigned *rowSizes,
+          const unsigned *rowOffsets,
+          const unsigned *colIds,
+          unsigned        nnz,
+          const double *  colVals)
+  {
+    MV Y((size_type)nLocal, (size_type)B, ctx(), 0.0);
+    std::memcpy(Y.data(), y, sizeof(double) * (size_t)nLocal * B);
+    auto r = mk(rowIds, nR), s = mk(rowSizes, nR), o = mk(rowOffsets, nR), c = mk(colIds, nnz);
+    auto v = mk(colVals, nnz);
+    basis::ConstraintsInternal<double, HOST>::constraintsDistributeChildToParent(
+      Y, B, r, s, c, o, v, *ctx());
+    std::memcpy(y, Y.data(), sizeof(double) * (size_t)nLocal * B);
+  }
+
+  void
+  ref_pack(const double *x, unsigned B, const unsigned *ids, unsigned n, double *buf)
+  {
+    utils::DiscontiguousDataOperations<double, HOST>::copyFromDiscontiguousMemory(x, buf, ids, n, B);
+  }
+  void
+  ref_unpack(const double *buf, unsigned B, const unsigned *ids, unsigned n, double *x)
+  {
+    utils::DiscontiguousDataOperations<double, HOST>::copyToDiscontiguousMemory(buf, x, ids, n, B);
+  }
+  void
+  ref_add(const double *buf, unsigned B, const unsigned *ids, unsigned n, double *x)
+  {
+    utils::DiscontiguousDataOperations<double, HOST>::addToDiscontiguousMemory(buf, x, ids, n, B);
+  }
+
+  void
+  ref_gemm_strided_var_batched(unsigned        numMats,
+                               const char *    transA,
+                               const char *    transB,
+                               const unsigned *sa,
+                               const unsigned *sb,
+                               const unsigned *sc,
+                               const unsigned *m,
+                               const unsigned *n,
+                               const unsigned *k,
+                               double          alpha,
+                               const double *  A,
+                               const unsigned *lda,
+                               const double *  Bm,
+                               const unsigned *ldb,
+                               double          beta,
+                               double *        Cm,
+                               const unsigned *ldc)
+  {
+    linearAlgebra::blasLapack::gemmStridedVarBatched<double, double, HOST>(
+      numMats, transA, transB, sa, sb, sc, m, n, k, alpha, A, lda, Bm, ldb, beta, Cm, ldc, *ctx());
+  }
+
+  void
+  ref_gemm(char          ta,
+           char          tb,
+           unsigned      m,
+           unsigned      n,
+           unsigned      k,
+           double        alpha,
+           const double *A,
+           unsigned      lda,
+           const double *Bm,
+           unsigned      ldb,
+           double        beta,
+           double *      Cm,
+           unsigned      ldc)
+  {
+    linearAlgebra::blasLapack::gemm<double, double, HOST>(
+      ta, tb, m, n, k, alpha, A, lda, Bm, ldb, beta, Cm, ldc, *ctx());
+  }
+
+  void
+  ref_axpby(unsigned n, double alpha, const double *x, double beta, const double *y, double *z)
+  {
+    linearAlgebra::blasLapack::axpby<double, double, HOST>(n, alpha, x, beta, y, z, *ctx());
+  }
+
+  void
+  ref_axpby_blocked(unsigned      n,
+                    unsigned      bs,
+                    double        alpha1,
+                    const double *alpha,
+                    const double *x,
+                    double        beta1,
+                    const double *beta,
+                    const double *y,
+                    double *      z)
+  {
+    linearAlgebra::blasLapack::axpbyBlocked<double, double, HOST>(
+      n, bs, alpha1, alpha, x, beta1, beta, y, z, *ctx());
+  }
+
+  void
+  ref_row_scale(const double *d, const double *x, double *z, unsigned B, unsigned n)
+  {
+    linearAlgebra::blasLapack::khatriRaoProduct<double, double, HOST>(
+      linearAlgebra::blasLapack::Layout::ColMajor, 1, B, n, d, x, z, *ctx());
+  }
+
+  // the call of AtomCenterNonLocalOpContextFE::applyVOnCconjtransX
+  void
+  ref_scale_rows_strided(const double *V, double *cx, unsigned B, unsigned nLocal)
+  {
+    size_type stride = 0, m = 1, n = B, k = nLocal;
+    linearAlgebra::blasLapack::scaleStridedVarBatched<double, double, HOST>(
+      1,
+      linearAlgebra::blasLapack::Layout::ColMajor,
+      linearAlgebra::blasLapack::ScalarOp::Identity,
+      linearAlgebra::blasLapack::ScalarOp::Identity,
+      &stride,
+      &stride,
+      &stride,
+      &m,
+      &n,
+      &k,
+      V,
+      cx,
+      cx,
+      *ctx());
+  }
+
+  // ---- filters over caller-supplied operators ---------------------------------
+  // cb(user, opId, X, Y, nLocal, B, updateGhostX, updateGhostY)
+  typedef void (*apply_cb)(void *, int, double *, double *, unsigned, unsigned, int, int);
+}
+
+namespace
+{
+  class CallbackOp : public linearAlgebra::OperatorContext<double, double, HOST>
+  {
+  public:
+    CallbackOp(apply_cb cb, void *user, int id)
+      : d_cb(cb)
+      , d_user(user)
+      , d_id(id)
+    {}
+    void
+    apply(MV &X, MV &Y, bool ugx = false, bool ugy = false) const override
+    {
+      d_cb(d_user, d_id, X.data(), Y.data(), X.localSize(), X.getNumberComponents(), ugx, ugy);
+    }
+
+  private:
+    apply_cb d_cb;
+    void *   d_user;
+    int      d_id;
+  };
+} // namespace
+
+extern "C"
+{
+  // X (in/out, n x B) ; Y (out) ; opIds: 0 = A (Hamiltonian), 1 = BInv, 2 = B
+  void
+  ref_chebyshev_filter(apply_cb cb,
+                       void *   user,
+                       double * x,
+                       double * y,
+                       unsigned n,
+                       unsigned B,
+                       unsigned degree,
+                       double   a0,
+                       double   a,
+                       double   b)
+  {
+    CallbackOp A(cb, user, 0), BInv(cb, user, 1);
+    MV         X((size_type)n, (size_type)B, ctx(), 0.0), Y((size_type)n, (size_type)B, ctx(), 0.0);
+    std::memcpy(X.data(), x, sizeof(double) * (size_t)n * B);
+    linearAlgebra::ChebyshevFilter<double, double, HOST>(A, BInv, X, degree, a0, a, b, Y);
+    std::memcpy(x, X.data(), sizeof(double) * (size_t)n * B);
+    std::memcpy(y, Y.data(), sizeof(double) * (size_t)n * B);
+  }
+
+  void
+  ref_residual_chebyshev_filter(apply_cb      cb,
+                                void *        user,
+                                const double *eig,
+                                double *      x,
+                                double *      y,
+                                unsigned      n,
+                                unsigned      B,
+                                unsigned      degree,
+                                double        a0,
+                                double        a,
+                                double        b)
+  {
+    CallbackOp          A(cb, user, 0), BInv(cb, user, 1), Bop(cb, user, 2);
+    std::vector<double> ev(eig, eig + B);
+    MV                  X((size_type)n, (size_type)B, ctx(), 0.0), Y((size_type)n, (size_type)B, ctx(), 0.0);
+    std::memcpy(X.data(), x, sizeof(double) * (size_t)n * B);
+    linearAlgebra::ResidualChebyshevFilterGEP<double, double, HOST>(
+      A, Bop, BInv, ev, X, degree, a0, a, b, Y);
+    std::memcpy(x, X.data(), sizeof(double) * (size_t)n * B);
+    std::memcpy(y, Y.data(), sizeof(double) * (size_t)n * B);
+  }
+
+  // MultiVector::l2Norms (serial)
+  void
+  ref_l2_norms(const double *x, unsigned n, unsigned B, double *out)
+  {
+    MV X((size_type)n, (size_type)B, ctx(), 0.0);
+    std::memcpy(X.data(), x, sizeof(double) * (size_t)n * B);
+    std::vector<double> r = X.l2Norms();
+    for (unsigned j = 0; j < B; ++j)
+      out[j] = r[j];
+  }
+}

@@ -1,0 +1,329 @@
+"""CPU tests (no GPU): pin the oracle.
+
+ * against the golden vector in the reference's own test
+   (test/linearAlgebra/src/TestBlasLapackDoubleGemmHost.cpp),
+ * against the reference's own compiled leaf sources (oracle/_ref),
+ * against the known-answer / invariant tests the reference's test-suite uses for
+   the neighbouring components: hanging-node polynomial
+   reproduction (test/basis/src/TestHomogeneousConstraintMatrix.cpp:226-262),
+   ghost accumulate/update semantics
+   (test/utils/src/TestMPICommunicatorP2PAccumulateAdd.cpp:159-188),
+   M M^-1 x = x (test/basis/src/TestOrthoEFEOverlapMatrix.cpp:430-440),
+ * and mathematical invariants of H.X (symmetry, partition independence).
+"""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+from dft_efe_b200 import synth
+from oracle import oracle as orc
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def small_spec(nranks=1, p=3, nc=(4, 4, 4), refine=True, enr=3, proj=2, boundary="dirichlet"):
+    L = nc[0] * 1.0
+    atoms = np.array([[L / 2, L / 2, L / 2], [0.3 * L, 0.72 * L, 0.28 * L]])
+    return synth.MeshSpec(
+        ncell=nc, p=p,
+        refine_mask=synth.refine_ball(nc, 1.0, [atoms[0]], 0.9) if refine else None,
+        atoms=atoms if (enr or proj) else None,
+        n_enr_per_atom=enr, enr_cutoff=1.2, n_proj_per_atom=proj, proj_cutoff=1.0,
+        nranks=nranks, boundary=boundary)
+
+
+@pytest.fixture(scope="module")
+def probs():
+    return {n: synth.build_problem(small_spec(n)) for n in (1, 2, 4)}
+
+
+def to_natural(ps, Ys):
+    out = {}
+    for p, y in zip(ps, Ys):
+        for l in range(p.n_owned):
+            out[int(p.natural_ids[l])] = y[l]
+    keys = sorted(out)
+    return np.array([out[k] for k in keys])
+
+
+# ---------------------------------------------------------------- golden ---
+def test_dgemm_golden_vector():
+    g = json.load(open(os.path.join(HERE, "golden", "ref_dgemm_10x5x3.json")))
+    A = np.array(g["A_colmajor"]); Bm = np.array(g["B_colmajor"]); Cref = np.array(g["C_colmajor"])
+    Cm = np.zeros(g["m"] * g["n"])
+    L = orc.lib()
+    L.orc_dgemm(C.c_char(b"N"), C.c_char(b"N"), C.c_uint32(g["m"]), C.c_uint32(g["n"]), C.c_uint32(g["k"]),
+                C.c_double(1.0), orc._f64(A), C.c_uint32(g["m"]), orc._f64(Bm), C.c_uint32(g["k"]), C.c_double(0.0),
+                orc._f64(Cm), C.c_uint32(g["m"]))
+    # the reference asserts 1e-12 on values printed to 11 decimals; 1e-10 is what the digits support
+    assert np.abs(Cm - Cref).max() < 1e-10
+
+
+def test_dgemm_golden_vector_ref(ref_lib):
+    g = json.load(open(os.path.join(HERE, "golden", "ref_dgemm_10x5x3.json")))
+    A = np.array(g["A_colmajor"]); Bm = np.array(g["B_colmajor"]); Cref = np.array(g["C_colmajor"])
+    Cm = np.zeros(g["m"] * g["n"])
+    ref_lib.lib().ref_gemm(C.c_char(b"N"), C.c_char(b"N"), C.c_uint32(g["m"]), C.c_uint32(g["n"]), C.c_uint32(g["k"]),
+                           C.c_double(1.0), orc._f64(A), C.c_uint32(g["m"]), orc._f64(Bm), C.c_uint32(g["k"]),
+                           C.c_double(0.0), orc._f64(Cm), C.c_uint32(g["m"]))
+    assert np.abs(Cm - Cref).max() < 1e-10
+
+
+# ------------------------------------------------------ oracle vs _ref -----
+def test_constraints_match_reference_sources(ref_lib, probs):
+    p = probs[1][0]
+    assert len(p.row_ids) > 0 and p.col_vals.size > 0
+    rng = np.random.default_rng(0)
+    for B in (1, 5):
+        X = rng.standard_normal((p.n_local, B))
+        p.inhom[:] = rng.standard_normal(len(p.row_ids))  # exercise inhomogeneities too
+        R = orc.OracleRank(p)
+        a, b = X.copy(), X.copy()
+        R.p2c(a); ref_lib.p2c(b, p)
+        assert np.array_equal(a, b)
+        a, b = X.copy(), X.copy()
+        R.c2p(a); ref_lib.c2p(b, p)
+        assert np.array_equal(a, b)
+        p.inhom[:] = 0.0
+
+
+def test_halo_pack_unpack_add_match_reference_sources(ref_lib):
+    rng = np.random.default_rng(1)
+    n, B, m = 50, 3, 17
+    X = rng.standard_normal((n, B))
+    ids = rng.integers(0, n, m).astype(np.uint32)
+    uniq = rng.permutation(n)[:m].astype(np.uint32)
+    L, Rf = orc.lib(), ref_lib.lib()
+    b1, b2 = np.zeros((m, B)), np.zeros((m, B))
+    L.orc_pack(orc._f64(X), C.c_uint32(B), ids.ctypes.data_as(orc.c_u32p), C.c_uint32(m), orc._f64(b1))
+    Rf.ref_pack(orc._f64(X), C.c_uint32(B), ids.ctypes.data_as(orc.c_u32p), C.c_uint32(m), orc._f64(b2))
+    assert np.array_equal(b1, b2) and np.array_equal(b1, X[ids])
+    y1, y2 = X.copy(), X.copy()
+    L.orc_unpack(orc._f64(b1), C.c_uint32(B), uniq.ctypes.data_as(orc.c_u32p), C.c_uint32(m), orc._f64(y1))
+    Rf.ref_unpack(orc._f64(b1), C.c_uint32(B), uniq.ctypes.data_as(orc.c_u32p), C.c_uint32(m), orc._f64(y2))
+    assert np.array_equal(y1, y2)
+    y1, y2 = X.copy(), X.copy()
+    L.orc_add_from_buf(orc._f64(b1), C.c_uint32(B), ids.ctypes.data_as(orc.c_u32p), C.c_uint32(m), orc._f64(y1))
+    Rf.ref_add(orc._f64(b1), C.c_uint32(B), ids.ctypes.data_as(orc.c_u32p), C.c_uint32(m), orc._f64(y2))
+    assert np.array_equal(y1, y2)
+
+
+def test_cell_gemm_matches_reference_sources(ref_lib, probs):
+    p = probs[1][0]
+    B = 6
+    R = orc.OracleRank(p)
+    X = synth.make_block(p, B)
+    xc = R.xcell(B)
+    R.loop_a(X, None, use_nonlocal=False)
+    yref = ref_lib.cell_gemm_batched(xc, R.h_cell, p.num_cell_dofs, B)
+    # oracle: same contraction cell by cell, scattered; compare the scattered result
+    Y1 = np.zeros_like(X); Y2 = np.zeros_like(X)
+    R.loop_b(Y1, None, use_nonlocal=False)
+    orc.lib().orc_scatter_add(orc._f64(yref), C.c_uint32(B), R.ids_p, R.ncd_p, C.c_uint32(R.C), orc._f64(Y2))
+    assert np.abs(Y1 - Y2).max() <= 1e-13 * np.abs(Y2).max()
+
+
+def test_blas1_match_reference_sources(ref_lib):
+    rng = np.random.default_rng(2)
+    n, B = 40, 7
+    x, y = rng.standard_normal(n * B), rng.standard_normal(n * B)
+    al, be = rng.standard_normal(B), rng.standard_normal(B)
+    d = rng.standard_normal(n)
+    L, Rf = orc.lib(), ref_lib.lib()
+    z1, z2 = np.zeros(n * B), np.zeros(n * B)
+    L.orc_axpby(C.c_size_t(n * B), C.c_double(0.3), orc._f64(x), C.c_double(-1.7), orc._f64(y), orc._f64(z1))
+    Rf.ref_axpby(C.c_uint32(n * B), C.c_double(0.3), orc._f64(x), C.c_double(-1.7), orc._f64(y), orc._f64(z2))
+    assert np.array_equal(z1, z2)
+    L.orc_axpby_blocked(C.c_size_t(n), C.c_uint32(B), C.c_double(0.3), orc._f64(al), orc._f64(x), C.c_double(-1.7),
+                        orc._f64(be), orc._f64(y), orc._f64(z1))
+    Rf.ref_axpby_blocked(C.c_uint32(n), C.c_uint32(B), C.c_double(0.3), orc._f64(al), orc._f64(x), C.c_double(-1.7),
+                         orc._f64(be), orc._f64(y), orc._f64(z2))
+    assert np.array_equal(z1, z2)
+    L.orc_row_scale(orc._f64(d), orc._f64(x), orc._f64(z1), C.c_uint32(B), C.c_size_t(n))
+    Rf.ref_row_scale(orc._f64(d), orc._f64(x), orc._f64(z2), C.c_uint32(B), C.c_uint32(n))
+    assert np.array_equal(z1, z2)
+    z2[:] = x
+    Rf.ref_scale_rows_strided(orc._f64(d), orc._f64(z2), C.c_uint32(B), C.c_uint32(n))
+    assert np.array_equal(z1, z2)
+
+
+def _cb_world(W):
+    """Callback that lets the reference's filter templates drive the oracle's operators (1 rank)."""
+    from oracle import ref
+
+    def cb(user, op_id, xp, yp, n, B, ugx, ugy):
+        X = np.ctypeslib.as_array(xp, shape=(n, B))
+        Y = np.ctypeslib.as_array(yp, shape=(n, B))
+        if op_id == 0:
+            W.hx_apply([X], [Y], bool(ugx), bool(ugy))
+        elif op_id == 1:
+            W.minv_apply([X], [Y], bool(ugx), bool(ugy))
+        else:
+            W.m_apply([X], [Y], bool(ugx), bool(ugy))
+    return ref.APPLY_CB(cb)
+
+
+def test_chebyshev_filters_match_reference_sources(ref_lib, probs):
+    p = probs[1][0]
+    W = orc.OracleWorld([p])
+    B, deg = 4, 7
+    a0, a, b = -3.0, 1.0, 60.0
+    X0 = synth.make_block(p, B)
+    cb = _cb_world(W)
+    xr, yr = X0.copy(), np.zeros_like(X0)
+    ref_lib.lib().ref_chebyshev_filter(cb, None, orc._f64(xr), orc._f64(yr), C.c_uint32(p.n_local), C.c_uint32(B),
+                                       C.c_uint32(deg), C.c_double(a0), C.c_double(a), C.c_double(b))
+    xo = [X0.copy()]
+    F = W.chebyshev_filter(xo, deg, a0, a, b)
+    assert np.abs(F[0] - yr).max() <= 1e-13 * np.abs(yr).max()
+    # residual (GEP) filter
+    ev = np.linspace(-2.5, 0.5, B)
+    xr, yr = X0.copy(), np.zeros_like(X0)
+    ref_lib.lib().ref_residual_chebyshev_filter(cb, None, orc._f64(ev), orc._f64(xr), orc._f64(yr),
+                                                C.c_uint32(p.n_local), C.c_uint32(B), C.c_uint32(deg),
+                                                C.c_double(a0), C.c_double(a), C.c_double(b))
+    Yo = W.residual_chebyshev_filter([X0.copy()], ev, deg, a0, a, b)
+    assert np.abs(Yo[0] - yr).max() <= 1e-12 * np.abs(yr).max()
+
+
+# ------------------------------------------- known-answer / invariants -----
+def test_hanging_node_polynomial_reproduction():
+    """reference test/basis/src/TestHomogeneousConstraintMatrix.cpp: a polynomial of degree <= p per
+    direction, set on the unconstrained nodes, is reproduced on the hanging nodes by
+    distributeParentToChild (there: tol 1e-8 at quadrature points, FE order 3)."""
+    nc = (4, 4, 4)
+    spec = synth.MeshSpec(ncell=nc, p=3, refine_mask=synth.refine_ball(nc, 1.0, [[2, 2, 2]], 0.9), boundary="none")
+    p = synth.build_problem(spec)[0]
+    assert p.col_vals.size > 0
+    c = p.node_coords
+    f = (c[:, 0] - 0.1) * c[:, 0] * (c[:, 1] - 0.2) * c[:, 1] * (c[:, 2] - 0.3) * c[:, 2] + c[:, 0] ** 3
+    X = f[:, None].copy()
+    X[p.row_ids.astype(np.int64)] = 123.0  # garbage on constrained rows
+    orc.OracleRank(p).p2c(X)
+    assert np.abs(X[:, 0] - f).max() < 1e-10 * np.abs(f).max()
+    # weights of each hanging row sum to 1 (partition of unity)
+    sums = np.add.reduceat(p.col_vals, p.row_offsets.astype(np.int64)[p.row_sizes > 0])
+    assert np.abs(sums - 1.0).max() < 1e-12
+
+
+def test_partition_independence(probs):
+    B = 4
+    res = {}
+    for n, ps in probs.items():
+        W = orc.OracleWorld(ps)
+        Xs = [synth.make_block(p, B) for p in ps]
+        Ys = [np.zeros_like(x) for x in Xs]
+        W.hx_apply(Xs, Ys, True, False)
+        res[n] = to_natural(ps, Ys)
+    for n in (2, 4):
+        assert np.abs(res[n] - res[1]).max() <= 1e-13 * np.abs(res[1]).max()
+
+
+def test_hx_is_symmetric(probs):
+    """<HX, Y> = <X, HY> on owned unconstrained DoFs (H_c symmetric, C D C^T symmetric)."""
+    ps = probs[2]
+    W = orc.OracleWorld(ps)
+    B = 3
+    Xs = [synth.make_block(p, B, seed=1) for p in ps]
+    Zs = [synth.make_block(p, B, seed=2) for p in ps]
+    for p, X, Z in zip(ps, Xs, Zs):  # constrained rows carry no independent value
+        X[p.row_ids.astype(np.int64)] = 0.0
+        Z[p.row_ids.astype(np.int64)] = 0.0
+    HX = [np.zeros_like(x) for x in Xs]; HZ = [np.zeros_like(x) for x in Xs]
+    W.hx_apply(Xs, HX, True, False)
+    W.hx_apply(Zs, HZ, True, False)
+    a = sum(float(np.sum(h[:p.n_owned] * z[:p.n_owned])) for p, h, z in zip(ps, HX, Zs))
+    b = sum(float(np.sum(x[:p.n_owned] * h[:p.n_owned])) for p, x, h in zip(ps, Xs, HZ))
+    assert abs(a - b) < 1e-11 * max(abs(a), 1.0)
+
+
+def test_ghost_exchange_semantics(probs):
+    """test/utils/src/TestMPICommunicatorP2PUpdateGhosts.cpp / ...AccumulateAdd.cpp:159-188."""
+    ps = probs[4]
+    W = orc.OracleWorld(ps)
+    B = 2
+    # update: every ghost row ends up equal to its owner's value
+    Xs = []
+    for p in ps:
+        x = np.zeros((p.n_local, B))
+        x[:p.n_owned] = p.local_to_global[:p.n_owned, None].astype(float) + np.arange(B)[None, :] * 0.5
+        Xs.append(x)
+    W.update_ghost_values(Xs)
+    for p, x in zip(ps, Xs):
+        assert np.array_equal(x[:, 0], p.local_to_global.astype(float))
+    # accumulate: owned += sum of the ghosts' values; ghost rows untouched
+    Ys = [np.ones((p.n_local, B)) for p in ps]
+    count = {}
+    for p in ps:
+        for g in p.local_to_global[p.n_owned:]:
+            count[int(g)] = count.get(int(g), 0) + 1
+    W.accumulate_add_locally_owned(Ys)
+    for p, y in zip(ps, Ys):
+        exp = np.array([1 + count.get(int(g), 0) for g in p.local_to_global[:p.n_owned]], float)
+        assert np.array_equal(y[:p.n_owned, 0], exp)
+        assert np.all(y[p.n_owned:] == 1.0)
+
+
+def test_m_minv_identity(probs):
+    """M M^-1 x = x on owned unconstrained rows (test/basis/src/TestOrthoEFEOverlapMatrix.cpp:430-440)."""
+    ps = probs[2]
+    W = orc.OracleWorld(ps)
+    B = 3
+    Xs = [synth.make_block(p, B) for p in ps]
+    for p, X in zip(ps, Xs):
+        X[p.row_ids.astype(np.int64)] = 0.0
+    W.update_ghost_values(Xs)
+    X0 = [x.copy() for x in Xs]
+    T = [np.zeros_like(x) for x in Xs]; U = [np.zeros_like(x) for x in Xs]
+    W.minv_apply(Xs, T, True, True)
+    W.m_apply(T, U, True, True)
+    for p, u, x in zip(ps, U, X0):
+        free = np.ones(p.n_owned, bool)
+        free[p.row_ids[p.row_ids < p.n_owned].astype(np.int64)] = False
+        # hanging-node condensation makes M^-1 (diag) only an approximate inverse on parents of
+        # hanging rows; rows untouched by any constraint must be exact
+        touched = np.zeros(p.n_local, bool)
+        touched[p.col_ids.astype(np.int64)] = True
+        m = free & ~touched[:p.n_owned]
+        assert np.abs(u[:p.n_owned][m] - x[:p.n_owned][m]).max() < 1e-12
+
+
+def test_long_double_referee(probs):
+    p = probs[1][0]
+    W = orc.OracleWorld([p])
+    B = 4
+    X = synth.make_block(p, B)
+    Y1 = np.zeros_like(X); Y2 = np.zeros_like(X)
+    W.hx_apply([X.copy()], [Y1], use_nonlocal=False)
+    W.hx_apply([X.copy()], [Y2], use_nonlocal=False, long_double=True)
+    assert np.linalg.norm(Y1 - Y2) <= 1e-14 * np.linalg.norm(Y2)
+
+
+def test_xtopx_and_rotation(probs):
+    ps = probs[2]
+    W = orc.OracleWorld(ps)
+    B = 6
+    Xs = [synth.make_block(p, B) for p in ps]
+    for p, X in zip(ps, Xs):
+        X[p.row_ids.astype(np.int64)] = 0.0
+    S = W.xtopx([x.copy() for x in Xs], lambda a, b, c, d: W.hx_apply(a, b, c, d), batch=4)
+    # dense check through full applies
+    HX = [np.zeros_like(x) for x in Xs]
+    W.hx_apply([x.copy() for x in Xs], HX, True, False)
+    full = sum(x[:p.n_owned].T @ h[:p.n_owned] for p, x, h in zip(ps, Xs, HX))
+    assert np.abs(np.tril(S) - np.tril(full)).max() < 1e-12 * np.abs(full).max()
+    assert np.all(np.triu(S, 1) == 0.0)
+    # rotation X <- X Q
+    Q = np.random.default_rng(3).standard_normal((B, B))
+    Xr = [x.copy() for x in Xs]
+    W.subspace_rotation(Xr, Q, transpose=True, lower_tri=False, dof_block=100, vec_block=4)
+    for p, xr, x in zip(ps, Xr, Xs):
+        assert np.abs(xr[:p.n_owned] - x[:p.n_owned] @ Q).max() < 1e-12
+    Xr = [x.copy() for x in Xs]
+    Ql = np.tril(Q)
+    W.subspace_rotation(Xr, Ql, transpose=False, lower_tri=True, dof_block=100, vec_block=4)
+    for p, xr, x in zip(ps, Xr, Xs):
+        assert np.abs(xr[:p.n_owned] - x[:p.n_owned] @ Ql.T).max() < 1e-12
