@@ -1,0 +1,343 @@
+#!/usr/bin/env python
+"""bench.py — H.X throughput (GDoF.vec/s, FP64) + Chebyshev-filter time on N B200s, beside the CPU path.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|small]
+
+A "step" is one H.X apply (KohnShamOperatorContextFE::apply, updateGhostX=true) over one block of B
+wavefunctions.  N=1 workload = BASELINE.json configs[1]: CH4-like pseudopotential OrthoEFE, FE order 4,
+25^3 cells (1.03 M DoFs), 5 atoms x 4 enrichment functions, nonlocal projectors, B = 32.  For N > 1 the mesh is
+N times longer in z and cut into N slabs (one per GPU, "weak" scaling, per-GPU work fixed); the only
+data-path communication is the halo exchange (NCCL send/recv).
+
+Prints ONE JSON line (rank 0).  `value` = N_global*B / t with inputs resident in HBM; `e2e` = the same metric
+through hx_op_apply_host (pinned HOST buffers, H2D + D2H inside the timed region); `roofline` is for the
+dominant kernel (the fused gather->DMMA->scatter cell kernel), timed with CUDA events on its own stream inside
+the timed region; `cpu_baseline` = the oracle port timed on this box's host cores on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "hx_throughput_fp64"
+UNIT = "GDoF*vec/s"
+
+
+def workload_spec(name: str, nranks: int):
+    from dft_efe_b200 import synth
+    if name == "c2":
+        nc, p, B, h = (25, 25, 25 * nranks), 4, 32, 0.8
+        n_atoms = 5 * nranks
+    elif name == "small":
+        nc, p, B, h = (8, 8, 8 * nranks), 4, 32, 0.8
+        n_atoms = 2 * nranks
+    else:
+        raise SystemExit(f"unknown workload {name}")
+    rng = np.random.default_rng(7)
+    L = np.array(nc) * h
+    atoms = (0.25 + 0.5 * rng.uniform(size=(n_atoms, 3))) * L[None, :]
+    spec = synth.MeshSpec(ncell=nc, p=p, h=h, atoms=atoms, n_enr_per_atom=4, enr_cutoff=1.6 * h,
+                          n_proj_per_atom=4, proj_cutoff=1.3 * h, nranks=nranks, boundary="dirichlet")
+    return spec, B
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        reasons = []
+        for i, name in enumerate(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]):
+            if any(s[2 + i].lower().startswith("active") for s in self.samples if len(s) > 2 + i):
+                reasons.append(name)
+        mx = [int(s[1]) for s in self.samples if s[1].isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.samples)}
+
+
+# ----------------------------------------------------------------------------- CPU leg ----
+def cpu_hx_throughput(sample_cells=(10, 10, 10), p=4, B=32, threads=1, seconds=12.0, warm=1):
+    """Oracle port (reference-faithful: gather, one dgemm per cell through an optimised BLAS, sequential
+    scatter, BLAS-1 constraints) on a bounded sample of the same cell shape; `threads` partitions run
+    concurrently (the stand-in for `mpirun -n threads`)."""
+    os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
+    from concurrent.futures import ThreadPoolExecutor
+    from dft_efe_b200 import synth
+    from oracle import oracle as orc
+    blas = orc.use_scipy_dgemm(True)
+    nc = (sample_cells[0], sample_cells[1], sample_cells[2] * threads)
+    rng = np.random.default_rng(7)
+    L = np.array(nc) * 0.8
+    atoms = (0.25 + 0.5 * rng.uniform(size=(2 * threads, 3))) * L[None, :]
+    spec = synth.MeshSpec(ncell=nc, p=p, h=0.8, atoms=atoms, n_enr_per_atom=4, enr_cutoff=1.28,
+                          n_proj_per_atom=4, proj_cutoff=1.04, nranks=threads, boundary="dirichlet")
+    probs = synth.build_problem(spec)
+    W = orc.OracleWorld(probs)
+    Xs = [synth.make_block(q, B) for q in probs]
+    Ys = [np.zeros_like(x) for x in Xs]
+    N = sum(q.n_owned for q in probs)
+    pool = ThreadPoolExecutor(max_workers=threads)
+
+    def step():
+        # KohnShamOperatorContextFE::apply, rank-parallel sections run on the thread pool
+        W.update_ghost_values(Xs)
+        list(pool.map(lambda i: W.ranks[i].p2c(Xs[i]), range(threads)))
+        for Y in Ys:
+            Y[...] = 0.0
+        CXs = [np.zeros((r.n_proj_local, B)) for r in W.ranks]
+        list(pool.map(lambda i: W.ranks[i].loop_a(Xs[i], CXs[i]), range(threads)))
+        if threads > 1:
+            orc._exchange_accumulate(W.phalos, CXs, W.np_owned)
+            orc._exchange_update(W.phalos, CXs, W.np_owned)
+        for r, CX in zip(W.ranks, CXs):
+            CX *= r.proj_v[:, None]
+        list(pool.map(lambda i: W.ranks[i].loop_b(Ys[i], CXs[i]), range(threads)))
+        list(pool.map(lambda i: W.ranks[i].c2p(Ys[i]), range(threads)))
+        W.accumulate_add_locally_owned(Ys)
+
+    for _ in range(warm):
+        step()
+    t0 = time.perf_counter()
+    n = 0
+    while True:
+        step()
+        n += 1
+        if time.perf_counter() - t0 > seconds or n >= 50:
+            break
+    dt = (time.perf_counter() - t0) / n
+    return {"value": N * B / dt / 1e9, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"H.X on {nc[0]}x{nc[1]}x{nc[2]} cells order {p} ({N} DoFs) B={B}, {threads} partition(s), "
+                      f"{n} applies, per-cell dgemm via {'SciPy OpenBLAS' if blas else 'built-in loops'}",
+            "ms_per_step": dt * 1e3}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    spec, B = workload_spec(args.workload, 1)
+    # bounded sample: each step = one H.X over `cores` partitions of 8^3 cells
+    secs = max(2.0, min(30.0, 3.0 * args.steps))
+    res = cpu_hx_throughput(sample_cells=(8, 8, 8), p=spec.p, B=B, threads=cores, seconds=secs, warm=max(1, min(args.warmup, 2)))
+    line = {"metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
+            "config": {"workload": f"{args.workload}: order-{spec.p} OrthoEFE-like mesh, B={B} (bounded CPU sample)",
+                       "sample": res["sample"]},
+            "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------- GPU leg ----
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from dft_efe_b200 import capi, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node N for --gpus N"
+    nranks = world
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    capi.check(capi.lib().hx_set_device(local_rank))
+    if nranks > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    spec, B = workload_spec(args.workload, nranks)
+    prob = synth.build_problem(spec, only_rank=rank)[0]
+    stream = torch.cuda.Stream()
+    plan = capi.Plan(prob, max_block=B, stream=stream.cuda_stream)
+    if nranks > 1:
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(capi.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        plan.attach_comm(bytes(uid.cpu().numpy().tobytes()))
+    H = capi.CellOp(plan)
+    minv = capi.DiagOp(plan, prob.diag_inv, prob.enr_block_inv, capi.DIAG_OEFE_ATOMBLOCK)
+    X = synth.make_block(prob, B)
+    dX, dY = plan.block(B, X), plan.block(B)
+    N_local = prob.n_owned
+    N_global = N_local
+    if nranks > 1:
+        t = torch.tensor([N_local], dtype=torch.int64, device="cuda")
+        dist.all_reduce(t)
+        N_global = int(t.item())
+
+    def barrier():
+        if nranks > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        H.apply(dX, dY, True, False)
+
+    with torch.cuda.stream(stream):
+        for _ in range(max(args.warmup, 3)):
+            step()
+        plan.synchronize()
+        barrier()
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        plan.enable_kernel_timing(True)
+        l0 = plan.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            step()
+        e1.record(stream)
+        plan.synchronize()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = plan.launch_count() - l0
+        cell_ms, cell_launches = plan.cell_kernel_time_ms()
+        plan.enable_kernel_timing(False)
+
+        # Chebyshev filter (fused step) — degree from CHEBY_ORDER_LOOKUP for a <= 500 Ha bound (Defaults.cpp:51-58)
+        degree = 24
+        dF = plan.block(B)
+        dXf = plan.block(B, X)
+        capi.chebyshev_filter(H, minv, dXf, dF, 2, -3.0, 1.0, 400.0)
+        plan.synchronize()
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record(stream)
+        capi.chebyshev_filter(H, minv, dXf, dF, degree, -3.0, 1.0, 400.0)
+        f1.record(stream)
+        plan.synchronize()
+        barrier()
+        filt_ms = f0.elapsed_time(f1)
+
+        # end to end through the host-buffer entry point (pinned host memory, H2D + D2H every step)
+        xh = torch.from_numpy(X).pin_memory()
+        yh = torch.zeros_like(xh).pin_memory()
+        for _ in range(2):
+            H.apply_host_ptr(xh.data_ptr(), yh.data_ptr(), B, True, False)
+        barrier()
+        e2e_steps = max(3, min(args.steps, 10))
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            H.apply_host_ptr(xh.data_ptr(), yh.data_ptr(), B, True, False)
+        barrier()
+        e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+        sampler.stop_flag = True
+        sampler.join(timeout=2)
+
+    tms = torch.tensor([ms, filt_ms, e2e_ms, cell_ms], dtype=torch.float64, device="cuda")
+    if nranks > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms, filt_ms, e2e_ms, cell_ms = [float(v) for v in tms.cpu()]
+    ms_per_step = ms / args.steps
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
+        # algorithmic bytes per H.X apply on one rank: stream the cell matrices once, read X once,
+        # write Y once, the cell->DoF map and the constraint CSR
+        S2 = prob.S2 + int(np.sum(prob.num_cell_proj.astype(np.int64) * prob.num_cell_dofs.astype(np.int64))) \
+            if prob.num_cell_proj is not None else prob.S2
+        alg_bytes = 8 * S2 + 16 * B * prob.n_local + 4 * prob.S + 12 * prob.col_vals.size + 16 * len(prob.row_ids)
+        flops = 2.0 * B * S2
+        cell_ms_per_apply = cell_ms / args.steps
+        achieved = alg_bytes / (cell_ms_per_apply * 1e-3) / 1e9
+        micro = None
+        try:
+            micro = capi.microbench()
+        except Exception:
+            pass
+        line = {
+            "metric": METRIC, "value": N_global * B / (ms_per_step * 1e-3) / 1e9, "unit": UNIT, "n_gpus": nranks,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: CH4-like PSP OrthoEFE, FE order {spec.p}, "
+                                   f"{spec.ncell[0]}x{spec.ncell[1]}x{spec.ncell[2]} cells, {N_global} DoFs, B={B}, "
+                                   f"{len(spec.atoms)} atoms x {spec.n_enr_per_atom} enrichment fns + "
+                                   f"{spec.n_proj_per_atom} projectors, z-slab per GPU",
+                       "global_dofs": N_global, "block": B, "cells_per_gpu": prob.n_cells, "parallelism": f"cells/{nranks}",
+                       "l2_policy": "inputs larger than L2 (cell matrices %.2f GB + 2 block vectors %.2f GB per GPU)"
+                                    % (8 * S2 / 1e9, 16 * B * prob.n_local / 1e9)},
+            "e2e": {"value": N_global * B / (e2e_ms * 1e-3) / 1e9, "unit": UNIT,
+                    "h2d_bytes_per_step": 8 * B * prob.n_local,
+                    "d2h_bytes_per_step": 8 * B * prob.n_local * (2 if len(prob.row_ids) else 1), "ms_per_step": e2e_ms},
+            "gpu_launches": int(launches),
+            "clocks": sampler.summary(),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                         "kernel": "cell_apply_kernel (all colour launches of one apply)",
+                         "kernel_ms_per_apply": cell_ms_per_apply, "kernel_share_of_step": cell_ms_per_apply / ms_per_step,
+                         "algorithmic_bytes_per_apply": alg_bytes, "flops_per_apply": flops,
+                         "tensor": {"achieved_tflops": flops / (cell_ms_per_apply * 1e-3) / 1e12,
+                                    "dmma_peak_tflops_measured": micro["dmma_tflops"] if micro else None,
+                                    "dfma_peak_tflops_measured": micro["dfma_tflops"] if micro else None,
+                                    "copy_gbs_measured": micro["copy_gbs"] if micro else None}},
+            "chebyshev_filter": {"degree": degree, "seconds_per_scf_iter": filt_ms * 1e-3, "ms_per_degree": filt_ms / degree,
+                                 "fused_recurrence": True},
+        }
+        if not args.no_cpu and nranks == 1:
+            try:
+                line["cpu_baseline"] = {k: v for k, v in cpu_hx_throughput(threads=1, seconds=10.0, p=spec.p, B=B).items()
+                                        if k != "ms_per_step"}
+            except Exception as e:  # the oracle is a checker; its absence must not hide the GPU number
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "port", "sample": f"failed: {e}"}
+        print(json.dumps(line))
+    if nranks > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "small"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

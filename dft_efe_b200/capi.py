@@ -1,0 +1,345 @@
+"""ctypes binding of the C ABI in include/hxb200.h (harness for tests and bench; the product is the .so).
+
+Fails loudly when the library is missing or no CUDA device is usable: there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libhxb200.so")
+
+u32p = C.POINTER(C.c_uint32)
+f64p = C.POINTER(C.c_double)
+
+EXPORTS = [
+    "hx_last_error", "hx_version", "hx_device_count", "hx_set_device", "hx_device_alloc", "hx_device_free",
+    "hx_host_alloc_pinned", "hx_host_free_pinned", "hx_memcpy_h2d", "hx_memcpy_d2h", "hx_memset_zero",
+    "hx_plan_create", "hx_plan_destroy", "hx_plan_synchronize", "hx_comm_unique_id", "hx_plan_attach_comm",
+    "hx_plan_num_colours", "hx_plan_get_cell_colours", "hx_plan_get_c2p_transpose", "hx_update_ghost_values",
+    "hx_accumulate_add_locally_owned", "hx_distribute_parent_to_child", "hx_distribute_child_to_parent",
+    "hx_set_constrained_nodes_to_zero", "hx_cellop_create", "hx_cellop_set_matrices", "hx_cellop_set_nonlocal",
+    "hx_diagop_create", "hx_op_destroy", "hx_op_apply", "hx_op_apply_host", "hx_chebyshev_filter",
+    "hx_residual_chebyshev_filter", "hx_xtopx", "hx_subspace_rotation", "hx_l2_norms", "hx_axpby",
+    "hx_axpby_blocked", "hx_plan_launch_count", "hx_plan_cell_kernel_time_ms", "hx_plan_enable_kernel_timing",
+    "hx_microbench",
+]
+
+
+class HaloDesc(C.Structure):
+    _fields_ = [("n_owned", C.c_uint32), ("n_ghost", C.c_uint32), ("n_ghost_procs", C.c_uint32),
+                ("ghost_proc_ids", u32p), ("ghost_ranges", u32p), ("ghost_local_ids", u32p),
+                ("n_target_procs", C.c_uint32), ("target_proc_ids", u32p), ("num_owned_for_target", u32p),
+                ("owned_local_ids_for_targets", u32p)]
+
+
+class MeshDesc(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("rank", C.c_int32), ("nranks", C.c_int32), ("halo", HaloDesc),
+                ("n_owned_classical", C.c_uint32), ("n_cells", C.c_uint32), ("num_cell_dofs", u32p),
+                ("cell_local_ids", u32p), ("n_constraint_rows", C.c_uint32), ("row_ids", u32p), ("row_sizes", u32p),
+                ("row_offsets", u32p), ("col_ids", u32p), ("col_vals", f64p), ("inhom", f64p),
+                ("max_block", C.c_uint32)]
+
+
+class NonlocalDesc(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("proj_halo", HaloDesc), ("num_cell_proj", u32p),
+                ("cell_proj_local_ids", u32p), ("cell_c", f64p), ("v", f64p)]
+
+
+class HxError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise HxError(f"{LIB_PATH} not built (run python dft_efe_b200/build.py or __graft_entry__.build())")
+        _lib = C.CDLL(LIB_PATH)
+        _lib.hx_last_error.restype = C.c_char_p
+    return _lib
+
+
+def check(rc: int):
+    if rc != 0:
+        raise HxError(f"hxb200 error {rc}: {lib().hx_last_error().decode()}")
+
+
+def _u32(a):
+    a = np.ascontiguousarray(a, dtype=np.uint32)
+    return a, a.ctypes.data_as(u32p)
+
+
+def _f64(a):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return a, a.ctypes.data_as(f64p)
+
+
+def _halo_desc(h, keep):
+    d = HaloDesc()
+    d.n_owned, d.n_ghost = h.n_owned, h.n_ghost
+    d.n_ghost_procs = len(h.ghost_proc_ids)
+    d.n_target_procs = len(h.target_proc_ids)
+    for name in ("ghost_proc_ids", "ghost_ranges", "ghost_local_ids", "target_proc_ids", "num_owned_for_target",
+                 "owned_local_ids_for_targets"):
+        a, p = _u32(getattr(h, name))
+        keep.append(a)
+        setattr(d, name, p)
+    return d
+
+
+def device_count() -> int:
+    n = C.c_int(0)
+    check(lib().hx_device_count(C.byref(n)))
+    return n.value
+
+
+class DeviceBlock:
+    """A block vector [n_rows, B] of doubles in device memory."""
+
+    def __init__(self, n_rows: int, B: int, host: Optional[np.ndarray] = None):
+        self.n_rows, self.B = n_rows, B
+        self.ptr = C.c_void_p()
+        check(lib().hx_device_alloc(C.byref(self.ptr), C.c_size_t(max(n_rows * B, 1) * 8)))
+        if host is not None:
+            self.upload(host)
+        else:
+            check(lib().hx_memset_zero(self.ptr, C.c_size_t(n_rows * B * 8)))
+
+    @property
+    def p(self):
+        return C.cast(self.ptr, f64p)
+
+    def upload(self, host):
+        a, p = _f64(host)
+        assert a.size == self.n_rows * self.B
+        check(lib().hx_memcpy_h2d(self.ptr, p, C.c_size_t(a.size * 8)))
+
+    def download(self) -> np.ndarray:
+        out = np.empty((self.n_rows, self.B))
+        check(lib().hx_memcpy_d2h(out.ctypes.data_as(f64p), self.ptr, C.c_size_t(out.size * 8)))
+        return out
+
+    def free(self):
+        if self.ptr:
+            lib().hx_device_free(self.ptr)
+            self.ptr = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Plan:
+    def __init__(self, prob, max_block: int, stream=None):
+        self.prob = prob
+        keep = []
+        m = MeshDesc()
+        m.struct_size = C.sizeof(MeshDesc)
+        m.rank, m.nranks = prob.rank, prob.nranks
+        m.halo = _halo_desc(prob.halo, keep)
+        m.n_owned_classical = prob.n_owned_classical
+        m.n_cells = prob.n_cells
+        for name, src in (("num_cell_dofs", prob.num_cell_dofs), ("cell_local_ids", prob.cell_local_ids),
+                          ("row_ids", prob.row_ids), ("row_sizes", prob.row_sizes), ("row_offsets", prob.row_offsets),
+                          ("col_ids", prob.col_ids)):
+            a, p = _u32(src)
+            keep.append(a)
+            setattr(m, name, p)
+        m.n_constraint_rows = len(prob.row_ids)
+        for name, src in (("col_vals", prob.col_vals), ("inhom", prob.inhom)):
+            a, p = _f64(src)
+            keep.append(a)
+            setattr(m, name, p)
+        m.max_block = max_block
+        self.h = C.c_void_p()
+        check(lib().hx_plan_create(C.byref(self.h), C.byref(m), C.c_void_p(stream) if stream else None))
+        self.max_block = max_block
+        self.n_local, self.n_owned = prob.n_local, prob.n_owned
+
+    def destroy(self):
+        if self.h:
+            lib().hx_plan_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+    def synchronize(self):
+        check(lib().hx_plan_synchronize(self.h))
+
+    def attach_comm(self, uid: bytes):
+        assert len(uid) == 128
+        check(lib().hx_plan_attach_comm(self.h, C.c_char_p(uid)))
+
+    def colours(self):
+        n = C.c_uint32()
+        check(lib().hx_plan_num_colours(self.h, C.byref(n)))
+        col = np.zeros(self.prob.n_cells, np.uint32)
+        check(lib().hx_plan_get_cell_colours(self.h, col.ctypes.data_as(u32p)))
+        return n.value, col
+
+    def c2p_transpose(self):
+        n = C.c_uint32()
+        check(lib().hx_plan_get_c2p_transpose(self.h, C.byref(n), None, None, None, None))
+        ids = np.zeros(n.value, np.uint32)
+        off = np.zeros(n.value + 1, np.uint32)
+        nnz = int(self.prob.row_sizes.sum())
+        ch = np.zeros(nnz, np.uint32)
+        w = np.zeros(nnz)
+        check(lib().hx_plan_get_c2p_transpose(self.h, C.byref(n), ids.ctypes.data_as(u32p), off.ctypes.data_as(u32p),
+                                              ch.ctypes.data_as(u32p), w.ctypes.data_as(f64p)))
+        return ids, off, ch, w
+
+    def block(self, B, host=None) -> DeviceBlock:
+        return DeviceBlock(self.n_local, B, host)
+
+    def update_ghost_values(self, X: DeviceBlock):
+        check(lib().hx_update_ghost_values(self.h, X.p, C.c_uint32(X.B)))
+
+    def accumulate_add_locally_owned(self, Y: DeviceBlock):
+        check(lib().hx_accumulate_add_locally_owned(self.h, Y.p, C.c_uint32(Y.B)))
+
+    def p2c(self, X: DeviceBlock):
+        check(lib().hx_distribute_parent_to_child(self.h, X.p, C.c_uint32(X.B)))
+
+    def c2p(self, Y: DeviceBlock):
+        check(lib().hx_distribute_child_to_parent(self.h, Y.p, C.c_uint32(Y.B)))
+
+    def l2_norms(self, X: DeviceBlock) -> np.ndarray:
+        out = np.zeros(X.B)
+        check(lib().hx_l2_norms(self.h, X.p, C.c_uint32(X.B), out.ctypes.data_as(f64p)))
+        return out
+
+    def subspace_rotation(self, X: DeviceBlock, Q: np.ndarray, transpose: bool, lower_tri: bool):
+        Qc = np.asfortranarray(Q, dtype=np.float64)
+        check(lib().hx_subspace_rotation(self.h, X.p, C.c_uint32(X.B), Qc.ctypes.data_as(f64p), C.c_int(int(transpose)),
+                                         C.c_int(int(lower_tri))))
+
+    def launch_count(self) -> int:
+        n = C.c_uint64()
+        check(lib().hx_plan_launch_count(self.h, C.byref(n)))
+        return n.value
+
+    def enable_kernel_timing(self, on=True):
+        check(lib().hx_plan_enable_kernel_timing(self.h, C.c_int(int(on))))
+
+    def cell_kernel_time_ms(self):
+        ms = C.c_double()
+        n = C.c_uint64()
+        check(lib().hx_plan_cell_kernel_time_ms(self.h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+
+class Op:
+    def __init__(self, plan: Plan):
+        self.plan = plan
+        self.h = C.c_void_p()
+
+    def apply(self, X: DeviceBlock, Y: DeviceBlock, update_ghost_x=False, update_ghost_y=False):
+        assert X.B == Y.B
+        check(lib().hx_op_apply(self.h, X.p, Y.p, C.c_uint32(X.B), C.c_int(int(update_ghost_x)),
+                                C.c_int(int(update_ghost_y))))
+
+    def apply_host(self, Xh: np.ndarray, Yh: np.ndarray, update_ghost_x=False, update_ghost_y=False):
+        assert Xh.flags["C_CONTIGUOUS"] and Yh.flags["C_CONTIGUOUS"] and Xh.dtype == np.float64
+        check(lib().hx_op_apply_host(self.h, Xh.ctypes.data_as(f64p), Yh.ctypes.data_as(f64p), C.c_uint32(Xh.shape[1]),
+                                     C.c_int(int(update_ghost_x)), C.c_int(int(update_ghost_y))))
+
+    def apply_host_ptr(self, xptr, yptr, B, update_ghost_x=False, update_ghost_y=False):
+        check(lib().hx_op_apply_host(self.h, C.cast(xptr, f64p), C.cast(yptr, f64p), C.c_uint32(B),
+                                     C.c_int(int(update_ghost_x)), C.c_int(int(update_ghost_y))))
+
+    def xtopx(self, X: DeviceBlock, batch: int) -> np.ndarray:
+        S = np.zeros((X.B, X.B), order="F")
+        check(lib().hx_xtopx(self.h, X.p, C.c_uint32(X.B), C.c_uint32(batch), S.ctypes.data_as(f64p)))
+        return S
+
+    def destroy(self):
+        if self.h:
+            lib().hx_op_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+
+class CellOp(Op):
+    """KohnShamOperatorContextFE-shaped operator (cell matrices + optional nonlocal projectors)."""
+
+    def __init__(self, plan: Plan, h_cell=None, with_nonlocal=True):
+        super().__init__(plan)
+        check(lib().hx_cellop_create(plan.h, C.byref(self.h)))
+        prob = plan.prob
+        if with_nonlocal and prob.num_cell_proj is not None:
+            keep = []
+            d = NonlocalDesc()
+            d.struct_size = C.sizeof(NonlocalDesc)
+            d.proj_halo = _halo_desc(prob.proj_halo, keep)
+            a, d.num_cell_proj = _u32(prob.num_cell_proj); keep.append(a)
+            a, d.cell_proj_local_ids = _u32(prob.cell_proj_local_ids); keep.append(a)
+            a, d.cell_c = _f64(prob.cell_c); keep.append(a)
+            a, d.v = _f64(prob.proj_v); keep.append(a)
+            check(lib().hx_cellop_set_nonlocal(self.h, C.byref(d)))
+        self.set_matrices(prob.h_cell if h_cell is None else h_cell)
+
+    def set_matrices(self, h_cell: np.ndarray):
+        a, p = _f64(h_cell)
+        assert a.size == self.plan.prob.S2
+        check(lib().hx_cellop_set_matrices(self.h, p, C.c_int(0)))
+
+    def set_matrices_device(self, dev_ptr):
+        check(lib().hx_cellop_set_matrices(self.h, C.cast(dev_ptr, f64p), C.c_int(1)))
+
+
+DIAG_CFE, DIAG_OEFE_ATOMBLOCK, DIAG_OEFE_MASS = 0, 1, 2
+
+
+class DiagOp(Op):
+    def __init__(self, plan: Plan, diag: np.ndarray, enr_block: Optional[np.ndarray], variant: int):
+        super().__init__(plan)
+        a, p = _f64(diag)
+        assert a.size == plan.n_local
+        if enr_block is not None and enr_block.size:
+            e, ep = _f64(enr_block)
+        else:
+            e, ep = None, None
+        check(lib().hx_diagop_create(plan.h, p, ep, C.c_int(variant), C.byref(self.h)))
+
+
+def chebyshev_filter(A: Op, BInv: Op, X: DeviceBlock, Y: DeviceBlock, degree, a0, a, b):
+    check(lib().hx_chebyshev_filter(A.h, BInv.h, X.p, Y.p, C.c_uint32(X.B), C.c_uint32(degree), C.c_double(a0),
+                                    C.c_double(a), C.c_double(b)))
+
+
+def residual_chebyshev_filter(A: Op, Bop: Op, BInv: Op, eig: np.ndarray, X: DeviceBlock, Y: DeviceBlock, degree, a0, a, b):
+    e, ep = _f64(eig)
+    check(lib().hx_residual_chebyshev_filter(A.h, Bop.h, BInv.h, ep, X.p, Y.p, C.c_uint32(X.B), C.c_uint32(degree),
+                                             C.c_double(a0), C.c_double(a), C.c_double(b)))
+
+
+def comm_unique_id() -> bytes:
+    buf = C.create_string_buffer(128)
+    check(lib().hx_comm_unique_id(buf))
+    return buf.raw
+
+
+def microbench():
+    a, b, c = C.c_double(), C.c_double(), C.c_double()
+    check(lib().hx_microbench(C.byref(a), C.byref(b), C.byref(c)))
+    return {"dmma_tflops": a.value, "dfma_tflops": b.value, "copy_gbs": c.value}

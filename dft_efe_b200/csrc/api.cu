@@ -1,0 +1,1010 @@
+// api.cu — host-side logic of libhxb200 and the extern "C" entry points declared in include/hxb200.h.
+#include <stdarg.h>
+
+#include <algorithm>
+#include <map>
+#include <new>
+
+#include "hx_internal.h"
+
+namespace hx
+{
+  static thread_local char g_err[1024] = "";
+  void
+  set_error(const char *fmt, ...)
+  {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+  }
+
+  int
+  Halo::init(const hx_halo_desc &h, uint32_t max_block)
+  {
+    n_owned = h.n_owned;
+    n_ghost = h.n_ghost;
+    ghost_procs.assign(h.ghost_proc_ids, h.ghost_proc_ids + h.n_ghost_procs);
+    ghost_ranges.assign(h.ghost_ranges, h.ghost_ranges + 2 * (size_t)h.n_ghost_procs);
+    target_procs.assign(h.target_proc_ids, h.target_proc_ids + h.n_target_procs);
+    target_counts.assign(h.num_owned_for_target, h.num_owned_for_target + h.n_target_procs);
+    n_send = 0;
+    for (uint32_t c : target_counts)
+      n_send += c;
+    uint32_t nrecv = 0;
+    for (uint32_t i = 0; i < h.n_ghost_procs; ++i)
+      {
+        HX_CHECK(ghost_ranges[2 * i + 1] >= ghost_ranges[2 * i], HX_ERR_INVALID, "halo: bad ghost range %u", i);
+        nrecv += ghost_ranges[2 * i + 1] - ghost_ranges[2 * i];
+      }
+    HX_CHECK(nrecv == n_ghost, HX_ERR_INVALID, "halo: ghost ranges cover %u of %u ghosts", nrecv, n_ghost);
+    for (uint32_t i = 0; i < n_ghost; ++i)
+      HX_CHECK(h.ghost_local_ids[i] < n_ghost, HX_ERR_INVALID, "halo: ghost local id out of range");
+    for (uint32_t i = 0; i < n_send; ++i)
+      HX_CHECK(h.owned_local_ids_for_targets[i] < n_owned, HX_ERR_INVALID, "halo: owned id for target out of range");
+    HX_TRY(d_ghost_local_ids.upload(h.ghost_local_ids, n_ghost));
+    HX_TRY(d_owned_ids_for_targets.upload(h.owned_local_ids_for_targets, n_send));
+    // accumulate CSR: owned row -> positions in the receive buffer, ascending (= reference buffer order)
+    std::vector<std::pair<uint32_t, uint32_t>> rp(n_send);
+    for (uint32_t i = 0; i < n_send; ++i)
+      rp[i] = {h.owned_local_ids_for_targets[i], i};
+    std::stable_sort(rp.begin(), rp.end(), [](auto &x, auto &y) { return x.first < y.first; });
+    std::vector<uint32_t> rows, off, pos(n_send);
+    for (uint32_t i = 0; i < n_send; ++i)
+      {
+        if (i == 0 || rp[i].first != rp[i - 1].first)
+          {
+            rows.push_back(rp[i].first);
+            off.push_back(i);
+          }
+        pos[i] = rp[i].second;
+      }
+    off.push_back(n_send);
+    n_acc_rows = (uint32_t)rows.size();
+    HX_TRY(d_acc_rows.upload(rows));
+    HX_TRY(d_acc_off.upload(off));
+    HX_TRY(d_acc_pos.upload(pos));
+    const size_t m = (size_t)std::max(n_send, n_ghost) * max_block;
+    HX_TRY(d_send.alloc(m));
+    HX_TRY(d_recv.alloc(m));
+    return HX_OK;
+  }
+
+  static int
+  halo_update(hx_plan *p, Halo &h, double *X, uint32_t B)
+  {
+    if (p->nranks == 1 || (h.n_ghost == 0 && h.n_send == 0))
+      return HX_OK;
+    HX_CHECK(p->comm != nullptr, HX_ERR_COMM, "nranks > 1 but no communicator attached (hx_plan_attach_comm)");
+    HX_TRY(launch_pack(p, X, B, h.d_owned_ids_for_targets.p, h.n_send, h.d_send.p));
+    std::vector<size_t> sc(h.target_counts.size()), rc(h.ghost_procs.size());
+    for (size_t i = 0; i < sc.size(); ++i)
+      sc[i] = (size_t)h.target_counts[i] * B;
+    for (size_t i = 0; i < rc.size(); ++i)
+      rc[i] = (size_t)(h.ghost_ranges[2 * i + 1] - h.ghost_ranges[2 * i]) * B;
+    HX_TRY(comm_exchange(p->comm, p->stream, h.d_send.p, h.target_procs, sc, h.d_recv.p, h.ghost_procs, rc));
+    return launch_unpack(p, h.d_recv.p, B, h.d_ghost_local_ids.p, h.n_ghost, X + (size_t)h.n_owned * B);
+  }
+
+  static int
+  halo_accumulate(hx_plan *p, Halo &h, double *Y, uint32_t B)
+  {
+    if (p->nranks == 1 || (h.n_ghost == 0 && h.n_send == 0))
+      return HX_OK;
+    HX_CHECK(p->comm != nullptr, HX_ERR_COMM, "nranks > 1 but no communicator attached (hx_plan_attach_comm)");
+    HX_TRY(launch_pack(p, Y + (size_t)h.n_owned * B, B, h.d_ghost_local_ids.p, h.n_ghost, h.d_send.p));
+    std::vector<size_t> sc(h.ghost_procs.size()), rc(h.target_counts.size());
+    for (size_t i = 0; i < sc.size(); ++i)
+      sc[i] = (size_t)(h.ghost_ranges[2 * i + 1] - h.ghost_ranges[2 * i]) * B;
+    for (size_t i = 0; i < rc.size(); ++i)
+      rc[i] = (size_t)h.target_counts[i] * B;
+    HX_TRY(comm_exchange(p->comm, p->stream, h.d_send.p, h.ghost_procs, sc, h.d_recv.p, h.target_procs, rc));
+    return launch_add_rows(p, h.d_recv.p, B, h.d_acc_rows.p, h.d_acc_off.p, h.d_acc_pos.p, h.n_acc_rows, Y);
+  }
+
+  // ---------------------------------------------------------------------------------------------
+  static int
+  build_plan(hx_plan *p, const hx_mesh_desc *m)
+  {
+    p->rank              = m->rank;
+    p->nranks            = m->nranks;
+    p->n_owned           = m->halo.n_owned;
+    p->n_ghost           = m->halo.n_ghost;
+    p->n_local           = p->n_owned + p->n_ghost;
+    p->n_owned_classical = m->n_owned_classical;
+    p->C                 = m->n_cells;
+    p->max_block         = m->max_block ? m->max_block : 1;
+    HX_CHECK(p->n_owned_classical <= p->n_owned, HX_ERR_INVALID, "n_owned_classical > n_owned");
+    HX_CHECK(p->nranks >= 1 && p->rank >= 0 && p->rank < p->nranks, HX_ERR_INVALID, "bad rank/nranks");
+    HX_CHECK(p->n_local < 0x7fffffffu, HX_ERR_INVALID, "too many local rows");
+
+    p->h_ncd.assign(m->num_cell_dofs, m->num_cell_dofs + p->C);
+    p->h_cell_off.assign(p->C + 1, 0);
+    p->S2    = 0;
+    p->max_n = 0;
+    for (uint32_t c = 0; c < p->C; ++c)
+      {
+        HX_CHECK((uint64_t)p->h_cell_off[c] + p->h_ncd[c] < 0xffffffffull, HX_ERR_INVALID, "cell map too large");
+        p->h_cell_off[c + 1] = p->h_cell_off[c] + p->h_ncd[c];
+        p->S2 += (size_t)p->h_ncd[c] * p->h_ncd[c];
+        p->max_n = std::max(p->max_n, p->h_ncd[c]);
+      }
+    p->S = p->h_cell_off[p->C];
+    p->h_ids.assign(m->cell_local_ids, m->cell_local_ids + p->S);
+    for (uint32_t i = 0; i < p->S; ++i)
+      HX_CHECK(p->h_ids[i] < p->n_local, HX_ERR_INVALID, "cell_local_ids[%u] = %u out of range", i, p->h_ids[i]);
+    HX_TRY(p->d_ids.upload(p->h_ids));
+    HX_TRY(p->d_cell_off.upload(p->h_cell_off));
+    HX_TRY(p->d_ncd.upload(p->h_ncd));
+
+    // ---- constraints ----
+    p->nR  = m->n_constraint_rows;
+    p->nnz = 0;
+    std::vector<uint32_t> rowinfo(p->n_local, 0xFFFFFFFFu);
+    for (uint32_t i = 0; i < p->nR; ++i)
+      {
+        HX_CHECK(m->row_ids[i] < p->n_local, HX_ERR_INVALID, "constraint row id out of range");
+        HX_CHECK(rowinfo[m->row_ids[i]] == 0xFFFFFFFFu, HX_ERR_INVALID, "duplicate constraint row %u", m->row_ids[i]);
+        rowinfo[m->row_ids[i]] = 0xFFFFFFFEu;
+        p->nnz                 = std::max(p->nnz, m->row_offsets[i] + m->row_sizes[i]);
+      }
+    std::map<uint32_t, std::vector<std::pair<uint32_t, double>>> par;
+    for (uint32_t i = 0; i < p->nR; ++i)
+      for (uint32_t j = 0; j < m->row_sizes[i]; ++j)
+        {
+          const uint32_t col = m->col_ids[m->row_offsets[i] + j];
+          HX_CHECK(col < p->n_local, HX_ERR_INVALID, "constraint column id out of range");
+          // the parallel distribute kernels need closed constraints (deal.II AffineConstraints::close(),
+          // reference src/basis/CFEConstraintsLocalDealii.t.cpp:96-104)
+          HX_CHECK(rowinfo[col] != 0xFFFFFFFEu, HX_ERR_UNSUPPORTED,
+                   "constraint chain: row %u depends on constrained row %u (constraints must be closed)",
+                   m->row_ids[i], col);
+          par[col].push_back({m->row_ids[i], m->col_vals[m->row_offsets[i] + j]});
+        }
+    p->h_par_ids.clear();
+    p->h_par_off.assign(1, 0);
+    p->h_par_child.clear();
+    p->h_par_w.clear();
+    for (auto &kv : par)
+      {
+        rowinfo[kv.first] = (uint32_t)p->h_par_ids.size();
+        p->h_par_ids.push_back(kv.first);
+        for (auto &e : kv.second)
+          {
+            p->h_par_child.push_back(e.first);
+            p->h_par_w.push_back(e.second);
+          }
+        p->h_par_off.push_back((uint32_t)p->h_par_child.size());
+      }
+    p->nPar = (uint32_t)p->h_par_ids.size();
+    HX_TRY(p->d_row_ids.upload(m->row_ids, p->nR));
+    HX_TRY(p->d_row_sizes.upload(m->row_sizes, p->nR));
+    HX_TRY(p->d_row_offsets.upload(m->row_offsets, p->nR));
+    HX_TRY(p->d_col_ids.upload(m->col_ids, p->nnz));
+    HX_TRY(p->d_col_vals.upload(m->col_vals, p->nnz));
+    HX_TRY(p->d_inhom.upload(m->inhom, p->nR));
+    HX_TRY(p->d_par_ids.upload(p->h_par_ids));
+    HX_TRY(p->d_par_off.upload(p->h_par_off));
+    HX_TRY(p->d_par_child.upload(p->h_par_child));
+    HX_TRY(p->d_par_w.upload(p->h_par_w));
+    HX_TRY(p->d_rowinfo.upload(rowinfo));
+
+    // ---- shared rows: touched by more than 8 cells (enrichment DoFs); they bypass the colouring ----
+    std::vector<uint32_t> incidence(p->n_local, 0);
+    for (uint32_t i = 0; i < p->S; ++i)
+      incidence[p->h_ids[i]]++;
+    const uint32_t        SHARED_THRESHOLD = 8;
+    std::vector<uint32_t> dest(p->S);
+    std::map<uint32_t, std::vector<uint32_t>> shared;
+    p->n_slots = 0;
+    for (uint32_t i = 0; i < p->S; ++i)
+      {
+        const uint32_t r = p->h_ids[i];
+        if (incidence[r] > SHARED_THRESHOLD)
+          {
+            shared[r].push_back(p->n_slots);
+            dest[i] = 0x80000000u | p->n_slots;
+            p->n_slots++;
+          }
+        else
+          dest[i] = r;
+      }
+    std::vector<uint32_t> sh_rows, sh_off(1, 0), sh_slots;
+    for (auto &kv : shared)
+      {
+        sh_rows.push_back(kv.first);
+        sh_slots.insert(sh_slots.end(), kv.second.begin(), kv.second.end());
+        sh_off.push_back((uint32_t)sh_slots.size());
+      }
+    p->n_shared = (uint32_t)sh_rows.size();
+    HX_TRY(p->d_dest.upload(dest));
+    HX_TRY(p->d_sh_rows.upload(sh_rows));
+    HX_TRY(p->d_sh_off.upload(sh_off));
+    HX_TRY(p->d_sh_slots.upload(sh_slots));
+    HX_TRY(p->d_stage.alloc((size_t)p->n_slots * p->max_block));
+
+    // ---- greedy cell colouring on the cell-DoF graph (non-shared rows only) ----
+    // cell c takes the lowest colour not used by any earlier cell sharing a row with it.
+    std::vector<uint64_t> used(p->n_local, 0);
+    p->h_colour.assign(p->C, 0);
+    p->n_colours = 0;
+    for (uint32_t c = 0; c < p->C; ++c)
+      {
+        uint64_t mask = 0;
+        for (uint32_t i = p->h_cell_off[c]; i < p->h_cell_off[c + 1]; ++i)
+          if (!(dest[i] & 0x80000000u))
+            mask |= used[p->h_ids[i]];
+        HX_CHECK(mask != ~0ull, HX_ERR_UNSUPPORTED, "cell %u needs more than 64 colours", c);
+        uint32_t col = 0;
+        while (mask & (1ull << col))
+          ++col;
+        p->h_colour[c] = col;
+        p->n_colours   = std::max(p->n_colours, col + 1);
+        for (uint32_t i = p->h_cell_off[c]; i < p->h_cell_off[c + 1]; ++i)
+          if (!(dest[i] & 0x80000000u))
+            used[p->h_ids[i]] |= (1ull << col);
+      }
+    // a row listed twice inside one cell would race inside the CTA: reject
+    {
+      std::vector<uint32_t> seen(p->n_local, 0xffffffffu);
+      for (uint32_t c = 0; c < p->C; ++c)
+        for (uint32_t i = p->h_cell_off[c]; i < p->h_cell_off[c + 1]; ++i)
+          {
+            HX_CHECK(seen[p->h_ids[i]] != c, HX_ERR_UNSUPPORTED, "cell %u lists local row %u twice", c, p->h_ids[i]);
+            seen[p->h_ids[i]] = c;
+          }
+    }
+    p->h_colour_off.assign(p->n_colours + 1, 0);
+    for (uint32_t c = 0; c < p->C; ++c)
+      p->h_colour_off[p->h_colour[c] + 1]++;
+    for (uint32_t k = 0; k < p->n_colours; ++k)
+      p->h_colour_off[k + 1] += p->h_colour_off[k];
+    p->h_colour_cells.resize(p->C);
+    {
+      std::vector<uint32_t> fill(p->h_colour_off.begin(), p->h_colour_off.end() - 1);
+      for (uint32_t c = 0; c < p->C; ++c)
+        p->h_colour_cells[fill[p->h_colour[c]]++] = c;
+    }
+    HX_TRY(p->d_colour_cells.upload(p->h_colour_cells));
+
+    HX_TRY(p->halo.init(m->halo, p->max_block));
+    HX_CUDA(cudaEventCreate(&p->ev0));
+    HX_CUDA(cudaEventCreate(&p->ev1));
+    return HX_OK;
+  }
+
+  // ---------------------------------------------------------------------------------------------
+  static int
+  cellop_apply(hx_op *op, double *X, double *Y, uint32_t B, int ugx, int ugy)
+  {
+    hx_plan *p = op->plan;
+    if (ugx)
+      HX_TRY(halo_update(p, p->halo, X, B));
+    HX_TRY(launch_p2c(p, X, B));
+    HX_CUDA(cudaMemsetAsync(Y, 0, (size_t)p->n_local * B * sizeof(double), p->stream));
+    if (op->has_nl)
+      {
+        HX_TRY(launch_nl_phase_a(op, X, B));
+        if (p->nranks > 1)
+          {
+            // applyAllReduceOnCconjtransX + applyVOnCconjtransX
+            HX_TRY(halo_accumulate(p, op->phalo, op->d_cx.p, B));
+            HX_TRY(halo_update(p, op->phalo, op->d_cx.p, B));
+            HX_TRY(launch_row_scale(p, op->d_v.p, op->d_cx.p, op->d_cx.p, B, op->n_proj_local));
+          }
+      }
+    HX_TRY(launch_cell_apply(op, X, Y, B));
+    HX_TRY(launch_shared_reduce(p, Y, B));
+    HX_TRY(launch_c2p(p, Y, B));
+    HX_TRY(halo_accumulate(p, p->halo, Y, B));
+    if (ugy)
+      HX_TRY(halo_update(p, p->halo, Y, B));
+    return HX_OK;
+  }
+
+  static int
+  diagop_apply(hx_op *op, double *X, double *Y, uint32_t B, int ugx, int ugy)
+  {
+    hx_plan *p = op->plan;
+    if (op->variant == HX_DIAG_OEFE_MASS)
+      ugx = ugy = 0;
+    if (ugx)
+      HX_TRY(halo_update(p, p->halo, X, B));
+    HX_TRY(launch_p2c(p, X, B));
+    HX_TRY(launch_row_scale(p, op->d_diag.p, X, Y, B, p->n_local));
+    if (op->variant != HX_DIAG_CFE)
+      {
+        const size_t o = (size_t)p->n_owned_classical * B;
+        HX_TRY(launch_enr_block(p, op->d_enr_block.p, op->nE, X + o, Y + o, B));
+        HX_TRY(halo_update(p, p->halo, Y, B));
+      }
+    HX_TRY(launch_c2p(p, Y, B));
+    if (ugy)
+      HX_TRY(halo_update(p, p->halo, Y, B));
+    return HX_OK;
+  }
+
+  static int
+  op_apply(hx_op *op, double *X, double *Y, uint32_t B, int ugx, int ugy)
+  {
+    HX_CHECK(op && X && Y, HX_ERR_INVALID, "null argument");
+    HX_CHECK(B >= 1 && B <= op->plan->max_block, HX_ERR_INVALID, "B = %u outside [1, max_block = %u]", B,
+             op->plan->max_block);
+    HX_CHECK(X != Y, HX_ERR_INVALID, "X and Y must not alias");
+    return op->kind == HX_OP_CELL ? cellop_apply(op, X, Y, B, ugx, ugy) : diagop_apply(op, X, Y, B, ugx, ugy);
+  }
+
+  __global__ void
+  copy_cols_kernel(const double *src, uint32_t ldsrc, uint32_t c0s, double *dst, uint32_t lddst, uint32_t c0d,
+                   uint32_t ncols, size_t nrows)
+  {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nrows * ncols)
+      return;
+    const size_t r = i / ncols;
+    const uint32_t c = (uint32_t)(i % ncols);
+    dst[r * lddst + c0d + c] = src[r * ldsrc + c0s + c];
+  }
+  static int
+  copy_cols(hx_plan *p, const double *src, uint32_t ldsrc, uint32_t c0s, double *dst, uint32_t lddst, uint32_t c0d,
+            uint32_t ncols, size_t nrows)
+  {
+    const size_t tot = nrows * ncols;
+    if (!tot)
+      return HX_OK;
+    copy_cols_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, p->stream>>>(src, ldsrc, c0s, dst, lddst, c0d, ncols, nrows);
+    p->launches++;
+    HX_CUDA(cudaGetLastError());
+    return HX_OK;
+  }
+} // namespace hx
+
+using namespace hx;
+
+hx_plan::~hx_plan()
+{
+  for (auto *s : scratch)
+    delete s;
+  if (h_pinned)
+    cudaFreeHost(h_pinned);
+  if (ev0)
+    cudaEventDestroy(ev0);
+  if (ev1)
+    cudaEventDestroy(ev1);
+  for (auto e : ev_pool)
+    cudaEventDestroy(e);
+  if (comm)
+    comm_destroy(comm);
+  if (own_stream && stream)
+    cudaStreamDestroy(stream);
+}
+
+int
+hx_plan::get_scratch(size_t idx, double **out)
+{
+  while (scratch.size() <= idx)
+    scratch.push_back(new DevBuf<double>());
+  const size_t need = (size_t)n_local * max_block;
+  if (scratch[idx]->n < need)
+    HX_TRY(scratch[idx]->alloc(need));
+  *out = scratch[idx]->p;
+  return HX_OK;
+}
+int
+hx_plan::ensure_small(size_t doubles)
+{
+  if (d_small.n < doubles)
+    HX_TRY(d_small.alloc(doubles));
+  return HX_OK;
+}
+int
+hx_plan::ensure_pinned(size_t bytes)
+{
+  if (h_pinned_bytes < bytes)
+    {
+      if (h_pinned)
+        cudaFreeHost(h_pinned);
+      h_pinned       = nullptr;
+      h_pinned_bytes = 0;
+      HX_CUDA(cudaMallocHost((void **)&h_pinned, bytes));
+      h_pinned_bytes = bytes;
+    }
+  return HX_OK;
+}
+
+extern "C"
+{
+  const char *
+  hx_last_error(void)
+  {
+    return g_err;
+  }
+  int
+  hx_version(void)
+  {
+    return 100;
+  }
+
+  int
+  hx_device_count(int *n)
+  {
+    HX_CUDA(cudaGetDeviceCount(n));
+    return HX_OK;
+  }
+  int
+  hx_set_device(int d)
+  {
+    HX_CUDA(cudaSetDevice(d));
+    return HX_OK;
+  }
+  int
+  hx_device_alloc(void **ptr, size_t bytes)
+  {
+    HX_CUDA(cudaMalloc(ptr, bytes ? bytes : 8));
+    return HX_OK;
+  }
+  int
+  hx_device_free(void *ptr)
+  {
+    HX_CUDA(cudaFree(ptr));
+    return HX_OK;
+  }
+  int
+  hx_host_alloc_pinned(void **ptr, size_t bytes)
+  {
+    HX_CUDA(cudaMallocHost(ptr, bytes ? bytes : 8));
+    return HX_OK;
+  }
+  int
+  hx_host_free_pinned(void *ptr)
+  {
+    HX_CUDA(cudaFreeHost(ptr));
+    return HX_OK;
+  }
+  int
+  hx_memcpy_h2d(void *d, const void *s, size_t bytes)
+  {
+    HX_CUDA(cudaMemcpy(d, s, bytes, cudaMemcpyHostToDevice));
+    return HX_OK;
+  }
+  int
+  hx_memcpy_d2h(void *d, const void *s, size_t bytes)
+  {
+    HX_CUDA(cudaMemcpy(d, s, bytes, cudaMemcpyDeviceToHost));
+    return HX_OK;
+  }
+  int
+  hx_memset_zero(void *d, size_t bytes)
+  {
+    HX_CUDA(cudaMemset(d, 0, bytes));
+    return HX_OK;
+  }
+
+  int
+  hx_plan_create(hx_plan **plan, const hx_mesh_desc *mesh, void *stream)
+  {
+    HX_CHECK(plan && mesh, HX_ERR_INVALID, "null argument");
+    HX_CHECK(mesh->struct_size == sizeof(hx_mesh_desc), HX_ERR_INVALID, "hx_mesh_desc size mismatch (%u vs %zu)",
+             mesh->struct_size, sizeof(hx_mesh_desc));
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+      {
+        set_error("no CUDA device available: libhxb200 has no CPU fallback");
+        return HX_ERR_CUDA;
+      }
+    hx_plan *p = new (std::nothrow) hx_plan();
+    HX_CHECK(p, HX_ERR_NOMEM, "out of host memory");
+    if (stream)
+      p->stream = (cudaStream_t)stream;
+    else
+      {
+        cudaError_t e = cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess)
+          {
+            set_error("cudaStreamCreate: %s", cudaGetErrorString(e));
+            delete p;
+            return HX_ERR_CUDA;
+          }
+        p->own_stream = true;
+      }
+    int r = build_plan(p, mesh);
+    if (r != HX_OK)
+      {
+        delete p;
+        return r;
+      }
+    *plan = p;
+    return HX_OK;
+  }
+
+  int
+  hx_plan_destroy(hx_plan *plan)
+  {
+    if (plan)
+      {
+        cudaStreamSynchronize(plan->stream);
+        delete plan;
+      }
+    return HX_OK;
+  }
+
+  int
+  hx_plan_synchronize(hx_plan *plan)
+  {
+    HX_CHECK(plan, HX_ERR_INVALID, "null plan");
+    HX_CUDA(cudaStreamSynchronize(plan->stream));
+    return HX_OK;
+  }
+
+  int
+  hx_comm_unique_id(char id[128])
+  {
+    return comm_unique_id(id);
+  }
+  int
+  hx_plan_attach_comm(hx_plan *plan, const char id[128])
+  {
+    HX_CHECK(plan, HX_ERR_INVALID, "null plan");
+    if (plan->comm)
+      {
+        comm_destroy(plan->comm);
+        plan->comm = nullptr;
+      }
+    return comm_create(&plan->comm, id, plan->nranks, plan->rank);
+  }
+
+  int
+  hx_plan_num_colours(hx_plan *plan, uint32_t *n)
+  {
+    HX_CHECK(plan && n, HX_ERR_INVALID, "null argument");
+    *n = plan->n_colours;
+    return HX_OK;
+  }
+  int
+  hx_plan_get_cell_colours(hx_plan *plan, uint32_t *colour)
+  {
+    HX_CHECK(plan && colour, HX_ERR_INVALID, "null argument");
+    memcpy(colour, plan->h_colour.data(), sizeof(uint32_t) * plan->C);
+    return HX_OK;
+  }
+  int
+  hx_plan_get_c2p_transpose(hx_plan *plan, uint32_t *n_parents, uint32_t *parent_ids, uint32_t *offsets,
+                            uint32_t *child_rows, double *weights)
+  {
+    HX_CHECK(plan && n_parents, HX_ERR_INVALID, "null argument");
+    *n_parents = plan->nPar;
+    if (parent_ids)
+      memcpy(parent_ids, plan->h_par_ids.data(), sizeof(uint32_t) * plan->nPar);
+    if (offsets)
+      memcpy(offsets, plan->h_par_off.data(), sizeof(uint32_t) * (plan->nPar + 1));
+    if (child_rows)
+      memcpy(child_rows, plan->h_par_child.data(), sizeof(uint32_t) * plan->h_par_child.size());
+    if (weights)
+      memcpy(weights, plan->h_par_w.data(), sizeof(double) * plan->h_par_w.size());
+    return HX_OK;
+  }
+
+#define HX_CHECK_B(plan, B)                                                                        \
+  HX_CHECK((plan) != nullptr, HX_ERR_INVALID, "null plan");                                        \
+  HX_CHECK((B) >= 1 && (B) <= (plan)->max_block, HX_ERR_INVALID, "B = %u outside [1, max_block = %u]", (B), \
+           (plan)->max_block)
+
+  int
+  hx_update_ghost_values(hx_plan *plan, double *X, uint32_t B)
+  {
+    HX_CHECK_B(plan, B);
+    return halo_update(plan, plan->halo, X, B);
+  }
+  int
+  hx_accumulate_add_locally_owned(hx_plan *plan, double *Y, uint32_t B)
+  {
+    HX_CHECK_B(plan, B);
+    return halo_accumulate(plan, plan->halo, Y, B);
+  }
+  int
+  hx_distribute_parent_to_child(hx_plan *plan, double *X, uint32_t B)
+  {
+    HX_CHECK_B(plan, B);
+    return launch_p2c(plan, X, B);
+  }
+  int
+  hx_distribute_child_to_parent(hx_plan *plan, double *Y, uint32_t B)
+  {
+    HX_CHECK_B(plan, B);
+    return launch_c2p(plan, Y, B);
+  }
+  int
+  hx_set_constrained_nodes_to_zero(hx_plan *plan, double *Y, uint32_t B)
+  {
+    HX_CHECK_B(plan, B);
+    return launch_zero_constrained(plan, Y, B);
+  }
+
+  int
+  hx_cellop_create(hx_plan *plan, hx_op **op)
+  {
+    HX_CHECK(plan && op, HX_ERR_INVALID, "null argument");
+    hx_op *o = new (std::nothrow) hx_op();
+    HX_CHECK(o, HX_ERR_NOMEM, "out of host memory");
+    o->plan = plan;
+    o->kind = HX_OP_CELL;
+    *op     = o;
+    return HX_OK;
+  }
+
+  int
+  hx_cellop_set_nonlocal(hx_op *op, const hx_nonlocal_desc *nl)
+  {
+    HX_CHECK(op && nl && op->kind == HX_OP_CELL, HX_ERR_INVALID, "bad argument");
+    HX_CHECK(nl->struct_size == sizeof(hx_nonlocal_desc), HX_ERR_INVALID, "hx_nonlocal_desc size mismatch");
+    hx_plan *p       = op->plan;
+    op->have_matrices = false; // the packed layout carries the projector columns: matrices must be (re)set
+    op->h_ncp.assign(nl->num_cell_proj, nl->num_cell_proj + p->C);
+    op->sum_proj = 0;
+    op->h_c_off.assign(p->C + 1, 0);
+    op->h_nl_cells.clear();
+    std::vector<unsigned long long> coff(p->C + 1, 0);
+    for (uint32_t c = 0; c < p->C; ++c)
+      {
+        op->sum_proj += op->h_ncp[c];
+        coff[c + 1] = coff[c] + (unsigned long long)op->h_ncp[c] * p->h_ncd[c];
+        if (op->h_ncp[c])
+          op->h_nl_cells.push_back(c);
+      }
+    op->n_proj_local = nl->proj_halo.n_owned + nl->proj_halo.n_ghost;
+    op->h_pids.assign(nl->cell_proj_local_ids, nl->cell_proj_local_ids + op->sum_proj);
+    for (uint32_t i = 0; i < op->sum_proj; ++i)
+      HX_CHECK(op->h_pids[i] < op->n_proj_local, HX_ERR_INVALID, "projector id out of range");
+    HX_TRY(op->d_pids.upload(op->h_pids));
+    HX_TRY(op->d_nl_cells.upload(op->h_nl_cells));
+    HX_TRY(op->d_cell_c.upload(nl->cell_c, (size_t)coff[p->C]));
+    HX_TRY(op->d_c_off.upload(coff.data(), coff.size()));
+    HX_TRY(op->d_v.upload(nl->v, op->n_proj_local));
+    HX_TRY(op->d_cx.alloc((size_t)std::max(op->n_proj_local, 1u) * p->max_block));
+    HX_TRY(op->d_cx_stage.alloc((size_t)std::max(op->sum_proj, 1u) * p->max_block));
+    HX_CUDA(cudaMemset(op->d_cx.p, 0, op->d_cx.n * sizeof(double)));
+    // projector row -> staging slots (slot = position in cell_proj_local_ids, i.e. ascending cell order)
+    std::vector<uint32_t> cnt(op->n_proj_local + 1, 0), slots(op->sum_proj);
+    for (uint32_t i = 0; i < op->sum_proj; ++i)
+      cnt[op->h_pids[i] + 1]++;
+    for (uint32_t r = 0; r < op->n_proj_local; ++r)
+      cnt[r + 1] += cnt[r];
+    {
+      std::vector<uint32_t> fill(cnt.begin(), cnt.end() - 1);
+      for (uint32_t i = 0; i < op->sum_proj; ++i)
+        slots[fill[op->h_pids[i]]++] = i;
+    }
+    HX_TRY(op->d_pr_off.upload(cnt));
+    HX_TRY(op->d_pr_slots.upload(slots));
+    HX_TRY(op->phalo.init(nl->proj_halo, p->max_block));
+    op->has_nl = true;
+    return HX_OK;
+  }
+
+  int
+  hx_cellop_set_matrices(hx_op *op, const double *cell_matrices, int on_device)
+  {
+    HX_CHECK(op && cell_matrices && op->kind == HX_OP_CELL, HX_ERR_INVALID, "bad argument");
+    return pack_cell_matrices(op, cell_matrices, on_device);
+  }
+
+  int
+  hx_diagop_create(hx_plan *plan, const double *diag, const double *enr_block, int variant, hx_op **op)
+  {
+    HX_CHECK(plan && diag && op, HX_ERR_INVALID, "null argument");
+    HX_CHECK(variant >= HX_DIAG_CFE && variant <= HX_DIAG_OEFE_MASS, HX_ERR_INVALID, "bad variant");
+    hx_op *o = new (std::nothrow) hx_op();
+    HX_CHECK(o, HX_ERR_NOMEM, "out of host memory");
+    o->plan    = plan;
+    o->kind    = HX_OP_DIAG;
+    o->variant = variant;
+    o->nE      = plan->n_owned - plan->n_owned_classical;
+    int r      = o->d_diag.upload(diag, plan->n_local);
+    if (r == HX_OK && variant != HX_DIAG_CFE && o->nE)
+      {
+        if (!enr_block)
+          {
+            set_error("enrichment block required for %u owned enrichment rows", o->nE);
+            r = HX_ERR_INVALID;
+          }
+        else
+          r = o->d_enr_block.upload(enr_block, (size_t)o->nE * o->nE);
+      }
+    if (r != HX_OK)
+      {
+        delete o;
+        return r;
+      }
+    *op = o;
+    return HX_OK;
+  }
+
+  int
+  hx_op_destroy(hx_op *op)
+  {
+    if (op)
+      {
+        cudaStreamSynchronize(op->plan->stream);
+        delete op;
+      }
+    return HX_OK;
+  }
+
+  int
+  hx_op_apply(hx_op *op, double *X, double *Y, uint32_t B, int ugx, int ugy)
+  {
+    return op_apply(op, X, Y, B, ugx, ugy);
+  }
+
+  int
+  hx_op_apply_host(hx_op *op, double *Xh, double *Yh, uint32_t B, int ugx, int ugy)
+  {
+    HX_CHECK(op && Xh && Yh, HX_ERR_INVALID, "null argument");
+    hx_plan *p = op->plan;
+    HX_CHECK_B(p, B);
+    double *dX, *dY;
+    HX_TRY(p->get_scratch(4, &dX));
+    HX_TRY(p->get_scratch(5, &dY));
+    const size_t bytes = (size_t)p->n_local * B * sizeof(double);
+    HX_CUDA(cudaMemcpyAsync(dX, Xh, bytes, cudaMemcpyHostToDevice, p->stream));
+    HX_TRY(op_apply(op, dX, dY, B, ugx, ugy));
+    HX_CUDA(cudaMemcpyAsync(Yh, dY, bytes, cudaMemcpyDeviceToHost, p->stream));
+    if (p->nR || ugx)
+      HX_CUDA(cudaMemcpyAsync(Xh, dX, bytes, cudaMemcpyDeviceToHost, p->stream));
+    HX_CUDA(cudaStreamSynchronize(p->stream));
+    return HX_OK;
+  }
+
+  // ------------------------------------------------------------------------------- filters ----
+  int
+  hx_chebyshev_filter(hx_op *A, hx_op *BInv, double *X, double *Y, uint32_t B, uint32_t degree, double a0, double a,
+                      double b)
+  {
+    HX_CHECK(A && BInv && X && Y, HX_ERR_INVALID, "null argument");
+    HX_CHECK(A->plan == BInv->plan, HX_ERR_INVALID, "operators belong to different plans");
+    HX_CHECK(degree >= 1, HX_ERR_INVALID, "polynomial degree must be >= 1");
+    hx_plan *p = A->plan;
+    HX_CHECK_B(p, B);
+    // ChebyshevFilter.t.cpp:62-70
+    const double e      = 0.5 * (b - a);
+    const double c      = 0.5 * (b + a);
+    double       sigma  = e / (a0 - c);
+    const double sigma1 = sigma;
+    const double gamma  = 2.0 / sigma1;
+    const size_t nown   = (size_t)p->n_owned * B;
+    const bool   fused  = BInv->kind == HX_OP_DIAG && (BInv->variant == HX_DIAG_CFE || p->nranks == 1);
+    double *     s1, *s2 = nullptr;
+    HX_TRY(p->get_scratch(0, &s1));
+    if (!fused)
+      HX_TRY(p->get_scratch(1, &s2));
+    double *cur = X, *oth = Y; // cur = "eigenSubspaceGuess", oth = "filteredSubspace"
+    HX_TRY(op_apply(A, cur, s1, B, 1, 0));
+    if (fused)
+      {
+        HX_TRY(launch_p2c(p, s1, B));
+        HX_TRY(launch_cheb_fused(p, BInv, s1, cur, nullptr, oth, B, sigma1 / e, -sigma1 / e * c, 0.0));
+      }
+    else
+      {
+        HX_TRY(op_apply(BInv, s1, s2, B, 0, 0));
+        HX_TRY(launch_axpby(p, nown, sigma1 / e, s2, -sigma1 / e * c, cur, oth));
+      }
+    for (uint32_t deg = 2; deg <= degree; ++deg)
+      {
+        const double sigma2 = 1.0 / (gamma - sigma);
+        HX_TRY(op_apply(A, oth, s1, B, 1, 0));
+        if (fused)
+          {
+            HX_TRY(launch_p2c(p, s1, B));
+            HX_TRY(launch_cheb_fused(p, BInv, s1, oth, cur, cur, B, 2.0 * sigma2 / e, -2.0 * sigma2 / e * c,
+                                     -sigma * sigma2));
+          }
+        else
+          {
+            HX_TRY(op_apply(BInv, s1, s2, B, 0, 0));
+            HX_TRY(launch_axpby(p, nown, 2.0 * sigma2 / e, s2, -2.0 * sigma2 / e * c, oth, s1));
+            HX_TRY(launch_axpby(p, nown, 1.0, s1, -sigma * sigma2, cur, cur));
+          }
+        std::swap(cur, oth);
+        sigma = sigma2;
+      }
+    // result is in `oth`; the reference ends with eigenSubspaceGuess = filteredSubspace: both hold it
+    HX_CUDA(cudaMemcpyAsync(cur, oth, (size_t)p->n_local * B * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
+    return HX_OK;
+  }
+
+  int
+  hx_residual_chebyshev_filter(hx_op *A, hx_op *Bop, hx_op *BInv, const double *eigenvalues, double *X, double *Y,
+                               uint32_t B, uint32_t degree, double a0, double a, double b)
+  {
+    HX_CHECK(A && Bop && BInv && eigenvalues && X && Y, HX_ERR_INVALID, "null argument");
+    hx_plan *p = A->plan;
+    HX_CHECK(p == Bop->plan && p == BInv->plan, HX_ERR_INVALID, "operators belong to different plans");
+    HX_CHECK_B(p, B);
+    const double e      = 0.5 * (b - a);
+    const double c      = 0.5 * (b + a);
+    double       sigma  = e / (a0 - c);
+    const double sigma1 = sigma;
+    const double gamma  = 2.0 / sigma1;
+    const size_t nown   = (size_t)p->n_owned * B;
+    const size_t nloc   = (size_t)p->n_local * B;
+    double *     s1, *s2, *s3, *Res, *ResNew;
+    HX_TRY(p->get_scratch(0, &s1));
+    HX_TRY(p->get_scratch(1, &s2));
+    HX_TRY(p->get_scratch(2, &s3));
+    HX_TRY(p->get_scratch(3, &Res));
+    HX_TRY(p->get_scratch(6, &ResNew));
+    // per-column scalars on the host (the reference keeps them in MemoryStorage and filters them with the
+    // same blas kernels, ChebyshevFilter.t.cpp:286-326,400-423); device copies: ones | ev | ev2
+    std::vector<double> ones(B, 1.0), ev(eigenvalues, eigenvalues + B), ev1(B, 1.0), ev2(ev);
+    HX_TRY(p->ensure_small(3 * (size_t)B));
+    double *d_ones = p->d_small.p, *d_ev = p->d_small.p + B, *d_ev2 = p->d_small.p + 2 * (size_t)B;
+    HX_CUDA(cudaMemcpyAsync(d_ones, ones.data(), B * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    HX_CUDA(cudaMemcpyAsync(d_ev, ev.data(), B * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    HX_CUDA(cudaStreamSynchronize(p->stream));
+    double alpha1 = sigma1 / e, alpha2 = -c;
+    HX_TRY(op_apply(Bop, X, Y, B, 1, 0));
+    HX_TRY(op_apply(A, X, s3, B, 1, 0));
+    HX_TRY(launch_axpby_blocked(p, p->n_owned, B, 1.0, d_ones, s3, -1.0, d_ev, Y, Y)); // Y = AX - lambda BX
+    HX_CUDA(cudaMemcpyAsync(ResNew, Y, nloc * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
+    HX_CUDA(cudaMemsetAsync(Res, 0, nloc * sizeof(double), p->stream));
+    for (uint32_t j = 0; j < B; ++j)
+      ev2[j] = 1.0 * 1.0 * (alpha1 * alpha2) + alpha1 * ev[j] * ev1[j];
+    HX_TRY(launch_axpby(p, nown, alpha1, ResNew, 0.0, ResNew, ResNew)); // ascale
+    for (uint32_t deg = 2; deg <= degree; ++deg)
+      {
+        const double sigma2 = 1.0 / (gamma - sigma);
+        alpha1              = 2.0 * sigma2 / e;
+        alpha2              = -(sigma * sigma2);
+        HX_TRY(op_apply(BInv, ResNew, s1, B, 1, 0));
+        HX_TRY(op_apply(A, s1, s2, B, 0, 0));
+        HX_TRY(launch_axpby(p, nown, alpha1, s2, -c * alpha1, ResNew, s1));
+        HX_TRY(launch_axpby(p, nown, 1.0, s1, alpha2, Res, Res));
+        HX_CUDA(cudaMemcpyAsync(d_ev2, ev2.data(), B * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+        HX_TRY(launch_axpby_blocked(p, p->n_owned, B, 1.0, d_ones, Res, alpha1, d_ev2, Y, Res));
+        HX_CUDA(cudaStreamSynchronize(p->stream)); // ev2 (host) is rewritten below
+        for (uint32_t j = 0; j < B; ++j)
+          {
+            ev1[j] = (-c * alpha1) * ev2[j] + alpha2 * ev1[j];
+            ev1[j] = 1.0 * 1.0 * ev1[j] + alpha1 * ev[j] * ev2[j];
+          }
+        std::swap(ResNew, Res);
+        std::swap(ev1, ev2);
+        sigma = sigma2;
+      }
+    HX_TRY(op_apply(BInv, ResNew, Res, B, 1, 1));
+    HX_CUDA(cudaMemcpyAsync(d_ev2, ev2.data(), B * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    HX_TRY(launch_axpby_blocked(p, p->n_owned, B, 1.0, d_ones, Res, 1.0, d_ev2, X, Y));
+    HX_CUDA(cudaStreamSynchronize(p->stream));
+    return HX_OK;
+  }
+
+  // --------------------------------------------------------------------- subspace projections ----
+  int
+  hx_xtopx(hx_op *op, double *X, uint32_t B, uint32_t batch, double *S_host)
+  {
+    HX_CHECK(op && X && S_host, HX_ERR_INVALID, "null argument");
+    hx_plan *p = op->plan;
+    HX_CHECK_B(p, B);
+    HX_CHECK(batch >= 1, HX_ERR_INVALID, "batch must be >= 1");
+    batch = std::min(batch, B);
+    double *xin, *xout;
+    HX_TRY(p->get_scratch(2, &xin));
+    HX_TRY(p->get_scratch(3, &xout));
+    HX_TRY(p->ensure_small((size_t)B * batch * 3 + (size_t)604 * 4096));
+    HX_TRY(p->ensure_pinned((size_t)B * batch * sizeof(double)));
+    for (size_t i = 0; i < (size_t)B * B; ++i)
+      S_host[i] = 0.0;
+    for (uint32_t j0 = 0; j0 < B; j0 += batch)
+      {
+        const uint32_t b = std::min(batch, B - j0);
+        HX_TRY(copy_cols(p, X, B, j0, xin, b, 0, b, p->n_local));
+        HX_TRY(op_apply(op, xin, xout, b, 1, 0));
+        double *Sd = p->d_small.p;
+        HX_TRY(gram_block(p, X, B, j0, xout, b, p->n_owned, Sd));
+        if (p->nranks > 1)
+          HX_TRY(comm_allreduce_sum(p->comm, p->stream, Sd, (size_t)(B - j0) * b));
+        HX_CUDA(cudaMemcpyAsync(p->h_pinned, Sd, (size_t)(B - j0) * b * sizeof(double), cudaMemcpyDeviceToHost,
+                                p->stream));
+        // the reference copies the (possibly constraint-filled) batch back into X
+        HX_TRY(copy_cols(p, xin, b, 0, X, B, j0, b, p->n_local));
+        HX_CUDA(cudaStreamSynchronize(p->stream));
+        for (uint32_t i = 0; i < b; ++i)
+          for (uint32_t j = j0 + i; j < B; ++j)
+            S_host[(size_t)j + (size_t)(i + j0) * B] = p->h_pinned[(size_t)i * (B - j0) + (j - j0)];
+      }
+    return HX_OK;
+  }
+
+  int
+  hx_subspace_rotation(hx_plan *plan, double *X, uint32_t B, const double *Q_host, int transpose, int lowerTri)
+  {
+    HX_CHECK(plan && X && Q_host, HX_ERR_INVALID, "null argument");
+    HX_CHECK_B(plan, B);
+    // effective K x N operand, row-major: Qeff[i*B + j] = Q(i,j) (transpose) or Q(j,i); lower-triangular
+    // rotation matrices only couple i <= j-block end, the zeros are kept explicit
+    std::vector<double> qeff((size_t)B * B);
+    for (uint32_t i = 0; i < B; ++i)
+      for (uint32_t j = 0; j < B; ++j)
+        qeff[(size_t)i * B + j] = transpose ? Q_host[(size_t)i + (size_t)j * B] : Q_host[(size_t)j + (size_t)i * B];
+    HX_TRY(plan->ensure_small((size_t)B * B));
+    HX_CUDA(cudaMemcpyAsync(plan->d_small.p, qeff.data(), qeff.size() * sizeof(double), cudaMemcpyHostToDevice,
+                            plan->stream));
+    HX_CUDA(cudaStreamSynchronize(plan->stream));
+    double *tmp;
+    HX_TRY(plan->get_scratch(2, &tmp));
+    return rotate(plan, X, B, plan->n_owned, plan->d_small.p, transpose, lowerTri, tmp);
+  }
+
+  int
+  hx_l2_norms(hx_plan *plan, const double *X, uint32_t B, double *norms_host)
+  {
+    HX_CHECK(plan && X && norms_host, HX_ERR_INVALID, "null argument");
+    HX_CHECK_B(plan, B);
+    HX_CHECK(B <= 256, HX_ERR_UNSUPPORTED, "hx_l2_norms supports B <= 256 per call (batch the columns)");
+    HX_TRY(plan->ensure_small((size_t)600 * B + 2 * B));
+    double *out = plan->d_small.p + (size_t)600 * B;
+    HX_TRY(launch_colsumsq(plan, X, B, plan->n_owned, out));
+    if (plan->nranks > 1)
+      HX_TRY(comm_allreduce_sum(plan->comm, plan->stream, out, B));
+    HX_CUDA(cudaMemcpyAsync(norms_host, out, B * sizeof(double), cudaMemcpyDeviceToHost, plan->stream));
+    HX_CUDA(cudaStreamSynchronize(plan->stream));
+    for (uint32_t j = 0; j < B; ++j)
+      norms_host[j] = sqrt(norms_host[j]);
+    return HX_OK;
+  }
+
+  int
+  hx_axpby(hx_plan *plan, uint32_t n_rows, uint32_t B, double alpha, const double *x, double beta, const double *y,
+           double *z)
+  {
+    HX_CHECK(plan && x && y && z, HX_ERR_INVALID, "null argument");
+    return launch_axpby(plan, (size_t)n_rows * B, alpha, x, beta, y, z);
+  }
+  int
+  hx_axpby_blocked(hx_plan *plan, uint32_t n_rows, uint32_t B, double alpha1, const double *alpha_host,
+                   const double *x, double beta1, const double *beta_host, const double *y, double *z)
+  {
+    HX_CHECK(plan && x && y && z && alpha_host && beta_host, HX_ERR_INVALID, "null argument");
+    HX_TRY(plan->ensure_small(2 * (size_t)B));
+    HX_CUDA(cudaMemcpyAsync(plan->d_small.p, alpha_host, B * sizeof(double), cudaMemcpyHostToDevice, plan->stream));
+    HX_CUDA(cudaMemcpyAsync(plan->d_small.p + B, beta_host, B * sizeof(double), cudaMemcpyHostToDevice, plan->stream));
+    HX_CUDA(cudaStreamSynchronize(plan->stream));
+    return launch_axpby_blocked(plan, n_rows, B, alpha1, plan->d_small.p, x, beta1, plan->d_small.p + B, y, z);
+  }
+
+  int
+  hx_plan_launch_count(hx_plan *plan, uint64_t *n)
+  {
+    HX_CHECK(plan && n, HX_ERR_INVALID, "null argument");
+    *n = plan->launches;
+    return HX_OK;
+  }
+  int
+  hx_plan_enable_kernel_timing(hx_plan *plan, int on)
+  {
+    HX_CHECK(plan, HX_ERR_INVALID, "null plan");
+    plan->timing        = on != 0;
+    plan->ev_used       = 0;
+    plan->cell_launches = 0;
+    return HX_OK;
+  }
+  int
+  hx_plan_cell_kernel_time_ms(hx_plan *plan, double *ms, uint64_t *launches)
+  {
+    HX_CHECK(plan && ms && launches, HX_ERR_INVALID, "null argument");
+    HX_CUDA(cudaStreamSynchronize(plan->stream));
+    double tot = 0.0;
+    for (size_t i = 0; i + 1 < plan->ev_used; i += 2)
+      {
+        float t = 0.f;
+        HX_CUDA(cudaEventElapsedTime(&t, plan->ev_pool[i], plan->ev_pool[i + 1]));
+        tot += t;
+      }
+    plan->ev_used       = 0;
+    *ms                 = tot;
+    *launches           = plan->cell_launches;
+    plan->cell_launches = 0;
+    return HX_OK;
+  }
+}

@@ -1,0 +1,331 @@
+// gram.cu — the subspace projections as FP64 tensor-core (DMMA) GEMMs.
+//
+//  gram_block : S[(B-j0) x b] = X[:, j0:]^T . OpX_batch   over the owned rows
+//               (blasLapack::gemm('N','C', B-j0, b, nOwned, X+j0, B, OpXb, b) of
+//                src/linearAlgebra/RayleighRitzEigenSolver.t.cpp:782-796), split-K over DoF slabs with a
+//               fixed-order second-stage reduction (deterministic), tiles strictly above the diagonal skipped
+//               (the reference keeps the lower trapezoid only, :819-836).
+//  rotate     : X[dof,:] <- X[dof,:] . Qeff   (subspaceRotation, src/linearAlgebra/ElpaScalapackOperations.t.cpp:303-330)
+//
+// Both stage 64-wide operand tiles in shared memory with cp.async (16-B, double-buffered) and feed
+// mma.sync.m8n8k4.f64 from conflict-free padded rows.
+#include "hx_internal.h"
+
+namespace hx
+{
+  __device__ __forceinline__ void
+  dmma884g(double &d0, double &d1, const double a, const double b)
+  {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+        : "+d"(d0), "+d"(d1)
+        : "d"(a), "d"(b));
+  }
+  __device__ __forceinline__ void
+  cp_async16(void *smem, const void *gmem)
+  {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem));
+  }
+  __device__ __forceinline__ void
+  cp_async_commit()
+  {
+    asm volatile("cp.async.commit_group;");
+  }
+  template <int N>
+  __device__ __forceinline__ void
+  cp_async_wait()
+  {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N));
+  }
+
+  constexpr int GT  = 64; // tile edge (outputs)
+  constexpr int GKC = 16; // k rows per stage
+  constexpr int GLD = GT + 4;
+
+  // load a [GKC x 64] tile of a row-major matrix (row stride ld, columns c0.., rows r0..) into smem[GKC][GLD];
+  // out-of-range rows/columns are zero-filled.
+  __device__ __forceinline__ void
+  load_tile_rows(double *sm, const double *g, size_t ld, size_t r0, size_t rend, uint32_t c0, uint32_t cend,
+                 bool aligned, int tid)
+  {
+    // 16 rows x 32 double2 chunks = 512 chunks, 256 threads -> 2 each
+#pragma unroll
+    for (int it = 0; it < 2; ++it)
+      {
+        const int      ch = tid + it * 256;
+        const int      r  = ch >> 5;
+        const int      cc = (ch & 31) * 2;
+        double *       d  = sm + r * GLD + cc;
+        const size_t   gr = r0 + r;
+        const uint32_t gc = c0 + cc;
+        if (gr < rend && gc + 1 < cend && aligned)
+          cp_async16(d, g + gr * ld + gc);
+        else
+          {
+            d[0] = (gr < rend && gc < cend) ? g[gr * ld + gc] : 0.0;
+            d[1] = (gr < rend && gc + 1 < cend) ? g[gr * ld + gc + 1] : 0.0;
+          }
+      }
+  }
+
+  // grid: (tiles, nSplit).  W: [nSplit][M*N] col-major partials.
+  __global__ void __launch_bounds__(256)
+  gram_kernel(const double *X, uint32_t B, uint32_t j0, const double *O, uint32_t b, size_t nOwned, uint32_t M,
+              uint32_t N, uint32_t tilesM, size_t slab, double *W, int alignedX, int alignedO)
+  {
+    __shared__ __align__(16) double As[2][GKC * GLD];
+    __shared__ __align__(16) double Bs[2][GKC * GLD];
+    const int      tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t tm = blockIdx.x % tilesM, tn = blockIdx.x / tilesM;
+    const uint32_t m0 = tm * GT, n0 = tn * GT;
+    if (m0 + GT <= n0)
+      return; // tile strictly above the diagonal (rows j < cols i): not part of the lower trapezoid
+    const size_t kb = (size_t)blockIdx.y * slab;
+    const size_t ke = kb + slab < nOwned ? kb + slab : nOwned;
+    double       acc[2][4][2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int t = 0; t < 4; ++t)
+        acc[j][t][0] = acc[j][t][1] = 0.0;
+    const int wm = (warp & 3) * 16, wn = (warp >> 2) * 32;
+    if (kb < ke)
+      {
+        const int nchunks = (int)((ke - kb + GKC - 1) / GKC);
+        load_tile_rows(As[0], X, B, kb, ke, j0 + m0, j0 + M, alignedX, tid);
+        load_tile_rows(Bs[0], O, b, kb, ke, n0, N, alignedO, tid);
+        cp_async_commit();
+        for (int c = 0; c < nchunks; ++c)
+          {
+            const int cur = c & 1;
+            if (c + 1 < nchunks)
+              {
+                load_tile_rows(As[cur ^ 1], X, B, kb + (size_t)(c + 1) * GKC, ke, j0 + m0, j0 + M, alignedX, tid);
+                load_tile_rows(Bs[cur ^ 1], O, b, kb + (size_t)(c + 1) * GKC, ke, n0, N, alignedO, tid);
+                cp_async_commit();
+                cp_async_wait<1>();
+              }
+            else
+              cp_async_wait<0>();
+            __syncthreads();
+            const double *as = As[cur] + (lane & 3) * GLD + wm + (lane >> 2);
+            const double *bs = Bs[cur] + (lane & 3) * GLD + wn + (lane >> 2);
+#pragma unroll
+            for (int k4 = 0; k4 < GKC / 4; ++k4)
+              {
+                double a[2], bb[4];
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+                  a[j] = as[k4 * 4 * GLD + j * 8];
+#pragma unroll
+                for (int t = 0; t < 4; ++t)
+                  bb[t] = bs[k4 * 4 * GLD + t * 8];
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+#pragma unroll
+                  for (int t = 0; t < 4; ++t)
+                    dmma884g(acc[j][t][0], acc[j][t][1], a[j], bb[t]);
+              }
+            __syncthreads();
+          }
+      }
+    double *w = W + (size_t)blockIdx.y * M * N;
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int t = 0; t < 4; ++t)
+        {
+          const uint32_t r = m0 + wm + j * 8 + (lane >> 2);
+          const uint32_t c = n0 + wn + t * 8 + (lane & 3) * 2;
+          if (r < M)
+            {
+              if (c < N)
+                w[(size_t)r + (size_t)c * M] = acc[j][t][0];
+              if (c + 1 < N)
+                w[(size_t)r + (size_t)(c + 1) * M] = acc[j][t][1];
+            }
+        }
+  }
+
+  __global__ void
+  gram_reduce_kernel(const double *W, uint32_t M, uint32_t N, uint32_t nSplit, double *S)
+  {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)M * N)
+      return;
+    const uint32_t r = (uint32_t)(i % M), c = (uint32_t)(i / M);
+    // tiles strictly above the diagonal were skipped
+    if ((r / GT) * GT + GT <= (c / GT) * GT)
+      {
+        S[i] = 0.0;
+        return;
+      }
+    double s = 0.0;
+    for (uint32_t k = 0; k < nSplit; ++k)
+      s += W[(size_t)k * M * N + i];
+    S[i] = s;
+  }
+
+  int
+  gram_block(hx_plan *p, const double *X, uint32_t B, uint32_t j0, const double *OpXb, uint32_t b, size_t nOwned,
+             double *S_dev)
+  {
+    const uint32_t M = B - j0, N = b;
+    const uint32_t tilesM = (M + GT - 1) / GT, tilesN = (N + GT - 1) / GT;
+    const uint32_t tiles  = tilesM * tilesN;
+    uint32_t       nSplit = (592 + tiles - 1) / tiles;
+    const uint32_t maxSplit = (uint32_t)std::max<size_t>(1, (nOwned + 255) / 256);
+    nSplit                  = std::max(1u, std::min(nSplit, maxSplit));
+    size_t slab             = (nOwned + nSplit - 1) / nSplit;
+    slab                    = (slab + GKC - 1) / GKC * GKC;
+    if (slab == 0)
+      slab = GKC;
+    nSplit = (uint32_t)std::max<size_t>(1, (nOwned + slab - 1) / slab);
+    // workspace lives behind S in the same small buffer (caller sized it: see hx_xtopx)
+    double *W = S_dev + (size_t)M * N;
+    HX_CHECK(p->d_small.p && S_dev >= p->d_small.p &&
+               (size_t)(S_dev - p->d_small.p) + (size_t)M * N * (1 + (size_t)nSplit) <= p->d_small.n,
+             HX_ERR_INVALID, "gram workspace too small");
+    const int alignedX = (B % 2 == 0) && (j0 % 2 == 0) && (((uintptr_t)X & 15) == 0);
+    const int alignedO = (b % 2 == 0) && (((uintptr_t)OpXb & 15) == 0);
+    dim3      grid(tiles, nSplit);
+    gram_kernel<<<grid, 256, 0, p->stream>>>(X, B, j0, OpXb, b, nOwned, M, N, tilesM, slab, W, alignedX, alignedO);
+    gram_reduce_kernel<<<(unsigned)(((size_t)M * N + 255) / 256), 256, 0, p->stream>>>(W, M, N, nSplit, S_dev);
+    p->launches += 2;
+    HX_CUDA(cudaGetLastError());
+    return HX_OK;
+  }
+
+  // upper bound of the split count gram_block will choose (for workspace sizing)
+  uint32_t
+  gram_max_split(uint32_t M, uint32_t N)
+  {
+    const uint32_t tiles = ((M + GT - 1) / GT) * ((N + GT - 1) / GT);
+    return std::max(1u, (592 + tiles - 1) / tiles) + 1;
+  }
+
+  // ---------------------------------------------------------------------------------------------------
+  constexpr int RLDA = GKC + 4;
+  // Out[r, n0..n0+63] = sum_k X[r, k] Q[k, n]   (Q row-major K x N = B x B)
+  __global__ void __launch_bounds__(256)
+  rotate_kernel(const double *X, uint32_t B, size_t nRows, const double *Q, double *Out, int lowerTri, int transpose,
+                int aligned)
+  {
+    __shared__ __align__(16) double As[2][GT * RLDA];
+    __shared__ __align__(16) double Bs[2][GKC * GLD];
+    const int      tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t tilesN = (B + GT - 1) / GT;
+    const uint32_t tn     = blockIdx.x % tilesN;
+    const size_t   tmi    = blockIdx.x / tilesN;
+    const size_t   r0     = tmi * GT;
+    const uint32_t n0     = tn * GT;
+    uint32_t       kbeg = 0, kend = B;
+    if (lowerTri)
+      {
+        if (transpose)
+          kbeg = (n0 / GKC) * GKC; // Qeff[i][j] = Q(i,j) != 0 only for i >= j
+        else
+          kend = (n0 + GT < B) ? n0 + GT : B; // Qeff[i][j] = Q(j,i) != 0 only for i <= j
+      }
+    double acc[2][4][2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int t = 0; t < 4; ++t)
+        acc[j][t][0] = acc[j][t][1] = 0.0;
+    const int wm = (warp & 3) * 16, wn = (warp >> 2) * 32;
+
+    auto load = [&](int buf, uint32_t k0) {
+      // A: 64 rows x 16 k  -> 64*8 double2 chunks = 512 -> 2 per thread
+#pragma unroll
+      for (int it = 0; it < 2; ++it)
+        {
+          const int      ch = tid + it * 256;
+          const int      r  = ch >> 3;
+          const int      kk = (ch & 7) * 2;
+          double *       d  = As[buf] + r * RLDA + kk;
+          const size_t   gr = r0 + r;
+          const uint32_t gk = k0 + kk;
+          if (gr < nRows && gk + 1 < kend && aligned)
+            cp_async16(d, X + gr * B + gk);
+          else
+            {
+              d[0] = (gr < nRows && gk < kend) ? X[gr * B + gk] : 0.0;
+              d[1] = (gr < nRows && gk + 1 < kend) ? X[gr * B + gk + 1] : 0.0;
+            }
+        }
+      load_tile_rows(Bs[buf], Q, B, k0, kend, n0, B, aligned, tid);
+    };
+
+    const int nchunks = (kend > kbeg) ? (int)((kend - kbeg + GKC - 1) / GKC) : 0;
+    if (nchunks)
+      {
+        load(0, kbeg);
+        cp_async_commit();
+      }
+    for (int c = 0; c < nchunks; ++c)
+      {
+        const int cur = c & 1;
+        if (c + 1 < nchunks)
+          {
+            load(cur ^ 1, kbeg + (uint32_t)(c + 1) * GKC);
+            cp_async_commit();
+            cp_async_wait<1>();
+          }
+        else
+          cp_async_wait<0>();
+        __syncthreads();
+        const double *as = As[cur] + (wm + (lane >> 2)) * RLDA + (lane & 3);
+        const double *bs = Bs[cur] + (lane & 3) * GLD + wn + (lane >> 2);
+#pragma unroll
+        for (int k4 = 0; k4 < GKC / 4; ++k4)
+          {
+            double a[2], bb[4];
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+              a[j] = as[j * 8 * RLDA + k4 * 4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+              bb[t] = bs[k4 * 4 * GLD + t * 8];
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+              for (int t = 0; t < 4; ++t)
+                dmma884g(acc[j][t][0], acc[j][t][1], a[j], bb[t]);
+          }
+        __syncthreads();
+      }
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int t = 0; t < 4; ++t)
+        {
+          const size_t   r = r0 + wm + j * 8 + (lane >> 2);
+          const uint32_t c = n0 + wn + t * 8 + (lane & 3) * 2;
+          if (r < nRows)
+            {
+              if (c < B)
+                Out[r * B + c] = acc[j][t][0];
+              if (c + 1 < B)
+                Out[r * B + c + 1] = acc[j][t][1];
+            }
+        }
+  }
+
+  int
+  rotate(hx_plan *p, double *X, uint32_t B, size_t nOwned, const double *Q_dev, int transpose, int lowerTri,
+         double *tmp)
+  {
+    if (nOwned == 0)
+      return HX_OK;
+    const uint32_t tilesN  = (B + GT - 1) / GT;
+    const size_t   tilesM  = (nOwned + GT - 1) / GT;
+    const int      aligned = (B % 2 == 0) && (((uintptr_t)X & 15) == 0) && (((uintptr_t)Q_dev & 15) == 0);
+    rotate_kernel<<<(unsigned)(tilesM * tilesN), 256, 0, p->stream>>>(X, B, nOwned, Q_dev, tmp, lowerTri, transpose,
+                                                                      aligned);
+    p->launches++;
+    HX_CUDA(cudaGetLastError());
+    HX_CUDA(cudaMemcpyAsync(X, tmp, nOwned * B * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
+    return HX_OK;
+  }
+} // namespace hx

@@ -1,0 +1,254 @@
+// hx_internal.h — internal structures of libhxb200 (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/hxb200.h"
+
+namespace hx
+{
+  void set_error(const char *fmt, ...);
+
+#define HX_CUDA(call)                                                                    \
+  do                                                                                     \
+    {                                                                                    \
+      cudaError_t e_ = (call);                                                           \
+      if (e_ != cudaSuccess)                                                             \
+        {                                                                                \
+          hx::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+          return HX_ERR_CUDA;                                                            \
+        }                                                                                \
+    }                                                                                    \
+  while (0)
+
+#define HX_CHECK(cond, code, ...)   \
+  do                                \
+    {                               \
+      if (!(cond))                  \
+        {                           \
+          hx::set_error(__VA_ARGS__); \
+          return (code);            \
+        }                           \
+    }                               \
+  while (0)
+
+#define HX_TRY(call)      \
+  do                      \
+    {                     \
+      int r_ = (call);    \
+      if (r_ != HX_OK)    \
+        return r_;        \
+    }                     \
+  while (0)
+
+  template <typename T>
+  struct DevBuf
+  {
+    T *    p = nullptr;
+    size_t n = 0;
+    DevBuf()               = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &
+    operator=(const DevBuf &) = delete;
+    ~DevBuf() { release(); }
+    void
+    release()
+    {
+      if (p)
+        cudaFree(p);
+      p = nullptr;
+      n = 0;
+    }
+    int
+    alloc(size_t count)
+    {
+      release();
+      n = count;
+      if (count == 0)
+        return HX_OK;
+      cudaError_t e = cudaMalloc((void **)&p, count * sizeof(T));
+      if (e != cudaSuccess)
+        {
+          p = nullptr;
+          n = 0;
+          set_error("cudaMalloc(%zu bytes) failed: %s", count * sizeof(T), cudaGetErrorString(e));
+          return HX_ERR_NOMEM;
+        }
+      return HX_OK;
+    }
+    int
+    upload(const T *h, size_t count)
+    {
+      int r = alloc(count);
+      if (r != HX_OK)
+        return r;
+      if (count)
+        HX_CUDA(cudaMemcpy(p, h, count * sizeof(T), cudaMemcpyHostToDevice));
+      return HX_OK;
+    }
+    int
+    upload(const std::vector<T> &v)
+    {
+      return upload(v.data(), v.size());
+    }
+  };
+
+  // device-side copy of one MPIPatternP2P + the communicator buffers of MPICommunicatorP2P
+  struct Halo
+  {
+    uint32_t              n_owned = 0, n_ghost = 0;
+    std::vector<uint32_t> ghost_procs, ghost_ranges, target_procs, target_counts;
+    uint32_t              n_send = 0; // total owned indices for targets
+    DevBuf<uint32_t>      d_ghost_local_ids, d_owned_ids_for_targets;
+    // accumulate side: unique owned rows receiving halo contributions -> ordered buffer positions
+    uint32_t              n_acc_rows = 0;
+    DevBuf<uint32_t>      d_acc_rows, d_acc_off, d_acc_pos;
+    DevBuf<double>        d_send, d_recv; // sized for max_block
+    int
+    init(const hx_halo_desc &h, uint32_t max_block);
+  };
+
+  struct CellMeta
+  {
+    unsigned long long h_off;    // offset (doubles) of this cell's packed matrix
+    uint32_t           ids_off;  // offset into cell_local_ids / dest
+    uint32_t           n;        // DoFs of the cell
+    uint32_t           nproj;    // projectors of the cell (0 without nonlocal part)
+    uint32_t           proj_off; // offset into cell_proj_local_ids
+  };
+
+  struct Comm; // NCCL communicator wrapper (comm.cu)
+} // namespace hx
+
+struct hx_plan
+{
+  int          rank = 0, nranks = 1;
+  cudaStream_t stream     = nullptr;
+  bool         own_stream = false;
+  uint32_t     n_owned = 0, n_ghost = 0, n_local = 0, n_owned_classical = 0;
+  uint32_t     C = 0, S = 0, max_n = 0, max_block = 0;
+  size_t       S2 = 0;
+
+  std::vector<uint32_t> h_ncd, h_ids, h_cell_off; // h_cell_off[C+1]
+  hx::DevBuf<uint32_t>  d_ids, d_cell_off, d_ncd;
+
+  // constraints (reference CSR) + parent-side transpose for the deterministic child->parent
+  uint32_t              nR = 0, nnz = 0;
+  hx::DevBuf<uint32_t>  d_row_ids, d_row_sizes, d_row_offsets, d_col_ids;
+  hx::DevBuf<double>    d_col_vals, d_inhom;
+  uint32_t              nPar = 0;
+  std::vector<uint32_t> h_par_ids, h_par_off, h_par_child;
+  std::vector<double>   h_par_w;
+  hx::DevBuf<uint32_t>  d_par_ids, d_par_off, d_par_child;
+  hx::DevBuf<double>    d_par_w;
+  hx::DevBuf<uint32_t>  d_rowinfo; // [n_local]: 0xFFFFFFFF free, 0xFFFFFFFE constrained, else parent index
+
+  // colouring of cells over non-shared DoFs; shared (high-incidence, e.g. enrichment) rows go
+  // through a staging buffer + ordered reduction
+  uint32_t              n_colours = 0;
+  std::vector<uint32_t> h_colour, h_colour_off, h_colour_cells;
+  hx::DevBuf<uint32_t>  d_colour_cells;
+  hx::DevBuf<uint32_t>  d_dest; // [S]: local row id, or 0x80000000 | staging slot
+  uint32_t              n_shared = 0, n_slots = 0;
+  hx::DevBuf<uint32_t>  d_sh_rows, d_sh_off, d_sh_slots;
+  hx::DevBuf<double>    d_stage; // n_slots x max_block
+
+  hx::Halo  halo;
+  hx::Comm *comm = nullptr;
+
+  // scratch block vectors (n_local x max_block), allocated on demand
+  std::vector<hx::DevBuf<double> *> scratch;
+  hx::DevBuf<double>                d_small; // small device scratch (norms, gram blocks, per-column scalars)
+  double *                          h_pinned = nullptr;
+  size_t                            h_pinned_bytes = 0;
+
+  uint64_t    launches = 0;
+  bool        timing   = false;
+  double      cell_ms  = 0.0;
+  uint64_t    cell_launches = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::vector<cudaEvent_t> ev_pool; // (start, stop) pairs recorded around the cell-kernel launches
+  size_t                   ev_used = 0;
+
+  ~hx_plan();
+  int
+  get_scratch(size_t idx, double **p); // n_local * max_block doubles
+  int
+  ensure_small(size_t doubles);
+  int
+  ensure_pinned(size_t bytes);
+};
+
+enum hx_op_kind
+{
+  HX_OP_CELL = 1,
+  HX_OP_DIAG = 2
+};
+
+struct hx_op
+{
+  hx_plan *plan = nullptr;
+  int      kind = 0;
+  // --- cell operator ---
+  std::vector<hx::CellMeta> h_meta;
+  hx::DevBuf<hx::CellMeta>  d_meta;
+  hx::DevBuf<double>        d_packed; // fragment-major packed cell matrices (+ projector columns)
+  size_t                    packed_doubles = 0;
+  bool                      have_matrices  = false;
+  uint32_t                  max_kp = 0, max_mp = 0;
+  // nonlocal
+  bool                      has_nl = false;
+  hx::Halo                  phalo;
+  uint32_t                  n_proj_local = 0, sum_proj = 0;
+  std::vector<uint32_t>     h_ncp, h_pids, h_nl_cells; // cells with projectors
+  hx::DevBuf<uint32_t>      d_pids, d_nl_cells;
+  hx::DevBuf<double>        d_cell_c, d_v, d_cx, d_cx_stage;
+  std::vector<size_t>       h_c_off;                   // per cell offset into cell_c
+  hx::DevBuf<unsigned long long> d_c_off;
+  hx::DevBuf<uint32_t>      d_pr_off, d_pr_slots;      // projector row -> staging slots (ordered)
+  // --- diagonal operator ---
+  int                variant = 0;
+  hx::DevBuf<double> d_diag, d_enr_block;
+  uint32_t           nE = 0;
+};
+
+namespace hx
+{
+  // kernels.cu / cell_kernel.cu entry points (host launchers)
+  int launch_p2c(hx_plan *p, double *X, uint32_t B);
+  int launch_c2p(hx_plan *p, double *Y, uint32_t B);
+  int launch_zero_constrained(hx_plan *p, double *Y, uint32_t B);
+  int launch_pack(hx_plan *p, const double *x, uint32_t B, const uint32_t *ids, uint32_t n, double *buf);
+  int launch_unpack(hx_plan *p, const double *buf, uint32_t B, const uint32_t *ids, uint32_t n, double *x);
+  int launch_add_rows(hx_plan *p, const double *buf, uint32_t B, const uint32_t *rows, const uint32_t *off,
+                      const uint32_t *pos, uint32_t nrows, double *x);
+  int launch_row_scale(hx_plan *p, const double *d, const double *x, double *y, uint32_t B, size_t nrows);
+  int launch_axpby(hx_plan *p, size_t n, double a, const double *x, double b, const double *y, double *z);
+  int launch_axpby_blocked(hx_plan *p, size_t nrows, uint32_t B, double a1, const double *a, const double *x,
+                           double b1, const double *b, const double *y, double *z);
+  int launch_colsumsq(hx_plan *p, const double *x, uint32_t B, size_t nrows, double *out_dev);
+  int launch_shared_reduce(hx_plan *p, double *Y, uint32_t B);
+  int launch_enr_block(hx_plan *p, const double *blk, uint32_t nE, const double *Xenr, double *Yenr, uint32_t B);
+  int launch_cell_apply(hx_op *op, const double *X, double *Y, uint32_t B);
+  int launch_nl_phase_a(hx_op *op, const double *X, uint32_t B);
+  int pack_cell_matrices(hx_op *op, const double *raw_dev_or_host, int on_device);
+  int launch_cheb_fused(hx_plan *p, hx_op *binv, const double *s1, const double *xcur, const double *xprev,
+                        double *out, uint32_t B, double a, double b, double c);
+  int gram_block(hx_plan *p, const double *X, uint32_t B, uint32_t j0, const double *OpXb, uint32_t b,
+                 size_t nOwned, double *S_dev);
+  int rotate(hx_plan *p, double *X, uint32_t B, size_t nOwned, const double *Q_dev, int transpose, int lowerTri,
+             double *tmp);
+  // comm.cu
+  int comm_unique_id(char id[128]);
+  int comm_create(Comm **c, const char id[128], int nranks, int rank);
+  void comm_destroy(Comm *c);
+  int comm_exchange(Comm *c, cudaStream_t s, const double *send, const std::vector<uint32_t> &send_procs,
+                    const std::vector<size_t> &send_counts, double *recv, const std::vector<uint32_t> &recv_procs,
+                    const std::vector<size_t> &recv_counts);
+  int comm_allreduce_sum(Comm *c, cudaStream_t s, double *buf, size_t n);
+} // namespace hx

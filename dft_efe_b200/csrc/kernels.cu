@@ -1,0 +1,400 @@
+// kernels.cu — the HBM-bound helpers around the cell contraction: hanging-node constraints, halo
+// pack/unpack/accumulate, row scaling, fused Chebyshev recurrence, column norms, shared-row reduction.
+// All are bandwidth kernels: coalesced row-contiguous accesses (a row of the block vector is B contiguous
+// doubles), 16-B vector accesses when B is even, grids sized from the data.
+#include "hx_internal.h"
+
+namespace hx
+{
+  static inline unsigned
+  nblk(size_t n, unsigned t = 256)
+  {
+    return (unsigned)((n + t - 1) / t);
+  }
+
+  // ---- constraints -------------------------------------------------------------------------------
+  // distributeParentToChild (src/basis/ConstraintsInternal.cpp:35-108): X[r,:] = inh_r + sum_j w_rj X[col_rj,:].
+  // Rows are independent once the constraints are closed (checked at plan creation), so one thread per
+  // (row, vector); the j-order of the reference is kept.
+  __global__ void
+  p2c_kernel(double *X, uint32_t B, uint32_t nR, const uint32_t *rowIds, const uint32_t *rowSizes,
+             const uint32_t *rowOffsets, const uint32_t *colIds, const double *colVals, const double *inhom)
+  {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)nR * B)
+      return;
+    const uint32_t r = (uint32_t)(i / B), v = (uint32_t)(i % B);
+    double         s = inhom[r];
+    const uint32_t o = rowOffsets[r], m = rowSizes[r];
+    for (uint32_t j = 0; j < m; ++j)
+      s += colVals[o + j] * X[(size_t)colIds[o + j] * B + v];
+    X[(size_t)rowIds[r] * B + v] = s;
+  }
+
+  // distributeChildToParent (src/basis/ConstraintsInternal.cpp:110-170) without atomics: one thread per
+  // (parent, vector) walks the parent-side transpose in the reference's (row, entry) order.
+  __global__ void
+  c2p_kernel(double *Y, uint32_t B, uint32_t nPar, const uint32_t *parIds, const uint32_t *parOff,
+             const uint32_t *parChild, const double *parW)
+  {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)nPar * B)
+      return;
+    const uint32_t q = (uint32_t)(i / B), v = (uint32_t)(i % B);
+    double *       y = Y + (size_t)parIds[q] * B + v;
+    double         s = *y;
+    for (uint32_t e = parOff[q]; e < parOff[q + 1]; ++e)
+      s += parW[e] * Y[(size_t)parChild[e] * B + v];
+    *y = s;
+  }
+
+  __global__ void
+  zero_rows_kernel(double *Y, uint32_t B, uint32_t nR, const uint32_t *rowIds)
+  {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)nR * B)
+      return;
+    Y[(size_t)rowIds[i / B] * B + (i % B)] = 0.0;
+  }
+
+  int
+  launch_p2c(hx_plan *p, double *X, uint32_t B)
+  {
+    if (p->nR == 0)
+      return HX_OK;
+    p2c_kernel<<<nblk((size_t)p->nR * B), 256, 0, p->stream>>>(X, B, p->nR, p->d_row_ids.p, p->d_row_sizes.p,
+                                                               p->d_row_offsets.p, p->d_col_ids.p, p->d_col_vals.p,
+                                                               p->d_inhom.p);
+    p->launches++;
+    HX_CUDA(cudaGetLastError());
+    return HX_OK;
+  }
+
+  int
+  launch_zero_constrained(hx_plan *p, double *Y, uint32_t B)
+  {
+    if (p->nR == 0)
+      return HX_OK;
+    zero_rows_kernel<<<nblk((size_t)p->nR * B), 256, 0, p->stream>>>(Y, B, p->nR, p->d_row_ids.p);
+    p->launches++;
+    HX_CUDA(cudaGetLastError());
+    return HX_OK;
+  }
+
+  int
+  launch_c2p(hx_plan *p, double *Y, uint32_t B)
+  {
+    if (p->nR == 0)
+      return HX_OK;
+    if (p->nPar)
+      {
+        c2p_kernel<<<nblk((size_t)p->nPar * B), 256, 0, p->stream>>>(Y, B, p->nPar, p->d_par_ids.p, p->d_par_off.p,
+                                                                     p->d_par_child.p, p->d_par_w.p);
+        p->launches++;
+      }
+    HX_CUDA(cudaGetLastError());
+    return launch_zero_constrained(p, Y, B);
+  }
+
+  // ---- halo pack / unpack / accumulate (src/utils/DiscontiguousDataOperations.cpp:36-92) ------------
+  __global__ void
+  pack_rows_kernel(const double *x, uint32_t B, const uint32_t *ids, uint32_t n, double *buf)
+  {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)n * B)
+      return;
+    buf[i] = x[(size_t)ids[i / B] * B + (i % B)];
+  }
+  __global__ void
+  unpack_rows_kernel(const double *buf, uint32_t B, const uint32_t *ids, uint32_t n, double *x)
+  {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)n * B)
+      return;
+    x[(size_t)ids[i / B] * B + (i % B)] = buf[i];
+  }
+  // accumulate: ids may repeat (one owned row wanted by several ranks); a CSR row -> buffer positions
+  // built at plan creation keeps the reference's buffer order and needs no atomics.
+  __global__ void
+  add_rows_kernel(const double *buf, uint32_t B, const uint32_t *rows, const uint32_t *off, const uint32_t *pos,
+                  uint32_t nrows, double *x)
+  {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)nrows * B)
+      return;
+    const uint32_t r = (uint32_t)(i / B), v = (uint32_t)(i % B);
+    double *       d = x + (size_t)rows[r] * B + v;
+    double         s = *d;
+    for (uint32_t e = off[r]; e < off[r + 1]; ++e)
+      s += buf[(size_t)pos[e] * B + v];
+    *d = s;
+  }
+
+  int
+  launch_pack(hx_plan *p, const double *x, uint32_t B, const uint32_t *ids, uint32_t n, double *buf)
+  {
+    if (n == 0)
+      return HX_OK;
+    pack_rows_kernel<<<nblk((size_t)n * B), 256, 0, p->stream>>>(x, B, ids, n, buf);
+    p->launches++;
+    HX_CUDA(cudaGetLastError());
+    return HX_OK;
+  }
+  int
+  launch_unpack(hx_plan *p, const double *buf, uint32_t B, const uint32_t *ids, uint32_t n, double *x)
+  {
+    if (n == 0)
+      return HX_OK;
+    unpack_rows_kernel<<<nblk((size_t)n * B), 256, 0, p->stream>>>(buf, B, ids, n, x);
+    p->launches++;
+    HX_CUDA(cudaGetLastError());
+    return HX_OK;
+  }
+  int
+  launch_add_rows(hx_plan *p, const double *buf, uint32_t B, const uint32_t *rows, const uint32_t *off,
+                  const uint32_t *pos, uint32_t nrows, double *x)
+  {
+    if (nrows == 0)
+      return HX_OK;
+    add_rows_kernel<<<nblk((size_t)nrows * B), 256, 0, p->stream>>>(buf, B, rows, off, pos, nrows, x);
+    p->launches++;
+    HX_CUDA(cudaGetLastError());
+    return HX_OK;
+  }
+
+  // ---- elementwise ---------------------------------------------------------------------------------
+  // khatriRaoProduct(ColMajor,1,B,N) (src/linearAlgebra/BlasLapackKernels.cpp:356-372): y[i,:] = d[i] x[i,:]
+  __global__ void
+  row_scale_kernel(const double *d, const double *x, double *y, uint32_t B, size_t total)
+  {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < total)
+      y[i] = d[i / B] * x[i];
+  }
+  int
+  launch_row_scale(hx_plan *p, const double *d, const double *x, double *y, uint32_t B, size_t nrows)
+  {
+    const size_t tot = nrows * B;
+    if (tot == 0)
+      return HX_OK;
+    row_scale_kernel<<<nblk(tot), 256, 0, p->stream>>>(d, x, y, B, tot);
+    p->launches++;
+    HX_CUDA(cudaGetLastError());
+    return HX_OK;
+  }
+
+  __global__ void
+  axpby_kernel(size_t n, double a, const double *x, double b, const double *y, double *z)
+  {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n)
+      z[i] = a * x[i] + b * y[i];
+  }
+  int
+  launch_axpby(hx_plan *p, size_t n, double a, const double *x, double b, const double *y, double *z)
+  {
+    if (n == 0)
+      return HX_OK;
+    axpby_kernel<<<nblk(n), 256, 0, p->stream>>>(n, a, x, b, y, z);
+    p->launches++;
+    HX_CUDA(cudaGetLastError());
+    return HX_OK;
+  }
+
+  __global__ void
+  axpby_blocked_kernel(size_t total, uint32_t B, double a1, const double *a, const double *x, double b1,
+                       const double *b, const double *y, double *z)
+  {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < total)
+      {
+        const uint32_t j = (uint32_t)(i % B);
+        z[i]             = a1 * a[j] * x[i] + b1 * b[j] * y[i];
+      }
+  }
+  int
+  launch_axpby_blocked(hx_plan *p, size_t nrows, uint32_t B, double a1, const double *a, const double *x, double b1,
+                       const double *b, const double *y, double *z)
+  {
+    const size_t tot = nrows * B;
+    if (tot == 0)
+      return HX_OK;
+    axpby_blocked_kernel<<<nblk(tot), 256, 0, p->stream>>>(tot, B, a1, a, x, b1, b, y, z);
+    p->launches++;
+    HX_CUDA(cudaGetLastError());
+    return HX_OK;
+  }
+
+  // ---- column sums of squares (MultiVector::l2Norms, src/linearAlgebra/MultiVector.t.cpp:553-578) ----
+  // deterministic two-stage reduction: each block reduces a contiguous slab of rows per column in a fixed
+  // order, a second kernel adds the block partials in block order.
+  constexpr int CS_BLOCKS = 592; // 4 x 148 SMs
+  __global__ void
+  colsumsq_partial_kernel(const double *x, uint32_t B, size_t nrows, double *partial)
+  {
+    extern __shared__ double sh[]; // [rowsPerIter][B]
+    const uint32_t           rpi   = blockDim.x / B; // rows handled per iteration (>=1 because B <= blockDim)
+    const uint32_t           rr    = threadIdx.x / B, c = threadIdx.x % B;
+    const size_t             per   = (nrows + gridDim.x - 1) / gridDim.x;
+    const size_t             begin = (size_t)blockIdx.x * per;
+    const size_t             end   = begin + per < nrows ? begin + per : nrows;
+    double                   s     = 0.0;
+    if (rr < rpi)
+      for (size_t r = begin + rr; r < end; r += rpi)
+        {
+          const double v = x[r * B + c];
+          s += v * v;
+        }
+    if (rr < rpi)
+      sh[rr * B + c] = s;
+    __syncthreads();
+    if (threadIdx.x < B)
+      {
+        double t = 0.0;
+        for (uint32_t q = 0; q < rpi; ++q)
+          t += sh[q * B + threadIdx.x];
+        partial[(size_t)blockIdx.x * B + threadIdx.x] = t;
+      }
+  }
+  __global__ void
+  colsumsq_final_kernel(const double *partial, uint32_t B, uint32_t nb, double *out)
+  {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= B)
+      return;
+    double s = 0.0;
+    for (uint32_t b = 0; b < nb; ++b)
+      s += partial[(size_t)b * B + c];
+    out[c] = s;
+  }
+  int
+  launch_colsumsq(hx_plan *p, const double *x, uint32_t B, size_t nrows, double *out_dev)
+  {
+    HX_CHECK(B <= 256, HX_ERR_UNSUPPORTED, "l2 norms: B > 256 must be called per column batch");
+    HX_TRY(p->ensure_small((size_t)CS_BLOCKS * B + B));
+    double *partial = p->d_small.p;
+    const unsigned threads = 256;
+    colsumsq_partial_kernel<<<CS_BLOCKS, threads, (threads / B) * B * sizeof(double), p->stream>>>(x, B, nrows, partial);
+    colsumsq_final_kernel<<<nblk(B), 256, 0, p->stream>>>(partial, B, CS_BLOCKS, out_dev);
+    p->launches += 2;
+    HX_CUDA(cudaGetLastError());
+    return HX_OK;
+  }
+
+  // ---- shared-row (enrichment) reduction after the coloured scatter --------------------------------
+  __global__ void
+  shared_reduce_kernel(double *Y, const double *stage, const uint32_t *rows, const uint32_t *off,
+                       const uint32_t *slots, uint32_t nrows, uint32_t B)
+  {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)nrows * B)
+      return;
+    const uint32_t r = (uint32_t)(i / B), v = (uint32_t)(i % B);
+    double *       d = Y + (size_t)rows[r] * B + v;
+    double         s = *d;
+    for (uint32_t e = off[r]; e < off[r + 1]; ++e)
+      s += stage[(size_t)slots[e] * B + v];
+    *d = s;
+  }
+  int
+  launch_shared_reduce(hx_plan *p, double *Y, uint32_t B)
+  {
+    if (p->n_shared == 0)
+      return HX_OK;
+    shared_reduce_kernel<<<nblk((size_t)p->n_shared * B), 256, 0, p->stream>>>(Y, p->d_stage.p, p->d_sh_rows.p,
+                                                                               p->d_sh_off.p, p->d_sh_slots.p,
+                                                                               p->n_shared, B);
+    p->launches++;
+    HX_CUDA(cudaGetLastError());
+    return HX_OK;
+  }
+
+  // ---- atom-block enrichment matrix: Yenr (B x nE) = Xenr (B x nE) * blk (nE x nE), col-major ----------
+  // (src/basis/OEFEAtomBlockOverlapInvOpContextGLL.t.cpp:1005-1021)
+  __global__ void
+  enr_block_kernel(const double *blk, uint32_t nE, const double *Xenr, double *Yenr, uint32_t B)
+  {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)nE * B)
+      return;
+    const uint32_t j = (uint32_t)(i / B), v = (uint32_t)(i % B);
+    double         s = 0.0;
+    for (uint32_t k = 0; k < nE; ++k)
+      s += Xenr[(size_t)k * B + v] * blk[(size_t)k + (size_t)j * nE];
+    Yenr[i] = s;
+  }
+  int
+  launch_enr_block(hx_plan *p, const double *blk, uint32_t nE, const double *Xenr, double *Yenr, uint32_t B)
+  {
+    if (nE == 0)
+      return HX_OK;
+    enr_block_kernel<<<nblk((size_t)nE * B), 256, 0, p->stream>>>(blk, nE, Xenr, Yenr, B);
+    p->launches++;
+    HX_CUDA(cudaGetLastError());
+    return HX_OK;
+  }
+
+  // ---- fused Chebyshev recurrence step ---------------------------------------------------------------
+  // One pass over the owned rows does, for the diagonal (mass-lumped) M^-1 of the reference,
+  //   t      = C2P( dinv .* P2C(s1) ) [+ atom-block rows]      (M^-1 apply, a11)
+  //   out    = a*t + b*xcur + c*xprev                           (the two axpby of ChebyshevFilter.t.cpp:105-124)
+  // s1 must already have its constrained rows filled (p2c launched before).  rowinfo[i]: 0xFFFFFFFF = free row
+  // without children, 0xFFFFFFFE = constrained row (-> t = 0), else index into the parent-side CSR.
+  __global__ void
+  cheb_fused_kernel(const double *s1, const double *xcur, const double *xprev, double *out, const double *dinv,
+                    const uint32_t *rowinfo, const uint32_t *parOff, const uint32_t *parChild, const double *parW,
+                    const double *blk, uint32_t ncl, uint32_t nE, uint32_t nOwned, uint32_t B, double a, double b,
+                    double c)
+  {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)nOwned * B)
+      return;
+    const uint32_t r = (uint32_t)(i / B), v = (uint32_t)(i % B);
+    double         t;
+    const uint32_t info = rowinfo[r];
+    if (info == 0xFFFFFFFEu)
+      t = 0.0;
+    else
+      {
+        if (r >= ncl && nE > 0)
+          {
+            t = 0.0;
+            const uint32_t j = r - ncl;
+            for (uint32_t k = 0; k < nE; ++k)
+              t += s1[(size_t)(ncl + k) * B + v] * blk[(size_t)k + (size_t)j * nE];
+          }
+        else
+          t = dinv[r] * s1[i];
+        if (info != 0xFFFFFFFFu)
+          for (uint32_t e = parOff[info]; e < parOff[info + 1]; ++e)
+            {
+              const uint32_t ch = parChild[e];
+              t += parW[e] * (dinv[ch] * s1[(size_t)ch * B + v]);
+            }
+      }
+    double o = a * t + b * xcur[i];
+    if (c != 0.0)
+      o += c * xprev[i];
+    out[i] = o;
+  }
+} // namespace hx
+
+namespace hx
+{
+  int
+  launch_cheb_fused(hx_plan *p, hx_op *binv, const double *s1, const double *xcur, const double *xprev, double *out,
+                    uint32_t B, double a, double b, double c)
+  {
+    const size_t tot = (size_t)p->n_owned * B;
+    if (tot == 0)
+      return HX_OK;
+    cheb_fused_kernel<<<nblk(tot), 256, 0, p->stream>>>(s1, xcur, xprev ? xprev : xcur, out, binv->d_diag.p,
+                                                        p->d_rowinfo.p, p->d_par_off.p, p->d_par_child.p,
+                                                        p->d_par_w.p, binv->d_enr_block.p, p->n_owned_classical,
+                                                        binv->variant == HX_DIAG_CFE ? 0u : binv->nE, p->n_owned, B,
+                                                        a, b, xprev ? c : 0.0);
+    p->launches++;
+    HX_CUDA(cudaGetLastError());
+    return HX_OK;
+  }
+} // namespace hx

@@ -317,7 +317,9 @@ def _key1d(o, s, a, p, n):
     return key
 
 
-def build_problem(spec: MeshSpec) -> List[RankProblem]:
+def build_problem(spec: MeshSpec, only_rank: Optional[int] = None) -> List[RankProblem]:
+    """Returns one RankProblem per rank (or, with only_rank=r, a list holding just rank r's problem —
+    every rank of a multi-GPU job builds the same global mesh and keeps its own part)."""
     nx, ny, nz = spec.ncell
     p = spec.p
     npc = (p + 1) ** 3
@@ -588,6 +590,8 @@ def build_problem(spec: MeshSpec) -> List[RankProblem]:
 
     problems = []
     for r in range(spec.nranks):
+        if only_rank is not None and r != only_rank:
+            continue
         cells = per_rank[r]
         halo = halos[r]
         n_owned, n_ghost = halo.n_owned, halo.n_ghost

@@ -1,0 +1,194 @@
+/*
+ * hxb200.h — C ABI of the B200-native H.X / Chebyshev-filter / Rayleigh-Ritz hot path of dft-efe.
+ *
+ * One hx_plan per GPU (= per reference MPI rank).  All block vectors are DEVICE pointers to FP64
+ * data in the reference MultiVector layout data[iDof*B + iVec], owned rows [0,n_owned) (range 0 =
+ * classical, range 1 = enrichment) followed by ghost rows in ascending global id
+ * (reference src/linearAlgebra/MultiVector.h:134-160, src/utils/MPIPatternP2P.h:107-116).
+ * Index arrays in descriptors are HOST pointers (uint32_t = dftefe::size_type,
+ * src/utils/TypeConfig.h:8-9) and are copied at creation.  Every call returns 0 or a negative
+ * hx_status; hx_last_error() gives the message (no exceptions cross this boundary — the C++ mirror
+ * in dft_efe_b200/include/ turns them into utils::throwException-style exceptions,
+ * reference src/utils/Exceptions.h:128).  Calls are asynchronous on the plan's stream unless they
+ * return host data.  A plan is not thread-safe (the reference operator is not re-entrant either:
+ * const apply() with mutable scratch, src/ksdft/KohnShamOperatorContextFE.h:130-157).
+ *
+ * There is no CPU fallback: every entry point fails with HX_ERR_CUDA when no device is usable.
+ *
+ * Each entry point cites the reference interface it replaces.
+ */
+#ifndef HXB200_H
+#define HXB200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct hx_plan hx_plan;
+typedef struct hx_op   hx_op;
+
+typedef enum hx_status {
+  HX_OK              = 0,
+  HX_ERR_INVALID     = -1, /* bad argument / inconsistent descriptor */
+  HX_ERR_CUDA        = -2, /* CUDA runtime error, or no usable device */
+  HX_ERR_COMM        = -3, /* NCCL error / communicator missing for nranks > 1 */
+  HX_ERR_UNSUPPORTED = -4, /* e.g. unresolved constraint chains */
+  HX_ERR_NOMEM       = -5
+} hx_status;
+
+/* The getters of utils::mpi::MPIPatternP2P the ghost communicator consumes
+ * (reference src/utils/MPIPatternP2P.h:425-459). */
+typedef struct hx_halo_desc {
+  uint32_t        n_owned;                     /* localOwnedSize()                       */
+  uint32_t        n_ghost;                     /* localGhostSize()                       */
+  uint32_t        n_ghost_procs;               /* getGhostProcIds().size()               */
+  const uint32_t *ghost_proc_ids;              /* getGhostProcIds()                      */
+  const uint32_t *ghost_ranges;                /* getGhostLocalIndicesRanges()  [2*nGP]  */
+  const uint32_t *ghost_local_ids;             /* getGhostLocalIndicesForGhostProcs()    */
+  uint32_t        n_target_procs;              /* getTargetProcIds().size()              */
+  const uint32_t *target_proc_ids;             /* getTargetProcIds()                     */
+  const uint32_t *num_owned_for_target;        /* getNumOwnedIndicesForTargetProcs()     */
+  const uint32_t *owned_local_ids_for_targets; /* getOwnedLocalIndicesForTargetProcs()   */
+} hx_halo_desc;
+
+/* The arrays basis::FEBasisManager and basis::ConstraintsLocal expose
+ * (reference src/basis/FEBasisManager.h:143-160, FEBasisManager.t.cpp:414-428,545-557;
+ *  src/basis/CFEConstraintsLocalDealii.t.cpp:286-462). */
+typedef struct hx_mesh_desc {
+  uint32_t        struct_size; /* sizeof(hx_mesh_desc), ABI guard */
+  int32_t         rank, nranks;
+  hx_halo_desc    halo;
+  uint32_t        n_owned_classical; /* size of owned range 0; enrichment rows follow */
+  uint32_t        n_cells;           /* nLocallyOwnedCells()                  */
+  const uint32_t *num_cell_dofs;     /* nLocallyOwnedCellDofs(c)     [C]      */
+  const uint32_t *cell_local_ids;    /* locallyOwnedCellLocalDofIds  [S]      */
+  uint32_t        n_constraint_rows;
+  const uint32_t *row_ids;     /* rowConstraintsIdsLocal        [nR]  */
+  const uint32_t *row_sizes;   /* rowConstraintsSizes           [nR]  */
+  const uint32_t *row_offsets; /* columnConstraintsAccumulated  [nR]  */
+  const uint32_t *col_ids;     /* columnConstraintsIdsLocal     [nnz] */
+  const double *  col_vals;    /* columnConstraintsValues       [nnz] */
+  const double *  inhom;       /* constraintsInhomogenities     [nR]  */
+  uint32_t        max_block;   /* largest number of vectors any call will pass (d_maxWaveFnBatch) */
+} hx_mesh_desc;
+
+/* Nonlocal pseudopotential projector data of basis::AtomCenterNonLocalOpContextFE
+ * (reference src/basis/AtomCenterNonLocalOpContextFE.t.cpp:478-494,595-619). */
+typedef struct hx_nonlocal_desc {
+  uint32_t        struct_size;
+  hx_halo_desc    proj_halo;           /* d_mpiPatternP2PProj                                   */
+  const uint32_t *num_cell_proj;       /* d_numProjsInCells                  [C]                */
+  const uint32_t *cell_proj_local_ids; /* d_locallyOwnedCellLocalProjectorIds [sum nProj_c]     */
+  const double *  cell_c;              /* d_cellWiseC: per cell column-major nProj_c x n_c      */
+  const double *  v;                   /* d_V                                [nProjLocal]       */
+} hx_nonlocal_desc;
+
+typedef enum hx_diag_variant {
+  HX_DIAG_CFE            = 0, /* CFEOverlapInverseOpContextGLL::apply  (src/basis/CFEOverlapInverseOpContextGLL.t.cpp:529-558) */
+  HX_DIAG_OEFE_ATOMBLOCK = 1, /* OEFEAtomBlockOverlapInvOpContextGLL::apply (src/basis/OEFEAtomBlockOverlapInvOpContextGLL.t.cpp:953-1108) */
+  HX_DIAG_OEFE_MASS      = 2  /* OrthoEFEOverlapOperatorContext::apply, mass-lumped atom-block branch: as ATOMBLOCK
+                                 but both ghost flags are forced to false (src/basis/OrthoEFEOverlapOperatorContext.t.cpp:2093-2235) */
+} hx_diag_variant;
+
+const char *hx_last_error(void);
+int         hx_version(void);
+
+/* ---- device helpers (so a host-only caller needs no CUDA runtime of its own) ---- */
+int hx_device_count(int *n);
+int hx_set_device(int device);
+int hx_device_alloc(void **ptr, size_t bytes);
+int hx_device_free(void *ptr);
+int hx_host_alloc_pinned(void **ptr, size_t bytes);
+int hx_host_free_pinned(void *ptr);
+int hx_memcpy_h2d(void *dst_dev, const void *src_host, size_t bytes);
+int hx_memcpy_d2h(void *dst_host, const void *src_dev, size_t bytes);
+int hx_memset_zero(void *dst_dev, size_t bytes);
+
+/* ---- plan ---- */
+/* Replaces: the construction-time flattening in FEBasisManager (src/basis/FEBasisManager.t.cpp:161-285)
+ * + MultiVector's MPICommunicatorP2P buffers (src/utils/MPICommunicatorP2P.t.cpp:39-75).
+ * `stream` is a cudaStream_t (NULL = a stream the plan creates). */
+int hx_plan_create(hx_plan **plan, const hx_mesh_desc *mesh, void *stream);
+int hx_plan_destroy(hx_plan *plan);
+int hx_plan_synchronize(hx_plan *plan);
+/* Multi-GPU: rank 0 calls hx_comm_unique_id, the caller broadcasts the 128 bytes (MPI_Bcast /
+ * torch.distributed), every rank calls hx_plan_attach_comm.  Replaces the MPI communicator held by
+ * MPIPatternP2P (src/utils/MPIPatternP2P.h:489).  Ranks of the halo descriptors are communicator ranks. */
+int hx_comm_unique_id(char id[128]);
+int hx_plan_attach_comm(hx_plan *plan, const char id[128]);
+/* Introspection used by the bit-exact parity tests of the integer work. */
+int hx_plan_num_colours(hx_plan *plan, uint32_t *n);
+int hx_plan_get_cell_colours(hx_plan *plan, uint32_t *colour /*[C]*/);
+int hx_plan_get_c2p_transpose(hx_plan *plan, uint32_t *n_parents, uint32_t *parent_ids, uint32_t *offsets,
+                              uint32_t *child_rows, double *weights); /* pass NULLs to query n_parents */
+
+/* ---- ghost communicator (src/utils/MPICommunicatorP2P.t.cpp:77-273, 278-470) ---- */
+int hx_update_ghost_values(hx_plan *plan, double *X, uint32_t B);
+int hx_accumulate_add_locally_owned(hx_plan *plan, double *Y, uint32_t B);
+/* ---- constraints (src/basis/ConstraintsInternal.cpp:35-108, 110-170, 172-196) ---- */
+int hx_distribute_parent_to_child(hx_plan *plan, double *X, uint32_t B);
+int hx_distribute_child_to_parent(hx_plan *plan, double *Y, uint32_t B);
+int hx_set_constrained_nodes_to_zero(hx_plan *plan, double *Y, uint32_t B);
+
+/* ---- operators: linearAlgebra::OperatorContext<double,double,DEVICE> (src/linearAlgebra/OperatorContext.h:48-111) ---- */
+/* Cell-matrix operator: KohnShamOperatorContextFE (src/ksdft/KohnShamOperatorContextFE.h:102-127); also the
+ * non-lumped overlap operators (src/basis/OrthoEFEOverlapOperatorContext.t.cpp:2237-2290,
+ * src/basis/CFEOverlapOperatorContext.t.cpp:539-660) which run the same path with cell mass matrices. */
+int hx_cellop_create(hx_plan *plan, hx_op **op);
+/* reinit (src/ksdft/KohnShamOperatorContextFE.t.cpp:1240-1311): cell matrices concatenated, each n_c x n_c
+ * row-major, S2 doubles; `on_device` says where `cell_matrices` lives.  Re-tiled internally. */
+int hx_cellop_set_matrices(hx_op *op, const double *cell_matrices, int on_device);
+int hx_cellop_set_nonlocal(hx_op *op, const hx_nonlocal_desc *nl);
+/* Mass-lumped M / M^-1 style operator: diagonal over local rows + atom-block enrichment matrix
+ * (nE_owned x nE_owned, column-major; may be NULL when nE_owned == 0). Host pointers. */
+int hx_diagop_create(hx_plan *plan, const double *diag, const double *enr_block, int variant, hx_op **op);
+int hx_op_destroy(hx_op *op);
+/* OperatorContext::apply(X, Y, updateGhostX, updateGhostY): X may be modified (ghost update + hanging-node
+ * fill, OperatorContext.h:98-101); Y fully overwritten; Y's owned rows final, ghost rows hold the rank's
+ * partial sums unless updateGhostY (src/ksdft/KohnShamOperatorContextFE.t.cpp:1313-1443). */
+int hx_op_apply(hx_op *op, double *X, double *Y, uint32_t B, int updateGhostX, int updateGhostY);
+/* Same call with HOST buffers (n_local*B doubles each): copies X in, applies, copies X (modified) and Y out. */
+int hx_op_apply_host(hx_op *op, double *X_host, double *Y_host, uint32_t B, int updateGhostX, int updateGhostY);
+
+/* ---- Chebyshev filters (src/linearAlgebra/ChebyshevFilter.h:54-113, ChebyshevFilter.t.cpp:39-134, 242-445) ---- */
+/* X = eigenSubspaceGuess (in/out), Y = filteredSubspace (out); on return both hold the filtered block. */
+int hx_chebyshev_filter(hx_op *A, hx_op *BInv, double *X, double *Y, uint32_t B, uint32_t degree,
+                        double wantedLower, double wantedUpper, double unwantedUpper);
+/* eigenvalues: HOST array of B doubles (std::vector<RealType>& in the reference). */
+int hx_residual_chebyshev_filter(hx_op *A, hx_op *Bop, hx_op *BInv, const double *eigenvalues, double *X,
+                                 double *Y, uint32_t B, uint32_t degree, double wantedLower,
+                                 double wantedUpper, double unwantedUpper);
+
+/* ---- subspace projections ---- */
+/* computeXTransOpX (src/linearAlgebra/RayleighRitzEigenSolver.t.cpp:685-844 and the identical copy in
+ * OrthonormalizationFunctions.t.cpp:1419-1581): column batches of `batch`, Op.apply(batch,true,false),
+ * lower-trapezoid Gram block, sum over ranks.  S_host: B x B column-major, lower triangle written,
+ * strict upper triangle zero. */
+int hx_xtopx(hx_op *op, double *X, uint32_t B, uint32_t batch, double *S_host);
+/* elpaScalaOpInternal::subspaceRotation (src/linearAlgebra/ElpaScalapackOperations.t.cpp:185-335):
+ * X[dof,:] <- X[dof,:] * Q (rotationMatTranspose) or * Q^T; Q HOST, B x B column-major (replicated). */
+int hx_subspace_rotation(hx_plan *plan, double *X, uint32_t B, const double *Q_host, int rotationMatTranspose,
+                         int isRotationMatLowerTria);
+/* MultiVector::l2Norms (src/linearAlgebra/MultiVector.t.cpp:553-578): owned rows, summed over ranks. */
+int hx_l2_norms(hx_plan *plan, const double *X, uint32_t B, double *norms_host);
+/* blasLapack::axpby / axpbyBlocked over the first n_rows rows (src/linearAlgebra/BlasLapackKernels.cpp:456-502). */
+int hx_axpby(hx_plan *plan, uint32_t n_rows, uint32_t B, double alpha, const double *x, double beta,
+             const double *y, double *z);
+int hx_axpby_blocked(hx_plan *plan, uint32_t n_rows, uint32_t B, double alpha1, const double *alpha_host,
+                     const double *x, double beta1, const double *beta_host, const double *y, double *z);
+
+/* ---- measurement hooks (bench.py / tests) ---- */
+/* Number of kernel launches issued through this plan since creation, and device time of the dominant
+ * cell-contraction kernel accumulated with CUDA events on the plan's stream (reset on read). */
+int hx_plan_launch_count(hx_plan *plan, uint64_t *n);
+int hx_plan_cell_kernel_time_ms(hx_plan *plan, double *ms, uint64_t *launches);
+int hx_plan_enable_kernel_timing(hx_plan *plan, int on);
+/* FP64 DMMA / DFMA / copy microbenchmarks used for the roofline denominators. */
+int hx_microbench(double *dmma_tflops, double *dfma_tflops, double *copy_gbs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HXB200_H */

@@ -31,7 +31,7 @@ def build(force: bool = False) -> str:
     src = os.path.join(_HERE, "hx_oracle.c")
     out = os.path.join(_HERE, "liborc.so")
     if force or not os.path.exists(out) or os.path.getmtime(out) < os.path.getmtime(src):
-        subprocess.check_call(["gcc", "-O3", "-march=native", "-ffp-contract=off", "-fPIC", "-shared", "-std=c11",
+        subprocess.check_call(["gcc", "-O3", "-march=x86-64-v3", "-ffp-contract=off", "-fPIC", "-shared", "-std=c11",
                                "-o", out, src, "-lm"])
     return out
 
@@ -431,3 +431,51 @@ class OracleWorld:
             lib().orc_col_sumsq(_f64(X), C.c_uint32(B), C.c_size_t(self.n_owned[i]), _f64(part))
             tot += part
         return np.sqrt(tot)
+
+
+# ---------------------------------------------------------------------------
+# integer work the CUDA library derives at plan creation (bit-exact parity targets)
+# ---------------------------------------------------------------------------
+def cell_colouring(prob, shared_threshold: int = 8):
+    """Greedy colouring of the cell-DoF graph: cells in ascending order take the lowest colour not used
+    by an earlier cell that shares a local row with them; rows touched by more than `shared_threshold`
+    cells (enrichment DoFs) do not constrain the colouring (they are reduced separately).  This is the
+    specification of the deterministic scatter that replaces the reference's sequential
+    addCellWiseDataToFieldData (basis/FECellWiseDataOperations.t.cpp:87-153)."""
+    ids = prob.cell_local_ids.astype(np.int64)
+    ncd = prob.num_cell_dofs.astype(np.int64)
+    off = np.concatenate(([0], np.cumsum(ncd)))
+    inc = np.bincount(ids, minlength=prob.n_local)
+    used = [0] * prob.n_local
+    colour = np.zeros(prob.n_cells, np.uint32)
+    for c in range(prob.n_cells):
+        rows = [int(r) for r in ids[off[c]:off[c + 1]] if inc[r] <= shared_threshold]
+        mask = 0
+        for r in rows:
+            mask |= used[r]
+        col = 0
+        while mask & (1 << col):
+            col += 1
+        colour[c] = col
+        for r in rows:
+            used[r] |= (1 << col)
+    return int(colour.max()) + 1 if prob.n_cells else 0, colour
+
+
+def c2p_transpose(prob):
+    """Parent-side view of the constraint CSR: parents ascending, entries in the reference's (row, entry)
+    order — the order in which basis/ConstraintsInternal.cpp:110-170 adds into each parent."""
+    par = {}
+    for i in range(len(prob.row_ids)):
+        o = int(prob.row_offsets[i])
+        for j in range(int(prob.row_sizes[i])):
+            par.setdefault(int(prob.col_ids[o + j]), []).append((int(prob.row_ids[i]), float(prob.col_vals[o + j])))
+    ids = np.array(sorted(par), np.uint32)
+    off = [0]
+    ch, w = [], []
+    for p_ in ids:
+        for r, v in par[int(p_)]:
+            ch.append(r)
+            w.append(v)
+        off.append(len(ch))
+    return ids, np.array(off, np.uint32), np.array(ch, np.uint32), np.array(w, np.float64)

@@ -1,0 +1,336 @@
+"""GPU parity tests: every call goes through the C ABI (dft_efe_b200.capi -> libhxb200.so) and is compared
+with the CPU oracle on identical seeded inputs.
+
+Tolerances (BASELINE.json north_star): integer/index work bit-exact; FP64 H.X within 1e-12 relative in the
+L2 norm per vector.
+"""
+import numpy as np
+import pytest
+
+from dft_efe_b200 import synth
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+RTOL_HX = 1e-12
+
+
+def rel_l2_per_vector(a, b):
+    num = np.linalg.norm(a - b, axis=0)
+    den = np.linalg.norm(b, axis=0)
+    den[den == 0] = 1.0
+    return (num / den).max()
+
+
+@pytest.fixture(scope="module")
+def capi():
+    from dft_efe_b200 import capi as c
+    assert c.device_count() >= 1, "no CUDA device"
+    return c
+
+
+def spec_full(nranks=1, p=3, nc=(4, 4, 4), refine=True, enr=3, proj=2, boundary="dirichlet"):
+    L = float(nc[0])
+    atoms = np.array([[L / 2, L / 2, L / 2], [0.3 * L, 0.72 * L, 0.28 * L]])
+    return synth.MeshSpec(ncell=nc, p=p, refine_mask=synth.refine_ball(nc, 1.0, [atoms[0]], 0.9) if refine else None,
+                          atoms=atoms if (enr or proj) else None, n_enr_per_atom=enr, enr_cutoff=1.2,
+                          n_proj_per_atom=proj, proj_cutoff=1.0, nranks=nranks, boundary=boundary)
+
+
+@pytest.fixture(scope="module")
+def prob_full():
+    return synth.build_problem(spec_full())[0]
+
+
+@pytest.fixture(scope="module")
+def prob_plain():
+    return synth.build_problem(synth.MeshSpec(ncell=(5, 4, 3), p=4, boundary="none"))[0]
+
+
+# ------------------------------------------------------------------ integer work: bit exact ----
+def test_colouring_and_constraint_transpose_bit_exact(capi, prob_full):
+    plan = capi.Plan(prob_full, max_block=8)
+    n, col = plan.colours()
+    n_o, col_o = orc.cell_colouring(prob_full)
+    assert n == n_o and np.array_equal(col, col_o)
+    # a colouring is valid: cells of one colour share no non-shared row
+    ids = prob_full.cell_local_ids.astype(np.int64)
+    off = np.concatenate(([0], np.cumsum(prob_full.num_cell_dofs.astype(np.int64))))
+    inc = np.bincount(ids, minlength=prob_full.n_local)
+    for k in range(n):
+        seen = set()
+        for c in np.nonzero(col == k)[0]:
+            rows = [r for r in ids[off[c]:off[c + 1]] if inc[r] <= 8]
+            assert not (seen & set(rows))
+            seen |= set(rows)
+    a = plan.c2p_transpose()
+    b = orc.c2p_transpose(prob_full)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+
+
+# --------------------------------------------------------------------------------- leaf ops ----
+@pytest.mark.parametrize("B", [1, 3, 8, 32])
+def test_constraints_match_oracle(capi, prob_full, B):
+    plan = capi.Plan(prob_full, max_block=32)
+    R = orc.OracleRank(prob_full)
+    X = synth.make_block(prob_full, B)
+    d = plan.block(B, X)
+    plan.p2c(d)
+    xo = X.copy(); R.p2c(xo)
+    assert rel_l2_per_vector(d.download(), xo) < 1e-14
+    d = plan.block(B, X)
+    plan.c2p(d)
+    xo = X.copy(); R.c2p(xo)
+    assert rel_l2_per_vector(d.download(), xo) < 1e-14
+
+
+# ---------------------------------------------------------------------------------- H.X ----
+@pytest.mark.parametrize("B", [1, 2, 5, 8, 16, 32, 40, 64, 96])
+def test_hx_plain_mesh(capi, prob_plain, B):
+    """uniform mesh, no constraints, uniform n_c: the minimum slice of SURVEY 7 step 2."""
+    p = prob_plain
+    plan = capi.Plan(p, max_block=96)
+    op = capi.CellOp(plan)
+    W = orc.OracleWorld([p])
+    X = synth.make_block(p, B)
+    dX, dY = plan.block(B, X), plan.block(B)
+    op.apply(dX, dY, True, False)
+    Xo, Yo = X.copy(), np.zeros_like(X)
+    W.hx_apply([Xo], [Yo], True, False, long_double=True)
+    assert rel_l2_per_vector(dY.download(), Yo) < RTOL_HX
+
+
+@pytest.mark.parametrize("B", [1, 4, 7, 32, 48])
+def test_hx_full_features(capi, prob_full, B):
+    """hanging nodes + Dirichlet rows + enrichment (variable n_c, shared rows) + nonlocal projectors."""
+    p = prob_full
+    plan = capi.Plan(p, max_block=48)
+    op = capi.CellOp(plan)
+    W = orc.OracleWorld([p])
+    X = synth.make_block(p, B)
+    dX, dY = plan.block(B, X), plan.block(B)
+    op.apply(dX, dY, True, False)
+    Xo, Yo = X.copy(), np.zeros_like(X)
+    W.hx_apply([Xo], [Yo], True, False)
+    assert rel_l2_per_vector(dY.download(), Yo) < RTOL_HX
+    # X is modified in place exactly like the reference (constrained rows filled)
+    assert rel_l2_per_vector(dX.download(), Xo) < 1e-14
+    # constrained rows of Y are zero
+    assert np.all(dY.download()[p.row_ids.astype(np.int64)] == 0.0)
+
+
+def test_hx_without_nonlocal_and_reinit(capi, prob_full):
+    p = prob_full
+    B = 8
+    plan = capi.Plan(p, max_block=B)
+    op = capi.CellOp(plan, with_nonlocal=False)
+    W = orc.OracleWorld([p])
+    X = synth.make_block(p, B)
+    dX, dY = plan.block(B, X), plan.block(B)
+    op.apply(dX, dY)
+    Yo = np.zeros_like(X)
+    W.hx_apply([X.copy()], [Yo], use_nonlocal=False)
+    assert rel_l2_per_vector(dY.download(), Yo) < RTOL_HX
+    # reinit with new cell matrices (one SCF iteration later): index maps unchanged
+    h2 = p.h_cell * 1.5 + 0.01
+    op.set_matrices(h2)
+    dX = plan.block(B, X)
+    op.apply(dX, dY)
+    Yo = np.zeros_like(X)
+    W.hx_apply([X.copy()], [Yo], use_nonlocal=False, h_cells=[h2])
+    assert rel_l2_per_vector(dY.download(), Yo) < RTOL_HX
+
+
+def test_hx_bitwise_deterministic(capi, prob_full):
+    p = prob_full
+    B = 16
+    plan = capi.Plan(p, max_block=B)
+    op = capi.CellOp(plan)
+    X = synth.make_block(p, B)
+    outs = []
+    for _ in range(3):
+        dX, dY = plan.block(B, X), plan.block(B)
+        op.apply(dX, dY)
+        outs.append(dY.download())
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
+
+
+def test_hx_host_entry_point(capi, prob_full):
+    p = prob_full
+    B = 8
+    plan = capi.Plan(p, max_block=B)
+    op = capi.CellOp(plan)
+    X = synth.make_block(p, B)
+    Xh, Yh = X.copy(), np.zeros_like(X)
+    op.apply_host(Xh, Yh, True, False)
+    Xo, Yo = X.copy(), np.zeros_like(X)
+    orc.OracleWorld([p]).hx_apply([Xo], [Yo], True, False)
+    assert rel_l2_per_vector(Yh, Yo) < RTOL_HX
+    assert rel_l2_per_vector(Xh, Xo) < 1e-14
+
+
+@pytest.mark.parametrize("p_order", [1, 2, 5, 6])
+def test_hx_other_orders(capi, p_order):
+    nc = (3, 3, 3) if p_order >= 5 else (4, 4, 4)
+    p = synth.build_problem(synth.MeshSpec(ncell=nc, p=p_order, refine_mask=synth.refine_ball(nc, 1.0, [[1.5, 1.5, 1.5]], 0.9)))[0]
+    B = 12
+    plan = capi.Plan(p, max_block=B)
+    op = capi.CellOp(plan)
+    X = synth.make_block(p, B)
+    dX, dY = plan.block(B, X), plan.block(B)
+    op.apply(dX, dY)
+    Yo = np.zeros_like(X)
+    orc.OracleWorld([p]).hx_apply([X.copy()], [Yo])
+    assert rel_l2_per_vector(dY.download(), Yo) < RTOL_HX
+
+
+def test_empty_and_error_paths(capi, prob_full):
+    plan = capi.Plan(prob_full, max_block=4)
+    op = capi.CellOp(plan)
+    dX, dY = plan.block(8), plan.block(8)
+    with pytest.raises(capi.HxError):       # B > max_block
+        op.apply(dX, dY)
+    d4 = plan.block(4)
+    with pytest.raises(capi.HxError):       # aliasing
+        op.apply(d4, d4)
+    # zero cells / zero constraints
+    import copy
+    e = copy.copy(prob_full)
+    e.n_cells = 0
+    e.num_cell_dofs = np.zeros(0, np.uint32); e.cell_local_ids = np.zeros(0, np.uint32); e.h_cell = np.zeros(0)
+    e.num_cell_proj = None
+    e.row_ids = e.row_sizes = e.row_offsets = e.col_ids = np.zeros(0, np.uint32)
+    e.col_vals = e.inhom = np.zeros(0)
+    pl = capi.Plan(e, max_block=4)
+    o = capi.CellOp(pl)
+    dX, dY = pl.block(4, synth.make_block(e, 4)), pl.block(4)
+    o.apply(dX, dY)
+    assert np.all(dY.download() == 0.0)
+
+
+# ---------------------------------------------------------------------------- M, M^-1 ----
+@pytest.mark.parametrize("variant", ["cfe", "oefe_atomblock"])
+def test_diag_ops(capi, prob_full, variant):
+    p = prob_full
+    B = 8
+    plan = capi.Plan(p, max_block=B)
+    W = orc.OracleWorld([p])
+    vid = capi.DIAG_CFE if variant == "cfe" else capi.DIAG_OEFE_ATOMBLOCK
+    minv = capi.DiagOp(plan, p.diag_inv, p.enr_block_inv, vid)
+    X = synth.make_block(p, B)
+    dX, dY = plan.block(B, X), plan.block(B)
+    minv.apply(dX, dY, True, True)
+    Xo, Yo = X.copy(), np.zeros_like(X)
+    W.minv_apply([Xo], [Yo], True, True, variant)
+    assert rel_l2_per_vector(dY.download(), Yo) < 1e-14
+    m = capi.DiagOp(plan, p.diag, p.enr_block, capi.DIAG_OEFE_MASS)
+    dX = plan.block(B, X)
+    m.apply(dX, dY, True, True)
+    Xo, Yo = X.copy(), np.zeros_like(X)
+    W.m_apply([Xo], [Yo], True, True)
+    assert rel_l2_per_vector(dY.download(), Yo) < 1e-14
+
+
+# ------------------------------------------------------------------------- filters ----
+@pytest.mark.parametrize("variant", ["cfe", "oefe_atomblock"])
+def test_chebyshev_filter(capi, prob_full, variant):
+    p = prob_full
+    B, deg = 8, 9
+    a0, a, b = -3.0, 1.0, 60.0
+    plan = capi.Plan(p, max_block=B)
+    H = capi.CellOp(plan)
+    vid = capi.DIAG_CFE if variant == "cfe" else capi.DIAG_OEFE_ATOMBLOCK
+    minv = capi.DiagOp(plan, p.diag_inv, p.enr_block_inv, vid)
+    X = synth.make_block(p, B)
+    dX, dY = plan.block(B, X), plan.block(B)
+    capi.chebyshev_filter(H, minv, dX, dY, deg, a0, a, b)
+    F = orc.OracleWorld([p]).chebyshev_filter([X.copy()], deg, a0, a, b, minv_variant=variant)[0]
+    own = p.n_owned
+    assert rel_l2_per_vector(dY.download()[:own], F[:own]) < 1e-11   # degree-9 recurrence of 1e-12-accurate applies
+    assert np.array_equal(dX.download()[:own], dY.download()[:own])  # both hold the result
+
+
+def test_residual_chebyshev_filter(capi, prob_full):
+    p = prob_full
+    B, deg = 6, 7
+    a0, a, b = -3.0, 1.0, 60.0
+    plan = capi.Plan(p, max_block=B)
+    H = capi.CellOp(plan)
+    minv = capi.DiagOp(plan, p.diag_inv, p.enr_block_inv, capi.DIAG_OEFE_ATOMBLOCK)
+    m = capi.DiagOp(plan, p.diag, p.enr_block, capi.DIAG_OEFE_MASS)
+    ev = np.linspace(-2.5, 0.5, B)
+    X = synth.make_block(p, B)
+    dX, dY = plan.block(B, X), plan.block(B)
+    capi.residual_chebyshev_filter(H, m, minv, ev, dX, dY, deg, a0, a, b)
+    Yo = orc.OracleWorld([p]).residual_chebyshev_filter([X.copy()], ev, deg, a0, a, b)[0]
+    own = p.n_owned
+    assert rel_l2_per_vector(dY.download()[:own], Yo[:own]) < 1e-11
+
+
+# --------------------------------------------------------------- subspace projections ----
+@pytest.mark.parametrize("B,batch", [(6, 4), (32, 32), (40, 16), (96, 64)])
+def test_xtopx(capi, prob_full, B, batch):
+    p = prob_full
+    plan = capi.Plan(p, max_block=B)
+    H = capi.CellOp(plan)
+    W = orc.OracleWorld([p])
+    X = synth.make_block(p, B)
+    dX = plan.block(B, X)
+    S = H.xtopx(dX, batch)
+    So = W.xtopx([X.copy()], lambda a, b, c, d: W.hx_apply(a, b, c, d), batch)
+    assert np.abs(S - So).max() < 1e-12 * np.abs(So).max()
+    assert np.all(np.triu(S, 1) == 0.0)
+
+
+@pytest.mark.parametrize("B", [6, 32, 72])
+@pytest.mark.parametrize("transpose,lower", [(True, False), (False, True), (True, True)])
+def test_subspace_rotation(capi, prob_full, B, transpose, lower):
+    p = prob_full
+    plan = capi.Plan(p, max_block=B)
+    W = orc.OracleWorld([p])
+    X = synth.make_block(p, B)
+    Q = np.random.default_rng(5).standard_normal((B, B))
+    if lower:
+        Q = np.tril(Q)
+    dX = plan.block(B, X)
+    plan.subspace_rotation(dX, Q, transpose, lower)
+    Xo = [X.copy()]
+    W.subspace_rotation(Xo, Q, transpose, lower)
+    own = p.n_owned
+    assert rel_l2_per_vector(dX.download()[:own], Xo[0][:own]) < 1e-13
+
+
+def test_l2_norms(capi, prob_full):
+    p = prob_full
+    B = 24
+    plan = capi.Plan(p, max_block=B)
+    X = synth.make_block(p, B)
+    n = plan.l2_norms(plan.block(B, X))
+    no = orc.OracleWorld([p]).l2_norms([X])
+    assert np.abs(n - no).max() < 1e-13 * no.max()
+
+
+# ----------------------------------------------------- size-independent properties at scale ----
+def test_properties_at_bench_scale(capi):
+    """C2-shaped problem (order 4, ~1M DoFs would take the oracle minutes): a 12^3 mesh of the same cell
+    shape checked through properties that do not need the oracle: symmetry <HX,Z> = <X,HZ>, linearity,
+    and agreement of two column tilings (B=32 as one tile vs 4 applies of 8 columns)."""
+    p = synth.build_problem(synth.MeshSpec(ncell=(12, 12, 12), p=4))[0]
+    B = 32
+    plan = capi.Plan(p, max_block=B)
+    H = capi.CellOp(plan)
+    X = synth.make_block(p, B, seed=1); Z = synth.make_block(p, B, seed=2)
+    X[p.row_ids.astype(np.int64)] = 0.0; Z[p.row_ids.astype(np.int64)] = 0.0
+    dX, dZ, dHX, dHZ = plan.block(B, X), plan.block(B, Z), plan.block(B), plan.block(B)
+    H.apply(dX, dHX); H.apply(dZ, dHZ)
+    HX, HZ = dHX.download(), dHZ.download()
+    a = np.sum(HX * Z, axis=0); b = np.sum(X * HZ, axis=0)
+    assert np.abs(a - b).max() < 1e-11 * np.abs(a).max()
+    dS = plan.block(B, 2.0 * X - 0.5 * Z); dHS = plan.block(B)
+    H.apply(dS, dHS)
+    assert rel_l2_per_vector(dHS.download(), 2.0 * HX - 0.5 * HZ) < 1e-12
+    for j0 in range(0, B, 8):
+        d8, dh8 = plan.block(8, np.ascontiguousarray(X[:, j0:j0 + 8])), plan.block(8)
+        H.apply(d8, dh8)
+        assert rel_l2_per_vector(dh8.download(), HX[:, j0:j0 + 8]) < 1e-13
