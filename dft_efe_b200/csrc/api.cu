@@ -464,19 +464,26 @@ extern "C"
   int
   hx_memcpy_h2d(void *d, const void *s, size_t bytes)
   {
+    // plan streams are non-blocking (no implicit ordering with the legacy stream these helpers use):
+    // make the helpers device-synchronous on both sides so a harness cannot race a plan's kernels
+    HX_CUDA(cudaDeviceSynchronize());
     HX_CUDA(cudaMemcpy(d, s, bytes, cudaMemcpyHostToDevice));
+    HX_CUDA(cudaDeviceSynchronize());
     return HX_OK;
   }
   int
   hx_memcpy_d2h(void *d, const void *s, size_t bytes)
   {
+    HX_CUDA(cudaDeviceSynchronize());
     HX_CUDA(cudaMemcpy(d, s, bytes, cudaMemcpyDeviceToHost));
     return HX_OK;
   }
   int
   hx_memset_zero(void *d, size_t bytes)
   {
+    HX_CUDA(cudaDeviceSynchronize());
     HX_CUDA(cudaMemset(d, 0, bytes));
+    HX_CUDA(cudaDeviceSynchronize());
     return HX_OK;
   }
 
@@ -508,6 +515,11 @@ extern "C"
         p->own_stream = true;
       }
     int r = build_plan(p, mesh);
+    if (r == HX_OK && cudaDeviceSynchronize() != cudaSuccess) // pageable uploads: DMA must have landed
+      {
+        set_error("cudaDeviceSynchronize failed after plan upload");
+        r = HX_ERR_CUDA;
+      }
     if (r != HX_OK)
       {
         delete p;
@@ -677,6 +689,7 @@ extern "C"
     HX_TRY(op->d_pr_off.upload(cnt));
     HX_TRY(op->d_pr_slots.upload(slots));
     HX_TRY(op->phalo.init(nl->proj_halo, p->max_block));
+    HX_CUDA(cudaDeviceSynchronize());
     op->has_nl = true;
     return HX_OK;
   }
@@ -709,6 +722,11 @@ extern "C"
           }
         else
           r = o->d_enr_block.upload(enr_block, (size_t)o->nE * o->nE);
+      }
+    if (r == HX_OK && cudaDeviceSynchronize() != cudaSuccess)
+      {
+        set_error("cudaDeviceSynchronize failed after operator upload");
+        r = HX_ERR_CUDA;
       }
     if (r != HX_OK)
       {
