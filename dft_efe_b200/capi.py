@@ -20,7 +20,7 @@ EXPORTS = [
     "hx_last_error", "hx_version", "hx_device_count", "hx_set_device", "hx_device_alloc", "hx_device_free",
     "hx_host_alloc_pinned", "hx_host_free_pinned", "hx_memcpy_h2d", "hx_memcpy_d2h", "hx_memset_zero",
     "hx_plan_create", "hx_plan_destroy", "hx_plan_synchronize", "hx_comm_unique_id", "hx_plan_attach_comm",
-    "hx_plan_num_colours", "hx_plan_get_cell_colours", "hx_plan_get_c2p_transpose", "hx_update_ghost_values",
+    "hx_plan_set_scatter_mode", "hx_plan_get_wait_lists", "hx_plan_get_processing_order", "hx_plan_num_colours", "hx_plan_get_cell_colours", "hx_plan_get_c2p_transpose", "hx_update_ghost_values",
     "hx_accumulate_add_locally_owned", "hx_distribute_parent_to_child", "hx_distribute_child_to_parent",
     "hx_set_constrained_nodes_to_zero", "hx_cellop_create", "hx_cellop_set_matrices", "hx_cellop_set_nonlocal",
     "hx_diagop_create", "hx_op_destroy", "hx_op_apply", "hx_op_apply_host", "hx_chebyshev_filter",
@@ -183,6 +183,22 @@ class Plan:
     def attach_comm(self, uid: bytes):
         assert len(uid) == 128
         check(lib().hx_plan_attach_comm(self.h, C.c_char_p(uid)))
+
+    def set_scatter_mode(self, mode: int):
+        check(lib().hx_plan_set_scatter_mode(self.h, C.c_int(mode)))
+
+    def processing_order(self):
+        order = np.zeros(self.prob.n_cells, np.uint32)
+        check(lib().hx_plan_get_processing_order(self.h, order.ctypes.data_as(u32p)))
+        return order
+
+    def wait_lists(self):
+        n = C.c_uint32()
+        check(lib().hx_plan_get_wait_lists(self.h, C.byref(n), None, None))
+        off = np.zeros(self.prob.n_cells + 1, np.uint32)
+        preds = np.zeros(max(n.value, 1), np.uint32)
+        check(lib().hx_plan_get_wait_lists(self.h, C.byref(n), off.ctypes.data_as(u32p), preds.ctypes.data_as(u32p)))
+        return off, preds[:n.value]
 
     def colours(self):
         n = C.c_uint32()

@@ -1,5 +1,6 @@
 // api.cu — host-side logic of libhxb200 and the extern "C" entry points declared in include/hxb200.h.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <map>
@@ -116,7 +117,7 @@ namespace hx
     p->max_block         = m->max_block ? m->max_block : 1;
     HX_CHECK(p->n_owned_classical <= p->n_owned, HX_ERR_INVALID, "n_owned_classical > n_owned");
     HX_CHECK(p->nranks >= 1 && p->rank >= 0 && p->rank < p->nranks, HX_ERR_INVALID, "bad rank/nranks");
-    HX_CHECK(p->n_local < 0x7fffffffu, HX_ERR_INVALID, "too many local rows");
+    HX_CHECK(p->n_local < 0x3fffffffu, HX_ERR_INVALID, "too many local rows");
 
     p->h_ncd.assign(m->num_cell_dofs, m->num_cell_dofs + p->C);
     p->h_cell_off.assign(p->C + 1, 0);
@@ -203,7 +204,7 @@ namespace hx
         if (incidence[r] > SHARED_THRESHOLD)
           {
             shared[r].push_back(p->n_slots);
-            dest[i] = 0x80000000u | p->n_slots;
+            dest[i] = HX_DEST_STAGED | p->n_slots;
             p->n_slots++;
           }
         else
@@ -217,7 +218,6 @@ namespace hx
         sh_off.push_back((uint32_t)sh_slots.size());
       }
     p->n_shared = (uint32_t)sh_rows.size();
-    HX_TRY(p->d_dest.upload(dest));
     HX_TRY(p->d_sh_rows.upload(sh_rows));
     HX_TRY(p->d_sh_off.upload(sh_off));
     HX_TRY(p->d_sh_slots.upload(sh_slots));
@@ -232,7 +232,7 @@ namespace hx
       {
         uint64_t mask = 0;
         for (uint32_t i = p->h_cell_off[c]; i < p->h_cell_off[c + 1]; ++i)
-          if (!(dest[i] & 0x80000000u))
+          if (!(dest[i] & HX_DEST_STAGED))
             mask |= used[p->h_ids[i]];
         HX_CHECK(mask != ~0ull, HX_ERR_UNSUPPORTED, "cell %u needs more than 64 colours", c);
         uint32_t col = 0;
@@ -241,7 +241,7 @@ namespace hx
         p->h_colour[c] = col;
         p->n_colours   = std::max(p->n_colours, col + 1);
         for (uint32_t i = p->h_cell_off[c]; i < p->h_cell_off[c + 1]; ++i)
-          if (!(dest[i] & 0x80000000u))
+          if (!(dest[i] & HX_DEST_STAGED))
             used[p->h_ids[i]] |= (1ull << col);
       }
     // a row listed twice inside one cell would race inside the CTA: reject
@@ -267,6 +267,70 @@ namespace hx
     }
     HX_TRY(p->d_colour_cells.upload(p->h_colour_cells));
 
+    // ---- ordered scatter: processing order, first-touch flags, predecessor (wait) lists ----
+    // Processing order: the caller's cell order (deal.II: p4est z-order) cut into blocks of `order_block`
+    // consecutive cells, each block stably sorted by colour.  Blocks keep the touches of a row close in time
+    // (its X and Y lines stay in L2); the colour sort keeps them far enough apart (>= a colour group) that a
+    // cell practically never stalls on a predecessor that is still contracting.  For every non-shared row the
+    // touching cells form a chain in processing order; a cell waits only for the immediately preceding
+    // toucher of each of its rows (completion is transitive).
+    {
+      uint32_t order_block = 1024;
+      if (const char *e = getenv("HXB200_ORDER_BLOCK"))
+        order_block = (uint32_t)std::max(1, atoi(e));
+      p->h_order.resize(p->C);
+      for (uint32_t c = 0; c < p->C; ++c)
+        p->h_order[c] = c;
+      for (uint32_t b0 = 0; b0 < p->C; b0 += order_block)
+        std::stable_sort(p->h_order.begin() + b0, p->h_order.begin() + std::min(p->C, b0 + order_block),
+                         [&](uint32_t x, uint32_t y) { return p->h_colour[x] < p->h_colour[y]; });
+      std::vector<uint32_t> last(p->n_local, 0xffffffffu); // last processing index that touched the row
+      p->h_wait_off.assign(p->C + 1, 0);
+      p->h_wait_list.clear();
+      std::vector<uint32_t> tmp;
+      for (uint32_t w = 0; w < p->C; ++w)
+        {
+          const uint32_t c = p->h_order[w];
+          tmp.clear();
+          for (uint32_t i = p->h_cell_off[c]; i < p->h_cell_off[c + 1]; ++i)
+            {
+              if (dest[i] & HX_DEST_STAGED)
+                continue;
+              const uint32_t r = p->h_ids[i];
+              if (last[r] == 0xffffffffu)
+                dest[i] |= HX_DEST_FIRST;
+              else if (last[r] != w)
+                tmp.push_back(last[r]);
+              last[r] = w;
+            }
+          std::sort(tmp.begin(), tmp.end());
+          tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
+          p->h_wait_list.insert(p->h_wait_list.end(), tmp.begin(), tmp.end());
+          p->h_wait_off[w + 1] = (uint32_t)p->h_wait_list.size();
+        }
+      std::vector<uint32_t> untouched;
+      for (uint32_t r = 0; r < p->n_local; ++r)
+        if (last[r] == 0xffffffffu && shared.find(r) == shared.end())
+          untouched.push_back(r);
+      p->n_untouched = (uint32_t)untouched.size();
+      HX_TRY(p->d_untouched.upload(untouched));
+      HX_TRY(p->d_order.upload(p->h_order));
+      HX_TRY(p->d_wait_off.upload(p->h_wait_off));
+      HX_TRY(p->d_wait_list.upload(p->h_wait_list));
+      const size_t nflags = (size_t)std::max(p->C, 1u) * ((p->max_block + 7) / 8);
+      HX_TRY(p->d_flags.alloc(nflags));
+      HX_CUDA(cudaMemset(p->d_flags.p, 0, nflags * sizeof(uint32_t)));
+      HX_TRY(p->d_counters.alloc(2));
+      HX_CUDA(cudaMemset(p->d_counters.p, 0, 2 * sizeof(uint32_t)));
+      p->epoch = 0;
+      int dev = 0;
+      HX_CUDA(cudaGetDevice(&dev));
+      HX_CUDA(cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, dev));
+      if (const char *m = getenv("HXB200_SCATTER"))
+        p->scatter_mode = (strcmp(m, "coloured") == 0) ? 1 : 0;
+    }
+    HX_TRY(p->d_dest.upload(dest));
+
     HX_TRY(p->halo.init(m->halo, p->max_block));
     HX_CUDA(cudaEventCreate(&p->ev0));
     HX_CUDA(cudaEventCreate(&p->ev1));
@@ -281,7 +345,10 @@ namespace hx
     if (ugx)
       HX_TRY(halo_update(p, p->halo, X, B));
     HX_TRY(launch_p2c(p, X, B));
-    HX_CUDA(cudaMemsetAsync(Y, 0, (size_t)p->n_local * B * sizeof(double), p->stream));
+    if (p->scatter_mode == 1)
+      HX_CUDA(cudaMemsetAsync(Y, 0, (size_t)p->n_local * B * sizeof(double), p->stream));
+    else // first touchers store instead of add: only rows no cell writes need clearing
+      HX_TRY(launch_zero_rows(p, Y, B, p->d_untouched.p, p->n_untouched));
     if (op->has_nl)
       {
         HX_TRY(launch_nl_phase_a(op, X, B));
@@ -563,6 +630,33 @@ extern "C"
         plan->comm = nullptr;
       }
     return comm_create(&plan->comm, id, plan->nranks, plan->rank);
+  }
+
+  int
+  hx_plan_set_scatter_mode(hx_plan *plan, int mode)
+  {
+    HX_CHECK(plan, HX_ERR_INVALID, "null plan");
+    HX_CHECK(mode == 0 || mode == 1, HX_ERR_INVALID, "scatter mode must be 0 (ordered) or 1 (coloured)");
+    plan->scatter_mode = mode;
+    return HX_OK;
+  }
+  int
+  hx_plan_get_processing_order(hx_plan *plan, uint32_t *order)
+  {
+    HX_CHECK(plan && order, HX_ERR_INVALID, "null argument");
+    memcpy(order, plan->h_order.data(), sizeof(uint32_t) * plan->C);
+    return HX_OK;
+  }
+  int
+  hx_plan_get_wait_lists(hx_plan *plan, uint32_t *nnz, uint32_t *offsets, uint32_t *preds)
+  {
+    HX_CHECK(plan && nnz, HX_ERR_INVALID, "null argument");
+    *nnz = (uint32_t)plan->h_wait_list.size();
+    if (offsets)
+      memcpy(offsets, plan->h_wait_off.data(), sizeof(uint32_t) * (plan->C + 1));
+    if (preds)
+      memcpy(preds, plan->h_wait_list.data(), sizeof(uint32_t) * plan->h_wait_list.size());
+    return HX_OK;
   }
 
   int

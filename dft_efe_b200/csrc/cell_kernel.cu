@@ -1,4 +1,4 @@
-// cell_kernel.cu — the dominant kernel: fused cell gather -> FP64 DMMA cell contraction -> coloured scatter.
+// cell_kernel.cu — the dominant kernel: fused cell gather -> FP64 DMMA cell contraction -> deterministic scatter.
 //
 // Replaces, per reference H.X apply (src/ksdft/KohnShamOperatorContextFE.t.cpp:951-1199):
 //   FECellWiseDataOperations::copyFieldToCellWiseData   (src/basis/FECellWiseDataOperations.t.cpp:58-86)
@@ -6,23 +6,39 @@
 //   AtomCenterNonLocalOpContextFE::applyCOnVCconjtransX  (src/basis/AtomCenterNonLocalOpContextFE.t.cpp:998-1036)
 //   FECellWiseDataOperations::addCellWiseDataToFieldData (src/basis/FECellWiseDataOperations.t.cpp:87-153)
 //
-// Layout / algorithm (B200, sm_100a):
+// Design (B200, sm_100a):
 //   * tcgen05 has no FP64 kind; the FP64 tensor path on sm_100a is mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4).
-//   * One CTA = one cell x one tile of BT = 8*NT wavefunction columns.  y_c[j,v] = sum_k A_c[j,k] xk[k,v] with
-//     A_c = [H_c | C_c^T] (the nonlocal C.(V C^H X) term is a K-extension: rows n..n+nProj of the B operand are
-//     the V-scaled projector coefficients), so projector cells cost no extra pass.
-//   * A_c is pre-tiled once per reinit into DMMA-fragment-major order (pack_kernel): the 32 doubles of one 8x4
-//     A fragment are contiguous, so every warp streams its row panel from HBM with perfectly coalesced 256-B
-//     loads straight into registers (register prefetch ring, depth PD), no shared-memory staging of A:
-//     each A element is used by exactly one warp of one CTA.
-//   * The gathered x_c tile lives in shared memory (row stride BT+4 doubles -> conflict-free B-fragment reads).
-//   * Accumulators stay in registers and are scattered with 16-B read-modify-writes; cells of one launch have
-//     the same colour (share no DoF), so there are no atomics and the result is bitwise reproducible.  Rows
-//     shared by many cells (enrichment DoFs) are written to a staging slot and reduced in fixed order afterwards.
+//   * y_c[j,v] = sum_k A_c[j,k] xk[k,v] with A_c = [H_c | C_c^T]: the nonlocal C.(V C^H X) term is a K-extension
+//     (rows n..n+nProj of the B operand are the V-scaled projector coefficients), so projector cells cost no
+//     extra pass.
+//   * A_c is pre-tiled once per reinit (pack_kernel) into the exact order the kernel consumes it: per cell a
+//     linear stream of "stages"; stage (chunk, kc) holds, for the <= 8*MTW m-tiles of the chunk and KC k-steps, the
+//     32-double DMMA A-fragments.  One cp.async.bulk (TMA, 1-D) per stage moves it into a shared-memory ring
+//     guarded by full/empty mbarriers; compute warps read their fragments with conflict-free 256-B LDS.
+//   * Persistent CTAs (grid = SMs x CTAs/SM), warp-specialised: 8 DMMA warps, 1 A-stream warp (claims work
+//     items from a global counter and issues the bulk copies, running ahead across items), 1 gather warp
+//     (cp.async 16-B zero-filling gathers of the cell's rows of X / VCX into a padded shared tile).
+//   * Deterministic scatter without colour launches: work items are claimed in processing order; a cell adds
+//     its rows into Y only after the immediately preceding toucher of each row has published an epoch stamp
+//     (release/acquire through L2).  Per row the summation order is therefore ascending cell order - the
+//     reference's CPU order - and bitwise reproducible.  The first toucher of a row stores instead of adding, so
+//     Y needs no memset.  Neighbouring cells run close in time, so their shared rows of X and Y hit L2.
+//     Rows shared by many cells (enrichment DoFs) go to a staging slot and are reduced in fixed order afterwards.
+//   * The one-launch-per-colour variant (cells of one launch share no row) is kept as scatter_mode 1
+//     (HXB200_SCATTER=coloured) for comparison.
 #include "hx_internal.h"
 
 namespace hx
 {
+  constexpr int KC            = 4;               // k-steps (of 4) per stage
+  constexpr int STAGE_DOUBLES = 16 * KC * 32;    // max stage: 16 m-tiles x KC k-steps x 32 doubles = 16 KB
+  constexpr int CWARPS        = 8;               // DMMA warps
+  constexpr int CTHREADS      = CWARPS * 32;
+  constexpr int V2_THREADS    = CTHREADS + 64;   // + A-stream warp + gather warp
+  constexpr int QD            = 8;               // item queue depth (A-stream warp -> gather warp)
+  constexpr int MAX_STAGES    = 8;
+  constexpr uint32_t ITEM_END = 0xffffffffu;
+
   struct CellArgs
   {
     const double *  X;
@@ -34,9 +50,18 @@ namespace hx
     const uint32_t *ids;
     const uint32_t *dest;
     const uint32_t *pids;
-    const uint32_t *cell_list;
+    const uint32_t *cell_list; // coloured mode: cells of this launch; ordered mode: processing order
+    const uint32_t *wait_off;
+    const uint32_t *wait_list;
+    uint32_t *      flags;
+    uint32_t *      counters;
+    uint32_t        epoch;
+    uint32_t        nItems;
     uint32_t        B;
     uint32_t        nBt;
+    uint32_t        xtile_doubles;
+    uint32_t        nStages;
+    uint32_t        nXbuf;
   };
 
   __device__ __forceinline__ void
@@ -55,17 +80,521 @@ namespace hx
     return v;
   }
 
+  // ---- mbarrier / bulk-copy / cp.async PTX wrappers ------------------------------------------------
+  __device__ __forceinline__ uint32_t
+  smem_u32(const void *p)
+  {
+    return (uint32_t)__cvta_generic_to_shared(p);
+  }
+  __device__ __forceinline__ void
+  mbar_init(uint32_t bar, uint32_t count)
+  {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+  }
+  __device__ __forceinline__ void
+  mbar_arrive(uint32_t bar)
+  {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+  }
+  __device__ __forceinline__ void
+  mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes)
+  {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+  }
+  __device__ __forceinline__ void
+  mbar_wait(uint32_t bar, uint32_t parity)
+  {
+    asm volatile("{\n"
+                 ".reg .pred p;\n"
+                 "WAIT_%=:\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                 "@p bra DONE_%=;\n"
+                 "bra WAIT_%=;\n"
+                 "DONE_%=:\n"
+                 "}" ::"r"(bar),
+                 "r"(parity)
+                 : "memory");
+  }
+  __device__ __forceinline__ void
+  bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+  {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+  }
+  __device__ __forceinline__ void
+  bulk_g2s_hint(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar, uint64_t policy)
+  {
+    asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+      "l"(src), "r"(bytes), "r"(bar), "l"(policy)
+      : "memory");
+  }
+  __device__ __forceinline__ void
+  cp_async_zfill16(uint32_t dst, const void *src, uint32_t src_bytes)
+  {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+  }
+  __device__ __forceinline__ void
+  cp_async_zfill8(uint32_t dst, const void *src, uint32_t src_bytes)
+  {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+  }
+  __device__ __forceinline__ void
+  cp_async_mbar_arrive_noinc(uint32_t bar)
+  {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+  }
+  __device__ __forceinline__ uint32_t
+  ld_volatile_shared(uint32_t addr)
+  {
+    uint32_t v;
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+  }
+  __device__ __forceinline__ void
+  st_volatile_shared(uint32_t addr, uint32_t v)
+  {
+    asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+  }
+  __device__ __forceinline__ uint32_t
+  ld_acquire_gpu(const uint32_t *p)
+  {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+  }
+  __device__ __forceinline__ void
+  st_release_gpu(uint32_t *p, uint32_t v)
+  {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+  }
+  __device__ __forceinline__ void
+  bar_compute()
+  {
+    asm volatile("bar.sync 1, %0;" ::"n"(CTHREADS) : "memory");
+  }
+
+  // offset (doubles, relative to the cell's packed base) of stage (chunk starting at m-tile mc, k-chunk kc)
+  __device__ __host__ __forceinline__ size_t
+  stage_offset(int mc, int mtc, int kc, int nKC)
+  {
+    return ((size_t)mc * nKC + (size_t)mtc * kc) * (KC * 32);
+  }
+
+  // shared-memory header of the ordered kernel (bytes from the dynamic smem base, 128-B aligned)
+  constexpr int SM_FULL   = 0;   // MAX_STAGES x 8
+  constexpr int SM_EMPTY  = 64;  // MAX_STAGES x 8
+  constexpr int SM_XFULL  = 128; // 2 x 8
+  constexpr int SM_XEMPTY = 144; // 2 x 8
+  constexpr int SM_QUEUE  = 256; // QD x 32   (A-stream warp -> gather warp)
+  constexpr int SM_XITEM  = 512; // 2 x 32    (gather warp -> DMMA warps, one per X buffer)
+  constexpr int SM_HEADER = 640;
+
+  // what the three roles need to know about a work item; loaded once (A-stream warp) and handed on in smem
+  struct ItemInfo
+  {
+    uint32_t tag; // item index + 1; 0 = slot empty; ITEM_END = no more work
+    uint32_t ids_off, n, nproj, proj_off, wait_off, nwait, pad;
+  };
+  __device__ __forceinline__ void
+  item_store(uint32_t addr, const ItemInfo &it)
+  {
+    asm volatile("st.volatile.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr + 16), "r"(it.proj_off), "r"(it.wait_off),
+                 "r"(it.nwait), "r"(it.pad)
+                 : "memory");
+    asm volatile("st.volatile.shared.v2.u32 [%0], {%1,%2};" ::"r"(addr + 8), "r"(it.n), "r"(it.nproj) : "memory");
+    st_volatile_shared(addr + 4, it.ids_off);
+    __threadfence_block();
+    st_volatile_shared(addr, it.tag);
+  }
+  __device__ __forceinline__ void
+  item_load_payload(uint32_t addr, ItemInfo &it)
+  {
+    __threadfence_block();
+    it.ids_off = ld_volatile_shared(addr + 4);
+    asm volatile("ld.volatile.shared.v2.u32 {%0,%1}, [%2];" : "=r"(it.n), "=r"(it.nproj) : "r"(addr + 8) : "memory");
+    asm volatile("ld.volatile.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(it.proj_off), "=r"(it.wait_off), "=r"(it.nwait), "=r"(it.pad)
+                 : "r"(addr + 16)
+                 : "memory");
+  }
+
+  // =================================================================================================
+  // Ordered persistent kernel
+  // =================================================================================================
+  template <int NT, int MTW, bool VEC, int MINB>
+  __global__ void __launch_bounds__(V2_THREADS, MINB) cell_apply_ordered_kernel(const CellArgs a)
+  {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int  BT  = NT * 8;
+    constexpr int  LDX = BT + 4;
+    constexpr int  MPC = CWARPS * MTW; // m-tiles per chunk
+    const int      tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t sbase = smem_u32(smem_raw);
+    double *       ring   = reinterpret_cast<double *>(smem_raw + SM_HEADER);
+    double *       xtiles = ring + (size_t)a.nStages * STAGE_DOUBLES;
+    const uint32_t NS = a.nStages, NXB = a.nXbuf;
+
+    if (tid == 0)
+      {
+        for (uint32_t s = 0; s < NS; ++s)
+          {
+            mbar_init(sbase + SM_FULL + 8 * s, 1);
+            mbar_init(sbase + SM_EMPTY + 8 * s, CWARPS);
+          }
+        for (uint32_t b = 0; b < NXB; ++b)
+          {
+            mbar_init(sbase + SM_XFULL + 8 * b, 32);
+            mbar_init(sbase + SM_XEMPTY + 8 * b, CWARPS);
+          }
+        for (int q = 0; q < QD; ++q)
+          st_volatile_shared(sbase + SM_QUEUE + 32 * q, 0u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      }
+    __syncthreads();
+
+    if (warp == CWARPS)
+      {
+        // ------------------------------ A-stream warp (one elected lane) ------------------------------
+        if (lane == 0)
+          {
+            uint32_t stage = 0, ph = 0;
+            // a cell matrix is read once per apply when one column tile covers B: keep it from evicting
+            // the X / Y lines that neighbouring cells are about to reuse
+            uint64_t evict_first;
+            asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(evict_first));
+            const bool once = (a.nBt == 1);
+            // the next item is claimed (and its metadata fetched) while the current one streams
+            uint32_t w = atomicAdd(a.counters, 1u);
+            CellMeta cm;
+            uint32_t wo = 0, nwait = 0;
+            if (w < a.nItems)
+              {
+                const uint32_t pidx = w / a.nBt;
+                cm                  = a.meta[a.cell_list[pidx]];
+                wo                  = a.wait_off[pidx];
+                nwait               = a.wait_off[pidx + 1] - wo;
+              }
+            for (uint32_t it = 0;; ++it)
+              {
+                const uint32_t slot = sbase + SM_QUEUE + 32 * (it % QD);
+                while (ld_volatile_shared(slot) != 0u)
+                  {
+                  }
+                if (w >= a.nItems)
+                  {
+                    st_volatile_shared(slot, ITEM_END);
+                    break;
+                  }
+                ItemInfo info;
+                info.tag = w + 1u, info.ids_off = cm.ids_off, info.n = cm.n, info.nproj = cm.nproj;
+                info.proj_off = cm.proj_off, info.wait_off = wo, info.nwait = nwait, info.pad = 0;
+                item_store(slot, info);
+                const int     nKC = ((int)(cm.n + cm.nproj) + 4 * KC - 1) / (4 * KC);
+                const int     nMt = ((int)cm.n + 7) >> 3;
+                const double *src = a.packed + cm.h_off;
+                // claim + prefetch the next item
+                w = atomicAdd(a.counters, 1u);
+                if (w < a.nItems)
+                  {
+                    const uint32_t pidx = w / a.nBt;
+                    cm                  = a.meta[a.cell_list[pidx]];
+                    wo                  = a.wait_off[pidx];
+                    nwait               = a.wait_off[pidx + 1] - wo;
+                  }
+                for (int mc = 0; mc < nMt; mc += MPC)
+                  {
+                    const int      mtc   = min(MPC, nMt - mc);
+                    const uint32_t bytes = (uint32_t)mtc * KC * 256u;
+                    for (int kc = 0; kc < nKC; ++kc)
+                      {
+                        mbar_wait(sbase + SM_EMPTY + 8 * stage, ph ^ 1u);
+                        mbar_arrive_expect_tx(sbase + SM_FULL + 8 * stage, bytes);
+                        const uint32_t dst = sbase + SM_HEADER + stage * (STAGE_DOUBLES * 8);
+                        if (once)
+                          bulk_g2s_hint(dst, src, bytes, sbase + SM_FULL + 8 * stage, evict_first);
+                        else
+                          bulk_g2s(dst, src, bytes, sbase + SM_FULL + 8 * stage);
+                        src += bytes / 8;
+                        if (++stage == NS)
+                          {
+                            stage = 0;
+                            ph ^= 1u;
+                          }
+                      }
+                  }
+              }
+          }
+      }
+    else if (warp == CWARPS + 1)
+      {
+        // ------------------------------------ gather warp ------------------------------------
+        const uint32_t xs0 = smem_u32(xtiles);
+        constexpr int  CPR = VEC ? BT / 2 : BT; // copies per row (<= 32)
+        constexpr int  RPI = 32 / CPR;          // rows per warp instruction
+        const int      cc  = lane % CPR;
+        const int      rr  = lane / CPR;
+        for (uint32_t it = 0;; ++it)
+          {
+            const uint32_t slot = sbase + SM_QUEUE + 32 * (it % QD);
+            uint32_t       tag;
+            while ((tag = ld_volatile_shared(slot)) == 0u)
+              {
+              }
+            ItemInfo info = {};
+            info.tag      = tag;
+            if (tag != ITEM_END)
+              item_load_payload(slot, info);
+            __syncwarp();
+            if (lane == 0)
+              st_volatile_shared(slot, 0u);
+            const uint32_t buf = it % NXB, use = it / NXB;
+            const uint32_t xi  = sbase + SM_XITEM + 32 * buf;
+            // row codes of the first 32 rows: fetched before waiting for the tile to be free
+            const int n = (int)info.n, ktot = n + (int)info.nproj;
+            auto      row_code = [&](int k) -> uint32_t {
+              if (tag == ITEM_END || k >= ktot)
+                return 0xffffffffu; // zero row
+              if (k < n)
+                return __ldg(a.ids + info.ids_off + k);
+              return 0x80000000u | __ldg(a.pids + info.proj_off + (k - n));
+            };
+            uint32_t code = row_code(lane);
+            mbar_wait(sbase + SM_XEMPTY + 8 * buf, (use & 1u) ^ 1u);
+            if (tag == ITEM_END)
+              {
+                if (lane == 0)
+                  st_volatile_shared(xi, ITEM_END);
+                __syncwarp();
+                mbar_arrive(sbase + SM_XFULL + 8 * buf);
+                break;
+              }
+            if (lane == 0)
+              item_store(xi, info);
+            __syncwarp();
+            const uint32_t b0 = ((tag - 1u) % a.nBt) * BT;
+            const int      Kp = (ktot + 4 * KC - 1) / (4 * KC) * (4 * KC);
+            const uint32_t xs = xs0 + buf * a.xtile_doubles * 8u;
+            const uint32_t col  = b0 + (VEC ? cc * 2 : cc);
+            const bool     colok = col < a.B;
+            for (int kb = 0; kb < Kp; kb += 32)
+              {
+                const uint32_t code_next = (kb + 32 < Kp) ? row_code(kb + 32 + lane) : 0xffffffffu;
+                const int      rows      = min(32, Kp - kb);
+                for (int r = 0; r < rows; r += RPI)
+                  {
+                    const uint32_t c   = __shfl_sync(0xffffffffu, code, r + rr);
+                    const bool     ok  = (c != 0xffffffffu) && colok;
+                    const double * src = a.X;
+                    if (ok)
+                      src = ((c & 0x80000000u) ? a.VCX + (size_t)(c & 0x7fffffffu) * a.B : a.X + (size_t)c * a.B) + col;
+                    const uint32_t dst = xs + ((uint32_t)(kb + r + rr) * LDX + (VEC ? cc * 2 : cc)) * 8u;
+                    if (VEC)
+                      cp_async_zfill16(dst, src, ok ? 16u : 0u);
+                    else
+                      cp_async_zfill8(dst, src, ok ? 8u : 0u);
+                  }
+                code = code_next;
+              }
+            cp_async_mbar_arrive_noinc(sbase + SM_XFULL + 8 * buf);
+          }
+      }
+    else
+      {
+        // ------------------------------------ DMMA warps ------------------------------------
+        uint32_t stage = 0, ph = 0;
+        for (uint32_t it = 0;; ++it)
+          {
+            const uint32_t buf = it % NXB, use = it / NXB;
+            mbar_wait(sbase + SM_XFULL + 8 * buf, use & 1u);
+            const uint32_t xi = sbase + SM_XITEM + 32 * buf;
+            ItemInfo       info;
+            info.tag = ld_volatile_shared(xi);
+            if (info.tag == ITEM_END)
+              break;
+            item_load_payload(xi, info);
+            const uint32_t w    = info.tag - 1u;
+            const uint32_t bt   = w % a.nBt;
+            const int      n    = (int)info.n;
+            const int      nKC  = (n + (int)info.nproj + 4 * KC - 1) / (4 * KC);
+            const int      nMt  = (n + 7) >> 3;
+            const uint32_t B    = a.B;
+            const uint32_t b0   = bt * BT;
+            const double * xs   = xtiles + (size_t)buf * a.xtile_doubles;
+            const double * xrow = xs + (size_t)(lane & 3) * LDX + (lane >> 2);
+            const uint32_t wo = info.wait_off, nwait = info.nwait;
+            // predecessor stamps to poll (prefetch the addresses' indices early)
+            uint32_t pred = 0;
+            if ((uint32_t)tid < nwait)
+              pred = __ldg(a.wait_list + wo + tid);
+
+            for (int mc = 0; mc < nMt; mc += MPC)
+              {
+                const int  mtc    = min(MPC, nMt - mc);
+                const int  mtl0   = warp * MTW; // first local m-tile of this warp
+                const bool active = mtl0 < mtc;
+                // destinations of this thread's rows (latency hidden behind the k loop)
+                uint32_t dst_code[MTW];
+#pragma unroll
+                for (int j = 0; j < MTW; ++j)
+                  {
+                    const int r = (mc + mtl0 + j) * 8 + (lane >> 2);
+                    dst_code[j] = (r < n) ? __ldg(a.dest + info.ids_off + r) : 0xffffffffu;
+                  }
+                int aoff[MTW];
+#pragma unroll
+                for (int j = 0; j < MTW; ++j)
+                  aoff[j] = min(mtl0 + j, mtc - 1) * (KC * 32) + lane;
+
+                double acc[MTW][NT][2];
+#pragma unroll
+                for (int j = 0; j < MTW; ++j)
+#pragma unroll
+                  for (int t = 0; t < NT; ++t)
+                    acc[j][t][0] = acc[j][t][1] = 0.0;
+
+                for (int kc = 0; kc < nKC; ++kc)
+                  {
+                    mbar_wait(sbase + SM_FULL + 8 * stage, ph);
+                    if (active)
+                      {
+                        const double *As = ring + (size_t)stage * STAGE_DOUBLES;
+                        const double *xr = xrow + (size_t)kc * (4 * KC) * LDX;
+#pragma unroll
+                        for (int ks = 0; ks < KC; ++ks)
+                          {
+                            double af[MTW], bf[NT];
+#pragma unroll
+                            for (int j = 0; j < MTW; ++j)
+                              af[j] = As[aoff[j] + ks * 32];
+#pragma unroll
+                            for (int t = 0; t < NT; ++t)
+                              bf[t] = xr[(size_t)ks * 4 * LDX + t * 8];
+#pragma unroll
+                            for (int j = 0; j < MTW; ++j)
+#pragma unroll
+                              for (int t = 0; t < NT; ++t)
+                                dmma884(acc[j][t][0], acc[j][t][1], af[j], bf[t]);
+                          }
+                      }
+                    __syncwarp();
+                    if (lane == 0)
+                      mbar_arrive(sbase + SM_EMPTY + 8 * stage);
+                    if (++stage == NS)
+                      {
+                        stage = 0;
+                        ph ^= 1u;
+                      }
+                  }
+                if (mc + MPC >= nMt)
+                  {
+                    // the X tile is no longer needed: let the gather warp refill it
+                    __syncwarp();
+                    if (lane == 0)
+                      mbar_arrive(sbase + SM_XEMPTY + 8 * buf);
+                  }
+                if (mc == 0 && nwait)
+                  {
+                    // wait until the preceding toucher of every row of this cell has scattered; the acquire
+                    // loads + the CTA barrier order every compute thread's RMW after the predecessors' stores
+                    for (uint32_t i = tid; i < nwait; i += CTHREADS)
+                      {
+                        const uint32_t  pi = (i == (uint32_t)tid) ? pred : __ldg(a.wait_list + wo + i);
+                        const uint32_t *f  = a.flags + (size_t)pi * a.nBt + bt;
+                        while (ld_acquire_gpu(f) != a.epoch)
+                          {
+                          }
+                      }
+                    bar_compute();
+                  }
+                // ---- scatter-add (ordered: plain RMW through L2; shared rows: staging slot) ----
+                if (active)
+                  {
+#pragma unroll
+                    for (int j = 0; j < MTW; ++j)
+                      {
+                        const uint32_t d = dst_code[j];
+                        if (d != 0xffffffffu)
+                          {
+                            const bool staged = (d & HX_DEST_STAGED) != 0;
+                            const bool add    = !staged && !(d & HX_DEST_FIRST);
+                            double *   dst    = staged ? a.stage + (size_t)(d & 0x7fffffffu) * B : a.Y + (size_t)HX_DEST_ROW(d) * B;
+                            if (VEC)
+                              {
+                                double2 y[NT];
+#pragma unroll
+                                for (int t = 0; t < NT; ++t)
+                                  {
+                                    const uint32_t col = b0 + t * 8 + (lane & 3) * 2;
+                                    y[t]               = make_double2(0.0, 0.0);
+                                    if (add && col < B)
+                                      y[t] = __ldcg(reinterpret_cast<const double2 *>(dst + col));
+                                  }
+#pragma unroll
+                                for (int t = 0; t < NT; ++t)
+                                  {
+                                    const uint32_t col = b0 + t * 8 + (lane & 3) * 2;
+                                    if (col < B)
+                                      {
+                                        y[t].x += acc[j][t][0];
+                                        y[t].y += acc[j][t][1];
+                                        __stcg(reinterpret_cast<double2 *>(dst + col), y[t]);
+                                      }
+                                  }
+                              }
+                            else
+                              {
+#pragma unroll
+                                for (int t = 0; t < NT; ++t)
+                                  {
+                                    const uint32_t col = b0 + t * 8 + (lane & 3) * 2;
+                                    if (col < B)
+                                      __stcg(dst + col, (add ? __ldcg(dst + col) : 0.0) + acc[j][t][0]);
+                                    if (col + 1 < B)
+                                      __stcg(dst + col + 1, (add ? __ldcg(dst + col + 1) : 0.0) + acc[j][t][1]);
+                                  }
+                              }
+                          }
+                      }
+                  }
+              }
+            // publish completion of this (cell, column tile): the CTA barrier orders every compute thread's
+            // stores before thread 0's release store (cumulative at gpu scope)
+            bar_compute();
+            if (tid == 0)
+              st_release_gpu(a.flags + w, a.epoch);
+          }
+        // last CTA out resets the work counters for the next launch
+        if (tid == 0)
+          {
+            __threadfence();
+            const uint32_t done = atomicAdd(a.counters + 1, 1u);
+            if (done == gridDim.x - 1)
+              {
+                a.counters[0] = 0u;
+                a.counters[1] = 0u;
+                __threadfence();
+              }
+          }
+      }
+  }
+
+  // =================================================================================================
+  // One launch per colour (scatter_mode 1): one CTA = one cell x one column tile, A streamed from HBM
+  // straight into registers.
+  // =================================================================================================
   constexpr int CELL_THREADS = 256;
   constexpr int CELL_WARPS   = CELL_THREADS / 32;
-  constexpr int MTW          = 2; // m-tiles (8 rows each) per warp per chunk
   constexpr int PD           = 4; // register prefetch depth (k-steps) of the A stream
 
-  template <int NT, bool VEC, int MINB>
-  __global__ void __launch_bounds__(CELL_THREADS, MINB) cell_apply_kernel(const CellArgs a)
+  template <int NT, int MTW, bool VEC, int MINB>
+  __global__ void __launch_bounds__(CELL_THREADS, MINB) cell_apply_coloured_kernel(const CellArgs a)
   {
     extern __shared__ __align__(16) double xs[];
     constexpr int BT  = NT * 8;
     constexpr int LDX = BT + 4;
+    constexpr int MPC = CELL_WARPS * MTW;
     const int     tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     const uint32_t bt   = blockIdx.x % a.nBt;
@@ -74,7 +603,8 @@ namespace hx
     const CellMeta cm   = a.meta[cell];
     const int      n    = (int)cm.n;
     const int      ktot = n + (int)cm.nproj;
-    const int      Kp   = (ktot + 3) & ~3;
+    const int      nKC  = (ktot + 4 * KC - 1) / (4 * KC);
+    const int      Kp   = nKC * 4 * KC;
     const int      nK   = Kp >> 2;
     const int      nMt  = (n + 7) >> 3;
     const uint32_t B    = a.B;
@@ -133,21 +663,22 @@ namespace hx
     }
     __syncthreads();
 
-    // ---- contraction: each warp owns MTW m-tiles per chunk of CELL_WARPS*MTW tiles ----
     const double *Abase = a.packed + cm.h_off + lane;
     const double *xrow  = xs + (size_t)(lane & 3) * LDX + (lane >> 2);
-    for (int mc = 0; mc < nMt; mc += CELL_WARPS * MTW)
+    for (int mc = 0; mc < nMt; mc += MPC)
       {
-        const int mt0 = mc + warp * MTW;
-        if (mt0 >= nMt)
+        const int mtc  = min(MPC, nMt - mc);
+        const int mtl0 = warp * MTW;
+        if (mtl0 >= mtc)
           break;
+        // fragment (m-tile mtl, k-step k) of this chunk sits at stage_offset(mc,mtc,k/KC) + (mtl*KC + k%KC)*32
         const double *Ap[MTW];
 #pragma unroll
         for (int j = 0; j < MTW; ++j)
-          {
-            const int mt = min(mt0 + j, nMt - 1);
-            Ap[j]        = Abase + (size_t)mt * nK * 32;
-          }
+          Ap[j] = Abase + stage_offset(mc, mtc, 0, nKC) + (size_t)min(mtl0 + j, mtc - 1) * (KC * 32);
+        const size_t kc_stride = (size_t)mtc * (KC * 32);
+        auto         frag      = [&](int j, int k) { return Ap[j] + (size_t)(k / KC) * kc_stride + (size_t)(k % KC) * 32; };
+
         double acc[MTW][NT][2];
 #pragma unroll
         for (int j = 0; j < MTW; ++j)
@@ -160,7 +691,7 @@ namespace hx
         for (int i = 0; i < PD; ++i)
 #pragma unroll
           for (int j = 0; j < MTW; ++j)
-            af[i][j] = (i < nK) ? ld_stream(Ap[j] + (size_t)i * 32) : 0.0;
+            af[i][j] = (i < nK) ? ld_stream(frag(j, i)) : 0.0;
 
         for (int ks = 0; ks < nK; ks += PD)
           {
@@ -179,7 +710,7 @@ namespace hx
                       {
 #pragma unroll
                         for (int j = 0; j < MTW; ++j)
-                          af[i][j] = ld_stream(Ap[j] + (size_t)kn * 32);
+                          af[i][j] = ld_stream(frag(j, kn));
                       }
                     const double *xr = xrow + (size_t)k * 4 * LDX;
                     double        b[NT];
@@ -195,16 +726,17 @@ namespace hx
               }
           }
 
-        // ---- scatter-add (colour-exclusive rows: plain RMW; shared rows: staging slot) ----
+        // ---- scatter-add (colour-exclusive rows: plain RMW on the zeroed Y; shared rows: staging slot) ----
 #pragma unroll
         for (int j = 0; j < MTW; ++j)
           {
-            const int r = (mt0 + j) * 8 + (lane >> 2);
-            if (mt0 + j < nMt && r < n)
+            const int r = (mc + mtl0 + j) * 8 + (lane >> 2);
+            if (mtl0 + j < mtc && r < n)
               {
-                const uint32_t d   = __ldg(a.dest + cm.ids_off + r);
-                double *       dst = (d & 0x80000000u) ? a.stage + (size_t)(d & 0x7fffffffu) * B : a.Y + (size_t)d * B;
-                const bool     add = !(d & 0x80000000u);
+                const uint32_t d      = __ldg(a.dest + cm.ids_off + r);
+                const bool     staged = (d & HX_DEST_STAGED) != 0;
+                double *       dst    = staged ? a.stage + (size_t)(d & 0x7fffffffu) * B : a.Y + (size_t)HX_DEST_ROW(d) * B;
+                const bool     add    = !staged;
 #pragma unroll
                 for (int t = 0; t < NT; ++t)
                   {
@@ -234,8 +766,9 @@ namespace hx
   }
 
   // -------------------------------------------------------------------------------------------------
-  // pack: raw row-major n x n cell matrices (+ column-major nProj x n projector matrices) -> fragment-major
-  // tiles.  packed[((mt*nK + ks)*32 + lane)] = A[mt*8 + lane/4][ks*4 + lane%4].
+  // pack: raw row-major n x n cell matrices (+ column-major nProj x n projector matrices) -> the stage stream.
+  // For chunk mc (mtc m-tiles), k-chunk kc, local m-tile mtl, k-step ks, lane:
+  //   packed[stage_offset(mc,mtc,kc) + ((mtl*KC + ks)*32 + lane)] = A[(mc+mtl)*8 + lane/4][(kc*KC + ks)*4 + lane%4]
   __global__ void
   pack_kernel(const double *            raw,
               unsigned long long        raw_base,
@@ -244,22 +777,31 @@ namespace hx
               const unsigned long long *c_off,
               const CellMeta *          meta,
               double *                  packed,
-              uint32_t                  cell_begin)
+              uint32_t                  cell_begin,
+              int                       mpc)
   {
     const uint32_t cell = cell_begin + blockIdx.x;
     const CellMeta cm   = meta[cell];
     const int      n = (int)cm.n, np = (int)cm.nproj;
-    const int      Kp = (n + np + 3) & ~3, nK = Kp >> 2, Mp = (n + 7) & ~7;
-    const double * H  = raw + (raw_off[cell] - raw_base);
-    const double * Cc = (np > 0) ? cellC + c_off[cell] : nullptr;
+    const int      nKC = (n + np + 4 * KC - 1) / (4 * KC), nMt = (n + 7) >> 3;
+    const double * H   = raw + (raw_off[cell] - raw_base);
+    const double * Cc  = (np > 0) ? cellC + c_off[cell] : nullptr;
     double *       out = packed + cm.h_off;
-    const size_t   tot = (size_t)Mp * Kp;
+    const size_t   tot = (size_t)nMt * nKC * KC * 32;
     for (size_t idx = threadIdx.x; idx < tot; idx += blockDim.x)
       {
-        const int lane = (int)(idx & 31);
-        const size_t f = idx >> 5;
-        const int ks = (int)(f % nK), mt = (int)(f / nK);
-        const int r = mt * 8 + (lane >> 2), k = ks * 4 + (lane & 3);
+        // decode idx in stream order
+        const size_t per_chunk = (size_t)mpc * nKC * KC * 32;
+        const int    ch        = (int)(idx / per_chunk);
+        const int    mc        = ch * mpc;
+        const int    mtc       = min(mpc, nMt - mc);
+        size_t       rem       = idx - (size_t)ch * per_chunk;
+        const int    kc        = (int)(rem / ((size_t)mtc * KC * 32));
+        rem -= (size_t)kc * mtc * KC * 32;
+        const int mtl  = (int)(rem / (KC * 32));
+        const int ks   = (int)((rem / 32) % KC);
+        const int lane = (int)(rem & 31);
+        const int r = (mc + mtl) * 8 + (lane >> 2), k = (kc * KC + ks) * 4 + (lane & 3);
         double    v = 0.0;
         if (r < n)
           {
@@ -276,8 +818,10 @@ namespace hx
   pack_cell_matrices(hx_op *op, const double *raw, int on_device)
   {
     hx_plan *p = op->plan;
-    // packed offsets
-    size_t tot = 0;
+    // m-tiles per warp: small cells (n <= 64) keep all 8 DMMA warps busy with one m-tile each
+    op->mtw       = (p->max_n <= 64) ? 1 : 2;
+    const int mpc = CWARPS * op->mtw;
+    size_t    tot = 0;
     op->h_meta.resize(p->C);
     uint32_t poff = 0;
     op->max_kp = op->max_mp = 0;
@@ -289,7 +833,7 @@ namespace hx
         m.nproj     = op->has_nl ? op->h_ncp[c] : 0;
         m.proj_off  = poff;
         poff += m.nproj;
-        const uint32_t Kp = (m.n + m.nproj + 3) & ~3u, Mp = (m.n + 7) & ~7u;
+        const uint32_t Kp = (m.n + m.nproj + 4 * KC - 1) / (4 * KC) * (4 * KC), Mp = (m.n + 7) & ~7u;
         m.h_off = tot;
         tot += (size_t)Kp * Mp;
         op->max_kp = Kp > op->max_kp ? Kp : op->max_kp;
@@ -307,13 +851,14 @@ namespace hx
       raw_off[c + 1] = raw_off[c] + (unsigned long long)p->h_ncd[c] * p->h_ncd[c];
     DevBuf<unsigned long long> d_raw_off;
     HX_TRY(d_raw_off.upload(raw_off.data(), raw_off.size()));
+    HX_CUDA(cudaDeviceSynchronize());
 
     if (on_device)
       {
         if (p->C)
           {
             pack_kernel<<<p->C, 256, 0, p->stream>>>(raw, 0ull, d_raw_off.p, op->d_cell_c.p, op->d_c_off.p,
-                                                     op->d_meta.p, op->d_packed.p, 0);
+                                                     op->d_meta.p, op->d_packed.p, 0, mpc);
             p->launches++;
           }
         HX_CUDA(cudaGetLastError());
@@ -335,7 +880,7 @@ namespace hx
               HX_TRY(tmp.alloc(cnt));
             HX_CUDA(cudaMemcpyAsync(tmp.p, raw + raw_off[c0], cnt * sizeof(double), cudaMemcpyHostToDevice, p->stream));
             pack_kernel<<<c1 - c0, 256, 0, p->stream>>>(tmp.p, raw_off[c0], d_raw_off.p, op->d_cell_c.p,
-                                                        op->d_c_off.p, op->d_meta.p, op->d_packed.p, c0);
+                                                        op->d_c_off.p, op->d_meta.p, op->d_packed.p, c0, mpc);
             p->launches++;
             HX_CUDA(cudaGetLastError());
             HX_CUDA(cudaStreamSynchronize(p->stream));
@@ -346,29 +891,35 @@ namespace hx
     return HX_OK;
   }
 
-  template <int NT, bool VEC, int MINB>
+  // ---- event bracket around the cell-kernel launches of one apply (read back in hx_plan_cell_kernel_time_ms) ----
+  static int
+  timing_begin(hx_plan *p, cudaEvent_t *e1)
+  {
+    *e1 = nullptr;
+    if (!p->timing)
+      return HX_OK;
+    if (p->ev_used + 2 > p->ev_pool.size())
+      for (int i = 0; i < 64; ++i)
+        {
+          cudaEvent_t e;
+          HX_CUDA(cudaEventCreate(&e));
+          p->ev_pool.push_back(e);
+        }
+    cudaEvent_t e0 = p->ev_pool[p->ev_used++];
+    *e1            = p->ev_pool[p->ev_used++];
+    HX_CUDA(cudaEventRecord(e0, p->stream));
+    return HX_OK;
+  }
+
+  template <int NT, int MTW, bool VEC, int MINB>
   static int
   launch_colours(hx_op *op, const CellArgs &base, size_t smem)
   {
     hx_plan *p = op->plan;
-    auto     k = cell_apply_kernel<NT, VEC, MINB>;
+    auto     k = cell_apply_coloured_kernel<NT, MTW, VEC, MINB>;
     HX_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
-    if (p->timing)
-      {
-        // events are only recorded here (no host sync inside the timed region); they are read back in
-        // hx_plan_cell_kernel_time_ms
-        if (p->ev_used + 2 > p->ev_pool.size())
-          for (int i = 0; i < 64; ++i)
-            {
-              cudaEvent_t e;
-              HX_CUDA(cudaEventCreate(&e));
-              p->ev_pool.push_back(e);
-            }
-        e0 = p->ev_pool[p->ev_used++];
-        e1 = p->ev_pool[p->ev_used++];
-        HX_CUDA(cudaEventRecord(e0, p->stream));
-      }
+    cudaEvent_t e1;
+    HX_TRY(timing_begin(p, &e1));
     for (uint32_t col = 0; col < p->n_colours; ++col)
       {
         const uint32_t nc = p->h_colour_off[col + 1] - p->h_colour_off[col];
@@ -380,7 +931,45 @@ namespace hx
         p->launches++;
         p->cell_launches++;
       }
-    if (p->timing)
+    if (e1)
+      HX_CUDA(cudaEventRecord(e1, p->stream));
+    HX_CUDA(cudaGetLastError());
+    return HX_OK;
+  }
+
+  template <int NT, int MTW, bool VEC, int MINB>
+  static int
+  launch_ordered(hx_op *op, CellArgs a, size_t xtile_bytes)
+  {
+    hx_plan *    p      = op->plan;
+    auto         k      = cell_apply_ordered_kernel<NT, MTW, VEC, MINB>;
+    const size_t budget = 225 * 1024 / MINB - 1024; // per CTA (1 KB reserved by the runtime per CTA)
+    // X tiles: double-buffer when it still leaves >= 3 stages; A ring takes the rest
+    uint32_t nxb = 1;
+    if (SM_HEADER + 2 * xtile_bytes + 4 * (size_t)STAGE_DOUBLES * 8 <= budget)
+      nxb = 2;
+    HX_CHECK(SM_HEADER + nxb * xtile_bytes + 2 * (size_t)STAGE_DOUBLES * 8 <= budget, HX_ERR_UNSUPPORTED,
+             "cell with %u DoFs does not fit shared memory", op->max_kp);
+    size_t ns = (budget - SM_HEADER - nxb * xtile_bytes) / ((size_t)STAGE_DOUBLES * 8);
+    if (ns > MAX_STAGES)
+      ns = MAX_STAGES;
+    const size_t smem = SM_HEADER + ns * (size_t)STAGE_DOUBLES * 8 + nxb * xtile_bytes;
+    a.nStages         = (uint32_t)ns;
+    a.nXbuf           = nxb;
+    a.xtile_doubles   = (uint32_t)(xtile_bytes / 8);
+    HX_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    HX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, V2_THREADS, smem));
+    HX_CHECK(occ >= 1, HX_ERR_UNSUPPORTED, "ordered cell kernel does not fit on an SM (smem %zu)", smem);
+    uint32_t grid = (uint32_t)(p->sm_count * std::min(occ, MINB));
+    if (grid > a.nItems)
+      grid = a.nItems;
+    cudaEvent_t e1;
+    HX_TRY(timing_begin(p, &e1));
+    k<<<grid, V2_THREADS, smem, p->stream>>>(a);
+    p->launches++;
+    p->cell_launches++;
+    if (e1)
       HX_CUDA(cudaEventRecord(e1, p->stream));
     HX_CUDA(cudaGetLastError());
     return HX_OK;
@@ -394,39 +983,99 @@ namespace hx
     if (p->C == 0)
       return HX_OK;
     CellArgs a;
-    a.X      = X;
-    a.Y      = Y;
-    a.VCX    = op->d_cx.p;
-    a.stage  = p->d_stage.p;
-    a.packed = op->d_packed.p;
-    a.meta   = op->d_meta.p;
-    a.ids    = p->d_ids.p;
-    a.dest   = p->d_dest.p;
-    a.pids   = op->d_pids.p;
-    a.B      = B;
-    // tile width: widest of {8,16,32,64} columns that B needs and shared memory allows
-    int nt = B > 32 ? 8 : (B > 16 ? 4 : (B > 8 ? 2 : 1));
-    auto smem_of = [&](int nt_) { return (size_t)op->max_kp * (nt_ * 8 + 4) * sizeof(double); };
-    while (nt > 1 && smem_of(nt) > 200 * 1024)
+    memset(&a, 0, sizeof(a));
+    a.X         = X;
+    a.Y         = Y;
+    a.VCX       = op->d_cx.p;
+    a.stage     = p->d_stage.p;
+    a.packed    = op->d_packed.p;
+    a.meta      = op->d_meta.p;
+    a.ids       = p->d_ids.p;
+    a.dest      = p->d_dest.p;
+    a.pids      = op->d_pids.p;
+    a.cell_list = p->d_order.p;
+    a.wait_off  = p->d_wait_off.p;
+    a.wait_list = p->d_wait_list.p;
+    a.flags     = p->d_flags.p;
+    a.counters  = p->d_counters.p;
+    a.B         = B;
+    // column tile: widest of {8,16,32} columns that B needs and shared memory allows
+    int  nt      = B > 16 ? 4 : (B > 8 ? 2 : 1);
+    auto xtile_of = [&](int nt_) { return (size_t)op->max_kp * (nt_ * 8 + 4) * sizeof(double); };
+    const bool vec = (B % 2 == 0) && ((((uintptr_t)X | (uintptr_t)Y | (uintptr_t)a.VCX | (uintptr_t)a.stage) & 15) == 0);
+    const bool ordered = (p->scatter_mode == 0);
+    if (ordered)
+      {
+        // prefer two CTAs per SM (one scatters while the other contracts); fall back to one
+        int minb = 2;
+        while (nt > 1 && SM_HEADER + xtile_of(nt) + 3 * (size_t)STAGE_DOUBLES * 8 > 225 * 1024 - 1024)
+          nt >>= 1;
+        if (SM_HEADER + xtile_of(nt) + 3 * (size_t)STAGE_DOUBLES * 8 > 225 * 1024 / 2 - 1024)
+          minb = 1;
+        a.nBt    = (B + nt * 8 - 1) / (nt * 8);
+        a.nItems = p->C * a.nBt;
+        a.epoch  = ++p->epoch;
+        if (p->epoch == 0xfffffff0u)
+          {
+            // epoch wrap: clear the stamps (never reached in practice)
+            HX_CUDA(cudaMemsetAsync(p->d_flags.p, 0, p->d_flags.n * sizeof(uint32_t), p->stream));
+            p->epoch = 0;
+            a.epoch  = ++p->epoch;
+          }
+        HX_CHECK((size_t)a.nItems <= p->d_flags.n, HX_ERR_INVALID, "flag array too small");
+        const size_t xt = xtile_of(nt);
+#define HX_ORD(NT_, MTW_, MINB_) \
+  (vec ? launch_ordered<NT_, MTW_, true, MINB_>(op, a, xt) : launch_ordered<NT_, MTW_, false, MINB_>(op, a, xt))
+#define HX_ORD_M(NT_, MTW_) (minb == 2 ? HX_ORD(NT_, MTW_, 2) : HX_ORD(NT_, MTW_, 1))
+        if (op->mtw == 1)
+          switch (nt)
+            {
+              case 4:
+                return HX_ORD_M(4, 1);
+              case 2:
+                return HX_ORD_M(2, 1);
+              default:
+                return HX_ORD_M(1, 1);
+            }
+        switch (nt)
+          {
+            case 4:
+              return HX_ORD_M(4, 2);
+            case 2:
+              return HX_ORD_M(2, 2);
+            default:
+              return HX_ORD_M(1, 2);
+          }
+#undef HX_ORD_M
+#undef HX_ORD
+      }
+    while (nt > 1 && xtile_of(nt) > 200 * 1024)
       nt >>= 1;
-    HX_CHECK(smem_of(nt) <= 220 * 1024, HX_ERR_UNSUPPORTED, "cell with %u DoFs does not fit shared memory", op->max_kp);
-    a.nBt          = (B + nt * 8 - 1) / (nt * 8);
-    const bool vec = (B % 2 == 0);
-    const size_t smem = smem_of(nt);
-#define HX_DISPATCH(NT_, MINB_)                                  \
-  (vec ? launch_colours<NT_, true, MINB_>(op, a, smem) : launch_colours<NT_, false, MINB_>(op, a, smem))
+    HX_CHECK(xtile_of(nt) <= 220 * 1024, HX_ERR_UNSUPPORTED, "cell with %u DoFs does not fit shared memory", op->max_kp);
+    a.nBt             = (B + nt * 8 - 1) / (nt * 8);
+    const size_t smem = xtile_of(nt);
+#define HX_COL(NT_, MTW_) \
+  (vec ? launch_colours<NT_, MTW_, true, 2>(op, a, smem) : launch_colours<NT_, MTW_, false, 2>(op, a, smem))
+    if (op->mtw == 1)
+      switch (nt)
+        {
+          case 4:
+            return HX_COL(4, 1);
+          case 2:
+            return HX_COL(2, 1);
+          default:
+            return HX_COL(1, 1);
+        }
     switch (nt)
       {
-        case 8:
-          return HX_DISPATCH(8, 1);
         case 4:
-          return HX_DISPATCH(4, 2);
+          return HX_COL(4, 2);
         case 2:
-          return HX_DISPATCH(2, 2);
+          return HX_COL(2, 2);
         default:
-          return HX_DISPATCH(1, 2);
+          return HX_COL(1, 2);
       }
-#undef HX_DISPATCH
+#undef HX_COL
   }
 
   // -------------------------------------------------------------------------------------------------

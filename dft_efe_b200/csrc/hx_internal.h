@@ -125,6 +125,10 @@ namespace hx
   struct Comm; // NCCL communicator wrapper (comm.cu)
 } // namespace hx
 
+#define HX_DEST_STAGED 0x80000000u
+#define HX_DEST_FIRST 0x40000000u
+#define HX_DEST_ROW(d) ((d)&0x3fffffffu)
+
 struct hx_plan
 {
   int          rank = 0, nranks = 1;
@@ -153,10 +157,24 @@ struct hx_plan
   uint32_t              n_colours = 0;
   std::vector<uint32_t> h_colour, h_colour_off, h_colour_cells;
   hx::DevBuf<uint32_t>  d_colour_cells;
-  hx::DevBuf<uint32_t>  d_dest; // [S]: local row id, or 0x80000000 | staging slot
+  hx::DevBuf<uint32_t>  d_dest; // [S]: local row id (| HX_DEST_FIRST when the cell is the row's first toucher in
+                                // processing order), or HX_DEST_STAGED | staging slot
   uint32_t              n_shared = 0, n_slots = 0;
   hx::DevBuf<uint32_t>  d_sh_rows, d_sh_off, d_sh_slots;
   hx::DevBuf<double>    d_stage; // n_slots x max_block
+
+  // ordered (persistent) scatter: cells are processed in `order`; a cell adds into Y only after the
+  // immediately preceding toucher of each of its rows has signalled completion -> fixed summation order
+  // per row (ascending processing order, the reference's CPU order) without colour launches or atomics
+  int                   scatter_mode = 0; // 0 = ordered persistent kernel, 1 = one launch per colour
+  std::vector<uint32_t> h_order, h_wait_off, h_wait_list;
+  hx::DevBuf<uint32_t>  d_order, d_wait_off, d_wait_list;
+  hx::DevBuf<uint32_t>  d_flags;    // [C * ceil(max_block/8)] epoch stamps
+  hx::DevBuf<uint32_t>  d_counters; // [0] work counter, [1] finished CTAs
+  uint32_t              epoch = 0;
+  uint32_t              n_untouched = 0;
+  hx::DevBuf<uint32_t>  d_untouched; // rows no cell writes (zeroed explicitly each apply)
+  int                   sm_count = 0;
 
   hx::Halo  halo;
   hx::Comm *comm = nullptr;
@@ -201,6 +219,7 @@ struct hx_op
   size_t                    packed_doubles = 0;
   bool                      have_matrices  = false;
   uint32_t                  max_kp = 0, max_mp = 0;
+  int                       mtw = 2; // m-tiles (8 rows) per compute warp per chunk: packed layout depends on it
   // nonlocal
   bool                      has_nl = false;
   hx::Halo                  phalo;
@@ -233,6 +252,7 @@ namespace hx
                            double b1, const double *b, const double *y, double *z);
   int launch_colsumsq(hx_plan *p, const double *x, uint32_t B, size_t nrows, double *out_dev);
   int launch_shared_reduce(hx_plan *p, double *Y, uint32_t B);
+  int launch_zero_rows(hx_plan *p, double *Y, uint32_t B, const uint32_t *rows, uint32_t n);
   int launch_enr_block(hx_plan *p, const double *blk, uint32_t nE, const double *Xenr, double *Yenr, uint32_t B);
   int launch_cell_apply(hx_op *op, const double *X, double *Y, uint32_t B);
   int launch_nl_phase_a(hx_op *op, const double *X, uint32_t B);

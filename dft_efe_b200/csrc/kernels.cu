@@ -82,6 +82,17 @@ namespace hx
   }
 
   int
+  launch_zero_rows(hx_plan *p, double *Y, uint32_t B, const uint32_t *rows, uint32_t n)
+  {
+    if (n == 0)
+      return HX_OK;
+    zero_rows_kernel<<<nblk((size_t)n * B), 256, 0, p->stream>>>(Y, B, n, rows);
+    p->launches++;
+    HX_CUDA(cudaGetLastError());
+    return HX_OK;
+  }
+
+  int
   launch_c2p(hx_plan *p, double *Y, uint32_t B)
   {
     if (p->nR == 0)
@@ -290,11 +301,11 @@ namespace hx
     if (i >= (size_t)nrows * B)
       return;
     const uint32_t r = (uint32_t)(i / B), v = (uint32_t)(i % B);
-    double *       d = Y + (size_t)rows[r] * B + v;
-    double         s = *d;
+    // shared rows receive every contribution through a staging slot: Y is written, not accumulated
+    double s = 0.0;
     for (uint32_t e = off[r]; e < off[r + 1]; ++e)
       s += stage[(size_t)slots[e] * B + v];
-    *d = s;
+    Y[(size_t)rows[r] * B + v] = s;
   }
   int
   launch_shared_reduce(hx_plan *p, double *Y, uint32_t B)

@@ -118,9 +118,19 @@ int hx_plan_synchronize(hx_plan *plan);
  * MPIPatternP2P (src/utils/MPIPatternP2P.h:489).  Ranks of the halo descriptors are communicator ranks. */
 int hx_comm_unique_id(char id[128]);
 int hx_plan_attach_comm(hx_plan *plan, const char id[128]);
+/* Scatter strategy of the cell kernel: 0 (default) = one persistent launch, cells in the caller's order, each
+ * row accumulated in ascending cell order behind per-cell completion stamps (no atomics, bitwise reproducible,
+ * same per-row summation order as the reference's CPU loop, src/basis/FECellWiseDataOperations.t.cpp:87-153);
+ * 1 = one launch per colour of a greedy cell colouring (cells of a launch share no row). */
+int hx_plan_set_scatter_mode(hx_plan *plan, int mode);
 /* Introspection used by the bit-exact parity tests of the integer work. */
 int hx_plan_num_colours(hx_plan *plan, uint32_t *n);
 int hx_plan_get_cell_colours(hx_plan *plan, uint32_t *colour /*[C]*/);
+/* ordered scatter: the processing order (position -> cell): the caller's order cut into blocks of 1024 cells
+ * (HXB200_ORDER_BLOCK), each block stably sorted by colour. */
+int hx_plan_get_processing_order(hx_plan *plan, uint32_t *order /*[C]*/);
+/* ordered scatter: per cell (in processing order) the preceding cells it must wait for; pass NULLs to query nnz. */
+int hx_plan_get_wait_lists(hx_plan *plan, uint32_t *nnz, uint32_t *offsets /*[C+1]*/, uint32_t *preds /*[nnz]*/);
 int hx_plan_get_c2p_transpose(hx_plan *plan, uint32_t *n_parents, uint32_t *parent_ids, uint32_t *offsets,
                               uint32_t *child_rows, double *weights); /* pass NULLs to query n_parents */
 

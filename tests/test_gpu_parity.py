@@ -156,6 +156,68 @@ def test_hx_bitwise_deterministic(capi, prob_full):
     assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
 
 
+def test_wait_lists_bit_exact(capi, prob_full):
+    """Ordered scatter: each cell waits for the immediately preceding toucher of each of its non-shared rows."""
+    p = prob_full
+    plan = capi.Plan(p, max_block=8)
+    off, preds = plan.wait_lists()
+    order = plan.processing_order()
+    _, colour = plan.colours()
+    exp_order = np.concatenate([b0 + np.argsort(colour[b0:b0 + 1024], kind="stable")
+                                for b0 in range(0, p.n_cells, 1024)]).astype(np.uint32)
+    assert np.array_equal(order, exp_order)
+    ids = p.cell_local_ids.astype(np.int64)
+    coff = np.concatenate(([0], np.cumsum(p.num_cell_dofs.astype(np.int64))))
+    inc = np.bincount(ids, minlength=p.n_local)
+    last = -np.ones(p.n_local, np.int64)
+    exp_off, exp = [0], []
+    for w, c in enumerate(order):
+        rows = ids[coff[c]:coff[c + 1]]
+        rows = rows[inc[rows] <= 8]
+        pr = np.unique(last[rows][last[rows] >= 0])
+        exp.extend(pr.tolist())
+        exp_off.append(len(exp))
+        last[rows] = w
+    assert np.array_equal(off, np.array(exp_off, np.uint32))
+    assert np.array_equal(preds, np.array(exp, np.uint32))
+    assert all((preds[off[c]:off[c + 1]] < c).all() for c in range(p.n_cells))
+
+
+@pytest.mark.parametrize("B", [3, 8, 32, 40])
+def test_ordered_and_coloured_scatter_agree(capi, prob_full, B):
+    p = prob_full
+    plan = capi.Plan(p, max_block=B)
+    op = capi.CellOp(plan)
+    X = synth.make_block(p, B)
+    Yo = np.zeros_like(X)
+    orc.OracleWorld([p]).hx_apply([X.copy()], [Yo], True, False)
+    res = []
+    for mode in (0, 1):
+        plan.set_scatter_mode(mode)
+        dX = plan.block(B, X)
+        dY = plan.block(B, np.full_like(X, 1e300))  # Y is fully overwritten: garbage must not leak
+        op.apply(dX, dY, True, False)
+        res.append(dY.download())
+        assert rel_l2_per_vector(res[-1], Yo) < RTOL_HX
+    assert rel_l2_per_vector(res[0], res[1]) < 1e-14
+
+
+def test_ordered_scatter_many_applies(capi, prob_plain):
+    """Epoch stamps / work counters survive repeated launches with changing block widths."""
+    p = prob_plain
+    plan = capi.Plan(p, max_block=64)
+    op = capi.CellOp(plan)
+    W = orc.OracleWorld([p])
+    for B in (64, 8, 1, 32, 64, 2, 16):
+        X = synth.make_block(p, B)
+        dX, dY = plan.block(B, X), plan.block(B)
+        for _ in range(3):
+            op.apply(dX, dY)
+        Yo = np.zeros_like(X)
+        W.hx_apply([X.copy()], [Yo])
+        assert rel_l2_per_vector(dY.download(), Yo) < RTOL_HX
+
+
 def test_hx_host_entry_point(capi, prob_full):
     p = prob_full
     B = 8
