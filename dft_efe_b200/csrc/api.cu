@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <map>
+#include <queue>
 #include <new>
 
 #include "hx_internal.h"
@@ -104,6 +105,15 @@ namespace hx
   }
 
   // ---------------------------------------------------------------------------------------------
+  static int
+  sm_count_for_order()
+  {
+    int dev = 0, n = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess)
+      cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    return n;
+  }
+
   static int
   build_plan(hx_plan *p, const hx_mesh_desc *m)
   {
@@ -268,22 +278,107 @@ namespace hx
     HX_TRY(p->d_colour_cells.upload(p->h_colour_cells));
 
     // ---- ordered scatter: processing order, first-touch flags, predecessor (wait) lists ----
-    // Processing order: the caller's cell order (deal.II: p4est z-order) cut into blocks of `order_block`
-    // consecutive cells, each block stably sorted by colour.  Blocks keep the touches of a row close in time
-    // (its X and Y lines stay in L2); the colour sort keeps them far enough apart (>= a colour group) that a
-    // cell practically never stalls on a predecessor that is still contracting.  For every non-shared row the
-    // touching cells form a chain in processing order; a cell waits only for the immediately preceding
-    // toucher of each of its rows (completion is transitive).
+    // For every non-shared row the touching cells form a chain in processing order; a cell waits only for the
+    // immediately preceding toucher of each of its rows (completion is transitive).  The order keeps the
+    // touches of a row close in time (its X and Y lines stay in L2) yet at least D positions apart, so a cell
+    // practically never stalls on a predecessor that is still contracting.
     {
-      uint32_t order_block = 1024;
-      if (const char *e = getenv("HXB200_ORDER_BLOCK"))
-        order_block = (uint32_t)std::max(1, atoi(e));
       p->h_order.resize(p->C);
       for (uint32_t c = 0; c < p->C; ++c)
         p->h_order[c] = c;
-      for (uint32_t b0 = 0; b0 < p->C; b0 += order_block)
-        std::stable_sort(p->h_order.begin() + b0, p->h_order.begin() + std::min(p->C, b0 + order_block),
-                         [&](uint32_t x, uint32_t y) { return p->h_colour[x] < p->h_colour[y]; });
+      if (const char *e = getenv("HXB200_ORDER_BLOCK"))
+        {
+          // alternative: blocks of consecutive cells, each stably sorted by colour
+          const uint32_t order_block = (uint32_t)std::max(1, atoi(e));
+          for (uint32_t b0 = 0; b0 < p->C; b0 += order_block)
+            std::stable_sort(p->h_order.begin() + b0, p->h_order.begin() + std::min(p->C, b0 + order_block),
+                             [&](uint32_t x, uint32_t y) { return p->h_colour[x] < p->h_colour[y]; });
+        }
+      else
+        {
+          // delay-D list schedule: sweep the cells in the caller's order, but place a cell only when every
+          // neighbour (cell sharing a non-staged row) already placed sits >= D positions back; skipped cells
+          // are picked up as soon as they become eligible.  D ~ twice the number of resident CTAs.
+          uint32_t D = 4u * (uint32_t)std::max(1, sm_count_for_order());
+          if (const char *e2 = getenv("HXB200_ORDER_DELAY"))
+            D = (uint32_t)std::max(0, atoi(e2));
+          // row -> cells CSR over non-staged rows
+          std::vector<uint32_t> rc_off(p->n_local + 1, 0), rc;
+          for (uint32_t i = 0; i < p->S; ++i)
+            if (!(dest[i] & HX_DEST_STAGED))
+              rc_off[p->h_ids[i] + 1]++;
+          for (uint32_t r = 0; r < p->n_local; ++r)
+            rc_off[r + 1] += rc_off[r];
+          rc.resize(rc_off[p->n_local]);
+          {
+            std::vector<uint32_t> fill(rc_off.begin(), rc_off.end() - 1);
+            for (uint32_t c = 0; c < p->C; ++c)
+              for (uint32_t i = p->h_cell_off[c]; i < p->h_cell_off[c + 1]; ++i)
+                if (!(dest[i] & HX_DEST_STAGED))
+                  rc[fill[p->h_ids[i]]++] = c;
+          }
+          typedef std::pair<uint32_t, uint32_t> PR; // (key, cell)
+          std::priority_queue<uint32_t, std::vector<uint32_t>, std::greater<uint32_t>> eligible;
+          std::priority_queue<PR, std::vector<PR>, std::greater<PR>>                   waiting;
+          std::vector<uint32_t> ready(p->C, 0);
+          std::vector<char>     placed(p->C, 0);
+          for (uint32_t c = 0; c < p->C; ++c)
+            eligible.push(c);
+          for (uint32_t t = 0; t < p->C; ++t)
+            {
+              while (!waiting.empty() && waiting.top().first <= t)
+                {
+                  const PR e = waiting.top();
+                  waiting.pop();
+                  if (!placed[e.second])
+                    {
+                      if (ready[e.second] <= t)
+                        eligible.push(e.second);
+                      else if (ready[e.second] != e.first)
+                        waiting.push(PR(ready[e.second], e.second));
+                    }
+                }
+              uint32_t c = 0xffffffffu;
+              while (!eligible.empty())
+                {
+                  const uint32_t x = eligible.top();
+                  eligible.pop();
+                  if (placed[x])
+                    continue;
+                  if (ready[x] > t)
+                    {
+                      waiting.push(PR(ready[x], x));
+                      continue;
+                    }
+                  c = x;
+                  break;
+                }
+              while (c == 0xffffffffu)
+                {
+                  // every remaining cell is delayed: take the one that becomes eligible first
+                  const PR e = waiting.top();
+                  waiting.pop();
+                  if (placed[e.second])
+                    continue;
+                  if (ready[e.second] != e.first)
+                    {
+                      waiting.push(PR(ready[e.second], e.second));
+                      continue;
+                    }
+                  c = e.second;
+                }
+              placed[c]     = 1;
+              p->h_order[t] = c;
+              for (uint32_t i = p->h_cell_off[c]; i < p->h_cell_off[c + 1]; ++i)
+                if (!(dest[i] & HX_DEST_STAGED))
+                  {
+                    const uint32_t r = p->h_ids[i];
+                    for (uint32_t e = rc_off[r]; e < rc_off[r + 1]; ++e)
+                      if (!placed[rc[e]])
+                        ready[rc[e]] = t + D;
+                  }
+            }
+        }
       std::vector<uint32_t> last(p->n_local, 0xffffffffu); // last processing index that touched the row
       p->h_wait_off.assign(p->C + 1, 0);
       p->h_wait_list.clear();

@@ -31,11 +31,10 @@
 namespace hx
 {
   constexpr int KC            = 4;               // k-steps (of 4) per stage
-  constexpr int STAGE_DOUBLES = 16 * KC * 32;    // max stage: 16 m-tiles x KC k-steps x 32 doubles = 16 KB
   constexpr int CWARPS        = 8;               // DMMA warps
   constexpr int CTHREADS      = CWARPS * 32;
   constexpr int V2_THREADS    = CTHREADS + 64;   // + A-stream warp + gather warp
-  constexpr int QD            = 8;               // item queue depth (A-stream warp -> gather warp)
+  constexpr int QD            = 16;              // item queue depth (A-stream warp -> gather / DMMA warps)
   constexpr int MAX_STAGES    = 8;
   constexpr uint32_t ITEM_END = 0xffffffffu;
 
@@ -59,9 +58,7 @@ namespace hx
     uint32_t        nItems;
     uint32_t        B;
     uint32_t        nBt;
-    uint32_t        xtile_doubles;
     uint32_t        nStages;
-    uint32_t        nXbuf;
   };
 
   __device__ __forceinline__ void
@@ -183,13 +180,11 @@ namespace hx
   }
 
   // shared-memory header of the ordered kernel (bytes from the dynamic smem base, 128-B aligned)
-  constexpr int SM_FULL   = 0;   // MAX_STAGES x 8
-  constexpr int SM_EMPTY  = 64;  // MAX_STAGES x 8
-  constexpr int SM_XFULL  = 128; // 2 x 8
-  constexpr int SM_XEMPTY = 144; // 2 x 8
-  constexpr int SM_QUEUE  = 256; // QD x 32   (A-stream warp -> gather warp)
-  constexpr int SM_XITEM  = 512; // 2 x 32    (gather warp -> DMMA warps, one per X buffer)
-  constexpr int SM_HEADER = 640;
+  constexpr int SM_FULL   = 0;                 // MAX_STAGES x 8
+  constexpr int SM_EMPTY  = 64;                // MAX_STAGES x 8
+  constexpr int SM_Q1     = 128;               // QD x 32   (A-stream warp -> gather warp)
+  constexpr int SM_Q2     = SM_Q1 + QD * 32;   // QD x 32   (A-stream warp -> DMMA warps)
+  constexpr int SM_HEADER = SM_Q2 + QD * 32;   // 1152
 
   // what the three roles need to know about a work item; loaded once (A-stream warp) and handed on in smem
   struct ItemInfo
@@ -220,6 +215,18 @@ namespace hx
                  : "memory");
   }
 
+  // bytes of one pipeline stage: the A fragments of one (m-chunk, k-chunk) + the 4*KC gathered rows of X
+  __host__ __device__ constexpr int
+  stage_a_bytes(int mtw)
+  {
+    return CWARPS * mtw * KC * 256;
+  }
+  __host__ __device__ constexpr int
+  stage_bytes(int nt, int mtw)
+  {
+    return stage_a_bytes(mtw) + 4 * KC * (nt * 8 + 4) * 8;
+  }
+
   // =================================================================================================
   // Ordered persistent kernel
   // =================================================================================================
@@ -227,29 +234,25 @@ namespace hx
   __global__ void __launch_bounds__(V2_THREADS, MINB) cell_apply_ordered_kernel(const CellArgs a)
   {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    constexpr int  BT  = NT * 8;
-    constexpr int  LDX = BT + 4;
-    constexpr int  MPC = CWARPS * MTW; // m-tiles per chunk
+    constexpr int  BT      = NT * 8;
+    constexpr int  LDX     = BT + 4;
+    constexpr int  MPC     = CWARPS * MTW; // m-tiles per chunk
+    constexpr int  KROWS   = 4 * KC;       // rows of X per stage
+    constexpr int  A_BYTES = stage_a_bytes(MTW);
+    constexpr int  S_BYTES = stage_bytes(NT, MTW);
     const int      tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t sbase = smem_u32(smem_raw);
-    double *       ring   = reinterpret_cast<double *>(smem_raw + SM_HEADER);
-    double *       xtiles = ring + (size_t)a.nStages * STAGE_DOUBLES;
-    const uint32_t NS = a.nStages, NXB = a.nXbuf;
+    const uint32_t NS    = a.nStages;
 
     if (tid == 0)
       {
         for (uint32_t s = 0; s < NS; ++s)
           {
-            mbar_init(sbase + SM_FULL + 8 * s, 1);
+            mbar_init(sbase + SM_FULL + 8 * s, 33); // A-stream arrive.expect_tx + 32 gather lanes
             mbar_init(sbase + SM_EMPTY + 8 * s, CWARPS);
           }
-        for (uint32_t b = 0; b < NXB; ++b)
-          {
-            mbar_init(sbase + SM_XFULL + 8 * b, 32);
-            mbar_init(sbase + SM_XEMPTY + 8 * b, CWARPS);
-          }
-        for (int q = 0; q < QD; ++q)
-          st_volatile_shared(sbase + SM_QUEUE + 32 * q, 0u);
+        for (int q = 0; q < 2 * QD; ++q)
+          st_volatile_shared(sbase + SM_Q1 + 32 * q, 0u);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
       }
     __syncthreads();
@@ -278,20 +281,22 @@ namespace hx
               }
             for (uint32_t it = 0;; ++it)
               {
-                const uint32_t slot = sbase + SM_QUEUE + 32 * (it % QD);
-                while (ld_volatile_shared(slot) != 0u)
+                const uint32_t q1 = sbase + SM_Q1 + 32 * (it % QD), q2 = sbase + SM_Q2 + 32 * (it % QD);
+                while (ld_volatile_shared(q1) != 0u || ld_volatile_shared(q2) != 0u)
                   {
                   }
                 if (w >= a.nItems)
                   {
-                    st_volatile_shared(slot, ITEM_END);
+                    st_volatile_shared(q1, ITEM_END);
+                    st_volatile_shared(q2, ITEM_END);
                     break;
                   }
                 ItemInfo info;
                 info.tag = w + 1u, info.ids_off = cm.ids_off, info.n = cm.n, info.nproj = cm.nproj;
                 info.proj_off = cm.proj_off, info.wait_off = wo, info.nwait = nwait, info.pad = 0;
-                item_store(slot, info);
-                const int     nKC = ((int)(cm.n + cm.nproj) + 4 * KC - 1) / (4 * KC);
+                item_store(q1, info);
+                item_store(q2, info);
+                const int     nKC = ((int)(cm.n + cm.nproj) + KROWS - 1) / KROWS;
                 const int     nMt = ((int)cm.n + 7) >> 3;
                 const double *src = a.packed + cm.h_off;
                 // claim + prefetch the next item
@@ -311,7 +316,7 @@ namespace hx
                       {
                         mbar_wait(sbase + SM_EMPTY + 8 * stage, ph ^ 1u);
                         mbar_arrive_expect_tx(sbase + SM_FULL + 8 * stage, bytes);
-                        const uint32_t dst = sbase + SM_HEADER + stage * (STAGE_DOUBLES * 8);
+                        const uint32_t dst = sbase + SM_HEADER + stage * S_BYTES;
                         if (once)
                           bulk_g2s_hint(dst, src, bytes, sbase + SM_FULL + 8 * stage, evict_first);
                         else
@@ -330,74 +335,76 @@ namespace hx
     else if (warp == CWARPS + 1)
       {
         // ------------------------------------ gather warp ------------------------------------
-        const uint32_t xs0 = smem_u32(xtiles);
-        constexpr int  CPR = VEC ? BT / 2 : BT; // copies per row (<= 32)
-        constexpr int  RPI = 32 / CPR;          // rows per warp instruction
-        const int      cc  = lane % CPR;
-        const int      rr  = lane / CPR;
+        // per stage: the KROWS rows k of X (k < n), of V C^H X (n <= k < ktot) or zeros, columns b0..b0+BT-1
+        constexpr int CPR = VEC ? BT / 2 : BT; // copies per row (<= 32)
+        constexpr int RPI = 32 / CPR;          // rows per warp instruction
+        const int     cc  = lane % CPR;
+        const int     rr  = lane / CPR;
+        uint32_t      stage = 0, ph = 0;
         for (uint32_t it = 0;; ++it)
           {
-            const uint32_t slot = sbase + SM_QUEUE + 32 * (it % QD);
+            const uint32_t slot = sbase + SM_Q1 + 32 * (it % QD);
             uint32_t       tag;
             while ((tag = ld_volatile_shared(slot)) == 0u)
               {
               }
-            ItemInfo info = {};
-            info.tag      = tag;
-            if (tag != ITEM_END)
-              item_load_payload(slot, info);
+            if (tag == ITEM_END)
+              break;
+            ItemInfo info;
+            info.tag = tag;
+            item_load_payload(slot, info);
             __syncwarp();
             if (lane == 0)
               st_volatile_shared(slot, 0u);
-            const uint32_t buf = it % NXB, use = it / NXB;
-            const uint32_t xi  = sbase + SM_XITEM + 32 * buf;
-            // row codes of the first 32 rows: fetched before waiting for the tile to be free
             const int n = (int)info.n, ktot = n + (int)info.nproj;
             auto      row_code = [&](int k) -> uint32_t {
-              if (tag == ITEM_END || k >= ktot)
+              if (k >= ktot)
                 return 0xffffffffu; // zero row
               if (k < n)
                 return __ldg(a.ids + info.ids_off + k);
               return 0x80000000u | __ldg(a.pids + info.proj_off + (k - n));
             };
-            uint32_t code = row_code(lane);
-            mbar_wait(sbase + SM_XEMPTY + 8 * buf, (use & 1u) ^ 1u);
-            if (tag == ITEM_END)
-              {
-                if (lane == 0)
-                  st_volatile_shared(xi, ITEM_END);
-                __syncwarp();
-                mbar_arrive(sbase + SM_XFULL + 8 * buf);
-                break;
-              }
-            if (lane == 0)
-              item_store(xi, info);
-            __syncwarp();
-            const uint32_t b0 = ((tag - 1u) % a.nBt) * BT;
-            const int      Kp = (ktot + 4 * KC - 1) / (4 * KC) * (4 * KC);
-            const uint32_t xs = xs0 + buf * a.xtile_doubles * 8u;
-            const uint32_t col  = b0 + (VEC ? cc * 2 : cc);
+            const uint32_t b0    = ((tag - 1u) % a.nBt) * BT;
+            const int      nKC   = (ktot + KROWS - 1) / KROWS;
+            const int      nMt   = (n + 7) >> 3;
+            const uint32_t col   = b0 + (VEC ? cc * 2 : cc);
             const bool     colok = col < a.B;
-            for (int kb = 0; kb < Kp; kb += 32)
+            for (int mc = 0; mc < nMt; mc += MPC)
               {
-                const uint32_t code_next = (kb + 32 < Kp) ? row_code(kb + 32 + lane) : 0xffffffffu;
-                const int      rows      = min(32, Kp - kb);
-                for (int r = 0; r < rows; r += RPI)
+                // row codes: lane l holds row 32*j + l of the current / next block of 32 rows
+                uint32_t code = row_code(lane), code_next = row_code(32 + lane);
+                for (int kc = 0; kc < nKC; ++kc)
                   {
-                    const uint32_t c   = __shfl_sync(0xffffffffu, code, r + rr);
-                    const bool     ok  = (c != 0xffffffffu) && colok;
-                    const double * src = a.X;
-                    if (ok)
-                      src = ((c & 0x80000000u) ? a.VCX + (size_t)(c & 0x7fffffffu) * a.B : a.X + (size_t)c * a.B) + col;
-                    const uint32_t dst = xs + ((uint32_t)(kb + r + rr) * LDX + (VEC ? cc * 2 : cc)) * 8u;
-                    if (VEC)
-                      cp_async_zfill16(dst, src, ok ? 16u : 0u);
-                    else
-                      cp_async_zfill8(dst, src, ok ? 8u : 0u);
+                    constexpr int SPB = 32 / KROWS; // stages per 32-row block
+                    if (kc && (kc % SPB) == 0)
+                      {
+                        code      = code_next;
+                        code_next = row_code((kc / SPB + 1) * 32 + lane);
+                      }
+                    mbar_wait(sbase + SM_EMPTY + 8 * stage, ph ^ 1u);
+                    const uint32_t xs = sbase + SM_HEADER + stage * S_BYTES + A_BYTES;
+#pragma unroll
+                    for (int r = 0; r < KROWS; r += RPI)
+                      {
+                        const uint32_t c   = __shfl_sync(0xffffffffu, code, (kc % SPB) * KROWS + r + rr);
+                        const bool     ok  = (c != 0xffffffffu) && colok;
+                        const double * src = a.X;
+                        if (ok)
+                          src = ((c & 0x80000000u) ? a.VCX + (size_t)(c & 0x7fffffffu) * a.B : a.X + (size_t)c * a.B) + col;
+                        const uint32_t dst = xs + ((uint32_t)(r + rr) * LDX + (VEC ? cc * 2 : cc)) * 8u;
+                        if (VEC)
+                          cp_async_zfill16(dst, src, ok ? 16u : 0u);
+                        else
+                          cp_async_zfill8(dst, src, ok ? 8u : 0u);
+                      }
+                    cp_async_mbar_arrive_noinc(sbase + SM_FULL + 8 * stage);
+                    if (++stage == NS)
+                      {
+                        stage = 0;
+                        ph ^= 1u;
+                      }
                   }
-                code = code_next;
               }
-            cp_async_mbar_arrive_noinc(sbase + SM_XFULL + 8 * buf);
           }
       }
     else
@@ -406,25 +413,24 @@ namespace hx
         uint32_t stage = 0, ph = 0;
         for (uint32_t it = 0;; ++it)
           {
-            const uint32_t buf = it % NXB, use = it / NXB;
-            mbar_wait(sbase + SM_XFULL + 8 * buf, use & 1u);
-            const uint32_t xi = sbase + SM_XITEM + 32 * buf;
+            const uint32_t slot = sbase + SM_Q2 + 32 * (it % QD);
             ItemInfo       info;
-            info.tag = ld_volatile_shared(xi);
+            while ((info.tag = ld_volatile_shared(slot)) == 0u)
+              {
+              }
             if (info.tag == ITEM_END)
               break;
-            item_load_payload(xi, info);
+            item_load_payload(slot, info);
             const uint32_t w    = info.tag - 1u;
             const uint32_t bt   = w % a.nBt;
             const int      n    = (int)info.n;
-            const int      nKC  = (n + (int)info.nproj + 4 * KC - 1) / (4 * KC);
+            const int      nKC  = (n + (int)info.nproj + KROWS - 1) / KROWS;
             const int      nMt  = (n + 7) >> 3;
             const uint32_t B    = a.B;
             const uint32_t b0   = bt * BT;
-            const double * xs   = xtiles + (size_t)buf * a.xtile_doubles;
-            const double * xrow = xs + (size_t)(lane & 3) * LDX + (lane >> 2);
             const uint32_t wo = info.wait_off, nwait = info.nwait;
-            // predecessor stamps to poll (prefetch the addresses' indices early)
+            const int      xoff = A_BYTES / 8 + (lane & 3) * LDX + (lane >> 2); // B fragment inside a stage
+            // predecessor stamps to poll (indices fetched early)
             uint32_t pred = 0;
             if ((uint32_t)tid < nwait)
               pred = __ldg(a.wait_list + wo + tid);
@@ -459,18 +465,18 @@ namespace hx
                     mbar_wait(sbase + SM_FULL + 8 * stage, ph);
                     if (active)
                       {
-                        const double *As = ring + (size_t)stage * STAGE_DOUBLES;
-                        const double *xr = xrow + (size_t)kc * (4 * KC) * LDX;
+                        const double *St = reinterpret_cast<const double *>(smem_raw + SM_HEADER + (size_t)stage * S_BYTES);
+                        const double *xr = St + xoff;
 #pragma unroll
                         for (int ks = 0; ks < KC; ++ks)
                           {
                             double af[MTW], bf[NT];
 #pragma unroll
                             for (int j = 0; j < MTW; ++j)
-                              af[j] = As[aoff[j] + ks * 32];
+                              af[j] = St[aoff[j] + ks * 32];
 #pragma unroll
                             for (int t = 0; t < NT; ++t)
-                              bf[t] = xr[(size_t)ks * 4 * LDX + t * 8];
+                              bf[t] = xr[ks * 4 * LDX + t * 8];
 #pragma unroll
                             for (int j = 0; j < MTW; ++j)
 #pragma unroll
@@ -486,13 +492,6 @@ namespace hx
                         stage = 0;
                         ph ^= 1u;
                       }
-                  }
-                if (mc + MPC >= nMt)
-                  {
-                    // the X tile is no longer needed: let the gather warp refill it
-                    __syncwarp();
-                    if (lane == 0)
-                      mbar_arrive(sbase + SM_XEMPTY + 8 * buf);
                   }
                 if (mc == 0 && nwait)
                   {
@@ -563,7 +562,10 @@ namespace hx
             // stores before thread 0's release store (cumulative at gpu scope)
             bar_compute();
             if (tid == 0)
-              st_release_gpu(a.flags + w, a.epoch);
+              {
+                st_release_gpu(a.flags + w, a.epoch);
+                st_volatile_shared(slot, 0u); // queue slot free again
+              }
           }
         // last CTA out resets the work counters for the next launch
         if (tid == 0)
@@ -939,24 +941,16 @@ namespace hx
 
   template <int NT, int MTW, bool VEC, int MINB>
   static int
-  launch_ordered(hx_op *op, CellArgs a, size_t xtile_bytes)
+  launch_ordered(hx_op *op, CellArgs a)
   {
     hx_plan *    p      = op->plan;
     auto         k      = cell_apply_ordered_kernel<NT, MTW, VEC, MINB>;
     const size_t budget = 225 * 1024 / MINB - 1024; // per CTA (1 KB reserved by the runtime per CTA)
-    // X tiles: double-buffer when it still leaves >= 3 stages; A ring takes the rest
-    uint32_t nxb = 1;
-    if (SM_HEADER + 2 * xtile_bytes + 4 * (size_t)STAGE_DOUBLES * 8 <= budget)
-      nxb = 2;
-    HX_CHECK(SM_HEADER + nxb * xtile_bytes + 2 * (size_t)STAGE_DOUBLES * 8 <= budget, HX_ERR_UNSUPPORTED,
-             "cell with %u DoFs does not fit shared memory", op->max_kp);
-    size_t ns = (budget - SM_HEADER - nxb * xtile_bytes) / ((size_t)STAGE_DOUBLES * 8);
+    size_t       ns     = (budget - SM_HEADER) / (size_t)stage_bytes(NT, MTW);
     if (ns > MAX_STAGES)
       ns = MAX_STAGES;
-    const size_t smem = SM_HEADER + ns * (size_t)STAGE_DOUBLES * 8 + nxb * xtile_bytes;
+    const size_t smem = SM_HEADER + ns * (size_t)stage_bytes(NT, MTW);
     a.nStages         = (uint32_t)ns;
-    a.nXbuf           = nxb;
-    a.xtile_doubles   = (uint32_t)(xtile_bytes / 8);
     HX_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     HX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, V2_THREADS, smem));
@@ -1006,12 +1000,8 @@ namespace hx
     const bool ordered = (p->scatter_mode == 0);
     if (ordered)
       {
-        // prefer two CTAs per SM (one scatters while the other contracts); fall back to one
-        int minb = 2;
-        while (nt > 1 && SM_HEADER + xtile_of(nt) + 3 * (size_t)STAGE_DOUBLES * 8 > 225 * 1024 - 1024)
-          nt >>= 1;
-        if (SM_HEADER + xtile_of(nt) + 3 * (size_t)STAGE_DOUBLES * 8 > 225 * 1024 / 2 - 1024)
-          minb = 1;
+        // two CTAs per SM: one scatters / waits for predecessors while the other contracts
+        const int minb = 2;
         a.nBt    = (B + nt * 8 - 1) / (nt * 8);
         a.nItems = p->C * a.nBt;
         a.epoch  = ++p->epoch;
@@ -1023,9 +1013,8 @@ namespace hx
             a.epoch  = ++p->epoch;
           }
         HX_CHECK((size_t)a.nItems <= p->d_flags.n, HX_ERR_INVALID, "flag array too small");
-        const size_t xt = xtile_of(nt);
 #define HX_ORD(NT_, MTW_, MINB_) \
-  (vec ? launch_ordered<NT_, MTW_, true, MINB_>(op, a, xt) : launch_ordered<NT_, MTW_, false, MINB_>(op, a, xt))
+  (vec ? launch_ordered<NT_, MTW_, true, MINB_>(op, a) : launch_ordered<NT_, MTW_, false, MINB_>(op, a))
 #define HX_ORD_M(NT_, MTW_) (minb == 2 ? HX_ORD(NT_, MTW_, 2) : HX_ORD(NT_, MTW_, 1))
         if (op->mtw == 1)
           switch (nt)

@@ -126,8 +126,9 @@ int hx_plan_set_scatter_mode(hx_plan *plan, int mode);
 /* Introspection used by the bit-exact parity tests of the integer work. */
 int hx_plan_num_colours(hx_plan *plan, uint32_t *n);
 int hx_plan_get_cell_colours(hx_plan *plan, uint32_t *colour /*[C]*/);
-/* ordered scatter: the processing order (position -> cell): the caller's order cut into blocks of 1024 cells
- * (HXB200_ORDER_BLOCK), each block stably sorted by colour. */
+/* ordered scatter: the processing order (position -> cell): a delay-D list schedule of the caller's order (a
+ * cell is placed only once all its placed neighbours sit >= D positions back; D = 4 x SM count, or
+ * HXB200_ORDER_DELAY). */
 int hx_plan_get_processing_order(hx_plan *plan, uint32_t *order /*[C]*/);
 /* ordered scatter: per cell (in processing order) the preceding cells it must wait for; pass NULLs to query nnz. */
 int hx_plan_get_wait_lists(hx_plan *plan, uint32_t *nnz, uint32_t *offsets /*[C+1]*/, uint32_t *preds /*[nnz]*/);

@@ -462,6 +462,74 @@ def cell_colouring(prob, shared_threshold: int = 8):
     return int(colour.max()) + 1 if prob.n_cells else 0, colour
 
 
+def processing_order(prob, delay: int, shared_threshold: int = 8):
+    """Specification of the ordered scatter's processing order (delay-D list schedule) and of the per-cell
+    predecessor lists.  Cells are swept in the caller's order - the order of the reference's sequential
+    scatter loop, basis/FECellWiseDataOperations.t.cpp:87-153 - but a cell is placed only when every
+    already-placed neighbour (a cell sharing a non-shared row) sits at least `delay` positions back; if no
+    cell qualifies, the one that qualifies soonest (ties: lowest index) is taken.
+    Returns (order[C], wait_off[C+1], wait_list): position -> cell, and for each position the sorted
+    positions of the immediately preceding toucher of each of the cell's non-shared rows."""
+    import heapq
+    ids = prob.cell_local_ids.astype(np.int64)
+    ncd = prob.num_cell_dofs.astype(np.int64)
+    off = np.concatenate(([0], np.cumsum(ncd)))
+    inc = np.bincount(ids, minlength=prob.n_local)
+    C = prob.n_cells
+    rows_of = [[int(r) for r in ids[off[c]:off[c + 1]] if inc[r] <= shared_threshold] for c in range(C)]
+    cells_of = {}
+    for c in range(C):
+        for r in rows_of[c]:
+            cells_of.setdefault(r, []).append(c)
+    ready = [0] * C
+    placed = [False] * C
+    eligible = list(range(C))
+    heapq.heapify(eligible)
+    waiting = []
+    order = []
+    for t in range(C):
+        while waiting and waiting[0][0] <= t:
+            key, x = heapq.heappop(waiting)
+            if not placed[x]:
+                if ready[x] <= t:
+                    heapq.heappush(eligible, x)
+                elif ready[x] != key:
+                    heapq.heappush(waiting, (ready[x], x))
+        c = None
+        while eligible:
+            x = heapq.heappop(eligible)
+            if placed[x]:
+                continue
+            if ready[x] > t:
+                heapq.heappush(waiting, (ready[x], x))
+                continue
+            c = x
+            break
+        while c is None:
+            key, x = heapq.heappop(waiting)
+            if placed[x]:
+                continue
+            if ready[x] != key:
+                heapq.heappush(waiting, (ready[x], x))
+                continue
+            c = x
+        placed[c] = True
+        order.append(c)
+        for r in rows_of[c]:
+            for nb in cells_of[r]:
+                if not placed[nb]:
+                    ready[nb] = t + delay
+    last = {}
+    wait_off, wait_list = [0], []
+    for w, c in enumerate(order):
+        pr = sorted({last[r] for r in rows_of[c] if r in last})
+        wait_list.extend(pr)
+        wait_off.append(len(wait_list))
+        for r in rows_of[c]:
+            last[r] = w
+    return np.array(order, np.uint32), np.array(wait_off, np.uint32), np.array(wait_list, np.uint32)
+
+
 def c2p_transpose(prob):
     """Parent-side view of the constraint CSR: parents ascending, entries in the reference's (row, entry)
     order — the order in which basis/ConstraintsInternal.cpp:110-170 adds into each parent."""

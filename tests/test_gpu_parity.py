@@ -156,31 +156,29 @@ def test_hx_bitwise_deterministic(capi, prob_full):
     assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
 
 
-def test_wait_lists_bit_exact(capi, prob_full):
-    """Ordered scatter: each cell waits for the immediately preceding toucher of each of its non-shared rows."""
+@pytest.mark.parametrize("delay", [0, 5, 23, 592])
+def test_processing_order_and_wait_lists_bit_exact(capi, prob_full, delay, monkeypatch):
+    """Ordered scatter: delay-D list schedule + per-cell predecessor lists match the oracle's specification."""
     p = prob_full
+    monkeypatch.setenv("HXB200_ORDER_DELAY", str(delay))
     plan = capi.Plan(p, max_block=8)
     off, preds = plan.wait_lists()
     order = plan.processing_order()
-    _, colour = plan.colours()
-    exp_order = np.concatenate([b0 + np.argsort(colour[b0:b0 + 1024], kind="stable")
-                                for b0 in range(0, p.n_cells, 1024)]).astype(np.uint32)
-    assert np.array_equal(order, exp_order)
-    ids = p.cell_local_ids.astype(np.int64)
-    coff = np.concatenate(([0], np.cumsum(p.num_cell_dofs.astype(np.int64))))
-    inc = np.bincount(ids, minlength=p.n_local)
-    last = -np.ones(p.n_local, np.int64)
-    exp_off, exp = [0], []
-    for w, c in enumerate(order):
-        rows = ids[coff[c]:coff[c + 1]]
-        rows = rows[inc[rows] <= 8]
-        pr = np.unique(last[rows][last[rows] >= 0])
-        exp.extend(pr.tolist())
-        exp_off.append(len(exp))
-        last[rows] = w
-    assert np.array_equal(off, np.array(exp_off, np.uint32))
-    assert np.array_equal(preds, np.array(exp, np.uint32))
-    assert all((preds[off[c]:off[c + 1]] < c).all() for c in range(p.n_cells))
+    o_order, o_off, o_preds = orc.processing_order(p, delay)
+    assert sorted(order.tolist()) == list(range(p.n_cells))
+    assert np.array_equal(order, o_order)
+    assert np.array_equal(off, o_off)
+    assert np.array_equal(preds, o_preds)
+    assert all((preds[off[w]:off[w + 1]] < w).all() for w in range(p.n_cells))
+    # H.X is independent of the processing order up to rounding
+    B = 8
+    op = capi.CellOp(plan)
+    X = synth.make_block(p, B)
+    dX, dY = plan.block(B, X), plan.block(B)
+    op.apply(dX, dY, True, False)
+    Yo = np.zeros_like(X)
+    orc.OracleWorld([p]).hx_apply([X.copy()], [Yo], True, False)
+    assert rel_l2_per_vector(dY.download(), Yo) < RTOL_HX
 
 
 @pytest.mark.parametrize("B", [3, 8, 32, 40])
