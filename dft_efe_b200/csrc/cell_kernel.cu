@@ -49,7 +49,8 @@ namespace hx
     const uint32_t *ids;
     const uint32_t *dest;
     const uint32_t *pids;
-    const uint32_t *cell_list; // coloured mode: cells of this launch; ordered mode: processing order
+    const uint32_t *cell_list; // coloured mode: cells of this launch
+    const ItemDesc *items;     // ordered mode: descriptors in processing order
     const uint32_t *wait_off;
     const uint32_t *wait_list;
     uint32_t *      flags;
@@ -180,23 +181,24 @@ namespace hx
   }
 
   // shared-memory header of the ordered kernel (bytes from the dynamic smem base, 128-B aligned)
-  constexpr int SM_FULL   = 0;                 // MAX_STAGES x 8
-  constexpr int SM_EMPTY  = 64;                // MAX_STAGES x 8
-  constexpr int SM_Q1     = 128;               // QD x 32   (A-stream warp -> gather warp)
-  constexpr int SM_Q2     = SM_Q1 + QD * 32;   // QD x 32   (A-stream warp -> DMMA warps)
-  constexpr int SM_HEADER = SM_Q2 + QD * 32;   // 1152
+  constexpr int SM_FULL   = 0;               // MAX_STAGES x 8
+  constexpr int SM_EMPTY  = 64;              // MAX_STAGES x 8
+  constexpr int SM_PRED   = 128;             // 2 x 8: predecessors of item (it & 1) have scattered
+  constexpr int SM_DONE   = 144;             // 2 x 8: all DMMA warps have scattered item (it & 1)
+  constexpr int SM_Q      = 256;             // QD x 32: item queue, producer warp -> DMMA warps + sync warp
+  constexpr int SM_HEADER = SM_Q + QD * 32;  // 768
 
-  // what the three roles need to know about a work item; loaded once (A-stream warp) and handed on in smem
+  // queue entry: what the DMMA warps and the sync warp need to know about a work item
   struct ItemInfo
   {
     uint32_t tag; // item index + 1; 0 = slot empty; ITEM_END = no more work
-    uint32_t ids_off, n, nproj, proj_off, wait_off, nwait, pad;
+    uint32_t ids_off, n, nproj, wait_off, nwait;
   };
   __device__ __forceinline__ void
   item_store(uint32_t addr, const ItemInfo &it)
   {
-    asm volatile("st.volatile.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr + 16), "r"(it.proj_off), "r"(it.wait_off),
-                 "r"(it.nwait), "r"(it.pad)
+    asm volatile("st.volatile.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr + 16), "r"(it.wait_off), "r"(it.nwait),
+                 "r"(0u), "r"(0u)
                  : "memory");
     asm volatile("st.volatile.shared.v2.u32 [%0], {%1,%2};" ::"r"(addr + 8), "r"(it.n), "r"(it.nproj) : "memory");
     st_volatile_shared(addr + 4, it.ids_off);
@@ -207,10 +209,11 @@ namespace hx
   item_load_payload(uint32_t addr, ItemInfo &it)
   {
     __threadfence_block();
+    uint32_t d0, d1;
     it.ids_off = ld_volatile_shared(addr + 4);
     asm volatile("ld.volatile.shared.v2.u32 {%0,%1}, [%2];" : "=r"(it.n), "=r"(it.nproj) : "r"(addr + 8) : "memory");
     asm volatile("ld.volatile.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(it.proj_off), "=r"(it.wait_off), "=r"(it.nwait), "=r"(it.pad)
+                 : "=r"(it.wait_off), "=r"(it.nwait), "=r"(d0), "=r"(d1)
                  : "r"(addr + 16)
                  : "memory");
   }
@@ -248,129 +251,106 @@ namespace hx
       {
         for (uint32_t s = 0; s < NS; ++s)
           {
-            mbar_init(sbase + SM_FULL + 8 * s, 33); // A-stream arrive.expect_tx + 32 gather lanes
+            mbar_init(sbase + SM_FULL + 8 * s, 33); // lane 0's arrive.expect_tx (A) + 32 gather lanes (X)
             mbar_init(sbase + SM_EMPTY + 8 * s, CWARPS);
           }
-        for (int q = 0; q < 2 * QD; ++q)
-          st_volatile_shared(sbase + SM_Q1 + 32 * q, 0u);
+        for (int b = 0; b < 2; ++b)
+          {
+            mbar_init(sbase + SM_PRED + 8 * b, 1);
+            mbar_init(sbase + SM_DONE + 8 * b, CWARPS);
+          }
+        for (int q = 0; q < QD; ++q)
+          st_volatile_shared(sbase + SM_Q + 32 * q, 0u);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
       }
     __syncthreads();
 
     if (warp == CWARPS)
       {
-        // ------------------------------ A-stream warp (one elected lane) ------------------------------
-        if (lane == 0)
-          {
-            uint32_t stage = 0, ph = 0;
-            // a cell matrix is read once per apply when one column tile covers B: keep it from evicting
-            // the X / Y lines that neighbouring cells are about to reuse
-            uint64_t evict_first;
-            asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(evict_first));
-            const bool once = (a.nBt == 1);
-            // the next item is claimed (and its metadata fetched) while the current one streams
-            uint32_t w = atomicAdd(a.counters, 1u);
-            CellMeta cm;
-            uint32_t wo = 0, nwait = 0;
-            if (w < a.nItems)
-              {
-                const uint32_t pidx = w / a.nBt;
-                cm                  = a.meta[a.cell_list[pidx]];
-                wo                  = a.wait_off[pidx];
-                nwait               = a.wait_off[pidx + 1] - wo;
-              }
-            for (uint32_t it = 0;; ++it)
-              {
-                const uint32_t q1 = sbase + SM_Q1 + 32 * (it % QD), q2 = sbase + SM_Q2 + 32 * (it % QD);
-                while (ld_volatile_shared(q1) != 0u || ld_volatile_shared(q2) != 0u)
-                  {
-                  }
-                if (w >= a.nItems)
-                  {
-                    st_volatile_shared(q1, ITEM_END);
-                    st_volatile_shared(q2, ITEM_END);
-                    break;
-                  }
-                ItemInfo info;
-                info.tag = w + 1u, info.ids_off = cm.ids_off, info.n = cm.n, info.nproj = cm.nproj;
-                info.proj_off = cm.proj_off, info.wait_off = wo, info.nwait = nwait, info.pad = 0;
-                item_store(q1, info);
-                item_store(q2, info);
-                const int     nKC = ((int)(cm.n + cm.nproj) + KROWS - 1) / KROWS;
-                const int     nMt = ((int)cm.n + 7) >> 3;
-                const double *src = a.packed + cm.h_off;
-                // claim + prefetch the next item
-                w = atomicAdd(a.counters, 1u);
-                if (w < a.nItems)
-                  {
-                    const uint32_t pidx = w / a.nBt;
-                    cm                  = a.meta[a.cell_list[pidx]];
-                    wo                  = a.wait_off[pidx];
-                    nwait               = a.wait_off[pidx + 1] - wo;
-                  }
-                for (int mc = 0; mc < nMt; mc += MPC)
-                  {
-                    const int      mtc   = min(MPC, nMt - mc);
-                    const uint32_t bytes = (uint32_t)mtc * KC * 256u;
-                    for (int kc = 0; kc < nKC; ++kc)
-                      {
-                        mbar_wait(sbase + SM_EMPTY + 8 * stage, ph ^ 1u);
-                        mbar_arrive_expect_tx(sbase + SM_FULL + 8 * stage, bytes);
-                        const uint32_t dst = sbase + SM_HEADER + stage * S_BYTES;
-                        if (once)
-                          bulk_g2s_hint(dst, src, bytes, sbase + SM_FULL + 8 * stage, evict_first);
-                        else
-                          bulk_g2s(dst, src, bytes, sbase + SM_FULL + 8 * stage);
-                        src += bytes / 8;
-                        if (++stage == NS)
-                          {
-                            stage = 0;
-                            ph ^= 1u;
-                          }
-                      }
-                  }
-              }
-          }
-      }
-    else if (warp == CWARPS + 1)
-      {
-        // ------------------------------------ gather warp ------------------------------------
-        // per stage: the KROWS rows k of X (k < n), of V C^H X (n <= k < ktot) or zeros, columns b0..b0+BT-1
+        // ---------------- producer warp: claims items, streams A (TMA bulk), gathers X (cp.async) ----------------
         constexpr int CPR = VEC ? BT / 2 : BT; // copies per row (<= 32)
         constexpr int RPI = 32 / CPR;          // rows per warp instruction
         const int     cc  = lane % CPR;
         const int     rr  = lane / CPR;
         uint32_t      stage = 0, ph = 0;
+        // a cell matrix is read once per apply when one column tile covers B: keep it from evicting
+        // the X / Y lines that neighbouring cells are about to reuse
+        uint64_t evict_first;
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(evict_first));
+        const bool once = (a.nBt == 1);
+        // claims run two items ahead, descriptors one item ahead (all lanes hold the same values)
+        auto claim = [&]() -> uint32_t {
+          uint32_t v = 0;
+          if (lane == 0)
+            v = atomicAdd(a.counters, 1u);
+          return __shfl_sync(0xffffffffu, v, 0);
+        };
+        auto fetch = [&](uint32_t w_) -> ItemDesc {
+          ItemDesc d;
+          d.n = 0;
+          if (w_ < a.nItems)
+            {
+              const uint4 *q  = reinterpret_cast<const uint4 *>(a.items + w_ / a.nBt);
+              const uint4  lo = __ldg(q), hi = __ldg(q + 1);
+              d.h_off    = ((unsigned long long)lo.y << 32) | lo.x;
+              d.ids_off  = lo.z;
+              d.n        = lo.w;
+              d.nproj    = hi.x;
+              d.proj_off = hi.y;
+              d.wait_off = hi.z;
+              d.nwait    = hi.w;
+            }
+          return d;
+        };
+        uint32_t w_cur  = claim();
+        ItemDesc d_cur  = fetch(w_cur);
+        uint32_t w_next = claim();
         for (uint32_t it = 0;; ++it)
           {
-            const uint32_t slot = sbase + SM_Q1 + 32 * (it % QD);
-            uint32_t       tag;
-            while ((tag = ld_volatile_shared(slot)) == 0u)
-              {
-              }
-            if (tag == ITEM_END)
-              break;
-            ItemInfo info;
-            info.tag = tag;
-            item_load_payload(slot, info);
-            __syncwarp();
+            const uint32_t slot = sbase + SM_Q + 32 * (it % QD);
             if (lane == 0)
-              st_volatile_shared(slot, 0u);
-            const int n = (int)info.n, ktot = n + (int)info.nproj;
+              while (ld_volatile_shared(slot) != 0u)
+                {
+                }
+            __syncwarp();
+            if (w_cur >= a.nItems)
+              {
+                if (lane == 0)
+                  st_volatile_shared(slot, ITEM_END);
+                break;
+              }
+            const ItemDesc d = d_cur;
+            const uint32_t w = w_cur;
+            if (lane == 0)
+              {
+                ItemInfo info;
+                info.tag = w + 1u, info.ids_off = d.ids_off, info.n = d.n, info.nproj = d.nproj;
+                info.wait_off = d.wait_off, info.nwait = d.nwait;
+                item_store(slot, info);
+              }
+            // prefetch: next descriptor (its index was claimed one item ago), and one more claim
+            w_cur  = w_next;
+            d_cur  = fetch(w_cur);
+            w_next = claim();
+
+            const int n = (int)d.n, ktot = n + (int)d.nproj;
             auto      row_code = [&](int k) -> uint32_t {
               if (k >= ktot)
                 return 0xffffffffu; // zero row
               if (k < n)
-                return __ldg(a.ids + info.ids_off + k);
-              return 0x80000000u | __ldg(a.pids + info.proj_off + (k - n));
+                return __ldg(a.ids + d.ids_off + k);
+              return 0x80000000u | __ldg(a.pids + d.proj_off + (k - n));
             };
-            const uint32_t b0    = ((tag - 1u) % a.nBt) * BT;
+            const uint32_t b0    = (w % a.nBt) * BT;
             const int      nKC   = (ktot + KROWS - 1) / KROWS;
             const int      nMt   = (n + 7) >> 3;
             const uint32_t col   = b0 + (VEC ? cc * 2 : cc);
             const bool     colok = col < a.B;
+            const double * srcA  = a.packed + d.h_off;
             for (int mc = 0; mc < nMt; mc += MPC)
               {
+                const int      mtc   = min(MPC, nMt - mc);
+                const uint32_t bytes = (uint32_t)mtc * KC * 256u;
                 // row codes: lane l holds row 32*j + l of the current / next block of 32 rows
                 uint32_t code = row_code(lane), code_next = row_code(32 + lane);
                 for (int kc = 0; kc < nKC; ++kc)
@@ -382,7 +362,18 @@ namespace hx
                         code_next = row_code((kc / SPB + 1) * 32 + lane);
                       }
                     mbar_wait(sbase + SM_EMPTY + 8 * stage, ph ^ 1u);
-                    const uint32_t xs = sbase + SM_HEADER + stage * S_BYTES + A_BYTES;
+                    const uint32_t st_addr = sbase + SM_HEADER + stage * S_BYTES;
+                    const uint32_t full    = sbase + SM_FULL + 8 * stage;
+                    if (lane == 0)
+                      {
+                        mbar_arrive_expect_tx(full, bytes);
+                        if (once)
+                          bulk_g2s_hint(st_addr, srcA, bytes, full, evict_first);
+                        else
+                          bulk_g2s(st_addr, srcA, bytes, full);
+                      }
+                    srcA += bytes / 8;
+                    const uint32_t xs = st_addr + A_BYTES;
 #pragma unroll
                     for (int r = 0; r < KROWS; r += RPI)
                       {
@@ -397,7 +388,7 @@ namespace hx
                         else
                           cp_async_zfill8(dst, src, ok ? 8u : 0u);
                       }
-                    cp_async_mbar_arrive_noinc(sbase + SM_FULL + 8 * stage);
+                    cp_async_mbar_arrive_noinc(full);
                     if (++stage == NS)
                       {
                         stage = 0;
@@ -407,13 +398,49 @@ namespace hx
               }
           }
       }
+    else if (warp == CWARPS + 1)
+      {
+        // ---------------- sync warp: waits for the predecessors' stamps, publishes this item's stamp ----------------
+        for (uint32_t it = 0;; ++it)
+          {
+            const uint32_t slot = sbase + SM_Q + 32 * (it % QD);
+            ItemInfo       info;
+            while ((info.tag = ld_volatile_shared(slot)) == 0u)
+              {
+              }
+            if (info.tag == ITEM_END)
+              break;
+            item_load_payload(slot, info);
+            const uint32_t w = info.tag - 1u, bt = w % a.nBt;
+            // the acquire loads order the DMMA warps' read-modify-writes (released to them through the
+            // mbarrier) after the predecessors' stores
+            for (uint32_t i = lane; i < info.nwait; i += 32)
+              {
+                const uint32_t *f = a.flags + (size_t)__ldg(a.wait_list + info.wait_off + i) * a.nBt + bt;
+                while (ld_acquire_gpu(f) != a.epoch)
+                  {
+                  }
+              }
+            __syncwarp();
+            if (lane == 0)
+              mbar_arrive(sbase + SM_PRED + 8 * (it & 1u));
+            // all DMMA warps have stored their rows of this item: publish (release, cumulative at gpu scope)
+            mbar_wait(sbase + SM_DONE + 8 * (it & 1u), (it >> 1) & 1u);
+            if (lane == 0)
+              {
+                st_release_gpu(a.flags + w, a.epoch);
+                st_volatile_shared(slot, 0u); // queue slot free again
+              }
+            __syncwarp();
+          }
+      }
     else
       {
         // ------------------------------------ DMMA warps ------------------------------------
         uint32_t stage = 0, ph = 0;
         for (uint32_t it = 0;; ++it)
           {
-            const uint32_t slot = sbase + SM_Q2 + 32 * (it % QD);
+            const uint32_t slot = sbase + SM_Q + 32 * (it % QD);
             ItemInfo       info;
             while ((info.tag = ld_volatile_shared(slot)) == 0u)
               {
@@ -422,18 +449,12 @@ namespace hx
               break;
             item_load_payload(slot, info);
             const uint32_t w    = info.tag - 1u;
-            const uint32_t bt   = w % a.nBt;
             const int      n    = (int)info.n;
             const int      nKC  = (n + (int)info.nproj + KROWS - 1) / KROWS;
             const int      nMt  = (n + 7) >> 3;
             const uint32_t B    = a.B;
-            const uint32_t b0   = bt * BT;
-            const uint32_t wo = info.wait_off, nwait = info.nwait;
+            const uint32_t b0   = (w % a.nBt) * BT;
             const int      xoff = A_BYTES / 8 + (lane & 3) * LDX + (lane >> 2); // B fragment inside a stage
-            // predecessor stamps to poll (indices fetched early)
-            uint32_t pred = 0;
-            if ((uint32_t)tid < nwait)
-              pred = __ldg(a.wait_list + wo + tid);
 
             for (int mc = 0; mc < nMt; mc += MPC)
               {
@@ -493,20 +514,8 @@ namespace hx
                         ph ^= 1u;
                       }
                   }
-                if (mc == 0 && nwait)
-                  {
-                    // wait until the preceding toucher of every row of this cell has scattered; the acquire
-                    // loads + the CTA barrier order every compute thread's RMW after the predecessors' stores
-                    for (uint32_t i = tid; i < nwait; i += CTHREADS)
-                      {
-                        const uint32_t  pi = (i == (uint32_t)tid) ? pred : __ldg(a.wait_list + wo + i);
-                        const uint32_t *f  = a.flags + (size_t)pi * a.nBt + bt;
-                        while (ld_acquire_gpu(f) != a.epoch)
-                          {
-                          }
-                      }
-                    bar_compute();
-                  }
+                if (mc == 0) // the preceding toucher of every row of this cell has scattered (sync warp)
+                  mbar_wait(sbase + SM_PRED + 8 * (it & 1u), (it >> 1) & 1u);
                 // ---- scatter-add (ordered: plain RMW through L2; shared rows: staging slot) ----
                 if (active)
                   {
@@ -558,14 +567,10 @@ namespace hx
                       }
                   }
               }
-            // publish completion of this (cell, column tile): the CTA barrier orders every compute thread's
-            // stores before thread 0's release store (cumulative at gpu scope)
-            bar_compute();
-            if (tid == 0)
-              {
-                st_release_gpu(a.flags + w, a.epoch);
-                st_volatile_shared(slot, 0u); // queue slot free again
-              }
+            // this warp's rows of the item are stored (the arrive releases them to the sync warp)
+            __syncwarp();
+            if (lane == 0)
+              mbar_arrive(sbase + SM_DONE + 8 * (it & 1u));
           }
         // last CTA out resets the work counters for the next launch
         if (tid == 0)
@@ -842,6 +847,17 @@ namespace hx
         op->max_mp = Mp > op->max_mp ? Mp : op->max_mp;
       }
     HX_TRY(op->d_meta.upload(op->h_meta));
+    {
+      std::vector<ItemDesc> items(p->C);
+      for (uint32_t w = 0; w < p->C; ++w)
+        {
+          const CellMeta &m = op->h_meta[p->h_order[w]];
+          ItemDesc &      d = items[w];
+          d.h_off = m.h_off, d.ids_off = m.ids_off, d.n = m.n, d.nproj = m.nproj, d.proj_off = m.proj_off;
+          d.wait_off = p->h_wait_off[w], d.nwait = p->h_wait_off[w + 1] - p->h_wait_off[w];
+        }
+      HX_TRY(op->d_items.upload(items));
+    }
     if (op->packed_doubles != tot || op->d_packed.p == nullptr)
       {
         HX_TRY(op->d_packed.alloc(tot));
@@ -988,6 +1004,7 @@ namespace hx
     a.dest      = p->d_dest.p;
     a.pids      = op->d_pids.p;
     a.cell_list = p->d_order.p;
+    a.items     = op->d_items.p;
     a.wait_off  = p->d_wait_off.p;
     a.wait_list = p->d_wait_list.p;
     a.flags     = p->d_flags.p;

@@ -122,6 +122,14 @@ namespace hx
     uint32_t           proj_off; // offset into cell_proj_local_ids
   };
 
+  // one work descriptor per processing position (ordered kernel): everything a CTA needs to know about a cell,
+  // fetched with a single 32-byte load after the work counter returns
+  struct ItemDesc
+  {
+    unsigned long long h_off;
+    uint32_t           ids_off, n, nproj, proj_off, wait_off, nwait;
+  };
+
   struct Comm; // NCCL communicator wrapper (comm.cu)
 } // namespace hx
 
@@ -215,6 +223,7 @@ struct hx_op
   // --- cell operator ---
   std::vector<hx::CellMeta> h_meta;
   hx::DevBuf<hx::CellMeta>  d_meta;
+  hx::DevBuf<hx::ItemDesc>  d_items; // [C] in processing order
   hx::DevBuf<double>        d_packed; // fragment-major packed cell matrices (+ projector columns)
   size_t                    packed_doubles = 0;
   bool                      have_matrices  = false;
