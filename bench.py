@@ -242,6 +242,31 @@ def run_ours(args):
         barrier()
         filt_ms = f0.elapsed_time(f1)
 
+        # subspace projections: X^T H X (one column batch, Op.apply + Gram GEMM) and the rotation X <- X Q
+        sub = {}
+        try:
+            dXs = plan.block(B, X)
+            H.xtopx(dXs, B)
+            plan.synchronize()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record(stream)
+            for _ in range(3):
+                H.xtopx(dXs, B)
+            g1.record(stream)
+            plan.synchronize()
+            sub["xtopx_ms"] = g0.elapsed_time(g1) / 3
+            Q = np.linalg.qr(np.random.default_rng(3).standard_normal((B, B)))[0]
+            plan.subspace_rotation(dXs, Q, True, False)
+            plan.synchronize()
+            g0.record(stream)
+            for _ in range(3):
+                plan.subspace_rotation(dXs, Q, True, False)
+            g1.record(stream)
+            plan.synchronize()
+            sub["rotation_ms"] = g0.elapsed_time(g1) / 3
+        except Exception as e:  # noqa: BLE001
+            sub["error"] = str(e)[:200]
+
         # end to end through the host-buffer entry point (pinned host memory, H2D + D2H every step)
         xh = torch.from_numpy(X).pin_memory()
         yh = torch.zeros_like(xh).pin_memory()
@@ -257,6 +282,7 @@ def run_ours(args):
         sampler.stop_flag = True
         sampler.join(timeout=2)
 
+    n_mod_rows = len(prob.row_ids) + (prob.n_ghost if nranks > 1 else 0)
     tms = torch.tensor([ms, filt_ms, e2e_ms, cell_ms], dtype=torch.float64, device="cuda")
     if nranks > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
@@ -284,6 +310,13 @@ def run_ours(args):
             micro = capi.microbench()
         except Exception:
             pass
+        traffic, traffic_src = None, None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "cell_kernel_traffic.json")))
+            if tj.get("workload") == args.workload and nranks == 1:
+                traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
+        except Exception:
+            pass
         line = {
             "metric": METRIC, "value": N_global * B / (ms_per_step * 1e-3) / 1e9, "unit": UNIT, "n_gpus": nranks,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -297,18 +330,21 @@ def run_ours(args):
                                     % (8 * S2 / 1e9, 16 * B * prob.n_local / 1e9)},
             "e2e": {"value": N_global * B / (e2e_ms * 1e-3) / 1e9, "unit": UNIT,
                     "h2d_bytes_per_step": 8 * B * prob.n_local,
-                    "d2h_bytes_per_step": 8 * B * prob.n_local * (2 if len(prob.row_ids) else 1), "ms_per_step": e2e_ms},
+                    "d2h_bytes_per_step": 8 * B * (prob.n_local + n_mod_rows), "ms_per_step": e2e_ms,
+                    "call": "hx_op_apply_host (pinned host X, Y; H2D X, apply, D2H Y + the rows of X the operator modified)"},
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
-                         "kernel": "cell_apply_kernel (all colour launches of one apply)",
+                         "frac": achieved / hbm_peak, "traffic": traffic, "traffic_source": traffic_src,
+                         "peak_source": peak_src,
+                         "kernel": "cell_apply_ordered_kernel (one persistent launch per apply)",
                          "kernel_ms_per_apply": cell_ms_per_apply, "kernel_share_of_step": cell_ms_per_apply / ms_per_step,
                          "algorithmic_bytes_per_apply": alg_bytes, "flops_per_apply": flops,
                          "tensor": {"achieved_tflops": flops / (cell_ms_per_apply * 1e-3) / 1e12,
                                     "dmma_peak_tflops_measured": micro["dmma_tflops"] if micro else None,
                                     "dfma_peak_tflops_measured": micro["dfma_tflops"] if micro else None,
                                     "copy_gbs_measured": micro["copy_gbs"] if micro else None}},
+            "subspace": sub,
             "chebyshev_filter": {"degree": degree, "seconds_per_scf_iter": filt_ms * 1e-3, "ms_per_degree": filt_ms / degree,
                                  "fused_recurrence": True},
         }

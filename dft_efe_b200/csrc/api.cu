@@ -188,6 +188,7 @@ namespace hx
         p->h_par_off.push_back((uint32_t)p->h_par_child.size());
       }
     p->nPar = (uint32_t)p->h_par_ids.size();
+    p->h_row_ids.assign(m->row_ids, m->row_ids + p->nR);
     HX_TRY(p->d_row_ids.upload(m->row_ids, p->nR));
     HX_TRY(p->d_row_sizes.upload(m->row_sizes, p->nR));
     HX_TRY(p->d_row_offsets.upload(m->row_offsets, p->nR));
@@ -956,9 +957,30 @@ extern "C"
     HX_CUDA(cudaMemcpyAsync(dX, Xh, bytes, cudaMemcpyHostToDevice, p->stream));
     HX_TRY(op_apply(op, dX, dY, B, ugx, ugy));
     HX_CUDA(cudaMemcpyAsync(Yh, dY, bytes, cudaMemcpyDeviceToHost, p->stream));
-    if (p->nR || ugx)
-      HX_CUDA(cudaMemcpyAsync(Xh, dX, bytes, cudaMemcpyDeviceToHost, p->stream));
+    // X is modified in place by the operator (OperatorContext.h:98-101): only the constrained rows (hanging-node
+    // fill) and, after a ghost update, the ghost rows change - bring just those back
+    const bool     ghosts = ugx && p->nranks > 1 && p->n_ghost > 0;
+    const uint32_t nmod   = p->nR + (ghosts ? p->n_ghost : 0);
+    if (nmod)
+      {
+        if (p->d_modrows.n != (size_t)p->nR + p->n_ghost)
+          {
+            std::vector<uint32_t> rows(p->h_row_ids);
+            for (uint32_t g = 0; g < p->n_ghost; ++g)
+              rows.push_back(p->n_owned + g);
+            HX_TRY(p->d_modrows.upload(rows));
+            p->h_modrows = rows;
+            HX_CUDA(cudaDeviceSynchronize());
+          }
+        double *buf;
+        HX_TRY(p->get_scratch(7, &buf));
+        HX_TRY(launch_pack(p, dX, B, p->d_modrows.p, nmod, buf));
+        HX_TRY(p->ensure_pinned((size_t)nmod * B * sizeof(double)));
+        HX_CUDA(cudaMemcpyAsync(p->h_pinned, buf, (size_t)nmod * B * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+      }
     HX_CUDA(cudaStreamSynchronize(p->stream));
+    for (uint32_t i = 0; i < nmod; ++i)
+      memcpy(Xh + (size_t)p->h_modrows[i] * B, p->h_pinned + (size_t)i * B, (size_t)B * sizeof(double));
     return HX_OK;
   }
 

@@ -158,6 +158,8 @@ struct hx_plan
   std::vector<double>   h_par_w;
   hx::DevBuf<uint32_t>  d_par_ids, d_par_off, d_par_child;
   hx::DevBuf<double>    d_par_w;
+  std::vector<uint32_t> h_row_ids, h_modrows; // constrained rows; rows an apply may modify in X (+ ghosts)
+  hx::DevBuf<uint32_t>  d_modrows;
   hx::DevBuf<uint32_t>  d_rowinfo; // [n_local]: 0xFFFFFFFF free, 0xFFFFFFFE constrained, else parent index
 
   // colouring of cells over non-shared DoFs; shared (high-incidence, e.g. enrichment) rows go

@@ -1,0 +1,112 @@
+"""One rank of the multi-GPU parity run (launched by tests/test_multi_gpu.py through torch.distributed.run).
+
+Every rank builds its own partition of the same synthetic mesh (synth.build_problem(only_rank=r)), creates a
+plan on its GPU, joins the NCCL communicator (unique id broadcast over torch.distributed), and runs the H.X
+apply, the Chebyshev filter, X^T H X and the column norms through the C ABI.  The checker is the CPU oracle of
+the WHOLE rank set computed redundantly on every rank (OracleWorld over all partitions, in-process "MPI").
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def rel(a, b):
+    den = np.linalg.norm(b, axis=0)
+    den[den == 0] = 1.0
+    return float((np.linalg.norm(a - b, axis=0) / den).max())
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    from dft_efe_b200 import capi, synth
+    from oracle import oracle as orc
+
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    capi.check(capi.lib().hx_set_device(local))
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    nc = (4, 4, 3 * world)
+    L = np.array(nc, float)
+    atoms = np.array([[0.5 * L[0], 0.5 * L[1], 0.5 * L[2]], [0.3 * L[0], 0.7 * L[1], 0.26 * L[2]]])
+    spec = synth.MeshSpec(ncell=nc, p=3, refine_mask=synth.refine_ball(nc, 1.0, [atoms[0]], 0.9), atoms=atoms,
+                          n_enr_per_atom=3, enr_cutoff=1.2, n_proj_per_atom=2, proj_cutoff=1.0, nranks=world)
+    probs = synth.build_problem(spec)          # all partitions: needed by the oracle world
+    mine = synth.build_problem(spec, only_rank=rank)[0]
+    ref = probs[rank]
+    for name in ("cell_local_ids", "row_ids", "col_ids"):
+        assert np.array_equal(getattr(mine, name), getattr(ref, name)), f"only_rank build differs in {name}"
+
+    B = 16
+    plan = capi.Plan(mine, max_block=B)
+    uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        uid.copy_(torch.frombuffer(bytearray(capi.comm_unique_id()), dtype=torch.uint8))
+    dist.broadcast(uid, 0)
+    plan.attach_comm(bytes(uid.cpu().numpy().tobytes()))
+
+    H = capi.CellOp(plan)
+    minv = capi.DiagOp(plan, mine.diag_inv, mine.enr_block_inv, capi.DIAG_OEFE_ATOMBLOCK)
+    W = orc.OracleWorld(probs)
+    Xs = [synth.make_block(q, B) for q in probs]
+    for q, x in zip(probs, Xs):          # start from stale ghosts: the update must fix them
+        x[q.n_owned:] = 7.0
+    errs = {}
+
+    # ---- ghost communicator ----
+    d = plan.block(B, Xs[rank])
+    plan.update_ghost_values(d)
+    Xo = [x.copy() for x in Xs]
+    W.update_ghost_values(Xo)
+    errs["update_ghost"] = float(np.abs(d.download() - Xo[rank]).max())
+    d = plan.block(B, Xs[rank])
+    plan.accumulate_add_locally_owned(d)
+    Yo = [x.copy() for x in Xs]
+    W.accumulate_add_locally_owned(Yo)
+    errs["accumulate_add"] = rel(d.download()[:mine.n_owned], Yo[rank][:mine.n_owned])
+
+    # ---- H.X with ghost update on both sides ----
+    dX, dY = plan.block(B, Xs[rank]), plan.block(B)
+    H.apply(dX, dY, True, True)
+    Xo = [x.copy() for x in Xs]
+    Yo = [np.zeros_like(x) for x in Xs]
+    W.hx_apply(Xo, Yo, True, True)
+    errs["hx"] = rel(dY.download(), Yo[rank])
+    errs["hx_x_modified"] = rel(dX.download(), Xo[rank])
+
+    # ---- Chebyshev filter ----
+    dX, dF = plan.block(B, Xs[rank]), plan.block(B)
+    capi.chebyshev_filter(H, minv, dX, dF, 6, -3.0, 1.0, 60.0)
+    F = W.chebyshev_filter([x.copy() for x in Xs], 6, -3.0, 1.0, 60.0)
+    errs["cheb"] = rel(dF.download()[:mine.n_owned], F[rank][:mine.n_owned])
+
+    # ---- X^T H X (NCCL all-reduce of the Gram blocks) and column norms ----
+    dX = plan.block(B, Xs[rank])
+    S = H.xtopx(dX, 8)
+    So = W.xtopx([x.copy() for x in Xs], lambda a, b, c, d_: W.hx_apply(a, b, c, d_), 8)
+    errs["xtopx"] = float(np.abs(S - So).max() / np.abs(So).max())
+    dX = plan.block(B, Xs[rank])
+    nr = plan.l2_norms(dX)
+    errs["l2"] = float(np.abs(nr - W.l2_norms(Xs)).max() / np.abs(nr).max())
+
+    tol = {"update_ghost": 0.0, "accumulate_add": 1e-14, "hx": 1e-12, "hx_x_modified": 1e-14, "cheb": 1e-11,
+           "xtopx": 1e-12, "l2": 1e-13}
+    bad = {k: v for k, v in errs.items() if not v <= tol[k]}
+    print(f"[rank {rank}/{world}] " + " ".join(f"{k}={v:.2e}" for k, v in errs.items()), flush=True)
+    t = torch.tensor([len(bad)], device="cuda")
+    dist.all_reduce(t)
+    dist.barrier()
+    dist.destroy_process_group()
+    if int(t.item()):
+        print(f"[rank {rank}] FAILED: {bad}", flush=True)
+        sys.exit(1)
+
+
+if __name__ == "__main__":
+    main()
