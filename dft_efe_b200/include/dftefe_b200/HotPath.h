@@ -1,0 +1,664 @@
+// HotPath.h — C++17 host-side mirror of the reference's operator-context API for the H.X / Chebyshev /
+// Rayleigh-Ritz hot path, implemented on top of the C ABI of libhxb200 (include/hxb200.h).
+//
+// Names, argument meaning and error behaviour follow the reference so that its call sites compile against
+// these classes unchanged for MemorySpace::DEVICE:
+//   dftefe::linearAlgebra::OperatorContext<double,double,DEVICE>::apply(X, Y, updateGhostX, updateGhostY)
+//                                                   (reference src/linearAlgebra/OperatorContext.h:48-111)
+//   dftefe::linearAlgebra::MultiVector<double,DEVICE> (src/linearAlgebra/MultiVector.h:134-508)
+//   dftefe::ksdft::KohnShamOperatorContextFE          (src/ksdft/KohnShamOperatorContextFE.h:57-157)
+//   dftefe::basis::{CFEOverlapInverseOpContextGLL, OEFEAtomBlockOverlapInvOpContextGLL,
+//                   OrthoEFEOverlapOperatorContext}   (src/basis/*OpContext*.h, apply only)
+//   dftefe::linearAlgebra::{ChebyshevFilter, ResidualChebyshevFilterGEP}
+//                                                   (src/linearAlgebra/ChebyshevFilter.h:54-113)
+//   computeXTransOpX / subspaceRotation              (src/linearAlgebra/RayleighRitzEigenSolver.t.cpp:685-844,
+//                                                    src/linearAlgebra/ElpaScalapackOperations.t.cpp:185-335)
+// The reference's FEBasisManager / ConstraintsLocal / MPIPatternP2P need deal.II and MPI; what the hot path
+// consumes of them is their flat index arrays, carried here by basis::FEBasisManagerArrays (INTEGRATION.md
+// lists the getter each field is filled from).  Errors surface as utils::HxException, thrown the way the
+// reference's utils::throwException does (src/utils/Exceptions.h:128-132).  There is no CPU fallback.
+#ifndef DFTEFE_B200_HOTPATH_H
+#define DFTEFE_B200_HOTPATH_H
+
+#include <cstdint>
+#include <cstring>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../../include/hxb200.h"
+
+namespace dftefe
+{
+  using size_type        = unsigned int;  // src/utils/TypeConfig.h:8
+  using global_size_type = unsigned long; // src/utils/TypeConfig.h:9
+
+  namespace utils
+  {
+    enum class MemorySpace
+    {
+      HOST,
+      HOST_PINNED,
+      DEVICE
+    }; // src/utils/MemorySpaceType.h:36-41
+
+    class HxException : public std::runtime_error
+    {
+    public:
+      HxException(int code, const std::string &msg)
+        : std::runtime_error(msg)
+        , d_code(code)
+      {}
+      int
+      code() const
+      {
+        return d_code;
+      }
+
+    private:
+      int d_code;
+    };
+
+    inline void
+    throwException(bool condition, const std::string &msg = "")
+    {
+      if (!condition)
+        throw HxException(HX_ERR_INVALID, msg);
+    }
+
+    inline void
+    hxCheck(int rc)
+    {
+      if (rc != HX_OK)
+        throw HxException(rc, std::string("libhxb200: ") + hx_last_error());
+    }
+  } // namespace utils
+
+  namespace utils
+  {
+    namespace mpi
+    {
+      // the getters of utils::mpi::MPIPatternP2P the ghost communicator consumes (src/utils/MPIPatternP2P.h:425-459)
+      struct MPIPatternP2PArrays
+      {
+        size_type              localOwnedSize = 0, localGhostSize = 0;
+        std::vector<size_type> ghostProcIds, ghostLocalIndicesRanges, ghostLocalIndicesForGhostProcs;
+        std::vector<size_type> targetProcIds, numOwnedIndicesForTargetProcs, ownedLocalIndicesForTargetProcs;
+
+        hx_halo_desc
+        desc() const
+        {
+          hx_halo_desc h;
+          h.n_owned                     = localOwnedSize;
+          h.n_ghost                     = localGhostSize;
+          h.n_ghost_procs               = (uint32_t)ghostProcIds.size();
+          h.ghost_proc_ids              = ghostProcIds.data();
+          h.ghost_ranges                = ghostLocalIndicesRanges.data();
+          h.ghost_local_ids             = ghostLocalIndicesForGhostProcs.data();
+          h.n_target_procs              = (uint32_t)targetProcIds.size();
+          h.target_proc_ids             = targetProcIds.data();
+          h.num_owned_for_target        = numOwnedIndicesForTargetProcs.data();
+          h.owned_local_ids_for_targets = ownedLocalIndicesForTargetProcs.data();
+          return h;
+        }
+      };
+    } // namespace mpi
+  }   // namespace utils
+
+  namespace basis
+  {
+    // What FEBasisManager + ConstraintsLocal hand to the hot path, as flat arrays
+    // (src/basis/FEBasisManager.h:143-160, FEBasisManager.t.cpp:414-428,545-557;
+    //  src/basis/CFEConstraintsLocalDealii.t.cpp:286-462).
+    struct FEBasisManagerArrays
+    {
+      int                             rank = 0, nRanks = 1;
+      utils::mpi::MPIPatternP2PArrays mpiPatternP2P;
+      size_type                       nLocallyOwnedClassicalDofs = 0;
+      std::vector<size_type>          nLocallyOwnedCellDofs;       // per cell
+      std::vector<size_type>          locallyOwnedCellLocalDofIds; // concatenated
+      std::vector<size_type>          rowConstraintsIdsLocal, rowConstraintsSizes, columnConstraintsAccumulated,
+        columnConstraintsIdsLocal;
+      std::vector<double> columnConstraintsValues, constraintsInhomogenities;
+    };
+
+    // AtomCenterNonLocalOpContextFE's apply-time data (src/basis/AtomCenterNonLocalOpContextFE.t.cpp:478-494,595-619)
+    struct AtomCenterNonLocalArrays
+    {
+      utils::mpi::MPIPatternP2PArrays mpiPatternP2PProj;
+      std::vector<size_type>          numProjsInCells, locallyOwnedCellLocalProjectorIds;
+      std::vector<double>             cellWiseC, V;
+    };
+  } // namespace basis
+
+  namespace linearAlgebra
+  {
+    // One per GPU / MPI rank: owns the device copies of the index maps, the ghost communicator buffers and the
+    // stream (the role MPIPatternP2P + MPICommunicatorP2P + LinAlgOpContext<DEVICE> play together).
+    class DeviceContext
+    {
+    public:
+      DeviceContext(const basis::FEBasisManagerArrays &fe, size_type maxWaveFnBatch, void *cudaStream = nullptr)
+        : d_nLocal(fe.mpiPatternP2P.localOwnedSize + fe.mpiPatternP2P.localGhostSize)
+        , d_nOwned(fe.mpiPatternP2P.localOwnedSize)
+        , d_maxBlock(maxWaveFnBatch)
+      {
+        hx_mesh_desc m;
+        std::memset(&m, 0, sizeof(m));
+        m.struct_size       = sizeof(m);
+        m.rank              = fe.rank;
+        m.nranks            = fe.nRanks;
+        m.halo              = fe.mpiPatternP2P.desc();
+        m.n_owned_classical = fe.nLocallyOwnedClassicalDofs;
+        m.n_cells           = (uint32_t)fe.nLocallyOwnedCellDofs.size();
+        m.num_cell_dofs     = fe.nLocallyOwnedCellDofs.data();
+        m.cell_local_ids    = fe.locallyOwnedCellLocalDofIds.data();
+        m.n_constraint_rows = (uint32_t)fe.rowConstraintsIdsLocal.size();
+        m.row_ids           = fe.rowConstraintsIdsLocal.data();
+        m.row_sizes         = fe.rowConstraintsSizes.data();
+        m.row_offsets       = fe.columnConstraintsAccumulated.data();
+        m.col_ids           = fe.columnConstraintsIdsLocal.data();
+        m.col_vals          = fe.columnConstraintsValues.data();
+        m.inhom             = fe.constraintsInhomogenities.data();
+        m.max_block         = maxWaveFnBatch;
+        d_S2                = 0;
+        for (size_type n : fe.nLocallyOwnedCellDofs)
+          d_S2 += (size_t)n * n;
+        utils::hxCheck(hx_plan_create(&d_plan, &m, cudaStream));
+      }
+      ~DeviceContext() { hx_plan_destroy(d_plan); }
+      DeviceContext(const DeviceContext &) = delete;
+      DeviceContext &
+      operator=(const DeviceContext &) = delete;
+
+      // multi-GPU: rank 0 calls uniqueId(), the application broadcasts the 128 bytes (MPI_Bcast), all attach
+      static std::vector<char>
+      uniqueId()
+      {
+        std::vector<char> id(128);
+        utils::hxCheck(hx_comm_unique_id(id.data()));
+        return id;
+      }
+      void
+      attachCommunicator(const std::vector<char> &id)
+      {
+        utils::throwException(id.size() == 128, "communicator id must be 128 bytes");
+        utils::hxCheck(hx_plan_attach_comm(d_plan, id.data()));
+      }
+      void
+      synchronize() const
+      {
+        utils::hxCheck(hx_plan_synchronize(d_plan));
+      }
+      hx_plan *
+      plan() const
+      {
+        return d_plan;
+      }
+      size_type
+      localSize() const
+      {
+        return d_nLocal;
+      }
+      size_type
+      locallyOwnedSize() const
+      {
+        return d_nOwned;
+      }
+      size_type
+      maxBlock() const
+      {
+        return d_maxBlock;
+      }
+      size_t
+      cellMatrixSize() const
+      {
+        return d_S2;
+      }
+
+    private:
+      hx_plan * d_plan = nullptr;
+      size_type d_nLocal, d_nOwned, d_maxBlock;
+      size_t    d_S2;
+    };
+
+    template <typename ValueType, utils::MemorySpace memorySpace>
+    class MultiVector;
+
+    // MultiVector<double, DEVICE>: data()[iDof*numVectors + iVec], owned rows then ghost rows
+    // (src/linearAlgebra/MultiVector.h:134-160).
+    template <>
+    class MultiVector<double, utils::MemorySpace::DEVICE>
+    {
+    public:
+      using value_type = double;
+      MultiVector(std::shared_ptr<const DeviceContext> ctx, size_type numVectors, double initVal = 0.0)
+        : d_ctx(std::move(ctx))
+        , d_numVectors(numVectors)
+      {
+        utils::throwException(numVectors >= 1 && numVectors <= d_ctx->maxBlock(),
+                              "MultiVector: numVectors outside [1, maxWaveFnBatch]");
+        utils::hxCheck(hx_device_alloc((void **)&d_data, bytes()));
+        setValue(initVal);
+      }
+      MultiVector(const MultiVector &u)
+        : MultiVector(u.d_ctx, u.d_numVectors)
+      {
+        std::vector<double> tmp(u.localSize() * (size_t)d_numVectors);
+        u.copyTo(tmp.data());
+        copyFrom(tmp.data());
+      }
+      MultiVector(MultiVector &&u) noexcept
+        : d_ctx(std::move(u.d_ctx))
+        , d_numVectors(u.d_numVectors)
+        , d_data(u.d_data)
+      {
+        u.d_data = nullptr;
+      }
+      ~MultiVector()
+      {
+        if (d_data)
+          hx_device_free(d_data);
+      }
+      double *
+      data()
+      {
+        return d_data;
+      }
+      const double *
+      data() const
+      {
+        return d_data;
+      }
+      double *
+      begin()
+      {
+        return d_data;
+      }
+      double *
+      end()
+      {
+        return d_data + (size_t)localSize() * d_numVectors;
+      }
+      void
+      setValue(const double val)
+      {
+        if (val == 0.0)
+          utils::hxCheck(hx_memset_zero(d_data, bytes()));
+        else
+          {
+            std::vector<double> tmp((size_t)localSize() * d_numVectors, val);
+            copyFrom(tmp.data());
+          }
+      }
+      // host <-> device transfer of the whole local block (utils::MemoryTransfer<DEVICE,HOST> in the reference)
+      void
+      copyFrom(const double *host)
+      {
+        utils::hxCheck(hx_memcpy_h2d(d_data, host, bytes()));
+      }
+      void
+      copyTo(double *host) const
+      {
+        utils::hxCheck(hx_memcpy_d2h(host, d_data, bytes()));
+      }
+      std::vector<double>
+      l2Norms() const
+      {
+        std::vector<double> out(d_numVectors);
+        utils::hxCheck(hx_l2_norms(d_ctx->plan(), d_data, d_numVectors, out.data()));
+        return out;
+      }
+      size_type
+      getNumberComponents() const
+      {
+        return d_numVectors;
+      }
+      size_type
+      numVectors() const
+      {
+        return d_numVectors;
+      }
+      void
+      updateGhostValues(const size_type /*communicationChannel*/ = 0)
+      {
+        utils::hxCheck(hx_update_ghost_values(d_ctx->plan(), d_data, d_numVectors));
+      }
+      void
+      accumulateAddLocallyOwned(const size_type /*communicationChannel*/ = 0)
+      {
+        utils::hxCheck(hx_accumulate_add_locally_owned(d_ctx->plan(), d_data, d_numVectors));
+      }
+      size_type
+      localSize() const
+      {
+        return d_ctx->localSize();
+      }
+      size_type
+      locallyOwnedSize() const
+      {
+        return d_ctx->locallyOwnedSize();
+      }
+      size_type
+      ghostSize() const
+      {
+        return d_ctx->localSize() - d_ctx->locallyOwnedSize();
+      }
+      const std::shared_ptr<const DeviceContext> &
+      getDeviceContext() const
+      {
+        return d_ctx;
+      }
+      bool
+      isCompatible(const MultiVector &rhs) const
+      {
+        return d_ctx == rhs.d_ctx;
+      }
+      friend void
+      swap(MultiVector &X, MultiVector &Y)
+      {
+        std::swap(X.d_ctx, Y.d_ctx);
+        std::swap(X.d_numVectors, Y.d_numVectors);
+        std::swap(X.d_data, Y.d_data);
+      }
+
+    private:
+      size_t
+      bytes() const
+      {
+        return (size_t)localSize() * d_numVectors * sizeof(double);
+      }
+      std::shared_ptr<const DeviceContext> d_ctx;
+      size_type                            d_numVectors;
+      double *                             d_data = nullptr;
+    };
+
+    // src/linearAlgebra/OperatorContext.h:48-111
+    template <typename ValueTypeOperator, typename ValueTypeOperand, utils::MemorySpace memorySpace>
+    class OperatorContext
+    {
+    public:
+      using ValueTypeUnion = double;
+      virtual ~OperatorContext() = default;
+      // X may be modified (ghost update + hanging-node fill); Y is fully overwritten
+      virtual void
+      apply(MultiVector<ValueTypeOperand, memorySpace> &X,
+            MultiVector<ValueTypeUnion, memorySpace> &  Y,
+            bool                                        updateGhostX = false,
+            bool                                        updateGhostY = false) const = 0;
+    };
+
+    using DeviceMultiVector     = MultiVector<double, utils::MemorySpace::DEVICE>;
+    using DeviceOperatorContext = OperatorContext<double, double, utils::MemorySpace::DEVICE>;
+
+    // operators implemented natively by libhxb200 expose their handle so the filters can run fused
+    class NativeOperator : public DeviceOperatorContext
+    {
+    public:
+      hx_op *
+      handle() const
+      {
+        return d_op;
+      }
+      void
+      apply(DeviceMultiVector &X, DeviceMultiVector &Y, bool updateGhostX = false, bool updateGhostY = false) const override
+      {
+        utils::throwException(X.getNumberComponents() == Y.getNumberComponents(),
+                              "apply: X and Y hold different numbers of vectors");
+        utils::hxCheck(hx_op_apply(d_op, X.data(), Y.data(), X.getNumberComponents(), updateGhostX, updateGhostY));
+      }
+      ~NativeOperator() override
+      {
+        if (d_op)
+          hx_op_destroy(d_op);
+      }
+
+    protected:
+      NativeOperator() = default;
+      hx_op *                              d_op = nullptr;
+      std::shared_ptr<const DeviceContext> d_ctx;
+    };
+  } // namespace linearAlgebra
+
+  namespace ksdft
+  {
+    // One summand of the cell Hamiltonian (Hamiltonian<T>::getLocal(), src/ksdft/Hamiltonian.h:33-52): S2 doubles,
+    // cells concatenated, each n_c x n_c row-major, in host or device memory.
+    struct LocalHamiltonianComponent
+    {
+      const double *cellMatrices = nullptr;
+      bool          onDevice     = false;
+    };
+
+    // KohnShamOperatorContextFE<double,double,double,double,DEVICE,3>
+    class KohnShamOperatorContextFE : public linearAlgebra::NativeOperator
+    {
+    public:
+      KohnShamOperatorContextFE(std::shared_ptr<const linearAlgebra::DeviceContext> ctx,
+                                const std::vector<LocalHamiltonianComponent> &      hamiltonianComponentsVec,
+                                const basis::AtomCenterNonLocalArrays *             nonLocal = nullptr)
+      {
+        d_ctx = std::move(ctx);
+        utils::hxCheck(hx_cellop_create(d_ctx->plan(), &d_op));
+        if (nonLocal)
+          {
+            hx_nonlocal_desc nl;
+            std::memset(&nl, 0, sizeof(nl));
+            nl.struct_size         = sizeof(nl);
+            nl.proj_halo           = nonLocal->mpiPatternP2PProj.desc();
+            nl.num_cell_proj       = nonLocal->numProjsInCells.data();
+            nl.cell_proj_local_ids = nonLocal->locallyOwnedCellLocalProjectorIds.data();
+            nl.cell_c              = nonLocal->cellWiseC.data();
+            nl.v                   = nonLocal->V.data();
+            utils::hxCheck(hx_cellop_set_nonlocal(d_op, &nl));
+          }
+        reinit(hamiltonianComponentsVec);
+      }
+
+      // src/ksdft/KohnShamOperatorContextFE.t.cpp:1240-1311: sum the components' cell matrices, (re)tile them
+      void
+      reinit(const std::vector<LocalHamiltonianComponent> &comps)
+      {
+        utils::throwException(!comps.empty(), "reinit: no Hamiltonian component");
+        const size_t S2 = d_ctx->cellMatrixSize();
+        if (comps.size() == 1)
+          {
+            utils::hxCheck(hx_cellop_set_matrices(d_op, comps[0].cellMatrices, comps[0].onDevice ? 1 : 0));
+            return;
+          }
+        double *sum = nullptr, *tmp = nullptr;
+        utils::hxCheck(hx_device_alloc((void **)&sum, S2 * sizeof(double)));
+        utils::hxCheck(hx_memset_zero(sum, S2 * sizeof(double)));
+        for (const auto &c : comps)
+          {
+            const double *src = c.cellMatrices;
+            if (!c.onDevice)
+              {
+                if (!tmp)
+                  utils::hxCheck(hx_device_alloc((void **)&tmp, S2 * sizeof(double)));
+                utils::hxCheck(hx_memcpy_h2d(tmp, c.cellMatrices, S2 * sizeof(double)));
+                src = tmp;
+              }
+            // flat axpby over S2 entries, in slabs that fit the 32-bit row count of the ABI
+            for (size_t o = 0; o < S2; o += (size_t)1 << 30)
+              {
+                const uint32_t n = (uint32_t)std::min<size_t>((size_t)1 << 30, S2 - o);
+                utils::hxCheck(hx_axpby(d_ctx->plan(), n, 1, 1.0, sum + o, 1.0, src + o, sum + o));
+              }
+          }
+        utils::hxCheck(hx_plan_synchronize(d_ctx->plan()));
+        utils::hxCheck(hx_cellop_set_matrices(d_op, sum, 1));
+        hx_device_free(sum);
+        if (tmp)
+          hx_device_free(tmp);
+      }
+    };
+  } // namespace ksdft
+
+  namespace basis
+  {
+    // mass-lumped (GLL) overlap / overlap-inverse operators, apply only
+    class DiagonalOverlapOperator : public linearAlgebra::NativeOperator
+    {
+    protected:
+      DiagonalOverlapOperator(std::shared_ptr<const linearAlgebra::DeviceContext> ctx,
+                              const std::vector<double> &                         diagonal,
+                              const std::vector<double> *                         atomBlock,
+                              int                                                 variant)
+      {
+        d_ctx = std::move(ctx);
+        utils::throwException(diagonal.size() == d_ctx->localSize(), "diagonal must cover the local (owned+ghost) rows");
+        utils::hxCheck(hx_diagop_create(d_ctx->plan(), diagonal.data(), atomBlock ? atomBlock->data() : nullptr, variant, &d_op));
+      }
+    };
+    // src/basis/CFEOverlapInverseOpContextGLL.t.cpp:499-560
+    class CFEOverlapInverseOpContextGLL : public DiagonalOverlapOperator
+    {
+    public:
+      CFEOverlapInverseOpContextGLL(std::shared_ptr<const linearAlgebra::DeviceContext> ctx,
+                                    const std::vector<double> &                         diagonalInv)
+        : DiagonalOverlapOperator(std::move(ctx), diagonalInv, nullptr, HX_DIAG_CFE)
+      {}
+    };
+    // src/basis/OEFEAtomBlockOverlapInvOpContextGLL.t.cpp:953-1108
+    class OEFEAtomBlockOverlapInvOpContextGLL : public DiagonalOverlapOperator
+    {
+    public:
+      OEFEAtomBlockOverlapInvOpContextGLL(std::shared_ptr<const linearAlgebra::DeviceContext> ctx,
+                                          const std::vector<double> &                         diagonalInv,
+                                          const std::vector<double> &atomBlockEnrichmentOverlapInv)
+        : DiagonalOverlapOperator(std::move(ctx), diagonalInv, &atomBlockEnrichmentOverlapInv, HX_DIAG_OEFE_ATOMBLOCK)
+      {}
+    };
+    // src/basis/OrthoEFEOverlapOperatorContext.t.cpp:2085-2235 (mass-lumped branch)
+    class OrthoEFEOverlapOperatorContext : public DiagonalOverlapOperator
+    {
+    public:
+      OrthoEFEOverlapOperatorContext(std::shared_ptr<const linearAlgebra::DeviceContext> ctx,
+                                     const std::vector<double> &                         diagonal,
+                                     const std::vector<double> &                         atomBlockEnrichmentOverlap)
+        : DiagonalOverlapOperator(std::move(ctx), diagonal, &atomBlockEnrichmentOverlap, HX_DIAG_OEFE_MASS)
+      {}
+    };
+  } // namespace basis
+
+  namespace linearAlgebra
+  {
+    namespace blasLapack
+    {
+      // z = alpha x + beta y over the first nRows rows (src/linearAlgebra/BlasLapackKernels.cpp:456-475)
+      inline void
+      axpby(const DeviceContext &ctx, size_type nRows, size_type B, double alpha, const double *x, double beta,
+            const double *y, double *z)
+      {
+        utils::hxCheck(hx_axpby(ctx.plan(), nRows, B, alpha, x, beta, y, z));
+      }
+    } // namespace blasLapack
+
+    // src/linearAlgebra/ChebyshevFilter.t.cpp:39-134.  Native operators run the fused device path; any other
+    // OperatorContext subclass runs the same recurrence through its apply().
+    inline void
+    ChebyshevFilter(const DeviceOperatorContext &A,
+                    const DeviceOperatorContext &BInv,
+                    DeviceMultiVector &          eigenSubspaceGuess,
+                    const size_type              polynomialDegree,
+                    const double                 wantedSpectrumLowerBound,
+                    const double                 wantedSpectrumUpperBound,
+                    const double                 unWantedSpectrumUpperBound,
+                    DeviceMultiVector &          filteredSubspace)
+    {
+      auto *      nA = dynamic_cast<const NativeOperator *>(&A);
+      auto *      nB = dynamic_cast<const NativeOperator *>(&BInv);
+      const auto  B  = eigenSubspaceGuess.getNumberComponents();
+      if (nA && nB)
+        {
+          utils::hxCheck(hx_chebyshev_filter(nA->handle(), nB->handle(), eigenSubspaceGuess.data(), filteredSubspace.data(), B,
+                                             polynomialDegree, wantedSpectrumLowerBound, wantedSpectrumUpperBound,
+                                             unWantedSpectrumUpperBound));
+          return;
+        }
+      const DeviceContext &ctx   = *eigenSubspaceGuess.getDeviceContext();
+      const size_type      nOwn  = eigenSubspaceGuess.locallyOwnedSize();
+      const double         e     = (unWantedSpectrumUpperBound - wantedSpectrumUpperBound) / 2.0;
+      const double         c     = (unWantedSpectrumUpperBound + wantedSpectrumUpperBound) / 2.0;
+      double               sigma = e / (wantedSpectrumLowerBound - c);
+      const double         sigma1 = sigma, gamma = 2.0 / sigma1;
+      DeviceMultiVector    scratch1(eigenSubspaceGuess.getDeviceContext(), B), scratch2(eigenSubspaceGuess.getDeviceContext(), B);
+      A.apply(eigenSubspaceGuess, scratch1, true, false);
+      BInv.apply(scratch1, scratch2, false, false);
+      blasLapack::axpby(ctx, nOwn, B, sigma1 / e, scratch2.data(), -sigma1 / e * c, eigenSubspaceGuess.data(),
+                        filteredSubspace.data());
+      for (size_type degree = 2; degree <= polynomialDegree; degree++)
+        {
+          const double sigma2 = 1.0 / (gamma - sigma);
+          A.apply(filteredSubspace, scratch1, true, false);
+          BInv.apply(scratch1, scratch2, false, false);
+          blasLapack::axpby(ctx, nOwn, B, 2.0 * sigma2 / e, scratch2.data(), -2.0 * sigma2 / e * c, filteredSubspace.data(),
+                            scratch1.data());
+          blasLapack::axpby(ctx, nOwn, B, 1.0, scratch1.data(), -sigma * sigma2, eigenSubspaceGuess.data(),
+                            eigenSubspaceGuess.data());
+          swap(eigenSubspaceGuess, filteredSubspace);
+          sigma = sigma2;
+        }
+      std::vector<double> tmp((size_t)filteredSubspace.localSize() * B);
+      filteredSubspace.copyTo(tmp.data());
+      eigenSubspaceGuess.copyFrom(tmp.data());
+    }
+
+    // src/linearAlgebra/ChebyshevFilter.t.cpp:242-445 (native operators only)
+    inline void
+    ResidualChebyshevFilterGEP(const DeviceOperatorContext &A,
+                               const DeviceOperatorContext &B,
+                               const DeviceOperatorContext &BInv,
+                               std::vector<double> &        eigenvalues,
+                               DeviceMultiVector &          eigenSubspaceGuess,
+                               const size_type              polynomialDegree,
+                               const double                 wantedSpectrumLowerBound,
+                               const double                 wantedSpectrumUpperBound,
+                               const double                 unWantedSpectrumUpperBound,
+                               DeviceMultiVector &          filteredSubspace)
+    {
+      auto *nA = dynamic_cast<const NativeOperator *>(&A);
+      auto *nB = dynamic_cast<const NativeOperator *>(&B);
+      auto *nI = dynamic_cast<const NativeOperator *>(&BInv);
+      utils::throwException(nA && nB && nI, "ResidualChebyshevFilterGEP<DEVICE> needs libhxb200 operators");
+      utils::throwException(eigenvalues.size() == eigenSubspaceGuess.getNumberComponents(), "one eigenvalue per vector");
+      utils::hxCheck(hx_residual_chebyshev_filter(nA->handle(), nB->handle(), nI->handle(), eigenvalues.data(),
+                                                  eigenSubspaceGuess.data(), filteredSubspace.data(),
+                                                  eigenSubspaceGuess.getNumberComponents(), polynomialDegree,
+                                                  wantedSpectrumLowerBound, wantedSpectrumUpperBound,
+                                                  unWantedSpectrumUpperBound));
+    }
+
+    namespace RayleighRitzEigenSolverInternal
+    {
+      // computeXTransOpX (src/linearAlgebra/RayleighRitzEigenSolver.t.cpp:685-844): B x B column-major, lower
+      // triangle filled, summed over ranks.
+      inline std::vector<double>
+      computeXTransOpX(DeviceMultiVector &X, const NativeOperator &Op, size_type eigenVectorBatchSize)
+      {
+        const size_type     B = X.getNumberComponents();
+        std::vector<double> S((size_t)B * B);
+        utils::hxCheck(hx_xtopx(Op.handle(), X.data(), B, eigenVectorBatchSize, S.data()));
+        return S;
+      }
+    } // namespace RayleighRitzEigenSolverInternal
+
+    namespace elpaScalaOpInternal
+    {
+      // subspaceRotation (src/linearAlgebra/ElpaScalapackOperations.t.cpp:185-335); Q: B x B column-major, replicated
+      inline void
+      subspaceRotation(DeviceMultiVector &X, const std::vector<double> &rotationMat, bool rotationMatTranspose,
+                       bool isRotationMatLowerTria)
+      {
+        const size_type B = X.getNumberComponents();
+        utils::throwException(rotationMat.size() == (size_t)B * B, "rotation matrix must be B x B");
+        utils::hxCheck(hx_subspace_rotation(X.getDeviceContext()->plan(), X.data(), B, rotationMat.data(), rotationMatTranspose,
+                                            isRotationMatLowerTria));
+      }
+    } // namespace elpaScalaOpInternal
+  }   // namespace linearAlgebra
+} // namespace dftefe
+#endif

@@ -1,0 +1,190 @@
+// mirror_driver.cpp — exercises the C++ host-side mirror (dft_efe_b200/include/dftefe_b200/HotPath.h) the way a
+// reference call site would: build the operator contexts, X/Y MultiVectors, apply, ChebyshevFilter,
+// computeXTransOpX, subspaceRotation.  Input = a binary dump of one synthetic rank problem written by
+// tests/test_cpp_mirror.py; output = a binary dump of the results, compared there with the CPU oracle.
+//
+//   mirror_driver <problem.bin> <result.bin>
+#include <cstdio>
+#include <fstream>
+#include <iostream>
+#include <map>
+#include <string>
+
+#include "../../dft_efe_b200/include/dftefe_b200/HotPath.h"
+
+using namespace dftefe;
+
+struct Blob
+{
+  std::map<std::string, std::vector<uint32_t>> u;
+  std::map<std::string, std::vector<double>>   f;
+};
+
+static Blob
+readBlob(const char *path)
+{
+  Blob          b;
+  std::ifstream in(path, std::ios::binary);
+  if (!in)
+    throw std::runtime_error(std::string("cannot open ") + path);
+  for (;;)
+    {
+      uint32_t nameLen = 0, dtype = 0;
+      uint64_t count = 0;
+      if (!in.read((char *)&nameLen, 4))
+        break;
+      std::string name(nameLen, ' ');
+      in.read(&name[0], nameLen);
+      in.read((char *)&dtype, 4);
+      in.read((char *)&count, 8);
+      if (dtype == 0)
+        {
+          auto &v = b.u[name];
+          v.resize(count);
+          in.read((char *)v.data(), count * 4);
+        }
+      else
+        {
+          auto &v = b.f[name];
+          v.resize(count);
+          in.read((char *)v.data(), count * 8);
+        }
+    }
+  return b;
+}
+
+static void
+writeArray(std::ofstream &out, const std::string &name, const std::vector<double> &v)
+{
+  uint32_t nameLen = (uint32_t)name.size(), dtype = 1;
+  uint64_t count = v.size();
+  out.write((const char *)&nameLen, 4);
+  out.write(name.data(), nameLen);
+  out.write((const char *)&dtype, 4);
+  out.write((const char *)&count, 8);
+  out.write((const char *)v.data(), count * 8);
+}
+
+static utils::mpi::MPIPatternP2PArrays
+pattern(const Blob &b, const std::string &pre)
+{
+  utils::mpi::MPIPatternP2PArrays p;
+  const auto &                    sz = b.u.at(pre + "sizes");
+  p.localOwnedSize                   = sz[0];
+  p.localGhostSize                   = sz[1];
+  p.ghostProcIds                     = b.u.at(pre + "ghost_proc_ids");
+  p.ghostLocalIndicesRanges          = b.u.at(pre + "ghost_ranges");
+  p.ghostLocalIndicesForGhostProcs   = b.u.at(pre + "ghost_local_ids");
+  p.targetProcIds                    = b.u.at(pre + "target_proc_ids");
+  p.numOwnedIndicesForTargetProcs    = b.u.at(pre + "num_owned_for_target");
+  p.ownedLocalIndicesForTargetProcs  = b.u.at(pre + "owned_local_ids_for_targets");
+  return p;
+}
+
+// a user-defined operator that is NOT native: ChebyshevFilter must still work through apply()
+class ScaledOperator : public linearAlgebra::DeviceOperatorContext
+{
+public:
+  ScaledOperator(const linearAlgebra::DeviceOperatorContext &inner)
+    : d_inner(inner)
+  {}
+  void
+  apply(linearAlgebra::DeviceMultiVector &X, linearAlgebra::DeviceMultiVector &Y, bool ugx, bool ugy) const override
+  {
+    d_inner.apply(X, Y, ugx, ugy);
+  }
+
+private:
+  const linearAlgebra::DeviceOperatorContext &d_inner;
+};
+
+int
+main(int argc, char **argv)
+{
+  if (argc < 3)
+    {
+      std::cerr << "usage: mirror_driver problem.bin result.bin\n";
+      return 2;
+    }
+  try
+    {
+      Blob                        b = readBlob(argv[1]);
+      basis::FEBasisManagerArrays fe;
+      fe.mpiPatternP2P              = pattern(b, "halo.");
+      fe.nLocallyOwnedClassicalDofs = b.u.at("scalars")[0];
+      const size_type B             = b.u.at("scalars")[1];
+      const size_type degree        = b.u.at("scalars")[2];
+      fe.nLocallyOwnedCellDofs        = b.u.at("num_cell_dofs");
+      fe.locallyOwnedCellLocalDofIds  = b.u.at("cell_local_ids");
+      fe.rowConstraintsIdsLocal       = b.u.at("row_ids");
+      fe.rowConstraintsSizes          = b.u.at("row_sizes");
+      fe.columnConstraintsAccumulated = b.u.at("row_offsets");
+      fe.columnConstraintsIdsLocal    = b.u.at("col_ids");
+      fe.columnConstraintsValues      = b.f.at("col_vals");
+      fe.constraintsInhomogenities    = b.f.at("inhom");
+
+      auto ctx = std::make_shared<const linearAlgebra::DeviceContext>(fe, B);
+
+      basis::AtomCenterNonLocalArrays nl;
+      nl.mpiPatternP2PProj                 = pattern(b, "proj_halo.");
+      nl.numProjsInCells                   = b.u.at("num_cell_proj");
+      nl.locallyOwnedCellLocalProjectorIds = b.u.at("cell_proj_local_ids");
+      nl.cellWiseC                         = b.f.at("cell_c");
+      nl.V                                 = b.f.at("proj_v");
+
+      // two Hamiltonian components (kinetic-like + potential-like), summed by reinit as the reference does
+      std::vector<ksdft::LocalHamiltonianComponent> comps = {{b.f.at("h_part1").data(), false},
+                                                             {b.f.at("h_part2").data(), false}};
+      ksdft::KohnShamOperatorContextFE             H(ctx, comps, &nl);
+      basis::OEFEAtomBlockOverlapInvOpContextGLL   MInv(ctx, b.f.at("diag_inv"), b.f.at("enr_block_inv"));
+
+      const double a0 = b.f.at("bounds")[0], a = b.f.at("bounds")[1], bb = b.f.at("bounds")[2];
+      std::ofstream out(argv[2], std::ios::binary);
+      std::vector<double> host((size_t)ctx->localSize() * B);
+
+      linearAlgebra::DeviceMultiVector X(ctx, B), Y(ctx, B);
+      X.copyFrom(b.f.at("X").data());
+      H.apply(X, Y, true, false);
+      Y.copyTo(host.data());
+      writeArray(out, "HX", host);
+      writeArray(out, "norms", Y.l2Norms());
+
+      X.copyFrom(b.f.at("X").data());
+      linearAlgebra::ChebyshevFilter(H, MInv, X, degree, a0, a, bb, Y);
+      Y.copyTo(host.data());
+      writeArray(out, "filtered_native", host);
+
+      ScaledOperator Hgeneric(H); // forces the generic (apply-based) recurrence
+      X.copyFrom(b.f.at("X").data());
+      linearAlgebra::ChebyshevFilter(Hgeneric, MInv, X, degree, a0, a, bb, Y);
+      Y.copyTo(host.data());
+      writeArray(out, "filtered_generic", host);
+
+      X.copyFrom(b.f.at("X").data());
+      writeArray(out, "XtHX", linearAlgebra::RayleighRitzEigenSolverInternal::computeXTransOpX(X, H, B));
+
+      X.copyFrom(b.f.at("X").data());
+      linearAlgebra::elpaScalaOpInternal::subspaceRotation(X, b.f.at("Q"), true, false);
+      X.copyTo(host.data());
+      writeArray(out, "rotated", host);
+
+      // error convention: a wrong block width must throw, not crash
+      bool threw = false;
+      try
+        {
+          linearAlgebra::DeviceMultiVector bad(ctx, B + 1);
+        }
+      catch (const utils::HxException &)
+        {
+          threw = true;
+        }
+      writeArray(out, "threw", std::vector<double>{threw ? 1.0 : 0.0});
+      std::cout << "mirror_driver ok\n";
+      return 0;
+    }
+  catch (const std::exception &e)
+    {
+      std::cerr << "mirror_driver failed: " << e.what() << "\n";
+      return 1;
+    }
+}

@@ -1,0 +1,112 @@
+"""The C++ host-side mirror of the reference operator API (dft_efe_b200/include/dftefe_b200/HotPath.h):
+compiles with a bare g++ against the C ABI (CPU check) and, on a GPU box, reproduces the oracle."""
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+from dft_efe_b200 import capi, synth
+from oracle import oracle as orc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "tests", "cpp", "mirror_driver")
+
+
+def build_driver():
+    src = os.path.join(ROOT, "tests", "cpp", "mirror_driver.cpp")
+    hdr = os.path.join(ROOT, "dft_efe_b200", "include", "dftefe_b200", "HotPath.h")
+    if (not os.path.exists(EXE)) or os.path.getmtime(EXE) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        libdir = os.path.dirname(capi.LIB_PATH)
+        subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-o", EXE, src, "-L" + libdir, "-lhxb200",
+                               "-Wl,-rpath," + libdir])
+    return EXE
+
+
+def write_blob(path, arrays):
+    with open(path, "wb") as f:
+        for name, a in arrays.items():
+            a = np.ascontiguousarray(a)
+            dt = 0 if a.dtype == np.uint32 else 1
+            assert a.dtype in (np.uint32, np.float64), (name, a.dtype)
+            f.write(struct.pack("<I", len(name)) + name.encode() + struct.pack("<IQ", dt, a.size) + a.tobytes())
+
+
+def read_blob(path):
+    out = {}
+    with open(path, "rb") as f:
+        data = f.read()
+    o = 0
+    while o < len(data):
+        (n,) = struct.unpack_from("<I", data, o); o += 4
+        name = data[o:o + n].decode(); o += n
+        dt, cnt = struct.unpack_from("<IQ", data, o); o += 12
+        out[name] = np.frombuffer(data, np.uint32 if dt == 0 else np.float64, cnt, o).copy()
+        o += cnt * (4 if dt == 0 else 8)
+    return out
+
+
+def halo_arrays(h, pre):
+    return {pre + "sizes": np.array([h.n_owned, h.n_ghost], np.uint32),
+            **{pre + k: np.asarray(getattr(h, k), np.uint32) for k in
+               ("ghost_proc_ids", "ghost_ranges", "ghost_local_ids", "target_proc_ids", "num_owned_for_target",
+                "owned_local_ids_for_targets")}}
+
+
+def test_cpp_mirror_compiles_against_c_abi():
+    assert os.path.exists(capi.LIB_PATH), "libhxb200.so not built"
+    assert os.path.exists(build_driver())
+
+
+@pytest.mark.gpu
+def test_cpp_mirror_matches_oracle(tmp_path):
+    exe = build_driver()
+    nc = (4, 4, 4)
+    atoms = np.array([[2.0, 2.0, 2.0], [1.2, 2.9, 1.1]])
+    spec = synth.MeshSpec(ncell=nc, p=3, refine_mask=synth.refine_ball(nc, 1.0, [atoms[0]], 0.9), atoms=atoms,
+                          n_enr_per_atom=3, enr_cutoff=1.2, n_proj_per_atom=2, proj_cutoff=1.0)
+    p = synth.build_problem(spec)[0]
+    B, degree = 8, 6
+    a0, a, b = -3.0, 1.0, 60.0
+    X = synth.make_block(p, B)
+    rng = np.random.default_rng(5)
+    part1 = p.h_cell * rng.uniform(0.2, 0.8, size=p.h_cell.shape)
+    Q = np.asfortranarray(np.linalg.qr(rng.standard_normal((B, B)))[0])
+    arrays = {"scalars": np.array([p.n_owned_classical, B, degree], np.uint32),
+              **halo_arrays(p.halo, "halo."), **halo_arrays(p.proj_halo, "proj_halo."),
+              "num_cell_dofs": p.num_cell_dofs, "cell_local_ids": p.cell_local_ids, "row_ids": p.row_ids,
+              "row_sizes": p.row_sizes, "row_offsets": p.row_offsets, "col_ids": p.col_ids,
+              "col_vals": p.col_vals, "inhom": p.inhom, "num_cell_proj": p.num_cell_proj,
+              "cell_proj_local_ids": p.cell_proj_local_ids, "cell_c": p.cell_c, "proj_v": p.proj_v,
+              "h_part1": part1, "h_part2": p.h_cell - part1, "diag_inv": p.diag_inv,
+              "enr_block_inv": np.asarray(p.enr_block_inv, np.float64).ravel(order="F"),
+              "bounds": np.array([a0, a, b]), "X": X, "Q": Q.ravel(order="F")}
+    arrays = {k: (np.asarray(v, np.uint32) if np.asarray(v).dtype.kind in "ui" else np.asarray(v, np.float64))
+              for k, v in arrays.items()}
+    write_blob(tmp_path / "problem.bin", arrays)
+    r = subprocess.run([exe, str(tmp_path / "problem.bin"), str(tmp_path / "result.bin")], capture_output=True,
+                       text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    res = read_blob(tmp_path / "result.bin")
+
+    def rel(x, y):
+        den = np.linalg.norm(y, axis=0); den[den == 0] = 1.0
+        return (np.linalg.norm(x - y, axis=0) / den).max()
+
+    W = orc.OracleWorld([p])
+    Yo = np.zeros_like(X)
+    W.hx_apply([X.copy()], [Yo], True, False)
+    assert rel(res["HX"].reshape(X.shape), Yo) < 1e-12
+    own = p.n_owned
+    assert np.abs(res["norms"] - np.linalg.norm(Yo[:own], axis=0)).max() < 1e-12 * np.linalg.norm(Yo[:own], axis=0).max()
+    F = W.chebyshev_filter([X.copy()], degree, a0, a, b)[0]
+    assert rel(res["filtered_native"].reshape(X.shape)[:own], F[:own]) < 1e-11
+    assert rel(res["filtered_generic"].reshape(X.shape)[:own], F[:own]) < 1e-11
+    So = W.xtopx([X.copy()], lambda a_, b_, c_, d_: W.hx_apply(a_, b_, c_, d_), B)
+    S = res["XtHX"].reshape((B, B), order="F")
+    assert np.abs(S - So).max() < 1e-12 * np.abs(So).max()
+    Xr = [X.copy()]
+    W.subspace_rotation(Xr, Q, True, False)
+    assert rel(res["rotated"].reshape(X.shape)[:own], Xr[0][:own]) < 1e-13
+    assert res["threw"][0] == 1.0
