@@ -23,7 +23,7 @@ EXPORTS = [
     "hx_plan_set_scatter_mode", "hx_plan_get_wait_lists", "hx_plan_get_processing_order", "hx_plan_num_colours", "hx_plan_get_cell_colours", "hx_plan_get_c2p_transpose", "hx_update_ghost_values",
     "hx_accumulate_add_locally_owned", "hx_distribute_parent_to_child", "hx_distribute_child_to_parent",
     "hx_set_constrained_nodes_to_zero", "hx_cellop_create", "hx_cellop_set_matrices", "hx_cellop_set_nonlocal",
-    "hx_diagop_create", "hx_op_destroy", "hx_op_apply", "hx_op_apply_host", "hx_chebyshev_filter",
+    "hx_diagop_create", "hx_op_destroy", "hx_op_apply", "hx_op_apply_host", "hx_chebyshev_filter", "hx_chebyshev_filter_host",
     "hx_residual_chebyshev_filter", "hx_xtopx", "hx_subspace_rotation", "hx_l2_norms", "hx_axpby",
     "hx_axpby_blocked", "hx_plan_launch_count", "hx_plan_cell_kernel_time_ms", "hx_plan_enable_kernel_timing",
     "hx_microbench",
@@ -341,6 +341,17 @@ class DiagOp(Op):
 def chebyshev_filter(A: Op, BInv: Op, X: DeviceBlock, Y: DeviceBlock, degree, a0, a, b):
     check(lib().hx_chebyshev_filter(A.h, BInv.h, X.p, Y.p, C.c_uint32(X.B), C.c_uint32(degree), C.c_double(a0),
                                     C.c_double(a), C.c_double(b)))
+
+
+def chebyshev_filter_host_ptr(A: Op, BInv: Op, xptr, yptr, B, degree, a0, a, b, write_back_x=False):
+    check(lib().hx_chebyshev_filter_host(A.h, BInv.h, C.cast(xptr, f64p), C.cast(yptr, f64p), C.c_uint32(B),
+                                         C.c_uint32(degree), C.c_double(a0), C.c_double(a), C.c_double(b),
+                                         C.c_int(int(write_back_x))))
+
+
+def chebyshev_filter_host(A: Op, BInv: Op, Xh: np.ndarray, Yh: np.ndarray, degree, a0, a, b, write_back_x=True):
+    assert Xh.flags["C_CONTIGUOUS"] and Yh.flags["C_CONTIGUOUS"] and Xh.dtype == np.float64 and Yh.dtype == np.float64
+    chebyshev_filter_host_ptr(A, BInv, Xh.ctypes.data, Yh.ctypes.data, Xh.shape[1], degree, a0, a, b, write_back_x)
 
 
 def residual_chebyshev_filter(A: Op, Bop: Op, BInv: Op, eig: np.ndarray, X: DeviceBlock, Y: DeviceBlock, degree, a0, a, b):

@@ -1043,6 +1043,26 @@ extern "C"
   }
 
   int
+  hx_chebyshev_filter_host(hx_op *A, hx_op *BInv, double *Xh, double *Yh, uint32_t B, uint32_t degree, double a0,
+                           double a, double b, int write_back_x)
+  {
+    HX_CHECK(A && BInv && Xh && Yh, HX_ERR_INVALID, "null argument");
+    hx_plan *p = A->plan;
+    HX_CHECK_B(p, B);
+    double *dX, *dY;
+    HX_TRY(p->get_scratch(4, &dX));
+    HX_TRY(p->get_scratch(5, &dY));
+    const size_t bytes = (size_t)p->n_local * B * sizeof(double);
+    HX_CUDA(cudaMemcpyAsync(dX, Xh, bytes, cudaMemcpyHostToDevice, p->stream));
+    HX_TRY(hx_chebyshev_filter(A, BInv, dX, dY, B, degree, a0, a, b));
+    HX_CUDA(cudaMemcpyAsync(Yh, dY, bytes, cudaMemcpyDeviceToHost, p->stream));
+    if (write_back_x)
+      HX_CUDA(cudaMemcpyAsync(Xh, dX, bytes, cudaMemcpyDeviceToHost, p->stream));
+    HX_CUDA(cudaStreamSynchronize(p->stream));
+    return HX_OK;
+  }
+
+  int
   hx_residual_chebyshev_filter(hx_op *A, hx_op *Bop, hx_op *BInv, const double *eigenvalues, double *X, double *Y,
                                uint32_t B, uint32_t degree, double a0, double a, double b)
   {

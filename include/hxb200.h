@@ -167,6 +167,12 @@ int hx_op_apply_host(hx_op *op, double *X_host, double *Y_host, uint32_t B, int 
 /* X = eigenSubspaceGuess (in/out), Y = filteredSubspace (out); on return both hold the filtered block. */
 int hx_chebyshev_filter(hx_op *A, hx_op *BInv, double *X, double *Y, uint32_t B, uint32_t degree,
                         double wantedLower, double wantedUpper, double unwantedUpper);
+/* Same call with HOST buffers (n_local*B doubles each; pinned memory gives full PCIe rate): X is copied in once,
+ * all `degree` applications run on the device, the filtered block is copied out into Y_host (and into X_host
+ * too when write_back_x != 0, the reference's final `eigenSubspaceGuess = filteredSubspace`,
+ * ChebyshevFilter.t.cpp:133).  Blocks until the result is in host memory. */
+int hx_chebyshev_filter_host(hx_op *A, hx_op *BInv, double *X_host, double *Y_host, uint32_t B, uint32_t degree,
+                             double wantedLower, double wantedUpper, double unwantedUpper, int write_back_x);
 /* eigenvalues: HOST array of B doubles (std::vector<RealType>& in the reference). */
 int hx_residual_chebyshev_filter(hx_op *A, hx_op *Bop, hx_op *BInv, const double *eigenvalues, double *X,
                                  double *Y, uint32_t B, uint32_t degree, double wantedLower,

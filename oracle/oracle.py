@@ -215,6 +215,16 @@ class OracleWorld:
         if self.has_nonlocal:
             self.phalos = [p.proj_halo for p in problems]
             self.np_owned = [p.proj_halo.n_owned for p in problems]
+        self.pool = None  # optional concurrent.futures executor: rank-local sections run one partition per thread
+
+    def _each_rank(self, fn):
+        """Run fn(i) for every rank i - concurrently when a pool is attached (the stand-in for `mpirun -n nr`:
+        the C routines release the GIL), else in rank order.  Rank-local work only."""
+        if self.pool is not None and self.nr > 1:
+            list(self.pool.map(fn, range(self.nr)))
+        else:
+            for i in range(self.nr):
+                fn(i)
 
     # a2 / a8
     def update_ghost_values(self, Xs):
@@ -231,14 +241,14 @@ class OracleWorld:
         B = Xs[0].shape[1]
         if update_ghost_x:
             self.update_ghost_values(Xs)
-        for r, X in zip(self.ranks, Xs):
-            r.p2c(X)
-        for Y in Ys:
-            Y[...] = 0.0
         nl = self.has_nonlocal and use_nonlocal
         CXs = [np.zeros((r.n_proj_local, B)) if nl else None for r in self.ranks]
-        for r, X, CX in zip(self.ranks, Xs, CXs):
-            r.loop_a(X, CX, use_nonlocal=nl)
+
+        def sec_a(i):
+            self.ranks[i].p2c(Xs[i])
+            Ys[i][...] = 0.0
+            self.ranks[i].loop_a(Xs[i], CXs[i], use_nonlocal=nl)
+        self._each_rank(sec_a)
         if nl:
             # applyAllReduceOnCconjtransX + applyVOnCconjtransX
             # (basis/AtomCenterNonLocalOpContextFE.t.cpp:944-986)
@@ -247,11 +257,12 @@ class OracleWorld:
                 _exchange_update(self.phalos, CXs, self.np_owned)
             for r, CX in zip(self.ranks, CXs):
                 lib().orc_row_scale(_f64(r.proj_v), _f64(CX), _f64(CX), C.c_uint32(B), C.c_size_t(r.n_proj_local))
-        for i, (r, Y, CX) in enumerate(zip(self.ranks, Ys, CXs)):
-            r.loop_b(Y, CX, h_cell=None if h_cells is None else h_cells[i], long_double=long_double,
-                     use_nonlocal=nl)
-        for r, Y in zip(self.ranks, Ys):
-            r.c2p(Y)
+
+        def sec_b(i):
+            self.ranks[i].loop_b(Ys[i], CXs[i], h_cell=None if h_cells is None else h_cells[i],
+                                 long_double=long_double, use_nonlocal=nl)
+            self.ranks[i].c2p(Ys[i])
+        self._each_rank(sec_b)
         self.accumulate_add_locally_owned(Ys)
         if update_ghost_y:
             self.update_ghost_values(Ys)
@@ -266,9 +277,10 @@ class OracleWorld:
         B = Xs[0].shape[1]
         if update_ghost_x:
             self.update_ghost_values(Xs)
-        for r, X in zip(self.ranks, Xs):
+
+        def sec(i):
+            r, X, Y = self.ranks[i], Xs[i], Ys[i]
             r.p2c(X)
-        for i, (r, X, Y) in enumerate(zip(self.ranks, Xs, Ys)):
             Y[...] = 0.0
             d = np.ascontiguousarray(diags[i], dtype=np.float64)
             lib().orc_row_scale(_f64(d), _f64(X), _f64(Y), C.c_uint32(B), C.c_size_t(r.n_local))
@@ -281,10 +293,10 @@ class OracleWorld:
                     blk = np.ascontiguousarray(enr_blocks[i], dtype=np.float64)
                     lib().orc_enr_block_apply(_f64(xe), _f64(ye), C.c_uint32(B), C.c_uint32(nE), _f64(blk))
                     Y[ncl:ncl + nE] = ye
+        self._each_rank(sec)
         if variant == "oefe_atomblock":
             self.update_ghost_values(Ys)
-        for r, Y in zip(self.ranks, Ys):
-            r.c2p(Y)
+        self._each_rank(lambda i: self.ranks[i].c2p(Ys[i]))
         if update_ghost_y:
             self.update_ghost_values(Ys)
 
@@ -315,18 +327,22 @@ class OracleWorld:
         nown = [n * B for n in self.n_owned]
         self.hx_apply(Xs, s1, True, False)
         self.minv_apply(s1, s2, False, False, minv_variant)
-        for i in range(self.nr):
+
+        def first(i):
             L.orc_axpby(C.c_size_t(nown[i]), C.c_double(sigma1 / e), _f64(s2[i]), C.c_double(-sigma1 / e * c),
                         _f64(Xs[i]), _f64(Fs[i]))
+        self._each_rank(first)
         for _deg in range(2, degree + 1):
             sigma2 = 1.0 / (gamma - sigma)
             self.hx_apply(Fs, s1, True, False)
             self.minv_apply(s1, s2, False, False, minv_variant)
-            for i in range(self.nr):
+
+            def rec(i, Xs=Xs, Fs=Fs, sigma=sigma, sigma2=sigma2):
                 L.orc_axpby(C.c_size_t(nown[i]), C.c_double(2.0 * sigma2 / e), _f64(s2[i]),
                             C.c_double(-2.0 * sigma2 / e * c), _f64(Fs[i]), _f64(s1[i]))
                 L.orc_axpby(C.c_size_t(nown[i]), C.c_double(1.0), _f64(s1[i]), C.c_double(-sigma * sigma2),
                             _f64(Xs[i]), _f64(Xs[i]))
+            self._each_rank(rec)
             Xs, Fs = Fs, Xs
             sigma = sigma2
         return Fs

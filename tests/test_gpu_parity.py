@@ -311,6 +311,27 @@ def test_chebyshev_filter(capi, prob_full, variant):
     assert np.array_equal(dX.download()[:own], dY.download()[:own])  # both hold the result
 
 
+def test_chebyshev_filter_host_entry(capi, prob_full):
+    """hx_chebyshev_filter_host (HOST buffers in/out) == the device entry point, bit for bit."""
+    p = prob_full
+    B, deg = 8, 6
+    a0, a, b = -3.0, 1.0, 60.0
+    plan = capi.Plan(p, max_block=B)
+    H = capi.CellOp(plan)
+    minv = capi.DiagOp(plan, p.diag_inv, p.enr_block_inv, capi.DIAG_OEFE_ATOMBLOCK)
+    X = synth.make_block(p, B)
+    dX, dY = plan.block(B, X), plan.block(B)
+    capi.chebyshev_filter(H, minv, dX, dY, deg, a0, a, b)
+    Xh, Yh = X.copy(), np.zeros_like(X)
+    capi.chebyshev_filter_host(H, minv, Xh, Yh, deg, a0, a, b, write_back_x=True)
+    own = p.n_owned
+    assert np.array_equal(Yh[:own], dY.download()[:own])
+    assert np.array_equal(Xh[:own], Yh[:own])
+    Xh2, Yh2 = X.copy(), np.zeros_like(X)
+    capi.chebyshev_filter_host(H, minv, Xh2, Yh2, deg, a0, a, b, write_back_x=False)
+    assert np.array_equal(Xh2, X) and np.array_equal(Yh2[:own], Yh[:own])
+
+
 def test_residual_chebyshev_filter(capi, prob_full):
     p = prob_full
     B, deg = 6, 7
