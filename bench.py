@@ -297,7 +297,11 @@ def run_ours(args):
         # write Y once, the cell->DoF map and the constraint CSR
         S2 = prob.S2 + int(np.sum(prob.num_cell_proj.astype(np.int64) * prob.num_cell_dofs.astype(np.int64))) \
             if prob.num_cell_proj is not None else prob.S2
-        alg_bytes = 8 * S2 + 16 * B * prob.n_local + 4 * prob.S + 12 * prob.col_vals.size + 16 * len(prob.row_ids)
+        alg_apply = 8 * S2 + 16 * B * prob.n_local + 4 * prob.S + 12 * prob.col_vals.size + 16 * len(prob.row_ids)
+        # inside the filter the kernel also applies the recurrence on the fusable rows: + xprev (8B) and dinv per
+        # such row; `out` replaces the Y write of those rows
+        n_fus, n_other = plan.fusable_rows()
+        alg_bytes = alg_apply + (8 * B + 8) * n_fus
         flops = 2.0 * B * S2
         cell_ms_per_launch = cell_ms / max(cell_launches, 1)
         achieved = alg_bytes / (cell_ms_per_launch * 1e-3) / 1e9
@@ -336,7 +340,9 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak, "traffic": traffic, "traffic_source": traffic_src,
                          "peak_source": peak_src,
-                         "kernel": "cell_apply_ordered_kernel (one persistent launch per H.X apply)",
+                         "kernel": "cell_apply_ordered_kernel<FUSE> (one persistent launch per H.X apply; the Chebyshev "
+                                   "update of %d of %d owned rows is applied in its scatter epilogue)" % (n_fus, n_fus + n_other),
+                         "algorithmic_bytes_bare_apply": alg_apply,
                          "kernel_ms_per_launch": cell_ms_per_launch, "kernel_launches_timed": int(cell_launches),
                          "kernel_share_of_step": cell_ms / args.steps / ms_per_step,
                          "algorithmic_bytes_per_launch": alg_bytes, "flops_per_launch": flops,

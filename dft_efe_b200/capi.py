@@ -20,7 +20,7 @@ EXPORTS = [
     "hx_last_error", "hx_version", "hx_device_count", "hx_set_device", "hx_device_alloc", "hx_device_free",
     "hx_host_alloc_pinned", "hx_host_free_pinned", "hx_memcpy_h2d", "hx_memcpy_d2h", "hx_memset_zero",
     "hx_plan_create", "hx_plan_destroy", "hx_plan_synchronize", "hx_comm_unique_id", "hx_plan_attach_comm",
-    "hx_plan_set_scatter_mode", "hx_plan_get_wait_lists", "hx_plan_get_processing_order", "hx_plan_num_colours", "hx_plan_get_cell_colours", "hx_plan_get_c2p_transpose", "hx_update_ghost_values",
+    "hx_plan_set_scatter_mode", "hx_plan_get_wait_lists", "hx_plan_get_processing_order", "hx_plan_num_colours", "hx_plan_get_cell_colours", "hx_plan_get_c2p_transpose", "hx_plan_get_fusable_rows", "hx_update_ghost_values",
     "hx_accumulate_add_locally_owned", "hx_distribute_parent_to_child", "hx_distribute_child_to_parent",
     "hx_set_constrained_nodes_to_zero", "hx_cellop_create", "hx_cellop_set_matrices", "hx_cellop_set_nonlocal",
     "hx_diagop_create", "hx_op_destroy", "hx_op_apply", "hx_op_apply_host", "hx_chebyshev_filter", "hx_chebyshev_filter_host",
@@ -218,6 +218,11 @@ class Plan:
         check(lib().hx_plan_get_c2p_transpose(self.h, C.byref(n), ids.ctypes.data_as(u32p), off.ctypes.data_as(u32p),
                                               ch.ctypes.data_as(u32p), w.ctypes.data_as(f64p)))
         return ids, off, ch, w
+
+    def fusable_rows(self):
+        a, b = C.c_uint32(), C.c_uint32()
+        check(lib().hx_plan_get_fusable_rows(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def block(self, B, host=None) -> DeviceBlock:
         return DeviceBlock(self.n_local, B, host)

@@ -127,7 +127,7 @@ namespace hx
     p->max_block         = m->max_block ? m->max_block : 1;
     HX_CHECK(p->n_owned_classical <= p->n_owned, HX_ERR_INVALID, "n_owned_classical > n_owned");
     HX_CHECK(p->nranks >= 1 && p->rank >= 0 && p->rank < p->nranks, HX_ERR_INVALID, "bad rank/nranks");
-    HX_CHECK(p->n_local < 0x3fffffffu, HX_ERR_INVALID, "too many local rows");
+    HX_CHECK(p->n_local < 0x1fffffffu, HX_ERR_INVALID, "too many local rows");
 
     p->h_ncd.assign(m->num_cell_dofs, m->num_cell_dofs + p->C);
     p->h_cell_off.assign(p->C + 1, 0);
@@ -381,6 +381,7 @@ namespace hx
             }
         }
       std::vector<uint32_t> last(p->n_local, 0xffffffffu); // last processing index that touched the row
+      std::vector<uint32_t> last_entry(p->n_local, 0xffffffffu); // its position in the cell->row map
       p->h_wait_off.assign(p->C + 1, 0);
       p->h_wait_list.clear();
       std::vector<uint32_t> tmp;
@@ -397,13 +398,47 @@ namespace hx
                 dest[i] |= HX_DEST_FIRST;
               else if (last[r] != w)
                 tmp.push_back(last[r]);
-              last[r] = w;
+              last[r]       = w;
+              last_entry[r] = i;
             }
           std::sort(tmp.begin(), tmp.end());
           tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
           p->h_wait_list.insert(p->h_wait_list.end(), tmp.begin(), tmp.end());
           p->h_wait_off[w + 1] = (uint32_t)p->h_wait_list.size();
         }
+      // Chebyshev epilogue fusion: the last toucher of a fusable row applies the recurrence (hx_internal.h)
+      {
+        std::vector<char> acc_target(p->n_local, 0);
+        uint32_t          nsend = 0;
+        for (uint32_t t = 0; t < m->halo.n_target_procs; ++t)
+          nsend += m->halo.num_owned_for_target[t];
+        if (p->nranks > 1)
+          for (uint32_t i = 0; i < nsend; ++i)
+            if (m->halo.owned_local_ids_for_targets[i] < p->n_local)
+              acc_target[m->halo.owned_local_ids_for_targets[i]] = 1;
+        std::vector<uint32_t> nonfuse;
+        p->n_fusable = 0;
+        for (uint32_t r = 0; r < p->n_owned; ++r)
+          {
+            const bool ok = r < p->n_owned_classical && rowinfo[r] == 0xFFFFFFFFu && !acc_target[r] &&
+                            last_entry[r] != 0xffffffffu;
+            if (ok)
+              {
+                dest[last_entry[r]] |= HX_DEST_LASTF;
+                p->n_fusable++;
+              }
+            else
+              nonfuse.push_back(r);
+          }
+        p->n_nonfuse = (uint32_t)nonfuse.size();
+        HX_TRY(p->d_nonfuse_rows.upload(nonfuse));
+        // the fused M^-1 skips the ghost update between its row scaling and its child->parent pass: exact unless a
+        // constrained GHOST row has parents (its scaled value would come from the owner)
+        p->cheb_fusable_multirank = true;
+        for (uint32_t i = 0; i < p->nR; ++i)
+          if (m->row_ids[i] >= p->n_owned && m->row_sizes[i] > 0)
+            p->cheb_fusable_multirank = false;
+      }
       std::vector<uint32_t> untouched;
       for (uint32_t r = 0; r < p->n_local; ++r)
         if (last[r] == 0xffffffffu && shared.find(r) == shared.end())
@@ -435,7 +470,8 @@ namespace hx
 
   // ---------------------------------------------------------------------------------------------
   static int
-  cellop_apply(hx_op *op, double *X, double *Y, uint32_t B, int ugx, int ugy)
+  cellop_apply(hx_op *op, double *X, double *Y, uint32_t B, int ugx, int ugy, const FuseArgs *fuse = nullptr,
+               bool *fused_applied = nullptr)
   {
     hx_plan *p = op->plan;
     if (ugx)
@@ -456,7 +492,7 @@ namespace hx
             HX_TRY(launch_row_scale(p, op->d_v.p, op->d_cx.p, op->d_cx.p, B, op->n_proj_local));
           }
       }
-    HX_TRY(launch_cell_apply(op, X, Y, B));
+    HX_TRY(launch_cell_apply(op, X, Y, B, fuse, fused_applied));
     HX_TRY(launch_shared_reduce(p, Y, B));
     HX_TRY(launch_c2p(p, Y, B));
     HX_TRY(halo_accumulate(p, p->halo, Y, B));
@@ -770,6 +806,14 @@ extern "C"
     return HX_OK;
   }
   int
+  hx_plan_get_fusable_rows(hx_plan *plan, uint32_t *n_fusable, uint32_t *n_other_owned)
+  {
+    HX_CHECK(plan && n_fusable && n_other_owned, HX_ERR_INVALID, "null argument");
+    *n_fusable     = plan->n_fusable;
+    *n_other_owned = plan->n_nonfuse;
+    return HX_OK;
+  }
+  int
   hx_plan_get_c2p_transpose(hx_plan *plan, uint32_t *n_parents, uint32_t *parent_ids, uint32_t *offsets,
                             uint32_t *child_rows, double *weights)
   {
@@ -1001,35 +1045,49 @@ extern "C"
     const double sigma1 = sigma;
     const double gamma  = 2.0 / sigma1;
     const size_t nown   = (size_t)p->n_owned * B;
-    const bool   fused  = BInv->kind == HX_OP_DIAG && (BInv->variant == HX_DIAG_CFE || p->nranks == 1);
+    const bool   fused  = BInv->kind == HX_OP_DIAG && X != Y &&
+                       (BInv->variant == HX_DIAG_CFE || p->nranks == 1 || p->cheb_fusable_multirank);
     double *     s1, *s2 = nullptr;
     HX_TRY(p->get_scratch(0, &s1));
     if (!fused)
       HX_TRY(p->get_scratch(1, &s2));
     double *cur = X, *oth = Y; // cur = "eigenSubspaceGuess", oth = "filteredSubspace"
-    HX_TRY(op_apply(A, cur, s1, B, 1, 0));
+    // one degree of the mass-lumped path: s1 = A xc (updateGhostX), then out = ca*M^-1 s1 + cb*xc + cc*xp.  The
+    // update of most rows happens inside the cell kernel's scatter (FuseArgs); the remaining owned rows (and all
+    // rows, when the launched kernel variant cannot fuse) go through cheb_fused_kernel.
+    const bool epilogue = fused && A->kind == HX_OP_CELL && p->scatter_mode == 0 && !getenv("HXB200_NO_EPILOGUE_FUSION");
+    auto       degree_fused = [&](double *xc, const double *xp, double *out, double ca, double cb, double cc) -> int {
+      bool applied = false;
+      if (epilogue)
+        {
+          FuseArgs f;
+          f.dinv = BInv->d_diag.p, f.xprev = xp, f.out = out, f.a = ca, f.b = cb, f.c = xp ? cc : 0.0;
+          HX_CHECK(xc != s1 && out != xc, HX_ERR_INVALID, "aliasing in the fused Chebyshev step");
+          HX_TRY(cellop_apply(A, xc, s1, B, 1, 0, &f, &applied));
+        }
+      else
+        HX_TRY(op_apply(A, xc, s1, B, 1, 0));
+      HX_TRY(launch_p2c(p, s1, B));
+      if (applied)
+        return launch_cheb_fused(p, BInv, s1, xc, xp, out, B, ca, cb, cc, true, p->d_nonfuse_rows.p, p->n_nonfuse);
+      return launch_cheb_fused(p, BInv, s1, xc, xp, out, B, ca, cb, cc);
+    };
     if (fused)
-      {
-        HX_TRY(launch_p2c(p, s1, B));
-        HX_TRY(launch_cheb_fused(p, BInv, s1, cur, nullptr, oth, B, sigma1 / e, -sigma1 / e * c, 0.0));
-      }
+      HX_TRY(degree_fused(cur, nullptr, oth, sigma1 / e, -sigma1 / e * c, 0.0));
     else
       {
+        HX_TRY(op_apply(A, cur, s1, B, 1, 0));
         HX_TRY(op_apply(BInv, s1, s2, B, 0, 0));
         HX_TRY(launch_axpby(p, nown, sigma1 / e, s2, -sigma1 / e * c, cur, oth));
       }
     for (uint32_t deg = 2; deg <= degree; ++deg)
       {
         const double sigma2 = 1.0 / (gamma - sigma);
-        HX_TRY(op_apply(A, oth, s1, B, 1, 0));
         if (fused)
-          {
-            HX_TRY(launch_p2c(p, s1, B));
-            HX_TRY(launch_cheb_fused(p, BInv, s1, oth, cur, cur, B, 2.0 * sigma2 / e, -2.0 * sigma2 / e * c,
-                                     -sigma * sigma2));
-          }
+          HX_TRY(degree_fused(oth, cur, cur, 2.0 * sigma2 / e, -2.0 * sigma2 / e * c, -sigma * sigma2));
         else
           {
+            HX_TRY(op_apply(A, oth, s1, B, 1, 0));
             HX_TRY(op_apply(BInv, s1, s2, B, 0, 0));
             HX_TRY(launch_axpby(p, nown, 2.0 * sigma2 / e, s2, -2.0 * sigma2 / e * c, oth, s1));
             HX_TRY(launch_axpby(p, nown, 1.0, s1, -sigma * sigma2, cur, cur));

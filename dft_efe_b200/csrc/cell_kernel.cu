@@ -60,6 +60,11 @@ namespace hx
     uint32_t        B;
     uint32_t        nBt;
     uint32_t        nStages;
+    // Chebyshev epilogue (FUSE kernels only): see FuseArgs in hx_internal.h
+    const double *  f_dinv;
+    const double *  f_xprev;
+    double *        f_out;
+    double          f_a, f_b, f_c;
   };
 
   __device__ __forceinline__ void
@@ -233,7 +238,7 @@ namespace hx
   // =================================================================================================
   // Ordered persistent kernel
   // =================================================================================================
-  template <int NT, int MTW, bool VEC, int MINB>
+  template <int NT, int MTW, bool VEC, int MINB, bool FUSE>
   __global__ void __launch_bounds__(V2_THREADS, MINB) cell_apply_ordered_kernel(const CellArgs a)
   {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -468,6 +473,15 @@ namespace hx
                   {
                     const int r = (mc + mtl0 + j) * 8 + (lane >> 2);
                     dst_code[j] = (r < n) ? __ldg(a.dest + info.ids_off + r) : 0xffffffffu;
+                    if (FUSE)
+                      {
+                        // the last toucher will need xprev[row, tile]: pull its lines into L2 behind the k loop
+                        const uint32_t d  = dst_code[j];
+                        const uint32_t pc = b0 + (lane & 3) * 16;
+                        if (d != 0xffffffffu && (d & (HX_DEST_LASTF | HX_DEST_STAGED)) == HX_DEST_LASTF && a.f_c != 0.0 &&
+                            (lane & 3) * 16 < BT && pc < B)
+                          asm volatile("prefetch.global.L2 [%0];" ::"l"(a.f_xprev + (size_t)HX_DEST_ROW(d) * B + pc));
+                      }
                   }
                 int aoff[MTW];
 #pragma unroll
@@ -539,15 +553,40 @@ namespace hx
                                     if (add && col < B)
                                       y[t] = __ldcg(reinterpret_cast<const double2 *>(dst + col));
                                   }
-#pragma unroll
-                                for (int t = 0; t < NT; ++t)
+                                if (FUSE && !staged && (d & HX_DEST_LASTF))
                                   {
-                                    const uint32_t col = b0 + t * 8 + (lane & 3) * 2;
-                                    if (col < B)
+                                    // final value of (H X)[row, tile] is in registers: apply the recurrence here
+                                    const size_t ro = (size_t)HX_DEST_ROW(d) * B;
+                                    const double dv = __ldg(a.f_dinv + HX_DEST_ROW(d));
+#pragma unroll
+                                    for (int t = 0; t < NT; ++t)
                                       {
-                                        y[t].x += acc[j][t][0];
-                                        y[t].y += acc[j][t][1];
-                                        __stcg(reinterpret_cast<double2 *>(dst + col), y[t]);
+                                        const uint32_t col = b0 + t * 8 + (lane & 3) * 2;
+                                        if (col < B)
+                                          {
+                                            const double2 xc = __ldcg(reinterpret_cast<const double2 *>(a.X + ro + col));
+                                            double2       xp = make_double2(0.0, 0.0);
+                                            if (a.f_c != 0.0)
+                                              xp = __ldcg(reinterpret_cast<const double2 *>(a.f_xprev + ro + col));
+                                            double2 o;
+                                            o.x = cheb_combine(a.f_a, __dmul_rn(dv, y[t].x + acc[j][t][0]), a.f_b, xc.x, a.f_c, xp.x);
+                                            o.y = cheb_combine(a.f_a, __dmul_rn(dv, y[t].y + acc[j][t][1]), a.f_b, xc.y, a.f_c, xp.y);
+                                            __stcg(reinterpret_cast<double2 *>(a.f_out + ro + col), o);
+                                          }
+                                      }
+                                  }
+                                else
+                                  {
+#pragma unroll
+                                    for (int t = 0; t < NT; ++t)
+                                      {
+                                        const uint32_t col = b0 + t * 8 + (lane & 3) * 2;
+                                        if (col < B)
+                                          {
+                                            y[t].x += acc[j][t][0];
+                                            y[t].y += acc[j][t][1];
+                                            __stcg(reinterpret_cast<double2 *>(dst + col), y[t]);
+                                          }
                                       }
                                   }
                               }
@@ -955,12 +994,12 @@ namespace hx
     return HX_OK;
   }
 
-  template <int NT, int MTW, bool VEC, int MINB>
+  template <int NT, int MTW, bool VEC, int MINB, bool FUSE>
   static int
   launch_ordered(hx_op *op, CellArgs a)
   {
     hx_plan *    p      = op->plan;
-    auto         k      = cell_apply_ordered_kernel<NT, MTW, VEC, MINB>;
+    auto         k      = cell_apply_ordered_kernel<NT, MTW, VEC, MINB, FUSE>;
     const size_t budget = 225 * 1024 / MINB - 1024; // per CTA (1 KB reserved by the runtime per CTA)
     size_t       ns     = (budget - SM_HEADER) / (size_t)stage_bytes(NT, MTW);
     if (ns > MAX_STAGES)
@@ -986,8 +1025,10 @@ namespace hx
   }
 
   int
-  launch_cell_apply(hx_op *op, const double *X, double *Y, uint32_t B)
+  launch_cell_apply(hx_op *op, const double *X, double *Y, uint32_t B, const FuseArgs *fuse, bool *fused_applied)
   {
+    if (fused_applied)
+      *fused_applied = false;
     hx_plan *p = op->plan;
     HX_CHECK(op->have_matrices, HX_ERR_INVALID, "cell operator has no matrices (call hx_cellop_set_matrices)");
     if (p->C == 0)
@@ -1030,8 +1071,19 @@ namespace hx
             a.epoch  = ++p->epoch;
           }
         HX_CHECK((size_t)a.nItems <= p->d_flags.n, HX_ERR_INVALID, "flag array too small");
-#define HX_ORD(NT_, MTW_, MINB_) \
-  (vec ? launch_ordered<NT_, MTW_, true, MINB_>(op, a) : launch_ordered<NT_, MTW_, false, MINB_>(op, a))
+        // the Chebyshev epilogue exists for the vectorised variants (B even, 16-B aligned operands)
+        const bool fz = fuse != nullptr && vec && fuse->dinv && fuse->out && (fuse->c == 0.0 || fuse->xprev) &&
+                        ((((uintptr_t)fuse->out | (uintptr_t)fuse->xprev) & 15) == 0);
+        if (fz)
+          {
+            a.f_dinv = fuse->dinv, a.f_xprev = fuse->xprev ? fuse->xprev : fuse->out, a.f_out = fuse->out;
+            a.f_a = fuse->a, a.f_b = fuse->b, a.f_c = fuse->c;
+            if (fused_applied)
+              *fused_applied = true;
+          }
+#define HX_ORD(NT_, MTW_, MINB_)                                                                       \
+  (fz ? launch_ordered<NT_, MTW_, true, MINB_, true>(op, a) :                                          \
+        (vec ? launch_ordered<NT_, MTW_, true, MINB_, false>(op, a) : launch_ordered<NT_, MTW_, false, MINB_, false>(op, a)))
 #define HX_ORD_M(NT_, MTW_) (minb == 2 ? HX_ORD(NT_, MTW_, 2) : HX_ORD(NT_, MTW_, 1))
         if (op->mtw == 1)
           switch (nt)

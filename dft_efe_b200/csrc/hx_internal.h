@@ -135,7 +135,36 @@ namespace hx
 
 #define HX_DEST_STAGED 0x80000000u
 #define HX_DEST_FIRST 0x40000000u
-#define HX_DEST_ROW(d) ((d)&0x3fffffffu)
+#define HX_DEST_LASTF 0x20000000u /* last toucher (processing order) of a row whose Chebyshev update can be fused */
+#define HX_DEST_ROW(d) ((d)&0x1fffffffu)
+
+namespace hx
+{
+  // Chebyshev recurrence epilogue fused into the cell kernel's scatter: the last toucher of a "fusable" row
+  // (owned classical row, unconstrained, no hanging-node children, no halo contribution, not staged) holds the
+  // final (H X)[r,:] in registers and writes out[r,:] = a*dinv[r]*(H X)[r,:] + b*X[r,:] + c*xprev[r,:] directly,
+  // so H X never goes to memory for those rows.  All other owned rows go through cheb_fused_kernel on a row list.
+  struct FuseArgs
+  {
+    const double *dinv  = nullptr; // M^-1 diagonal over local rows
+    const double *xprev = nullptr; // may alias out; ignored when c == 0
+    double *      out   = nullptr;
+    double        a = 0.0, b = 0.0, c = 0.0;
+  };
+
+#ifdef __CUDACC__
+  // one definition of the update so the fused epilogue and the row-list kernel agree bit for bit
+  // (ChebyshevFilter.t.cpp:105-124: temp = a*t + b*xcur; new = 1*temp + c*xprev)
+  __device__ __forceinline__ double
+  cheb_combine(double a, double t, double b, double xc, double c, double xp)
+  {
+    double o = __fma_rn(a, t, __dmul_rn(b, xc));
+    if (c != 0.0)
+      o = __fma_rn(c, xp, o);
+    return o;
+  }
+#endif
+} // namespace hx
 
 struct hx_plan
 {
@@ -184,6 +213,10 @@ struct hx_plan
   uint32_t              epoch = 0;
   uint32_t              n_untouched = 0;
   hx::DevBuf<uint32_t>  d_untouched; // rows no cell writes (zeroed explicitly each apply)
+  // Chebyshev epilogue fusion: owned rows NOT updated inside the cell kernel (row-list pass afterwards)
+  uint32_t              n_nonfuse = 0, n_fusable = 0;
+  hx::DevBuf<uint32_t>  d_nonfuse_rows;
+  bool                  cheb_fusable_multirank = true; // no constrained ghost row has parents (see api.cu)
   int                   sm_count = 0;
 
   hx::Halo  halo;
@@ -265,11 +298,15 @@ namespace hx
   int launch_shared_reduce(hx_plan *p, double *Y, uint32_t B);
   int launch_zero_rows(hx_plan *p, double *Y, uint32_t B, const uint32_t *rows, uint32_t n);
   int launch_enr_block(hx_plan *p, const double *blk, uint32_t nE, const double *Xenr, double *Yenr, uint32_t B);
-  int launch_cell_apply(hx_op *op, const double *X, double *Y, uint32_t B);
+  // fuse != nullptr asks for the Chebyshev epilogue; *fused_applied tells whether the launched variant did it
+  int launch_cell_apply(hx_op *op, const double *X, double *Y, uint32_t B, const FuseArgs *fuse = nullptr,
+                        bool *fused_applied = nullptr);
   int launch_nl_phase_a(hx_op *op, const double *X, uint32_t B);
   int pack_cell_matrices(hx_op *op, const double *raw_dev_or_host, int on_device);
+  // use_row_list false: all owned rows; true: only the n_rows listed rows
   int launch_cheb_fused(hx_plan *p, hx_op *binv, const double *s1, const double *xcur, const double *xprev,
-                        double *out, uint32_t B, double a, double b, double c);
+                        double *out, uint32_t B, double a, double b, double c, bool use_row_list = false,
+                        const uint32_t *rows = nullptr, uint32_t n_rows = 0);
   int gram_block(hx_plan *p, const double *X, uint32_t B, uint32_t j0, const double *OpXb, uint32_t b,
                  size_t nOwned, double *S_dev);
   int rotate(hx_plan *p, double *X, uint32_t B, size_t nOwned, const double *Q_dev, int transpose, int lowerTri,

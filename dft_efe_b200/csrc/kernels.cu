@@ -354,13 +354,19 @@ namespace hx
   __global__ void
   cheb_fused_kernel(const double *s1, const double *xcur, const double *xprev, double *out, const double *dinv,
                     const uint32_t *rowinfo, const uint32_t *parOff, const uint32_t *parChild, const double *parW,
-                    const double *blk, uint32_t ncl, uint32_t nE, uint32_t nOwned, uint32_t B, double a, double b,
-                    double c)
+                    const double *blk, uint32_t ncl, uint32_t nE, uint32_t nRows, uint32_t B, double a, double b,
+                    double c, const uint32_t *rows)
   {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (size_t)nOwned * B)
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)nRows * B)
       return;
-    const uint32_t r = (uint32_t)(i / B), v = (uint32_t)(i % B);
+    uint32_t r = (uint32_t)(i / B);
+    const uint32_t v = (uint32_t)(i % B);
+    if (rows)
+      {
+        r = rows[r];
+        i = (size_t)r * B + v;
+      }
     double         t;
     const uint32_t info = rowinfo[r];
     if (info == 0xFFFFFFFEu)
@@ -383,10 +389,7 @@ namespace hx
               t += parW[e] * (dinv[ch] * s1[(size_t)ch * B + v]);
             }
       }
-    double o = a * t + b * xcur[i];
-    if (c != 0.0)
-      o += c * xprev[i];
-    out[i] = o;
+    out[i] = cheb_combine(a, t, b, xcur[i], c, c != 0.0 ? xprev[i] : 0.0);
   }
 } // namespace hx
 
@@ -394,16 +397,19 @@ namespace hx
 {
   int
   launch_cheb_fused(hx_plan *p, hx_op *binv, const double *s1, const double *xcur, const double *xprev, double *out,
-                    uint32_t B, double a, double b, double c)
+                    uint32_t B, double a, double b, double c, bool use_row_list, const uint32_t *rows, uint32_t n_rows)
   {
-    const size_t tot = (size_t)p->n_owned * B;
+    if (!use_row_list)
+      rows = nullptr;
+    const uint32_t nr  = use_row_list ? n_rows : p->n_owned;
+    const size_t   tot = (size_t)nr * B;
     if (tot == 0)
       return HX_OK;
     cheb_fused_kernel<<<nblk(tot), 256, 0, p->stream>>>(s1, xcur, xprev ? xprev : xcur, out, binv->d_diag.p,
                                                         p->d_rowinfo.p, p->d_par_off.p, p->d_par_child.p,
                                                         p->d_par_w.p, binv->d_enr_block.p, p->n_owned_classical,
-                                                        binv->variant == HX_DIAG_CFE ? 0u : binv->nE, p->n_owned, B,
-                                                        a, b, xprev ? c : 0.0);
+                                                        binv->variant == HX_DIAG_CFE ? 0u : binv->nE, nr, B, a, b,
+                                                        xprev ? c : 0.0, rows);
     p->launches++;
     HX_CUDA(cudaGetLastError());
     return HX_OK;

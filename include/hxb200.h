@@ -132,6 +132,10 @@ int hx_plan_get_cell_colours(hx_plan *plan, uint32_t *colour /*[C]*/);
 int hx_plan_get_processing_order(hx_plan *plan, uint32_t *order /*[C]*/);
 /* ordered scatter: per cell (in processing order) the preceding cells it must wait for; pass NULLs to query nnz. */
 int hx_plan_get_wait_lists(hx_plan *plan, uint32_t *nnz, uint32_t *offsets /*[C+1]*/, uint32_t *preds /*[nnz]*/);
+/* Chebyshev epilogue fusion: rows whose recurrence update is applied by their last toucher inside the cell kernel
+ * (owned classical, unconstrained, no hanging-node children, no halo contribution, <= 8 incident cells), and the
+ * remaining owned rows that the row-list pass updates. */
+int hx_plan_get_fusable_rows(hx_plan *plan, uint32_t *n_fusable, uint32_t *n_other_owned);
 int hx_plan_get_c2p_transpose(hx_plan *plan, uint32_t *n_parents, uint32_t *parent_ids, uint32_t *offsets,
                               uint32_t *child_rows, double *weights); /* pass NULLs to query n_parents */
 

@@ -311,6 +311,35 @@ def test_chebyshev_filter(capi, prob_full, variant):
     assert np.array_equal(dX.download()[:own], dY.download()[:own])  # both hold the result
 
 
+@pytest.mark.parametrize("B", [2, 7, 8, 32, 40])
+@pytest.mark.parametrize("mesh", ["full", "plain"])
+def test_chebyshev_epilogue_fusion_is_bitwise_the_unfused_recurrence(capi, prob_full, prob_plain, mesh, B):
+    """The recurrence applied by the last toucher inside the cell kernel's scatter (most rows) + the row-list pass
+    (constrained / parent / enrichment / halo rows) must equal the separate full-vector pass bit for bit, and the
+    oracle within the filter tolerance."""
+    import os
+    p = prob_full if mesh == "full" else prob_plain
+    deg = 5
+    a0, a, b = -3.0, 1.0, 60.0
+    plan = capi.Plan(p, max_block=B)
+    H = capi.CellOp(plan)
+    minv = capi.DiagOp(plan, p.diag_inv, p.enr_block_inv, capi.DIAG_OEFE_ATOMBLOCK)
+    X = synth.make_block(p, B)
+    res = []
+    for off in (False, True):
+        if off:
+            os.environ["HXB200_NO_EPILOGUE_FUSION"] = "1"
+        try:
+            dX, dY = plan.block(B, X), plan.block(B)
+            capi.chebyshev_filter(H, minv, dX, dY, deg, a0, a, b)
+            res.append(dY.download()[:p.n_owned])
+        finally:
+            os.environ.pop("HXB200_NO_EPILOGUE_FUSION", None)
+    assert np.array_equal(res[0], res[1])
+    F = orc.OracleWorld([p]).chebyshev_filter([X.copy()], deg, a0, a, b)[0]
+    assert rel_l2_per_vector(res[0], F[:p.n_owned]) < 1e-11
+
+
 def test_chebyshev_filter_host_entry(capi, prob_full):
     """hx_chebyshev_filter_host (HOST buffers in/out) == the device entry point, bit for bit."""
     p = prob_full
