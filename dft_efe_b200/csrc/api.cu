@@ -233,6 +233,31 @@ namespace hx
     HX_TRY(p->d_sh_off.upload(sh_off));
     HX_TRY(p->d_sh_slots.upload(sh_slots));
     HX_TRY(p->d_stage.alloc((size_t)p->n_slots * p->max_block));
+    {
+      const uint32_t SH_CHUNK = 64;
+      uint32_t       max_cnt  = 0;
+      for (uint32_t r = 0; r < p->n_shared; ++r)
+        max_cnt = std::max(max_cnt, sh_off[r + 1] - sh_off[r]);
+      p->n_sh_chunks = 0;
+      if (max_cnt > 2 * SH_CHUNK)
+        {
+          std::vector<uint32_t> cb, ce, coff(1, 0);
+          for (uint32_t r = 0; r < p->n_shared; ++r)
+            {
+              for (uint32_t e = sh_off[r]; e < sh_off[r + 1]; e += SH_CHUNK)
+                {
+                  cb.push_back(e);
+                  ce.push_back(std::min(e + SH_CHUNK, sh_off[r + 1]));
+                }
+              coff.push_back((uint32_t)cb.size());
+            }
+          p->n_sh_chunks = (uint32_t)cb.size();
+          HX_TRY(p->d_sh_ch_begin.upload(cb));
+          HX_TRY(p->d_sh_ch_end.upload(ce));
+          HX_TRY(p->d_sh_ch_off.upload(coff));
+          HX_TRY(p->d_sh_partial.alloc((size_t)p->n_sh_chunks * p->max_block));
+        }
+    }
 
     // ---- greedy cell colouring on the cell-DoF graph (non-shared rows only) ----
     // cell c takes the lowest colour not used by any earlier cell sharing a row with it.

@@ -201,6 +201,10 @@ struct hx_plan
   uint32_t              n_shared = 0, n_slots = 0;
   hx::DevBuf<uint32_t>  d_sh_rows, d_sh_off, d_sh_slots;
   hx::DevBuf<double>    d_stage; // n_slots x max_block
+  // two-stage reduction of heavily shared rows (used when some row has > 2*SH_CHUNK slots)
+  uint32_t              n_sh_chunks = 0;
+  hx::DevBuf<uint32_t>  d_sh_ch_begin, d_sh_ch_end, d_sh_ch_off;
+  hx::DevBuf<double>    d_sh_partial; // n_sh_chunks x max_block
 
   // ordered (persistent) scatter: cells are processed in `order`; a cell adds into Y only after the
   // immediately preceding toucher of each of its rows has signalled completion -> fixed summation order

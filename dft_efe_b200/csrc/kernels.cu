@@ -307,11 +307,51 @@ namespace hx
       s += stage[(size_t)slots[e] * B + v];
     Y[(size_t)rows[r] * B + v] = s;
   }
+  // rows shared by very many cells (an enrichment function spans every cell inside its cutoff): two-stage
+  // fixed-order reduction - chunks of SH_CHUNK consecutive slots are summed in parallel, then the chunk partials
+  // of a row in chunk order.  Deterministic; the grouping differs from the plain ascending sum only in rounding.
+  __global__ void
+  shared_reduce_chunks_kernel(const double *stage, const uint32_t *chBegin, const uint32_t *chEnd, const uint32_t *slots,
+                              double *partial, uint32_t nChunks, uint32_t B)
+  {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)nChunks * B)
+      return;
+    const uint32_t k = (uint32_t)(i / B), v = (uint32_t)(i % B);
+    double         s = 0.0;
+    for (uint32_t e = chBegin[k]; e < chEnd[k]; ++e)
+      s += stage[(size_t)slots[e] * B + v];
+    partial[i] = s;
+  }
+  __global__ void
+  shared_reduce_final_kernel(double *Y, const double *partial, const uint32_t *rows, const uint32_t *chOff, uint32_t nrows,
+                             uint32_t B)
+  {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)nrows * B)
+      return;
+    const uint32_t r = (uint32_t)(i / B), v = (uint32_t)(i % B);
+    double         s = 0.0;
+    for (uint32_t k = chOff[r]; k < chOff[r + 1]; ++k)
+      s += partial[(size_t)k * B + v];
+    Y[(size_t)rows[r] * B + v] = s;
+  }
+
   int
   launch_shared_reduce(hx_plan *p, double *Y, uint32_t B)
   {
     if (p->n_shared == 0)
       return HX_OK;
+    if (p->n_sh_chunks)
+      {
+        shared_reduce_chunks_kernel<<<nblk((size_t)p->n_sh_chunks * B), 256, 0, p->stream>>>(
+          p->d_stage.p, p->d_sh_ch_begin.p, p->d_sh_ch_end.p, p->d_sh_slots.p, p->d_sh_partial.p, p->n_sh_chunks, B);
+        shared_reduce_final_kernel<<<nblk((size_t)p->n_shared * B), 256, 0, p->stream>>>(
+          Y, p->d_sh_partial.p, p->d_sh_rows.p, p->d_sh_ch_off.p, p->n_shared, B);
+        p->launches += 2;
+        HX_CUDA(cudaGetLastError());
+        return HX_OK;
+      }
     shared_reduce_kernel<<<nblk((size_t)p->n_shared * B), 256, 0, p->stream>>>(Y, p->d_stage.p, p->d_sh_rows.p,
                                                                                p->d_sh_off.p, p->d_sh_slots.p,
                                                                                p->n_shared, B);

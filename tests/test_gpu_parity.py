@@ -292,6 +292,28 @@ def test_diag_ops(capi, prob_full, variant):
     assert rel_l2_per_vector(dY.download(), Yo) < 1e-14
 
 
+def test_hx_enrichment_rows_shared_by_every_cell(capi):
+    """an enrichment function whose cutoff covers the whole mesh: its row is touched by all 216 cells and goes
+    through the two-stage fixed-order reduction of the staging slots."""
+    nc = (6, 6, 6)
+    spec = synth.MeshSpec(ncell=nc, p=3, atoms=np.array([[2.9, 3.1, 3.0]]), n_enr_per_atom=3, enr_cutoff=1e3,
+                          n_proj_per_atom=2, proj_cutoff=1.1)
+    p = synth.build_problem(spec)[0]
+    assert int(np.bincount(p.cell_local_ids.astype(np.int64)).max()) == 216
+    B = 16
+    plan = capi.Plan(p, max_block=B)
+    op = capi.CellOp(plan)
+    X = synth.make_block(p, B)
+    dX, dY = plan.block(B, X), plan.block(B)
+    op.apply(dX, dY, True, False)
+    Y1 = dY.download()
+    Xo, Yo = X.copy(), np.zeros_like(X)
+    orc.OracleWorld([p]).hx_apply([Xo], [Yo], True, False)
+    assert rel_l2_per_vector(Y1, Yo) < RTOL_HX
+    op.apply(plan.block(B, X), dY, True, False)
+    assert np.array_equal(Y1, dY.download())  # fixed reduction order: bitwise reproducible
+
+
 # ------------------------------------------------------------------------- filters ----
 @pytest.mark.parametrize("variant", ["cfe", "oefe_atomblock"])
 def test_chebyshev_filter(capi, prob_full, variant):
