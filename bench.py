@@ -328,7 +328,7 @@ def run_ours(args):
                                    f"{len(spec.atoms)} atoms x {spec.n_enr_per_atom} enrichment fns + "
                                    f"{spec.n_proj_per_atom} projectors, z-slab per GPU",
                        "global_dofs": N_global, "block": B, "degree": DEGREE, "cells_per_gpu": prob.n_cells,
-                       "parallelism": f"cells/{nranks}",
+                       "parallelism": f"cells/{nranks}", "halo_transport": plan.halo_transport(),
                        "l2_policy": "inputs larger than L2 (cell matrices %.2f GB + 4 block vectors %.2f GB per GPU)"
                                     % (8 * S2 / 1e9, 4 * blk_bytes / 1e9)},
             "e2e": {"value": DEGREE * N_global * B / (e2e_ms * 1e-3) / 1e9, "unit": UNIT,

@@ -19,7 +19,7 @@ f64p = C.POINTER(C.c_double)
 EXPORTS = [
     "hx_last_error", "hx_version", "hx_device_count", "hx_set_device", "hx_device_alloc", "hx_device_free",
     "hx_host_alloc_pinned", "hx_host_free_pinned", "hx_memcpy_h2d", "hx_memcpy_d2h", "hx_memset_zero",
-    "hx_plan_create", "hx_plan_destroy", "hx_plan_synchronize", "hx_comm_unique_id", "hx_plan_attach_comm",
+    "hx_plan_create", "hx_plan_destroy", "hx_plan_synchronize", "hx_comm_unique_id", "hx_plan_attach_comm", "hx_plan_halo_transport",
     "hx_plan_set_scatter_mode", "hx_plan_get_wait_lists", "hx_plan_get_processing_order", "hx_plan_num_colours", "hx_plan_get_cell_colours", "hx_plan_get_c2p_transpose", "hx_plan_get_fusable_rows", "hx_update_ghost_values",
     "hx_accumulate_add_locally_owned", "hx_distribute_parent_to_child", "hx_distribute_child_to_parent",
     "hx_set_constrained_nodes_to_zero", "hx_cellop_create", "hx_cellop_set_matrices", "hx_cellop_set_nonlocal",
@@ -183,6 +183,11 @@ class Plan:
     def attach_comm(self, uid: bytes):
         assert len(uid) == 128
         check(lib().hx_plan_attach_comm(self.h, C.c_char_p(uid)))
+
+    def halo_transport(self) -> str:
+        t = C.c_int()
+        check(lib().hx_plan_halo_transport(self.h, C.byref(t)))
+        return {0: "none", 1: "nccl", 2: "nvlink-peer"}[t.value]
 
     def set_scatter_mode(self, mode: int):
         check(lib().hx_plan_set_scatter_mode(self.h, C.c_int(mode)))

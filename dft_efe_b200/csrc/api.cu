@@ -72,12 +72,52 @@ namespace hx
     return HX_OK;
   }
 
+  // first use of a halo after the communicator is attached: bring up the NVLink peer-memory transport (collective;
+  // every rank reaches this point for the same halo), or stay on NCCL send/recv (HXB200_HALO=nccl, or no IPC)
+  static int
+  halo_pick_transport(hx_plan *p, Halo &h)
+  {
+    if (h.peer || h.peer_failed)
+      return HX_OK;
+    const char *e = getenv("HXB200_HALO");
+    if (e && strcmp(e, "nccl") == 0)
+      h.peer_failed = true;
+    else
+      HX_TRY(peer_setup(p, h));
+    if (&h == &p->halo)
+      p->halo_transport = h.peer ? 2 : 1;
+    return HX_OK;
+  }
+
+  // collective teardown of a peer transport: no rank may unmap / free its arena while a neighbour's last
+  // acknowledgement can still be in flight
+  static void
+  halo_peer_release(hx_plan *p, Halo &h)
+  {
+    if (!h.peer)
+      return;
+    cudaStreamSynchronize(p->stream);
+    if (p->comm)
+      {
+        std::vector<unsigned char> f1(4, 0), fall(4 * (size_t)p->nranks, 0);
+        comm_allgather_bytes(p->comm, p->stream, f1.data(), fall.data(), 4);
+      }
+    p->peer_halos.erase(std::remove(p->peer_halos.begin(), p->peer_halos.end(), &h), p->peer_halos.end());
+    peer_destroy(h.peer);
+    h.peer = nullptr;
+  }
+
   static int
   halo_update(hx_plan *p, Halo &h, double *X, uint32_t B)
   {
-    if (p->nranks == 1 || (h.n_ghost == 0 && h.n_send == 0))
+    if (p->nranks == 1)
       return HX_OK;
     HX_CHECK(p->comm != nullptr, HX_ERR_COMM, "nranks > 1 but no communicator attached (hx_plan_attach_comm)");
+    HX_TRY(halo_pick_transport(p, h)); // collective: before the early-out of ranks with nothing to exchange
+    if (h.n_ghost == 0 && h.n_send == 0)
+      return HX_OK;
+    if (h.peer)
+      return peer_halo_update(p, h, X, B);
     HX_TRY(launch_pack(p, X, B, h.d_owned_ids_for_targets.p, h.n_send, h.d_send.p));
     std::vector<size_t> sc(h.target_counts.size()), rc(h.ghost_procs.size());
     for (size_t i = 0; i < sc.size(); ++i)
@@ -91,9 +131,14 @@ namespace hx
   static int
   halo_accumulate(hx_plan *p, Halo &h, double *Y, uint32_t B)
   {
-    if (p->nranks == 1 || (h.n_ghost == 0 && h.n_send == 0))
+    if (p->nranks == 1)
       return HX_OK;
     HX_CHECK(p->comm != nullptr, HX_ERR_COMM, "nranks > 1 but no communicator attached (hx_plan_attach_comm)");
+    HX_TRY(halo_pick_transport(p, h));
+    if (h.n_ghost == 0 && h.n_send == 0)
+      return HX_OK;
+    if (h.peer)
+      return peer_halo_accumulate(p, h, Y, B);
     HX_TRY(launch_pack(p, Y + (size_t)h.n_owned * B, B, h.d_ghost_local_ids.p, h.n_ghost, h.d_send.p));
     std::vector<size_t> sc(h.ghost_procs.size()), rc(h.target_counts.size());
     for (size_t i = 0; i < sc.size(); ++i)
@@ -759,6 +804,7 @@ extern "C"
     if (plan)
       {
         cudaStreamSynchronize(plan->stream);
+        halo_peer_release(plan, plan->halo);
         delete plan;
       }
     return HX_OK;
@@ -769,6 +815,16 @@ extern "C"
   {
     HX_CHECK(plan, HX_ERR_INVALID, "null plan");
     HX_CUDA(cudaStreamSynchronize(plan->stream));
+    for (Halo *h : plan->peer_halos)
+      HX_TRY(peer_check_status(*h));
+    return HX_OK;
+  }
+
+  int
+  hx_plan_halo_transport(hx_plan *plan, int *transport)
+  {
+    HX_CHECK(plan && transport, HX_ERR_INVALID, "null argument");
+    *transport = plan->halo_transport;
     return HX_OK;
   }
 
@@ -1002,6 +1058,7 @@ extern "C"
     if (op)
       {
         cudaStreamSynchronize(op->plan->stream);
+        halo_peer_release(op->plan, op->phalo);
         delete op;
       }
     return HX_OK;
@@ -1070,6 +1127,19 @@ extern "C"
     const double sigma1 = sigma;
     const double gamma  = 2.0 / sigma1;
     const size_t nown   = (size_t)p->n_owned * B;
+    // the fused M^-1 needs no ghost update only if NO rank has a constrained ghost row with parents: the ranks must
+    // agree (the unfused path contains an extra collective exchange), so the local flags are AND-ed once
+    if (p->nranks > 1 && !p->cheb_fusable_agreed && BInv->kind == HX_OP_DIAG && BInv->variant != HX_DIAG_CFE)
+      {
+        HX_CHECK(p->comm != nullptr, HX_ERR_COMM, "nranks > 1 but no communicator attached (hx_plan_attach_comm)");
+        std::vector<unsigned char> f1(4, 0), fall(4 * (size_t)p->nranks, 0);
+        f1[0] = p->cheb_fusable_multirank ? 1 : 0;
+        HX_TRY(comm_allgather_bytes(p->comm, p->stream, f1.data(), fall.data(), 4));
+        for (int q = 0; q < p->nranks; ++q)
+          if (!fall[4 * (size_t)q])
+            p->cheb_fusable_multirank = false;
+        p->cheb_fusable_agreed = true;
+      }
     const bool   fused  = BInv->kind == HX_OP_DIAG && X != Y &&
                        (BInv->variant == HX_DIAG_CFE || p->nranks == 1 || p->cheb_fusable_multirank);
     double *     s1, *s2 = nullptr;

@@ -38,6 +38,7 @@ namespace hx
     int (*Send)(const void *, size_t, int, int, ncclComm_t, cudaStream_t)                   = nullptr;
     int (*Recv)(void *, size_t, int, int, ncclComm_t, cudaStream_t)                         = nullptr;
     int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t)      = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t)           = nullptr;
     int (*GroupStart)()                                                                     = nullptr;
     int (*GroupEnd)()                                                                       = nullptr;
     const char *(*GetErrorString)(int)                                                      = nullptr;
@@ -67,6 +68,7 @@ namespace hx
     HX_SYM(Send, "ncclSend");
     HX_SYM(Recv, "ncclRecv");
     HX_SYM(AllReduce, "ncclAllReduce");
+    HX_SYM(AllGather, "ncclAllGather");
     HX_SYM(GroupStart, "ncclGroupStart");
     HX_SYM(GroupEnd, "ncclGroupEnd");
     HX_SYM(GetErrorString, "ncclGetErrorString");
@@ -157,6 +159,21 @@ namespace hx
         off += send_counts[i];
       }
     HX_NCCL(g_nccl.GroupEnd());
+    return HX_OK;
+  }
+
+  // small host-to-host all-gather (setup metadata of the peer-memory halo): staged through device memory
+  int
+  comm_allgather_bytes(Comm *c, cudaStream_t s, const void *mine, void *all, size_t bytes_per_rank)
+  {
+    HX_CHECK(c && c->comm, HX_ERR_COMM, "communicator not initialised");
+    DevBuf<unsigned char> ds, dr;
+    HX_TRY(ds.alloc(bytes_per_rank));
+    HX_TRY(dr.alloc(bytes_per_rank * (size_t)c->nranks));
+    HX_CUDA(cudaMemcpyAsync(ds.p, mine, bytes_per_rank, cudaMemcpyHostToDevice, s));
+    HX_NCCL(g_nccl.AllGather(ds.p, dr.p, bytes_per_rank, ncclInt8, c->comm, s));
+    HX_CUDA(cudaMemcpyAsync(all, dr.p, bytes_per_rank * (size_t)c->nranks, cudaMemcpyDeviceToHost, s));
+    HX_CUDA(cudaStreamSynchronize(s));
     return HX_OK;
   }
 

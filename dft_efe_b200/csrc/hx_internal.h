@@ -98,9 +98,23 @@ namespace hx
     }
   };
 
+  struct PeerState; // peer.cu: NVLink peer-memory transport of one halo
+  void peer_destroy(PeerState *s);
+
   // device-side copy of one MPIPatternP2P + the communicator buffers of MPICommunicatorP2P
   struct Halo
   {
+    PeerState *peer        = nullptr; // set once the peer-memory transport is up (lazy, collective)
+    bool       peer_failed = false;   // IPC mapping unavailable: NCCL send/recv stays in charge
+    Halo() = default;
+    Halo(const Halo &) = delete;
+    Halo &
+    operator=(const Halo &) = delete;
+    ~Halo()
+    {
+      if (peer)
+        peer_destroy(peer);
+    }
     uint32_t              n_owned = 0, n_ghost = 0;
     std::vector<uint32_t> ghost_procs, ghost_ranges, target_procs, target_counts;
     uint32_t              n_send = 0; // total owned indices for targets
@@ -221,10 +235,13 @@ struct hx_plan
   uint32_t              n_nonfuse = 0, n_fusable = 0;
   hx::DevBuf<uint32_t>  d_nonfuse_rows;
   bool                  cheb_fusable_multirank = true; // no constrained ghost row has parents (see api.cu)
+  bool                  cheb_fusable_agreed    = false; // ... on every rank (AND-ed across the communicator once)
   int                   sm_count = 0;
 
   hx::Halo  halo;
   hx::Comm *comm = nullptr;
+  int       halo_transport = 0;          // 0 = undecided / single rank, 1 = NCCL send/recv, 2 = NVLink peer memory
+  std::vector<hx::Halo *> peer_halos;    // halos with a live peer transport (status checked at synchronisation)
 
   // scratch block vectors (n_local x max_block), allocated on demand
   std::vector<hx::DevBuf<double> *> scratch;
@@ -323,4 +340,10 @@ namespace hx
                     const std::vector<size_t> &send_counts, double *recv, const std::vector<uint32_t> &recv_procs,
                     const std::vector<size_t> &recv_counts);
   int comm_allreduce_sum(Comm *c, cudaStream_t s, double *buf, size_t n);
+  int comm_allgather_bytes(Comm *c, cudaStream_t s, const void *mine, void *all, size_t bytes_per_rank);
+  // peer.cu
+  int peer_setup(hx_plan *p, Halo &h);
+  int peer_halo_update(hx_plan *p, Halo &h, double *X, uint32_t B);
+  int peer_halo_accumulate(hx_plan *p, Halo &h, double *Y, uint32_t B);
+  int peer_check_status(Halo &h);
 } // namespace hx

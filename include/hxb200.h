@@ -118,6 +118,10 @@ int hx_plan_synchronize(hx_plan *plan);
  * MPIPatternP2P (src/utils/MPIPatternP2P.h:489).  Ranks of the halo descriptors are communicator ranks. */
 int hx_comm_unique_id(char id[128]);
 int hx_plan_attach_comm(hx_plan *plan, const char id[128]);
+/* Transport the ghost communicator settled on at its first exchange: 0 = none yet / single rank, 1 = NCCL send/recv,
+ * 2 = NVLink peer memory (the pack kernel stores straight into the neighbour's receive buffer and raises a flag; the
+ * unpack / ordered-add kernel waits for it).  HXB200_HALO=nccl forces 1; 2 needs CUDA IPC between the ranks. */
+int hx_plan_halo_transport(hx_plan *plan, int *transport);
 /* Scatter strategy of the cell kernel: 0 (default) = one persistent launch, cells in the caller's order, each
  * row accumulated in ascending cell order behind per-cell completion stamps (no atomics, bitwise reproducible,
  * same per-row summation order as the reference's CPU loop, src/basis/FECellWiseDataOperations.t.cpp:87-153);

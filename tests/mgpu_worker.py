@@ -95,12 +95,41 @@ def main():
     nr = plan.l2_norms(dX)
     errs["l2"] = float(np.abs(nr - W.l2_norms(Xs)).max() / np.abs(nr).max())
 
-    tol = {"update_ghost": 0.0, "accumulate_add": 1e-14, "hx": 1e-12, "hx_x_modified": 1e-14, "cheb": 1e-11,
+    # ---- mesh without hanging nodes: the Chebyshev filter runs its fused path across ranks (recurrence applied in
+    # the cell kernel's scatter for interior rows, row-list pass for the partition-face rows) ----
+    spec2 = synth.MeshSpec(ncell=nc, p=4, atoms=atoms, n_enr_per_atom=2, enr_cutoff=1.2, n_proj_per_atom=2,
+                           proj_cutoff=1.0, nranks=world)
+    probs2 = synth.build_problem(spec2)
+    plan2 = capi.Plan(probs2[rank], max_block=B)
+    uid2 = torch.zeros(128, dtype=torch.uint8, device="cuda")   # a communicator needs its own unique id
+    if rank == 0:
+        uid2.copy_(torch.frombuffer(bytearray(capi.comm_unique_id()), dtype=torch.uint8))
+    dist.broadcast(uid2, 0)
+    plan2.attach_comm(bytes(uid2.cpu().numpy().tobytes()))
+    H2 = capi.CellOp(plan2)
+    minv2 = capi.DiagOp(plan2, probs2[rank].diag_inv, probs2[rank].enr_block_inv, capi.DIAG_OEFE_ATOMBLOCK)
+    X2 = [synth.make_block(q, B) for q in probs2]
+    dX, dF = plan2.block(B, X2[rank]), plan2.block(B)
+    capi.chebyshev_filter(H2, minv2, dX, dF, 7, -3.0, 1.0, 60.0)
+    F2 = orc.OracleWorld(probs2).chebyshev_filter([x.copy() for x in X2], 7, -3.0, 1.0, 60.0)
+    errs["cheb_fused"] = rel(dF.download()[:probs2[rank].n_owned], F2[rank][:probs2[rank].n_owned])
+    plan2.synchronize()
+    want = os.environ.get("HXB200_EXPECT_TRANSPORT")
+    if want:
+        assert plan.halo_transport() == want and plan2.halo_transport() == want, (plan.halo_transport(), want)
+
+    tol = {"update_ghost": 0.0, "cheb_fused": 1e-11, "accumulate_add": 1e-14, "hx": 1e-12, "hx_x_modified": 1e-14, "cheb": 1e-11,
            "xtopx": 1e-12, "l2": 1e-13}
     bad = {k: v for k, v in errs.items() if not v <= tol[k]}
-    print(f"[rank {rank}/{world}] " + " ".join(f"{k}={v:.2e}" for k, v in errs.items()), flush=True)
+    print(f"[rank {rank}/{world}] halo transport {plan.halo_transport()} " + " ".join(f"{k}={v:.2e}" for k, v in errs.items()), flush=True)
     t = torch.tensor([len(bad)], device="cuda")
     dist.all_reduce(t)
+    dist.barrier()
+    # collective teardown (peer transports synchronise across ranks): operators first, then plans
+    for o in (H, minv, H2, minv2):
+        o.destroy()
+    plan.destroy()
+    plan2.destroy()
     dist.barrier()
     dist.destroy_process_group()
     if int(t.item()):

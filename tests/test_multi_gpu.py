@@ -19,20 +19,29 @@ def _free_port():
     return port
 
 
-def _torchrun(script, nproc, timeout=600):
+def _torchrun(script, nproc, timeout=600, env=None):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
            "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), os.path.join(ROOT, "tests", script)]
-    return subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, cwd=ROOT)
+    e = dict(os.environ)
+    e.update(env or {})
+    return subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, cwd=ROOT, env=e)
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("transport", ["nvlink-peer", "nccl"])
 @pytest.mark.parametrize("nproc", [2, 4])
-def test_multi_gpu_parity(nproc):
+def test_multi_gpu_parity(nproc, transport):
+    """both halo transports: the fused pack->peer-store / wait->unpack kernels over NVLink peer memory (default) and
+    the NCCL send/recv fallback (HXB200_HALO=nccl)"""
     import torch
     if torch.cuda.device_count() < nproc:
         pytest.skip(f"needs {nproc} GPUs")
-    r = _torchrun("mgpu_worker.py", nproc)
+    env = {"HXB200_EXPECT_TRANSPORT": transport}
+    if transport == "nccl":
+        env["HXB200_HALO"] = "nccl"
+    r = _torchrun("mgpu_worker.py", nproc, timeout=240, env=env)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    print(r.stdout[-1500:])
 
 
 def test_partition_halo_logic_gloo_world2():
