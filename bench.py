@@ -158,6 +158,10 @@ def run_reference(args):
 
 # ----------------------------------------------------------------------------- GPU leg ----
 def run_ours(args):
+    # keep stdout for the ONE JSON line: libraries (NCCL's version banner) write to fd 1 during initialisation
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     from dft_efe_b200 import capi, synth
@@ -247,6 +251,17 @@ def run_ours(args):
         launches = plan.launch_count() - l0
         cell_ms, cell_launches = plan.cell_kernel_time_ms()
         plan.enable_kernel_timing(False)
+
+        # ---- phase breakdown of one filter call (untimed pass with CUDA events at the phase boundaries) ----
+        phases = {}
+        try:
+            plan.trace(True)
+            step()
+            rep = plan.trace_report()
+            plan.trace(False)
+            phases = {k: round(v["ms"] / DEGREE, 5) for k, v in rep.items()}
+        except Exception as e:  # noqa: BLE001
+            phases = {"error": str(e)[:200]}
 
         # ---- subspace projections: X^T H X (one column batch, Op.apply + Gram GEMM) and the rotation X <- X Q ----
         sub = {}
@@ -354,7 +369,8 @@ def run_ours(args):
                          "what": "bare KohnShamOperatorContextFE::apply (updateGhostX=true), block resident in HBM"},
             "subspace": sub,
             "chebyshev_filter": {"degree": DEGREE, "seconds_per_scf_iter": ms_per_step * 1e-3,
-                                 "ms_per_degree": ms_per_step / DEGREE, "fused_recurrence": True},
+                                 "ms_per_degree": ms_per_step / DEGREE, "fused_recurrence": True,
+                                 "phase_ms_per_degree": phases},
         }
         if not args.no_cpu and nranks == 1:
             try:
@@ -362,7 +378,10 @@ def run_ours(args):
                                         if k != "ms_per_step"}
             except Exception as e:  # the oracle is a checker; its absence must not hide the GPU number
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "port", "sample": f"failed: {e}"}
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     if nranks > 1:
         dist.barrier()
         dist.destroy_process_group()

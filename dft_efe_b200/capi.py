@@ -25,7 +25,7 @@ EXPORTS = [
     "hx_set_constrained_nodes_to_zero", "hx_cellop_create", "hx_cellop_set_matrices", "hx_cellop_set_nonlocal",
     "hx_diagop_create", "hx_op_destroy", "hx_op_apply", "hx_op_apply_host", "hx_chebyshev_filter", "hx_chebyshev_filter_host",
     "hx_residual_chebyshev_filter", "hx_xtopx", "hx_subspace_rotation", "hx_l2_norms", "hx_axpby",
-    "hx_axpby_blocked", "hx_plan_launch_count", "hx_plan_cell_kernel_time_ms", "hx_plan_enable_kernel_timing",
+    "hx_axpby_blocked", "hx_plan_launch_count", "hx_plan_cell_kernel_time_ms", "hx_plan_enable_kernel_timing", "hx_plan_trace", "hx_plan_trace_report",
     "hx_microbench",
 ]
 
@@ -253,6 +253,15 @@ class Plan:
         Qc = np.asfortranarray(Q, dtype=np.float64)
         check(lib().hx_subspace_rotation(self.h, X.p, C.c_uint32(X.B), Qc.ctypes.data_as(f64p), C.c_int(int(transpose)),
                                          C.c_int(int(lower_tri))))
+
+    def trace(self, on=True):
+        check(lib().hx_plan_trace(self.h, C.c_int(int(on))))
+
+    def trace_report(self) -> dict:
+        import json
+        buf = C.create_string_buffer(8192)
+        check(lib().hx_plan_trace_report(self.h, buf, C.c_size_t(8192)))
+        return json.loads(buf.value.decode())
 
     def launch_count(self) -> int:
         n = C.c_uint64()

@@ -544,30 +544,38 @@ namespace hx
                bool *fused_applied = nullptr)
   {
     hx_plan *p = op->plan;
+    p->mark("apply:begin");
     if (ugx)
       HX_TRY(halo_update(p, p->halo, X, B));
+    p->mark("x-halo");
     HX_TRY(launch_p2c(p, X, B));
     if (p->scatter_mode == 1)
       HX_CUDA(cudaMemsetAsync(Y, 0, (size_t)p->n_local * B * sizeof(double), p->stream));
     else // first touchers store instead of add: only rows no cell writes need clearing
       HX_TRY(launch_zero_rows(p, Y, B, p->d_untouched.p, p->n_untouched));
+    p->mark("p2c+zero");
     if (op->has_nl)
       {
         HX_TRY(launch_nl_phase_a(op, X, B));
+        p->mark("nl-phase-a");
         if (p->nranks > 1)
           {
             // applyAllReduceOnCconjtransX + applyVOnCconjtransX
             HX_TRY(halo_accumulate(p, op->phalo, op->d_cx.p, B));
             HX_TRY(halo_update(p, op->phalo, op->d_cx.p, B));
             HX_TRY(launch_row_scale(p, op->d_v.p, op->d_cx.p, op->d_cx.p, B, op->n_proj_local));
+            p->mark("nl-halo");
           }
       }
     HX_TRY(launch_cell_apply(op, X, Y, B, fuse, fused_applied));
+    p->mark("cell-kernel");
     HX_TRY(launch_shared_reduce(p, Y, B));
     HX_TRY(launch_c2p(p, Y, B));
+    p->mark("shared+c2p");
     HX_TRY(halo_accumulate(p, p->halo, Y, B));
     if (ugy)
       HX_TRY(halo_update(p, p->halo, Y, B));
+    p->mark("y-halo");
     return HX_OK;
   }
 
@@ -632,6 +640,10 @@ using namespace hx;
 
 hx_plan::~hx_plan()
 {
+  for (auto &m : trace_marks)
+    cudaEventDestroy(m.second);
+  for (auto e : trace_pool)
+    cudaEventDestroy(e);
   for (auto *s : scratch)
     delete s;
   if (h_pinned)
@@ -659,6 +671,26 @@ hx_plan::get_scratch(size_t idx, double **out)
   *out = scratch[idx]->p;
   return HX_OK;
 }
+void
+hx_plan::mark(const char *name)
+{
+  if (!trace)
+    return;
+  cudaEvent_t e;
+  if (trace_pool.empty())
+    {
+      if (cudaEventCreate(&e) != cudaSuccess)
+        return;
+    }
+  else
+    {
+      e = trace_pool.back();
+      trace_pool.pop_back();
+    }
+  cudaEventRecord(e, stream);
+  trace_marks.push_back({name, e});
+}
+
 int
 hx_plan::ensure_small(size_t doubles)
 {
@@ -1163,9 +1195,10 @@ extern "C"
       else
         HX_TRY(op_apply(A, xc, s1, B, 1, 0));
       HX_TRY(launch_p2c(p, s1, B));
-      if (applied)
-        return launch_cheb_fused(p, BInv, s1, xc, xp, out, B, ca, cb, cc, true, p->d_nonfuse_rows.p, p->n_nonfuse);
-      return launch_cheb_fused(p, BInv, s1, xc, xp, out, B, ca, cb, cc);
+      int r = applied ? launch_cheb_fused(p, BInv, s1, xc, xp, out, B, ca, cb, cc, true, p->d_nonfuse_rows.p, p->n_nonfuse) :
+                        launch_cheb_fused(p, BInv, s1, xc, xp, out, B, ca, cb, cc);
+      p->mark("cheb-rest");
+      return r;
     };
     if (fused)
       HX_TRY(degree_fused(cur, nullptr, oth, sigma1 / e, -sigma1 / e * c, 0.0));
@@ -1373,6 +1406,54 @@ extern "C"
     HX_CUDA(cudaMemcpyAsync(plan->d_small.p + B, beta_host, B * sizeof(double), cudaMemcpyHostToDevice, plan->stream));
     HX_CUDA(cudaStreamSynchronize(plan->stream));
     return launch_axpby_blocked(plan, n_rows, B, alpha1, plan->d_small.p, x, beta1, plan->d_small.p + B, y, z);
+  }
+
+  int
+  hx_plan_trace(hx_plan *plan, int on)
+  {
+    HX_CHECK(plan, HX_ERR_INVALID, "null plan");
+    HX_CUDA(cudaStreamSynchronize(plan->stream));
+    for (auto &m : plan->trace_marks)
+      plan->trace_pool.push_back(m.second);
+    plan->trace_marks.clear();
+    plan->trace = on != 0;
+    return HX_OK;
+  }
+
+  int
+  hx_plan_trace_report(hx_plan *plan, char *buf, size_t buf_bytes)
+  {
+    HX_CHECK(plan && buf && buf_bytes > 0, HX_ERR_INVALID, "null argument");
+    HX_CUDA(cudaStreamSynchronize(plan->stream));
+    std::vector<std::pair<std::string, std::pair<double, uint64_t>>> acc; // phase -> (ms, count), first-seen order
+    for (size_t i = 1; i < plan->trace_marks.size(); ++i)
+      {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, plan->trace_marks[i - 1].second, plan->trace_marks[i].second) != cudaSuccess)
+          continue;
+        const std::string name = plan->trace_marks[i].first;
+        if (name == "apply:begin")
+          continue; // gap between two applies belongs to the caller's phases
+        auto it = std::find_if(acc.begin(), acc.end(), [&](auto &kv) { return kv.first == name; });
+        if (it == acc.end())
+          acc.push_back({name, {ms, 1}});
+        else
+          it->second.first += ms, it->second.second++;
+      }
+    std::string out = "{";
+    for (size_t i = 0; i < acc.size(); ++i)
+      {
+        char tmp[160];
+        snprintf(tmp, sizeof(tmp), "%s\"%s\": {\"ms\": %.6f, \"n\": %llu}", i ? ", " : "", acc[i].first.c_str(), acc[i].second.first,
+                 (unsigned long long)acc[i].second.second);
+        out += tmp;
+      }
+    out += "}";
+    snprintf(buf, buf_bytes, "%s", out.c_str());
+    for (auto &m : plan->trace_marks)
+      plan->trace_pool.push_back(m.second);
+    plan->trace_marks.clear();
+    return HX_OK;
   }
 
   int

@@ -65,6 +65,7 @@ namespace hx
     const double *  f_xprev;
     double *        f_out;
     double          f_a, f_b, f_c;
+    uint32_t        f_discard; // Y tiles are whole 128-B lines (B % 16 == 0, aligned): dead partial sums are discarded
   };
 
   __device__ __forceinline__ void
@@ -528,6 +529,40 @@ namespace hx
                         ph ^= 1u;
                       }
                   }
+                // Chebyshev epilogue, part 1: z = b*X[row] + c*Xprev[row] for the rows this thread finishes.  It does not
+                // depend on the predecessors, so for the first m-tile it is issued before waiting for them; the other
+                // m-tiles load it together with their Y rows (registers).
+                auto load_z = [&](int j, double2(&z)[NT], double &dv) {
+                  const uint32_t d  = dst_code[j];
+                  const size_t   ro = (size_t)HX_DEST_ROW(d) * B;
+                  dv                = __ldg(a.f_dinv + HX_DEST_ROW(d));
+                  double2 xc[NT], xp[NT];
+#pragma unroll
+                  for (int t = 0; t < NT; ++t)
+                    {
+                      const uint32_t col = b0 + t * 8 + (lane & 3) * 2;
+                      xc[t] = xp[t] = make_double2(0.0, 0.0);
+                      if (col < B)
+                        {
+                          xc[t] = __ldcg(reinterpret_cast<const double2 *>(a.X + ro + col));
+                          if (a.f_c != 0.0)
+                            xp[t] = __ldcg(reinterpret_cast<const double2 *>(a.f_xprev + ro + col));
+                        }
+                    }
+#pragma unroll
+                  for (int t = 0; t < NT; ++t)
+                    {
+                      z[t].x = cheb_z(a.f_b, xc[t].x, a.f_c, xp[t].x);
+                      z[t].y = cheb_z(a.f_b, xc[t].y, a.f_c, xp[t].y);
+                    }
+                };
+                auto is_lastf = [&](int j) {
+                  return dst_code[j] != 0xffffffffu && (dst_code[j] & (HX_DEST_LASTF | HX_DEST_STAGED)) == HX_DEST_LASTF;
+                };
+                double2 z0[NT];
+                double  dv0 = 0.0;
+                if (FUSE && active && is_lastf(0))
+                  load_z(0, z0, dv0);
                 if (mc == 0) // the preceding toucher of every row of this cell has scattered (sync warp)
                   mbar_wait(sbase + SM_PRED + 8 * (it & 1u), (it >> 1) & 1u);
                 // ---- scatter-add (ordered: plain RMW through L2; shared rows: staging slot) ----
@@ -555,25 +590,35 @@ namespace hx
                                   }
                                 if (FUSE && !staged && (d & HX_DEST_LASTF))
                                   {
-                                    // final value of (H X)[row, tile] is in registers: apply the recurrence here
+                                    // part 2: the final (H X)[row, tile] is in registers: out = a*dinv*(H X) + z
                                     const size_t ro = (size_t)HX_DEST_ROW(d) * B;
-                                    const double dv = __ldg(a.f_dinv + HX_DEST_ROW(d));
+                                    double2      z[NT];
+                                    double       dv;
+                                    if (j == 0)
+                                      {
+                                        dv = dv0;
+#pragma unroll
+                                        for (int t = 0; t < NT; ++t)
+                                          z[t] = z0[t];
+                                      }
+                                    else
+                                      load_z(j, z, dv);
 #pragma unroll
                                     for (int t = 0; t < NT; ++t)
                                       {
                                         const uint32_t col = b0 + t * 8 + (lane & 3) * 2;
                                         if (col < B)
                                           {
-                                            const double2 xc = __ldcg(reinterpret_cast<const double2 *>(a.X + ro + col));
-                                            double2       xp = make_double2(0.0, 0.0);
-                                            if (a.f_c != 0.0)
-                                              xp = __ldcg(reinterpret_cast<const double2 *>(a.f_xprev + ro + col));
                                             double2 o;
-                                            o.x = cheb_combine(a.f_a, __dmul_rn(dv, y[t].x + acc[j][t][0]), a.f_b, xc.x, a.f_c, xp.x);
-                                            o.y = cheb_combine(a.f_a, __dmul_rn(dv, y[t].y + acc[j][t][1]), a.f_b, xc.y, a.f_c, xp.y);
+                                            o.x = __fma_rn(a.f_a, __dmul_rn(dv, y[t].x + acc[j][t][0]), z[t].x);
+                                            o.y = __fma_rn(a.f_a, __dmul_rn(dv, y[t].y + acc[j][t][1]), z[t].y);
                                             __stcg(reinterpret_cast<double2 *>(a.f_out + ro + col), o);
                                           }
                                       }
+                                    // the partial sums of this row are dead now: drop their (dirty) L2 lines instead of
+                                    // letting them be written back to HBM.  Only when the tile covers whole 128-B lines.
+                                    if (add && a.f_discard && (lane & 3) * 16 < BT)
+                                      asm volatile("discard.global.L2 [%0], 128;" ::"l"(dst + b0 + (lane & 3) * 16) : "memory");
                                   }
                                 else
                                   {
@@ -1078,6 +1123,7 @@ namespace hx
           {
             a.f_dinv = fuse->dinv, a.f_xprev = fuse->xprev ? fuse->xprev : fuse->out, a.f_out = fuse->out;
             a.f_a = fuse->a, a.f_b = fuse->b, a.f_c = fuse->c;
+            a.f_discard = (B % (uint32_t)(nt * 8) == 0 && nt >= 2 && (((uintptr_t)Y) & 127) == 0 && !getenv("HXB200_NO_DISCARD")) ? 1u : 0u;
             if (fused_applied)
               *fused_applied = true;
           }
@@ -1151,17 +1197,46 @@ namespace hx
     const int      n = (int)cm.n, np = (int)cm.nproj;
     const int      lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t col  = b0 + lane;
-    for (int k = warp; k < n; k += 8)
-      xs[k * 32 + lane] = (col < B) ? X[(size_t)ids[cm.ids_off + k] * B + col] : 0.0;
-    __syncthreads();
-    const double *Cc = cellC + c_off[cell];
-    for (int pj = warp; pj < np; pj += 8)
+    // gather: 4 rows per warp in flight (row id -> row is a dependent pair of loads)
+    for (int k0 = warp; k0 < n; k0 += 32)
       {
-        double s = 0.0;
-        for (int k = 0; k < n; ++k)
-          s += Cc[(size_t)pj + (size_t)k * np] * xs[k * 32 + lane];
-        if (col < B)
-          cx_stage[(size_t)(cm.proj_off + pj) * B + col] = s;
+        uint32_t r[4];
+        double   v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          r[u] = (k0 + 8 * u < n) ? __ldg(ids + cm.ids_off + k0 + 8 * u) : 0u;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          v[u] = (k0 + 8 * u < n && col < B) ? __ldg(X + (size_t)r[u] * B + col) : 0.0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (k0 + 8 * u < n)
+            xs[(k0 + 8 * u) * 32 + lane] = v[u];
+      }
+    __syncthreads();
+    // C_c (np x n, projector index fastest) is staged through shared memory 8 projectors at a time, so the dot
+    // products read it as broadcasts instead of a chain of dependent global loads
+    const double *Cc = cellC + c_off[cell];
+    double *      cs = xs + (size_t)n * 32; // [8][n]
+    for (int p0 = 0; p0 < np; p0 += 8)
+      {
+        const int pc = min(8, np - p0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < pc * n; i += blockDim.x)
+          {
+            const int k = i / pc, q = i % pc;
+            cs[q * n + k] = __ldg(Cc + (size_t)(p0 + q) + (size_t)k * np);
+          }
+        __syncthreads();
+        if (warp < pc)
+          {
+            const double *cr = cs + warp * n;
+            double        s  = 0.0;
+            for (int k = 0; k < n; ++k)
+              s += cr[k] * xs[k * 32 + lane];
+            if (col < B)
+              cx_stage[(size_t)(cm.proj_off + p0 + warp) * B + col] = s;
+          }
       }
   }
 
@@ -1189,7 +1264,7 @@ namespace hx
     const uint32_t ncell = (uint32_t)op->h_nl_cells.size();
     if (ncell)
       {
-        const size_t smem = (size_t)p->max_n * 32 * sizeof(double);
+        const size_t smem = (size_t)p->max_n * (32 + 8) * sizeof(double);
         HX_CUDA(cudaFuncSetAttribute(nl_phase_a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         dim3 grid(ncell, (B + 31) / 32);
         nl_phase_a_kernel<<<grid, 256, smem, p->stream>>>(X, p->d_ids.p, op->d_nl_cells.p, op->d_meta.p,

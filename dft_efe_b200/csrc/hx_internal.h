@@ -167,15 +167,19 @@ namespace hx
   };
 
 #ifdef __CUDACC__
-  // one definition of the update so the fused epilogue and the row-list kernel agree bit for bit
-  // (ChebyshevFilter.t.cpp:105-124: temp = a*t + b*xcur; new = 1*temp + c*xprev)
+  // one definition of the update so the fused epilogue and the row-list kernel agree bit for bit:
+  //   z = b*xcur + c*xprev (available before H X is final), out = a*t + z
+  // (ChebyshevFilter.t.cpp:105-124 computes (a*t + b*xcur) + c*xprev: same terms, association differs in the last ulp)
+  __device__ __forceinline__ double
+  cheb_z(double b, double xc, double c, double xp)
+  {
+    const double z = __dmul_rn(b, xc);
+    return (c != 0.0) ? __fma_rn(c, xp, z) : z;
+  }
   __device__ __forceinline__ double
   cheb_combine(double a, double t, double b, double xc, double c, double xp)
   {
-    double o = __fma_rn(a, t, __dmul_rn(b, xc));
-    if (c != 0.0)
-      o = __fma_rn(c, xp, o);
-    return o;
+    return __fma_rn(a, t, cheb_z(b, xc, c, xp));
   }
 #endif
 } // namespace hx
@@ -248,6 +252,13 @@ struct hx_plan
   hx::DevBuf<double>                d_small; // small device scratch (norms, gram blocks, per-column scalars)
   double *                          h_pinned = nullptr;
   size_t                            h_pinned_bytes = 0;
+
+  // phase trace (HXB200_TRACE=1 or hx_plan_trace): CUDA events at the phase boundaries of an apply / filter degree
+  bool                                     trace = false;
+  std::vector<std::pair<const char *, cudaEvent_t>> trace_marks;
+  std::vector<cudaEvent_t>                 trace_pool;
+  void
+  mark(const char *name); // no-op unless tracing
 
   uint64_t    launches = 0;
   bool        timing   = false;

@@ -210,6 +210,11 @@ int hx_axpby_blocked(hx_plan *plan, uint32_t n_rows, uint32_t B, double alpha1, 
 int hx_plan_launch_count(hx_plan *plan, uint64_t *n);
 int hx_plan_cell_kernel_time_ms(hx_plan *plan, double *ms, uint64_t *launches);
 int hx_plan_enable_kernel_timing(hx_plan *plan, int on);
+/* Phase trace: CUDA events at the phase boundaries of every apply / filter degree issued while tracing is on;
+ * the report is a JSON object {"phase": {"ms": total, "n": count}, ...} (phases: x-halo, p2c+zero, nl-phase-a,
+ * nl-halo, cell-kernel, shared+c2p, y-halo, cheb-rest) and clears the trace. */
+int hx_plan_trace(hx_plan *plan, int on);
+int hx_plan_trace_report(hx_plan *plan, char *buf, size_t buf_bytes);
 /* FP64 DMMA / DFMA / copy microbenchmarks used for the roofline denominators. */
 int hx_microbench(double *dmma_tflops, double *dfma_tflops, double *copy_gbs);
 
