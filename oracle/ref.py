@@ -74,3 +74,44 @@ def cell_gemm_batched(xcell, h_cell, ncd, B):
                                        C.c_double(1.0), f64(xcell), p(m), f64(h_cell), p(n), C.c_double(0.0),
                                        f64(y), p(m))
     return y
+
+
+def gather(X, prob):
+    """FECellWiseDataOperations::copyFieldToCellWiseData (basis/FECellWiseDataOperations.t.cpp:58-86), reference body."""
+    B = X.shape[1]
+    ids, ip = u32(prob.cell_local_ids); ncd, np_ = u32(prob.num_cell_dofs)
+    out = np.zeros((int(ncd.sum(dtype=np.int64)), B))
+    lib().ref_gather(f64(X), C.c_uint32(B), ip, np_, C.c_uint32(len(ncd)), f64(out))
+    return out
+
+
+def scatter_add(ycell, prob, Y):
+    """FECellWiseDataOperations::addCellWiseDataToFieldData (:87-153), reference body; adds into Y in place."""
+    B = Y.shape[1]
+    ids, ip = u32(prob.cell_local_ids); ncd, np_ = u32(prob.num_cell_dofs)
+    lib().ref_scatter_add(f64(ycell), C.c_uint32(B), ip, np_, C.c_uint32(len(ncd)), f64(Y))
+
+
+def hx_apply_serial(prob, X, cell_block=3, use_nonlocal=True):
+    """KohnShamOperatorContextFE::apply on one rank assembled from reference-compiled routines only
+    (ref_shim_cellwise.cpp: ref_hx_apply_serial).  X is modified in place like the reference; returns Y."""
+    assert prob.nranks == 1
+    B = X.shape[1]
+    Y = np.zeros_like(X)
+    ids, ip = u32(prob.cell_local_ids); ncd, ncdp = u32(prob.num_cell_dofs)
+    r, rp = u32(prob.row_ids); s, sp = u32(prob.row_sizes); o, op = u32(prob.row_offsets); c, cp = u32(prob.col_ids)
+    v = np.ascontiguousarray(prob.col_vals); ih = np.ascontiguousarray(prob.inhom)
+    h = np.ascontiguousarray(prob.h_cell)
+    nl = use_nonlocal and prob.num_cell_proj is not None
+    if nl:
+        ncp, ncpp = u32(prob.num_cell_proj); pids, pp = u32(prob.cell_proj_local_ids)
+        cc = np.ascontiguousarray(prob.cell_c); V = np.ascontiguousarray(prob.proj_v)
+        nproj = prob.proj_halo.n_local
+        lib().ref_hx_apply_serial(f64(X), f64(Y), C.c_uint32(X.shape[0]), C.c_uint32(B), C.c_uint32(len(ncd)), ncdp, ip,
+                                  f64(h), C.c_uint32(len(r)), rp, sp, op, cp, C.c_uint32(len(c)), f64(v), f64(ih),
+                                  ncpp, pp, f64(cc), f64(V), C.c_uint32(nproj), C.c_uint32(cell_block))
+    else:
+        lib().ref_hx_apply_serial(f64(X), f64(Y), C.c_uint32(X.shape[0]), C.c_uint32(B), C.c_uint32(len(ncd)), ncdp, ip,
+                                  f64(h), C.c_uint32(len(r)), rp, sp, op, cp, C.c_uint32(len(c)), f64(v), f64(ih),
+                                  None, None, None, None, C.c_uint32(0), C.c_uint32(cell_block))
+    return Y

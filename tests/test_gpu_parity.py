@@ -292,6 +292,21 @@ def test_diag_ops(capi, prob_full, variant):
     assert rel_l2_per_vector(dY.download(), Yo) < 1e-14
 
 
+def test_hx_against_reference_golden_fixture(capi):
+    """tests/golden/ref_hx_small.npz = KohnShamOperatorContextFE::apply assembled from the reference's own compiled
+    routines (tests/golden/make_golden.py): the CUDA path must match it within the H.X tolerance."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_hx_small.npz"))
+    p = synth.build_problem(spec_full(p=int(g["p"]), nc=tuple(int(v) for v in g["nc"])))[0]
+    B = int(g["B"])
+    plan = capi.Plan(p, max_block=B)
+    op = capi.CellOp(plan)
+    dX, dY = plan.block(B, np.ascontiguousarray(g["X"])), plan.block(B)
+    op.apply(dX, dY, True, False)
+    assert rel_l2_per_vector(dY.download(), g["Y"]) < RTOL_HX
+    assert rel_l2_per_vector(dX.download(), g["X_after"]) < 1e-14
+
+
 def test_hx_enrichment_rows_shared_by_every_cell(capi):
     """an enrichment function whose cutoff covers the whole mesh: its row is touched by all 216 cells and goes
     through the two-stage fixed-order reduction of the staging slots."""

@@ -126,6 +126,54 @@ def test_cell_gemm_matches_reference_sources(ref_lib, probs):
     assert np.abs(Y1 - Y2).max() <= 1e-13 * np.abs(Y2).max()
 
 
+def test_gather_scatter_match_reference_sources(ref_lib, probs):
+    """FECellWiseDataOperations::copyFieldToCellWiseData / addCellWiseDataToFieldData: the reference's own bodies
+    (compiled with a one-typedef stand-in for the deal.II-dependent BasisManager.h) vs the oracle, bit for bit."""
+    p = probs[1][0]
+    for B in (1, 4):
+        R = orc.OracleRank(p)
+        X = synth.make_block(p, B)
+        R.loop_a(X, None, use_nonlocal=False)
+        assert np.array_equal(R.xcell(B), ref_lib.gather(X, p))
+        yc = np.random.default_rng(3).standard_normal(R.xcell(B).shape)
+        Y1, Y2 = X.copy(), X.copy()
+        orc.lib().orc_scatter_add(orc._f64(yc), C.c_uint32(B), R.ids_p, R.ncd_p, C.c_uint32(R.C), orc._f64(Y1))
+        ref_lib.scatter_add(yc, p, Y2)
+        assert np.array_equal(Y1, Y2)
+
+
+@pytest.mark.parametrize("use_nonlocal", [False, True])
+@pytest.mark.parametrize("cell_block", [1, 3, 1000])
+def test_hx_composite_matches_reference_assembled_apply(ref_lib, probs, cell_block, use_nonlocal):
+    """The H.X composite of the oracle against KohnShamOperatorContextFE::apply assembled from the reference's own
+    compiled routines (gather, gemmStridedVarBatched, projector GEMMs, scaleStridedVarBatched, scatter-add,
+    constraint distribute), where only the call sequence and the cell-block loop are restated
+    (oracle/ref_shim_cellwise.cpp).  Hanging nodes, Dirichlet rows, enrichment and projectors are all present."""
+    p = probs[1][0]
+    B = 5
+    X = synth.make_block(p, B)
+    Xo, Yo = X.copy(), np.zeros_like(X)
+    orc.OracleWorld([p]).hx_apply([Xo], [Yo], True, False, use_nonlocal=use_nonlocal)
+    Xr = X.copy()
+    Yr = ref_lib.hx_apply_serial(p, Xr, cell_block=cell_block, use_nonlocal=use_nonlocal)
+    assert np.array_equal(Xo, Xr)                       # X modified in place identically (hanging-node fill)
+    err = np.linalg.norm(Yo - Yr, axis=0) / np.linalg.norm(Yr, axis=0)
+    assert err.max() < 1e-14, err                       # same operations; dgemm summation order may differ
+
+
+def test_hx_golden_fixture_from_reference_assembled_apply(probs):
+    """tests/golden/ref_hx_small.npz was produced by tests/golden/make_golden.py with the reference-assembled
+    apply; the oracle must reproduce it (this pin travels to machines without /root/reference)."""
+    g = np.load(os.path.join(HERE, "golden", "ref_hx_small.npz"))
+    p = synth.build_problem(small_spec(1, p=int(g["p"]), nc=tuple(int(v) for v in g["nc"])))[0]
+    X = synth.make_block(p, int(g["B"]))
+    assert np.array_equal(X, g["X"])
+    Yo = np.zeros_like(X)
+    orc.OracleWorld([p]).hx_apply([X.copy()], [Yo], True, False)
+    err = np.linalg.norm(Yo - g["Y"], axis=0) / np.linalg.norm(g["Y"], axis=0)
+    assert err.max() < 1e-14, err
+
+
 def test_blas1_match_reference_sources(ref_lib):
     rng = np.random.default_rng(2)
     n, B = 40, 7
