@@ -29,7 +29,7 @@ def _torchrun(script, nproc, timeout=600, env=None):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("transport", ["nvlink-peer", "nccl"])
-@pytest.mark.parametrize("nproc", [2, 4])
+@pytest.mark.parametrize("nproc", [2, 4, 8])
 def test_multi_gpu_parity(nproc, transport):
     """both halo transports: the fused pack->peer-store / wait->unpack kernels over NVLink peer memory (default) and
     the NCCL send/recv fallback (HXB200_HALO=nccl)"""
