@@ -22,7 +22,8 @@ EXPORTS = [
     "hx_plan_create", "hx_plan_destroy", "hx_plan_synchronize", "hx_comm_unique_id", "hx_plan_attach_comm", "hx_plan_halo_transport",
     "hx_plan_set_scatter_mode", "hx_plan_get_wait_lists", "hx_plan_get_processing_order", "hx_plan_num_colours", "hx_plan_get_cell_colours", "hx_plan_get_c2p_transpose", "hx_plan_get_fusable_rows", "hx_update_ghost_values",
     "hx_accumulate_add_locally_owned", "hx_distribute_parent_to_child", "hx_distribute_child_to_parent",
-    "hx_set_constrained_nodes_to_zero", "hx_cellop_create", "hx_cellop_set_matrices", "hx_cellop_set_nonlocal",
+    "hx_set_constrained_nodes_to_zero", "hx_plan_add_constraints", "hx_distribute_parent_to_child_set",
+    "hx_distribute_child_to_parent_set", "hx_cellop_set_constraint_sets", "hx_cg_solve", "hx_cellop_create", "hx_cellop_set_matrices", "hx_cellop_set_nonlocal",
     "hx_diagop_create", "hx_op_destroy", "hx_op_apply", "hx_op_apply_host", "hx_chebyshev_filter", "hx_chebyshev_filter_host",
     "hx_residual_chebyshev_filter", "hx_xtopx", "hx_subspace_rotation", "hx_l2_norms", "hx_axpby",
     "hx_axpby_blocked", "hx_plan_launch_count", "hx_plan_cell_kernel_time_ms", "hx_plan_enable_kernel_timing", "hx_plan_trace", "hx_plan_trace_report",
@@ -244,6 +245,24 @@ class Plan:
     def c2p(self, Y: DeviceBlock):
         check(lib().hx_distribute_child_to_parent(self.h, Y.p, C.c_uint32(Y.B)))
 
+    def add_constraints(self, row_ids, row_sizes, row_offsets, col_ids, col_vals, inhom) -> int:
+        """another ConstraintsLocal on the same DoF numbering; returns its set id (0 is the mesh's own)"""
+        keep = []
+        ptrs = []
+        for a in (row_ids, row_sizes, row_offsets, col_ids):
+            arr, ptr = _u32(a); keep.append(arr); ptrs.append(ptr)
+        cv, cvp = _f64(col_vals); ih, ihp = _f64(inhom)
+        sid = C.c_uint32()
+        check(lib().hx_plan_add_constraints(self.h, C.c_uint32(len(keep[0])), ptrs[0], ptrs[1], ptrs[2], ptrs[3], cvp, ihp,
+                                            C.byref(sid)))
+        return sid.value
+
+    def p2c_set(self, set_id: int, X: DeviceBlock):
+        check(lib().hx_distribute_parent_to_child_set(self.h, C.c_uint32(set_id), X.p, C.c_uint32(X.B)))
+
+    def c2p_set(self, set_id: int, Y: DeviceBlock):
+        check(lib().hx_distribute_child_to_parent_set(self.h, C.c_uint32(set_id), Y.p, C.c_uint32(Y.B)))
+
     def l2_norms(self, X: DeviceBlock) -> np.ndarray:
         out = np.zeros(X.B)
         check(lib().hx_l2_norms(self.h, X.p, C.c_uint32(X.B), out.ctypes.data_as(f64p)))
@@ -338,11 +357,15 @@ class CellOp(Op):
         assert a.size == self.plan.prob.S2
         check(lib().hx_cellop_set_matrices(self.h, p, C.c_int(0)))
 
+    def set_constraint_sets(self, x_set: int, y_set: int):
+        check(lib().hx_cellop_set_constraint_sets(self.h, C.c_uint32(x_set), C.c_uint32(y_set)))
+
     def set_matrices_device(self, dev_ptr):
         check(lib().hx_cellop_set_matrices(self.h, C.cast(dev_ptr, f64p), C.c_int(1)))
 
 
-DIAG_CFE, DIAG_OEFE_ATOMBLOCK, DIAG_OEFE_MASS = 0, 1, 2
+DIAG_CFE, DIAG_OEFE_ATOMBLOCK, DIAG_OEFE_MASS, DIAG_JACOBI = 0, 1, 2, 3
+CG_SUCCESS, CG_FAILED_TO_CONVERGE, CG_RESIDUAL_DIVERGENCE, CG_DIVISION_BY_ZERO, CG_OTHER_ERROR = 0, 1, 2, 3, 4
 
 
 class DiagOp(Op):
@@ -377,6 +400,15 @@ def residual_chebyshev_filter(A: Op, Bop: Op, BInv: Op, eig: np.ndarray, X: Devi
     e, ep = _f64(eig)
     check(lib().hx_residual_chebyshev_filter(A.h, Bop.h, BInv.h, ep, X.p, Y.p, C.c_uint32(X.B), C.c_uint32(degree),
                                              C.c_double(a0), C.c_double(a), C.c_double(b)))
+
+
+def cg_solve(A: Op, PC: Op, b: DeviceBlock, x: DeviceBlock, max_iter, abs_tol, rel_tol, div_tol):
+    """CGLinearSolver::solve; x holds the initial guess and receives xConverged.  Returns (iterations, status, norms)."""
+    it, st = C.c_uint32(), C.c_int()
+    rn = np.zeros(b.B)
+    check(lib().hx_cg_solve(A.h, PC.h, b.p, x.p, C.c_uint32(b.B), C.c_uint32(max_iter), C.c_double(abs_tol),
+                            C.c_double(rel_tol), C.c_double(div_tol), C.byref(it), C.byref(st), rn.ctypes.data_as(f64p)))
+    return it.value, st.value, rn
 
 
 def comm_unique_id() -> bytes:

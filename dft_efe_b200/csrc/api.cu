@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <map>
+#include <memory>
 #include <queue>
 #include <new>
 
@@ -548,7 +549,7 @@ namespace hx
     if (ugx)
       HX_TRY(halo_update(p, p->halo, X, B));
     p->mark("x-halo");
-    HX_TRY(launch_p2c(p, X, B));
+    HX_TRY(launch_p2c(p, X, B, op->x_set));
     if (p->scatter_mode == 1)
       HX_CUDA(cudaMemsetAsync(Y, 0, (size_t)p->n_local * B * sizeof(double), p->stream));
     else // first touchers store instead of add: only rows no cell writes need clearing
@@ -570,7 +571,7 @@ namespace hx
     HX_TRY(launch_cell_apply(op, X, Y, B, fuse, fused_applied));
     p->mark("cell-kernel");
     HX_TRY(launch_shared_reduce(p, Y, B));
-    HX_TRY(launch_c2p(p, Y, B));
+    HX_TRY(launch_c2p(p, Y, B, op->y_set));
     p->mark("shared+c2p");
     HX_TRY(halo_accumulate(p, p->halo, Y, B));
     if (ugy)
@@ -583,13 +584,23 @@ namespace hx
   diagop_apply(hx_op *op, double *X, double *Y, uint32_t B, int ugx, int ugy)
   {
     hx_plan *p = op->plan;
+    if (op->variant == HX_DIAG_JACOBI)
+      {
+        // PreconditionerJacobi::apply (src/linearAlgebra/PreconditionerJacobi.t.cpp:52-82): no constraints involved
+        if (ugx)
+          HX_TRY(halo_update(p, p->halo, X, B));
+        HX_TRY(launch_row_scale(p, op->d_diag.p, X, Y, B, p->n_local));
+        if (ugy)
+          HX_TRY(halo_update(p, p->halo, Y, B));
+        return HX_OK;
+      }
     if (op->variant == HX_DIAG_OEFE_MASS)
       ugx = ugy = 0;
     if (ugx)
       HX_TRY(halo_update(p, p->halo, X, B));
     HX_TRY(launch_p2c(p, X, B));
     HX_TRY(launch_row_scale(p, op->d_diag.p, X, Y, B, p->n_local));
-    if (op->variant != HX_DIAG_CFE)
+    if (op->variant != HX_DIAG_CFE && op->variant != HX_DIAG_JACOBI)
       {
         const size_t o = (size_t)p->n_owned_classical * B;
         HX_TRY(launch_enr_block(p, op->d_enr_block.p, op->nE, X + o, Y + o, B));
@@ -638,8 +649,23 @@ namespace hx
 
 using namespace hx;
 
+hx::ConstraintView
+hx_plan::constraint_view(uint32_t set) const
+{
+  if (set > 0 && set <= extra_constraints.size())
+    return extra_constraints[set - 1]->view();
+  hx::ConstraintView v;
+  v.nR = nR, v.nPar = nPar;
+  v.row_ids = d_row_ids.p, v.row_sizes = d_row_sizes.p, v.row_offsets = d_row_offsets.p, v.col_ids = d_col_ids.p;
+  v.col_vals = d_col_vals.p, v.inhom = d_inhom.p;
+  v.par_ids = d_par_ids.p, v.par_off = d_par_off.p, v.par_child = d_par_child.p, v.par_w = d_par_w.p;
+  return v;
+}
+
 hx_plan::~hx_plan()
 {
+  for (auto *c : extra_constraints)
+    delete c;
   for (auto &m : trace_marks)
     cudaEventDestroy(m.second);
   for (auto e : trace_pool)
@@ -992,6 +1018,74 @@ extern "C"
   }
 
   int
+  hx_plan_add_constraints(hx_plan *plan, uint32_t n_rows, const uint32_t *row_ids, const uint32_t *row_sizes,
+                          const uint32_t *row_offsets, const uint32_t *col_ids, const double *col_vals, const double *inhom,
+                          uint32_t *set_id)
+  {
+    HX_CHECK(plan && set_id, HX_ERR_INVALID, "null argument");
+    HX_CHECK(n_rows == 0 || (row_ids && row_sizes && row_offsets && inhom), HX_ERR_INVALID, "null constraint arrays");
+    std::unique_ptr<ConstraintSet> c(new (std::nothrow) ConstraintSet());
+    HX_CHECK(c, HX_ERR_NOMEM, "out of host memory");
+    c->nR = n_rows;
+    std::vector<char> constrained(plan->n_local, 0);
+    for (uint32_t i = 0; i < n_rows; ++i)
+      {
+        HX_CHECK(row_ids[i] < plan->n_local, HX_ERR_INVALID, "constraint row id out of range");
+        HX_CHECK(!constrained[row_ids[i]], HX_ERR_INVALID, "duplicate constraint row %u", row_ids[i]);
+        constrained[row_ids[i]] = 1;
+        c->nnz                  = std::max(c->nnz, row_offsets[i] + row_sizes[i]);
+      }
+    std::map<uint32_t, std::vector<std::pair<uint32_t, double>>> par;
+    for (uint32_t i = 0; i < n_rows; ++i)
+      for (uint32_t j = 0; j < row_sizes[i]; ++j)
+        {
+          const uint32_t col = col_ids[row_offsets[i] + j];
+          HX_CHECK(col < plan->n_local, HX_ERR_INVALID, "constraint column id out of range");
+          HX_CHECK(!constrained[col], HX_ERR_UNSUPPORTED, "constraint chain: row %u depends on constrained row %u", row_ids[i],
+                   col);
+          par[col].push_back({row_ids[i], col_vals[row_offsets[i] + j]});
+        }
+    std::vector<uint32_t> par_ids, par_off(1, 0), par_child;
+    std::vector<double>   par_w;
+    for (auto &kv : par)
+      {
+        par_ids.push_back(kv.first);
+        for (auto &e : kv.second)
+          {
+            par_child.push_back(e.first);
+            par_w.push_back(e.second);
+          }
+        par_off.push_back((uint32_t)par_child.size());
+      }
+    c->nPar = (uint32_t)par_ids.size();
+    HX_TRY(c->d_row_ids.upload(row_ids, n_rows));
+    HX_TRY(c->d_row_sizes.upload(row_sizes, n_rows));
+    HX_TRY(c->d_row_offsets.upload(row_offsets, n_rows));
+    HX_TRY(c->d_col_ids.upload(col_ids, c->nnz));
+    HX_TRY(c->d_col_vals.upload(col_vals, c->nnz));
+    HX_TRY(c->d_inhom.upload(inhom, n_rows));
+    HX_TRY(c->d_par_ids.upload(par_ids));
+    HX_TRY(c->d_par_off.upload(par_off));
+    HX_TRY(c->d_par_child.upload(par_child));
+    HX_TRY(c->d_par_w.upload(par_w));
+    HX_CUDA(cudaDeviceSynchronize());
+    plan->extra_constraints.push_back(c.release());
+    *set_id = (uint32_t)plan->extra_constraints.size();
+    return HX_OK;
+  }
+
+  int
+  hx_cellop_set_constraint_sets(hx_op *op, uint32_t x_set, uint32_t y_set)
+  {
+    HX_CHECK(op && op->kind == HX_OP_CELL, HX_ERR_INVALID, "bad argument");
+    const uint32_t n = (uint32_t)op->plan->extra_constraints.size();
+    HX_CHECK(x_set <= n && y_set <= n, HX_ERR_INVALID, "unknown constraint set");
+    op->x_set = x_set;
+    op->y_set = y_set;
+    return HX_OK;
+  }
+
+  int
   hx_cellop_set_nonlocal(hx_op *op, const hx_nonlocal_desc *nl)
   {
     HX_CHECK(op && nl && op->kind == HX_OP_CELL, HX_ERR_INVALID, "bad argument");
@@ -1052,7 +1146,7 @@ extern "C"
   hx_diagop_create(hx_plan *plan, const double *diag, const double *enr_block, int variant, hx_op **op)
   {
     HX_CHECK(plan && diag && op, HX_ERR_INVALID, "null argument");
-    HX_CHECK(variant >= HX_DIAG_CFE && variant <= HX_DIAG_OEFE_MASS, HX_ERR_INVALID, "bad variant");
+    HX_CHECK(variant >= HX_DIAG_CFE && variant <= HX_DIAG_JACOBI, HX_ERR_INVALID, "bad variant");
     hx_op *o = new (std::nothrow) hx_op();
     HX_CHECK(o, HX_ERR_NOMEM, "out of host memory");
     o->plan    = plan;
@@ -1060,7 +1154,7 @@ extern "C"
     o->variant = variant;
     o->nE      = plan->n_owned - plan->n_owned_classical;
     int r      = o->d_diag.upload(diag, plan->n_local);
-    if (r == HX_OK && variant != HX_DIAG_CFE && o->nE)
+    if (r == HX_OK && variant != HX_DIAG_CFE && variant != HX_DIAG_JACOBI && o->nE)
       {
         if (!enr_block)
           {
@@ -1142,6 +1236,133 @@ extern "C"
     return HX_OK;
   }
 
+  int
+  hx_distribute_parent_to_child_set(hx_plan *plan, uint32_t set, double *X, uint32_t B)
+  {
+    HX_CHECK_B(plan, B);
+    HX_CHECK(set <= plan->extra_constraints.size(), HX_ERR_INVALID, "unknown constraint set");
+    return launch_p2c(plan, X, B, set);
+  }
+  int
+  hx_distribute_child_to_parent_set(hx_plan *plan, uint32_t set, double *Y, uint32_t B)
+  {
+    HX_CHECK_B(plan, B);
+    HX_CHECK(set <= plan->extra_constraints.size(), HX_ERR_INVALID, "unknown constraint set");
+    return launch_c2p(plan, Y, B, set);
+  }
+
+  // ------------------------------------------------------------------------------ CG solver ----
+  // CGLinearSolver::solve (src/linearAlgebra/CGLinearSolver.t.cpp:68-300), scalar for scalar: per-column step
+  // lengths, the residual is b - A x, convergence per column against max(absTol, |b| relTol) with the converged
+  // column frozen in xConverged, divergence when a residual norm exceeds divTol.
+  int
+  hx_cg_solve(hx_op *A, hx_op *PC, const double *b, double *x, uint32_t B, uint32_t max_iter, double abs_tol,
+              double rel_tol, double div_tol, uint32_t *iterations, int *status, double *residual_norms_host)
+  {
+    HX_CHECK(A && PC && b && x && iterations && status, HX_ERR_INVALID, "null argument");
+    hx_plan *p = A->plan;
+    HX_CHECK(p == PC->plan, HX_ERR_INVALID, "operators belong to different plans");
+    HX_CHECK_B(p, B);
+    HX_CHECK(B <= 256, HX_ERR_UNSUPPORTED, "hx_cg_solve supports B <= 256 right-hand sides per call");
+    const size_t nloc = (size_t)p->n_local * B;
+    double *     r, *w, *z, *pd, *xconv;
+    HX_TRY(p->get_scratch(0, &r));
+    HX_TRY(p->get_scratch(1, &w));
+    HX_TRY(p->get_scratch(2, &z));
+    HX_TRY(p->get_scratch(3, &pd));
+    HX_TRY(p->get_scratch(6, &xconv));
+    HX_TRY(p->ensure_small((size_t)604 * B + 8 * (size_t)B));
+    double *d_dots = p->d_small.p + (size_t)600 * B; // [3][B] reduction outputs
+    double *d_coef = d_dots + 3 * (size_t)B;         // [4][B]: ones | coefficient a | coefficient b | spare
+    HX_TRY(p->ensure_pinned(8 * (size_t)B * sizeof(double)));
+    double *            h = p->h_pinned;
+    std::vector<double> ones(B, 1.0), coef(B), bnorm(B), rnorm(B), zdotr(B), pdotw(B), zdotr_new(B);
+    std::vector<char>   converged(B, 0);
+    auto reduce = [&](const double *u, const double *v, double *out_host) -> int {
+      HX_TRY(launch_coldot(p, u, v, B, p->n_owned, d_dots));
+      if (p->nranks > 1)
+        HX_TRY(comm_allreduce_sum(p->comm, p->stream, d_dots, B));
+      HX_CUDA(cudaMemcpyAsync(h, d_dots, B * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+      HX_CUDA(cudaStreamSynchronize(p->stream));
+      memcpy(out_host, h, B * sizeof(double));
+      return HX_OK;
+    };
+    // z = 1*u + c[j]*v per column (linearAlgebra::add, MultiVector.t.cpp), over the owned rows
+    auto add = [&](const double *u, const std::vector<double> &c, const double *v, double *out) -> int {
+      HX_CUDA(cudaMemcpyAsync(d_coef, ones.data(), B * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+      HX_CUDA(cudaMemcpyAsync(d_coef + B, c.data(), B * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+      HX_TRY(launch_axpby_blocked(p, p->n_owned, B, 1.0, d_coef, u, 1.0, d_coef + B, v, out));
+      HX_CUDA(cudaStreamSynchronize(p->stream)); // c is a caller-owned host vector
+      return HX_OK;
+    };
+    HX_TRY(reduce(b, b, bnorm.data()));
+    for (uint32_t j = 0; j < B; ++j)
+      bnorm[j] = sqrt(bnorm[j]);
+    HX_CUDA(cudaMemcpyAsync(xconv, x, nloc * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
+    int      err  = HX_CG_OTHER_ERROR; // until a column converges
+    bool     diverged = false, all_conv = false;
+    uint32_t iter = 0;
+    for (; iter <= max_iter; ++iter)
+      {
+        if (iter == 0)
+          {
+            HX_TRY(op_apply(A, x, w, B, 1, 1));
+            std::vector<double> neg(B, -1.0);
+            HX_TRY(add(b, neg, w, r)); // r = b - A x
+            HX_TRY(op_apply(PC, r, z, B, 0, 0));
+            HX_CUDA(cudaMemcpyAsync(pd, z, nloc * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
+          }
+        else
+          {
+            HX_TRY(op_apply(A, pd, w, B, 1, 1));
+            HX_TRY(reduce(z, r, zdotr.data()));
+            HX_TRY(reduce(pd, w, pdotw.data()));
+            for (uint32_t j = 0; j < B; ++j)
+              coef[j] = zdotr[j] / pdotw[j];
+            HX_TRY(add(x, coef, pd, x)); // x += alpha p
+            for (uint32_t j = 0; j < B; ++j)
+              coef[j] = -zdotr[j] / pdotw[j];
+            HX_TRY(add(r, coef, w, r)); // r -= alpha w
+            HX_TRY(op_apply(PC, r, z, B, 0, 0));
+            HX_TRY(reduce(z, r, zdotr_new.data()));
+            for (uint32_t j = 0; j < B; ++j)
+              coef[j] = zdotr_new[j] / zdotr[j];
+            HX_TRY(add(z, coef, pd, pd)); // p = z + beta p
+          }
+        HX_TRY(reduce(r, r, rnorm.data()));
+        for (uint32_t j = 0; j < B; ++j)
+          {
+            rnorm[j] = sqrt(rnorm[j]);
+            if (rnorm[j] < std::max(abs_tol, bnorm[j] * rel_tol) && !converged[j])
+              {
+                err          = HX_CG_SUCCESS;
+                converged[j] = 1;
+                HX_TRY(copy_cols(p, x, B, j, xconv, B, j, 1, p->n_owned));
+              }
+            if (rnorm[j] > div_tol && !diverged)
+              {
+                err      = HX_CG_RESIDUAL_DIVERGENCE;
+                diverged = true;
+              }
+          }
+        all_conv = true;
+        for (uint32_t j = 0; j < B; ++j)
+          all_conv = all_conv && converged[j];
+        if (diverged || all_conv)
+          break;
+      }
+    // linearSolverFunction.setSolution(xConverged)
+    HX_CUDA(cudaMemcpyAsync(x, xconv, nloc * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
+    HX_CUDA(cudaStreamSynchronize(p->stream));
+    if (iter > max_iter)
+      err = HX_CG_FAILED_TO_CONVERGE;
+    *iterations = iter;
+    *status     = err;
+    if (residual_norms_host)
+      memcpy(residual_norms_host, rnorm.data(), B * sizeof(double));
+    return HX_OK;
+  }
+
   // ------------------------------------------------------------------------------- filters ----
   int
   hx_chebyshev_filter(hx_op *A, hx_op *BInv, double *X, double *Y, uint32_t B, uint32_t degree, double a0, double a,
@@ -1182,7 +1403,8 @@ extern "C"
     // one degree of the mass-lumped path: s1 = A xc (updateGhostX), then out = ca*M^-1 s1 + cb*xc + cc*xp.  The
     // update of most rows happens inside the cell kernel's scatter (FuseArgs); the remaining owned rows (and all
     // rows, when the launched kernel variant cannot fuse) go through cheb_fused_kernel.
-    const bool epilogue = fused && A->kind == HX_OP_CELL && p->scatter_mode == 0 && !getenv("HXB200_NO_EPILOGUE_FUSION");
+    const bool epilogue = fused && A->kind == HX_OP_CELL && p->scatter_mode == 0 && A->x_set == 0 && A->y_set == 0 &&
+                          !getenv("HXB200_NO_EPILOGUE_FUSION");
     auto       degree_fused = [&](double *xc, const double *xp, double *out, double ca, double cb, double cc) -> int {
       bool applied = false;
       if (epilogue)

@@ -145,6 +145,35 @@ namespace hx
   };
 
   struct Comm; // NCCL communicator wrapper (comm.cu)
+
+  // one ConstraintsLocal object on the device: the reference CSR + the parent-side transpose used by the
+  // deterministic child->parent pass.  Set 0 lives in the plan's own fields (the mesh's constraints); further sets
+  // (e.g. the inhomogeneous-Dirichlet constraints of the Poisson problem's X basis manager) are added with
+  // hx_plan_add_constraints.
+  struct ConstraintView
+  {
+    uint32_t        nR = 0, nPar = 0;
+    const uint32_t *row_ids = nullptr, *row_sizes = nullptr, *row_offsets = nullptr, *col_ids = nullptr;
+    const double *  col_vals = nullptr, *inhom = nullptr;
+    const uint32_t *par_ids = nullptr, *par_off = nullptr, *par_child = nullptr;
+    const double *  par_w = nullptr;
+  };
+  struct ConstraintSet
+  {
+    uint32_t         nR = 0, nnz = 0, nPar = 0;
+    DevBuf<uint32_t> d_row_ids, d_row_sizes, d_row_offsets, d_col_ids, d_par_ids, d_par_off, d_par_child;
+    DevBuf<double>   d_col_vals, d_inhom, d_par_w;
+    ConstraintView
+    view() const
+    {
+      ConstraintView v;
+      v.nR = nR, v.nPar = nPar;
+      v.row_ids = d_row_ids.p, v.row_sizes = d_row_sizes.p, v.row_offsets = d_row_offsets.p, v.col_ids = d_col_ids.p;
+      v.col_vals = d_col_vals.p, v.inhom = d_inhom.p;
+      v.par_ids = d_par_ids.p, v.par_off = d_par_off.p, v.par_child = d_par_child.p, v.par_w = d_par_w.p;
+      return v;
+    }
+  };
 } // namespace hx
 
 #define HX_DEST_STAGED 0x80000000u
@@ -242,6 +271,10 @@ struct hx_plan
   bool                  cheb_fusable_agreed    = false; // ... on every rank (AND-ed across the communicator once)
   int                   sm_count = 0;
 
+  std::vector<hx::ConstraintSet *> extra_constraints; // sets 1.. (set 0 = the fields above)
+  hx::ConstraintView
+  constraint_view(uint32_t set) const;
+
   hx::Halo  halo;
   hx::Comm *comm = nullptr;
   int       halo_transport = 0;          // 0 = undecided / single rank, 1 = NCCL send/recv, 2 = NVLink peer memory
@@ -306,6 +339,7 @@ struct hx_op
   std::vector<size_t>       h_c_off;                   // per cell offset into cell_c
   hx::DevBuf<unsigned long long> d_c_off;
   hx::DevBuf<uint32_t>      d_pr_off, d_pr_slots;      // projector row -> staging slots (ordered)
+  uint32_t                  x_set = 0, y_set = 0; // constraint sets applied to X (parent->child) and Y (child->parent)
   // --- diagonal operator ---
   int                variant = 0;
   hx::DevBuf<double> d_diag, d_enr_block;
@@ -315,9 +349,10 @@ struct hx_op
 namespace hx
 {
   // kernels.cu / cell_kernel.cu entry points (host launchers)
-  int launch_p2c(hx_plan *p, double *X, uint32_t B);
-  int launch_c2p(hx_plan *p, double *Y, uint32_t B);
-  int launch_zero_constrained(hx_plan *p, double *Y, uint32_t B);
+  int launch_p2c(hx_plan *p, double *X, uint32_t B, uint32_t set = 0);
+  int launch_c2p(hx_plan *p, double *Y, uint32_t B, uint32_t set = 0);
+  int launch_coldot(hx_plan *p, const double *x, const double *y, uint32_t B, size_t nrows, double *out_dev);
+  int launch_zero_constrained(hx_plan *p, double *Y, uint32_t B, uint32_t set = 0);
   int launch_pack(hx_plan *p, const double *x, uint32_t B, const uint32_t *ids, uint32_t n, double *buf);
   int launch_unpack(hx_plan *p, const double *buf, uint32_t B, const uint32_t *ids, uint32_t n, double *x);
   int launch_add_rows(hx_plan *p, const double *buf, uint32_t B, const uint32_t *rows, const uint32_t *off,

@@ -58,24 +58,25 @@ namespace hx
   }
 
   int
-  launch_p2c(hx_plan *p, double *X, uint32_t B)
+  launch_p2c(hx_plan *p, double *X, uint32_t B, uint32_t set)
   {
-    if (p->nR == 0)
+    const ConstraintView c = p->constraint_view(set);
+    if (c.nR == 0)
       return HX_OK;
-    p2c_kernel<<<nblk((size_t)p->nR * B), 256, 0, p->stream>>>(X, B, p->nR, p->d_row_ids.p, p->d_row_sizes.p,
-                                                               p->d_row_offsets.p, p->d_col_ids.p, p->d_col_vals.p,
-                                                               p->d_inhom.p);
+    p2c_kernel<<<nblk((size_t)c.nR * B), 256, 0, p->stream>>>(X, B, c.nR, c.row_ids, c.row_sizes, c.row_offsets, c.col_ids,
+                                                              c.col_vals, c.inhom);
     p->launches++;
     HX_CUDA(cudaGetLastError());
     return HX_OK;
   }
 
   int
-  launch_zero_constrained(hx_plan *p, double *Y, uint32_t B)
+  launch_zero_constrained(hx_plan *p, double *Y, uint32_t B, uint32_t set)
   {
-    if (p->nR == 0)
+    const ConstraintView c = p->constraint_view(set);
+    if (c.nR == 0)
       return HX_OK;
-    zero_rows_kernel<<<nblk((size_t)p->nR * B), 256, 0, p->stream>>>(Y, B, p->nR, p->d_row_ids.p);
+    zero_rows_kernel<<<nblk((size_t)c.nR * B), 256, 0, p->stream>>>(Y, B, c.nR, c.row_ids);
     p->launches++;
     HX_CUDA(cudaGetLastError());
     return HX_OK;
@@ -93,18 +94,18 @@ namespace hx
   }
 
   int
-  launch_c2p(hx_plan *p, double *Y, uint32_t B)
+  launch_c2p(hx_plan *p, double *Y, uint32_t B, uint32_t set)
   {
-    if (p->nR == 0)
+    const ConstraintView c = p->constraint_view(set);
+    if (c.nR == 0)
       return HX_OK;
-    if (p->nPar)
+    if (c.nPar)
       {
-        c2p_kernel<<<nblk((size_t)p->nPar * B), 256, 0, p->stream>>>(Y, B, p->nPar, p->d_par_ids.p, p->d_par_off.p,
-                                                                     p->d_par_child.p, p->d_par_w.p);
+        c2p_kernel<<<nblk((size_t)c.nPar * B), 256, 0, p->stream>>>(Y, B, c.nPar, c.par_ids, c.par_off, c.par_child, c.par_w);
         p->launches++;
       }
     HX_CUDA(cudaGetLastError());
-    return launch_zero_constrained(p, Y, B);
+    return launch_zero_constrained(p, Y, B, set);
   }
 
   // ---- halo pack / unpack / accumulate (src/utils/DiscontiguousDataOperations.cpp:36-92) ------------
@@ -241,7 +242,7 @@ namespace hx
   // order, a second kernel adds the block partials in block order.
   constexpr int CS_BLOCKS = 592; // 4 x 148 SMs
   __global__ void
-  colsumsq_partial_kernel(const double *x, uint32_t B, size_t nrows, double *partial)
+  colsumsq_partial_kernel(const double *x, const double *y, uint32_t B, size_t nrows, double *partial)
   {
     extern __shared__ double sh[]; // [rowsPerIter][B]
     const uint32_t           rpi   = blockDim.x / B; // rows handled per iteration (>=1 because B <= blockDim)
@@ -253,8 +254,7 @@ namespace hx
     if (rr < rpi)
       for (size_t r = begin + rr; r < end; r += rpi)
         {
-          const double v = x[r * B + c];
-          s += v * v;
+          s += x[r * B + c] * y[r * B + c];
         }
     if (rr < rpi)
       sh[rr * B + c] = s;
@@ -281,11 +281,19 @@ namespace hx
   int
   launch_colsumsq(hx_plan *p, const double *x, uint32_t B, size_t nrows, double *out_dev)
   {
-    HX_CHECK(B <= 256, HX_ERR_UNSUPPORTED, "l2 norms: B > 256 must be called per column batch");
+    return launch_coldot(p, x, x, B, nrows, out_dev);
+  }
+
+  // column dot products over the first nrows rows (MultiVector dot / l2Norms, src/linearAlgebra/MultiVector.t.cpp:
+  // 553-578, 805-870): same deterministic two-stage reduction
+  int
+  launch_coldot(hx_plan *p, const double *x, const double *y, uint32_t B, size_t nrows, double *out_dev)
+  {
+    HX_CHECK(B <= 256, HX_ERR_UNSUPPORTED, "column reductions: B > 256 must be called per column batch");
     HX_TRY(p->ensure_small((size_t)CS_BLOCKS * B + B));
     double *partial = p->d_small.p;
     const unsigned threads = 256;
-    colsumsq_partial_kernel<<<CS_BLOCKS, threads, (threads / B) * B * sizeof(double), p->stream>>>(x, B, nrows, partial);
+    colsumsq_partial_kernel<<<CS_BLOCKS, threads, (threads / B) * B * sizeof(double), p->stream>>>(x, y, B, nrows, partial);
     colsumsq_final_kernel<<<nblk(B), 256, 0, p->stream>>>(partial, B, CS_BLOCKS, out_dev);
     p->launches += 2;
     HX_CUDA(cudaGetLastError());

@@ -165,6 +165,12 @@ class RankProblem:
     diag_inv: np.ndarray                # f64 [n_local]
     enr_block: np.ndarray               # f64 [nE_own^2]  atom-block overlap (col-major, symmetric)
     enr_block_inv: np.ndarray           # f64 [nE_own^2]
+    # electrostatics: grad N_i . grad N_j cell matrices of LaplaceOperatorContextFE (same layout as
+    # h_cell), the assembled diagonal on the local rows (Jacobi preconditioner) and the constraint set of the
+    # "X" basis manager: the mesh's constraints with inhomogeneous Dirichlet values on the boundary rows
+    k_cell: Optional[np.ndarray] = None
+    k_diag: Optional[np.ndarray] = None
+    inhom_dirichlet: Optional[np.ndarray] = None    # f64 [nR]: inhomogeneities of the X constraint set
     # nonlocal projectors
     proj_halo: Optional[HaloPattern] = None
     num_cell_proj: Optional[np.ndarray] = None      # u32 [C]
@@ -547,12 +553,15 @@ def build_problem(spec: MeshSpec, only_rank: Optional[int] = None) -> List[RankP
         d = np.linalg.norm(ccen - atoms[ia][None, :], axis=1)
         vcell += -2.0 / np.sqrt(d * d + 0.5)
 
-    # lumped mass assembled globally (every rank later picks its local rows)
+    # lumped mass (and the diagonal of the assembled stiffness matrix) assembled globally (every rank later picks
+    # its local rows)
     lump_g = np.zeros(nnode)
+    kdiag_g = np.zeros(nnode)
     for s_ in (1, 2):
         m = size == s_
         if m.any():
             np.add.at(lump_g, conn[m].ravel(), np.tile(mats[s_][2], int(m.sum())))
+            np.add.at(kdiag_g, conn[m].ravel(), np.tile(np.diag(mats[s_][0]), int(m.sum())))
 
     # per-atom enrichment overlap block (SPD) and projector strengths
     enr_blocks = []
@@ -618,6 +627,7 @@ def build_problem(spec: MeshSpec, only_rank: Optional[int] = None) -> List[RankP
         off2 = np.concatenate(([0], np.cumsum(ncd64 * ncd64)))
         ids = np.zeros(int(off1[-1]), np.int64)
         h_cell = np.zeros(int(off2[-1]))
+        k_cell = np.zeros(int(off2[-1]))
         plain = nenr_c == 0
         for s_ in (1, 2):
             m = plain & (size[cells] == s_)
@@ -626,6 +636,7 @@ def build_problem(spec: MeshSpec, only_rank: Optional[int] = None) -> List[RankP
             Kc, Mc, _ = mats[s_]
             blk = 0.5 * Kc.ravel()[None, :] + vcell[cells[m]][:, None] * Mc.ravel()[None, :]
             h_cell[(off2[:-1][m][:, None] + np.arange(npc * npc)[None, :]).ravel()] = blk.ravel()
+            k_cell[(off2[:-1][m][:, None] + np.arange(npc * npc)[None, :]).ravel()] = np.tile(Kc.ravel(), int(m.sum()))
             ids[(off1[:-1][m][:, None] + np.arange(npc)[None, :]).ravel()] = cl_all[m].ravel()
         for ic in np.nonzero(~plain)[0]:
             c = cells[ic]
@@ -644,6 +655,10 @@ def build_problem(spec: MeshSpec, only_rank: Optional[int] = None) -> List[RankP
             Hc[npc:, :npc] = Bc.T
             Hc[npc:, npc:] = 0.5 * (Ec + Ec.T) + np.eye(len(el)) * 0.5 * vol
             h_cell[off2[ic]:off2[ic + 1]] = Hc.ravel()
+            Kx = np.zeros((n_c, n_c))
+            Kx[:npc, :npc] = Kc
+            Kx[npc:, npc:] = np.eye(len(el)) * vol
+            k_cell[off2[ic]:off2[ic + 1]] = Kx.ravel()
         ncd = ncd64.astype(U32)
         ids = ids.astype(U32)
         ncp, pids, cblocks = [], [], []
@@ -706,6 +721,18 @@ def build_problem(spec: MeshSpec, only_rank: Optional[int] = None) -> List[RankP
         clm = l2g < Ncl
         prob.diag[clm] = lump_g[gid_to_node[l2g[clm]]]
         prob.diag_inv = 1.0 / prob.diag
+        prob.k_cell = k_cell
+        prob.k_diag = np.ones(halo.n_local)
+        prob.k_diag[clm] = kdiag_g[gid_to_node[l2g[clm]]]
+        if (~clm).any():  # enrichment rows: sum of the identity*vol blocks of the touching cells
+            kd = np.zeros(halo.n_local)
+            np.add.at(kd, ids.astype(np.int64), np.concatenate(
+                [np.diag(k_cell[off2[i]:off2[i + 1]].reshape(int(ncd64[i]), int(ncd64[i]))) for i in range(C)]))
+            prob.k_diag[~clm] = np.maximum(kd[~clm], 1e-12)
+        # inhomogeneous Dirichlet data for the Poisson "X" constraints: boundary rows (no parents) carry g(x)
+        xyz = coords[gid_to_node[l2g[prob.row_ids.astype(np.int64)]]] if len(row_ids) else np.zeros((0, 3))
+        prob.inhom_dirichlet = np.where(prob.row_sizes == 0, 0.3 + 0.1 * xyz[:, 0] - 0.05 * xyz[:, 1] * xyz[:, 2], 0.0) \
+            if len(row_ids) else np.zeros(0)
         nat = np.zeros(halo.n_local, np.int64)
         nat[clm] = gid_to_node[l2g[clm]]
         if (~clm).any():

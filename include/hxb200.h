@@ -88,9 +88,21 @@ typedef struct hx_nonlocal_desc {
 typedef enum hx_diag_variant {
   HX_DIAG_CFE            = 0, /* CFEOverlapInverseOpContextGLL::apply  (src/basis/CFEOverlapInverseOpContextGLL.t.cpp:529-558) */
   HX_DIAG_OEFE_ATOMBLOCK = 1, /* OEFEAtomBlockOverlapInvOpContextGLL::apply (src/basis/OEFEAtomBlockOverlapInvOpContextGLL.t.cpp:953-1108) */
-  HX_DIAG_OEFE_MASS      = 2  /* OrthoEFEOverlapOperatorContext::apply, mass-lumped atom-block branch: as ATOMBLOCK
+  HX_DIAG_OEFE_MASS      = 2, /* OrthoEFEOverlapOperatorContext::apply, mass-lumped atom-block branch: as ATOMBLOCK
                                  but both ghost flags are forced to false (src/basis/OrthoEFEOverlapOperatorContext.t.cpp:2093-2235) */
+  HX_DIAG_JACOBI         = 3  /* linearAlgebra::PreconditionerJacobi::apply: Y = diag .* X over local rows, ghost flags
+                                 honoured, no constraints (src/linearAlgebra/PreconditionerJacobi.t.cpp:52-82); pass the
+                                 RECIPROCAL diagonal (the reference inverts it in the constructor, :40-45) */
 } hx_diag_variant;
+
+/* linearAlgebra::LinearSolverErrorCode of CGLinearSolver (src/linearAlgebra/LinearAlgebraTypes.h) */
+typedef enum hx_cg_status {
+  HX_CG_SUCCESS             = 0,
+  HX_CG_FAILED_TO_CONVERGE  = 1,
+  HX_CG_RESIDUAL_DIVERGENCE = 2,
+  HX_CG_DIVISION_BY_ZERO    = 3,
+  HX_CG_OTHER_ERROR         = 4
+} hx_cg_status;
 
 const char *hx_last_error(void);
 int         hx_version(void);
@@ -151,6 +163,15 @@ int hx_distribute_parent_to_child(hx_plan *plan, double *X, uint32_t B);
 int hx_distribute_child_to_parent(hx_plan *plan, double *Y, uint32_t B);
 int hx_set_constrained_nodes_to_zero(hx_plan *plan, double *Y, uint32_t B);
 
+/* Further ConstraintsLocal objects on the same DoF numbering (set 0 = the mesh descriptor's): e.g. the inhomogeneous
+ * Dirichlet constraints of the Poisson problem's X basis manager next to the homogeneous ones of Y
+ * (src/electrostatics/LaplaceOperatorContextFE.t.cpp:421-433).  Same six arrays as hx_mesh_desc; returns the set id. */
+int hx_plan_add_constraints(hx_plan *plan, uint32_t n_rows, const uint32_t *row_ids, const uint32_t *row_sizes,
+                            const uint32_t *row_offsets, const uint32_t *col_ids, const double *col_vals,
+                            const double *inhom, uint32_t *set_id);
+int hx_distribute_parent_to_child_set(hx_plan *plan, uint32_t set, double *X, uint32_t B);
+int hx_distribute_child_to_parent_set(hx_plan *plan, uint32_t set, double *Y, uint32_t B);
+
 /* ---- operators: linearAlgebra::OperatorContext<double,double,DEVICE> (src/linearAlgebra/OperatorContext.h:48-111) ---- */
 /* Cell-matrix operator: KohnShamOperatorContextFE (src/ksdft/KohnShamOperatorContextFE.h:102-127); also the
  * non-lumped overlap operators (src/basis/OrthoEFEOverlapOperatorContext.t.cpp:2237-2290,
@@ -160,6 +181,10 @@ int hx_cellop_create(hx_plan *plan, hx_op **op);
  * row-major, S2 doubles; `on_device` says where `cell_matrices` lives.  Re-tiled internally. */
 int hx_cellop_set_matrices(hx_op *op, const double *cell_matrices, int on_device);
 int hx_cellop_set_nonlocal(hx_op *op, const hx_nonlocal_desc *nl);
+/* electrostatics::LaplaceOperatorContextFE (src/electrostatics/LaplaceOperatorContextFE.t.cpp:395-470): the same
+ * gather -> cell GEMM -> scatter path with the grad N_i . grad N_j cell matrices, where X is filled through the
+ * constraints of feBasisManagerX (x_set) and Y condensed through those of feBasisManagerY (y_set). */
+int hx_cellop_set_constraint_sets(hx_op *op, uint32_t x_set, uint32_t y_set);
 /* Mass-lumped M / M^-1 style operator: diagonal over local rows + atom-block enrichment matrix
  * (nE_owned x nE_owned, column-major; may be NULL when nE_owned == 0). Host pointers. */
 int hx_diagop_create(hx_plan *plan, const double *diag, const double *enr_block, int variant, hx_op **op);
@@ -170,6 +195,13 @@ int hx_op_destroy(hx_op *op);
 int hx_op_apply(hx_op *op, double *X, double *Y, uint32_t B, int updateGhostX, int updateGhostY);
 /* Same call with HOST buffers (n_local*B doubles each): copies X in, applies, copies X (modified) and Y out. */
 int hx_op_apply_host(hx_op *op, double *X_host, double *Y_host, uint32_t B, int updateGhostX, int updateGhostY);
+
+/* ---- preconditioned conjugate gradients: linearAlgebra::CGLinearSolver::solve (src/linearAlgebra/CGLinearSolver.t.cpp:
+ * 68-300) over B right-hand sides at once with per-column step lengths, as electrostatics::PoissonLinearSolverFunctionFE
+ * drives it.  b, x: DEVICE block vectors (x in: initial guess, out: xConverged); A.apply(.., true, true),
+ * PC.apply(.., false, false) exactly like the reference.  status: hx_cg_status. */
+int hx_cg_solve(hx_op *A, hx_op *PC, const double *b, double *x, uint32_t B, uint32_t max_iter, double abs_tol,
+                double rel_tol, double div_tol, uint32_t *iterations, int *status, double *residual_norms_host);
 
 /* ---- Chebyshev filters (src/linearAlgebra/ChebyshevFilter.h:54-113, ChebyshevFilter.t.cpp:39-134, 242-445) ---- */
 /* X = eigenSubspaceGuess (in/out), Y = filteredSubspace (out); on return both hold the filtered block. */

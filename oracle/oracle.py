@@ -103,10 +103,12 @@ class OracleRank:
         self._xcell = None
 
     # -- constraints (a3 / a7) --
-    def p2c(self, X):
+    def p2c(self, X, inhom=None):
+        """inhom: inhomogeneities of another ConstraintsLocal on the same rows (the Poisson X basis manager)"""
         B = X.shape[1]
+        ih = self.inhom if inhom is None else np.ascontiguousarray(inhom, dtype=np.float64)
         lib().orc_p2c(_f64(X), C.c_uint32(B), C.c_uint32(len(self.row_ids)), self.row_ids_p, self.row_sizes_p,
-                      self.row_offsets_p, self.col_ids_p, _f64(self.col_vals), _f64(self.inhom))
+                      self.row_offsets_p, self.col_ids_p, _f64(self.col_vals), _f64(ih))
 
     def c2p(self, Y):
         B = Y.shape[1]
@@ -237,7 +239,7 @@ class OracleWorld:
 
     # a10: KohnShamOperatorContextFE::apply (ksdft/KohnShamOperatorContextFE.t.cpp:1313-1443)
     def hx_apply(self, Xs, Ys, update_ghost_x=False, update_ghost_y=False, h_cells=None,
-                 long_double=False, use_nonlocal=True):
+                 long_double=False, use_nonlocal=True, x_inhoms=None):
         B = Xs[0].shape[1]
         if update_ghost_x:
             self.update_ghost_values(Xs)
@@ -245,7 +247,7 @@ class OracleWorld:
         CXs = [np.zeros((r.n_proj_local, B)) if nl else None for r in self.ranks]
 
         def sec_a(i):
-            self.ranks[i].p2c(Xs[i])
+            self.ranks[i].p2c(Xs[i], None if x_inhoms is None else x_inhoms[i])
             Ys[i][...] = 0.0
             self.ranks[i].loop_a(Xs[i], CXs[i], use_nonlocal=nl)
         self._each_rank(sec_a)
@@ -266,6 +268,86 @@ class OracleWorld:
         self.accumulate_add_locally_owned(Ys)
         if update_ghost_y:
             self.update_ghost_values(Ys)
+
+    # 8f rank 1: electrostatics::LaplaceOperatorContextFE::apply (electrostatics/LaplaceOperatorContextFE.t.cpp:
+    # 395-470): the H.X path with the grad N_i . grad N_j cell matrices and no nonlocal part; X is filled through the
+    # constraints of feBasisManagerX (inhomogeneous Dirichlet values), Y condensed through those of feBasisManagerY
+    def laplace_apply(self, Xs, Ys, update_ghost_x=False, update_ghost_y=False, inhomogeneous=True):
+        self.hx_apply(Xs, Ys, update_ghost_x, update_ghost_y, h_cells=[p.k_cell for p in self.problems],
+                      use_nonlocal=False,
+                      x_inhoms=[p.inhom_dirichlet for p in self.problems] if inhomogeneous else None)
+
+    # linearAlgebra::PreconditionerJacobi::apply (linearAlgebra/PreconditionerJacobi.t.cpp:52-82)
+    def jacobi_apply(self, Xs, Ys, update_ghost_x=False, update_ghost_y=False):
+        B = Xs[0].shape[1]
+        if update_ghost_x:
+            self.update_ghost_values(Xs)
+        for r, p, X, Y in zip(self.ranks, self.problems, Xs, Ys):
+            d = np.ascontiguousarray(1.0 / p.k_diag)
+            lib().orc_row_scale(_f64(d), _f64(X), _f64(Y), C.c_uint32(B), C.c_size_t(r.n_local))
+        if update_ghost_y:
+            self.update_ghost_values(Ys)
+
+    def col_dots(self, Us, Vs):
+        """MultiVector dot over the owned rows, summed over ranks (linearAlgebra/MultiVector.t.cpp:805-870)"""
+        B = Us[0].shape[1]
+        out = np.zeros(B)
+        for n, U, V in zip(self.n_owned, Us, Vs):
+            out += np.einsum("ij,ij->j", U[:n], V[:n])
+        return out
+
+    # linearAlgebra::CGLinearSolver::solve (linearAlgebra/CGLinearSolver.t.cpp:68-300)
+    def cg_solve(self, apply_A, apply_PC, bs, xs, max_iter, abs_tol, rel_tol, div_tol):
+        """bs, xs: per-rank [n_local, B]; xs holds the initial guess and receives xConverged.
+        Returns (iterations, error code [0 success, 1 failed to converge, 2 divergence, 4 other], residual norms)."""
+        B = bs[0].shape[1]
+        bnorm = np.sqrt(self.col_dots(bs, bs))
+        xconv = [x.copy() for x in xs]
+        r = [np.zeros_like(b) for b in bs]
+        w = [np.zeros_like(b) for b in bs]
+        z = [np.zeros_like(b) for b in bs]
+        pd = [np.zeros_like(b) for b in bs]
+        converged = np.zeros(B, bool)
+        err, diverged = 4, False
+        rnorm = np.zeros(B)
+        it = 0
+        while it <= max_iter:
+            if it == 0:
+                apply_A(xs, w, True, True)
+                for i, n in enumerate(self.n_owned):
+                    r[i][:n] = 1.0 * bs[i][:n] + (-1.0) * w[i][:n]
+                apply_PC(r, z, False, False)
+                for i in range(self.nr):
+                    pd[i][...] = z[i]
+            else:
+                apply_A(pd, w, True, True)
+                zdotr = self.col_dots(z, r)
+                pdotw = self.col_dots(pd, w)
+                alpha = zdotr / pdotw
+                for i, n in enumerate(self.n_owned):
+                    xs[i][:n] = 1.0 * xs[i][:n] + alpha[None, :] * pd[i][:n]
+                    r[i][:n] = 1.0 * r[i][:n] + (-alpha)[None, :] * w[i][:n]
+                apply_PC(r, z, False, False)
+                beta = self.col_dots(z, r) / zdotr
+                for i, n in enumerate(self.n_owned):
+                    pd[i][:n] = 1.0 * z[i][:n] + beta[None, :] * pd[i][:n]
+            rnorm = np.sqrt(self.col_dots(r, r))
+            for j in range(B):
+                if rnorm[j] < max(abs_tol, bnorm[j] * rel_tol) and not converged[j]:
+                    err = 0
+                    converged[j] = True
+                    for i, n in enumerate(self.n_owned):
+                        xconv[i][:n, j] = xs[i][:n, j]
+                if rnorm[j] > div_tol and not diverged:
+                    err, diverged = 2, True
+            if diverged or converged.all():
+                break
+            it += 1
+        for i in range(self.nr):
+            xs[i][...] = xconv[i]
+        if it > max_iter:
+            err = 1
+        return it, err, rnorm
 
     # a11 / a12 (mass-lumped): diag row-scale + atom-block enrichment GEMM
     def diag_apply(self, Xs, Ys, diags, enr_blocks, update_ghost_x=False, update_ghost_y=False,

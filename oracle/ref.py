@@ -115,3 +115,21 @@ def hx_apply_serial(prob, X, cell_block=3, use_nonlocal=True):
                                   f64(h), C.c_uint32(len(r)), rp, sp, op, cp, C.c_uint32(len(c)), f64(v), f64(ih),
                                   None, None, None, None, C.c_uint32(0), C.c_uint32(cell_block))
     return Y
+
+
+def cg_solve(apply_A, apply_PC, b, x0, max_iter, abs_tol, rel_tol, div_tol):
+    """The reference's own CGLinearSolver::solve (linearAlgebra/CGLinearSolver.t.cpp) on one rank over Python
+    operators: apply_X(X, Y, update_ghost_x, update_ghost_y) with [n, B] arrays.  Returns (x, isSuccess)."""
+    n, B = b.shape
+
+    def cb(_user, op_id, xp, yp, n_, B_, ugx, ugy):
+        X = np.ctypeslib.as_array(xp, shape=(n_, B_))
+        Y = np.ctypeslib.as_array(yp, shape=(n_, B_))
+        (apply_A if op_id == 0 else apply_PC)(X, Y, bool(ugx), bool(ugy))
+
+    c = APPLY_CB(cb)
+    x = np.ascontiguousarray(x0, dtype=np.float64).copy()
+    lib().ref_cg_solve.restype = C.c_int
+    ok = lib().ref_cg_solve(c, None, f64(np.ascontiguousarray(b)), f64(x), C.c_uint32(n), C.c_uint32(B),
+                            C.c_uint32(max_iter), C.c_double(abs_tol), C.c_double(rel_tol), C.c_double(div_tol))
+    return x, bool(ok)

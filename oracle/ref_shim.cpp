@@ -292,3 +292,78 @@ extern "C"
       out[j] = r[j];
   }
 }
+
+// ---- CGLinearSolver::solve over caller-supplied operators (opIds: 0 = A, 1 = preconditioner) -------------------
+#include <linearAlgebra/CGLinearSolver.h>
+namespace
+{
+  class CallbackLinearSolverFunction : public linearAlgebra::LinearSolverFunction<double, double, HOST>
+  {
+  public:
+    CallbackLinearSolverFunction(apply_cb cb, void *user, const double *b, const double *x0, unsigned n, unsigned B)
+      : d_A(cb, user, 0)
+      , d_PC(cb, user, 1)
+      , d_b((size_type)n, (size_type)B, ctx(), 0.0)
+      , d_x((size_type)n, (size_type)B, ctx(), 0.0)
+    {
+      std::memcpy(d_b.data(), b, sizeof(double) * (size_t)n * B);
+      std::memcpy(d_x.data(), x0, sizeof(double) * (size_t)n * B);
+      d_comm = d_b.getMPIPatternP2P()->mpiCommunicator();
+    }
+    const linearAlgebra::OperatorContext<double, double, HOST> &
+    getAxContext() const override
+    {
+      return d_A;
+    }
+    const linearAlgebra::OperatorContext<double, double, HOST> &
+    getPCContext() const override
+    {
+      return d_PC;
+    }
+    void
+    setSolution(const MV &x) override
+    {
+      d_x = x;
+    }
+    void
+    getSolution(MV &s) override
+    {
+      s = d_x;
+    }
+    const MV &
+    getRhs() const override
+    {
+      return d_b;
+    }
+    const MV &
+    getInitialGuess() const override
+    {
+      return d_x;
+    }
+    const utils::mpi::MPIComm &
+    getMPIComm() const override
+    {
+      return d_comm;
+    }
+    MV d_b, d_x;
+
+  private:
+    CallbackOp          d_A, d_PC;
+    utils::mpi::MPIComm d_comm;
+  };
+} // namespace
+
+extern "C"
+{
+  // returns the reference's isSuccess flag; x (n x B): initial guess in, xConverged out
+  int
+  ref_cg_solve(apply_cb cb, void *user, const double *b, double *x, unsigned n, unsigned B, unsigned maxIter, double absTol,
+               double relTol, double divTol)
+  {
+    CallbackLinearSolverFunction                          f(cb, user, b, x, n, B);
+    linearAlgebra::CGLinearSolver<double, double, HOST>   cg(maxIter, absTol, relTol, divTol);
+    const linearAlgebra::LinearSolverError                e = cg.solve(f);
+    std::memcpy(x, f.d_x.data(), sizeof(double) * (size_t)n * B);
+    return e.isSuccess ? 1 : 0;
+  }
+}

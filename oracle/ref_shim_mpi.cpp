@@ -3,6 +3,8 @@
 // (src/utils/MPIWrapper.cpp:188-361) does not compile (stray ';' at MPIWrapper.cpp:334), and MPI
 // is absent here, so oracle/_ref is a single-rank build: communicator size 1, rank 0, every
 // request complete.
+#include <string>
+#include <utility>
 #include <utils/MPITypes.h>
 #include <utils/MPIWrapper.h>
 namespace dftefe
@@ -22,6 +24,16 @@ namespace dftefe
       {
         *size = 1;
         return MPISuccess;
+      }
+      int
+      MPIBarrier(MPIComm)
+      {
+        return MPISuccess;
+      }
+      std::pair<bool, std::string>
+      MPIErrIsSuccessAndMsg(int errCode)
+      {
+        return std::make_pair(errCode == MPISuccess, std::string(errCode == MPISuccess ? "" : "serial MPI stub error"));
       }
       int
       MPIIbarrier(MPIComm, MPIRequest *)

@@ -415,6 +415,69 @@ def test_residual_chebyshev_filter(capi, prob_full):
     assert rel_l2_per_vector(dY.download()[:own], Yo[:own]) < 1e-11
 
 
+# ------------------------------------- electrostatics: Laplace operator + CG ----
+def _laplace_ops(capi, p, B):
+    plan = capi.Plan(p, max_block=B)
+    xset = plan.add_constraints(p.row_ids, p.row_sizes, p.row_offsets, p.col_ids, p.col_vals, p.inhom_dirichlet)
+    A = capi.CellOp(plan, h_cell=p.k_cell, with_nonlocal=False)
+    pc = capi.DiagOp(plan, 1.0 / p.k_diag, None, capi.DIAG_JACOBI)
+    return plan, xset, A, pc
+
+
+@pytest.mark.parametrize("B", [1, 2, 5])
+def test_laplace_operator_two_constraint_sets(capi, prob_full, B):
+    """LaplaceOperatorContextFE::apply: X filled through the inhomogeneous-Dirichlet constraints of feBasisManagerX,
+    Y condensed through the homogeneous ones of feBasisManagerY"""
+    p = prob_full
+    plan, xset, A, pc = _laplace_ops(capi, p, B)
+    A.set_constraint_sets(xset, 0)
+    W = orc.OracleWorld([p])
+    X = synth.make_block(p, B)
+    dX, dY = plan.block(B, X), plan.block(B)
+    A.apply(dX, dY, True, True)
+    Xo, Yo = X.copy(), np.zeros_like(X)
+    W.laplace_apply([Xo], [Yo], True, True, inhomogeneous=True)
+    assert rel_l2_per_vector(dY.download(), Yo) < RTOL_HX
+    assert rel_l2_per_vector(dX.download(), Xo) < 1e-14
+    assert np.abs(Xo[p.row_ids.astype(np.int64)][p.row_sizes == 0] - p.inhom_dirichlet[p.row_sizes == 0][:, None]).max() == 0.0
+    # Jacobi preconditioner
+    pc.apply(dX, dY, False, False)
+    Zo = np.zeros_like(X)
+    W.jacobi_apply([Xo], [Zo], False, False)
+    assert rel_l2_per_vector(dY.download(), Zo) < 1e-15
+
+
+@pytest.mark.parametrize("B", [1, 4])
+def test_cg_poisson_solve(capi, prob_full, B):
+    """CGLinearSolver::solve on the device against the oracle's restatement (itself pinned against the reference's
+    compiled CGLinearSolver, tests/test_oracle.py): same iteration count, same solution."""
+    p = prob_full
+    plan, xset, A, pc = _laplace_ops(capi, p, B)
+    rng = np.random.default_rng(5)
+    b = rng.standard_normal((p.n_local, B)); b[p.row_ids.astype(np.int64)] = 0.0
+    x0 = 0.1 * rng.standard_normal((p.n_local, B))
+    db, dx = plan.block(B, b), plan.block(B, x0)
+    it, st, rn = capi.cg_solve(A, pc, db, dx, 400, 1e-12, 1e-10, 1e10)
+    W = orc.OracleWorld([p])
+    xs = [x0.copy()]
+    ito, erro, rno = W.cg_solve(lambda X, Y, a, c: W.laplace_apply(X, Y, a, c, inhomogeneous=False),
+                                lambda X, Y, a, c: W.jacobi_apply(X, Y, a, c), [b], xs, 400, 1e-12, 1e-10, 1e10)
+    assert st == capi.CG_SUCCESS and erro == 0
+    assert abs(it - ito) <= 1
+    own = p.n_owned
+    xg = dx.download()
+    assert np.abs(xg[:own] - xs[0][:own]).max() < 1e-8 * np.abs(xs[0][:own]).max()
+    # residual of the device solution through the device operator
+    dy = plan.block(B)
+    A.apply(plan.block(B, xg), dy, True, True)
+    r = dy.download()[:own] - b[:own]
+    assert np.linalg.norm(r) < 1e-8 * np.linalg.norm(b[:own])
+    # failure mode: an iteration cap that cannot be met reports FAILED_TO_CONVERGE
+    dx2 = plan.block(B, x0)
+    it2, st2, _ = capi.cg_solve(A, pc, db, dx2, 3, 1e-14, 1e-14, 1e10)
+    assert st2 == capi.CG_FAILED_TO_CONVERGE and it2 == 4
+
+
 # --------------------------------------------------------------- subspace projections ----
 @pytest.mark.parametrize("B,batch", [(6, 4), (32, 32), (40, 16), (96, 64)])
 def test_xtopx(capi, prob_full, B, batch):

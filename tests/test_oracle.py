@@ -174,6 +174,68 @@ def test_hx_golden_fixture_from_reference_assembled_apply(probs):
     assert err.max() < 1e-14, err
 
 
+def _poisson_setup(p, B, seed=5):
+    """right-hand side with zero constrained rows and an initial guess (ghost rows arbitrary)"""
+    rng = np.random.default_rng(seed)
+    b = rng.standard_normal((p.n_local, B))
+    b[p.row_ids.astype(np.int64)] = 0.0
+    x0 = 0.1 * rng.standard_normal((p.n_local, B))
+    return b, x0
+
+
+def test_cg_matches_reference_cg_solver(ref_lib, probs):
+    """Poisson-type solve (LaplaceOperatorContextFE + PreconditionerJacobi) with the oracle's CG against the
+    reference's own compiled CGLinearSolver::solve driving the same operators: same iterates, same solution."""
+    p = probs[1][0]
+    B = 3
+    W = orc.OracleWorld([p])
+    b, x0 = _poisson_setup(p, B)
+
+    def A(X, Y, ugx, ugy):
+        W.laplace_apply([X], [Y], ugx, ugy, inhomogeneous=False)
+
+    def PC(X, Y, ugx, ugy):
+        W.jacobi_apply([X], [Y], ugx, ugy)
+
+    xs = [x0.copy()]
+    it, err, rn = W.cg_solve(lambda Xs, Ys, a, c: A(Xs[0], Ys[0], a, c), lambda Xs, Ys, a, c: PC(Xs[0], Ys[0], a, c),
+                             [b], xs, 400, 1e-12, 1e-10, 1e10)
+    assert err == 0 and it < 400
+    xr, ok = ref_lib.cg_solve(A, PC, b, x0, 400, 1e-12, 1e-10, 1e10)
+    assert ok
+    own = p.n_owned
+    assert np.abs(xs[0][:own] - xr[:own]).max() < 1e-9 * np.abs(xr[:own]).max()
+    # and it is a solution: A x = b on the unconstrained rows
+    Y = np.zeros_like(b)
+    A(xr.copy(), Y, True, True)
+    assert np.linalg.norm(Y[:own] - b[:own]) < 1e-8 * np.linalg.norm(b[:own])
+
+
+def test_cg_partition_independence(probs):
+    """2 and 4 partitions give the single-partition Poisson solution (halo semantics of A and of the dot products)"""
+    B = 2
+    sols = {}
+    for n in (1, 2, 4):
+        ps = probs[n]
+        W = orc.OracleWorld(ps)
+        rng = np.random.default_rng(9)
+        bs, xs = [], []
+        nat_b = {}
+        for p in ps:
+            b = np.zeros((p.n_local, B))
+            for v in range(B):
+                b[:, v] = synth.counter_uniform(77 + v, p.natural_ids.astype(np.int64))
+            b[p.row_ids.astype(np.int64)] = 0.0
+            bs.append(b)
+            xs.append(np.zeros((p.n_local, B)))
+        it, err, rn = W.cg_solve(lambda X, Y, a, c: W.laplace_apply(X, Y, a, c, inhomogeneous=False),
+                                 lambda X, Y, a, c: W.jacobi_apply(X, Y, a, c), bs, xs, 500, 1e-13, 1e-11, 1e10)
+        assert err == 0
+        sols[n] = to_natural(ps, xs)
+    for n in (2, 4):
+        assert np.abs(sols[n] - sols[1]).max() < 1e-8 * np.abs(sols[1]).max()
+
+
 def test_blas1_match_reference_sources(ref_lib):
     rng = np.random.default_rng(2)
     n, B = 40, 7
