@@ -275,6 +275,29 @@ def run_ours(args):
         except Exception as e:  # noqa: BLE001
             sub["error"] = str(e)[:200]
 
+        # ---- electrostatics: Laplace apply + Jacobi-preconditioned CG iterations on one right-hand side ----
+        poisson = {}
+        try:
+            if nranks == 1:
+                A_l = capi.CellOp(plan, h_cell=prob.k_cell, with_nonlocal=False)
+                pc_l = capi.DiagOp(plan, 1.0 / prob.k_diag, None, capi.DIAG_JACOBI)
+                rhs = np.zeros((prob.n_local, 1)); rhs[:prob.n_owned, 0] = X[:prob.n_owned, 0]
+                rhs[prob.row_ids.astype(np.int64)] = 0.0
+                db1, dx1, dy1 = capi.DeviceBlock(prob.n_local, 1, rhs), capi.DeviceBlock(prob.n_local, 1), capi.DeviceBlock(prob.n_local, 1)
+                A_l.apply(db1, dy1, True, True)
+                poisson["laplace_apply_ms_B1"] = timed(lambda: A_l.apply(db1, dy1, True, True), 10)
+                n_it = 40
+                plan.synchronize()
+                t0 = time.perf_counter()
+                it_done, st, rn = capi.cg_solve(A_l, pc_l, db1, dx1, n_it, 1e-30, 1e-30, 1e300)
+                poisson["cg_ms_per_iteration_B1"] = (time.perf_counter() - t0) * 1e3 / max(it_done, 1)
+                poisson["cg_iterations_timed"] = int(it_done)
+                poisson["cg_residual_reduction"] = float(rn[0] / np.linalg.norm(rhs[:prob.n_owned, 0]))
+                poisson["gdof_per_s_apply"] = N_global / (poisson["laplace_apply_ms_B1"] * 1e-3) / 1e9
+                del A_l, pc_l
+        except Exception as e:  # noqa: BLE001
+            poisson["error"] = str(e)[:200]
+
         # ---- end to end through the host-buffer entry point (pinned host memory, H2D + D2H every step) ----
         xh = torch.from_numpy(X).pin_memory()
         yh = torch.zeros_like(xh).pin_memory()
@@ -368,6 +391,7 @@ def run_ours(args):
             "hx_apply": {"ms": apply_ms, "value": N_global * B / (apply_ms * 1e-3) / 1e9, "unit": UNIT,
                          "what": "bare KohnShamOperatorContextFE::apply (updateGhostX=true), block resident in HBM"},
             "subspace": sub,
+            "poisson": poisson,
             "chebyshev_filter": {"degree": DEGREE, "seconds_per_scf_iter": ms_per_step * 1e-3,
                                  "ms_per_degree": ms_per_step / DEGREE, "fused_recurrence": True,
                                  "phase_ms_per_degree": phases},

@@ -660,5 +660,140 @@ namespace dftefe
       }
     } // namespace elpaScalaOpInternal
   }   // namespace linearAlgebra
+
+  // ---------------------------------------------------------------------------------------------------------------
+  // electrostatics: the Poisson solve that produces the Hartree / nuclear potentials every SCF
+  // iteration runs the same gather -> cell GEMM -> scatter kernel with grad N_i . grad N_j cell matrices
+  // ---------------------------------------------------------------------------------------------------------------
+  namespace basis
+  {
+    // one more ConstraintsLocal on the DoF numbering of the DeviceContext (e.g. feBasisManagerX of the Poisson
+    // problem: inhomogeneous Dirichlet data); the six arrays of src/basis/CFEConstraintsLocalDealii.t.cpp:286-462
+    struct ConstraintsLocalArrays
+    {
+      std::vector<size_type> rowConstraintsIdsLocal, rowConstraintsSizes, columnConstraintsAccumulated, columnConstraintsIdsLocal;
+      std::vector<double>    columnConstraintsValues, constraintsInhomogenities;
+    };
+    inline uint32_t
+    registerConstraints(const linearAlgebra::DeviceContext &ctx, const ConstraintsLocalArrays &c)
+    {
+      uint32_t id = 0;
+      utils::hxCheck(hx_plan_add_constraints(ctx.plan(), (uint32_t)c.rowConstraintsIdsLocal.size(), c.rowConstraintsIdsLocal.data(),
+                                             c.rowConstraintsSizes.data(), c.columnConstraintsAccumulated.data(),
+                                             c.columnConstraintsIdsLocal.data(), c.columnConstraintsValues.data(),
+                                             c.constraintsInhomogenities.data(), &id));
+      return id;
+    }
+  } // namespace basis
+
+  namespace electrostatics
+  {
+    // LaplaceOperatorContextFE<double,double,DEVICE,3> (src/electrostatics/LaplaceOperatorContextFE.t.cpp:395-470):
+    // constraintsX / constraintsY are ids from basis::registerConstraints (0 = the DeviceContext's own constraints)
+    class LaplaceOperatorContextFE : public linearAlgebra::NativeOperator
+    {
+    public:
+      LaplaceOperatorContextFE(std::shared_ptr<const linearAlgebra::DeviceContext> ctx, const double *gradNiGradNjInAllCells,
+                               bool onDevice, uint32_t constraintsX = 0, uint32_t constraintsY = 0)
+      {
+        d_ctx = std::move(ctx);
+        utils::hxCheck(hx_cellop_create(d_ctx->plan(), &d_op));
+        utils::hxCheck(hx_cellop_set_matrices(d_op, gradNiGradNjInAllCells, onDevice ? 1 : 0));
+        utils::hxCheck(hx_cellop_set_constraint_sets(d_op, constraintsX, constraintsY));
+      }
+    };
+  } // namespace electrostatics
+
+  namespace linearAlgebra
+  {
+    // PreconditionerJacobi (src/linearAlgebra/PreconditionerJacobi.t.cpp:35-82): takes the DIAGONAL like the reference
+    class PreconditionerJacobi : public NativeOperator
+    {
+    public:
+      PreconditionerJacobi(std::shared_ptr<const DeviceContext> ctx, const std::vector<double> &diagonal)
+      {
+        d_ctx = std::move(ctx);
+        utils::throwException(diagonal.size() == d_ctx->localSize(), "diagonal must cover the local (owned+ghost) rows");
+        std::vector<double> inv(diagonal.size());
+        for (size_t i = 0; i < inv.size(); ++i)
+          inv[i] = 1.0 / diagonal[i]; // blasLapack::reciprocalX in the reference constructor (:40-45)
+        utils::hxCheck(hx_diagop_create(d_ctx->plan(), inv.data(), nullptr, HX_DIAG_JACOBI, &d_op));
+      }
+    };
+
+    // LinearSolverFunction (src/linearAlgebra/LinearSolverFunction.h): the handles CGLinearSolver::solve asks for
+    class LinearSolverFunction
+    {
+    public:
+      virtual ~LinearSolverFunction() = default;
+      virtual const NativeOperator &
+      getAxContext() const = 0;
+      virtual const NativeOperator &
+      getPCContext() const = 0;
+      virtual const DeviceMultiVector &
+      getRhs() const = 0;
+      virtual const DeviceMultiVector &
+      getInitialGuess() const = 0;
+      virtual void
+      setSolution(const DeviceMultiVector &x) = 0;
+    };
+
+    // LinearSolverErrorCode / LinearSolverError (src/linearAlgebra/LinearAlgebraTypes.h:83-90, 120-160)
+    enum class LinearSolverErrorCode
+    {
+      SUCCESS,
+      FAILED_TO_CONVERGE,
+      RESIDUAL_DIVERGENCE,
+      DIVISON_BY_ZERO,
+      OTHER_ERROR
+    };
+    struct LinearSolverError
+    {
+      bool                  isSuccess;
+      LinearSolverErrorCode err;
+      std::string           msg;
+    };
+
+    // CGLinearSolver (src/linearAlgebra/CGLinearSolver.h:60-100, .t.cpp:68-300)
+    class CGLinearSolver
+    {
+    public:
+      CGLinearSolver(size_type maxIter, double absoluteTol, double relativeTol, double divergenceTol)
+        : d_maxIter(maxIter)
+        , d_absoluteTol(absoluteTol)
+        , d_relativeTol(relativeTol)
+        , d_divergenceTol(divergenceTol)
+      {}
+      LinearSolverError
+      solve(LinearSolverFunction &f)
+      {
+        const DeviceMultiVector &b = f.getRhs();
+        DeviceMultiVector        x(f.getInitialGuess());
+        uint32_t                 iters  = 0;
+        int                      status = 0;
+        utils::hxCheck(hx_cg_solve(f.getAxContext().handle(), f.getPCContext().handle(), b.data(), x.data(),
+                                   b.getNumberComponents(), d_maxIter, d_absoluteTol, d_relativeTol, d_divergenceTol, &iters,
+                                   &status, nullptr));
+        f.setSolution(x);
+        d_iterations = iters;
+        LinearSolverError e;
+        e.err       = static_cast<LinearSolverErrorCode>(status);
+        e.isSuccess = status == HX_CG_SUCCESS;
+        e.msg       = e.isSuccess ? "CGLinear solve converged in maximum " + std::to_string(iters) + " iterations" :
+                                    (status == HX_CG_FAILED_TO_CONVERGE ? "The linear solver failed to converge" :
+                                     status == HX_CG_RESIDUAL_DIVERGENCE ? "The residual diverged" : "Other error");
+        return e;
+      }
+      size_type
+      iterations() const
+      {
+        return d_iterations;
+      }
+
+    private:
+      size_type d_maxIter, d_iterations = 0;
+      double    d_absoluteTol, d_relativeTol, d_divergenceTol;
+    };
+  } // namespace linearAlgebra
 } // namespace dftefe
 #endif

@@ -168,6 +168,53 @@ main(int argc, char **argv)
       X.copyTo(host.data());
       writeArray(out, "rotated", host);
 
+      // ---- electrostatics call site (PoissonLinearSolverFunctionFE + CGLinearSolver, as KohnShamDFT drives them):
+      // Laplace operator with the X constraints carrying inhomogeneous Dirichlet data, Jacobi preconditioner, CG ----
+      {
+        basis::ConstraintsLocalArrays cx;
+        cx.rowConstraintsIdsLocal       = fe.rowConstraintsIdsLocal;
+        cx.rowConstraintsSizes          = fe.rowConstraintsSizes;
+        cx.columnConstraintsAccumulated = fe.columnConstraintsAccumulated;
+        cx.columnConstraintsIdsLocal    = fe.columnConstraintsIdsLocal;
+        cx.columnConstraintsValues      = fe.columnConstraintsValues;
+        cx.constraintsInhomogenities    = b.f.at("inhom_dirichlet");
+        const uint32_t                           xset = basis::registerConstraints(*ctx, cx);
+        electrostatics::LaplaceOperatorContextFE AxInhomo(ctx, b.f.at("k_cell").data(), false, xset, 0);
+        electrostatics::LaplaceOperatorContextFE Ax(ctx, b.f.at("k_cell").data(), false, 0, 0);
+        linearAlgebra::PreconditionerJacobi      pc(ctx, b.f.at("k_diag"));
+        X.copyFrom(b.f.at("X").data());
+        AxInhomo.apply(X, Y, true, true);
+        Y.copyTo(host.data());
+        writeArray(out, "laplace_inhomo", host);
+
+        struct Poisson : linearAlgebra::LinearSolverFunction
+        {
+          const linearAlgebra::NativeOperator &A, &P;
+          linearAlgebra::DeviceMultiVector     rhs, guess, solution;
+          Poisson(const linearAlgebra::NativeOperator &a, const linearAlgebra::NativeOperator &p_,
+                  std::shared_ptr<const linearAlgebra::DeviceContext> c, size_type nv)
+            : A(a), P(p_), rhs(c, nv), guess(c, nv), solution(c, nv)
+          {}
+          const linearAlgebra::NativeOperator &getAxContext() const override { return A; }
+          const linearAlgebra::NativeOperator &getPCContext() const override { return P; }
+          const linearAlgebra::DeviceMultiVector &getRhs() const override { return rhs; }
+          const linearAlgebra::DeviceMultiVector &getInitialGuess() const override { return guess; }
+          void setSolution(const linearAlgebra::DeviceMultiVector &x) override
+          {
+            std::vector<double> t((size_t)x.localSize() * x.getNumberComponents());
+            x.copyTo(t.data());
+            solution.copyFrom(t.data());
+          }
+        } poisson(Ax, pc, ctx, B);
+        poisson.rhs.copyFrom(b.f.at("poisson_rhs").data());
+        poisson.guess.copyFrom(b.f.at("poisson_guess").data());
+        linearAlgebra::CGLinearSolver        cg(400, 1e-12, 1e-10, 1e10);
+        const linearAlgebra::LinearSolverError e = cg.solve(poisson);
+        poisson.solution.copyTo(host.data());
+        writeArray(out, "poisson_solution", host);
+        writeArray(out, "poisson_status", std::vector<double>{e.isSuccess ? 1.0 : 0.0, (double)cg.iterations()});
+      }
+
       // error convention: a wrong block width must throw, not crash
       bool threw = false;
       try

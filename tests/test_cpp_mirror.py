@@ -81,7 +81,11 @@ def test_cpp_mirror_matches_oracle(tmp_path):
               "cell_proj_local_ids": p.cell_proj_local_ids, "cell_c": p.cell_c, "proj_v": p.proj_v,
               "h_part1": part1, "h_part2": p.h_cell - part1, "diag_inv": p.diag_inv,
               "enr_block_inv": np.asarray(p.enr_block_inv, np.float64).ravel(order="F"),
-              "bounds": np.array([a0, a, b]), "X": X, "Q": Q.ravel(order="F")}
+              "bounds": np.array([a0, a, b]), "X": X, "Q": Q.ravel(order="F"),
+              "k_cell": p.k_cell, "k_diag": p.k_diag, "inhom_dirichlet": p.inhom_dirichlet}
+    rhs = rng.standard_normal((p.n_local, B)); rhs[p.row_ids.astype(np.int64)] = 0.0
+    guess = 0.1 * rng.standard_normal((p.n_local, B))
+    arrays["poisson_rhs"], arrays["poisson_guess"] = rhs, guess
     arrays = {k: (np.asarray(v, np.uint32) if np.asarray(v).dtype.kind in "ui" else np.asarray(v, np.float64))
               for k, v in arrays.items()}
     write_blob(tmp_path / "problem.bin", arrays)
@@ -110,3 +114,13 @@ def test_cpp_mirror_matches_oracle(tmp_path):
     W.subspace_rotation(Xr, Q, True, False)
     assert rel(res["rotated"].reshape(X.shape)[:own], Xr[0][:own]) < 1e-13
     assert res["threw"][0] == 1.0
+    # electrostatics call site: Laplace operator with two constraint sets, Jacobi-preconditioned CG
+    Xl, Yl = X.copy(), np.zeros_like(X)
+    W.laplace_apply([Xl], [Yl], True, True, inhomogeneous=True)
+    assert rel(res["laplace_inhomo"].reshape(X.shape), Yl) < 1e-12
+    xs = [guess.copy()]
+    ito, erro, _ = W.cg_solve(lambda X_, Y_, a_, c_: W.laplace_apply(X_, Y_, a_, c_, inhomogeneous=False),
+                              lambda X_, Y_, a_, c_: W.jacobi_apply(X_, Y_, a_, c_), [rhs], xs, 400, 1e-12, 1e-10, 1e10)
+    assert erro == 0 and res["poisson_status"][0] == 1.0 and abs(res["poisson_status"][1] - ito) <= 1
+    sol = res["poisson_solution"].reshape(X.shape)
+    assert np.abs(sol[:own] - xs[0][:own]).max() < 1e-8 * np.abs(xs[0][:own]).max()
