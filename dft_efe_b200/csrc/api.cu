@@ -1271,31 +1271,37 @@ extern "C"
     HX_TRY(p->get_scratch(2, &z));
     HX_TRY(p->get_scratch(3, &pd));
     HX_TRY(p->get_scratch(6, &xconv));
-    HX_TRY(p->ensure_small((size_t)604 * B + 8 * (size_t)B));
-    double *d_dots = p->d_small.p + (size_t)600 * B; // [3][B] reduction outputs
-    double *d_coef = d_dots + 3 * (size_t)B;         // [4][B]: ones | coefficient a | coefficient b | spare
-    HX_TRY(p->ensure_pinned(8 * (size_t)B * sizeof(double)));
+    // per-column scalars stay on the device (one host synchronisation per iteration: the residual norms of the
+    // convergence test); layout after the reduction scratch: ones | zdotr | pdotw | zdotr_new | rr | alpha | -alpha | beta
+    HX_TRY(p->ensure_small((size_t)600 * B + 8 * (size_t)B));
+    double *d_ones = p->d_small.p + (size_t)600 * B, *d_zdotr = d_ones + B, *d_pdotw = d_zdotr + B, *d_zdotr_new = d_pdotw + B,
+           *d_rr = d_zdotr_new + B, *d_alpha = d_rr + B, *d_nalpha = d_alpha + B, *d_beta = d_nalpha + B;
+    HX_TRY(p->ensure_pinned(2 * (size_t)B * sizeof(double)));
     double *            h = p->h_pinned;
-    std::vector<double> ones(B, 1.0), coef(B), bnorm(B), rnorm(B), zdotr(B), pdotw(B), zdotr_new(B);
+    std::vector<double> ones(B, 1.0), bnorm(B), rnorm(B);
     std::vector<char>   converged(B, 0);
-    auto reduce = [&](const double *u, const double *v, double *out_host) -> int {
-      HX_TRY(launch_coldot(p, u, v, B, p->n_owned, d_dots));
+    HX_CUDA(cudaMemcpyAsync(d_ones, ones.data(), B * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    std::vector<double> neg(B, -1.0);
+    HX_CUDA(cudaMemcpyAsync(d_nalpha, neg.data(), B * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    HX_CUDA(cudaStreamSynchronize(p->stream));
+    auto reduce = [&](const double *u, const double *v, double *out_dev) -> int {
+      HX_TRY(launch_coldot(p, u, v, B, p->n_owned, out_dev));
       if (p->nranks > 1)
-        HX_TRY(comm_allreduce_sum(p->comm, p->stream, d_dots, B));
-      HX_CUDA(cudaMemcpyAsync(h, d_dots, B * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+        HX_TRY(comm_allreduce_sum(p->comm, p->stream, out_dev, B));
+      return HX_OK;
+    };
+    auto fetch = [&](const double *dev, double *out_host) -> int {
+      HX_CUDA(cudaMemcpyAsync(h, dev, B * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
       HX_CUDA(cudaStreamSynchronize(p->stream));
       memcpy(out_host, h, B * sizeof(double));
       return HX_OK;
     };
-    // z = 1*u + c[j]*v per column (linearAlgebra::add, MultiVector.t.cpp), over the owned rows
-    auto add = [&](const double *u, const std::vector<double> &c, const double *v, double *out) -> int {
-      HX_CUDA(cudaMemcpyAsync(d_coef, ones.data(), B * sizeof(double), cudaMemcpyHostToDevice, p->stream));
-      HX_CUDA(cudaMemcpyAsync(d_coef + B, c.data(), B * sizeof(double), cudaMemcpyHostToDevice, p->stream));
-      HX_TRY(launch_axpby_blocked(p, p->n_owned, B, 1.0, d_coef, u, 1.0, d_coef + B, v, out));
-      HX_CUDA(cudaStreamSynchronize(p->stream)); // c is a caller-owned host vector
-      return HX_OK;
+    // out = 1*u + c[j]*v per column (linearAlgebra::add), over the owned rows; c lives on the device
+    auto add = [&](const double *u, const double *c_dev, const double *v, double *out) -> int {
+      return launch_axpby_blocked(p, p->n_owned, B, 1.0, d_ones, u, 1.0, c_dev, v, out);
     };
-    HX_TRY(reduce(b, b, bnorm.data()));
+    HX_TRY(reduce(b, b, d_rr));
+    HX_TRY(fetch(d_rr, bnorm.data()));
     for (uint32_t j = 0; j < B; ++j)
       bnorm[j] = sqrt(bnorm[j]);
     HX_CUDA(cudaMemcpyAsync(xconv, x, nloc * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
@@ -1307,29 +1313,25 @@ extern "C"
         if (iter == 0)
           {
             HX_TRY(op_apply(A, x, w, B, 1, 1));
-            std::vector<double> neg(B, -1.0);
-            HX_TRY(add(b, neg, w, r)); // r = b - A x
+            HX_TRY(add(b, d_nalpha, w, r)); // r = b - A x   (d_nalpha holds -1 here)
             HX_TRY(op_apply(PC, r, z, B, 0, 0));
             HX_CUDA(cudaMemcpyAsync(pd, z, nloc * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
           }
         else
           {
             HX_TRY(op_apply(A, pd, w, B, 1, 1));
-            HX_TRY(reduce(z, r, zdotr.data()));
-            HX_TRY(reduce(pd, w, pdotw.data()));
-            for (uint32_t j = 0; j < B; ++j)
-              coef[j] = zdotr[j] / pdotw[j];
-            HX_TRY(add(x, coef, pd, x)); // x += alpha p
-            for (uint32_t j = 0; j < B; ++j)
-              coef[j] = -zdotr[j] / pdotw[j];
-            HX_TRY(add(r, coef, w, r)); // r -= alpha w
+            HX_TRY(reduce(z, r, d_zdotr));
+            HX_TRY(reduce(pd, w, d_pdotw));
+            HX_TRY(launch_col_divide(p, d_zdotr, d_pdotw, d_alpha, d_nalpha, B)); // alpha = z.r / p.w
+            HX_TRY(add(x, d_alpha, pd, x));                                        // x += alpha p
+            HX_TRY(add(r, d_nalpha, w, r));                                        // r -= alpha w
             HX_TRY(op_apply(PC, r, z, B, 0, 0));
-            HX_TRY(reduce(z, r, zdotr_new.data()));
-            for (uint32_t j = 0; j < B; ++j)
-              coef[j] = zdotr_new[j] / zdotr[j];
-            HX_TRY(add(z, coef, pd, pd)); // p = z + beta p
+            HX_TRY(reduce(z, r, d_zdotr_new));
+            HX_TRY(launch_col_divide(p, d_zdotr_new, d_zdotr, d_beta, nullptr, B)); // beta = z.r (new) / z.r
+            HX_TRY(add(z, d_beta, pd, pd));                                         // p = z + beta p
           }
-        HX_TRY(reduce(r, r, rnorm.data()));
+        HX_TRY(reduce(r, r, d_rr));
+        HX_TRY(fetch(d_rr, rnorm.data()));
         for (uint32_t j = 0; j < B; ++j)
           {
             rnorm[j] = sqrt(rnorm[j]);

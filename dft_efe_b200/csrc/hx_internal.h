@@ -352,6 +352,7 @@ namespace hx
   int launch_p2c(hx_plan *p, double *X, uint32_t B, uint32_t set = 0);
   int launch_c2p(hx_plan *p, double *Y, uint32_t B, uint32_t set = 0);
   int launch_coldot(hx_plan *p, const double *x, const double *y, uint32_t B, size_t nrows, double *out_dev);
+  int launch_col_divide(hx_plan *p, const double *num, const double *den, double *out, double *out_neg, uint32_t B);
   int launch_zero_constrained(hx_plan *p, double *Y, uint32_t B, uint32_t set = 0);
   int launch_pack(hx_plan *p, const double *x, uint32_t B, const uint32_t *ids, uint32_t n, double *buf);
   int launch_unpack(hx_plan *p, const double *buf, uint32_t B, const uint32_t *ids, uint32_t n, double *x);

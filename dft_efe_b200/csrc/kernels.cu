@@ -300,6 +300,27 @@ namespace hx
     return HX_OK;
   }
 
+  // per-column quotient of two reduction results, kept on the device (step lengths of the CG solver)
+  __global__ void
+  col_divide_kernel(const double *num, const double *den, double *out, double *out_neg, uint32_t B)
+  {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= B)
+      return;
+    const double q = num[j] / den[j];
+    out[j]         = q;
+    if (out_neg)
+      out_neg[j] = -q;
+  }
+  int
+  launch_col_divide(hx_plan *p, const double *num, const double *den, double *out, double *out_neg, uint32_t B)
+  {
+    col_divide_kernel<<<nblk(B), 256, 0, p->stream>>>(num, den, out, out_neg, B);
+    p->launches++;
+    HX_CUDA(cudaGetLastError());
+    return HX_OK;
+  }
+
   // ---- shared-row (enrichment) reduction after the coloured scatter --------------------------------
   __global__ void
   shared_reduce_kernel(double *Y, const double *stage, const uint32_t *rows, const uint32_t *off,
