@@ -28,6 +28,8 @@ EXPORTS = [
     "hx_residual_chebyshev_filter", "hx_xtopx", "hx_subspace_rotation", "hx_l2_norms", "hx_axpby",
     "hx_axpby_blocked", "hx_plan_launch_count", "hx_plan_cell_kernel_time_ms", "hx_plan_enable_kernel_timing", "hx_plan_trace", "hx_plan_trace_report",
     "hx_microbench",
+    "hx_xtopx_device", "hx_subspace_rotation_device", "hx_dense_cholesky_inverse", "hx_dense_sym_eig",
+    "hx_cholesky_gram_schmidt", "hx_rayleigh_ritz", "hx_chfsi_solve", "hx_eigen_residual_norms", "hx_lanczos_extreme",
 ]
 
 
@@ -409,6 +411,94 @@ def cg_solve(A: Op, PC: Op, b: DeviceBlock, x: DeviceBlock, max_iter, abs_tol, r
     check(lib().hx_cg_solve(A.h, PC.h, b.p, x.p, C.c_uint32(b.B), C.c_uint32(max_iter), C.c_double(abs_tol),
                             C.c_double(rel_tol), C.c_double(div_tol), C.byref(it), C.byref(st), rn.ctypes.data_as(f64p)))
     return it.value, st.value, rn
+
+
+# ---- the eigensolve around the path (device-resident) ----
+EIG_SUCCESS, EIG_LAPACK_ERROR, EIG_LANCZOS_BETA_ZERO, EIG_LANCZOS_SUBSPACE_INSUFFICIENT = 0, 1, 2, 3
+EIG_CHFSI_ORTHONORMALIZATION_ERROR, EIG_CHFSI_RAYLEIGH_RITZ_ERROR = 4, 5
+
+
+class DenseMatrix(DeviceBlock):
+    """B x B column-major matrix in device memory."""
+
+    def __init__(self, B: int, host: Optional[np.ndarray] = None):
+        super().__init__(B, B, None if host is None else np.asfortranarray(host).T)
+
+    def download(self) -> np.ndarray:  # as a [row, col] numpy array
+        return super().download().T.copy()
+
+
+def xtopx_device(op: Op, X: DeviceBlock, batch: int) -> DenseMatrix:
+    S = DenseMatrix(X.B)
+    check(lib().hx_xtopx_device(op.h, X.p, C.c_uint32(X.B), C.c_uint32(batch), S.p))
+    return S
+
+
+def subspace_rotation_device(plan: Plan, X: DeviceBlock, Q: DenseMatrix, transpose: bool, lower_tri: bool):
+    check(lib().hx_subspace_rotation_device(plan.h, X.p, C.c_uint32(X.B), Q.p, C.c_int(int(transpose)),
+                                            C.c_int(int(lower_tri))))
+
+
+def dense_cholesky_inverse(plan: Plan, S: DenseMatrix) -> int:
+    info = C.c_int()
+    check(lib().hx_dense_cholesky_inverse(plan.h, S.p, C.c_uint32(S.B), C.byref(info)))
+    return info.value
+
+
+def dense_sym_eig(plan: Plan, S: DenseMatrix):
+    info = C.c_int()
+    w = np.zeros(S.B)
+    check(lib().hx_dense_sym_eig(plan.h, S.p, C.c_uint32(S.B), w.ctypes.data_as(f64p), C.byref(info)))
+    return w, info.value
+
+
+def cholesky_gram_schmidt(Bop: Op, X: DeviceBlock, ortho: DeviceBlock, batch: int) -> int:
+    st = C.c_int()
+    check(lib().hx_cholesky_gram_schmidt(Bop.h, X.p, ortho.p, C.c_uint32(X.B), C.c_uint32(batch), C.byref(st)))
+    return st.value
+
+
+def rayleigh_ritz(A: Op, X: DeviceBlock, vecs: DeviceBlock, batch: int, compute_vectors=True):
+    st = C.c_int()
+    w = np.zeros(X.B)
+    check(lib().hx_rayleigh_ritz(A.h, X.p, vecs.p, C.c_uint32(X.B), C.c_uint32(batch), w.ctypes.data_as(f64p),
+                                 C.c_int(int(compute_vectors)), C.byref(st)))
+    return w, st.value
+
+
+def chfsi_solve(A: Op, Bop: Op, BInv: Op, guess: DeviceBlock, vecs: DeviceBlock, batch, degree, a0, a, b,
+                eigenvalues=None, residual_filter=False, compute_vectors=True):
+    """ChebyshevFilteredEigenSolver::solve: returns (Ritz values, EigenSolverErrorCode)."""
+    st = C.c_int()
+    w = np.zeros(guess.B) if eigenvalues is None else np.ascontiguousarray(eigenvalues, dtype=np.float64).copy()
+    check(lib().hx_chfsi_solve(A.h, Bop.h, BInv.h, guess.p, vecs.p, C.c_uint32(guess.B), C.c_uint32(batch),
+                               C.c_uint32(degree), C.c_double(a0), C.c_double(a), C.c_double(b),
+                               C.c_int(int(residual_filter)), w.ctypes.data_as(f64p), C.c_int(int(compute_vectors)),
+                               C.byref(st)))
+    return w, st.value
+
+
+def eigen_residual_norms(A: Op, Mop: Op, X: DeviceBlock, eigenvalues, batch) -> np.ndarray:
+    e, ep = _f64(eigenvalues)
+    out = np.zeros(X.B)
+    check(lib().hx_eigen_residual_norms(A.h, Mop.h, X.p, C.c_uint32(X.B), C.c_uint32(batch), ep,
+                                        out.ctypes.data_as(f64p)))
+    return out
+
+
+def lanczos_extreme(A: Op, Bop: Op, BInv: Op, guess: DeviceBlock, max_krylov, n_lower=1, n_upper=1, tol=None,
+                    beta_tol=1e-14, adaptive=False):
+    """LanczosExtremeEigenSolver::solve (eigenvalues only): returns (eigenvalues, diagonal, subdiagonal, status)."""
+    assert guess.B == 1
+    ev = np.zeros(n_lower + n_upper)
+    diag, sub = np.zeros(max_krylov), np.zeros(max_krylov)
+    k, st = C.c_uint32(), C.c_int()
+    t, tp = _f64(np.full(n_lower + n_upper, 1e-6) if tol is None else tol)
+    check(lib().hx_lanczos_extreme(A.h, Bop.h, BInv.h, guess.p, C.c_uint32(max_krylov), C.c_uint32(n_lower),
+                                   C.c_uint32(n_upper), tp, C.c_double(beta_tol), C.c_int(int(adaptive)),
+                                   ev.ctypes.data_as(f64p), diag.ctypes.data_as(f64p), sub.ctypes.data_as(f64p),
+                                   C.byref(k), C.byref(st)))
+    return ev, diag[:k.value], sub[:k.value], st.value
 
 
 def comm_unique_id() -> bytes:

@@ -108,7 +108,7 @@ namespace hx
     h.peer = nullptr;
   }
 
-  static int
+  int
   halo_update(hx_plan *p, Halo &h, double *X, uint32_t B)
   {
     if (p->nranks == 1)
@@ -612,7 +612,7 @@ namespace hx
     return HX_OK;
   }
 
-  static int
+  int
   op_apply(hx_op *op, double *X, double *Y, uint32_t B, int ugx, int ugy)
   {
     HX_CHECK(op && X && Y, HX_ERR_INVALID, "null argument");
@@ -633,7 +633,7 @@ namespace hx
     const uint32_t c = (uint32_t)(i % ncols);
     dst[r * lddst + c0d + c] = src[r * ldsrc + c0s + c];
   }
-  static int
+  int
   copy_cols(hx_plan *p, const double *src, uint32_t ldsrc, uint32_t c0s, double *dst, uint32_t lddst, uint32_t c0d,
             uint32_t ncols, size_t nrows)
   {
@@ -682,6 +682,8 @@ hx_plan::~hx_plan()
     cudaEventDestroy(e);
   if (comm)
     comm_destroy(comm);
+  if (dense)
+    dense_destroy(dense);
   if (own_stream && stream)
     cudaStreamDestroy(stream);
 }
@@ -968,11 +970,6 @@ extern "C"
       memcpy(weights, plan->h_par_w.data(), sizeof(double) * plan->h_par_w.size());
     return HX_OK;
   }
-
-#define HX_CHECK_B(plan, B)                                                                        \
-  HX_CHECK((plan) != nullptr, HX_ERR_INVALID, "null plan");                                        \
-  HX_CHECK((B) >= 1 && (B) <= (plan)->max_block, HX_ERR_INVALID, "B = %u outside [1, max_block = %u]", (B), \
-           (plan)->max_block)
 
   int
   hx_update_ghost_values(hx_plan *plan, double *X, uint32_t B)

@@ -1,0 +1,478 @@
+// eigen.cu — the callers of the H.X path inside one Kohn-Sham eigensolve, kept on the device end to end:
+//
+//   hx_xtopx_device / hx_subspace_rotation_device   projected matrix and rotation matrix stay in HBM
+//   hx_cholesky_gram_schmidt   OrthonormalizationFunctions::CholeskyGramSchmidt
+//                              (src/linearAlgebra/OrthonormalizationFunctions.t.cpp:154-352)
+//   hx_rayleigh_ritz           RayleighRitzEigenSolver::solve, standard problem
+//                              (src/linearAlgebra/RayleighRitzEigenSolver.t.cpp:70-290)
+//   hx_chfsi_solve             ChebyshevFilteredEigenSolver::solve: column-batched filter -> CholGS -> RR
+//                              (src/linearAlgebra/ChebyshevFilteredEigenSolver.t.cpp:189-438)
+//   hx_lanczos_extreme         LanczosExtremeEigenSolver::solve, eigenvalues only
+//                              (src/linearAlgebra/LanczosExtremeEigenSolver.t.cpp:216-520)
+//   hx_eigen_residual_norms    KohnShamEigenSolver::getLinearEigenSolveResidual
+//                              (src/ksdft/KohnShamEigenSolver.t.cpp:574-682)
+//
+// The dense B x B steps (Cholesky, triangular inverse, symmetric eigenproblem) are cuSOLVER calls (dense.cu), the
+// counterpart of the reference's ELPA / ScaLAPACK calls.
+#include <math.h>
+
+#include <algorithm>
+
+#include "hx_internal.h"
+
+namespace hx
+{
+  static int
+  dense_buffers(hx_plan *p, uint32_t B)
+  {
+    const size_t n = (size_t)B * B;
+    if (p->d_dense_s.n < n)
+      HX_TRY(p->d_dense_s.alloc(n));
+    if (p->d_dense_q.n < n)
+      HX_TRY(p->d_dense_q.alloc(n));
+    if (p->d_dense_w.n < B)
+      HX_TRY(p->d_dense_w.alloc(B));
+    return HX_OK;
+  }
+
+  // computeXTransOpX with the result left on the device: S (B x B column-major), lower triangle written, strict
+  // upper triangle zero; summed over ranks.
+  static int
+  xtopx_device(hx_op *op, double *X, uint32_t B, uint32_t batch, double *S)
+  {
+    hx_plan *p = op->plan;
+    batch      = std::max(1u, std::min(batch, B));
+    double *xin, *xout;
+    HX_TRY(p->get_scratch(2, &xin));
+    HX_TRY(p->get_scratch(3, &xout));
+    HX_TRY(p->ensure_small((size_t)B * batch * 3 + (size_t)604 * 4096));
+    for (uint32_t j0 = 0; j0 < B; j0 += batch)
+      {
+        const uint32_t b = std::min(batch, B - j0);
+        HX_TRY(copy_cols(p, X, B, j0, xin, b, 0, b, p->n_local));
+        HX_TRY(op_apply(op, xin, xout, b, 1, 0));
+        double *Sd = p->d_small.p;
+        HX_TRY(gram_block(p, X, B, j0, xout, b, p->n_owned, Sd));
+        if (p->nranks > 1)
+          HX_TRY(comm_allreduce_sum(p->comm, p->stream, Sd, (size_t)(B - j0) * b));
+        // columns [j0, j0+b) of S: rows >= column kept, the rest zero
+        HX_TRY(dense_place_gram_block(p, Sd, B - j0, b, j0, S, B));
+        // the reference copies the (possibly constraint-filled) batch back into X
+        HX_TRY(copy_cols(p, xin, b, 0, X, B, j0, b, p->n_local));
+      }
+    return HX_OK;
+  }
+
+  // X[dof,:] <- X[dof,:] . Q (rotationMatTranspose) or . Q^T, Q a DEVICE column-major B x B matrix
+  static int
+  rotation_device(hx_plan *p, double *X, uint32_t B, const double *Q_dev, int transpose, int lowerTri)
+  {
+    double *tmp;
+    HX_TRY(p->get_scratch(2, &tmp));
+    const double *qeff = Q_dev; // row-major Qeff[i*B+j] = Q(j,i): the column-major storage of Q itself
+    if (transpose)
+      {
+        // Qeff[i*B+j] = Q(i,j): the transpose of the storage
+        HX_CHECK(Q_dev != p->d_dense_q.p, HX_ERR_INVALID, "rotation matrix aliases the transpose scratch");
+        HX_TRY(dense_buffers(p, B));
+        HX_TRY(dense_transpose(p, Q_dev, p->d_dense_q.p, B));
+        qeff = p->d_dense_q.p;
+      }
+    return rotate(p, X, B, p->n_owned, qeff, transpose, lowerTri, tmp);
+  }
+
+  enum
+  {
+    ORTHO_SUCCESS           = 0,
+    ORTHO_LAPACK_ERROR      = 1,
+    ORTHO_NON_ORTHONORMALIZABLE = 2,
+  };
+
+  static int
+  cholesky_gram_schmidt(hx_op *Bop, double *X, double *orthoX, uint32_t B, uint32_t batch, int *status)
+  {
+    hx_plan *p = Bop->plan;
+    HX_TRY(dense_buffers(p, B));
+    double *S = p->d_dense_s.p;
+    HX_TRY(xtopx_device(Bop, X, B, batch, S)); // X^T M X, lower triangle
+    int info = 0;
+    HX_TRY(dense_cholesky_inverse(p, S, B, &info)); // S <- L^-1
+    if (info != 0)
+      {
+        *status = ORTHO_LAPACK_ERROR;
+        set_error("Cholesky factorisation / triangular inverse of X^T M X failed (info = %d)", info);
+        return HX_OK;
+      }
+    // the reference refuses a factor with a diagonal entry below 1e-14 (OrthonormalizationFunctions.t.cpp:279-308):
+    // on L^-1 that is a diagonal entry above 1e14
+    HX_TRY(p->ensure_pinned((size_t)B * sizeof(double)));
+    HX_CUDA(cudaMemcpy2DAsync(p->h_pinned, sizeof(double), S, ((size_t)B + 1) * sizeof(double), sizeof(double), B,
+                              cudaMemcpyDeviceToHost, p->stream));
+    HX_CUDA(cudaStreamSynchronize(p->stream));
+    for (uint32_t i = 0; i < B; ++i)
+      if (!(fabs(p->h_pinned[i]) < 1e14))
+        {
+          *status = ORTHO_NON_ORTHONORMALIZABLE;
+          set_error("Chol GS cannot orthogonalize the given multivector (L(%u,%u) below 1e-14)", i, i);
+          return HX_OK;
+        }
+    // XOrth^T = L^-1 X^T: subspaceRotation(X, LInv, rotationMatTranspose = false, isRotationMatLowerTria = true)
+    HX_TRY(rotation_device(p, X, B, S, 0, 1));
+    if (orthoX != X)
+      HX_CUDA(cudaMemcpyAsync(orthoX, X, (size_t)p->n_local * B * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
+    *status = ORTHO_SUCCESS;
+    return HX_OK;
+  }
+
+  static int
+  rayleigh_ritz(hx_op *A, double *X, double *eigvecs, uint32_t B, uint32_t batch, double *evals_host,
+                int compute_vectors, int *status)
+  {
+    hx_plan *p = A->plan;
+    HX_TRY(dense_buffers(p, B));
+    double *S = p->d_dense_s.p;
+    HX_TRY(xtopx_device(A, X, B, batch, S)); // X^T H X, lower triangle
+    int info = 0;
+    HX_TRY(dense_sym_eig(p, S, B, p->d_dense_w.p, &info)); // S <- Q
+    HX_CUDA(cudaMemcpyAsync(evals_host, p->d_dense_w.p, B * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    HX_CUDA(cudaStreamSynchronize(p->stream));
+    if (info != 0)
+      {
+        *status = 1;
+        set_error("symmetric eigenproblem of X^T H X failed (info = %d)", info);
+        return HX_OK;
+      }
+    if (compute_vectors)
+      {
+        // X_febasis = X_O Q: subspaceRotation(X, Q^T, rotationMatTranspose = false) of the reference
+        HX_TRY(rotation_device(p, X, B, S, 1, 0));
+        if (eigvecs != X)
+          HX_CUDA(cudaMemcpyAsync(eigvecs, X, (size_t)p->n_local * B * sizeof(double), cudaMemcpyDeviceToDevice,
+                                  p->stream));
+      }
+    *status = 0;
+    return HX_OK;
+  }
+
+  // eigenvalues of a real symmetric k x k matrix (row-major, destroyed) by cyclic Jacobi rotations, ascending.
+  // Used for the Lanczos tridiagonal matrix (k <= a few hundred), where the reference calls lapack steqr.
+  static bool
+  jacobi_eigenvalues(std::vector<double> &a, uint32_t k, std::vector<double> &w)
+  {
+    auto A = [&](uint32_t i, uint32_t j) -> double & { return a[(size_t)i * k + j]; };
+    for (int sweep = 0; sweep < 100; ++sweep)
+      {
+        double off = 0.0, diag = 0.0;
+        for (uint32_t i = 0; i < k; ++i)
+          {
+            diag += A(i, i) * A(i, i);
+            for (uint32_t j = i + 1; j < k; ++j)
+              off += A(i, j) * A(i, j);
+          }
+        if (off <= 1e-32 * (diag + off) || off == 0.0)
+          {
+            w.resize(k);
+            for (uint32_t i = 0; i < k; ++i)
+              w[i] = A(i, i);
+            std::sort(w.begin(), w.end());
+            return true;
+          }
+        for (uint32_t pi = 0; pi + 1 < k; ++pi)
+          for (uint32_t q = pi + 1; q < k; ++q)
+            {
+              const double apq = A(pi, q);
+              if (apq == 0.0)
+                continue;
+              const double theta = (A(q, q) - A(pi, pi)) / (2.0 * apq);
+              const double t     = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+              const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+              for (uint32_t r = 0; r < k; ++r)
+                {
+                  const double arp = A(r, pi), arq = A(r, q);
+                  A(r, pi) = c * arp - s * arq;
+                  A(r, q)  = s * arp + c * arq;
+                }
+              for (uint32_t r = 0; r < k; ++r)
+                {
+                  const double apr = A(pi, r), aqr = A(q, r);
+                  A(pi, r) = c * apr - s * aqr;
+                  A(q, r)  = s * apr + c * aqr;
+                }
+            }
+      }
+    return false;
+  }
+} // namespace hx
+
+using namespace hx;
+
+extern "C"
+{
+  int
+  hx_xtopx_device(hx_op *op, double *X, uint32_t B, uint32_t batch, double *S_dev)
+  {
+    HX_CHECK(op && X && S_dev, HX_ERR_INVALID, "null argument");
+    HX_CHECK_B(op->plan, B);
+    HX_CHECK(batch >= 1, HX_ERR_INVALID, "batch must be >= 1");
+    return xtopx_device(op, X, B, batch, S_dev);
+  }
+
+  int
+  hx_subspace_rotation_device(hx_plan *plan, double *X, uint32_t B, const double *Q_dev, int rotationMatTranspose,
+                              int isRotationMatLowerTria)
+  {
+    HX_CHECK(plan && X && Q_dev, HX_ERR_INVALID, "null argument");
+    HX_CHECK_B(plan, B);
+    return rotation_device(plan, X, B, Q_dev, rotationMatTranspose, isRotationMatLowerTria);
+  }
+
+  int
+  hx_dense_cholesky_inverse(hx_plan *plan, double *S_dev, uint32_t B, int *info)
+  {
+    HX_CHECK(plan && S_dev && info && B >= 1, HX_ERR_INVALID, "null argument");
+    return dense_cholesky_inverse(plan, S_dev, B, info);
+  }
+
+  int
+  hx_dense_sym_eig(hx_plan *plan, double *S_dev, uint32_t B, double *eigenvalues_host, int *info)
+  {
+    HX_CHECK(plan && S_dev && eigenvalues_host && info && B >= 1, HX_ERR_INVALID, "null argument");
+    HX_TRY(dense_buffers(plan, B));
+    HX_TRY(dense_sym_eig(plan, S_dev, B, plan->d_dense_w.p, info));
+    HX_CUDA(cudaMemcpyAsync(eigenvalues_host, plan->d_dense_w.p, B * sizeof(double), cudaMemcpyDeviceToHost, plan->stream));
+    HX_CUDA(cudaStreamSynchronize(plan->stream));
+    return HX_OK;
+  }
+
+  int
+  hx_cholesky_gram_schmidt(hx_op *Bop, double *X, double *orthogonalizedX, uint32_t B, uint32_t batch, int *status)
+  {
+    HX_CHECK(Bop && X && orthogonalizedX && status, HX_ERR_INVALID, "null argument");
+    HX_CHECK_B(Bop->plan, B);
+    HX_CHECK(batch >= 1, HX_ERR_INVALID, "batch must be >= 1");
+    return cholesky_gram_schmidt(Bop, X, orthogonalizedX, B, batch, status);
+  }
+
+  int
+  hx_rayleigh_ritz(hx_op *A, double *X, double *eigenVectors, uint32_t B, uint32_t batch, double *eigenvalues_host,
+                   int computeEigenVectors, int *status)
+  {
+    HX_CHECK(A && X && eigenvalues_host && status, HX_ERR_INVALID, "null argument");
+    HX_CHECK(!computeEigenVectors || eigenVectors, HX_ERR_INVALID, "eigenVectors is null");
+    HX_CHECK_B(A->plan, B);
+    HX_CHECK(batch >= 1, HX_ERR_INVALID, "batch must be >= 1");
+    return rayleigh_ritz(A, X, eigenVectors, B, batch, eigenvalues_host, computeEigenVectors, status);
+  }
+
+  int
+  hx_chfsi_solve(hx_op *A, hx_op *Bop, hx_op *BInv, double *eigenSubspaceGuess, double *eigenVectors, uint32_t B,
+                 uint32_t batch, uint32_t degree, double wantedLower, double wantedUpper, double unwantedUpper,
+                 int residualFilter, double *eigenvalues_host, int computeEigenVectors, int *status)
+  {
+    HX_CHECK(A && Bop && BInv && eigenSubspaceGuess && eigenVectors && eigenvalues_host && status, HX_ERR_INVALID,
+             "null argument");
+    hx_plan *p = A->plan;
+    HX_CHECK(p == Bop->plan && p == BInv->plan, HX_ERR_INVALID, "operators belong to different plans");
+    HX_CHECK_B(p, B);
+    HX_CHECK(batch >= 1 && eigenSubspaceGuess != eigenVectors, HX_ERR_INVALID, "bad batch / aliasing blocks");
+    batch = std::min(batch, B);
+    double *xin, *xout;
+    HX_TRY(p->get_scratch(4, &xin));
+    HX_TRY(p->get_scratch(5, &xout));
+    // [CF] column-batched filter (ChebyshevFilteredEigenSolver.t.cpp:231-335): the batch is copied out of the guess,
+    // filtered, and copied into BOTH blocks
+    for (uint32_t j0 = 0; j0 < B; j0 += batch)
+      {
+        const uint32_t b = std::min(batch, B - j0);
+        double *       in = xin, *out = xout;
+        if (b == B)
+          in = eigenSubspaceGuess, out = eigenVectors; // a single batch needs no strided copies
+        else
+          HX_TRY(copy_cols(p, eigenSubspaceGuess, B, j0, in, b, 0, b, p->n_local));
+        if (residualFilter)
+          HX_TRY(hx_residual_chebyshev_filter(A, Bop, BInv, eigenvalues_host + j0, in, out, b, degree, wantedLower,
+                                              wantedUpper, unwantedUpper));
+        else
+          HX_TRY(hx_chebyshev_filter(A, BInv, in, out, b, degree, wantedLower, wantedUpper, unwantedUpper));
+        if (b != B)
+          {
+            HX_TRY(copy_cols(p, out, b, 0, eigenVectors, B, j0, b, p->n_local));
+            HX_TRY(copy_cols(p, in, b, 0, eigenSubspaceGuess, B, j0, b, p->n_local));
+          }
+      }
+    // [O] X -> X_O, M-orthonormal (CHOLESKY_GRAMSCHMIDT branch, :352-358)
+    int ostat = 0;
+    HX_TRY(cholesky_gram_schmidt(Bop, eigenVectors, eigenSubspaceGuess, B, batch, &ostat));
+    if (ostat != ORTHO_SUCCESS)
+      {
+        *status = 4; // EigenSolverErrorCode::CHFSI_ORTHONORMALIZATION_ERROR
+        return HX_OK;
+      }
+    // [RR] (:393-397)
+    int rstat = 0;
+    HX_TRY(rayleigh_ritz(A, eigenSubspaceGuess, eigenVectors, B, batch, eigenvalues_host, computeEigenVectors, &rstat));
+    *status = rstat ? 5 /* CHFSI_RAYLEIGH_RITZ_ERROR */ : 0;
+    return HX_OK;
+  }
+
+  int
+  hx_eigen_residual_norms(hx_op *A, hx_op *Mop, const double *X, uint32_t B, uint32_t batch,
+                          const double *eigenvalues_host, double *norms_host)
+  {
+    HX_CHECK(A && Mop && X && eigenvalues_host && norms_host, HX_ERR_INVALID, "null argument");
+    hx_plan *p = A->plan;
+    HX_CHECK(p == Mop->plan, HX_ERR_INVALID, "operators belong to different plans");
+    HX_CHECK_B(p, B);
+    HX_CHECK(batch >= 1, HX_ERR_INVALID, "batch must be >= 1");
+    batch = std::min(std::min(batch, B), 256u);
+    double *xb, *hx, *mx;
+    HX_TRY(p->get_scratch(4, &xb));
+    HX_TRY(p->get_scratch(5, &hx));
+    HX_TRY(p->get_scratch(6, &mx));
+    std::vector<double> nones(batch, -1.0);
+    for (uint32_t j0 = 0; j0 < B; j0 += batch)
+      {
+        const uint32_t b = std::min(batch, B - j0);
+        HX_TRY(copy_cols(p, X, B, j0, xb, b, 0, b, p->n_local));
+        HX_TRY(op_apply(A, xb, hx, b, 1, 1));
+        HX_TRY(op_apply(Mop, xb, mx, b, 1, 1));
+        // XBatch = -1 * HX + lambda * MX over the local rows (KohnShamEigenSolver.t.cpp:657-668)
+        HX_TRY(hx_axpby_blocked(p, p->n_local, b, 1.0, nones.data(), hx, 1.0, eigenvalues_host + j0, mx, xb));
+        HX_TRY(hx_l2_norms(p, xb, b, norms_host + j0));
+      }
+    return HX_OK;
+  }
+
+  int
+  hx_lanczos_extreme(hx_op *A, hx_op *Bop, hx_op *BInv, const double *initialGuess, uint32_t maxKrylovSubspaceSize,
+                     uint32_t numLower, uint32_t numUpper, const double *tolerance, double lanczosBetaTolerance,
+                     int adaptive, double *eigenvalues_host, double *diagonal_host, double *subDiagonal_host,
+                     uint32_t *krylovSize, int *status)
+  {
+    HX_CHECK(A && Bop && BInv && initialGuess && eigenvalues_host && krylovSize && status, HX_ERR_INVALID,
+             "null argument");
+    hx_plan *p = A->plan;
+    HX_CHECK(p == Bop->plan && p == BInv->plan, HX_ERR_INVALID, "operators belong to different plans");
+    const uint32_t nWanted = numLower + numUpper;
+    HX_CHECK(nWanted >= 1 && maxKrylovSubspaceSize >= nWanted, HX_ERR_INVALID,
+             "Maximum Krylov subspace size should be more than number of required eigenPairs.");
+    HX_CHECK(!adaptive || tolerance, HX_ERR_INVALID, "adaptive solve needs tolerances");
+    const size_t nloc = p->n_local, nown = p->n_owned;
+    double *     guess, *temp, *v, *q, *qprev;
+    HX_TRY(p->get_scratch(2, &guess)); // the reference's operators may modify their input: work on a copy
+    HX_TRY(p->get_scratch(3, &temp));
+    HX_TRY(p->get_scratch(4, &v));
+    HX_TRY(p->get_scratch(5, &q));
+    HX_TRY(p->get_scratch(6, &qprev));
+    HX_TRY(p->ensure_small((size_t)600 + 8));
+    double *d_dot = p->d_small.p + 600;
+    HX_TRY(p->ensure_pinned(sizeof(double)));
+    auto dot = [&](const double *a, const double *b, double *out) -> int {
+      HX_TRY(launch_coldot(p, a, b, 1, nown, d_dot));
+      if (p->nranks > 1)
+        HX_TRY(comm_allreduce_sum(p->comm, p->stream, d_dot, 1));
+      HX_CUDA(cudaMemcpyAsync(p->h_pinned, d_dot, sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+      HX_CUDA(cudaStreamSynchronize(p->stream));
+      *out = p->h_pinned[0];
+      return HX_OK;
+    };
+    HX_CUDA(cudaMemcpyAsync(guess, initialGuess, nloc * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
+    HX_CUDA(cudaMemsetAsync(q, 0, nloc * sizeof(double), p->stream));
+    HX_CUDA(cudaMemsetAsync(qprev, 0, nloc * sizeof(double), p->stream));
+    HX_CUDA(cudaMemsetAsync(v, 0, nloc * sizeof(double), p->stream));
+    std::vector<double> alphaVec, betaVec, evPrev(nWanted, 0.0), ev;
+    double              alpha = 0.0, beta = 0.0;
+    // q = guess / sqrt(guess^T B guess)   (:283-301)
+    HX_TRY(op_apply(Bop, guess, temp, 1, 1, 1));
+    HX_TRY(dot(guess, temp, &alpha));
+    alpha = sqrt(alpha);
+    HX_TRY(launch_axpby(p, nown, 1.0 / alpha, guess, 0.0, guess, q));
+    int      err        = 11; // EigenSolverErrorCode::OTHER_ERROR
+    bool     isSuccess  = false;
+    uint32_t krylov     = 0;
+    for (uint32_t iter = 1; iter <= maxKrylovSubspaceSize; ++iter)
+      {
+        // v = BInv A q   (:310-311)
+        HX_TRY(op_apply(A, q, temp, 1, 1, 0));
+        HX_TRY(op_apply(BInv, temp, v, 1, 0, 0));
+        HX_TRY(dot(q, temp, &alpha));
+        alphaVec.push_back(alpha);
+        // v = v - alpha q - beta qPrev over the local rows (:340-355)
+        HX_TRY(launch_axpby(p, nloc, 1.0, v, -alpha, q, v));
+        HX_TRY(launch_axpby(p, nloc, 1.0, v, -beta, qprev, v));
+        // beta = sqrt(v^T B v)   (:359-368)
+        HX_TRY(op_apply(Bop, v, temp, 1, 1, 1));
+        HX_TRY(dot(v, temp, &beta));
+        beta = sqrt(beta);
+        if (beta < lanczosBetaTolerance && adaptive)
+          {
+            if (krylov >= nWanted)
+              isSuccess = true;
+            err = 2; // LANCZOS_BETA_ZERO
+            break;
+          }
+        betaVec.push_back(beta);
+        HX_CUDA(cudaMemcpyAsync(qprev, q, nloc * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
+        HX_TRY(launch_axpby(p, nown, 1.0 / beta, v, 0.0, v, q));
+        if (iter >= nWanted)
+          {
+            krylov = iter;
+            if (adaptive || iter == maxKrylovSubspaceSize)
+              {
+                // eigenvalues of tridiag(alphaVec, betaVec[0 .. iter-2])   (steqr in the reference, :395-452)
+                std::vector<double> T((size_t)iter * iter, 0.0);
+                for (uint32_t i = 0; i < iter; ++i)
+                  {
+                    T[(size_t)i * iter + i] = alphaVec[i];
+                    if (i + 1 < iter)
+                      T[(size_t)i * iter + i + 1] = T[(size_t)(i + 1) * iter + i] = betaVec[i];
+                  }
+                std::vector<double> w;
+                if (!jacobi_eigenvalues(T, iter, w))
+                  {
+                    err = 1; // LAPACK_ERROR
+                    set_error("tridiagonal eigenproblem of the Lanczos matrix did not converge");
+                    break;
+                  }
+                ev.assign(nWanted, 0.0);
+                for (uint32_t i = 0; i < numLower; ++i)
+                  ev[i] = w[i];
+                for (uint32_t i = 0; i < numUpper; ++i)
+                  ev[numLower + i] = w[iter - numUpper + i];
+                if (adaptive)
+                  {
+                    bool all = true;
+                    for (uint32_t i = 0; i < nWanted; ++i)
+                      all = all && fabs(evPrev[i] - ev[i]) <= tolerance[i];
+                    if (all)
+                      {
+                        err = 0, isSuccess = true;
+                        break;
+                      }
+                    evPrev = ev;
+                  }
+                else
+                  {
+                    err = 0, isSuccess = true;
+                    break;
+                  }
+              }
+          }
+      }
+    if (krylov >= maxKrylovSubspaceSize && adaptive && err != 0)
+      {
+        isSuccess = true;
+        err       = 3; // LANCZOS_SUBSPACE_INSUFFICIENT
+      }
+    (void)isSuccess;
+    for (uint32_t i = 0; i < nWanted && i < ev.size(); ++i)
+      eigenvalues_host[i] = ev[i];
+    if (diagonal_host)
+      memcpy(diagonal_host, alphaVec.data(), alphaVec.size() * sizeof(double));
+    if (subDiagonal_host)
+      memcpy(subDiagonal_host, betaVec.data(), betaVec.size() * sizeof(double));
+    *krylovSize = (uint32_t)alphaVec.size();
+    *status     = err;
+    return HX_OK;
+  }
+}

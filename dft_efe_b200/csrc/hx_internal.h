@@ -37,6 +37,11 @@ namespace hx
     }                               \
   while (0)
 
+#define HX_CHECK_B(plan, B)                                                                        \
+  HX_CHECK((plan) != nullptr, HX_ERR_INVALID, "null plan");                                        \
+  HX_CHECK((B) >= 1 && (B) <= (plan)->max_block, HX_ERR_INVALID, "B = %u outside [1, max_block = %u]", (B), \
+           (plan)->max_block)
+
 #define HX_TRY(call)      \
   do                      \
     {                     \
@@ -144,7 +149,8 @@ namespace hx
     uint32_t           ids_off, n, nproj, proj_off, wait_off, nwait;
   };
 
-  struct Comm; // NCCL communicator wrapper (comm.cu)
+  struct Comm;  // NCCL communicator wrapper (comm.cu)
+  struct Dense; // cuSOLVER handle + workspace (dense.cu)
 
   // one ConstraintsLocal object on the device: the reference CSR + the parent-side transpose used by the
   // deterministic child->parent pass.  Set 0 lives in the plan's own fields (the mesh's constraints); further sets
@@ -283,6 +289,8 @@ struct hx_plan
   // scratch block vectors (n_local x max_block), allocated on demand
   std::vector<hx::DevBuf<double> *> scratch;
   hx::DevBuf<double>                d_small; // small device scratch (norms, gram blocks, per-column scalars)
+  hx::DevBuf<double>                d_dense_s, d_dense_q, d_dense_w; // B x B projected matrix, rotation matrix, eigenvalues
+  hx::Dense *                       dense = nullptr;               // cuSOLVER handle + workspace (dense.cu)
   double *                          h_pinned = nullptr;
   size_t                            h_pinned_bytes = 0;
 
@@ -379,6 +387,19 @@ namespace hx
                  size_t nOwned, double *S_dev);
   int rotate(hx_plan *p, double *X, uint32_t B, size_t nOwned, const double *Q_dev, int transpose, int lowerTri,
              double *tmp);
+  // api.cu helpers shared with eigen.cu
+  int op_apply(hx_op *op, double *X, double *Y, uint32_t B, int ugx, int ugy);
+  int copy_cols(hx_plan *p, const double *src, uint32_t ldsrc, uint32_t c0s, double *dst, uint32_t lddst, uint32_t c0d,
+                uint32_t ncols, size_t nrows);
+  int halo_update(hx_plan *p, Halo &h, double *X, uint32_t B);
+  uint32_t gram_max_split(uint32_t M, uint32_t N);
+  // dense.cu: B x B subspace problems on the device (cuSOLVER, resolved with dlopen)
+  struct Dense;
+  void dense_destroy(Dense *d);
+  int  dense_cholesky_inverse(hx_plan *p, double *S_dev, uint32_t B, int *info_host);
+  int  dense_sym_eig(hx_plan *p, double *S_dev, uint32_t B, double *evals_dev, int *info_host);
+  int  dense_place_gram_block(hx_plan *p, const double *Sd, uint32_t M, uint32_t b, uint32_t j0, double *S, uint32_t B);
+  int  dense_transpose(hx_plan *p, const double *A, double *At, uint32_t B);
   // comm.cu
   int comm_unique_id(char id[128]);
   int comm_create(Comm **c, const char id[128], int nranks, int rank);

@@ -563,6 +563,17 @@ def build_problem(spec: MeshSpec, only_rank: Optional[int] = None) -> List[RankP
             np.add.at(lump_g, conn[m].ravel(), np.tile(mats[s_][2], int(m.sum())))
             np.add.at(kdiag_g, conn[m].ravel(), np.tile(np.diag(mats[s_][0]), int(m.sum())))
 
+    # The reference condenses the lumped diagonal through the constraints (distributeChildToParent: every parent
+    # collects w * child), then zeroes the constrained entries of M's diagonal
+    # (basis/OrthoEFEOverlapOperatorContext.t.cpp:1525-1535) and of the reciprocal
+    # (basis/CFEOverlapInverseOpContextGLL.t.cpp:447-466), so that M^-1 M = I on the unconstrained rows of
+    # non-conforming meshes too.
+    lump_c = lump_g.copy()
+    for n_, (cols_, ws_) in con_table.items():
+        if len(cols_):
+            np.add.at(lump_c, cols_, ws_ * lump_g[n_])
+    lump_c[constrained] = 0.0
+
     # per-atom enrichment overlap block (SPD) and projector strengths
     enr_blocks = []
     for ia in range(nA):
@@ -719,8 +730,8 @@ def build_problem(spec: MeshSpec, only_rank: Optional[int] = None) -> List[RankP
             enr_block=np.zeros(0), enr_block_inv=np.zeros(0), local_to_global=l2g.astype(U64))
         # lumped mass on classical local rows
         clm = l2g < Ncl
-        prob.diag[clm] = lump_g[gid_to_node[l2g[clm]]]
-        prob.diag_inv = 1.0 / prob.diag
+        prob.diag[clm] = lump_c[gid_to_node[l2g[clm]]]
+        prob.diag_inv = np.where(prob.diag != 0.0, 1.0 / np.where(prob.diag != 0.0, prob.diag, 1.0), 0.0)
         prob.k_cell = k_cell
         prob.k_diag = np.ones(halo.n_local)
         prob.k_diag[clm] = kdiag_g[gid_to_node[l2g[clm]]]

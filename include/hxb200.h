@@ -236,6 +236,51 @@ int hx_axpby(hx_plan *plan, uint32_t n_rows, uint32_t B, double alpha, const dou
 int hx_axpby_blocked(hx_plan *plan, uint32_t n_rows, uint32_t B, double alpha1, const double *alpha_host,
                      const double *x, double beta1, const double *beta_host, const double *y, double *z);
 
+/* ---- the eigensolve around the path, device-resident (8f rank 4) ---- */
+/* computeXTransOpX with the projected matrix left on the DEVICE: S_dev is B x B column-major, lower triangle written,
+ * strict upper triangle zero, summed over ranks (no D2H / host scatter, RayleighRitzEigenSolver.t.cpp:798-836). */
+int hx_xtopx_device(hx_op *op, double *X, uint32_t B, uint32_t batch, double *S_dev);
+/* subspaceRotation with a DEVICE rotation matrix (column-major B x B, replicated on every rank). */
+int hx_subspace_rotation_device(hx_plan *plan, double *X, uint32_t B, const double *Q_dev, int rotationMatTranspose,
+                                int isRotationMatLowerTria);
+/* Dense B x B steps on the device (cuSOLVER potrf + trtri / syevd on the plan's stream), the counterpart of
+ * elpa_cholesky + ScaLAPACKMatrix::invert (src/linearAlgebra/OrthonormalizationFunctions.t.cpp:204-309) and
+ * elpa_eigenvectors (src/linearAlgebra/RayleighRitzEigenSolver.t.cpp:154-164).
+ *   cholesky_inverse: S_dev (lower triangle of an SPD matrix) -> L^-1 with S = L L^T (lower, strict upper zero);
+ *   sym_eig:          S_dev (lower triangle of a symmetric matrix) -> eigenvectors in columns, eigenvalues ascending.
+ * info: LAPACK-style (0 = success). */
+int hx_dense_cholesky_inverse(hx_plan *plan, double *S_dev, uint32_t B, int *info);
+int hx_dense_sym_eig(hx_plan *plan, double *S_dev, uint32_t B, double *eigenvalues_host, int *info);
+/* OrthonormalizationFunctions::CholeskyGramSchmidt(X, orthogonalizedX, B) (OrthonormalizationFunctions.t.cpp:154-352):
+ * S = X^T (Bop X), S = L L^T, X <- X L^-T in place, orthogonalizedX = X.  status: OrthonormalizationErrorCode
+ * (0 SUCCESS, 1 LAPACK_ERROR, 2 NON_ORTHONORMALIZABLE_MULTIVECTOR). */
+int hx_cholesky_gram_schmidt(hx_op *Bop, double *X, double *orthogonalizedX, uint32_t B, uint32_t batch, int *status);
+/* RayleighRitzEigenSolver::solve(A, X, eigenValues, eigenVectors, computeEigenVectors), standard eigenproblem for an
+ * M-orthonormal X (RayleighRitzEigenSolver.t.cpp:70-290): X is rotated in place, eigenVectors = X.  status 0 / 1. */
+int hx_rayleigh_ritz(hx_op *A, double *X, double *eigenVectors, uint32_t B, uint32_t batch, double *eigenvalues_host,
+                     int computeEigenVectors, int *status);
+/* ChebyshevFilteredEigenSolver::solve (ChebyshevFilteredEigenSolver.t.cpp:189-438): filter eigenSubspaceGuess in
+ * column batches of `batch` (plain or residual filter; the latter reads eigenvalues_host), Cholesky-Gram-Schmidt,
+ * Rayleigh-Ritz.  On return eigenvalues_host holds the B Ritz values (ascending), eigenVectors the Ritz vectors,
+ * eigenSubspaceGuess the same block (the next pass's guess).  status: EigenSolverErrorCode (0 SUCCESS,
+ * 4 CHFSI_ORTHONORMALIZATION_ERROR, 5 CHFSI_RAYLEIGH_RITZ_ERROR).  B <= max_block. */
+int hx_chfsi_solve(hx_op *A, hx_op *Bop, hx_op *BInv, double *eigenSubspaceGuess, double *eigenVectors, uint32_t B,
+                   uint32_t batch, uint32_t degree, double wantedLower, double wantedUpper, double unwantedUpper,
+                   int residualFilter, double *eigenvalues_host, int computeEigenVectors, int *status);
+/* KohnShamEigenSolver::getLinearEigenSolveResidual (src/ksdft/KohnShamEigenSolver.t.cpp:574-682):
+ * norms[j] = || H x_j - lambda_j M x_j ||_2 over owned rows, in column batches. */
+int hx_eigen_residual_norms(hx_op *A, hx_op *Mop, const double *X, uint32_t B, uint32_t batch,
+                            const double *eigenvalues_host, double *norms_host);
+/* LanczosExtremeEigenSolver::solve, eigenvalues only (src/linearAlgebra/LanczosExtremeEigenSolver.t.cpp:216-520):
+ * B-orthogonal Lanczos on BInv A from initialGuess (DEVICE, n_local doubles, one vector).  eigenvalues_host:
+ * numLower lowest then numUpper highest Ritz values; diagonal/subDiagonal_host (maxKrylovSubspaceSize doubles each,
+ * may be NULL) receive the tridiagonal matrix (getTridiagonalMatrix), krylovSize its order.  status:
+ * EigenSolverErrorCode (0 SUCCESS, 1 LAPACK_ERROR, 2 LANCZOS_BETA_ZERO, 3 LANCZOS_SUBSPACE_INSUFFICIENT, 11 OTHER). */
+int hx_lanczos_extreme(hx_op *A, hx_op *Bop, hx_op *BInv, const double *initialGuess, uint32_t maxKrylovSubspaceSize,
+                       uint32_t numLower, uint32_t numUpper, const double *tolerance, double lanczosBetaTolerance,
+                       int adaptive, double *eigenvalues_host, double *diagonal_host, double *subDiagonal_host,
+                       uint32_t *krylovSize, int *status);
+
 /* ---- measurement hooks (bench.py / tests) ---- */
 /* Number of kernel launches issued through this plan since creation, and device time of the dominant
  * cell-contraction kernel accumulated with CUDA events on the plan's stream (reset on read). */

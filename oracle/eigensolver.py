@@ -1,0 +1,250 @@
+"""CPU restatement of the eigensolve that drives the H.X path (TEST INFRASTRUCTURE: only tests/, smoke() and
+bench.py's CPU leg may import this; nothing under dft_efe_b200/ does).
+
+Follows, step for step, on top of oracle.OracleWorld's operators:
+  * LanczosExtremeEigenSolver::solve          src/linearAlgebra/LanczosExtremeEigenSolver.t.cpp:216-520
+  * OrthonormalizationFunctions::CholeskyGramSchmidt   src/linearAlgebra/OrthonormalizationFunctions.t.cpp:154-352
+  * RayleighRitzEigenSolver::solve (standard problem)  src/linearAlgebra/RayleighRitzEigenSolver.t.cpp:70-290
+  * ChebyshevFilteredEigenSolver::solve       src/linearAlgebra/ChebyshevFilteredEigenSolver.t.cpp:189-438
+  * KohnShamEigenSolver::solve / getLinearEigenSolveResidual   src/ksdft/KohnShamEigenSolver.t.cpp:214-682
+  * FractionalOccupancyFunction, NewtonRaphsonSolver   src/ksdft/FractionalOccupancyFunction.cpp,
+                                                       src/linearAlgebra/NewtonRaphsonSolver.t.cpp:48-96
+The dense B x B steps use LAPACK through SciPy (potrf/trtri/syevd), where the reference calls ELPA / ScaLAPACK / LAPACK.
+
+Pinning: the filter, Gram, rotation, BLAS-1 and operator pieces these routines are built from are pinned against the
+reference's compiled sources (tests/test_oracle.py); the composites here are additionally checked against a dense
+generalized eigensolve of the assembled (H, M) pencil (scipy.linalg.eigh), the same kind of check the reference's own
+tests make (test/linearAlgebra/src/TestChebyshevFilteredEigenSolveHostDouble.cpp:647-666)."""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import scipy.linalg as sla
+
+# src/ksdft/Defaults.cpp:44-69
+LANCZOS_EXTREME_EIGENVAL_TOL = 1e-6
+LANCZOS_BETA_TOL = 1e-14
+LANCZOS_MAX_KRYLOV_SUBSPACE = 20
+BOLTZMANN_CONST_HARTREE = 3.166811429e-06
+NR_MAX_ITER = int(2e7)
+NR_FORCE_TOL = 1e-14
+CHEBY_ORDER_LOOKUP = [(10, 6), (50, 9), (100, 12), (200, 16), (300, 19), (500, 24), (750, 30), (1000, 39), (1500, 50),
+                      (2000, 53), (3000, 57), (4000, 62), (5000, 69), (9000, 77), (14000, 104), (20000, 119),
+                      (30000, 162), (50000, 300), (80000, 450), (100000, 550), (200000, 700), (500000, 1000)]
+
+
+def cheby_polynomial_degree(unwanted_upper: float) -> int:
+    """getChebyPolynomialDegree (KohnShamEigenSolver.t.cpp:37-46): the bound is truncated to size_type first."""
+    key = int(unwanted_upper)
+    for k, v in CHEBY_ORDER_LOOKUP:
+        if k >= key:
+            return v
+    return 1250
+
+
+def fermi_dirac(e, mu, kb, T):
+    f = (e - mu) / (kb * T)
+    return math.exp(-f) / (1.0 + math.exp(-f)) if f >= 0 else 1.0 / (1.0 + math.exp(f))
+
+
+def fermi_dirac_der(e, mu, kb, T):
+    f = (e - mu) / (kb * T)
+    beta = 1.0 / (kb * T)
+    if f >= 0:
+        return beta * math.exp(-f) / (1.0 + math.exp(-f)) / (1.0 + math.exp(-f))
+    return beta * math.exp(f) / (1.0 + math.exp(f)) / (1.0 + math.exp(f))
+
+
+def fermi_energy(eigenvalues, n_electrons, T, tol, kb=BOLTZMANN_CONST_HARTREE, max_iter=100000):
+    """FractionalOccupancyFunction + NewtonRaphsonSolver::solve.  Returns (mu, converged)."""
+    x = eigenvalues[int(math.ceil(n_electrons / 2.0)) - 1]
+    for _ in range(max_iter + 1):
+        val = sum(2.0 * fermi_dirac(e, x, kb, T) for e in eigenvalues) - float(n_electrons)
+        frc = sum(2.0 * fermi_dirac_der(e, x, kb, T) for e in eigenvalues)
+        if frc == 0.0:
+            return x, False
+        x1 = x - val / frc
+        if abs(x1 - x) < tol:
+            return x1, True
+        x = x1
+    return x, False
+
+
+def lanczos_extreme(W, apply_A, apply_B, apply_BInv, guesses, max_krylov, n_lower=1, n_upper=1, tol=None,
+                    beta_tol=LANCZOS_BETA_TOL, adaptive=False):
+    """guesses: per rank [n_local, 1].  Returns (eigenvalues, diagonal, subdiagonal, status) with status the
+    EigenSolverErrorCode value (0 SUCCESS, 2 LANCZOS_BETA_ZERO, 3 LANCZOS_SUBSPACE_INSUFFICIENT, 11 OTHER_ERROR)."""
+    n_wanted = n_lower + n_upper
+    assert max_krylov >= n_wanted
+    tol = np.full(n_wanted, LANCZOS_EXTREME_EIGENVAL_TOL) if tol is None else np.asarray(tol)
+    nown = W.n_owned
+    g = [x.copy() for x in guesses]
+    temp = [np.zeros_like(x) for x in g]
+    v = [np.zeros_like(x) for x in g]
+    q = [np.zeros_like(x) for x in g]
+    qprev = [np.zeros_like(x) for x in g]
+    alpha_vec, beta_vec = [], []
+    ev_prev = np.zeros(n_wanted)
+    ev = np.zeros(n_wanted)
+    apply_B(g, temp, True, True)
+    alpha = math.sqrt(W.col_dots(g, temp)[0])
+    for i, n in enumerate(nown):
+        q[i][:n] = (1.0 / alpha) * g[i][:n]
+    beta = 0.0
+    err, krylov = 11, 0
+    for it in range(1, max_krylov + 1):
+        apply_A(q, temp, True, False)
+        apply_BInv(temp, v, False, False)
+        alpha = W.col_dots(q, temp)[0]
+        alpha_vec.append(alpha)
+        for i in range(W.nr):
+            v[i] += (-alpha) * q[i]
+            v[i] += (-beta) * qprev[i]
+        apply_B(v, temp, True, True)
+        beta = math.sqrt(W.col_dots(v, temp)[0])
+        if beta < beta_tol and adaptive:
+            err = 2
+            break
+        beta_vec.append(beta)
+        for i, n in enumerate(nown):
+            qprev[i][...] = q[i]
+            q[i][:n] = (1.0 / beta) * v[i][:n]
+        if it >= n_wanted:
+            krylov = it
+            if adaptive or it == max_krylov:
+                w = sla.eigvalsh_tridiagonal(np.array(alpha_vec), np.array(beta_vec[:it - 1])) if it > 1 else \
+                    np.array(alpha_vec)
+                ev = np.concatenate([w[:n_lower], w[len(w) - n_upper:]])
+                if adaptive:
+                    if np.all(np.abs(ev_prev - ev) <= tol):
+                        err = 0
+                        break
+                    ev_prev = ev.copy()
+                else:
+                    err = 0
+                    break
+    if krylov >= max_krylov and adaptive and err != 0:
+        err = 3
+    return ev, np.array(alpha_vec), np.array(beta_vec), err
+
+
+def cholesky_gram_schmidt(W, Xs, apply_M, batch):
+    """X <- X L^-T with X^T M X = L L^T, in place; returns (status, L^-1)."""
+    S = W.xtopx(Xs, apply_M, batch)  # lower triangle
+    try:
+        L = sla.cholesky(S, lower=True)  # reads the lower triangle only (potrf 'L')
+    except sla.LinAlgError:
+        return 1, None
+    if np.any(np.abs(np.diag(L)) < 1e-14):
+        return 2, None
+    Linv = sla.lapack.dtrtri(L, lower=1)[0]
+    Linv = np.tril(Linv)
+    W.subspace_rotation(Xs, Linv, False, True)
+    return 0, Linv
+
+
+def rayleigh_ritz(W, Xs, apply_A, batch, compute_vectors=True):
+    S = W.xtopx(Xs, apply_A, batch)
+    full = S + S.T - np.diag(np.diag(S))  # projHam + projHam^T, diagonal halved
+    w, Q = sla.eigh(full)
+    if compute_vectors:
+        W.subspace_rotation(Xs, np.ascontiguousarray(Q.T), False, False)
+    return w, Q
+
+
+def chfsi_solve(W, guesses, eigenvalues, batch, degree, a0, a, b, apply_A=None, apply_M=None, residual_filter=False,
+                minv_variant="oefe_atomblock"):
+    """ChebyshevFilteredEigenSolver::solve.  guesses (per rank [n_local, B]) are overwritten with the Ritz vectors
+    (the next pass's guess); returns (Ritz values, status, Ritz vectors per rank)."""
+    B = guesses[0].shape[1]
+    apply_A = apply_A or (lambda Xs, Ys, gx, gy: W.hx_apply(Xs, Ys, gx, gy))
+    apply_M = apply_M or (lambda Xs, Ys, gx, gy: W.m_apply(Xs, Ys, gx, gy, minv_variant))
+    vecs = [np.zeros_like(g) for g in guesses]
+    for j0 in range(0, B, batch):
+        bb = min(batch, B - j0)
+        xin = [np.ascontiguousarray(g[:, j0:j0 + bb]) for g in guesses]
+        if residual_filter:
+            xout = W.residual_chebyshev_filter(xin, np.asarray(eigenvalues[j0:j0 + bb]), degree, a0, a, b, minv_variant)
+        else:
+            xout = W.chebyshev_filter(xin, degree, a0, a, b, minv_variant)
+            xin = xout  # eigenSubspaceGuess = filteredSubspace at the end of the plain filter
+        for r in range(W.nr):
+            vecs[r][:, j0:j0 + bb] = xout[r]
+            guesses[r][:, j0:j0 + bb] = xin[r]
+    st, _ = cholesky_gram_schmidt(W, vecs, apply_M, batch)
+    if st != 0:
+        return None, 4, vecs
+    for r in range(W.nr):
+        guesses[r][...] = vecs[r]
+    w, _ = rayleigh_ritz(W, guesses, apply_A, batch, True)
+    for r in range(W.nr):
+        vecs[r][...] = guesses[r]
+    return w, 0, vecs
+
+
+def eigen_residual_norms(W, Xs, eigenvalues, batch, apply_A=None, apply_M=None, minv_variant="oefe_atomblock"):
+    B = Xs[0].shape[1]
+    apply_A = apply_A or (lambda Xs_, Ys, gx, gy: W.hx_apply(Xs_, Ys, gx, gy))
+    apply_M = apply_M or (lambda Xs_, Ys, gx, gy: W.m_apply(Xs_, Ys, gx, gy, minv_variant))
+    out = np.zeros(B)
+    for j0 in range(0, B, batch):
+        bb = min(batch, B - j0)
+        xb = [np.ascontiguousarray(X[:, j0:j0 + bb]) for X in Xs]
+        hx = [np.zeros_like(x) for x in xb]
+        mx = [np.zeros_like(x) for x in xb]
+        apply_A(xb, hx, True, True)
+        apply_M(xb, mx, True, True)
+        lam = np.asarray(eigenvalues[j0:j0 + bb])
+        res = [-1.0 * h + lam[None, :] * m for h, m in zip(hx, mx)]
+        out[j0:j0 + bb] = W.l2_norms(res)
+    return out
+
+
+def ks_eigen_solve(W, guesses, lanczos_guesses, n_electrons, smearing_T, fermi_tol, frac_occ_tol, residual_tol,
+                   max_pass, batch, minv_variant="oefe_atomblock", residual_filter=False, degree=None, bounds=None):
+    """KohnShamEigenSolver::solve.  `bounds` = (wantedLower, wantedUpper) is reinitBounds() (d_isBoundKnown), `degree`
+    setChebyshevPolynomialDegree().  Returns a dict (eigenvalues, passes, bounds, degree, residual norms, status)."""
+    B = guesses[0].shape[1]
+    apply_A = lambda Xs, Ys, gx, gy: W.hx_apply(Xs, Ys, gx, gy)  # noqa: E731
+    apply_M = lambda Xs, Ys, gx, gy: W.m_apply(Xs, Ys, gx, gy, minv_variant)  # noqa: E731
+    apply_MInv = lambda Xs, Ys, gx, gy: W.minv_apply(Xs, Ys, gx, gy, minv_variant)  # noqa: E731
+    ev_l, diag, sub, lst = lanczos_extreme(W, apply_A, apply_M, apply_MInv, lanczos_guesses, LANCZOS_MAX_KRYLOV_SUBSPACE,
+                                           1, 1, [LANCZOS_EXTREME_EIGENVAL_TOL] * 2, LANCZOS_BETA_TOL, False)
+    if lst not in (0, 3):
+        return {"status": 8}
+    residual = sub[-1] / 10.0
+    n_global = sum(W.n_owned)
+    lower = ev_l[0]
+    unwanted = ev_l[1] + residual
+    upper = (unwanted - ev_l[0]) * (B * 200.0 / n_global) + ev_l[0]
+    if upper >= unwanted:
+        upper = (unwanted + ev_l[0]) * 0.5
+    if bounds is not None:
+        lower, upper = bounds
+    deg = degree if degree is not None else cheby_polynomial_degree(unwanted)
+    evals = np.zeros(B)
+    res, mu, occ = None, None, None
+    passes = 0
+    status = 6  # KS_MAX_PASS_ERROR
+    for ipass in range(max_pass):
+        passes = ipass + 1
+        evals, st, vecs = chfsi_solve(W, guesses, evals, batch, deg, lower, upper, unwanted, apply_A, apply_M,
+                                      residual_filter, minv_variant)
+        if st != 0:
+            status = 7
+            break
+        W.update_ghost_values(vecs)
+        mu, nr_ok = fermi_energy(list(evals), n_electrons, smearing_T, fermi_tol)
+        occ = np.array([fermi_dirac(e, mu, BOLTZMANN_CONST_HARTREE, smearing_T) for e in evals])
+        res = eigen_residual_norms(W, vecs, evals, batch, apply_A, apply_M, minv_variant)
+        below = int(np.sum(occ > frac_occ_tol))
+        conv = int(np.sum((occ > frac_occ_tol) & (res <= residual_tol)))
+        for r in range(W.nr):
+            guesses[r][...] = vecs[r]
+        if below == conv or not nr_ok:
+            status = 0 if nr_ok else 9
+            break
+        lower, upper = evals[0], evals[B - 1]
+    return {"eigenvalues": evals, "passes": passes, "bounds": (lower, upper, unwanted), "degree": deg,
+            "residual_norms": res, "status": status, "lanczos": ev_l, "fermi_energy": mu, "occupancy": occ}
