@@ -30,6 +30,7 @@ EXPORTS = [
     "hx_microbench",
     "hx_xtopx_device", "hx_subspace_rotation_device", "hx_dense_cholesky_inverse", "hx_dense_sym_eig",
     "hx_cholesky_gram_schmidt", "hx_rayleigh_ritz", "hx_chfsi_solve", "hx_eigen_residual_norms", "hx_lanczos_extreme",
+    "hx_chebyshev_polynomial_degree",
 ]
 
 
@@ -499,6 +500,12 @@ def lanczos_extreme(A: Op, Bop: Op, BInv: Op, guess: DeviceBlock, max_krylov, n_
                                    ev.ctypes.data_as(f64p), diag.ctypes.data_as(f64p), sub.ctypes.data_as(f64p),
                                    C.byref(k), C.byref(st)))
     return ev, diag[:k.value], sub[:k.value], st.value
+
+
+def chebyshev_polynomial_degree(unwanted_upper: float) -> int:
+    d = C.c_uint32()
+    check(lib().hx_chebyshev_polynomial_degree(C.c_double(unwanted_upper), C.byref(d)))
+    return d.value
 
 
 def comm_unique_id() -> bytes:

@@ -1653,8 +1653,8 @@ extern "C"
         if (cudaEventElapsedTime(&ms, plan->trace_marks[i - 1].second, plan->trace_marks[i].second) != cudaSuccess)
           continue;
         const std::string name = plan->trace_marks[i].first;
-        if (name == "apply:begin")
-          continue; // gap between two applies belongs to the caller's phases
+        if (name.size() > 6 && name.compare(name.size() - 6, 6, ":begin") == 0)
+          continue; // gap before a phase begins belongs to the caller
         auto it = std::find_if(acc.begin(), acc.end(), [&](auto &kv) { return kv.first == name; });
         if (it == acc.end())
           acc.push_back({name, {ms, 1}});

@@ -50,15 +50,19 @@ namespace hx
       {
         const uint32_t b = std::min(batch, B - j0);
         HX_TRY(copy_cols(p, X, B, j0, xin, b, 0, b, p->n_local));
+        p->mark("xtopx-copy");
         HX_TRY(op_apply(op, xin, xout, b, 1, 0));
+        p->mark("gram:begin");
         double *Sd = p->d_small.p;
         HX_TRY(gram_block(p, X, B, j0, xout, b, p->n_owned, Sd));
+        p->mark("gram");
         if (p->nranks > 1)
           HX_TRY(comm_allreduce_sum(p->comm, p->stream, Sd, (size_t)(B - j0) * b));
         // columns [j0, j0+b) of S: rows >= column kept, the rest zero
         HX_TRY(dense_place_gram_block(p, Sd, B - j0, b, j0, S, B));
         // the reference copies the (possibly constraint-filled) batch back into X
         HX_TRY(copy_cols(p, xin, b, 0, X, B, j0, b, p->n_local));
+        p->mark("xtopx-copy");
       }
     return HX_OK;
   }
@@ -78,7 +82,10 @@ namespace hx
         HX_TRY(dense_transpose(p, Q_dev, p->d_dense_q.p, B));
         qeff = p->d_dense_q.p;
       }
-    return rotate(p, X, B, p->n_owned, qeff, transpose, lowerTri, tmp);
+    p->mark("rotate:begin");
+    HX_TRY(rotate(p, X, B, p->n_owned, qeff, transpose, lowerTri, tmp));
+    p->mark(lowerTri ? "rotate-lower" : "rotate");
+    return HX_OK;
   }
 
   enum
@@ -96,7 +103,9 @@ namespace hx
     double *S = p->d_dense_s.p;
     HX_TRY(xtopx_device(Bop, X, B, batch, S)); // X^T M X, lower triangle
     int info = 0;
+    p->mark("dense:begin");
     HX_TRY(dense_cholesky_inverse(p, S, B, &info)); // S <- L^-1
+    p->mark("dense-cholesky");
     if (info != 0)
       {
         *status = ORTHO_LAPACK_ERROR;
@@ -133,7 +142,9 @@ namespace hx
     double *S = p->d_dense_s.p;
     HX_TRY(xtopx_device(A, X, B, batch, S)); // X^T H X, lower triangle
     int info = 0;
+    p->mark("dense:begin");
     HX_TRY(dense_sym_eig(p, S, B, p->d_dense_w.p, &info)); // S <- Q
+    p->mark("dense-eig");
     HX_CUDA(cudaMemcpyAsync(evals_host, p->d_dense_w.p, B * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
     HX_CUDA(cudaStreamSynchronize(p->stream));
     if (info != 0)
@@ -208,6 +219,28 @@ using namespace hx;
 
 extern "C"
 {
+  // getChebyPolynomialDegree + LinearEigenSolverDefaults::CHEBY_ORDER_LOOKUP (src/ksdft/KohnShamEigenSolver.t.cpp:37-46,
+  // src/ksdft/Defaults.cpp:51-58): std::map::lower_bound on the bound truncated to size_type
+  int
+  hx_chebyshev_polynomial_degree(double unWantedSpectrumUpperBound, uint32_t *degree)
+  {
+    HX_CHECK(degree, HX_ERR_INVALID, "null argument");
+    static const uint32_t table[][2] = {{10, 6},      {50, 9},       {100, 12},     {200, 16},      {300, 19},    {500, 24},
+                                        {750, 30},    {1000, 39},    {1500, 50},    {2000, 53},     {3000, 57},   {4000, 62},
+                                        {5000, 69},   {9000, 77},    {14000, 104},  {20000, 119},   {30000, 162}, {50000, 300},
+                                        {80000, 450}, {100000, 550}, {200000, 700}, {500000, 1000}};
+    const double   t   = unWantedSpectrumUpperBound < 0 ? 0.0 : unWantedSpectrumUpperBound;
+    const uint64_t key = t >= 1.8e19 ? ~0ull : (uint64_t)t;
+    *degree            = 1250;
+    for (const auto &kv : table)
+      if (kv[0] >= key)
+        {
+          *degree = kv[1];
+          break;
+        }
+    return HX_OK;
+  }
+
   int
   hx_xtopx_device(hx_op *op, double *X, uint32_t B, uint32_t batch, double *S_dev)
   {

@@ -20,6 +20,7 @@
 #ifndef DFTEFE_B200_HOTPATH_H
 #define DFTEFE_B200_HOTPATH_H
 
+#include <cmath>
 #include <cstdint>
 #include <cstring>
 #include <memory>
@@ -794,6 +795,520 @@ namespace dftefe
       size_type d_maxIter, d_iterations = 0;
       double    d_absoluteTol, d_relativeTol, d_divergenceTol;
     };
+    // ---------------------------------------------------------------------------------------------------------------
+    // The eigensolve around the path: same class names, argument order and error structs as
+    // the reference; all block-vector work and the dense B x B steps stay on the device (hx_chfsi_solve & co).
+    // ---------------------------------------------------------------------------------------------------------------
+    // src/linearAlgebra/LinearAlgebraTypes.h:92-160
+    enum class EigenSolverErrorCode
+    {
+      SUCCESS,
+      LAPACK_ERROR,
+      LANCZOS_BETA_ZERO,
+      LANCZOS_SUBSPACE_INSUFFICIENT,
+      CHFSI_ORTHONORMALIZATION_ERROR,
+      CHFSI_RAYLEIGH_RITZ_ERROR,
+      KS_MAX_PASS_ERROR,
+      KS_CHFSI_ERROR,
+      KS_LANCZOS_ERROR,
+      KS_NEWTON_RAPHSON_ERROR,
+      ELPASCALAPACK_ERROR,
+      OTHER_ERROR
+    };
+    struct EigenSolverError
+    {
+      bool                 isSuccess;
+      EigenSolverErrorCode err;
+      std::string          msg;
+    };
+    enum class OrthonormalizationErrorCode
+    {
+      SUCCESS,
+      LAPACK_ERROR,
+      NON_ORTHONORMALIZABLE_MULTIVECTOR,
+      ELPASCALAPACK_ERROR,
+      MAX_PASS_EXCEEDED
+    };
+    struct OrthonormalizationError
+    {
+      bool                        isSuccess;
+      OrthonormalizationErrorCode err;
+      std::string                 msg;
+    };
+    enum class OrthogonalizationType
+    {
+      CHOLESKY_GRAMSCHMIDT,
+      MULTIPASS_CGS
+    };
+    namespace EigenSolverErrorMsg
+    {
+      inline EigenSolverError
+      isSuccessAndMsg(EigenSolverErrorCode c)
+      {
+        static const char *msgs[] = {"Success",
+                                     "Lapack error",
+                                     "Lanczos beta reached zero",
+                                     "Lanczos Krylov subspace insufficient for the tolerance",
+                                     "ChFSI orthonormalization error: ",
+                                     "ChFSI Rayleigh-Ritz error: ",
+                                     "Maximum Chebyshev filter passes reached",
+                                     "ChFSI error: ",
+                                     "Lanczos error: ",
+                                     "Newton-Raphson error: ",
+                                     "ELPA/ScaLAPACK error",
+                                     "Other error"};
+        EigenSolverError e;
+        e.err       = c;
+        e.isSuccess = c == EigenSolverErrorCode::SUCCESS; // as in the reference: only SUCCESS counts
+        e.msg       = msgs[static_cast<int>(c)];
+        return e;
+      }
+    } // namespace EigenSolverErrorMsg
+
+    inline const NativeOperator &
+    asNative(const DeviceOperatorContext &op, const char *what)
+    {
+      auto *n = dynamic_cast<const NativeOperator *>(&op);
+      utils::throwException(n != nullptr, std::string(what) + "<DEVICE> needs libhxb200 operators");
+      return *n;
+    }
+
+    // OrthonormalizationFunctions (src/linearAlgebra/OrthonormalizationFunctions.h, .t.cpp:154-352)
+    class OrthonormalizationFunctions
+    {
+    public:
+      explicit OrthonormalizationFunctions(size_type eigenVectorBatchSize)
+        : d_eigenVecBatchSize(eigenVectorBatchSize)
+      {}
+      OrthonormalizationError
+      CholeskyGramSchmidt(DeviceMultiVector &X, DeviceMultiVector &orthogonalizedX, const DeviceOperatorContext &B)
+      {
+        int st = 0;
+        utils::hxCheck(hx_cholesky_gram_schmidt(asNative(B, "CholeskyGramSchmidt").handle(), X.data(), orthogonalizedX.data(),
+                                                X.getNumberComponents(), batch(X), &st));
+        OrthonormalizationError e;
+        e.err       = static_cast<OrthonormalizationErrorCode>(st);
+        e.isSuccess = st == 0;
+        e.msg       = st == 0 ? "Success" : hx_last_error();
+        return e;
+      }
+
+    private:
+      size_type
+      batch(const DeviceMultiVector &X) const
+      {
+        return d_eigenVecBatchSize ? d_eigenVecBatchSize : X.getNumberComponents();
+      }
+      size_type d_eigenVecBatchSize;
+    };
+
+    // RayleighRitzEigenSolver, standard problem (src/linearAlgebra/RayleighRitzEigenSolver.t.cpp:70-290)
+    class RayleighRitzEigenSolver
+    {
+    public:
+      explicit RayleighRitzEigenSolver(size_type eigenVectorBatchSize)
+        : d_eigenVecBatchSize(eigenVectorBatchSize)
+      {}
+      EigenSolverError
+      solve(const DeviceOperatorContext &A, DeviceMultiVector &X, std::vector<double> &eigenValues,
+            DeviceMultiVector &eigenVectors, bool computeEigenVectors = false)
+      {
+        const size_type B = X.getNumberComponents();
+        eigenValues.resize(B);
+        int st = 0;
+        utils::hxCheck(hx_rayleigh_ritz(asNative(A, "RayleighRitzEigenSolver").handle(), X.data(), eigenVectors.data(), B,
+                                        d_eigenVecBatchSize ? d_eigenVecBatchSize : B, eigenValues.data(),
+                                        computeEigenVectors, &st));
+        return EigenSolverErrorMsg::isSuccessAndMsg(st == 0 ? EigenSolverErrorCode::SUCCESS :
+                                                              EigenSolverErrorCode::LAPACK_ERROR);
+      }
+
+    private:
+      size_type d_eigenVecBatchSize;
+    };
+
+    // ChebyshevFilteredEigenSolver (src/linearAlgebra/ChebyshevFilteredEigenSolver.h:84-125, .t.cpp:39-438)
+    class ChebyshevFilteredEigenSolver
+    {
+    public:
+      ChebyshevFilteredEigenSolver(const double wantedSpectrumLowerBound, const double wantedSpectrumUpperBound,
+                                   const double unWantedSpectrumUpperBound, const double polynomialDegree,
+                                   const double illConditionTolerance, DeviceMultiVector &eigenSubspaceGuess,
+                                   bool isResidualChebyshevFilter = true, const size_type eigenVectorBatchSize = 0,
+                                   OrthogonalizationType orthoType = OrthogonalizationType::CHOLESKY_GRAMSCHMIDT)
+        : d_eigenVecBatchSize(eigenVectorBatchSize)
+        , d_isResidualChebyFilter(isResidualChebyshevFilter)
+        , d_orthoType(orthoType)
+      {
+        reinit(wantedSpectrumLowerBound, wantedSpectrumUpperBound, unWantedSpectrumUpperBound, polynomialDegree,
+               illConditionTolerance, eigenSubspaceGuess);
+      }
+      void
+      reinit(const double wantedSpectrumLowerBound, const double wantedSpectrumUpperBound,
+             const double unWantedSpectrumUpperBound, const double polynomialDegree, const double illConditionTolerance,
+             DeviceMultiVector &eigenSubspaceGuess)
+      {
+        d_wantedSpectrumLowerBound   = wantedSpectrumLowerBound;
+        d_wantedSpectrumUpperBound   = wantedSpectrumUpperBound;
+        d_unWantedSpectrumUpperBound = unWantedSpectrumUpperBound;
+        d_polynomialDegree           = polynomialDegree;
+        d_illConditionTolerance      = illConditionTolerance;
+        d_eigenSubspaceGuess         = &eigenSubspaceGuess;
+      }
+      // eigenValues: in (read by the residual filter) / out (Ritz values); eigenVectors: out
+      EigenSolverError
+      solve(const DeviceOperatorContext &A, std::vector<double> &eigenValues, DeviceMultiVector &eigenVectors,
+            bool computeEigenVectors, const DeviceOperatorContext &B, const DeviceOperatorContext &BInv)
+      {
+        utils::throwException(d_orthoType == OrthogonalizationType::CHOLESKY_GRAMSCHMIDT,
+                              "Orthogonalization type not present");
+        const size_type nVec = eigenVectors.getNumberComponents();
+        utils::throwException(d_eigenSubspaceGuess->getNumberComponents() == nVec, "guess and eigenVectors differ in width");
+        eigenValues.resize(nVec, 0.0);
+        int st = 0;
+        utils::hxCheck(hx_chfsi_solve(asNative(A, "ChebyshevFilteredEigenSolver").handle(),
+                                      asNative(B, "ChebyshevFilteredEigenSolver").handle(),
+                                      asNative(BInv, "ChebyshevFilteredEigenSolver").handle(), d_eigenSubspaceGuess->data(),
+                                      eigenVectors.data(), nVec, d_eigenVecBatchSize ? d_eigenVecBatchSize : nVec,
+                                      (size_type)d_polynomialDegree, d_wantedSpectrumLowerBound, d_wantedSpectrumUpperBound,
+                                      d_unWantedSpectrumUpperBound, d_isResidualChebyFilter, eigenValues.data(),
+                                      computeEigenVectors, &st));
+        EigenSolverError e = EigenSolverErrorMsg::isSuccessAndMsg(static_cast<EigenSolverErrorCode>(st));
+        if (st != 0)
+          e.msg += hx_last_error();
+        return e;
+      }
+
+    private:
+      double                d_wantedSpectrumLowerBound, d_wantedSpectrumUpperBound, d_unWantedSpectrumUpperBound;
+      double                d_polynomialDegree, d_illConditionTolerance;
+      DeviceMultiVector *   d_eigenSubspaceGuess = nullptr;
+      const size_type       d_eigenVecBatchSize;
+      bool                  d_isResidualChebyFilter;
+      OrthogonalizationType d_orthoType;
+    };
+
+    // LanczosExtremeEigenSolver (src/linearAlgebra/LanczosExtremeEigenSolver.h:60-150, .t.cpp:216-520); eigenvalues
+    // only (computeEigenVectors is what no reference driver asks of it: KohnShamEigenSolver.t.cpp:255-260)
+    class LanczosExtremeEigenSolver
+    {
+    public:
+      LanczosExtremeEigenSolver(const size_type maxKrylovSubspaceSize, const size_type numLowerExtermeEigenValues,
+                                const size_type numUpperExtermeEigenValues, std::vector<double> &tolerance,
+                                double lanczosBetaTolerance, const DeviceMultiVector &initialGuess,
+                                bool isAdaptiveSolve = true)
+        : d_initialGuess(initialGuess)
+        , d_isAdaptiveSolve(isAdaptiveSolve)
+      {
+        utils::throwException(initialGuess.getNumberComponents() == 1, "the Lanczos guess is one vector");
+        d_maxKrylovSubspaceSize      = maxKrylovSubspaceSize;
+        d_numLowerExtermeEigenValues = numLowerExtermeEigenValues;
+        d_numUpperExtermeEigenValues = numUpperExtermeEigenValues;
+        d_tolerance                  = tolerance;
+        d_lanczosBetaTolerance       = lanczosBetaTolerance;
+      }
+      EigenSolverError
+      solve(const DeviceOperatorContext &A, std::vector<double> &eigenValues, DeviceMultiVector & /*eigenVectors*/,
+            bool computeEigenVectors, const DeviceOperatorContext &B, const DeviceOperatorContext &BInv)
+      {
+        utils::throwException(!computeEigenVectors, "LanczosExtremeEigenSolver<DEVICE>: eigenvalues only");
+        const size_type nW = d_numLowerExtermeEigenValues + d_numUpperExtermeEigenValues;
+        utils::throwException(d_maxKrylovSubspaceSize >= nW,
+                              "Maximum Krylov subspace size should be more than number of required eigenPairs.");
+        eigenValues.assign(nW, 0.0);
+        d_diagonal.assign(d_maxKrylovSubspaceSize, 0.0);
+        d_subDiagonal.assign(d_maxKrylovSubspaceSize, 0.0);
+        uint32_t k  = 0;
+        int      st = 0;
+        utils::hxCheck(hx_lanczos_extreme(asNative(A, "Lanczos").handle(), asNative(B, "Lanczos").handle(),
+                                          asNative(BInv, "Lanczos").handle(), d_initialGuess.data(), d_maxKrylovSubspaceSize,
+                                          d_numLowerExtermeEigenValues, d_numUpperExtermeEigenValues, d_tolerance.data(),
+                                          d_lanczosBetaTolerance, d_isAdaptiveSolve, eigenValues.data(), d_diagonal.data(),
+                                          d_subDiagonal.data(), &k, &st));
+        d_diagonal.resize(k);
+        d_subDiagonal.resize(k);
+        d_isSolved = true;
+        return EigenSolverErrorMsg::isSuccessAndMsg(static_cast<EigenSolverErrorCode>(st));
+      }
+      void
+      getTridiagonalMatrix(std::vector<double> &diagonal, std::vector<double> &subDiagonal) const
+      {
+        utils::throwException(d_isSolved, "Cannot call getTridiagonalMatrix() before solving the eigenproblem.");
+        diagonal    = d_diagonal;
+        subDiagonal = d_subDiagonal;
+      }
+
+    private:
+      DeviceMultiVector   d_initialGuess;
+      size_type           d_maxKrylovSubspaceSize, d_numLowerExtermeEigenValues, d_numUpperExtermeEigenValues;
+      std::vector<double> d_tolerance, d_diagonal, d_subDiagonal;
+      double              d_lanczosBetaTolerance;
+      bool                d_isAdaptiveSolve, d_isSolved = false;
+    };
   } // namespace linearAlgebra
+
+  namespace ksdft
+  {
+    // src/ksdft/Defaults.cpp:44-69
+    struct LinearEigenSolverDefaults
+    {
+      static constexpr double    ILL_COND_TOL                 = 1e-14;
+      static constexpr double    LANCZOS_EXTREME_EIGENVAL_TOL = 1e-6;
+      static constexpr double    LANCZOS_BETA_TOL             = 1e-14;
+      static constexpr size_type LANCZOS_MAX_KRYLOV_SUBSPACE  = 20;
+    };
+    struct Constants
+    {
+      static constexpr double BOLTZMANN_CONST_HARTREE = 3.166811429e-06;
+    };
+    // getChebyPolynomialDegree + CHEBY_ORDER_LOOKUP (src/ksdft/KohnShamEigenSolver.t.cpp:37-46, Defaults.cpp:51-58)
+    inline size_type
+    getChebyPolynomialDegree(size_type unWantedSpectrumUpperBound)
+    {
+      uint32_t d = 0;
+      utils::hxCheck(hx_chebyshev_polynomial_degree((double)unWantedSpectrumUpperBound, &d));
+      return d;
+    }
+    // src/ksdft/FractionalOccupancyFunction.cpp:11-40
+    inline double
+    fermiDirac(const double eigenValue, const double fermiEnergy, const double kb, const double T)
+    {
+      const double factor = (eigenValue - fermiEnergy) / (kb * T);
+      return (factor >= 0) ? std::exp(-factor) / (1.0 + std::exp(-factor)) : 1.0 / (1.0 + std::exp(factor));
+    }
+    inline double
+    fermiDiracDer(const double eigenValue, const double fermiEnergy, const double kb, const double T)
+    {
+      const double factor = (eigenValue - fermiEnergy) / (kb * T);
+      const double beta   = 1.0 / (kb * T);
+      return (factor >= 0) ? (beta * std::exp(-factor) / (1.0 + std::exp(-factor)) / (1.0 + std::exp(-factor))) :
+                             (beta * std::exp(factor) / (1.0 + std::exp(factor)) / (1.0 + std::exp(factor)));
+    }
+
+    // KohnShamEigenSolver (src/ksdft/KohnShamEigenSolver.h:85-200, .t.cpp:52-560): Lanczos bounds -> Chebyshev degree
+    // -> ChFSI passes until every level with a non-negligible occupancy has a converged residual.
+    class KohnShamEigenSolver
+    {
+    public:
+      using OpContext = linearAlgebra::DeviceOperatorContext;
+      KohnShamEigenSolver(const size_type numElectrons, const double smearingTemperature, const double fermiEnergyTolerance,
+                          const double fracOccupancyTolerance, const double eigenSolveResidualTolerance,
+                          const size_type maxChebyshevFilterPass, linearAlgebra::DeviceMultiVector &waveFunctionSubspaceGuess,
+                          linearAlgebra::DeviceMultiVector &lanczosGuess, bool isResidualChebyshevFilter,
+                          const size_type waveFunctionBatchSize, const OpContext &MLanczos, const OpContext &MInvLanczos)
+        : d_numWantedEigenvalues(waveFunctionSubspaceGuess.getNumberComponents())
+        , d_eigenSolveResidualTolerance(eigenSolveResidualTolerance)
+        , d_maxChebyshevFilterPass(maxChebyshevFilterPass)
+        , d_waveFunctionBatchSize(waveFunctionBatchSize ? waveFunctionBatchSize : waveFunctionSubspaceGuess.getNumberComponents())
+        , d_fermiEnergyTolerance(fermiEnergyTolerance)
+        , d_fracOccupancyTolerance(fracOccupancyTolerance)
+        , d_smearingTemperature(smearingTemperature)
+        , d_fracOccupancy(d_numWantedEigenvalues)
+        , d_eigSolveResNorm(d_numWantedEigenvalues)
+        , d_numElectrons(numElectrons)
+        , d_isResidualChebyFilter(isResidualChebyshevFilter)
+        , d_waveFunctionSubspaceGuess(&waveFunctionSubspaceGuess)
+        , d_lanczosGuess(&lanczosGuess)
+        , d_MLanczos(&MLanczos)
+        , d_MInvLanczos(&MInvLanczos)
+      {}
+      void
+      reinitBounds(double wantedSpectrumLowerBound, double wantedSpectrumUpperBound)
+      {
+        d_isBoundKnown             = true;
+        d_wantedSpectrumLowerBound = wantedSpectrumLowerBound;
+        d_wantedSpectrumUpperBound = wantedSpectrumUpperBound;
+      }
+      void
+      setChebyshevPolynomialDegree(size_type chebyPolyDeg)
+      {
+        d_setChebyPolDegExternally  = true;
+        d_chebyshevPolynomialDegree = chebyPolyDeg;
+      }
+      void
+      setResidualChebyshevFilterFlag(bool flag)
+      {
+        d_isResidualChebyFilter = flag;
+      }
+
+      linearAlgebra::EigenSolverError
+      solve(const OpContext &kohnShamOperator, std::vector<double> &kohnShamEnergies,
+            linearAlgebra::DeviceMultiVector &kohnShamWaveFunctions, bool computeWaveFunctions, const OpContext &M,
+            const OpContext &MInv)
+      {
+        using namespace linearAlgebra;
+        d_isSolved = true;
+        const NativeOperator &Hn = asNative(kohnShamOperator, "KohnShamEigenSolver");
+        const NativeOperator &Mn = asNative(M, "KohnShamEigenSolver");
+        const size_type       B  = d_numWantedEigenvalues;
+        kohnShamEnergies.resize(B, 0.0);
+        std::vector<double>       tol{LinearEigenSolverDefaults::LANCZOS_EXTREME_EIGENVAL_TOL,
+                                LinearEigenSolverDefaults::LANCZOS_EXTREME_EIGENVAL_TOL};
+        LanczosExtremeEigenSolver lanczos(LinearEigenSolverDefaults::LANCZOS_MAX_KRYLOV_SUBSPACE, 1, 1, tol,
+                                          LinearEigenSolverDefaults::LANCZOS_BETA_TOL, *d_lanczosGuess, false);
+        std::vector<double>       eigenValuesLanczos(2);
+        EigenSolverError          lanczosErr =
+          lanczos.solve(kohnShamOperator, eigenValuesLanczos, kohnShamWaveFunctions, false, *d_MLanczos, *d_MInvLanczos);
+        if (!(lanczosErr.isSuccess || lanczosErr.err == EigenSolverErrorCode::LANCZOS_SUBSPACE_INSUFFICIENT))
+          {
+            EigenSolverError r = EigenSolverErrorMsg::isSuccessAndMsg(EigenSolverErrorCode::KS_LANCZOS_ERROR);
+            r.msg += lanczosErr.msg;
+            return r;
+          }
+        std::vector<double> diagonal, subDiagonal;
+        lanczos.getTridiagonalMatrix(diagonal, subDiagonal);
+        const double residual = subDiagonal[subDiagonal.size() - 1] / 10;
+        d_unWantedSpectrumUpperBound = eigenValuesLanczos[1] + residual;
+        if (!d_isBoundKnown)
+          {
+            const double globalSize    = (double)d_globalSize(kohnShamWaveFunctions);
+            d_wantedSpectrumLowerBound = eigenValuesLanczos[0];
+            d_wantedSpectrumUpperBound =
+              (d_unWantedSpectrumUpperBound - eigenValuesLanczos[0]) * ((double)(B * 200.0) / globalSize) + eigenValuesLanczos[0];
+            if (d_wantedSpectrumUpperBound >= d_unWantedSpectrumUpperBound)
+              d_wantedSpectrumUpperBound = (d_unWantedSpectrumUpperBound + eigenValuesLanczos[0]) * 0.5;
+          }
+        if (!d_setChebyPolDegExternally)
+          d_chebyshevPolynomialDegree = getChebyPolynomialDegree((size_type)d_unWantedSpectrumUpperBound);
+        ChebyshevFilteredEigenSolver chfsi(d_wantedSpectrumLowerBound, d_wantedSpectrumUpperBound,
+                                           d_unWantedSpectrumUpperBound, (double)d_chebyshevPolynomialDegree,
+                                           LinearEigenSolverDefaults::ILL_COND_TOL, *d_waveFunctionSubspaceGuess,
+                                           d_isResidualChebyFilter, d_waveFunctionBatchSize);
+        EigenSolverError chfsiErr = EigenSolverErrorMsg::isSuccessAndMsg(EigenSolverErrorCode::OTHER_ERROR);
+        bool             nrOk     = true;
+        size_type        iPass    = 0;
+        for (; iPass < d_maxChebyshevFilterPass; iPass++)
+          {
+            chfsiErr = chfsi.solve(kohnShamOperator, kohnShamEnergies, kohnShamWaveFunctions, computeWaveFunctions, M, MInv);
+            if (!chfsiErr.isSuccess)
+              break;
+            kohnShamWaveFunctions.updateGhostValues();
+            // chemical potential by Newton-Raphson on sum 2 f(eps_i) - N_e (NewtonRaphsonSolver.t.cpp:48-96)
+            nrOk = solveFermiEnergy(kohnShamEnergies);
+            size_type numLevelsBelowFermiEnergy = 0, numLevelsBelowFermiEnergyResidualConverged = 0;
+            for (size_type i = 0; i < B; i++)
+              {
+                d_fracOccupancy[i] =
+                  fermiDirac(kohnShamEnergies[i], d_fermiEnergy, Constants::BOLTZMANN_CONST_HARTREE, d_smearingTemperature);
+                if (d_fracOccupancy[i] > d_fracOccupancyTolerance)
+                  numLevelsBelowFermiEnergy += 1;
+              }
+            if (computeWaveFunctions)
+              {
+                utils::hxCheck(hx_eigen_residual_norms(Hn.handle(), Mn.handle(), kohnShamWaveFunctions.data(), B,
+                                                       d_waveFunctionBatchSize, kohnShamEnergies.data(), d_eigSolveResNorm.data()));
+                for (size_type i = 0; i < B; i++)
+                  if (d_fracOccupancy[i] > d_fracOccupancyTolerance && d_eigSolveResNorm[i] <= d_eigenSolveResidualTolerance)
+                    numLevelsBelowFermiEnergyResidualConverged += 1;
+              }
+            // *d_waveFunctionSubspaceGuess = kohnShamWaveFunctions (hx_chfsi_solve leaves the Ritz vectors in the guess)
+            if (numLevelsBelowFermiEnergy == numLevelsBelowFermiEnergyResidualConverged || !nrOk)
+              break;
+            d_wantedSpectrumLowerBound = kohnShamEnergies[0];
+            d_wantedSpectrumUpperBound = kohnShamEnergies[B - 1];
+            chfsi.reinit(d_wantedSpectrumLowerBound, d_wantedSpectrumUpperBound, d_unWantedSpectrumUpperBound,
+                         (double)d_chebyshevPolynomialDegree, LinearEigenSolverDefaults::ILL_COND_TOL,
+                         *d_waveFunctionSubspaceGuess);
+          }
+        d_numPasses = iPass < d_maxChebyshevFilterPass ? iPass + 1 : iPass;
+        EigenSolverError r;
+        if (!chfsiErr.isSuccess)
+          {
+            r = EigenSolverErrorMsg::isSuccessAndMsg(EigenSolverErrorCode::KS_CHFSI_ERROR);
+            r.msg += chfsiErr.msg;
+          }
+        else if (!nrOk)
+          r = EigenSolverErrorMsg::isSuccessAndMsg(EigenSolverErrorCode::KS_NEWTON_RAPHSON_ERROR);
+        else if (iPass >= d_maxChebyshevFilterPass)
+          r = EigenSolverErrorMsg::isSuccessAndMsg(EigenSolverErrorCode::KS_MAX_PASS_ERROR);
+        else
+          {
+            r = EigenSolverErrorMsg::isSuccessAndMsg(EigenSolverErrorCode::SUCCESS);
+            r.msg += "Number of CHFSI passes required are " + std::to_string(iPass + 1) + ".";
+          }
+        return r;
+      }
+      double
+      getFermiEnergy() const
+      {
+        utils::throwException(d_isSolved, "Cannot call getFermiEnergy() before solving the eigenproblem.");
+        return d_fermiEnergy;
+      }
+      std::vector<double>
+      getFractionalOccupancy() const
+      {
+        utils::throwException(d_isSolved, "Cannot call getFractionalOccupancy() before solving the eigenproblem.");
+        return d_fracOccupancy;
+      }
+      std::vector<double>
+      getEigenSolveResidualNorm() const
+      {
+        utils::throwException(d_isSolved, "Cannot call getEigenSolveResidualNorm() before solving the eigenproblem.");
+        return d_eigSolveResNorm;
+      }
+      size_type
+      getChebyshevPolynomialDegree() const
+      {
+        return d_chebyshevPolynomialDegree;
+      }
+      size_type
+      getNumberOfPasses() const
+      {
+        return d_numPasses;
+      }
+      // the global number of DoFs (MultiVector::globalSize); set by the caller for multi-rank runs
+      void
+      setGlobalSize(size_t n)
+      {
+        d_globalSizeOverride = n;
+      }
+
+    private:
+      size_t
+      d_globalSize(const linearAlgebra::DeviceMultiVector &X) const
+      {
+        return d_globalSizeOverride ? d_globalSizeOverride : X.locallyOwnedSize();
+      }
+      bool
+      solveFermiEnergy(const std::vector<double> &eps)
+      {
+        const double kb = Constants::BOLTZMANN_CONST_HARTREE, T = d_smearingTemperature;
+        double       x = eps[(size_t)std::ceil(static_cast<double>(d_numElectrons) / 2.0) - 1];
+        for (size_t iter = 0; iter <= 20000000; ++iter)
+          {
+            double val = 0, force = 0;
+            for (double e : eps)
+              {
+                val += 2 * fermiDirac(e, x, kb, T);
+                force += 2 * fermiDiracDer(e, x, kb, T);
+              }
+            val -= (double)d_numElectrons;
+            if (force == 0.0)
+              return false;
+            const double x1 = x - val / force;
+            if (std::fabs(x1 - x) < d_fermiEnergyTolerance)
+              {
+                d_fermiEnergy = x1;
+                return true;
+              }
+            x = x1;
+          }
+        return false;
+      }
+      size_type           d_numWantedEigenvalues;
+      double              d_eigenSolveResidualTolerance;
+      size_type           d_maxChebyshevFilterPass, d_waveFunctionBatchSize;
+      double              d_fermiEnergyTolerance, d_fracOccupancyTolerance, d_smearingTemperature;
+      std::vector<double> d_fracOccupancy, d_eigSolveResNorm;
+      size_type           d_numElectrons;
+      bool                d_isResidualChebyFilter, d_setChebyPolDegExternally = false, d_isBoundKnown = false, d_isSolved = false;
+      size_type           d_chebyshevPolynomialDegree = 0, d_numPasses = 0;
+      double              d_wantedSpectrumLowerBound = 0, d_wantedSpectrumUpperBound = 0, d_unWantedSpectrumUpperBound = 0;
+      double              d_fermiEnergy = 0;
+      size_t              d_globalSizeOverride = 0;
+      linearAlgebra::DeviceMultiVector *d_waveFunctionSubspaceGuess, *d_lanczosGuess;
+      const OpContext *                 d_MLanczos, *d_MInvLanczos;
+    };
+  } // namespace ksdft
 } // namespace dftefe
 #endif

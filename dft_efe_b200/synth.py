@@ -655,12 +655,14 @@ def build_problem(spec: MeshSpec, only_rank: Optional[int] = None) -> List[RankP
             el = g2l(eg)
             n_c = int(ncd64[ic])
             ids[off1[ic]:off1[ic + 1]] = np.concatenate([cl_all[ic], el])
-            Kc, Mc, _ = mats[int(size[c])]
+            Kc, Mc, lump_c_ = mats[int(size[c])]
             Hc = np.zeros((n_c, n_c))
             Hc[:npc, :npc] = 0.5 * Kc + vcell[c] * Mc
             crng = np.random.default_rng(spec.seed + 7919 * (int(c) + 1))
             vol = (spec.h * size[c] / 2.0) ** 3
-            Bc = crng.uniform(-1, 1, (npc, len(el))) * 1e-2 * vol
+            # classical-enrichment coupling weighted by the nodal mass (as an integral of N_i against a smooth
+            # enrichment function would be), so that the pencil (H, M) keeps a physical spectrum
+            Bc = crng.uniform(-1, 1, (npc, len(el))) * lump_c_[:, None] * 0.1
             Ec = crng.uniform(-1, 1, (len(el), len(el))) * 1e-2 * vol
             Hc[:npc, npc:] = Bc
             Hc[npc:, :npc] = Bc.T
@@ -687,7 +689,10 @@ def build_problem(spec: MeshSpec, only_rank: Optional[int] = None) -> List[RankP
                     pids.append(pl)
                     crng = np.random.default_rng(spec.seed + 104729 * (int(c) + 1))
                     vol = (spec.h * size[c] / 2.0) ** 3
-                    Cc = crng.uniform(-1, 1, (len(pg), int(ncd64[ic]))) * np.sqrt(vol) * 0.3   # [proj, dof]
+                    # projector values integrated against the shape functions: weighted by the nodal mass (see Bc)
+                    wdof = np.full(int(ncd64[ic]), np.sqrt(vol) * 0.05)
+                    wdof[:npc] = mats[int(size[c])][2] * (0.3 / np.sqrt(vol))
+                    Cc = crng.uniform(-1, 1, (len(pg), int(ncd64[ic]))) * wdof[None, :]   # [proj, dof]
                     cblocks.append(Cc.T.ravel())  # column-major nProj_c x n_c  == C[p + j*nP]
 
         # constraints restricted to local rows; owned rows first then ghosts, ascending gid

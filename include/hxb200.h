@@ -281,6 +281,10 @@ int hx_lanczos_extreme(hx_op *A, hx_op *Bop, hx_op *BInv, const double *initialG
                        int adaptive, double *eigenvalues_host, double *diagonal_host, double *subDiagonal_host,
                        uint32_t *krylovSize, int *status);
 
+/* Chebyshev polynomial degree for a spectral upper bound: LinearEigenSolverDefaults::CHEBY_ORDER_LOOKUP through
+ * getChebyPolynomialDegree (src/ksdft/Defaults.cpp:51-58, src/ksdft/KohnShamEigenSolver.t.cpp:37-46). */
+int hx_chebyshev_polynomial_degree(double unWantedSpectrumUpperBound, uint32_t *degree);
+
 /* ---- measurement hooks (bench.py / tests) ---- */
 /* Number of kernel launches issued through this plan since creation, and device time of the dominant
  * cell-contraction kernel accumulated with CUDA events on the plan's stream (reset on read). */

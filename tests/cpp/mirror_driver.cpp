@@ -142,6 +142,33 @@ main(int argc, char **argv)
       std::ofstream out(argv[2], std::ios::binary);
       std::vector<double> host((size_t)ctx->localSize() * B);
 
+      if (b.f.count("ks_params"))
+        {
+          // ---- Kohn-Sham eigensolve call site, written like KohnShamDFT drives it (src/ksdft/KohnShamDFT.t.cpp:
+          // 490-505, 2331-2340): Lanczos bounds -> ChFSI passes -> energies, occupancies, residuals ----
+          const auto &                          kp = b.f.at("ks_params"); // numElectrons, T, fermiTol, occTol, resTol, maxPass, batch, residualFilter, lower, upper
+          basis::OrthoEFEOverlapOperatorContext M(ctx, b.f.at("diag"), b.f.at("enr_block"));
+          linearAlgebra::DeviceMultiVector      waveFnGuess(ctx, B), lanczosGuess(ctx, 1), waveFns(ctx, B);
+          waveFnGuess.copyFrom(b.f.at("X").data());
+          lanczosGuess.copyFrom(b.f.at("lanczos_guess").data());
+          ksdft::KohnShamEigenSolver ks((size_type)kp[0], kp[1], kp[2], kp[3], kp[4], (size_type)kp[5], waveFnGuess,
+                                        lanczosGuess, kp[7] != 0.0, (size_type)kp[6], M, MInv);
+          if (kp[8] < kp[9])
+            ks.reinitBounds(kp[8], kp[9]);
+          std::vector<double>                   energies;
+          const linearAlgebra::EigenSolverError e = ks.solve(H, energies, waveFns, true, M, MInv);
+          writeArray(out, "ks_energies", energies);
+          writeArray(out, "ks_status",
+                     std::vector<double>{e.isSuccess ? 1.0 : 0.0, (double)static_cast<int>(e.err), (double)ks.getNumberOfPasses(),
+                                         (double)ks.getChebyshevPolynomialDegree(), ks.getFermiEnergy()});
+          writeArray(out, "ks_occupancy", ks.getFractionalOccupancy());
+          writeArray(out, "ks_residuals", ks.getEigenSolveResidualNorm());
+          waveFns.copyTo(host.data());
+          writeArray(out, "ks_wavefunctions", host);
+          std::cout << "mirror_driver ok (" << e.msg << ")\n";
+          return 0;
+        }
+
       linearAlgebra::DeviceMultiVector X(ctx, B), Y(ctx, B);
       X.copyFrom(b.f.at("X").data());
       H.apply(X, Y, true, false);

@@ -124,3 +124,52 @@ def test_cpp_mirror_matches_oracle(tmp_path):
     assert erro == 0 and res["poisson_status"][0] == 1.0 and abs(res["poisson_status"][1] - ito) <= 1
     sol = res["poisson_solution"].reshape(X.shape)
     assert np.abs(sol[:own] - xs[0][:own]).max() < 1e-8 * np.abs(xs[0][:own]).max()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("residual_filter", [False, True])
+def test_cpp_mirror_kohn_sham_eigensolver(tmp_path, residual_filter):
+    """ksdft::KohnShamEigenSolver::solve written against the mirror (Lanczos -> ChFSI passes -> Fermi level) converges
+    to the oracle's and the dense solver's eigenvalues within 1e-8 Ha."""
+    import scipy.linalg as sla
+    from oracle import eigensolver as es
+    from tests.test_eigensolver_oracle import dense_pencil, eig_spec
+    exe = build_driver()
+    p = synth.build_problem(eig_spec(1))[0]
+    W = orc.OracleWorld([p])
+    B, n_el, batch, bounds = 8, 8, 3, (-1.0, 6.0)
+    X = synth.make_block(p, B)
+    lg = np.random.default_rng(11).uniform(-0.5, 0.5, (p.n_local, 1))
+    arrays = {"scalars": np.array([p.n_owned_classical, B, 1], np.uint32),
+              **halo_arrays(p.halo, "halo."), **halo_arrays(p.proj_halo, "proj_halo."),
+              "num_cell_dofs": p.num_cell_dofs, "cell_local_ids": p.cell_local_ids, "row_ids": p.row_ids,
+              "row_sizes": p.row_sizes, "row_offsets": p.row_offsets, "col_ids": p.col_ids,
+              "col_vals": p.col_vals, "inhom": p.inhom, "num_cell_proj": p.num_cell_proj,
+              "cell_proj_local_ids": p.cell_proj_local_ids, "cell_c": p.cell_c, "proj_v": p.proj_v,
+              "h_part1": 0.25 * p.h_cell, "h_part2": 0.75 * p.h_cell, "diag_inv": p.diag_inv, "diag": p.diag,
+              "enr_block_inv": np.asarray(p.enr_block_inv, np.float64).ravel(order="F"),
+              "enr_block": np.asarray(p.enr_block, np.float64).ravel(order="F"),
+              "bounds": np.array([0.0, 0.0, 0.0]), "X": X, "lanczos_guess": lg,
+              "ks_params": np.array([n_el, 500.0, 1e-10, 1e-8, 1e-9, 60, batch, float(residual_filter), *bounds])}
+    arrays = {k: (np.asarray(v, np.uint32) if np.asarray(v).dtype.kind in "ui" else np.asarray(v, np.float64))
+              for k, v in arrays.items()}
+    write_blob(tmp_path / "problem.bin", arrays)
+    r = subprocess.run([exe, str(tmp_path / "problem.bin"), str(tmp_path / "result.bin")], capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    res = read_blob(tmp_path / "result.bin")
+    ok, err, passes, degree, mu = res["ks_status"]
+    assert ok == 1.0 and err == 0.0, r.stdout
+    out = es.ks_eigen_solve(W, [X.copy()], [lg.copy()], n_el, 500.0, 1e-10, 1e-8, 1e-9, 60, batch=batch,
+                            residual_filter=residual_filter, bounds=bounds)
+    assert out["status"] == 0 and degree == out["degree"] and abs(passes - out["passes"]) <= 1
+    Hd, Md, _ = dense_pencil(W, [p])
+    lam = sla.eigh(Hd, Md, eigvals_only=True)
+    occ = res["ks_occupancy"]
+    n_occ = int(np.sum(occ > 1e-8))
+    assert n_occ >= 4
+    assert np.abs(res["ks_energies"][:n_occ] - out["eigenvalues"][:n_occ]).max() < 1e-8
+    assert np.abs(res["ks_energies"][:n_occ] - lam[:n_occ]).max() < 1e-8
+    # the Fermi level lies in the gap above the occupied levels; its position depends on the unconverged buffer states
+    assert res["ks_energies"][n_occ - 1] < mu < res["ks_energies"][n_occ] and abs(mu - out["fermi_energy"]) < 1e-2
+    assert np.all(res["ks_residuals"][:n_occ] <= 1e-9)
