@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libhxb200.so")
-SOURCES = ["api.cu", "cell_kernel.cu", "kernels.cu", "gram.cu", "comm.cu", "peer.cu", "microbench.cu", "dense.cu", "eigen.cu"]
+SOURCES = ["api.cu", "cell_kernel.cu", "kernels.cu", "gram.cu", "comm.cu", "peer.cu", "microbench.cu", "dense.cu", "eigen.cu", "assemble.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 

@@ -30,7 +30,7 @@ EXPORTS = [
     "hx_microbench",
     "hx_xtopx_device", "hx_subspace_rotation_device", "hx_dense_cholesky_inverse", "hx_dense_sym_eig",
     "hx_cholesky_gram_schmidt", "hx_rayleigh_ritz", "hx_chfsi_solve", "hx_eigen_residual_norms", "hx_lanczos_extreme",
-    "hx_chebyshev_polynomial_degree",
+    "hx_chebyshev_polynomial_degree", "hx_fe_basis_create", "hx_fe_basis_destroy", "hx_compute_fe_matrices", "hx_compute_rho",
 ]
 
 
@@ -52,6 +52,11 @@ class MeshDesc(C.Structure):
 class NonlocalDesc(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("proj_halo", HaloDesc), ("num_cell_proj", u32p),
                 ("cell_proj_local_ids", u32p), ("cell_c", f64p), ("v", f64p)]
+
+
+class FeBasisDesc(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("same_basis_in_all_cells", C.c_int32), ("num_cell_quad", u32p),
+                ("basis_data", f64p), ("jxw", f64p)]
 
 
 class HxError(RuntimeError):
@@ -500,6 +505,50 @@ def lanczos_extreme(A: Op, Bop: Op, BInv: Op, guess: DeviceBlock, max_krylov, n_
                                    ev.ctypes.data_as(f64p), diag.ctypes.data_as(f64p), sub.ctypes.data_as(f64p),
                                    C.byref(k), C.byref(st)))
     return ev, diag[:k.value], sub[:k.value], st.value
+
+
+class FeBasis:
+    """FEBasisDataStorage arrays on the device + FEBasisOperations::computeFEMatrices."""
+
+    def __init__(self, plan: Plan, num_cell_quad, basis_data, jxw, same_basis: bool):
+        self.plan = plan
+        d = FeBasisDesc()
+        d.struct_size = C.sizeof(FeBasisDesc)
+        d.same_basis_in_all_cells = int(same_basis)
+        a, d.num_cell_quad = _u32(num_cell_quad)
+        b, d.basis_data = _f64(basis_data)
+        c, d.jxw = _f64(jxw)
+        self.n_quad = int(np.sum(a.astype(np.int64)))
+        self.h = C.c_void_p()
+        check(lib().hx_fe_basis_create(plan.h, C.byref(d), C.byref(self.h)))
+
+    def compute_fe_matrices(self, f, out: DeviceBlock, add_to: Optional[DeviceBlock] = None, f_device=None):
+        """out: DeviceBlock of S2 doubles.  f: host array (one value per quadrature point) or f_device: DeviceBlock."""
+        if f_device is not None:
+            check(lib().hx_compute_fe_matrices(self.h, f_device.p, C.c_int(1), add_to.p if add_to is not None else None, out.p))
+        else:
+            a, p = _f64(f)
+            assert a.size == self.n_quad
+            check(lib().hx_compute_fe_matrices(self.h, p, C.c_int(0), add_to.p if add_to is not None else None, out.p))
+
+    def compute_rho(self, X: DeviceBlock, occupation) -> np.ndarray:
+        """DensityCalculator::computeRho: rho at the quadrature points (host array)."""
+        o, op = _f64(occupation)
+        assert o.size == X.B
+        rho = np.zeros(self.n_quad)
+        check(lib().hx_compute_rho(self.h, X.p, C.c_uint32(X.B), op, rho.ctypes.data_as(f64p), C.c_int(0)))
+        return rho
+
+    def destroy(self):
+        if self.h:
+            lib().hx_fe_basis_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
 
 
 def chebyshev_polynomial_degree(unwanted_upper: float) -> int:

@@ -1,0 +1,455 @@
+// assemble.cu — the step BEFORE the H.X path each SCF iteration: the cell matrices of a local
+// potential, FEBasisOperations::computeFEMatrices(IDENTITY, MULT, MULT, IDENTITY, f)
+// (src/basis/FEBasisOperations.t.cpp:2210-2243 -> BasisWeakFormKernelWithField, :41-427):
+//
+//     C_c[i, j] = sum_q N_c[q, i] * f[q] * JxW[q] * N_c[q, j]          per cell c, n_c x n_c, k = nq_c
+//
+// The reference forms f x JxW (hadamardProduct), scales a copy of the basis values with it (scaleStridedVarBatched)
+// and calls one dgemm('N','C') per cell.  Here one CTA owns one 64 x 64 tile of one cell's matrix (tiles on and below
+// the diagonal only; the mirror image is written by the same CTA), streams the basis values of the cell in chunks of
+// 16 quadrature points through a cp.async double buffer, applies f x JxW to the A fragments in registers and feeds
+// mma.sync.m8n8k4.f64.  An optional `add_to` array (e.g. the kinetic cell matrices) is added in the epilogue, which
+// is KohnShamOperatorContextFE::reinit's component sum (src/ksdft/KohnShamOperatorContextFE.t.cpp:1259-1282) fused.
+// Output: the flat S2 array hx_cellop_set_matrices(.., on_device = 1) consumes - the potential never leaves the GPU.
+#include <algorithm>
+#include <memory>
+
+#include "hx_internal.h"
+
+struct hx_fe_basis
+{
+  hx_plan *                   plan = nullptr;
+  bool                        same_basis = false;
+  uint32_t                    C = 0, max_n = 0;
+  size_t                      n_quad_total = 0, S2 = 0;
+  std::vector<uint32_t>       h_nq;
+  hx::DevBuf<double>          d_basis, d_jxw, d_w, d_f, d_occ, d_rho;
+  struct Cell
+  {
+    unsigned long long basis_off, out_off;
+    uint32_t           q_off, n, nq, ids_off;
+  };
+  hx::DevBuf<Cell> d_cells;
+};
+
+namespace hx
+{
+  constexpr int FT  = 64; // tile edge
+  constexpr int FKC = 16; // quadrature points per stage
+  constexpr int FLD = FT + 4;
+
+  __device__ __forceinline__ void
+  fe_dmma(double &d0, double &d1, const double a, const double b)
+  {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+        : "+d"(d0), "+d"(d1)
+        : "d"(a), "d"(b));
+  }
+  __device__ __forceinline__ void
+  fe_cp16(void *smem, const void *gmem)
+  {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
+  }
+  __device__ __forceinline__ void
+  fe_cp8(void *smem, const void *gmem)
+  {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
+  }
+
+  // [FKC x 64] tile of the cell's basis values (row q, columns c0..c0+63 of an nq x n matrix, DoF index fastest)
+  __device__ __forceinline__ void
+  fe_load_tile(double *sm, const double *g, uint32_t n, uint32_t q0, uint32_t nq, uint32_t c0, bool aligned16, int tid)
+  {
+#pragma unroll
+    for (int it = 0; it < 2; ++it)
+      {
+        const int      ch = tid + it * 256;
+        const int      r  = ch >> 5;
+        const int      cc = (ch & 31) * 2;
+        double *       d  = sm + r * FLD + cc;
+        const uint32_t q = q0 + r, c = c0 + cc;
+        const double * s = g + (size_t)q * n + c;
+        if (q < nq && c + 1 < n)
+          {
+            if (aligned16)
+              fe_cp16(d, s);
+            else
+              {
+                fe_cp8(d, s);
+                fe_cp8(d + 1, s + 1);
+              }
+          }
+        else
+          {
+            d[0] = (q < nq && c < n) ? s[0] : 0.0;
+            d[1] = 0.0;
+          }
+      }
+  }
+
+  // grid: (cells, lower tiles of the largest cell)
+  __global__ void __launch_bounds__(256)
+  fe_matrices_kernel(const hx_fe_basis::Cell *cells, const double *basis, const double *w, const double *add_to, double *out)
+  {
+    __shared__ __align__(16) double As[2][FKC * FLD];
+    __shared__ __align__(16) double Bs[2][FKC * FLD];
+    __shared__ double               Ws[2][FKC];
+    const hx_fe_basis::Cell         cell = cells[blockIdx.x];
+    const uint32_t                  n = cell.n, nq = cell.nq;
+    const uint32_t                  tilesM = (n + FT - 1) / FT;
+    // tile index -> (tm, tn) with tn <= tm
+    uint32_t tm = 0, t = blockIdx.y;
+    while (t > tm)
+      {
+        t -= tm + 1;
+        ++tm;
+      }
+    const uint32_t tn = t;
+    if (tm >= tilesM)
+      return;
+    const int      tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t m0 = tm * FT, n0 = tn * FT;
+    const double * N  = basis + cell.basis_off;
+    const double * wc = w + cell.q_off;
+    const bool     aligned16 = ((n & 1u) == 0) && ((cell.basis_off & 1ull) == 0);
+    double         acc[2][4][2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        acc[j][u][0] = acc[j][u][1] = 0.0;
+    const int wm = (warp & 3) * 16, wn = (warp >> 2) * 32;
+    const int nchunks = (int)((nq + FKC - 1) / FKC);
+    auto      load    = [&](int buf, uint32_t q0) {
+      fe_load_tile(As[buf], N, n, q0, nq, m0, aligned16, tid);
+      fe_load_tile(Bs[buf], N, n, q0, nq, n0, aligned16, tid);
+      if (tid < FKC)
+        Ws[buf][tid] = (q0 + tid < nq) ? wc[q0 + tid] : 0.0;
+    };
+    if (nchunks)
+      {
+        load(0, 0);
+        asm volatile("cp.async.commit_group;");
+      }
+    for (int c = 0; c < nchunks; ++c)
+      {
+        const int cur = c & 1;
+        if (c + 1 < nchunks)
+          {
+            load(cur ^ 1, (uint32_t)(c + 1) * FKC);
+            asm volatile("cp.async.commit_group;");
+            asm volatile("cp.async.wait_group 1;");
+          }
+        else
+          asm volatile("cp.async.wait_group 0;");
+        __syncthreads();
+        const double *as = As[cur] + (lane & 3) * FLD + wm + (lane >> 2);
+        const double *bs = Bs[cur] + (lane & 3) * FLD + wn + (lane >> 2);
+#pragma unroll
+        for (int k4 = 0; k4 < FKC / 4; ++k4)
+          {
+            const double wk = Ws[cur][k4 * 4 + (lane & 3)];
+            double       a[2], bb[4];
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+              a[j] = as[k4 * 4 * FLD + j * 8] * wk; // fxJxWxN of the reference, formed in registers
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              bb[u] = bs[k4 * 4 * FLD + u * 8];
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+              for (int u = 0; u < 4; ++u)
+                fe_dmma(acc[j][u][0], acc[j][u][1], a[j], bb[u]);
+          }
+        __syncthreads();
+      }
+    double *      o   = out + cell.out_off;
+    const double *add = add_to ? add_to + cell.out_off : nullptr;
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+          {
+            const uint32_t r = m0 + wm + j * 8 + (lane >> 2);
+            const uint32_t cidx = n0 + wn + u * 8 + (lane & 3) * 2 + e;
+            if (r < n && cidx < n)
+              {
+                const double v  = acc[j][u][e];
+                const size_t i1 = (size_t)r * n + cidx;
+                o[i1]           = add ? v + add[i1] : v;
+                if (tm != tn)
+                  { // mirror image of an off-diagonal tile (the matrix is symmetric)
+                    const size_t i2 = (size_t)cidx * n + r;
+                    o[i2]           = add ? v + add[i2] : v;
+                  }
+              }
+          }
+  }
+
+  // ---------------------------------------------------------------------------------------------------------------
+  // 8f rank 3: DensityCalculator::computeRho (src/ksdft/DensityCalculator.t.cpp:283-437) =
+  //   FEBasisOperations::interpolate (src/basis/FEBasisOperations.t.cpp:996-1275: per cell psiQuad (B x nq) =
+  //   xCell (B x n_c) . N (n_c x nq)) followed by computeRhoInBatch (:37-70: rho[q] = sum_i 2 |psi_i(q)|^2 occ_i).
+  // One CTA = 64 quadrature points of one cell: for every 64-wide tile of wavefunctions it gathers the cell's rows of X
+  // (cell -> DoF map) in chunks of 16 DoFs next to the matching basis values, runs the DMMA contraction, squares the
+  // accumulators, weights them with 2 occ_i and keeps one partial sum per quadrature point; psi at the quadrature
+  // points never goes to memory.  Fixed summation order (no atomics).
+  constexpr int RLD = FKC + 4;
+  __global__ void __launch_bounds__(256)
+  rho_kernel(const hx_fe_basis::Cell *cells, const double *basis, const uint32_t *ids, const double *X, uint32_t B,
+             const double *occ2, double *rho)
+  {
+    __shared__ __align__(16) double As[2][FT * RLD];  // basis values [q][dof chunk]
+    __shared__ __align__(16) double Bs[2][FKC * FLD]; // gathered X rows [dof chunk][vectors]
+    __shared__ double               red[2][FT];
+    const hx_fe_basis::Cell         cell = cells[blockIdx.x];
+    const uint32_t                  n = cell.n, nq = cell.nq;
+    const uint32_t                  q0 = blockIdx.y * FT;
+    if (q0 >= nq)
+      return;
+    const int       tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double *  N   = basis + cell.basis_off;
+    const uint32_t *cid = ids + cell.ids_off;
+    const bool      alignedX = ((B & 1u) == 0) && ((((uintptr_t)X) & 15) == 0);
+    const int       wm = (warp & 3) * 16, wn = (warp >> 2) * 32;
+    double          part[2] = {0.0, 0.0}; // rows wm + j*8 + (lane >> 2)
+    const int       nchunks = (int)((n + FKC - 1) / FKC);
+    for (uint32_t v0 = 0; v0 < B; v0 += FT)
+      {
+        double acc[2][4][2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            acc[j][u][0] = acc[j][u][1] = 0.0;
+        auto load = [&](int buf, uint32_t k0) {
+          // A: 64 quadrature points x 16 DoFs; element (q, j) at N[q*n + j]
+#pragma unroll
+          for (int it = 0; it < 4; ++it)
+            {
+              const int      ch = tid + it * 256; // 1024 elements
+              const int      r = ch >> 4, kk = ch & 15;
+              const uint32_t q = q0 + r, j = k0 + kk;
+              double *       d = As[buf] + r * RLD + kk;
+              if (q < nq && j < n)
+                fe_cp8(d, N + (size_t)q * n + j);
+              else
+                *d = 0.0;
+            }
+          // B: 16 DoFs x 64 vectors gathered through the cell -> DoF map
+#pragma unroll
+          for (int it = 0; it < 2; ++it)
+            {
+              const int      ch = tid + it * 256;
+              const int      r = ch >> 5, cc = (ch & 31) * 2;
+              const uint32_t j = k0 + r, v = v0 + cc;
+              double *       d = Bs[buf] + r * FLD + cc;
+              if (j < n && v + 1 < B && alignedX)
+                fe_cp16(d, X + (size_t)cid[j] * B + v);
+              else
+                {
+                  const double *s = (j < n) ? X + (size_t)cid[j] * B : nullptr;
+                  d[0]            = (s && v < B) ? s[v] : 0.0;
+                  d[1]            = (s && v + 1 < B) ? s[v + 1] : 0.0;
+                }
+            }
+        };
+        load(0, 0);
+        asm volatile("cp.async.commit_group;");
+        for (int c = 0; c < nchunks; ++c)
+          {
+            const int cur = c & 1;
+            if (c + 1 < nchunks)
+              {
+                load(cur ^ 1, (uint32_t)(c + 1) * FKC);
+                asm volatile("cp.async.commit_group;");
+                asm volatile("cp.async.wait_group 1;");
+              }
+            else
+              asm volatile("cp.async.wait_group 0;");
+            __syncthreads();
+            const double *as = As[cur] + (wm + (lane >> 2)) * RLD + (lane & 3);
+            const double *bs = Bs[cur] + (lane & 3) * FLD + wn + (lane >> 2);
+#pragma unroll
+            for (int k4 = 0; k4 < FKC / 4; ++k4)
+              {
+                double a[2], bb[4];
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+                  a[j] = as[j * 8 * RLD + k4 * 4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                  bb[u] = bs[k4 * 4 * FLD + u * 8];
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+#pragma unroll
+                  for (int u = 0; u < 4; ++u)
+                    fe_dmma(acc[j][u][0], acc[j][u][1], a[j], bb[u]);
+              }
+            __syncthreads();
+          }
+        // b += 2 |psi|^2 occ over this tile's vectors (columns v0 + wn + u*8 + (lane&3)*2 + e)
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int e = 0; e < 2; ++e)
+            {
+              const uint32_t v = v0 + wn + u * 8 + (lane & 3) * 2 + e;
+              const double   o = (v < B) ? occ2[v] : 0.0;
+#pragma unroll
+              for (int j = 0; j < 2; ++j)
+                part[j] = fma(acc[j][u][e] * acc[j][u][e], o, part[j]);
+            }
+      }
+    // the 4 lanes of a quad share a row; then the two warp columns
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+      {
+        part[j] += __shfl_xor_sync(0xffffffffu, part[j], 1);
+        part[j] += __shfl_xor_sync(0xffffffffu, part[j], 2);
+        if ((lane & 3) == 0)
+          red[warp >> 2][wm + j * 8 + (lane >> 2)] = part[j];
+      }
+    __syncthreads();
+    if (tid < FT && q0 + tid < nq)
+      rho[cell.q_off + q0 + tid] = red[0][tid] + red[1][tid];
+  }
+
+  __global__ void
+  fe_weights_kernel(const double *jxw, const double *f, double *w, size_t n)
+  {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n)
+      w[i] = jxw[i] * f[i]; // hadamardProduct(jxwStorage, f) of FEBasisOperations.t.cpp:170-176
+  }
+} // namespace hx
+
+using namespace hx;
+
+extern "C"
+{
+  int
+  hx_fe_basis_create(hx_plan *plan, const hx_fe_basis_desc *d, hx_fe_basis **out)
+  {
+    HX_CHECK(plan && d && out, HX_ERR_INVALID, "null argument");
+    HX_CHECK(d->struct_size == sizeof(hx_fe_basis_desc), HX_ERR_INVALID, "hx_fe_basis_desc size mismatch (ABI)");
+    HX_CHECK(d->num_cell_quad && d->basis_data && d->jxw, HX_ERR_INVALID, "null array in hx_fe_basis_desc");
+    std::unique_ptr<hx_fe_basis> b(new hx_fe_basis());
+    b->plan       = plan;
+    b->same_basis = d->same_basis_in_all_cells != 0;
+    b->C          = plan->C;
+    b->h_nq.assign(d->num_cell_quad, d->num_cell_quad + plan->C);
+    std::vector<hx_fe_basis::Cell> cells(plan->C);
+    size_t                         boff = 0, ooff = 0, qoff = 0;
+    for (uint32_t c = 0; c < plan->C; ++c)
+      {
+        const uint32_t n = plan->h_ncd[c], nq = b->h_nq[c];
+        HX_CHECK(!b->same_basis || (n == plan->h_ncd[0] && nq == b->h_nq[0]), HX_ERR_INVALID,
+                 "same_basis_in_all_cells needs identical DoF and quadrature counts in every cell");
+        HX_CHECK(qoff + nq <= 0xffffffffull, HX_ERR_UNSUPPORTED, "more than 2^32 quadrature points on one rank");
+        cells[c].basis_off = b->same_basis ? 0 : boff;
+        cells[c].out_off   = ooff;
+        cells[c].q_off     = (uint32_t)qoff;
+        cells[c].n         = n;
+        cells[c].nq        = nq;
+        cells[c].ids_off   = plan->h_cell_off[c];
+        boff += (size_t)n * nq;
+        ooff += (size_t)n * n;
+        qoff += nq;
+        b->max_n = std::max(b->max_n, n);
+      }
+    b->n_quad_total = qoff;
+    b->S2           = ooff;
+    const size_t nbasis = b->same_basis ? (plan->C ? (size_t)plan->h_ncd[0] * b->h_nq[0] : 0) : boff;
+    HX_TRY(b->d_basis.upload(d->basis_data, nbasis));
+    HX_TRY(b->d_jxw.upload(d->jxw, qoff));
+    HX_TRY(b->d_w.alloc(qoff));
+    HX_TRY(b->d_cells.upload(cells));
+    *out = b.release();
+    return HX_OK;
+  }
+
+  int
+  hx_compute_rho(hx_fe_basis *b, const double *X_dev, uint32_t B, const double *occupation_host, double *rho,
+                 int rho_on_device)
+  {
+    HX_CHECK(b && X_dev && occupation_host && rho, HX_ERR_INVALID, "null argument");
+    HX_CHECK(B >= 1, HX_ERR_INVALID, "B must be >= 1");
+    hx_plan *p = b->plan;
+    if (b->C == 0 || b->n_quad_total == 0)
+      return HX_OK;
+    std::vector<double> occ2(B);
+    for (uint32_t i = 0; i < B; ++i)
+      occ2[i] = 2.0 * occupation_host[i]; // b += 2.0 * absSq(psi) * occupation (DensityCalculator.t.cpp:63-64)
+    if (b->d_occ.n < B)
+      HX_TRY(b->d_occ.alloc(B));
+    HX_CUDA(cudaMemcpyAsync(b->d_occ.p, occ2.data(), B * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    double *out = rho;
+    if (!rho_on_device)
+      {
+        if (b->d_rho.n < b->n_quad_total)
+          HX_TRY(b->d_rho.alloc(b->n_quad_total));
+        out = b->d_rho.p;
+      }
+    uint32_t max_nq = 0;
+    for (uint32_t q : b->h_nq)
+      max_nq = std::max(max_nq, q);
+    const uint32_t qt = (max_nq + FT - 1) / FT;
+    HX_CHECK(qt <= 65535, HX_ERR_UNSUPPORTED, "more than 4M quadrature points per cell are not supported");
+    p->mark("rho:begin");
+    dim3 grid(b->C, qt);
+    rho_kernel<<<grid, 256, 0, p->stream>>>(b->d_cells.p, b->d_basis.p, p->d_ids.p, X_dev, B, b->d_occ.p, out);
+    p->mark("rho");
+    p->launches++;
+    HX_CUDA(cudaGetLastError());
+    if (!rho_on_device)
+      HX_CUDA(cudaMemcpyAsync(rho, out, b->n_quad_total * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    HX_CUDA(cudaStreamSynchronize(p->stream)); // occ2 is a host temporary
+    return HX_OK;
+  }
+
+  int
+  hx_fe_basis_destroy(hx_fe_basis *b)
+  {
+    if (b)
+      {
+        cudaStreamSynchronize(b->plan->stream);
+        delete b;
+      }
+    return HX_OK;
+  }
+
+  int
+  hx_compute_fe_matrices(hx_fe_basis *b, const double *f, int f_on_device, const double *add_to_dev, double *cell_matrices_dev)
+  {
+    HX_CHECK(b && f && cell_matrices_dev, HX_ERR_INVALID, "null argument");
+    HX_CHECK(add_to_dev != cell_matrices_dev, HX_ERR_INVALID, "add_to and the output must not alias (mirrored tile writes)");
+    hx_plan *p = b->plan;
+    if (b->C == 0 || b->n_quad_total == 0)
+      return HX_OK;
+    const double *fd = f;
+    if (!f_on_device)
+      {
+        if (b->d_f.n < b->n_quad_total)
+          HX_TRY(b->d_f.alloc(b->n_quad_total));
+        HX_CUDA(cudaMemcpyAsync(b->d_f.p, f, b->n_quad_total * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+        fd = b->d_f.p;
+      }
+    fe_weights_kernel<<<(unsigned)((b->n_quad_total + 255) / 256), 256, 0, p->stream>>>(b->d_jxw.p, fd, b->d_w.p, b->n_quad_total);
+    const uint32_t tilesM = (b->max_n + FT - 1) / FT;
+    const uint32_t tiles  = tilesM * (tilesM + 1) / 2;
+    HX_CHECK(tiles <= 65535, HX_ERR_UNSUPPORTED, "cell matrices larger than 23000 x 23000 are not supported");
+    p->mark("fe-matrices:begin");
+    dim3 grid(b->C, tiles);
+    fe_matrices_kernel<<<grid, 256, 0, p->stream>>>(b->d_cells.p, b->d_basis.p, b->d_w.p, add_to_dev, cell_matrices_dev);
+    p->mark("fe-matrices");
+    p->launches += 2;
+    HX_CUDA(cudaGetLastError());
+    if (!f_on_device)
+      HX_CUDA(cudaStreamSynchronize(p->stream)); // the caller may reuse its host array
+    return HX_OK;
+  }
+}

@@ -171,6 +171,7 @@ class RankProblem:
     k_cell: Optional[np.ndarray] = None
     k_diag: Optional[np.ndarray] = None
     inhom_dirichlet: Optional[np.ndarray] = None    # f64 [nR]: inhomogeneities of the X constraint set
+    cell_edge: Optional[np.ndarray] = None          # f64 [C]: edge length of each local cell
     # nonlocal projectors
     proj_halo: Optional[HaloPattern] = None
     num_cell_proj: Optional[np.ndarray] = None      # u32 [C]
@@ -738,6 +739,7 @@ def build_problem(spec: MeshSpec, only_rank: Optional[int] = None) -> List[RankP
         prob.diag[clm] = lump_c[gid_to_node[l2g[clm]]]
         prob.diag_inv = np.where(prob.diag != 0.0, 1.0 / np.where(prob.diag != 0.0, prob.diag, 1.0), 0.0)
         prob.k_cell = k_cell
+        prob.cell_edge = spec.h * size[cells].astype(np.float64) / 2.0  # edge length of each local cell
         prob.k_diag = np.ones(halo.n_local)
         prob.k_diag[clm] = kdiag_g[gid_to_node[l2g[clm]]]
         if (~clm).any():  # enrichment rows: sum of the identity*vol blocks of the touching cells
@@ -810,3 +812,50 @@ def refine_ball(ncell, h, centers, radius) -> np.ndarray:
     for c in np.asarray(centers, float).reshape(-1, 3):
         mask |= np.linalg.norm(cen - c[None, None, None, :], axis=-1) <= radius
     return mask
+
+
+def fe_basis_data(prob: RankProblem, nq1d: Optional[int] = None, seed: int = 77):
+    """Synthetic FEBasisDataStorage arrays for FEBasisOperations::computeFEMatrices
+    (reference src/basis/FEBasisOperations.t.cpp:111-160): Gauss-Legendre tensor rule with nq1d points per direction
+    (default p + 2), basis values per cell as getBasisDataInCellRange lays them out (nq x n_c, DoF index fastest),
+    JxW per quadrature point.  Classical columns: the tensor-product Lagrange (GLL) shape functions in the cell-local
+    DoF order of the generator; enrichment columns: seeded smooth-ish values (counter-based on the global cell index, so
+    partition independent).  Returns dict(num_cell_quad, basis, jxw, same_basis, quad_weights_ref)."""
+    from numpy.polynomial import legendre as L
+    p = prob.p
+    nq1d = nq1d or (p + 2)
+    x, _ = gll_nodes_weights(p)
+    q1, w1 = L.leggauss(nq1d)
+    Lq = lagrange_eval(x, q1)                                   # [nq1d, p+1]
+    Ncl = np.einsum("ia,jb,kc->ijkabc", Lq, Lq, Lq).reshape(nq1d ** 3, (p + 1) ** 3)
+    wq = np.einsum("i,j,k->ijk", w1, w1, w1).ravel()
+    C = prob.n_cells
+    nq = nq1d ** 3
+    npc = (p + 1) ** 3
+    ncd = prob.num_cell_dofs.astype(np.int64)
+    same = bool(np.all(ncd == npc))
+    jxw = (wq[None, :] * ((prob.cell_edge / 2.0) ** 3)[:, None]).ravel()
+    if same:
+        basis = np.ascontiguousarray(Ncl).ravel()
+    else:
+        parts = []
+        for c in range(C):
+            ne = int(ncd[c] - npc)
+            if ne == 0:
+                parts.append(Ncl.ravel())
+            else:
+                crng = np.random.default_rng(seed + 15485863 * (int(prob.cell_global_index[c]) + 1))
+                E = 0.5 * crng.uniform(-1.0, 1.0, (nq, ne))
+                parts.append(np.concatenate([Ncl, E], axis=1).ravel())
+        basis = np.concatenate(parts)
+    return {"num_cell_quad": np.full(C, nq, np.uint32), "basis": basis, "jxw": jxw, "same_basis": same,
+            "quad_weights_ref": wq, "classical_basis": Ncl}
+
+
+def potential_at_quad_points(prob: RankProblem, nq: int, seed: int = 5) -> np.ndarray:
+    """A smooth-ish synthetic local potential at the quadrature points (counter-based on the global cell index)."""
+    out = np.empty((prob.n_cells, nq))
+    for c in range(prob.n_cells):
+        crng = np.random.default_rng(seed + 32452843 * (int(prob.cell_global_index[c]) + 1))
+        out[c] = -0.8 + 0.3 * crng.uniform(-1.0, 1.0) + 0.05 * crng.uniform(-1.0, 1.0, nq)
+    return out.ravel()

@@ -281,6 +281,40 @@ int hx_lanczos_extreme(hx_op *A, hx_op *Bop, hx_op *BInv, const double *initialG
                        int adaptive, double *eigenvalues_host, double *diagonal_host, double *subDiagonal_host,
                        uint32_t *krylovSize, int *status);
 
+/* ---- cell-matrix assembly, the step before the path each SCF iteration ---- */
+/* The per-cell data FEBasisOperations::computeFEMatrices reads from FEBasisDataStorage
+ * (src/basis/FEBasisOperations.t.cpp:111-160): quadrature points per cell, JxW, and the basis values per cell as
+ * getBasisDataInCellRange lays them out (nq_c x n_c, DoF index fastest).  HOST pointers, copied at creation.
+ * same_basis_in_all_cells = the reference's zeroStrideBasisVal (same quadrature rule in every cell and a fixed number of
+ * DoFs per cell, :133-137): basis_data then holds ONE matrix. */
+typedef struct hx_fe_basis hx_fe_basis;
+typedef struct hx_fe_basis_desc {
+  uint32_t        struct_size;
+  int32_t         same_basis_in_all_cells;
+  const uint32_t *num_cell_quad; /* nCellQuadraturePoints(c)  [C]                       */
+  const double *  basis_data;    /* concatenated per cell, or one matrix                */
+  const double *  jxw;           /* getJxWInAllCells()        [sum nq_c]                */
+} hx_fe_basis_desc;
+int hx_fe_basis_create(hx_plan *plan, const hx_fe_basis_desc *desc, hx_fe_basis **basis);
+int hx_fe_basis_destroy(hx_fe_basis *basis);
+/* FEBasisOperations::computeFEMatrices(IDENTITY, MULT, MULT, IDENTITY, f, cellWiseFEData)
+ * (src/basis/FEBasisOperations.t.cpp:2210-2243, 41-427): cell_matrices_dev[c] (n_c x n_c) =
+ * sum_q N[q,i] f[q] JxW[q] N[q,j] (+ add_to_dev[c] when given: the component sum of KohnShamOperatorContextFE::reinit,
+ * src/ksdft/KohnShamOperatorContextFE.t.cpp:1259-1282).  f: one value per quadrature point (host or device);
+ * output: DEVICE, S2 doubles, the layout hx_cellop_set_matrices(.., on_device = 1) takes. */
+int hx_compute_fe_matrices(hx_fe_basis *basis, const double *f_quad, int f_on_device, const double *add_to_dev,
+                           double *cell_matrices_dev);
+
+/* ---- density, the step after the path each SCF iteration ---- */
+/* DensityCalculator::computeRho(occupation, waveFunc, rho) (src/ksdft/DensityCalculator.t.cpp:283-437):
+ * rho[q] = sum_i 2 occupation[i] |psi_i(q)|^2 with psi_i(q) = sum_j N_c[q,j] X[cellLocalIds_c[j], i]
+ * (FEBasisOperations::interpolate, src/basis/FEBasisOperations.t.cpp:996-1275, then computeRhoInBatch, :37-70).
+ * X is used as it stands - like the reference, no ghost update or hanging-node fill happens here (the eigensolver
+ * leaves the wavefunctions ghost-updated, src/ksdft/KohnShamEigenSolver.t.cpp:333).  rho: one value per quadrature
+ * point, host or device. */
+int hx_compute_rho(hx_fe_basis *basis, const double *X_dev, uint32_t B, const double *occupation_host, double *rho,
+                   int rho_on_device);
+
 /* Chebyshev polynomial degree for a spectral upper bound: LinearEigenSolverDefaults::CHEBY_ORDER_LOOKUP through
  * getChebyPolynomialDegree (src/ksdft/Defaults.cpp:51-58, src/ksdft/KohnShamEigenSolver.t.cpp:37-46). */
 int hx_chebyshev_polynomial_degree(double unWantedSpectrumUpperBound, uint32_t *degree);

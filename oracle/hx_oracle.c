@@ -343,3 +343,73 @@ void orc_enr_block_apply(const double *Xenr, double *Yenr, u32 B, u32 nE, const 
 {
     if (nE) orc_dgemm('N', 'N', B, nE, nE, 1.0, Xenr, B, blk, nE, 0.0, Yenr, B);
 }
+
+/* FEBasisOperations::computeFEMatrices(IDENTITY, MULT, MULT, IDENTITY, f) =
+ * FEBasisOperationsInternal::BasisWeakFormKernelWithField (basis/FEBasisOperations.t.cpp:41-427): per cell
+ *   fxJxW[q]      = JxW[q] * f[q]                                   (hadamardProduct, :170-176)
+ *   fxJxWxN[q,i]  = fxJxW[q] * N[q,i]                               (scaleStridedVarBatched ColMajor, :276-292)
+ *   C (n x n col-major, ld n) = fxJxWxN('N') * N('C'), k = nq       (gemmStridedVarBatched, :392-411)
+ * i.e. C[i + j*n] = sum_q N[q*n+i] f[q] JxW[q] N[q*n+j].  basis: per cell nq_c x n_c, DoF index fastest
+ * (getBasisDataInCellRange); one shared matrix when zeroStride (sameQuadRuleInAllCells && !variableDofsPerCell, :133-137).
+ * The mathematically intended result is computed for every cell (the reference's zero-stride branch passes stride 0
+ * for the scaled operand, :345-346, which only gives this result for one cell per block). */
+void orc_compute_fe_matrices(u32 nCells, const u32 *numCellDofs, const u32 *numCellQuad, const double *basis,
+                             int zeroStride, const double *jxw, const double *f, double *out)
+{
+    size_t qoff = 0, boff = 0, coff = 0;
+    for (u32 c = 0; c < nCells; ++c) {
+        const u32 n = numCellDofs[c], nq = numCellQuad[c];
+        const double *N = zeroStride ? basis : basis + boff;
+        double *scaled = (double *)malloc(sizeof(double) * (size_t)n * nq);
+        for (u32 q = 0; q < nq; ++q) {
+            const double w = jxw[qoff + q] * f[qoff + q];
+            for (u32 i = 0; i < n; ++i) scaled[(size_t)q * n + i] = w * N[(size_t)q * n + i];
+        }
+        orc_dgemm('N', 'C', n, n, nq, 1.0, scaled, n, N, n, 0.0, out + coff, n);
+        free(scaled);
+        qoff += nq;
+        boff += (size_t)n * nq;
+        coff += (size_t)n * n;
+    }
+}
+
+/* DensityCalculator::computeRho (ksdft/DensityCalculator.t.cpp:283-437) in wavefunction batches of `batch`:
+ *   FEBasisOperations::interpolate (basis/FEBasisOperations.t.cpp:996-1275): per cell gather xCell (b x n_c, ld b)
+ *     through the cell->DoF map, psiQuad (b x nq, ld b) = xCell('N') * N('N')  (N: n_c x nq col-major = nq x n_c with
+ *     the DoF index fastest), i.e. psiQuad[q*b + i] = sum_j x[ids[j]*B + i0 + i] N[q*n + j];
+ *   computeRhoInBatch (:37-70): rhoBatch[q] = sum_i 2 |psi_i(q)|^2 occ_i;   rho += rhoBatch (quadrature::add, :343-348).
+ * X is used as given (no ghost update / constraint fill inside, as in the reference). */
+void orc_compute_rho(u32 nCells, const u32 *numCellDofs, const u32 *numCellQuad, const u32 *cellLocalIds,
+                     const double *basis, int zeroStride, const double *X, u32 B, u32 batch, const double *occupation,
+                     double *rho)
+{
+    size_t nqTot = 0;
+    for (u32 c = 0; c < nCells; ++c) nqTot += numCellQuad[c];
+    for (size_t q = 0; q < nqTot; ++q) rho[q] = 0.0;
+    for (u32 i0 = 0; i0 < B; i0 += batch) {
+        const u32 b = (B - i0) < batch ? (B - i0) : batch;
+        size_t qoff = 0, boff = 0, ioff = 0;
+        for (u32 c = 0; c < nCells; ++c) {
+            const u32 n = numCellDofs[c], nq = numCellQuad[c];
+            const double *N = zeroStride ? basis : basis + boff;
+            double *xc = (double *)malloc(sizeof(double) * (size_t)n * b);
+            double *psi = (double *)malloc(sizeof(double) * (size_t)nq * b);
+            for (u32 j = 0; j < n; ++j)
+                for (u32 i = 0; i < b; ++i) xc[(size_t)j * b + i] = X[(size_t)cellLocalIds[ioff + j] * B + i0 + i];
+            orc_dgemm('N', 'N', b, nq, n, 1.0, xc, b, N, n, 0.0, psi, b);
+            for (u32 q = 0; q < nq; ++q) {
+                double acc = 0.0;
+                for (u32 i = 0; i < b; ++i) {
+                    const double v = psi[(size_t)q * b + i];
+                    acc += 2.0 * (v * v) * occupation[i0 + i];
+                }
+                rho[qoff + q] = 1.0 * acc + 1.0 * rho[qoff + q];
+            }
+            free(xc);
+            free(psi);
+            qoff += nq;
+            boff += (size_t)n * nq;
+            ioff += n;
+        }
+    }
+}

@@ -531,6 +531,32 @@ class OracleWorld:
         return np.sqrt(tot)
 
 
+# 8f rank 2: FEBasisOperations::computeFEMatrices (basis/FEBasisOperations.t.cpp:41-427, 2210-2243)
+def compute_fe_matrices(num_cell_dofs, num_cell_quad, basis, jxw, f, zero_stride):
+    """Cell matrices C_c[i, j] = sum_q N_c[q, i] f[q] JxW[q] N_c[q, j], concatenated (S2 doubles).  basis: per cell
+    nq_c x n_c with the DoF index fastest (one shared matrix when zero_stride)."""
+    ncd, ncd_p = _u32(num_cell_dofs)
+    ncq, ncq_p = _u32(num_cell_quad)
+    basis, jxw, f = (np.ascontiguousarray(a, dtype=np.float64) for a in (basis, jxw, f))
+    out = np.zeros(int(np.sum(ncd.astype(np.int64) ** 2)))
+    lib().orc_compute_fe_matrices(C.c_uint32(len(ncd)), ncd_p, ncq_p, _f64(basis), C.c_int(int(zero_stride)), _f64(jxw),
+                                  _f64(f), _f64(out))
+    return out
+
+
+# 8f rank 3: DensityCalculator::computeRho (ksdft/DensityCalculator.t.cpp:283-437)
+def compute_rho(prob, num_cell_quad, basis, zero_stride, X, occupation, batch):
+    """rho[q] = sum_i 2 occ_i |psi_i(q)|^2 at the quadrature points of the rank's cells; X [n_local, B] as given."""
+    ncd, ncd_p = _u32(prob.num_cell_dofs)
+    ncq, ncq_p = _u32(num_cell_quad)
+    ids, ids_p = _u32(prob.cell_local_ids)
+    basis, X, occ = (np.ascontiguousarray(a, dtype=np.float64) for a in (basis, X, occupation))
+    rho = np.zeros(int(np.sum(ncq.astype(np.int64))))
+    lib().orc_compute_rho(C.c_uint32(len(ncd)), ncd_p, ncq_p, ids_p, _f64(basis), C.c_int(int(zero_stride)), _f64(X),
+                          C.c_uint32(X.shape[1]), C.c_uint32(batch), _f64(occ), _f64(rho))
+    return rho
+
+
 # ---------------------------------------------------------------------------
 # integer work the CUDA library derives at plan creation (bit-exact parity targets)
 # ---------------------------------------------------------------------------

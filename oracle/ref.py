@@ -76,6 +76,41 @@ def cell_gemm_batched(xcell, h_cell, ncd, B):
     return y
 
 
+def compute_fe_matrices(num_cell_dofs, num_cell_quad, basis, jxw, f, zero_stride, cell_block):
+    """FEBasisOperations::computeFEMatrices(IDENTITY, MULT, MULT, IDENTITY, f) assembled from the reference's own
+    hadamardProduct / scaleStridedVarBatched / gemmStridedVarBatched (ref_compute_fe_matrices in ref_shim.cpp)."""
+    ncd = np.ascontiguousarray(num_cell_dofs, dtype=np.uint32)
+    ncq = np.ascontiguousarray(num_cell_quad, dtype=np.uint32)
+    basis, jxw, f = (np.ascontiguousarray(a, dtype=np.float64) for a in (basis, jxw, f))
+    out = np.zeros(int(np.sum(ncd.astype(np.int64) ** 2)))
+    lib().ref_compute_fe_matrices(C.c_uint32(len(ncd)), ncd.ctypes.data_as(c_u32p), ncq.ctypes.data_as(c_u32p), f64(basis),
+                                  C.c_int(int(zero_stride)), f64(jxw), f64(f), C.c_uint32(cell_block), f64(out))
+    return out
+
+
+def interpolate(prob, num_cell_quad, basis, zero_stride, X):
+    """FEBasisOperations::interpolate assembled from the reference's own gather (copyFieldToCellWiseData) and
+    gemmStridedVarBatched with the operand conventions of basis/FEBasisOperations.t.cpp:1166-1262.  Returns psiQuad
+    (concatenated per cell, each nq_c x B with the vector index fastest)."""
+    B = X.shape[1]
+    n = np.ascontiguousarray(prob.num_cell_dofs, dtype=np.uint32)
+    nq = np.ascontiguousarray(num_cell_quad, dtype=np.uint32)
+    nm = len(n)
+    xcell = gather(np.ascontiguousarray(X), prob)
+    m = np.full(nm, B, np.uint32)
+    sa = (m * n).astype(np.uint32)
+    sb = np.zeros(nm, np.uint32) if zero_stride else (n * nq).astype(np.uint32)
+    sc = (m * nq).astype(np.uint32)
+    ta = (C.c_char * nm)(*([b"N"] * nm)); tb = (C.c_char * nm)(*([b"N"] * nm))
+    out = np.zeros(int(np.sum(sc.astype(np.int64))))
+    basis = np.ascontiguousarray(basis, dtype=np.float64)
+    p = lambda a: a.ctypes.data_as(c_u32p)
+    lib().ref_gemm_strided_var_batched(C.c_uint32(nm), ta, tb, p(sa), p(sb), p(sc), p(m), p(nq), p(n), C.c_double(1.0),
+                                       f64(np.ascontiguousarray(xcell)), p(m), f64(basis), p(n), C.c_double(0.0), f64(out),
+                                       p(m))
+    return out
+
+
 def gather(X, prob):
     """FECellWiseDataOperations::copyFieldToCellWiseData (basis/FECellWiseDataOperations.t.cpp:58-86), reference body."""
     B = X.shape[1]

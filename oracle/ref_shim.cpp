@@ -207,6 +207,86 @@ extern "C"
       *ctx());
   }
 
+  // FEBasisOperationsInternal::BasisWeakFormKernelWithField, IDENTITY/MULT/MULT/IDENTITY branch
+  // (src/basis/FEBasisOperations.t.cpp:41-427) = FEBasisOperations::computeFEMatrices(f): assembled from the
+  // reference's own compiled routines - hadamardProduct (f x JxW, :170-176), scaleStridedVarBatched (x N, :276-292),
+  // gemmStridedVarBatched('N','C') (:392-411) - in cell blocks; only the call sequence and the per-block size
+  // arrays of :240-350 are restated.  basis: per cell nq_c x n_c with the DoF index fastest (one matrix when zeroStride).
+  void
+  ref_compute_fe_matrices(unsigned        nCells,
+                          const unsigned *numCellDofs,
+                          const unsigned *numCellQuad,
+                          const double *  basis,
+                          int             zeroStrideBasisVal,
+                          const double *  jxw,
+                          const double *  f,
+                          unsigned        cellBlockSize,
+                          double *        cellWiseFEData)
+  {
+    size_type nQuadTotal = 0;
+    for (unsigned c = 0; c < nCells; ++c)
+      nQuadTotal += numCellQuad[c];
+    std::vector<double> fxJxW(nQuadTotal);
+    linearAlgebra::blasLapack::hadamardProduct<double, double, HOST>(nQuadTotal, jxw, f, fxJxW.data(), *ctx());
+    size_type NifNjStartOffset = 0, quadCellsInBlockOffSet = 0, basisOffset = 0;
+    for (unsigned cellStartId = 0; cellStartId < nCells; cellStartId += cellBlockSize)
+      {
+        const unsigned         cellEndId = std::min(cellStartId + cellBlockSize, nCells);
+        const unsigned         nb        = cellEndId - cellStartId;
+        std::vector<size_type> m1(nb, 1), nT(nb), kT(nb), stA(nb), stB(nb, 0), stC(nb);
+        std::vector<size_type> mS(nb), ldS(nb), strideA(nb, 0), strideB(nb), strideC(nb);
+        std::vector<char>      tA(nb, 'N'), tB(nb, 'C');
+        size_type              quadInBlock = 0, dofsxDofs = 0, quadxDofs = 0;
+        for (unsigned i = 0; i < nb; ++i)
+          {
+            nT[i] = numCellDofs[cellStartId + i];
+            kT[i] = numCellQuad[cellStartId + i];
+            stA[i] = kT[i];
+            if (!zeroStrideBasisVal)
+              stB[i] = nT[i] * kT[i];
+            stC[i] = nT[i] * kT[i];
+            mS[i] = ldS[i] = nT[i];
+            if (!zeroStrideBasisVal)
+              strideA[i] = nT[i] * kT[i];
+            strideB[i] = kT[i] * nT[i];
+            strideC[i] = nT[i] * nT[i];
+            quadInBlock += kT[i];
+            dofsxDofs += nT[i] * nT[i];
+            quadxDofs += nT[i] * kT[i];
+          }
+        std::vector<double> fxJxWxN(quadxDofs);
+        const double *      basisBlock = zeroStrideBasisVal ? basis : basis + basisOffset;
+        linearAlgebra::blasLapack::scaleStridedVarBatched<double, double, HOST>(
+          nb, linearAlgebra::blasLapack::Layout::ColMajor, linearAlgebra::blasLapack::ScalarOp::Identity,
+          linearAlgebra::blasLapack::ScalarOp::Identity, stA.data(), stB.data(), stC.data(), m1.data(), nT.data(), kT.data(),
+          fxJxW.data() + quadCellsInBlockOffSet, basisBlock, fxJxWxN.data(), *ctx());
+        // stride arrays exactly as the reference fills them (:338-349): strideA (of fxJxWxN!) is left 0 when
+        // zeroStrideBasisVal, strideB (of the basis block) is always k*n.  With a shared basis matrix and more than
+        // one cell per block every cell of the block therefore gets the first cell's scaled operand - callers that
+        // want the mathematically intended result in that mode pass cellBlockSize = 1 (see tests/test_fe_matrices.py)
+        std::vector<double> basisCopies;
+        const double *      gemmB = basisBlock;
+        if (zeroStrideBasisVal)
+          { // getBasisDataInCellRange fills one copy of the shared matrix per cell of the block
+            basisCopies.resize(quadxDofs);
+            size_type o = 0;
+            for (unsigned i = 0; i < nb; ++i)
+              {
+                std::memcpy(basisCopies.data() + o, basis, sizeof(double) * nT[i] * kT[i]);
+                o += nT[i] * kT[i];
+              }
+            gemmB = basisCopies.data();
+          }
+        linearAlgebra::blasLapack::gemmStridedVarBatched<double, double, HOST>(
+          nb, tA.data(), tB.data(), strideA.data(), strideB.data(), strideC.data(), mS.data(), mS.data(), kT.data(), 1.0,
+          fxJxWxN.data(), ldS.data(), gemmB, ldS.data(), 0.0, cellWiseFEData + NifNjStartOffset, ldS.data(), *ctx());
+        NifNjStartOffset += dofsxDofs;
+        quadCellsInBlockOffSet += quadInBlock;
+        if (!zeroStrideBasisVal)
+          basisOffset += quadxDofs;
+      }
+  }
+
   // ---- filters over caller-supplied operators ---------------------------------
   // cb(user, opId, X, Y, nLocal, B, updateGhostX, updateGhostY)
   typedef void (*apply_cb)(void *, int, double *, double *, unsigned, unsigned, int, int);
