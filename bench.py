@@ -315,6 +315,42 @@ def run_ours(args):
         except Exception as e:  # noqa: BLE001
             chfsi["error"] = str(e)[:300]
 
+        # ---- the steps either side of the path in one SCF iteration: cell matrices of the local
+        # potential (computeFEMatrices + reinit's component sum + re-tiling for the cell kernel) and the density ----
+        scf = {}
+        try:
+            if nranks == 1:
+                fe = synth.fe_basis_data(prob)
+                nqc = int(fe["num_cell_quad"][0])
+                feb = capi.FeBasis(plan, fe["num_cell_quad"], fe["basis"], fe["jxw"], fe["same_basis"])
+                vq = synth.potential_at_quad_points(prob, nqc)
+                d_kin = capi.DeviceBlock(prob.S2, 1, 0.5 * prob.k_cell)
+                d_h = capi.DeviceBlock(prob.S2, 1)
+                d_v = capi.DeviceBlock(vq.size, 1, vq)
+                feb.compute_fe_matrices(None, d_h, add_to=d_kin, f_device=d_v)
+                scf["compute_fe_matrices_ms"] = timed(lambda: feb.compute_fe_matrices(None, d_h, add_to=d_kin, f_device=d_v), 5)
+                H2 = capi.CellOp(plan, with_nonlocal=False)
+                H2.set_matrices_device(d_h.ptr)
+                scf["reinit_retile_ms"] = timed(lambda: H2.set_matrices_device(d_h.ptr), 3)
+                ncd64 = prob.num_cell_dofs.astype(np.int64)
+                tiles = (ncd64 + 63) // 64
+                fl_done = float(np.sum(2.0 * 64 * 64 * nqc * tiles * (tiles + 1) / 2))
+                fl_useful = float(np.sum(2.0 * ncd64 * ncd64 * nqc)) / 2.0
+                t_a = scf["compute_fe_matrices_ms"] * 1e-3
+                scf["compute_fe_matrices"] = {"quad_points_per_cell": nqc, "same_basis_in_all_cells": bool(fe["same_basis"]),
+                                              "dmma_tflops_issued": fl_done / t_a / 1e12,
+                                              "tflops_symmetric_minimum": fl_useful / t_a / 1e12,
+                                              "bytes_written_read": 16.0 * prob.S2, "gbs": 16.0 * prob.S2 / t_a / 1e9}
+                occ = np.clip(np.linspace(1.5, -0.5, B), 0.0, 1.0)
+                rho = feb.compute_rho(dX0, occ)
+                scf["compute_rho_ms"] = timed(lambda: feb.compute_rho(dX0, occ), 5)
+                fl_r = float(np.sum(2.0 * nqc * ncd64 * B))
+                scf["compute_rho"] = {"tflops": fl_r / (scf["compute_rho_ms"] * 1e-3) / 1e12, "rho_finite": bool(np.isfinite(rho).all()),
+                                      "electrons": float(np.dot(rho, fe["jxw"]))}
+                del feb, d_kin, d_h, d_v, H2, fe
+        except Exception as e:  # noqa: BLE001
+            scf["error"] = str(e)[:300]
+
         # ---- electrostatics: Laplace apply + Jacobi-preconditioned CG iterations on one right-hand side ----
         poisson = {}
         try:
@@ -432,6 +468,7 @@ def run_ours(args):
                          "what": "bare KohnShamOperatorContextFE::apply (updateGhostX=true), block resident in HBM"},
             "subspace": sub,
             "chfsi_pass": chfsi,
+            "scf_neighbours": scf,
             "poisson": poisson,
             "chebyshev_filter": {"degree": DEGREE, "seconds_per_scf_iter": ms_per_step * 1e-3,
                                  "ms_per_degree": ms_per_step / DEGREE, "fused_recurrence": True,

@@ -1047,6 +1047,92 @@ namespace dftefe
     };
   } // namespace linearAlgebra
 
+  namespace basis
+  {
+    // The arrays FEBasisDataStorage hands to FEBasisOperations (src/basis/FEBasisOperations.t.cpp:111-160): quadrature
+    // points per cell, JxW, basis values per cell (nq x n_c, DoF index fastest; ONE matrix when the same quadrature rule
+    // and DoF count hold in every cell)
+    struct FEBasisDataStorageArrays
+    {
+      std::vector<size_type> nCellQuadraturePoints;
+      std::vector<double>    basisDataInAllCells, JxWInAllCells;
+      bool                   sameBasisDataInAllCells = false;
+    };
+
+    // FEBasisOperations (src/basis/FEBasisOperations.h): the two members on either side of the H.X path
+    class FEBasisOperations
+    {
+    public:
+      FEBasisOperations(std::shared_ptr<const linearAlgebra::DeviceContext> ctx, const FEBasisDataStorageArrays &st)
+        : d_ctx(std::move(ctx))
+      {
+        utils::throwException(st.nCellQuadraturePoints.size() > 0, "no cells");
+        hx_fe_basis_desc d;
+        std::memset(&d, 0, sizeof(d));
+        d.struct_size             = sizeof(d);
+        d.same_basis_in_all_cells = st.sameBasisDataInAllCells;
+        d.num_cell_quad           = st.nCellQuadraturePoints.data();
+        d.basis_data              = st.basisDataInAllCells.data();
+        d.jxw                     = st.JxWInAllCells.data();
+        utils::hxCheck(hx_fe_basis_create(d_ctx->plan(), &d, &d_basis));
+        d_nQuad = st.JxWInAllCells.size();
+      }
+      FEBasisOperations(const FEBasisOperations &) = delete;
+      ~FEBasisOperations()
+      {
+        hx_fe_basis_destroy(d_basis);
+      }
+      // computeFEMatrices(IDENTITY, MULT, MULT, IDENTITY, f, cellWiseFEData) (src/basis/FEBasisOperations.t.cpp:
+      // 2210-2243): f = one value per quadrature point (host); cellWiseFEData = DEVICE array of cellMatrixSize() doubles;
+      // addTo (device, may be null) is added cell matrix by cell matrix (the reinit component sum)
+      void
+      computeFEMatrices(const std::vector<double> &f, double *cellWiseFEDataDevice, const double *addToDevice = nullptr) const
+      {
+        utils::throwException(f.size() == d_nQuad, "one value of f per quadrature point");
+        utils::hxCheck(hx_compute_fe_matrices(d_basis, f.data(), 0, addToDevice, cellWiseFEDataDevice));
+      }
+      hx_fe_basis *
+      handle() const
+      {
+        return d_basis;
+      }
+      size_t
+      nQuadraturePoints() const
+      {
+        return d_nQuad;
+      }
+
+    private:
+      std::shared_ptr<const linearAlgebra::DeviceContext> d_ctx;
+      hx_fe_basis *                                       d_basis = nullptr;
+      size_t                                              d_nQuad = 0;
+    };
+  } // namespace basis
+
+  namespace ksdft
+  {
+    // DensityCalculator::computeRho (src/ksdft/DensityCalculator.h, .t.cpp:283-437)
+    class DensityCalculator
+    {
+    public:
+      explicit DensityCalculator(std::shared_ptr<const basis::FEBasisOperations> feBasisOp)
+        : d_feBasisOp(std::move(feBasisOp))
+      {}
+      void
+      computeRho(const std::vector<double> &occupation, const linearAlgebra::DeviceMultiVector &waveFunc,
+                 std::vector<double> &rho) const
+      {
+        utils::throwException(occupation.size() == waveFunc.getNumberComponents(), "one occupation per wavefunction");
+        rho.resize(d_feBasisOp->nQuadraturePoints());
+        utils::hxCheck(hx_compute_rho(d_feBasisOp->handle(), waveFunc.data(), waveFunc.getNumberComponents(), occupation.data(),
+                                      rho.data(), 0));
+      }
+
+    private:
+      std::shared_ptr<const basis::FEBasisOperations> d_feBasisOp;
+    };
+  } // namespace ksdft
+
   namespace ksdft
   {
     // src/ksdft/Defaults.cpp:44-69

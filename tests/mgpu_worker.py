@@ -95,6 +95,30 @@ def main():
     nr = plan.l2_norms(dX)
     errs["l2"] = float(np.abs(nr - W.l2_norms(Xs)).max() / np.abs(nr).max())
 
+    # ---- the eigensolve around the path across ranks: Lanczos bounds, one ChebyshevFilteredEigenSolver pass (filter in
+    # column batches, Cholesky-Gram-Schmidt, Rayleigh-Ritz; Gram blocks all-reduced on the device), eigen-residuals ----
+    from oracle import eigensolver as es
+    Mop = capi.DiagOp(plan, mine.diag, mine.enr_block, capi.DIAG_OEFE_MASS)
+    A_ = lambda X_, Y_, gx, gy: W.hx_apply(X_, Y_, gx, gy)  # noqa: E731
+    M_ = lambda X_, Y_, gx, gy: W.m_apply(X_, Y_, gx, gy)  # noqa: E731
+    MI_ = lambda X_, Y_, gx, gy: W.minv_apply(X_, Y_, gx, gy)  # noqa: E731
+    lg = [np.random.default_rng(3 + q.rank).uniform(-0.5, 0.5, (q.n_local, 1)) for q in probs]
+    evo, do_, so_, sto = es.lanczos_extreme(W, A_, M_, MI_, [g.copy() for g in lg], 12)
+    ev, dg, sg, st = capi.lanczos_extreme(H, Mop, minv, plan.block(1, lg[rank]), 12)
+    assert st == 0 and sto == 0
+    errs["lanczos"] = float(max(np.abs(dg[:4] - do_[:4]).max() / np.abs(do_).max(), np.abs(sg[:4] - so_[:4]).max() / np.abs(so_).max()))
+    unwanted = float(evo[1] + so_[-1])
+    guesses = [x.copy() for x in Xs]
+    wo, sto, vo = es.chfsi_solve(W, guesses, np.zeros(B), 8, 10, -1.0, 6.0, unwanted)
+    dG, dV = plan.block(B, Xs[rank]), plan.block(B)
+    w, st = capi.chfsi_solve(H, Mop, minv, dG, dV, 8, 10, -1.0, 6.0, unwanted)
+    assert st == 0 and sto == 0, (st, sto)
+    errs["chfsi_ritz"] = float(np.abs(w - wo).max() / np.abs(wo).max())
+    rn = capi.eigen_residual_norms(H, Mop, dV, w, 8)
+    rno = es.eigen_residual_norms(W, vo, wo, 8)
+    errs["eig_residuals"] = float(np.abs(rn - rno).max() / np.abs(rno).max())
+    Mop.destroy()
+
     # ---- mesh without hanging nodes: the Chebyshev filter runs its fused path across ranks (recurrence applied in
     # the cell kernel's scatter for interior rows, row-list pass for the partition-face rows) ----
     spec2 = synth.MeshSpec(ncell=nc, p=4, atoms=atoms, n_enr_per_atom=2, enr_cutoff=1.2, n_proj_per_atom=2,
@@ -119,7 +143,7 @@ def main():
         assert plan.halo_transport() == want and plan2.halo_transport() == want, (plan.halo_transport(), want)
 
     tol = {"update_ghost": 0.0, "cheb_fused": 1e-11, "accumulate_add": 1e-14, "hx": 1e-12, "hx_x_modified": 1e-14, "cheb": 1e-11,
-           "xtopx": 1e-12, "l2": 1e-13}
+           "xtopx": 1e-12, "l2": 1e-13, "lanczos": 1e-10, "chfsi_ritz": 1e-9, "eig_residuals": 1e-6}
     bad = {k: v for k, v in errs.items() if not v <= tol[k]}
     print(f"[rank {rank}/{world}] halo transport {plan.halo_transport()} " + " ".join(f"{k}={v:.2e}" for k, v in errs.items()), flush=True)
     t = torch.tensor([len(bad)], device="cuda")
