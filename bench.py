@@ -343,7 +343,8 @@ def run_ours(args):
                                               "bytes_written_read": 16.0 * prob.S2, "gbs": 16.0 * prob.S2 / t_a / 1e9}
                 occ = np.clip(np.linspace(1.5, -0.5, B), 0.0, 1.0)
                 rho = feb.compute_rho(dX0, occ)
-                scf["compute_rho_ms"] = timed(lambda: feb.compute_rho(dX0, occ), 5)
+                d_rho = capi.DeviceBlock(rho.size, 1)
+                scf["compute_rho_ms"] = timed(lambda: feb.compute_rho_device(dX0, occ, d_rho), 5)
                 fl_r = float(np.sum(2.0 * nqc * ncd64 * B))
                 scf["compute_rho"] = {"tflops": fl_r / (scf["compute_rho_ms"] * 1e-3) / 1e12, "rho_finite": bool(np.isfinite(rho).all()),
                                       "electrons": float(np.dot(rho, fe["jxw"]))}

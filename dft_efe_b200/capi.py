@@ -539,6 +539,11 @@ class FeBasis:
         check(lib().hx_compute_rho(self.h, X.p, C.c_uint32(X.B), op, rho.ctypes.data_as(f64p), C.c_int(0)))
         return rho
 
+    def compute_rho_device(self, X: DeviceBlock, occupation, rho: DeviceBlock):
+        """same, rho left on the device (one value per quadrature point)"""
+        o, op = _f64(occupation)
+        check(lib().hx_compute_rho(self.h, X.p, C.c_uint32(X.B), op, rho.p, C.c_int(1)))
+
     def destroy(self):
         if self.h:
             lib().hx_fe_basis_destroy(self.h)

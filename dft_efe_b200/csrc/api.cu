@@ -1547,7 +1547,7 @@ extern "C"
     double *xin, *xout;
     HX_TRY(p->get_scratch(2, &xin));
     HX_TRY(p->get_scratch(3, &xout));
-    HX_TRY(p->ensure_small((size_t)B * batch * 3 + (size_t)604 * 4096));
+    HX_TRY(p->ensure_small((size_t)B * batch + (size_t)1300 * 4096)); // S block + split-K partials (gram_block)
     HX_TRY(p->ensure_pinned((size_t)B * batch * sizeof(double)));
     for (size_t i = 0; i < (size_t)B * B; ++i)
       S_host[i] = 0.0;

@@ -80,8 +80,12 @@ namespace hx
               }
           }
         else
-          {
-            d[0] = (q < nq && c < n) ? s[0] : 0.0;
+          { // last odd column / rows beyond the rule: still asynchronous (a synchronous load here would stall the
+            // whole stage on the global latency)
+            if (q < nq && c < n)
+              fe_cp8(d, s);
+            else
+              d[0] = 0.0;
             d[1] = 0.0;
           }
       }
@@ -193,69 +197,95 @@ namespace hx
   // 8f rank 3: DensityCalculator::computeRho (src/ksdft/DensityCalculator.t.cpp:283-437) =
   //   FEBasisOperations::interpolate (src/basis/FEBasisOperations.t.cpp:996-1275: per cell psiQuad (B x nq) =
   //   xCell (B x n_c) . N (n_c x nq)) followed by computeRhoInBatch (:37-70: rho[q] = sum_i 2 |psi_i(q)|^2 occ_i).
-  // One CTA = 64 quadrature points of one cell: for every 64-wide tile of wavefunctions it gathers the cell's rows of X
+  // One CTA = up to 256 quadrature points of one cell: for every 32-wide pass over the wavefunctions it gathers the cell's rows of X
   // (cell -> DoF map) in chunks of 16 DoFs next to the matching basis values, runs the DMMA contraction, squares the
   // accumulators, weights them with 2 occ_i and keeps one partial sum per quadrature point; psi at the quadrature
   // points never goes to memory.  Fixed summation order (no atomics).
   constexpr int RLD = FKC + 4;
-  __global__ void __launch_bounds__(256)
+  constexpr int RQ  = 256;    // quadrature points per CTA (8 warps x 32 rows)
+  constexpr int RV  = 32;     // wavefunctions per pass
+  constexpr int RBL = RV + 4; // padded row of the gathered X tile
+  constexpr size_t RHO_SMEM = (size_t)2 * (RQ * RLD + FKC * RBL) * sizeof(double);
+  __global__ void __launch_bounds__(256, 2)
   rho_kernel(const hx_fe_basis::Cell *cells, const double *basis, const uint32_t *ids, const double *X, uint32_t B,
              const double *occ2, double *rho)
   {
-    __shared__ __align__(16) double As[2][FT * RLD];  // basis values [q][dof chunk]
-    __shared__ __align__(16) double Bs[2][FKC * FLD]; // gathered X rows [dof chunk][vectors]
-    __shared__ double               red[2][FT];
-    const hx_fe_basis::Cell         cell = cells[blockIdx.x];
-    const uint32_t                  n = cell.n, nq = cell.nq;
-    const uint32_t                  q0 = blockIdx.y * FT;
+    extern __shared__ __align__(16) double rsm[];
+    double *                               As0 = rsm;                 // [2][RQ * RLD]  basis values [q][dof chunk]
+    double *                               Bs0 = rsm + 2 * RQ * RLD;  // [2][FKC * RBL] gathered X rows [dof chunk][vectors]
+    const hx_fe_basis::Cell                cell = cells[blockIdx.x];
+    const uint32_t                         n = cell.n, nq = cell.nq;
+    const uint32_t                         q0 = blockIdx.y * RQ;
     if (q0 >= nq)
       return;
     const int       tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double *  N   = basis + cell.basis_off;
     const uint32_t *cid = ids + cell.ids_off;
     const bool      alignedX = ((B & 1u) == 0) && ((((uintptr_t)X) & 15) == 0);
-    const int       wm = (warp & 3) * 16, wn = (warp >> 2) * 32;
-    double          part[2] = {0.0, 0.0}; // rows wm + j*8 + (lane >> 2)
+    const bool      alignedN = ((n & 1u) == 0) && ((cell.basis_off & 1ull) == 0);
+    const int       wm       = warp * 32;
+    // a warp whose 32 rows lie beyond the cell's quadrature points still helps loading, but skips the math
+    const bool      active = q0 + wm < nq;
+    double          part[4] = {0.0, 0.0, 0.0, 0.0}; // rows wm + j*8 + (lane >> 2)
     const int       nchunks = (int)((n + FKC - 1) / FKC);
-    for (uint32_t v0 = 0; v0 < B; v0 += FT)
+    for (uint32_t v0 = 0; v0 < B; v0 += RV)
       {
-        double acc[2][4][2];
+        double acc[4][4][2];
 #pragma unroll
-        for (int j = 0; j < 2; ++j)
+        for (int j = 0; j < 4; ++j)
 #pragma unroll
           for (int u = 0; u < 4; ++u)
             acc[j][u][0] = acc[j][u][1] = 0.0;
         auto load = [&](int buf, uint32_t k0) {
-          // A: 64 quadrature points x 16 DoFs; element (q, j) at N[q*n + j]
+          double *Ab = As0 + buf * RQ * RLD, *Bb = Bs0 + buf * FKC * RBL;
+          // A: RQ quadrature points x 16 DoFs; element (q, j) at N[q*n + j]: 2048 pairs, 8 per thread
 #pragma unroll
-          for (int it = 0; it < 4; ++it)
-            {
-              const int      ch = tid + it * 256; // 1024 elements
-              const int      r = ch >> 4, kk = ch & 15;
-              const uint32_t q = q0 + r, j = k0 + kk;
-              double *       d = As[buf] + r * RLD + kk;
-              if (q < nq && j < n)
-                fe_cp8(d, N + (size_t)q * n + j);
-              else
-                *d = 0.0;
-            }
-          // B: 16 DoFs x 64 vectors gathered through the cell -> DoF map
-#pragma unroll
-          for (int it = 0; it < 2; ++it)
+          for (int it = 0; it < 8; ++it)
             {
               const int      ch = tid + it * 256;
-              const int      r = ch >> 5, cc = (ch & 31) * 2;
-              const uint32_t j = k0 + r, v = v0 + cc;
-              double *       d = Bs[buf] + r * FLD + cc;
-              if (j < n && v + 1 < B && alignedX)
-                fe_cp16(d, X + (size_t)cid[j] * B + v);
+              const int      r = ch >> 3, kk = (ch & 7) * 2;
+              const uint32_t q = q0 + r, j = k0 + kk;
+              double *       d = Ab + r * RLD + kk;
+              const double * s = N + (size_t)q * n + j;
+              if (q < nq && j + 1 < n)
+                {
+                  if (alignedN)
+                    fe_cp16(d, s);
+                  else
+                    {
+                      fe_cp8(d, s);
+                      fe_cp8(d + 1, s + 1);
+                    }
+                }
               else
                 {
-                  const double *s = (j < n) ? X + (size_t)cid[j] * B : nullptr;
-                  d[0]            = (s && v < B) ? s[v] : 0.0;
-                  d[1]            = (s && v + 1 < B) ? s[v + 1] : 0.0;
+                  if (q < nq && j < n)
+                    fe_cp8(d, s);
+                  else
+                    d[0] = 0.0;
+                  d[1] = 0.0;
                 }
             }
+          // B: 16 DoFs x 32 vectors gathered through the cell -> DoF map: 256 pairs, one per thread
+          {
+            const int      r = tid >> 4, cc = (tid & 15) * 2;
+            const uint32_t j = k0 + r, v = v0 + cc;
+            double *       d = Bb + r * RBL + cc;
+            if (j < n && v + 1 < B && alignedX)
+              fe_cp16(d, X + (size_t)cid[j] * B + v);
+            else
+              {
+                const double *s = (j < n) ? X + (size_t)cid[j] * B : nullptr;
+                if (s && v < B)
+                  fe_cp8(d, s + v);
+                else
+                  d[0] = 0.0;
+                if (s && v + 1 < B)
+                  fe_cp8(d + 1, s + v + 1);
+                else
+                  d[1] = 0.0;
+              }
+          }
         };
         load(0, 0);
         asm volatile("cp.async.commit_group;");
@@ -271,51 +301,52 @@ namespace hx
             else
               asm volatile("cp.async.wait_group 0;");
             __syncthreads();
-            const double *as = As[cur] + (wm + (lane >> 2)) * RLD + (lane & 3);
-            const double *bs = Bs[cur] + (lane & 3) * FLD + wn + (lane >> 2);
-#pragma unroll
-            for (int k4 = 0; k4 < FKC / 4; ++k4)
+            if (active)
               {
-                double a[2], bb[4];
+                const double *as = As0 + cur * RQ * RLD + (wm + (lane >> 2)) * RLD + (lane & 3);
+                const double *bs = Bs0 + cur * FKC * RBL + (lane & 3) * RBL + (lane >> 2);
 #pragma unroll
-                for (int j = 0; j < 2; ++j)
-                  a[j] = as[j * 8 * RLD + k4 * 4];
+                for (int k4 = 0; k4 < FKC / 4; ++k4)
+                  {
+                    double a[4], bb[4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u)
-                  bb[u] = bs[k4 * 4 * FLD + u * 8];
+                    for (int j = 0; j < 4; ++j)
+                      a[j] = as[j * 8 * RLD + k4 * 4];
 #pragma unroll
-                for (int j = 0; j < 2; ++j)
+                    for (int u = 0; u < 4; ++u)
+                      bb[u] = bs[k4 * 4 * RBL + u * 8];
 #pragma unroll
-                  for (int u = 0; u < 4; ++u)
-                    fe_dmma(acc[j][u][0], acc[j][u][1], a[j], bb[u]);
+                    for (int j = 0; j < 4; ++j)
+#pragma unroll
+                      for (int u = 0; u < 4; ++u)
+                        fe_dmma(acc[j][u][0], acc[j][u][1], a[j], bb[u]);
+                  }
               }
             __syncthreads();
           }
-        // b += 2 |psi|^2 occ over this tile's vectors (columns v0 + wn + u*8 + (lane&3)*2 + e)
+        // b += 2 |psi|^2 occ over this pass's vectors (columns v0 + u*8 + (lane&3)*2 + e)
 #pragma unroll
         for (int u = 0; u < 4; ++u)
 #pragma unroll
           for (int e = 0; e < 2; ++e)
             {
-              const uint32_t v = v0 + wn + u * 8 + (lane & 3) * 2 + e;
+              const uint32_t v = v0 + u * 8 + (lane & 3) * 2 + e;
               const double   o = (v < B) ? occ2[v] : 0.0;
 #pragma unroll
-              for (int j = 0; j < 2; ++j)
+              for (int j = 0; j < 4; ++j)
                 part[j] = fma(acc[j][u][e] * acc[j][u][e], o, part[j]);
             }
       }
-    // the 4 lanes of a quad share a row; then the two warp columns
+    // the 4 lanes of a quad share a row
 #pragma unroll
-    for (int j = 0; j < 2; ++j)
+    for (int j = 0; j < 4; ++j)
       {
         part[j] += __shfl_xor_sync(0xffffffffu, part[j], 1);
         part[j] += __shfl_xor_sync(0xffffffffu, part[j], 2);
-        if ((lane & 3) == 0)
-          red[warp >> 2][wm + j * 8 + (lane >> 2)] = part[j];
+        const uint32_t q = q0 + wm + j * 8 + (lane >> 2);
+        if ((lane & 3) == 0 && q < nq)
+          rho[cell.q_off + q] = part[j];
       }
-    __syncthreads();
-    if (tid < FT && q0 + tid < nq)
-      rho[cell.q_off + q0 + tid] = red[0][tid] + red[1][tid];
   }
 
   __global__ void
@@ -397,11 +428,17 @@ extern "C"
     uint32_t max_nq = 0;
     for (uint32_t q : b->h_nq)
       max_nq = std::max(max_nq, q);
-    const uint32_t qt = (max_nq + FT - 1) / FT;
-    HX_CHECK(qt <= 65535, HX_ERR_UNSUPPORTED, "more than 4M quadrature points per cell are not supported");
+    const uint32_t qt = (max_nq + RQ - 1) / RQ;
+    HX_CHECK(qt <= 65535, HX_ERR_UNSUPPORTED, "more than 16M quadrature points per cell are not supported");
+    static bool attr_set = false;
+    if (!attr_set)
+      {
+        HX_CUDA(cudaFuncSetAttribute(rho_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RHO_SMEM));
+        attr_set = true;
+      }
     p->mark("rho:begin");
     dim3 grid(b->C, qt);
-    rho_kernel<<<grid, 256, 0, p->stream>>>(b->d_cells.p, b->d_basis.p, p->d_ids.p, X_dev, B, b->d_occ.p, out);
+    rho_kernel<<<grid, 256, RHO_SMEM, p->stream>>>(b->d_cells.p, b->d_basis.p, p->d_ids.p, X_dev, B, b->d_occ.p, out);
     p->mark("rho");
     p->launches++;
     HX_CUDA(cudaGetLastError());

@@ -45,7 +45,7 @@ namespace hx
     double *xin, *xout;
     HX_TRY(p->get_scratch(2, &xin));
     HX_TRY(p->get_scratch(3, &xout));
-    HX_TRY(p->ensure_small((size_t)B * batch * 3 + (size_t)604 * 4096));
+    HX_TRY(p->ensure_small((size_t)B * batch + (size_t)1300 * 4096)); // S block + split-K partials (gram_block)
     for (uint32_t j0 = 0; j0 < B; j0 += batch)
       {
         const uint32_t b = std::min(batch, B - j0);

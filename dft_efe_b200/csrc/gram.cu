@@ -173,7 +173,14 @@ namespace hx
     const uint32_t M = B - j0, N = b;
     const uint32_t tilesM = (M + GT - 1) / GT, tilesN = (N + GT - 1) / GT;
     const uint32_t tiles  = tilesM * tilesN;
-    uint32_t       nSplit = (592 + tiles - 1) / tiles;
+    // tiles on and below the diagonal do the work (the others exit at once): split K so that about 4 CTAs per SM
+    // (64 registers x 256 threads) are resident and all of them run in one wave
+    uint32_t active = 0;
+    for (uint32_t tn = 0; tn < tilesN; ++tn)
+      active += tilesM > tn ? tilesM - tn : 0;
+    active = std::max(active, 1u);
+    const uint32_t slots    = 4u * (uint32_t)std::max(p->sm_count, 1);
+    uint32_t       nSplit   = std::max(1u, slots / active);
     const uint32_t maxSplit = (uint32_t)std::max<size_t>(1, (nOwned + 255) / 256);
     nSplit                  = std::max(1u, std::min(nSplit, maxSplit));
     size_t slab             = (nOwned + nSplit - 1) / nSplit;
