@@ -46,6 +46,11 @@ def workload_spec(name: str, nranks: int):
     elif name == "small":
         nc, p, B, h = (8, 8, 8 * nranks), 4, 32, 0.8
         n_atoms = 2 * nranks
+    elif name == "c3":
+        # BASELINE configs[2]: benzene-dimer-like, FE order 6, ~7 M DoFs, 128-vector block; the mesh is FIXED and cut
+        # into nranks z-slabs (strong scaling; 31 GB of cell matrices in total, meant for 4 or 8 GPUs)
+        nc, p, B, h = (32, 32, 32), 6, 128, 0.8
+        n_atoms = 24
     else:
         raise SystemExit(f"unknown workload {name}")
     rng = np.random.default_rng(7)
@@ -436,7 +441,7 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": DEGREE * N_global * B / (ms_per_step * 1e-3) / 1e9, "unit": UNIT, "n_gpus": nranks,
             "steps": args.steps, "warmup": warm, "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": "strong" if args.workload == "c3" else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"{args.workload}: ChebyshevFilter degree {DEGREE} (= {DEGREE} H.X applies + M^-1 + recurrence "
                                    f"per step) on a CH4-like PSP OrthoEFE problem, FE order {spec.p}, "
                                    f"{spec.ncell[0]}x{spec.ncell[1]}x{spec.ncell[2]} cells, {N_global} DoFs, B={B}, "
@@ -496,7 +501,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c2", "small"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "small", "c3"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":
