@@ -9,6 +9,10 @@
 //
 // Both stage 64-wide operand tiles in shared memory with cp.async (16-B, double-buffered) and feed
 // mma.sync.m8n8k4.f64 from conflict-free padded rows.
+#include <stdlib.h>
+
+#include <algorithm>
+
 #include "hx_internal.h"
 
 namespace hx
@@ -166,11 +170,110 @@ namespace hx
     S[i] = s;
   }
 
+  // ---------------------------------------------------------------------------------------------------
+  // Narrow blocks (B - j0 <= 32 and b <= 32: the C1 / C2 shapes): the Gram block is one 32 x 32 tile and the GEMM is
+  // HBM-bound (16 N B bytes), so there is nothing to stage: every warp streams its own k-steps (4 rows of X and of
+  // Op X) straight from global memory into DMMA fragments - each 256-B row segment is consumed whole by the warp -
+  // and the 8 warps of a CTA are summed in warp order through one shared tile (deterministic).  grid = row slabs.
+  __global__ void __launch_bounds__(256)
+  gram_small_kernel(const double *X, uint32_t B, uint32_t j0, const double *O, uint32_t b, size_t nOwned, uint32_t M,
+                    uint32_t N, size_t slab, double *W)
+  {
+    __shared__ double tile[32 * 33];
+    const int         tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const size_t      kb = (size_t)blockIdx.x * slab;
+    const size_t      ke = kb + slab < nOwned ? kb + slab : nOwned;
+    double            acc[4][4][2];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int t = 0; t < 4; ++t)
+        acc[j][t][0] = acc[j][t][1] = 0.0;
+    const uint32_t mi = lane >> 2; // row of the fragment inside an 8-wide tile
+    auto           load = [&](size_t r0, double(&a)[4], double(&q)[4]) {
+      const size_t row = r0 + (lane & 3);
+      const bool   ok  = row < ke;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        {
+          const uint32_t m = j * 8 + mi;
+          a[j]             = (ok && m < M) ? __ldg(X + row * B + j0 + m) : 0.0;
+          q[j]             = (ok && m < N) ? __ldg(O + row * b + m) : 0.0;
+        }
+    };
+    double a0[4], q0[4], a1[4], q1[4];
+    size_t r = kb + (size_t)warp * 4;
+    if (r < ke)
+      load(r, a0, q0);
+    for (; r < ke; r += 64)
+      {
+        const bool more = r + 32 < ke;
+        if (more)
+          load(r + 32, a1, q1);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int t = 0; t < 4; ++t)
+            dmma884g(acc[j][t][0], acc[j][t][1], a0[j], q0[t]);
+        if (!more)
+          break;
+        if (r + 64 < ke)
+          load(r + 64, a0, q0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int t = 0; t < 4; ++t)
+            dmma884g(acc[j][t][0], acc[j][t][1], a1[j], q1[t]);
+      }
+    // sum the warps in warp order
+    for (int w = 0; w < 8; ++w)
+      {
+        if (warp == w)
+          {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+              for (int t = 0; t < 4; ++t)
+#pragma unroll
+                for (int e = 0; e < 2; ++e)
+                  {
+                    double *d = tile + (j * 8 + mi) * 33 + t * 8 + (lane & 3) * 2 + e;
+                    *d        = (w == 0) ? acc[j][t][e] : *d + acc[j][t][e];
+                  }
+          }
+        __syncthreads();
+      }
+    double *w_ = W + (size_t)blockIdx.x * M * N;
+    for (uint32_t i = tid; i < M * N; i += 256)
+      {
+        const uint32_t rr = i % M, cc = i / M;
+        w_[i]             = tile[rr * 33 + cc];
+      }
+  }
+
   int
   gram_block(hx_plan *p, const double *X, uint32_t B, uint32_t j0, const double *OpXb, uint32_t b, size_t nOwned,
              double *S_dev)
   {
     const uint32_t M = B - j0, N = b;
+    if (M <= 32 && N <= 32 && !getenv("HXB200_GRAM_TILED"))
+      {
+        // narrow block: one 32 x 32 tile, split over row slabs (2 resident CTAs per SM, >= 256 rows each)
+        uint32_t nSplit = 2u * (uint32_t)std::max(p->sm_count, 1);
+        nSplit          = (uint32_t)std::max<size_t>(1, std::min<size_t>(nSplit, (nOwned + 255) / 256));
+        size_t slab     = (nOwned + nSplit - 1) / nSplit;
+        slab            = std::max<size_t>(32, (slab + 31) / 32 * 32);
+        nSplit          = (uint32_t)std::max<size_t>(1, (nOwned + slab - 1) / slab);
+        double *W = S_dev + (size_t)M * N;
+        HX_CHECK(p->d_small.p && S_dev >= p->d_small.p &&
+                   (size_t)(S_dev - p->d_small.p) + (size_t)M * N * (1 + (size_t)nSplit) <= p->d_small.n,
+                 HX_ERR_INVALID, "gram workspace too small");
+        gram_small_kernel<<<nSplit, 256, 0, p->stream>>>(X, B, j0, OpXb, b, nOwned, M, N, slab, W);
+        gram_reduce_kernel<<<(unsigned)(((size_t)M * N + 255) / 256), 256, 0, p->stream>>>(W, M, N, nSplit, S_dev);
+        p->launches += 2;
+        HX_CUDA(cudaGetLastError());
+        return HX_OK;
+      }
     const uint32_t tilesM = (M + GT - 1) / GT, tilesN = (N + GT - 1) / GT;
     const uint32_t tiles  = tilesM * tilesN;
     // tiles on and below the diagonal do the work (the others exit at once): split K so that about 4 CTAs per SM
@@ -319,12 +422,85 @@ namespace hx
         }
   }
 
+  // Narrow blocks (B <= 32): the whole rotation matrix lives in registers as DMMA B fragments, every warp streams
+  // tiles of 16 rows of X straight from global memory, and writes them back IN PLACE (a row of the result depends on
+  // that row of X only, and the warp holds all of it before it stores) - no staging buffer, no copy back: 16 N B bytes.
+  __global__ void __launch_bounds__(128, 3)
+  rotate_small_kernel(double *X, uint32_t B, size_t nRows, const double *Q)
+  {
+    const int      lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t ki = lane & 3, mi = lane >> 2;
+    double         q[8][4];
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks)
+#pragma unroll
+      for (int t = 0; t < 4; ++t)
+        {
+          const uint32_t k = ks * 4 + ki, n = t * 8 + mi;
+          q[ks][t]         = (k < B && n < B) ? __ldg(Q + (size_t)k * B + n) : 0.0;
+        }
+    const size_t nTiles = (nRows + 15) / 16;
+    for (size_t rt = (size_t)blockIdx.x * 4 + warp; rt < nTiles; rt += (size_t)gridDim.x * 4)
+      {
+        double a[2][8];
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+          {
+            const size_t row = rt * 16 + j * 8 + mi;
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks)
+              {
+                const uint32_t k = ks * 4 + ki;
+                a[j][ks]         = (row < nRows && k < B) ? X[row * B + k] : 0.0;
+              }
+          }
+        double acc[2][4][2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+          for (int t = 0; t < 4; ++t)
+            acc[j][t][0] = acc[j][t][1] = 0.0;
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks)
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+              dmma884g(acc[j][t][0], acc[j][t][1], a[j][ks], q[ks][t]);
+        __syncwarp(); // every lane's loads of these 16 rows have been consumed by the (warp-synchronous) mma
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+          {
+            const size_t row = rt * 16 + j * 8 + mi;
+            if (row < nRows)
+#pragma unroll
+              for (int t = 0; t < 4; ++t)
+#pragma unroll
+                for (int e = 0; e < 2; ++e)
+                  {
+                    const uint32_t c = t * 8 + ki * 2 + e;
+                    if (c < B)
+                      X[row * B + c] = acc[j][t][e];
+                  }
+          }
+      }
+  }
+
   int
   rotate(hx_plan *p, double *X, uint32_t B, size_t nOwned, const double *Q_dev, int transpose, int lowerTri,
          double *tmp)
   {
     if (nOwned == 0)
       return HX_OK;
+    if (B <= 32 && !getenv("HXB200_GRAM_TILED"))
+      {
+        const size_t nTiles = (nOwned + 15) / 16;
+        unsigned     grid   = (unsigned)std::min<size_t>((nTiles + 3) / 4, (size_t)3 * std::max(p->sm_count, 1));
+        rotate_small_kernel<<<grid, 128, 0, p->stream>>>(X, B, nOwned, Q_dev);
+        p->launches++;
+        HX_CUDA(cudaGetLastError());
+        return HX_OK;
+      }
     const uint32_t tilesN  = (B + GT - 1) / GT;
     const size_t   tilesM  = (nOwned + GT - 1) / GT;
     const int      aligned = (B % 2 == 0) && (((uintptr_t)X & 15) == 0) && (((uintptr_t)Q_dev & 15) == 0);

@@ -228,3 +228,27 @@ def test_converged_kohn_sham_eigenvalues(capi, setup, residual_filter, refined):
     Vl = np.zeros((p.n_local, B)); Vl[:p.n_owned] = V
     W.m_apply([Vl], MV, True, False)
     assert np.abs(V.T @ MV[0][:p.n_owned] - np.eye(B)).max() < 1e-10
+
+
+def test_error_paths_of_the_eigensolve_entry_points(capi, setup):
+    """the error convention of the boundary: bad arguments come back as HxError (HX_ERR_INVALID), never a crash"""
+    p, W, plan, H, M, MInv = setup
+    B = plan.max_block
+    X = synth.make_block(p, B)
+    dG, dV = plan.block(B, X), plan.block(B)
+    with pytest.raises(capi.HxError):  # guess and eigenvectors must be different blocks
+        capi.chfsi_solve(H, M, MInv, dG, dG, 4, 5, -1.0, 6.0, 2500.0)
+    big = capi.DeviceBlock(p.n_local, B + 1)
+    with pytest.raises(capi.HxError):  # wider than max_block
+        capi.chfsi_solve(H, M, MInv, big, capi.DeviceBlock(p.n_local, B + 1), 4, 5, -1.0, 6.0, 2500.0)
+    with pytest.raises(capi.HxError):  # degree 0
+        capi.chfsi_solve(H, M, MInv, dG, dV, 4, 0, -1.0, 6.0, 2500.0)
+    with pytest.raises(capi.HxError):  # Krylov space smaller than the number of wanted eigenvalues
+        capi.lanczos_extreme(H, M, MInv, plan.block(1, X[:, :1].copy()), 1, 1, 1)
+    other = capi.Plan(p, max_block=4)
+    M2 = capi.DiagOp(other, p.diag, p.enr_block, capi.DIAG_OEFE_MASS)
+    with pytest.raises(capi.HxError):  # operators of different plans
+        capi.eigen_residual_norms(H, M2, dV, np.zeros(B), 4)
+    # a block that is fine afterwards: the failed calls left the plan usable
+    w, st = capi.chfsi_solve(H, M, MInv, dG, dV, 4, 5, -1.0, 6.0, 2500.0)
+    assert st == 0 and np.all(np.diff(w) >= 0)
