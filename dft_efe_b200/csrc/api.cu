@@ -1554,8 +1554,10 @@ extern "C"
     for (uint32_t j0 = 0; j0 < B; j0 += batch)
       {
         const uint32_t b = std::min(batch, B - j0);
-        HX_TRY(copy_cols(p, X, B, j0, xin, b, 0, b, p->n_local));
-        HX_TRY(op_apply(op, xin, xout, b, 1, 0));
+        double *xb = (b == B) ? X : xin; // whole block: applied in place (copy out / copy back is the identity)
+        if (xb != X)
+          HX_TRY(copy_cols(p, X, B, j0, xin, b, 0, b, p->n_local));
+        HX_TRY(op_apply(op, xb, xout, b, 1, 0));
         double *Sd = p->d_small.p;
         HX_TRY(gram_block(p, X, B, j0, xout, b, p->n_owned, Sd));
         if (p->nranks > 1)
@@ -1563,7 +1565,8 @@ extern "C"
         HX_CUDA(cudaMemcpyAsync(p->h_pinned, Sd, (size_t)(B - j0) * b * sizeof(double), cudaMemcpyDeviceToHost,
                                 p->stream));
         // the reference copies the (possibly constraint-filled) batch back into X
-        HX_TRY(copy_cols(p, xin, b, 0, X, B, j0, b, p->n_local));
+        if (xb != X)
+          HX_TRY(copy_cols(p, xin, b, 0, X, B, j0, b, p->n_local));
         HX_CUDA(cudaStreamSynchronize(p->stream));
         for (uint32_t i = 0; i < b; ++i)
           for (uint32_t j = j0 + i; j < B; ++j)

@@ -49,9 +49,13 @@ namespace hx
     for (uint32_t j0 = 0; j0 < B; j0 += batch)
       {
         const uint32_t b = std::min(batch, B - j0);
-        HX_TRY(copy_cols(p, X, B, j0, xin, b, 0, b, p->n_local));
+        // a batch that is the whole block is applied in place: the reference's copy out / copy back of the
+        // (constraint-filled, ghost-updated) batch is the identity then
+        double *xb = (b == B) ? X : xin;
+        if (xb != X)
+          HX_TRY(copy_cols(p, X, B, j0, xin, b, 0, b, p->n_local));
         p->mark("xtopx-copy");
-        HX_TRY(op_apply(op, xin, xout, b, 1, 0));
+        HX_TRY(op_apply(op, xb, xout, b, 1, 0));
         p->mark("gram:begin");
         double *Sd = p->d_small.p;
         HX_TRY(gram_block(p, X, B, j0, xout, b, p->n_owned, Sd));
@@ -61,7 +65,8 @@ namespace hx
         // columns [j0, j0+b) of S: rows >= column kept, the rest zero
         HX_TRY(dense_place_gram_block(p, Sd, B - j0, b, j0, S, B));
         // the reference copies the (possibly constraint-filled) batch back into X
-        HX_TRY(copy_cols(p, xin, b, 0, X, B, j0, b, p->n_local));
+        if (xb != X)
+          HX_TRY(copy_cols(p, xin, b, 0, X, B, j0, b, p->n_local));
         p->mark("xtopx-copy");
       }
     return HX_OK;
