@@ -361,12 +361,17 @@ def run_ours(args):
         poisson = {}
         try:
             if nranks == 1:
-                A_l = capi.CellOp(plan, h_cell=prob.k_cell, with_nonlocal=False)
+                A_u = capi.CellOp(plan, h_cell=prob.k_cell, with_nonlocal=False)
+                A_l = capi.CellOp(plan, h_cell=prob.k_cell, with_nonlocal=False, share_identical=True)
+                poisson["unique_cell_matrices"] = [A_l.num_unique_matrices(), prob.n_cells]
                 pc_l = capi.DiagOp(plan, 1.0 / prob.k_diag, None, capi.DIAG_JACOBI)
                 rhs = np.zeros((prob.n_local, 1)); rhs[:prob.n_owned, 0] = X[:prob.n_owned, 0]
                 rhs[prob.row_ids.astype(np.int64)] = 0.0
                 db1, dx1, dy1 = capi.DeviceBlock(prob.n_local, 1, rhs), capi.DeviceBlock(prob.n_local, 1), capi.DeviceBlock(prob.n_local, 1)
                 A_l.apply(db1, dy1, True, True)
+                A_u.apply(db1, dy1, True, True)
+                poisson["laplace_apply_ms_B1_every_cell_its_own_matrix"] = timed(lambda: A_u.apply(db1, dy1, True, True), 10)
+                del A_u
                 poisson["laplace_apply_ms_B1"] = timed(lambda: A_l.apply(db1, dy1, True, True), 10)
                 n_it = 40
                 plan.synchronize()

@@ -31,6 +31,7 @@ EXPORTS = [
     "hx_xtopx_device", "hx_subspace_rotation_device", "hx_dense_cholesky_inverse", "hx_dense_sym_eig",
     "hx_cholesky_gram_schmidt", "hx_rayleigh_ritz", "hx_chfsi_solve", "hx_eigen_residual_norms", "hx_lanczos_extreme",
     "hx_chebyshev_polynomial_degree", "hx_fe_basis_create", "hx_fe_basis_destroy", "hx_compute_fe_matrices", "hx_compute_rho",
+    "hx_cellop_set_matrix_sharing", "hx_cellop_num_unique_matrices",
 ]
 
 
@@ -344,9 +345,11 @@ class Op:
 class CellOp(Op):
     """KohnShamOperatorContextFE-shaped operator (cell matrices + optional nonlocal projectors)."""
 
-    def __init__(self, plan: Plan, h_cell=None, with_nonlocal=True):
+    def __init__(self, plan: Plan, h_cell=None, with_nonlocal=True, share_identical=False):
         super().__init__(plan)
         check(lib().hx_cellop_create(plan.h, C.byref(self.h)))
+        if share_identical:
+            check(lib().hx_cellop_set_matrix_sharing(self.h, C.c_int(1)))
         prob = plan.prob
         if with_nonlocal and prob.num_cell_proj is not None:
             keep = []
@@ -364,6 +367,11 @@ class CellOp(Op):
         a, p = _f64(h_cell)
         assert a.size == self.plan.prob.S2
         check(lib().hx_cellop_set_matrices(self.h, p, C.c_int(0)))
+
+    def num_unique_matrices(self) -> int:
+        n = C.c_uint32()
+        check(lib().hx_cellop_num_unique_matrices(self.h, C.byref(n)))
+        return n.value
 
     def set_constraint_sets(self, x_set: int, y_set: int):
         check(lib().hx_cellop_set_constraint_sets(self.h, C.c_uint32(x_set), C.c_uint32(y_set)))

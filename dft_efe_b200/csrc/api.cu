@@ -1083,6 +1083,22 @@ extern "C"
   }
 
   int
+  hx_cellop_set_matrix_sharing(hx_op *op, int enable)
+  {
+    HX_CHECK(op && op->kind == HX_OP_CELL, HX_ERR_INVALID, "not a cell operator");
+    op->share_identical = enable != 0;
+    return HX_OK;
+  }
+  int
+  hx_cellop_num_unique_matrices(hx_op *op, uint32_t *n)
+  {
+    HX_CHECK(op && n && op->kind == HX_OP_CELL, HX_ERR_INVALID, "not a cell operator");
+    HX_CHECK(op->have_matrices, HX_ERR_INVALID, "cell operator has no matrices (call hx_cellop_set_matrices)");
+    *n = op->n_unique;
+    return HX_OK;
+  }
+
+  int
   hx_cellop_set_nonlocal(hx_op *op, const hx_nonlocal_desc *nl)
   {
     HX_CHECK(op && nl && op->kind == HX_OP_CELL, HX_ERR_INVALID, "bad argument");
@@ -1269,9 +1285,11 @@ extern "C"
     HX_TRY(p->get_scratch(3, &pd));
     HX_TRY(p->get_scratch(6, &xconv));
     // per-column scalars stay on the device (one host synchronisation per iteration: the residual norms of the
-    // convergence test); layout after the reduction scratch: ones | zdotr | pdotw | zdotr_new | rr | alpha | -alpha | beta
-    HX_TRY(p->ensure_small((size_t)600 * B + 8 * (size_t)B));
-    double *d_ones = p->d_small.p + (size_t)600 * B, *d_zdotr = d_ones + B, *d_pdotw = d_zdotr + B, *d_zdotr_new = d_pdotw + B,
+    // convergence test); layout after the reduction scratch: ones | zdotr | pdotw | zdotr_new | rr | alpha | -alpha | beta.
+    // With the Jacobi preconditioner on one rank the BLAS-1 work of an iteration is two fused passes (dots of z.r and
+    // p.w; then x += alpha p, r -= alpha w, z = D^-1 r with the dots z.r and r.r) instead of ten launches.
+    HX_TRY(p->ensure_small((size_t)1200 * B + 8 * (size_t)B));
+    double *d_ones = p->d_small.p + (size_t)1200 * B, *d_zdotr = d_ones + B, *d_pdotw = d_zdotr + B, *d_zdotr_new = d_pdotw + B,
            *d_rr = d_zdotr_new + B, *d_alpha = d_rr + B, *d_nalpha = d_alpha + B, *d_beta = d_nalpha + B;
     HX_TRY(p->ensure_pinned(2 * (size_t)B * sizeof(double)));
     double *            h = p->h_pinned;
@@ -1302,6 +1320,8 @@ extern "C"
     for (uint32_t j = 0; j < B; ++j)
       bnorm[j] = sqrt(bnorm[j]);
     HX_CUDA(cudaMemcpyAsync(xconv, x, nloc * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
+    const bool fused_blas1 = p->nranks == 1 && PC->kind == HX_OP_DIAG && PC->variant == HX_DIAG_JACOBI && B <= 128 &&
+                             !getenv("HXB200_CG_UNFUSED");
     int      err  = HX_CG_OTHER_ERROR; // until a column converges
     bool     diverged = false, all_conv = false;
     uint32_t iter = 0;
@@ -1317,17 +1337,27 @@ extern "C"
         else
           {
             HX_TRY(op_apply(A, pd, w, B, 1, 1));
-            HX_TRY(reduce(z, r, d_zdotr));
-            HX_TRY(reduce(pd, w, d_pdotw));
-            HX_TRY(launch_col_divide(p, d_zdotr, d_pdotw, d_alpha, d_nalpha, B)); // alpha = z.r / p.w
-            HX_TRY(add(x, d_alpha, pd, x));                                        // x += alpha p
-            HX_TRY(add(r, d_nalpha, w, r));                                        // r -= alpha w
-            HX_TRY(op_apply(PC, r, z, B, 0, 0));
-            HX_TRY(reduce(z, r, d_zdotr_new));
-            HX_TRY(launch_col_divide(p, d_zdotr_new, d_zdotr, d_beta, nullptr, B)); // beta = z.r (new) / z.r
-            HX_TRY(add(z, d_beta, pd, pd));                                         // p = z + beta p
+            if (fused_blas1)
+              {
+                HX_TRY(launch_cg_dots2(p, z, r, pd, w, B, d_zdotr, d_pdotw, d_alpha, d_nalpha)); // alpha = z.r / p.w
+                HX_TRY(launch_cg_update(p, x, pd, r, w, z, PC->d_diag.p, d_alpha, B, d_zdotr_new, d_rr, d_zdotr, d_beta));
+                HX_TRY(add(z, d_beta, pd, pd)); // p = z + beta p
+              }
+            else
+              {
+                HX_TRY(reduce(z, r, d_zdotr));
+                HX_TRY(reduce(pd, w, d_pdotw));
+                HX_TRY(launch_col_divide(p, d_zdotr, d_pdotw, d_alpha, d_nalpha, B)); // alpha = z.r / p.w
+                HX_TRY(add(x, d_alpha, pd, x));                                        // x += alpha p
+                HX_TRY(add(r, d_nalpha, w, r));                                        // r -= alpha w
+                HX_TRY(op_apply(PC, r, z, B, 0, 0));
+                HX_TRY(reduce(z, r, d_zdotr_new));
+                HX_TRY(launch_col_divide(p, d_zdotr_new, d_zdotr, d_beta, nullptr, B)); // beta = z.r (new) / z.r
+                HX_TRY(add(z, d_beta, pd, pd));                                         // p = z + beta p
+              }
           }
-        HX_TRY(reduce(r, r, d_rr));
+        if (!(fused_blas1 && iter > 0))
+          HX_TRY(reduce(r, r, d_rr));
         HX_TRY(fetch(d_rr, rnorm.data()));
         for (uint32_t j = 0; j < B; ++j)
           {

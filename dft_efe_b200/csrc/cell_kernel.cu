@@ -26,6 +26,8 @@
 //     Rows shared by many cells (enrichment DoFs) go to a staging slot and are reduced in fixed order afterwards.
 //   * The one-launch-per-colour variant (cells of one launch share no row) is kept as scatter_mode 1
 //     (HXB200_SCATTER=coloured) for comparison.
+#include <map>
+
 #include "hx_internal.h"
 
 namespace hx
@@ -66,6 +68,7 @@ namespace hx
     double *        f_out;
     double          f_a, f_b, f_c;
     uint32_t        f_discard; // Y tiles are whole 128-B lines (B % 16 == 0, aligned): dead partial sums are discarded
+    uint32_t        shared_a;  // many cells stream the same packed matrix (hx_cellop_set_matrix_sharing): keep it in L2
   };
 
   __device__ __forceinline__ void
@@ -283,7 +286,7 @@ namespace hx
         // the X / Y lines that neighbouring cells are about to reuse
         uint64_t evict_first;
         asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(evict_first));
-        const bool once = (a.nBt == 1);
+        const bool once = (a.nBt == 1) && !a.shared_a;
         // claims run two items ahead, descriptors one item ahead (all lanes hold the same values)
         auto claim = [&]() -> uint32_t {
           uint32_t v = 0;
@@ -905,6 +908,142 @@ namespace hx
       }
   }
 
+  // ---- identical cell matrices share one packed copy (hx_cellop_set_matrix_sharing) ----
+  // order-independent 2 x 64-bit fingerprint of each cell's packed stream
+  __global__ void
+  hash_cells_kernel(const double *packed, const CellMeta *meta, const unsigned long long *len, unsigned long long *hash)
+  {
+    __shared__ unsigned long long s1[256], s2[256];
+    const uint32_t                cell = blockIdx.x;
+    const unsigned long long *    src  = reinterpret_cast<const unsigned long long *>(packed + meta[cell].h_off);
+    const unsigned long long      n    = len[cell];
+    unsigned long long            h1 = 0, h2 = 0;
+    for (unsigned long long i = threadIdx.x; i < n; i += blockDim.x)
+      {
+        const unsigned long long v = src[i];
+        h1 += v * ((0x9E3779B97F4A7C15ull * (i + 1)) | 1ull);
+        unsigned long long t = v + i * 0xBF58476D1CE4E5B9ull;
+        t ^= t >> 31;
+        t *= 0x94D049BB133111EBull;
+        h2 ^= t ^ (t >> 29);
+      }
+    s1[threadIdx.x] = h1, s2[threadIdx.x] = h2;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1)
+      {
+        if ((int)threadIdx.x < o)
+          {
+            s1[threadIdx.x] += s1[threadIdx.x + o];
+            s2[threadIdx.x] ^= s2[threadIdx.x + o];
+          }
+        __syncthreads();
+      }
+    if (threadIdx.x == 0)
+      hash[2 * (size_t)cell] = s1[0], hash[2 * (size_t)cell + 1] = s2[0];
+  }
+  // bitwise comparison of every candidate with its representative
+  __global__ void
+  verify_shared_kernel(const double *packed, const unsigned long long *off_self, const unsigned long long *off_rep,
+                       const unsigned long long *len, const uint32_t *cells, uint32_t *mismatch)
+  {
+    const uint32_t            c = cells[blockIdx.x];
+    const unsigned long long *a = reinterpret_cast<const unsigned long long *>(packed + off_self[blockIdx.x]);
+    const unsigned long long *b = reinterpret_cast<const unsigned long long *>(packed + off_rep[blockIdx.x]);
+    const unsigned long long  n = len[c];
+    bool                      bad = false;
+    for (unsigned long long i = threadIdx.x; i < n; i += blockDim.x)
+      bad = bad || (a[i] != b[i]);
+    if (bad)
+      atomicAdd(mismatch, 1u);
+  }
+
+  static int
+  share_identical_matrices(hx_op *op)
+  {
+    hx_plan *p = op->plan;
+    op->n_unique = p->C;
+    if (p->C < 2)
+      return HX_OK;
+    std::vector<unsigned long long> len(p->C);
+    for (uint32_t c = 0; c < p->C; ++c)
+      {
+        const CellMeta &m  = op->h_meta[c];
+        const uint32_t  Kp = (m.n + m.nproj + 4 * KC - 1) / (4 * KC) * (4 * KC), Mp = (m.n + 7) & ~7u;
+        len[c]             = (unsigned long long)Kp * Mp;
+      }
+    DevBuf<unsigned long long> d_len, d_hash;
+    HX_TRY(d_len.upload(len));
+    HX_TRY(d_hash.alloc(2 * (size_t)p->C));
+    hash_cells_kernel<<<p->C, 256, 0, p->stream>>>(op->d_packed.p, op->d_meta.p, d_len.p, d_hash.p);
+    p->launches++;
+    HX_CUDA(cudaGetLastError());
+    std::vector<unsigned long long> hash(2 * (size_t)p->C);
+    HX_CUDA(cudaMemcpyAsync(hash.data(), d_hash.p, hash.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, p->stream));
+    HX_CUDA(cudaStreamSynchronize(p->stream));
+    struct Key
+    {
+      unsigned long long a, b, l;
+      bool
+      operator<(const Key &o) const
+      {
+        return a != o.a ? a < o.a : (b != o.b ? b < o.b : l < o.l);
+      }
+    };
+    std::map<Key, uint32_t>         rep;
+    std::vector<uint32_t>           cand;
+    std::vector<unsigned long long> off_self, off_rep;
+    std::vector<uint32_t>           rep_of(p->C);
+    for (uint32_t c = 0; c < p->C; ++c)
+      {
+        const Key k{hash[2 * (size_t)c], hash[2 * (size_t)c + 1], len[c]};
+        auto      it = rep.find(k);
+        if (it == rep.end())
+          {
+            rep[k]    = c;
+            rep_of[c] = c;
+          }
+        else
+          {
+            rep_of[c] = it->second;
+            cand.push_back(c);
+            off_self.push_back(op->h_meta[c].h_off);
+            off_rep.push_back(op->h_meta[it->second].h_off);
+          }
+      }
+    if (cand.empty())
+      return HX_OK;
+    DevBuf<unsigned long long> d_self, d_rep;
+    DevBuf<uint32_t>           d_cand, d_mis;
+    HX_TRY(d_self.upload(off_self));
+    HX_TRY(d_rep.upload(off_rep));
+    HX_TRY(d_cand.upload(cand));
+    HX_TRY(d_mis.alloc(1));
+    HX_CUDA(cudaMemsetAsync(d_mis.p, 0, sizeof(uint32_t), p->stream));
+    verify_shared_kernel<<<(unsigned)cand.size(), 256, 0, p->stream>>>(op->d_packed.p, d_self.p, d_rep.p, d_len.p, d_cand.p,
+                                                                       d_mis.p);
+    p->launches++;
+    HX_CUDA(cudaGetLastError());
+    uint32_t mis = 0;
+    HX_CUDA(cudaMemcpyAsync(&mis, d_mis.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, p->stream));
+    HX_CUDA(cudaStreamSynchronize(p->stream));
+    if (mis != 0)
+      return HX_OK; // a fingerprint collision: keep every cell's own copy
+    for (uint32_t c : cand)
+      op->h_meta[c].h_off = op->h_meta[rep_of[c]].h_off;
+    op->n_unique = (uint32_t)rep.size();
+    HX_TRY(op->d_meta.upload(op->h_meta));
+    std::vector<ItemDesc> items(p->C);
+    for (uint32_t w = 0; w < p->C; ++w)
+      {
+        const CellMeta &m = op->h_meta[p->h_order[w]];
+        ItemDesc &      d = items[w];
+        d.h_off = m.h_off, d.ids_off = m.ids_off, d.n = m.n, d.nproj = m.nproj, d.proj_off = m.proj_off;
+        d.wait_off = p->h_wait_off[w], d.nwait = p->h_wait_off[w + 1] - p->h_wait_off[w];
+      }
+    HX_TRY(op->d_items.upload(items));
+    return HX_OK;
+  }
+
   int
   pack_cell_matrices(hx_op *op, const double *raw, int on_device)
   {
@@ -990,6 +1129,9 @@ namespace hx
           }
       }
     op->have_matrices = true;
+    op->n_unique      = p->C;
+    if (op->share_identical)
+      HX_TRY(share_identical_matrices(op));
     return HX_OK;
   }
 
@@ -1096,6 +1238,7 @@ namespace hx
     a.flags     = p->d_flags.p;
     a.counters  = p->d_counters.p;
     a.B         = B;
+    a.shared_a  = (op->n_unique * 2u < p->C) ? 1u : 0u;
     // column tile: widest of {8,16,32} columns that B needs and shared memory allows
     int  nt      = B > 16 ? 4 : (B > 8 ? 2 : 1);
     auto xtile_of = [&](int nt_) { return (size_t)op->max_kp * (nt_ * 8 + 4) * sizeof(double); };

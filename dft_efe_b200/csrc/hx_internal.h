@@ -348,6 +348,8 @@ struct hx_op
   hx::DevBuf<unsigned long long> d_c_off;
   hx::DevBuf<uint32_t>      d_pr_off, d_pr_slots;      // projector row -> staging slots (ordered)
   uint32_t                  x_set = 0, y_set = 0; // constraint sets applied to X (parent->child) and Y (child->parent)
+  bool                      share_identical = false; // hx_cellop_set_matrix_sharing
+  uint32_t                  n_unique = 0;            // distinct packed matrices after the last set_matrices
   // --- diagonal operator ---
   int                variant = 0;
   hx::DevBuf<double> d_diag, d_enr_block;
@@ -361,6 +363,10 @@ namespace hx
   int launch_c2p(hx_plan *p, double *Y, uint32_t B, uint32_t set = 0);
   int launch_coldot(hx_plan *p, const double *x, const double *y, uint32_t B, size_t nrows, double *out_dev);
   int launch_col_divide(hx_plan *p, const double *num, const double *den, double *out, double *out_neg, uint32_t B);
+  int launch_cg_dots2(hx_plan *p, const double *z, const double *r, const double *pd, const double *w, uint32_t B,
+                      double *zdotr, double *pdotw, double *alpha, double *nalpha);
+  int launch_cg_update(hx_plan *p, double *x, const double *pd, double *r, const double *w, double *z, const double *dinv,
+                       const double *alpha, uint32_t B, double *zdotr_new, double *rr, const double *zdotr_old, double *beta);
   int launch_zero_constrained(hx_plan *p, double *Y, uint32_t B, uint32_t set = 0);
   int launch_pack(hx_plan *p, const double *x, uint32_t B, const uint32_t *ids, uint32_t n, double *buf);
   int launch_unpack(hx_plan *p, const double *buf, uint32_t B, const uint32_t *ids, uint32_t n, double *x);

@@ -300,6 +300,140 @@ namespace hx
     return HX_OK;
   }
 
+  // ---- fused BLAS-1 of one CG iteration (CGLinearSolver.t.cpp:170-260) for a diagonal preconditioner ----
+  // cg_dots2: partial column sums of z.r and p.w over the owned rows (one pass instead of two reductions)
+  __global__ void
+  cg_dots2_partial_kernel(const double *z, const double *r, const double *pd, const double *w, uint32_t B, size_t nrows,
+                          double *partial)
+  {
+    extern __shared__ double sh[]; // [2][rowsPerIter][B]
+    const uint32_t           rpi = blockDim.x / B, rr = threadIdx.x / B, c = threadIdx.x % B;
+    const size_t             per = (nrows + gridDim.x - 1) / gridDim.x;
+    const size_t             begin = (size_t)blockIdx.x * per, end = begin + per < nrows ? begin + per : nrows;
+    double                   s0 = 0.0, s1 = 0.0;
+    if (rr < rpi)
+      for (size_t q = begin + rr; q < end; q += rpi)
+        {
+          s0 += z[q * B + c] * r[q * B + c];
+          s1 += pd[q * B + c] * w[q * B + c];
+        }
+    if (rr < rpi)
+      {
+        sh[rr * B + c]             = s0;
+        sh[(rpi + rr) * B + c]     = s1;
+      }
+    __syncthreads();
+    if (threadIdx.x < 2 * B)
+      {
+        const uint32_t which = threadIdx.x / B, col = threadIdx.x % B;
+        double         t = 0.0;
+        for (uint32_t q = 0; q < rpi; ++q)
+          t += sh[(which * rpi + q) * B + col];
+        partial[((size_t)blockIdx.x * 2 + which) * B + col] = t;
+      }
+  }
+  // sums the block partials in block order; out0 = first dot, out1 = second dot, quot = out0 / den (den = out1 when
+  // den_in is null), nquot = -quot
+  __global__ void
+  cg_finalize_kernel(const double *partial, uint32_t B, uint32_t nb, double *out0, double *out1, const double *den_in,
+                     int quot_of_first_over_den, double *quot, double *nquot)
+  {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= B)
+      return;
+    double s0 = 0.0, s1 = 0.0;
+    for (uint32_t b = 0; b < nb; ++b)
+      {
+        s0 += partial[((size_t)b * 2 + 0) * B + c];
+        s1 += partial[((size_t)b * 2 + 1) * B + c];
+      }
+    out0[c] = s0;
+    out1[c] = s1;
+    if (quot_of_first_over_den)
+      {
+        const double q = s0 / (den_in ? den_in[c] : s1);
+        quot[c]        = q;
+        if (nquot)
+          nquot[c] = -q;
+      }
+  }
+  // x += alpha p, r -= alpha w over the owned rows; z = dinv .* r over the local rows (PreconditionerJacobi::apply
+  // with both ghost flags false); partial column sums of z.r and r.r over the owned rows
+  __global__ void
+  cg_update_partial_kernel(double *x, const double *pd, double *r, const double *w, double *z, const double *dinv,
+                           const double *alpha, uint32_t B, size_t nowned, size_t nlocal, double *partial)
+  {
+    extern __shared__ double sh[];
+    const uint32_t           rpi = blockDim.x / B, rr = threadIdx.x / B, c = threadIdx.x % B;
+    const size_t             per = (nlocal + gridDim.x - 1) / gridDim.x;
+    const size_t             begin = (size_t)blockIdx.x * per, end = begin + per < nlocal ? begin + per : nlocal;
+    double                   s0 = 0.0, s1 = 0.0;
+    if (rr < rpi)
+      {
+        const double al = alpha[c];
+        for (size_t q = begin + rr; q < end; q += rpi)
+          {
+            const size_t i = q * B + c;
+            double       rv = r[i];
+            if (q < nowned)
+              {
+                x[i] = 1.0 * x[i] + al * pd[i];
+                rv   = 1.0 * rv + (-al) * w[i];
+                r[i] = rv;
+              }
+            const double zv = dinv[q] * rv;
+            z[i]            = zv;
+            if (q < nowned)
+              {
+                s0 += zv * rv;
+                s1 += rv * rv;
+              }
+          }
+      }
+    if (rr < rpi)
+      {
+        sh[rr * B + c]         = s0;
+        sh[(rpi + rr) * B + c] = s1;
+      }
+    __syncthreads();
+    if (threadIdx.x < 2 * B)
+      {
+        const uint32_t which = threadIdx.x / B, col = threadIdx.x % B;
+        double         t = 0.0;
+        for (uint32_t q = 0; q < rpi; ++q)
+          t += sh[(which * rpi + q) * B + col];
+        partial[((size_t)blockIdx.x * 2 + which) * B + col] = t;
+      }
+  }
+  int
+  launch_cg_dots2(hx_plan *p, const double *z, const double *r, const double *pd, const double *w, uint32_t B, double *zdotr,
+                  double *pdotw, double *alpha, double *nalpha)
+  {
+    HX_CHECK(B <= 128, HX_ERR_UNSUPPORTED, "fused CG reductions: B <= 128");
+    HX_TRY(p->ensure_small((size_t)2 * CS_BLOCKS * B + 16 * (size_t)B));
+    const unsigned threads = 256;
+    cg_dots2_partial_kernel<<<CS_BLOCKS, threads, 2 * (threads / B) * B * sizeof(double), p->stream>>>(z, r, pd, w, B, p->n_owned,
+                                                                                                      p->d_small.p);
+    cg_finalize_kernel<<<nblk(B), 256, 0, p->stream>>>(p->d_small.p, B, CS_BLOCKS, zdotr, pdotw, nullptr, 1, alpha, nalpha);
+    p->launches += 2;
+    HX_CUDA(cudaGetLastError());
+    return HX_OK;
+  }
+  int
+  launch_cg_update(hx_plan *p, double *x, const double *pd, double *r, const double *w, double *z, const double *dinv,
+                   const double *alpha, uint32_t B, double *zdotr_new, double *rr, const double *zdotr_old, double *beta)
+  {
+    HX_CHECK(B <= 128, HX_ERR_UNSUPPORTED, "fused CG reductions: B <= 128");
+    HX_TRY(p->ensure_small((size_t)2 * CS_BLOCKS * B + 16 * (size_t)B));
+    const unsigned threads = 256;
+    cg_update_partial_kernel<<<CS_BLOCKS, threads, 2 * (threads / B) * B * sizeof(double), p->stream>>>(
+      x, pd, r, w, z, dinv, alpha, B, p->n_owned, p->n_local, p->d_small.p);
+    cg_finalize_kernel<<<nblk(B), 256, 0, p->stream>>>(p->d_small.p, B, CS_BLOCKS, zdotr_new, rr, zdotr_old, 1, beta, nullptr);
+    p->launches += 2;
+    HX_CUDA(cudaGetLastError());
+    return HX_OK;
+  }
+
   // per-column quotient of two reduction results, kept on the device (step lengths of the CG solver)
   __global__ void
   col_divide_kernel(const double *num, const double *den, double *out, double *out_neg, uint32_t B)

@@ -181,6 +181,13 @@ int hx_cellop_create(hx_plan *plan, hx_op **op);
  * row-major, S2 doubles; `on_device` says where `cell_matrices` lives.  Re-tiled internally. */
 int hx_cellop_set_matrices(hx_op *op, const double *cell_matrices, int on_device);
 int hx_cellop_set_nonlocal(hx_op *op, const hx_nonlocal_desc *nl);
+/* Cells whose matrices are bitwise identical (the Laplace matrices of equally sized cells of a hexahedral mesh,
+ * src/electrostatics/LaplaceOperatorContextFE.t.cpp:89-260) can share ONE re-tiled copy, which the cell kernel then
+ * streams from L2 instead of HBM.  Off by default (a Kohn-Sham Hamiltonian differs cell by cell); call before
+ * hx_cellop_set_matrices.  Detection = 128-bit fingerprint per cell + bitwise verification on the device; results are
+ * unchanged bit for bit.  hx_cellop_num_unique_matrices reports the number of distinct matrices kept. */
+int hx_cellop_set_matrix_sharing(hx_op *op, int enable);
+int hx_cellop_num_unique_matrices(hx_op *op, uint32_t *n);
 /* electrostatics::LaplaceOperatorContextFE (src/electrostatics/LaplaceOperatorContextFE.t.cpp:395-470): the same
  * gather -> cell GEMM -> scatter path with the grad N_i . grad N_j cell matrices, where X is filled through the
  * constraints of feBasisManagerX (x_set) and Y condensed through those of feBasisManagerY (y_set). */

@@ -478,6 +478,53 @@ def test_cg_poisson_solve(capi, prob_full, B):
     assert st2 == capi.CG_FAILED_TO_CONVERGE and it2 == 4
 
 
+@pytest.mark.parametrize("B", [1, 8, 32])
+def test_identical_cell_matrices_share_one_copy(capi, prob_full, B):
+    """hx_cellop_set_matrix_sharing: the Laplace matrices of equally sized cells are bitwise identical and stream from one
+    re-tiled copy; the result does not change by a bit.  A Hamiltonian that differs cell by cell keeps every copy."""
+    p = prob_full
+    plan = capi.Plan(p, max_block=B)
+    A = capi.CellOp(plan, h_cell=p.k_cell, with_nonlocal=False)
+    As = capi.CellOp(plan, h_cell=p.k_cell, with_nonlocal=False, share_identical=True)
+    assert A.num_unique_matrices() == p.n_cells
+    nu = As.num_unique_matrices()
+    assert 2 <= nu < p.n_cells // 2, (nu, p.n_cells)  # two cell sizes + the enriched cells
+    X = synth.make_block(p, B)
+    y0, y1 = plan.block(B), plan.block(B)
+    A.apply(plan.block(B, X), y0, True, True)
+    As.apply(plan.block(B, X), y1, True, True)
+    assert np.array_equal(y0.download(), y1.download())
+    # re-setting different matrices undoes the sharing where they differ
+    As.set_matrices(p.h_cell)
+    assert As.num_unique_matrices() == p.n_cells
+    Hn = capi.CellOp(plan, with_nonlocal=False)
+    Hn.apply(plan.block(B, X), y0, True, False)
+    As.apply(plan.block(B, X), y1, True, False)
+    assert np.array_equal(y0.download(), y1.download())
+
+
+@pytest.mark.parametrize("B", [1, 3])
+def test_cg_fused_blas1_agrees_with_the_separate_passes(capi, prob_full, B, monkeypatch):
+    """the two fused BLAS-1 passes of an iteration (Jacobi preconditioner) against the launch-per-operation path"""
+    p = prob_full
+    plan, xset, A, pc = _laplace_ops(capi, p, B)
+    rng = np.random.default_rng(9)
+    b = rng.standard_normal((p.n_local, B)); b[p.row_ids.astype(np.int64)] = 0.0
+    x0 = 0.1 * rng.standard_normal((p.n_local, B))
+    res = []
+    for unfused in (False, True):
+        if unfused:
+            monkeypatch.setenv("HXB200_CG_UNFUSED", "1")
+        dx = plan.block(B, x0)
+        l0 = plan.launch_count()
+        it, st, rn = capi.cg_solve(A, pc, plan.block(B, b), dx, 400, 1e-12, 1e-10, 1e10)
+        res.append((it, st, dx.download()[:p.n_owned], plan.launch_count() - l0))
+    monkeypatch.delenv("HXB200_CG_UNFUSED")
+    assert res[0][1] == res[1][1] == capi.CG_SUCCESS and abs(res[0][0] - res[1][0]) <= 1
+    assert np.abs(res[0][2] - res[1][2]).max() < 1e-9 * np.abs(res[1][2]).max()
+    assert res[0][3] < res[1][3]  # fewer launches
+
+
 # --------------------------------------------------------------- subspace projections ----
 @pytest.mark.parametrize("B,batch", [(6, 4), (32, 32), (40, 16), (96, 64)])
 def test_xtopx(capi, prob_full, B, batch):
