@@ -51,6 +51,17 @@ def workload_spec(name: str, nranks: int):
         # into nranks z-slabs (strong scaling; 31 GB of cell matrices in total, meant for 4 or 8 GPUs)
         nc, p, B, h = (32, 32, 32), 6, 128, 0.8
         n_atoms = 24
+    elif name == "c1":
+        # BASELINE configs[0]: H2 all-electron classical EFE on a small adaptive mesh, block of 8 wavefunctions (the
+        # reference's own CPU-runnable test/ksdft case: 15^3 cells refined around the two nuclei, FE order 3, one
+        # enrichment function per atom, no pseudopotential)
+        nc, p, B, h = (15, 15, 15 * nranks), 3, 8, 1.0
+        L = np.array(nc) * h
+        atoms = np.concatenate([np.array([[0.5 * L[0] - 0.7, 0.5 * L[1], (k + 0.5) * 15.0 * h],
+                                          [0.5 * L[0] + 0.7, 0.5 * L[1], (k + 0.5) * 15.0 * h]]) for k in range(nranks)])
+        spec = synth.MeshSpec(ncell=nc, p=p, h=h, refine_mask=synth.refine_ball(nc, h, atoms, 2.5), atoms=atoms,
+                              n_enr_per_atom=1, enr_cutoff=3.0 * h, n_proj_per_atom=0, nranks=nranks, boundary="dirichlet")
+        return spec, B
     else:
         raise SystemExit(f"unknown workload {name}")
     rng = np.random.default_rng(7)
@@ -98,7 +109,7 @@ FILTER_BOUNDS = (-3.0, 1.0, 400.0)  # wantedLower, wantedUpper, unwantedUpper of
 
 
 def cpu_filter_throughput(sample_cells=(10, 10, 10), p=4, B=32, threads=1, seconds=12.0, warm=1, max_steps=50,
-                          degree=DEGREE):
+                          degree=DEGREE, workload=None):
     """Oracle port (reference-faithful: ChebyshevFilter = per degree one H.X [gather, one dgemm per cell through an
     optimised BLAS, sequential scatter, BLAS-1 constraints], one mass-lumped M^-1 apply, two axpby) on a bounded
     sample of the same cell shape; `threads` partitions run concurrently (the stand-in for `mpirun -n threads`)."""
@@ -107,12 +118,17 @@ def cpu_filter_throughput(sample_cells=(10, 10, 10), p=4, B=32, threads=1, secon
     from dft_efe_b200 import synth
     from oracle import oracle as orc
     blas = orc.use_scipy_dgemm(True)
-    nc = (sample_cells[0], sample_cells[1], sample_cells[2] * threads)
-    rng = np.random.default_rng(7)
-    L = np.array(nc) * 0.8
-    atoms = (0.25 + 0.5 * rng.uniform(size=(2 * threads, 3))) * L[None, :]
-    spec = synth.MeshSpec(ncell=nc, p=p, h=0.8, atoms=atoms, n_enr_per_atom=4, enr_cutoff=1.28,
-                          n_proj_per_atom=4, proj_cutoff=1.04, nranks=threads, boundary="dirichlet")
+    if workload == "c1":
+        # the reference's own CPU-runnable case is small enough to be timed whole: one full C1 mesh per thread
+        spec, B = workload_spec("c1", threads)
+        nc, p = spec.ncell, spec.p
+    else:
+        nc = (sample_cells[0], sample_cells[1], sample_cells[2] * threads)
+        rng = np.random.default_rng(7)
+        L = np.array(nc) * 0.8
+        atoms = (0.25 + 0.5 * rng.uniform(size=(2 * threads, 3))) * L[None, :]
+        spec = synth.MeshSpec(ncell=nc, p=p, h=0.8, atoms=atoms, n_enr_per_atom=4, enr_cutoff=1.28,
+                              n_proj_per_atom=4, proj_cutoff=1.04, nranks=threads, boundary="dirichlet")
     probs = synth.build_problem(spec)
     W = orc.OracleWorld(probs)
     if threads > 1:
@@ -148,7 +164,8 @@ def run_reference(args):
     spec, B = workload_spec(args.workload, 1)
     # bounded sample: each step = one filter call over `cores` partitions of 8^3 cells
     res = cpu_filter_throughput(sample_cells=(8, 8, 8), p=spec.p, B=B, threads=cores, seconds=1e9,
-                                warm=max(1, min(args.warmup, 2)), max_steps=max(1, min(args.steps, 20)))
+                                warm=max(1, min(args.warmup, 2)), max_steps=max(1, min(args.steps, 20)),
+                                workload=args.workload)
     line = {"metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
@@ -487,7 +504,8 @@ def run_ours(args):
         }
         if not args.no_cpu and nranks == 1:
             try:
-                line["cpu_baseline"] = {k: v for k, v in cpu_filter_throughput(threads=1, seconds=10.0, p=spec.p, B=B).items()
+                line["cpu_baseline"] = {k: v for k, v in cpu_filter_throughput(threads=1, seconds=10.0, p=spec.p, B=B,
+                                                                                 workload=args.workload).items()
                                         if k != "ms_per_step"}
             except Exception as e:  # the oracle is a checker; its absence must not hide the GPU number
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "port", "sample": f"failed: {e}"}
@@ -506,7 +524,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c2", "small", "c3"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "small", "c3", "c1"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -91,18 +91,20 @@ namespace hx
       }
   }
 
-  // grid: (cells, lower tiles of the largest cell)
-  __global__ void __launch_bounds__(256)
-  fe_matrices_kernel(const hx_fe_basis::Cell *cells, const double *basis, const double *w, const double *add_to, double *out)
+  // grid: cells x lower tiles of the largest cell, the tiles of one cell adjacent (they read the same basis values:
+  // launched together they share them through L2)
+  __global__ void __launch_bounds__(256, 4)
+  fe_matrices_kernel(const hx_fe_basis::Cell *cells, const double *basis, const double *w, const double *add_to, double *out,
+                     uint32_t tilesPerCell)
   {
     __shared__ __align__(16) double As[2][FKC * FLD];
     __shared__ __align__(16) double Bs[2][FKC * FLD];
     __shared__ double               Ws[2][FKC];
-    const hx_fe_basis::Cell         cell = cells[blockIdx.x];
+    const hx_fe_basis::Cell         cell = cells[blockIdx.x / tilesPerCell];
     const uint32_t                  n = cell.n, nq = cell.nq;
     const uint32_t                  tilesM = (n + FT - 1) / FT;
     // tile index -> (tm, tn) with tn <= tm
-    uint32_t tm = 0, t = blockIdx.y;
+    uint32_t tm = 0, t = blockIdx.x % tilesPerCell;
     while (t > tm)
       {
         t -= tm + 1;
@@ -124,12 +126,24 @@ namespace hx
         acc[j][u][0] = acc[j][u][1] = 0.0;
     const int wm = (warp & 3) * 16, wn = (warp >> 2) * 32;
     const int nchunks = (int)((nq + FKC - 1) / FKC);
-    auto      load    = [&](int buf, uint32_t q0) {
+    const bool diag    = (tm == tn); // both operands are the same columns of N: load them once
+    auto       load    = [&](int buf, uint32_t q0) {
       fe_load_tile(As[buf], N, n, q0, nq, m0, aligned16, tid);
-      fe_load_tile(Bs[buf], N, n, q0, nq, n0, aligned16, tid);
+      if (!diag)
+        fe_load_tile(Bs[buf], N, n, q0, nq, n0, aligned16, tid);
       if (tid < FKC)
         Ws[buf][tid] = (q0 + tid < nq) ? wc[q0 + tid] : 0.0;
     };
+    // the summand of the epilogue (reinit's component sum): pull its lines into L2 now, behind the k loop
+    const double *add = add_to ? add_to + cell.out_off : nullptr;
+    if (add)
+      {
+        const uint32_t r = tid >> 2, seg = (tid & 3) * 16;
+        if (m0 + r < n && n0 + seg < n)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(add + (size_t)(m0 + r) * n + n0 + seg));
+        if (!diag && n0 + r < n && m0 + seg < n)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(add + (size_t)(n0 + r) * n + m0 + seg));
+      }
     if (nchunks)
       {
         load(0, 0);
@@ -148,7 +162,7 @@ namespace hx
           asm volatile("cp.async.wait_group 0;");
         __syncthreads();
         const double *as = As[cur] + (lane & 3) * FLD + wm + (lane >> 2);
-        const double *bs = Bs[cur] + (lane & 3) * FLD + wn + (lane >> 2);
+        const double *bs = (diag ? As[cur] : Bs[cur]) + (lane & 3) * FLD + wn + (lane >> 2);
 #pragma unroll
         for (int k4 = 0; k4 < FKC / 4; ++k4)
           {
@@ -168,8 +182,7 @@ namespace hx
           }
         __syncthreads();
       }
-    double *      o   = out + cell.out_off;
-    const double *add = add_to ? add_to + cell.out_off : nullptr;
+    double *o = out + cell.out_off;
 #pragma unroll
     for (int j = 0; j < 2; ++j)
 #pragma unroll
@@ -184,7 +197,7 @@ namespace hx
                 const double v  = acc[j][u][e];
                 const size_t i1 = (size_t)r * n + cidx;
                 o[i1]           = add ? v + add[i1] : v;
-                if (tm != tn)
+                if (!diag)
                   { // mirror image of an off-diagonal tile (the matrix is symmetric)
                     const size_t i2 = (size_t)cidx * n + r;
                     o[i2]           = add ? v + add[i2] : v;
@@ -480,8 +493,9 @@ extern "C"
     const uint32_t tiles  = tilesM * (tilesM + 1) / 2;
     HX_CHECK(tiles <= 65535, HX_ERR_UNSUPPORTED, "cell matrices larger than 23000 x 23000 are not supported");
     p->mark("fe-matrices:begin");
-    dim3 grid(b->C, tiles);
-    fe_matrices_kernel<<<grid, 256, 0, p->stream>>>(b->d_cells.p, b->d_basis.p, b->d_w.p, add_to_dev, cell_matrices_dev);
+    HX_CHECK((unsigned long long)b->C * tiles < 0x7fffffffull, HX_ERR_UNSUPPORTED, "too many cell-matrix tiles for one launch");
+    fe_matrices_kernel<<<b->C * tiles, 256, 0, p->stream>>>(b->d_cells.p, b->d_basis.p, b->d_w.p, add_to_dev, cell_matrices_dev,
+                                                           tiles);
     p->mark("fe-matrices");
     p->launches += 2;
     HX_CUDA(cudaGetLastError());
