@@ -31,7 +31,7 @@ EXPORTS = [
     "hx_xtopx_device", "hx_subspace_rotation_device", "hx_dense_cholesky_inverse", "hx_dense_sym_eig",
     "hx_cholesky_gram_schmidt", "hx_rayleigh_ritz", "hx_chfsi_solve", "hx_eigen_residual_norms", "hx_lanczos_extreme",
     "hx_chebyshev_polynomial_degree", "hx_fe_basis_create", "hx_fe_basis_destroy", "hx_compute_fe_matrices", "hx_compute_rho",
-    "hx_cellop_set_matrix_sharing", "hx_cellop_num_unique_matrices",
+    "hx_cellop_set_matrix_sharing", "hx_cellop_num_unique_matrices", "hx_cellop_assemble_matrices",
 ]
 
 
@@ -538,6 +538,15 @@ class FeBasis:
             a, p = _f64(f)
             assert a.size == self.n_quad
             check(lib().hx_compute_fe_matrices(self.h, p, C.c_int(0), add_to.p if add_to is not None else None, out.p))
+
+    def assemble_into(self, op: "CellOp", f=None, add_to: Optional[DeviceBlock] = None, f_device=None):
+        """computeFEMatrices + component sum + reinit in one kernel: straight into the operator's packed stream"""
+        if f_device is not None:
+            check(lib().hx_cellop_assemble_matrices(op.h, self.h, f_device.p, C.c_int(1), add_to.p if add_to is not None else None))
+        else:
+            a, p = _f64(f)
+            assert a.size == self.n_quad
+            check(lib().hx_cellop_assemble_matrices(op.h, self.h, p, C.c_int(0), add_to.p if add_to is not None else None))
 
     def compute_rho(self, X: DeviceBlock, occupation) -> np.ndarray:
         """DensityCalculator::computeRho: rho at the quadrature points (host array)."""

@@ -93,9 +93,13 @@ namespace hx
 
   // grid: cells x lower tiles of the largest cell, the tiles of one cell adjacent (they read the same basis values:
   // launched together they share them through L2)
+  // PACKED: the result goes straight into the cell kernel's fragment-major stream (pack_kernel's layout): an 8 x 4
+  // block of the matrix is one 256-B fragment, and the two accumulator values a thread holds for (row, col..col+1)
+  // are neighbours inside it
+  template <bool PACKED>
   __global__ void __launch_bounds__(256, 4)
   fe_matrices_kernel(const hx_fe_basis::Cell *cells, const double *basis, const double *w, const double *add_to, double *out,
-                     uint32_t tilesPerCell)
+                     uint32_t tilesPerCell, const CellMeta *meta, int mpc)
   {
     __shared__ __align__(16) double As[2][FKC * FLD];
     __shared__ __align__(16) double Bs[2][FKC * FLD];
@@ -183,6 +187,22 @@ namespace hx
         __syncthreads();
       }
     double *o = out + cell.out_off;
+    // packed layout of this cell (PACKED only)
+    size_t per_chunk = 0;
+    int    nKC = 0, nMt = 0;
+    if (PACKED)
+      {
+        const CellMeta cm = meta[blockIdx.x / tilesPerCell];
+        o                 = out + cm.h_off;
+        nKC               = ((int)cm.n + (int)cm.nproj + 4 * KC - 1) / (4 * KC);
+        nMt               = ((int)cm.n + 7) >> 3;
+        per_chunk         = (size_t)mpc * nKC * KC * 32;
+      }
+    auto pidx = [&](uint32_t r, uint32_t c) -> size_t {
+      const int mt = (int)(r >> 3), ch = mt / mpc, mc = ch * mpc, mtc = min(mpc, nMt - mc), mtl = mt - mc;
+      const int kc = (int)(c >> 4), ks = (int)((c >> 2) & 3);
+      return (size_t)ch * per_chunk + (size_t)kc * mtc * KC * 32 + (size_t)(mtl * KC + ks) * 32 + (r & 7) * 4 + (c & 3);
+    };
 #pragma unroll
     for (int j = 0; j < 2; ++j)
 #pragma unroll
@@ -196,11 +216,11 @@ namespace hx
               {
                 const double v  = acc[j][u][e];
                 const size_t i1 = (size_t)r * n + cidx;
-                o[i1]           = add ? v + add[i1] : v;
+                o[PACKED ? pidx(r, cidx) : i1] = add ? v + add[i1] : v;
                 if (!diag)
                   { // mirror image of an off-diagonal tile (the matrix is symmetric)
                     const size_t i2 = (size_t)cidx * n + r;
-                    o[i2]           = add ? v + add[i2] : v;
+                    o[PACKED ? pidx(cidx, r) : i2] = add ? v + add[i2] : v;
                   }
               }
           }
@@ -472,11 +492,10 @@ extern "C"
     return HX_OK;
   }
 
-  int
-  hx_compute_fe_matrices(hx_fe_basis *b, const double *f, int f_on_device, const double *add_to_dev, double *cell_matrices_dev)
+  static int
+  compute_fe_matrices(hx_fe_basis *b, const double *f, int f_on_device, const double *add_to_dev, double *cell_matrices_dev,
+                      hx_op *packed_op)
   {
-    HX_CHECK(b && f && cell_matrices_dev, HX_ERR_INVALID, "null argument");
-    HX_CHECK(add_to_dev != cell_matrices_dev, HX_ERR_INVALID, "add_to and the output must not alias (mirrored tile writes)");
     hx_plan *p = b->plan;
     if (b->C == 0 || b->n_quad_total == 0)
       return HX_OK;
@@ -494,13 +513,40 @@ extern "C"
     HX_CHECK(tiles <= 65535, HX_ERR_UNSUPPORTED, "cell matrices larger than 23000 x 23000 are not supported");
     p->mark("fe-matrices:begin");
     HX_CHECK((unsigned long long)b->C * tiles < 0x7fffffffull, HX_ERR_UNSUPPORTED, "too many cell-matrix tiles for one launch");
-    fe_matrices_kernel<<<b->C * tiles, 256, 0, p->stream>>>(b->d_cells.p, b->d_basis.p, b->d_w.p, add_to_dev, cell_matrices_dev,
-                                                           tiles);
+    if (packed_op)
+      fe_matrices_kernel<true><<<b->C * tiles, 256, 0, p->stream>>>(b->d_cells.p, b->d_basis.p, b->d_w.p, add_to_dev,
+                                                                   packed_op->d_packed.p, tiles, packed_op->d_meta.p,
+                                                                   CWARPS * packed_op->mtw);
+    else
+      fe_matrices_kernel<false><<<b->C * tiles, 256, 0, p->stream>>>(b->d_cells.p, b->d_basis.p, b->d_w.p, add_to_dev,
+                                                                    cell_matrices_dev, tiles, nullptr, 0);
     p->mark("fe-matrices");
     p->launches += 2;
     HX_CUDA(cudaGetLastError());
     if (!f_on_device)
       HX_CUDA(cudaStreamSynchronize(p->stream)); // the caller may reuse its host array
+    return HX_OK;
+  }
+
+  int
+  hx_compute_fe_matrices(hx_fe_basis *b, const double *f, int f_on_device, const double *add_to_dev, double *cell_matrices_dev)
+  {
+    HX_CHECK(b && f && cell_matrices_dev, HX_ERR_INVALID, "null argument");
+    HX_CHECK(add_to_dev != cell_matrices_dev, HX_ERR_INVALID, "add_to and the output must not alias (mirrored tile writes)");
+    return compute_fe_matrices(b, f, f_on_device, add_to_dev, cell_matrices_dev, nullptr);
+  }
+
+  int
+  hx_cellop_assemble_matrices(hx_op *op, hx_fe_basis *b, const double *f, int f_on_device, const double *add_to_dev)
+  {
+    HX_CHECK(op && b && f, HX_ERR_INVALID, "null argument");
+    HX_CHECK(op->kind == HX_OP_CELL && op->plan == b->plan, HX_ERR_INVALID, "operator and basis data belong to different plans");
+    HX_CHECK(!op->share_identical, HX_ERR_INVALID, "matrix sharing is on for this operator");
+    // the stream layout, its zero padding and the projector columns are laid down once
+    if (!op->have_matrices || op->n_unique != op->plan->C)
+      HX_TRY(pack_cell_matrices(op, nullptr, 1));
+    HX_TRY(compute_fe_matrices(b, f, f_on_device, add_to_dev, nullptr, op));
+    op->have_matrices = true;
     return HX_OK;
   }
 }

@@ -32,8 +32,7 @@
 
 namespace hx
 {
-  constexpr int KC            = 4;               // k-steps (of 4) per stage
-  constexpr int CWARPS        = 8;               // DMMA warps
+  // KC (k-steps of 4 per stage) and CWARPS (DMMA warps) live in hx_internal.h: they define the packed layout
   constexpr int CTHREADS      = CWARPS * 32;
   constexpr int V2_THREADS    = CTHREADS + 64;   // + A-stream warp + gather warp
   constexpr int QD            = 16;              // item queue depth (A-stream warp -> gather / DMMA warps)
@@ -878,7 +877,7 @@ namespace hx
     const CellMeta cm   = meta[cell];
     const int      n = (int)cm.n, np = (int)cm.nproj;
     const int      nKC = (n + np + 4 * KC - 1) / (4 * KC), nMt = (n + 7) >> 3;
-    const double * H   = raw + (raw_off[cell] - raw_base);
+    const double * H   = raw ? raw + (raw_off[cell] - raw_base) : nullptr; // null: structure only (H part zero)
     const double * Cc  = (np > 0) ? cellC + c_off[cell] : nullptr;
     double *       out = packed + cm.h_off;
     const size_t   tot = (size_t)nMt * nKC * KC * 32;
@@ -900,7 +899,7 @@ namespace hx
         if (r < n)
           {
             if (k < n)
-              v = H[(size_t)r * n + k];
+              v = H ? H[(size_t)r * n + k] : 0.0;
             else if (k < n + np)
               v = Cc[(size_t)(k - n) + (size_t)r * np];
           }

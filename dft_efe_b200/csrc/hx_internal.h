@@ -182,6 +182,14 @@ namespace hx
   };
 } // namespace hx
 
+namespace hx
+{
+  // the packed (fragment-major) cell-matrix stream of the cell kernel: stages of KC k-steps (4 columns each) for the
+  // CWARPS * mtw m-tiles (8 rows each) of a chunk; see pack_kernel in cell_kernel.cu
+  constexpr int KC     = 4;
+  constexpr int CWARPS = 8;
+} // namespace hx
+
 #define HX_DEST_STAGED 0x80000000u
 #define HX_DEST_FIRST 0x40000000u
 #define HX_DEST_LASTF 0x20000000u /* last toucher (processing order) of a row whose Chebyshev update can be fused */
@@ -384,7 +392,7 @@ namespace hx
   int launch_cell_apply(hx_op *op, const double *X, double *Y, uint32_t B, const FuseArgs *fuse = nullptr,
                         bool *fused_applied = nullptr);
   int launch_nl_phase_a(hx_op *op, const double *X, uint32_t B);
-  int pack_cell_matrices(hx_op *op, const double *raw_dev_or_host, int on_device);
+  int pack_cell_matrices(hx_op *op, const double *raw_dev_or_host, int on_device); // raw == nullptr: structure only
   // use_row_list false: all owned rows; true: only the n_rows listed rows
   int launch_cheb_fused(hx_plan *p, hx_op *binv, const double *s1, const double *xcur, const double *xprev,
                         double *out, uint32_t B, double a, double b, double c, bool use_row_list = false,

@@ -1111,6 +1111,18 @@ namespace dftefe
 
   namespace ksdft
   {
+    // KohnShamOperatorContextFE::reinit for a local potential given at the quadrature points: computeFEMatrices, the sum
+    // with the other components (addToDevice: flat cell matrices on the device, e.g. the kinetic part; may be null) and
+    // the re-tiling for the cell kernel in ONE kernel (src/ksdft/KohnShamOperatorContextFE.t.cpp:1240-1311 +
+    // src/basis/FEBasisOperations.t.cpp:2210-2243); the operator's nonlocal part is kept
+    inline void
+    reinitFromPotential(const linearAlgebra::NativeOperator &H, const basis::FEBasisOperations &feOp,
+                        const std::vector<double> &fAtQuadPoints, const double *addToDevice = nullptr)
+    {
+      utils::throwException(fAtQuadPoints.size() == feOp.nQuadraturePoints(), "one value of f per quadrature point");
+      utils::hxCheck(hx_cellop_assemble_matrices(H.handle(), feOp.handle(), fAtQuadPoints.data(), 0, addToDevice));
+    }
+
     // DensityCalculator::computeRho (src/ksdft/DensityCalculator.h, .t.cpp:283-437)
     class DensityCalculator
     {

@@ -312,6 +312,12 @@ int hx_fe_basis_destroy(hx_fe_basis *basis);
 int hx_compute_fe_matrices(hx_fe_basis *basis, const double *f_quad, int f_on_device, const double *add_to_dev,
                            double *cell_matrices_dev);
 
+/* The same computation written straight into the operator's re-tiled matrix stream: computeFEMatrices + the component
+ * sum + KohnShamOperatorContextFE::reinit in ONE kernel (no flat S2 array, no re-tiling pass).  The operator keeps its
+ * nonlocal part (hx_cellop_set_nonlocal); add_to_dev (flat S2 layout, e.g. the kinetic cell matrices) may be NULL. */
+int hx_cellop_assemble_matrices(hx_op *op, hx_fe_basis *basis, const double *f_quad, int f_on_device,
+                                const double *add_to_dev);
+
 /* ---- density, the step after the path each SCF iteration ---- */
 /* DensityCalculator::computeRho(occupation, waveFunc, rho) (src/ksdft/DensityCalculator.t.cpp:283-437):
  * rho[q] = sum_i 2 occupation[i] |psi_i(q)|^2 with psi_i(q) = sum_j N_c[q,j] X[cellLocalIds_c[j], i]

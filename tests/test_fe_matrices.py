@@ -125,6 +125,48 @@ def test_assembled_matrices_feed_the_hx_operator(capi):
     assert err.max() < 1e-12
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("enr,p_order,proj", [(2, 3, 0), (0, 4, 0), (3, 2, 2), (2, 5, 2)])
+def test_assembly_straight_into_the_packed_stream(capi, enr, p_order, proj):
+    """hx_cellop_assemble_matrices (assembly + component sum + reinit in one kernel) gives bit for bit the operator the
+    two-step path (flat array, then hx_cellop_set_matrices) gives - with and without a nonlocal part, whose projector
+    columns stay in place."""
+    spec = fe_spec(enr=enr, p=p_order)
+    if proj:
+        spec.n_proj_per_atom, spec.proj_cutoff = proj, 1.0
+        if spec.atoms is None:
+            spec.atoms = np.array([[1.5, 1.5, 1.5]])
+    p = synth.build_problem(spec)[0]
+    fe = synth.fe_basis_data(p)
+    f = synth.potential_at_quad_points(p, int(fe["num_cell_quad"][0]))
+    B = 8
+    plan = capi.Plan(p, max_block=B)
+    feb = capi.FeBasis(plan, fe["num_cell_quad"], fe["basis"], fe["jxw"], fe["same_basis"])
+    base = capi.DeviceBlock(p.S2, 1, 0.5 * p.k_cell)
+    flat = capi.DeviceBlock(p.S2, 1)
+    feb.compute_fe_matrices(f, flat, add_to=base)
+    H2 = capi.CellOp(plan, with_nonlocal=bool(proj))
+    H2.set_matrices_device(flat.ptr)
+    H1 = capi.CellOp(plan, with_nonlocal=bool(proj))   # starts with the generator's matrices: fully overwritten
+    feb.assemble_into(H1, f, add_to=base)
+    X = synth.make_block(p, B)
+    y1, y2 = plan.block(B), plan.block(B)
+    H1.apply(plan.block(B, X), y1, True, False)
+    H2.apply(plan.block(B, X), y2, True, False)
+    assert np.array_equal(y1.download(), y2.download())
+    # a fresh operator (nothing packed yet) and a second assembly with another potential
+    H3 = capi.CellOp.__new__(capi.CellOp)
+    capi.Op.__init__(H3, plan)
+    capi.check(capi.lib().hx_cellop_create(plan.h, __import__("ctypes").byref(H3.h)))
+    feb.assemble_into(H3, 2.0 * f)
+    feb.compute_fe_matrices(2.0 * f, flat)
+    H2.set_matrices_device(flat.ptr)
+    if not proj:
+        H3.apply(plan.block(B, X), y1, True, False)
+        H2.apply(plan.block(B, X), y2, True, False)
+        assert np.array_equal(y1.download(), y2.download())
+
+
 # ------------------------------------------------------------------ 8f rank 3: density ----
 def test_oracle_interpolation_matches_reference_routines(ref_lib):
     """psi at the quadrature points: the oracle's interpolate against the reference's own gather + batched GEMM with
