@@ -288,6 +288,8 @@ def run_ours(args):
         # ---- subspace projections: X^T H X (one column batch, Op.apply + Gram GEMM) and the rotation X <- X Q ----
         sub = {}
         try:
+            if args.quick:
+                raise RuntimeError("skipped (--quick)")
             dXs = Block(X)
             H.xtopx(dXs, B)
             sub["xtopx_ms"] = timed(lambda: H.xtopx(dXs, B), 3)
@@ -302,6 +304,8 @@ def run_ours(args):
         # Rayleigh-Ritz - everything on the device, only the B Ritz values come back ----
         chfsi = {}
         try:
+            if args.quick:
+                raise RuntimeError("skipped (--quick)")
             Mop = capi.DiagOp(plan, prob.diag, prob.enr_block, capi.DIAG_OEFE_MASS)
             lg = np.random.default_rng(11).uniform(-0.5, 0.5, (prob.n_local, 1))
             dlg = capi.DeviceBlock(prob.n_local, 1, lg)
@@ -341,6 +345,8 @@ def run_ours(args):
         # potential (computeFEMatrices + reinit's component sum + re-tiling for the cell kernel) and the density ----
         scf = {}
         try:
+            if args.quick:
+                raise RuntimeError("skipped (--quick)")
             if nranks == 1:
                 fe = synth.fe_basis_data(prob)
                 nqc = int(fe["num_cell_quad"][0])
@@ -379,6 +385,8 @@ def run_ours(args):
         # ---- electrostatics: Laplace apply + Jacobi-preconditioned CG iterations on one right-hand side ----
         poisson = {}
         try:
+            if args.quick:
+                raise RuntimeError("skipped (--quick)")
             if nranks == 1:
                 A_u = capi.CellOp(plan, h_cell=prob.k_cell, with_nonlocal=False)
                 A_l = capi.CellOp(plan, h_cell=prob.k_cell, with_nonlocal=False, share_identical=True)
@@ -473,6 +481,7 @@ def run_ours(args):
                                    f"{spec.n_proj_per_atom} projectors, z-slab per GPU",
                        "global_dofs": N_global, "block": B, "degree": DEGREE, "cells_per_gpu": prob.n_cells,
                        "parallelism": f"cells/{nranks}", "halo_transport": plan.halo_transport(),
+                       "programmatic_dependent_launch": capi.pdl_enabled(),
                        "l2_policy": "inputs larger than L2 (cell matrices %.2f GB + 4 block vectors %.2f GB per GPU)"
                                     % (8 * S2 / 1e9, 4 * blk_bytes / 1e9)},
             "e2e": {"value": DEGREE * N_global * B / (e2e_ms * 1e-3) / 1e9, "unit": UNIT,
@@ -504,7 +513,7 @@ def run_ours(args):
                                  "ms_per_degree": ms_per_step / DEGREE, "fused_recurrence": True,
                                  "phase_ms_per_degree": phases},
         }
-        if not args.no_cpu and nranks == 1:
+        if not args.no_cpu and not args.quick and nranks == 1:
             try:
                 line["cpu_baseline"] = {k: v for k, v in cpu_filter_throughput(threads=1, seconds=10.0, p=spec.p, B=B,
                                                                                  workload=args.workload).items()
@@ -528,6 +537,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=["c2", "small", "c3", "c1"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--quick", action="store_true",
+                    help="only the step, its phase trace, the bare apply and e2e (skips the subspace / ChFSI pass / SCF-neighbour / "
+                         "Poisson extras and the cpu_baseline leg): for A/B runs of one setting")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

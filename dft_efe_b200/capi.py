@@ -27,7 +27,7 @@ EXPORTS = [
     "hx_diagop_create", "hx_op_destroy", "hx_op_apply", "hx_op_apply_host", "hx_chebyshev_filter", "hx_chebyshev_filter_host",
     "hx_residual_chebyshev_filter", "hx_xtopx", "hx_subspace_rotation", "hx_l2_norms", "hx_axpby",
     "hx_axpby_blocked", "hx_plan_launch_count", "hx_plan_cell_kernel_time_ms", "hx_plan_enable_kernel_timing", "hx_plan_trace", "hx_plan_trace_report",
-    "hx_microbench",
+    "hx_microbench", "hx_programmatic_launch_enabled",
     "hx_xtopx_device", "hx_subspace_rotation_device", "hx_dense_cholesky_inverse", "hx_dense_sym_eig",
     "hx_cholesky_gram_schmidt", "hx_rayleigh_ritz", "hx_chfsi_solve", "hx_eigen_residual_norms", "hx_lanczos_extreme",
     "hx_chebyshev_polynomial_degree", "hx_fe_basis_create", "hx_fe_basis_destroy", "hx_compute_fe_matrices", "hx_compute_rho",
@@ -583,6 +583,10 @@ def comm_unique_id() -> bytes:
     buf = C.create_string_buffer(128)
     check(lib().hx_comm_unique_id(buf))
     return buf.raw
+
+
+def pdl_enabled() -> bool:
+    return bool(lib().hx_programmatic_launch_enabled())
 
 
 def microbench():

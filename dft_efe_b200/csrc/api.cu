@@ -22,6 +22,15 @@ namespace hx
     va_end(ap);
   }
 
+  // HXB200_PDL=1 switches programmatic dependent launch on for the small kernels of an apply (read per launch so a
+  // test can toggle it)
+  bool
+  pdl_enabled()
+  {
+    const char *e = getenv("HXB200_PDL");
+    return e && e[0] == '1';
+  }
+
   int
   Halo::init(const hx_halo_desc &h, uint32_t max_block)
   {
@@ -930,6 +939,12 @@ extern "C"
     if (preds)
       memcpy(preds, plan->h_wait_list.data(), sizeof(uint32_t) * plan->h_wait_list.size());
     return HX_OK;
+  }
+
+  int
+  hx_programmatic_launch_enabled(void)
+  {
+    return hx::pdl_enabled() ? 1 : 0;
   }
 
   int

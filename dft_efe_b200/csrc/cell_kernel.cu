@@ -271,6 +271,10 @@ namespace hx
           st_volatile_shared(sbase + SM_Q + 32 * q, 0u);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
       }
+    // programmatic dependent launch: the barrier setup above overlaps the tail of the preceding kernel; nothing in
+    // global memory is touched before the preceding grid has completed
+    pdl_wait();
+    pdl_launch();
     __syncthreads();
 
     if (warp == CWARPS)
@@ -1201,12 +1205,11 @@ namespace hx
       grid = a.nItems;
     cudaEvent_t e1;
     HX_TRY(timing_begin(p, &e1));
-    k<<<grid, V2_THREADS, smem, p->stream>>>(a);
+    HX_CUDA(launch_pdl(k, grid, V2_THREADS, smem, p->stream, a));
     p->launches++;
     p->cell_launches++;
     if (e1)
       HX_CUDA(cudaEventRecord(e1, p->stream));
-    HX_CUDA(cudaGetLastError());
     return HX_OK;
   }
 
@@ -1333,6 +1336,8 @@ namespace hx
                     const double *cellC, const unsigned long long *c_off, double *cx_stage, uint32_t B)
   {
     extern __shared__ __align__(16) double xs[]; // [n][32]
+    pdl_wait();
+    pdl_launch();
     const uint32_t cell = nl_cells[blockIdx.x];
     const uint32_t b0   = blockIdx.y * 32;
     const CellMeta cm   = meta[cell];
@@ -1387,13 +1392,31 @@ namespace hx
   nl_reduce_kernel(const double *cx_stage, const uint32_t *pr_off, const uint32_t *pr_slots, const double *V,
                    double *CX, uint32_t n_rows, uint32_t B, int scale)
   {
+    pdl_wait();
+    pdl_launch();
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (size_t)n_rows * B)
       return;
     const uint32_t row = (uint32_t)(i / B), v = (uint32_t)(i % B);
     double         s = 0.0;
-    for (uint32_t e = pr_off[row]; e < pr_off[row + 1]; ++e)
-      s += cx_stage[(size_t)pr_slots[e] * B + v];
+    // fixed ascending order; the loads of NL_ILP consecutive slots are in flight together (only the adds are serial)
+    constexpr int  NL_ILP = 16;
+    const uint32_t end    = pr_off[row + 1];
+    for (uint32_t e0 = pr_off[row]; e0 < end; e0 += NL_ILP)
+      {
+        uint32_t sl[NL_ILP];
+        double   t[NL_ILP];
+#pragma unroll
+        for (int u = 0; u < NL_ILP; ++u)
+          sl[u] = pr_slots[min(e0 + u, end - 1)]; // clamped: every load is unconditional and in range
+#pragma unroll
+        for (int u = 0; u < NL_ILP; ++u)
+          t[u] = cx_stage[(size_t)sl[u] * B + v];
+#pragma unroll
+        for (int u = 0; u < NL_ILP; ++u)
+          if (e0 + u < end)
+            s += t[u];
+      }
     CX[i] = scale ? V[row] * s : s;
   }
 
@@ -1409,16 +1432,16 @@ namespace hx
         const size_t smem = (size_t)p->max_n * (32 + 8) * sizeof(double);
         HX_CUDA(cudaFuncSetAttribute(nl_phase_a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         dim3 grid(ncell, (B + 31) / 32);
-        nl_phase_a_kernel<<<grid, 256, smem, p->stream>>>(X, p->d_ids.p, op->d_nl_cells.p, op->d_meta.p,
-                                                          op->d_cell_c.p, op->d_c_off.p, op->d_cx_stage.p, B);
+        HX_CUDA(launch_pdl(nl_phase_a_kernel, grid, 256, smem, p->stream, X, p->d_ids.p, op->d_nl_cells.p, op->d_meta.p,
+                           op->d_cell_c.p, op->d_c_off.p, op->d_cx_stage.p, B));
         p->launches++;
       }
     const bool   single = (p->nranks == 1);
     const size_t tot    = (size_t)op->n_proj_local * B;
     if (tot)
       {
-        nl_reduce_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, p->stream>>>(
-          op->d_cx_stage.p, op->d_pr_off.p, op->d_pr_slots.p, op->d_v.p, op->d_cx.p, op->n_proj_local, B, single ? 1 : 0);
+        HX_CUDA(launch_pdl(nl_reduce_kernel, (unsigned)((tot + 255) / 256), 256, 0, p->stream, op->d_cx_stage.p, op->d_pr_off.p,
+                           op->d_pr_slots.p, op->d_v.p, op->d_cx.p, op->n_proj_local, B, single ? 1 : 0));
         p->launches++;
       }
     HX_CUDA(cudaGetLastError());

@@ -51,6 +51,42 @@ namespace hx
     }                     \
   while (0)
 
+  // Programmatic dependent launch (HXB200_PDL=1): the small kernels of one H.X apply / filter degree are launched with
+  // cudaLaunchAttributeProgrammaticStreamSerialization, so the launch and block scheduling of kernel k+1 overlap the
+  // tail of kernel k.  Every such kernel executes pdl_wait() before its first global-memory access (it returns once
+  // the preceding grid has completed and its writes are visible: the stream-order semantics are unchanged) and
+  // pdl_launch() right after it, which lets the next kernel in the stream be scheduled behind this one.  Launched
+  // without the attribute both instructions are no-ops.
+  bool pdl_enabled();
+#ifdef __CUDACC__
+  __device__ __forceinline__ void
+  pdl_wait()
+  {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+  }
+  __device__ __forceinline__ void
+  pdl_launch()
+  {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  }
+  template <typename... KArgs, typename... Args>
+  inline cudaError_t
+  launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args)
+  {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim            = grid;
+    cfg.blockDim           = block;
+    cfg.dynamicSmemBytes   = smem;
+    cfg.stream             = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id                                         = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs                                        = at;
+    cfg.numAttrs                                     = pdl_enabled() ? 1u : 0u;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+  }
+#endif
+
   template <typename T>
   struct DevBuf
   {

@@ -12,6 +12,12 @@ namespace hx
     return (unsigned)((n + t - 1) / t);
   }
 
+  // The fixed-order sums below (constraint rows, parent-side transposes, shared-row slots) are chains of
+  // index -> value loads.  Only the additions have to be serial: the loads of ILP consecutive terms are issued
+  // together, so a chain of m terms costs m / ILP memory latencies instead of m (summation order unchanged).
+  constexpr int ILP    = 8;
+  constexpr int ILP_SH = 16;
+
   // ---- constraints -------------------------------------------------------------------------------
   // distributeParentToChild (src/basis/ConstraintsInternal.cpp:35-108): X[r,:] = inh_r + sum_j w_rj X[col_rj,:].
   // Rows are independent once the constraints are closed (checked at plan creation), so one thread per
@@ -20,14 +26,33 @@ namespace hx
   p2c_kernel(double *X, uint32_t B, uint32_t nR, const uint32_t *rowIds, const uint32_t *rowSizes,
              const uint32_t *rowOffsets, const uint32_t *colIds, const double *colVals, const double *inhom)
   {
+    pdl_wait();
+    pdl_launch();
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (size_t)nR * B)
       return;
     const uint32_t r = (uint32_t)(i / B), v = (uint32_t)(i % B);
     double         s = inhom[r];
     const uint32_t o = rowOffsets[r], m = rowSizes[r];
-    for (uint32_t j = 0; j < m; ++j)
-      s += colVals[o + j] * X[(size_t)colIds[o + j] * B + v];
+    for (uint32_t j0 = 0; j0 < m; j0 += ILP)
+      {
+        uint32_t cid[ILP];
+        double   w[ILP], x[ILP];
+#pragma unroll
+        for (int u = 0; u < ILP; ++u)
+          {
+            const uint32_t j = min(j0 + u, m - 1); // clamped: every load is unconditional and in range
+            cid[u]           = colIds[o + j];
+            w[u]             = colVals[o + j];
+          }
+#pragma unroll
+        for (int u = 0; u < ILP; ++u)
+          x[u] = X[(size_t)cid[u] * B + v];
+#pragma unroll
+        for (int u = 0; u < ILP; ++u)
+          if (j0 + u < m)
+            s += w[u] * x[u];
+      }
     X[(size_t)rowIds[r] * B + v] = s;
   }
 
@@ -37,20 +62,42 @@ namespace hx
   c2p_kernel(double *Y, uint32_t B, uint32_t nPar, const uint32_t *parIds, const uint32_t *parOff,
              const uint32_t *parChild, const double *parW)
   {
+    pdl_wait();
+    pdl_launch();
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (size_t)nPar * B)
       return;
     const uint32_t q = (uint32_t)(i / B), v = (uint32_t)(i % B);
     double *       y = Y + (size_t)parIds[q] * B + v;
     double         s = *y;
-    for (uint32_t e = parOff[q]; e < parOff[q + 1]; ++e)
-      s += parW[e] * Y[(size_t)parChild[e] * B + v];
+    const uint32_t end = parOff[q + 1];
+    for (uint32_t e0 = parOff[q]; e0 < end; e0 += ILP)
+      {
+        uint32_t ch[ILP];
+        double   w[ILP], x[ILP];
+#pragma unroll
+        for (int u = 0; u < ILP; ++u)
+          {
+            const uint32_t e = min(e0 + u, end - 1);
+            ch[u]            = parChild[e];
+            w[u]             = parW[e];
+          }
+#pragma unroll
+        for (int u = 0; u < ILP; ++u)
+          x[u] = Y[(size_t)ch[u] * B + v];
+#pragma unroll
+        for (int u = 0; u < ILP; ++u)
+          if (e0 + u < end)
+            s += w[u] * x[u];
+      }
     *y = s;
   }
 
   __global__ void
   zero_rows_kernel(double *Y, uint32_t B, uint32_t nR, const uint32_t *rowIds)
   {
+    pdl_wait();
+    pdl_launch();
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (size_t)nR * B)
       return;
@@ -63,10 +110,9 @@ namespace hx
     const ConstraintView c = p->constraint_view(set);
     if (c.nR == 0)
       return HX_OK;
-    p2c_kernel<<<nblk((size_t)c.nR * B), 256, 0, p->stream>>>(X, B, c.nR, c.row_ids, c.row_sizes, c.row_offsets, c.col_ids,
-                                                              c.col_vals, c.inhom);
+    HX_CUDA(launch_pdl(p2c_kernel, nblk((size_t)c.nR * B), 256, 0, p->stream, X, B, c.nR, c.row_ids, c.row_sizes, c.row_offsets,
+                       c.col_ids, c.col_vals, c.inhom));
     p->launches++;
-    HX_CUDA(cudaGetLastError());
     return HX_OK;
   }
 
@@ -76,9 +122,8 @@ namespace hx
     const ConstraintView c = p->constraint_view(set);
     if (c.nR == 0)
       return HX_OK;
-    zero_rows_kernel<<<nblk((size_t)c.nR * B), 256, 0, p->stream>>>(Y, B, c.nR, c.row_ids);
+    HX_CUDA(launch_pdl(zero_rows_kernel, nblk((size_t)c.nR * B), 256, 0, p->stream, Y, B, c.nR, c.row_ids));
     p->launches++;
-    HX_CUDA(cudaGetLastError());
     return HX_OK;
   }
 
@@ -87,9 +132,8 @@ namespace hx
   {
     if (n == 0)
       return HX_OK;
-    zero_rows_kernel<<<nblk((size_t)n * B), 256, 0, p->stream>>>(Y, B, n, rows);
+    HX_CUDA(launch_pdl(zero_rows_kernel, nblk((size_t)n * B), 256, 0, p->stream, Y, B, n, rows));
     p->launches++;
-    HX_CUDA(cudaGetLastError());
     return HX_OK;
   }
 
@@ -101,7 +145,8 @@ namespace hx
       return HX_OK;
     if (c.nPar)
       {
-        c2p_kernel<<<nblk((size_t)c.nPar * B), 256, 0, p->stream>>>(Y, B, c.nPar, c.par_ids, c.par_off, c.par_child, c.par_w);
+        HX_CUDA(launch_pdl(c2p_kernel, nblk((size_t)c.nPar * B), 256, 0, p->stream, Y, B, c.nPar, c.par_ids, c.par_off,
+                           c.par_child, c.par_w));
         p->launches++;
       }
     HX_CUDA(cudaGetLastError());
@@ -137,8 +182,22 @@ namespace hx
     const uint32_t r = (uint32_t)(i / B), v = (uint32_t)(i % B);
     double *       d = x + (size_t)rows[r] * B + v;
     double         s = *d;
-    for (uint32_t e = off[r]; e < off[r + 1]; ++e)
-      s += buf[(size_t)pos[e] * B + v];
+    const uint32_t end = off[r + 1];
+    for (uint32_t e0 = off[r]; e0 < end; e0 += ILP)
+      {
+        uint32_t ps[ILP];
+        double   t[ILP];
+#pragma unroll
+        for (int u = 0; u < ILP; ++u)
+          ps[u] = pos[min(e0 + u, end - 1)];
+#pragma unroll
+        for (int u = 0; u < ILP; ++u)
+          t[u] = buf[(size_t)ps[u] * B + v];
+#pragma unroll
+        for (int u = 0; u < ILP; ++u)
+          if (e0 + u < end)
+            s += t[u];
+      }
     *d = s;
   }
 
@@ -456,19 +515,44 @@ namespace hx
   }
 
   // ---- shared-row (enrichment) reduction after the coloured scatter --------------------------------
+  // s = sum over e in [begin, end), ascending, of src[slot(e) * B + v]
+  template <bool INDIRECT>
+  __device__ __forceinline__ double
+  ordered_slot_sum(const double *src, const uint32_t *slots, uint32_t begin, uint32_t end, uint32_t B, uint32_t v)
+  {
+    double s = 0.0;
+    for (uint32_t e0 = begin; e0 < end; e0 += ILP_SH)
+      {
+        uint32_t sl[ILP_SH];
+        double   t[ILP_SH];
+#pragma unroll
+        for (int u = 0; u < ILP_SH; ++u)
+          {
+            const uint32_t e = min(e0 + u, end - 1); // clamped: every load is unconditional and in range
+            sl[u]            = INDIRECT ? slots[e] : e;
+          }
+#pragma unroll
+        for (int u = 0; u < ILP_SH; ++u)
+          t[u] = src[(size_t)sl[u] * B + v];
+#pragma unroll
+        for (int u = 0; u < ILP_SH; ++u)
+          if (e0 + u < end)
+            s += t[u];
+      }
+    return s;
+  }
   __global__ void
   shared_reduce_kernel(double *Y, const double *stage, const uint32_t *rows, const uint32_t *off,
                        const uint32_t *slots, uint32_t nrows, uint32_t B)
   {
+    pdl_wait();
+    pdl_launch();
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (size_t)nrows * B)
       return;
     const uint32_t r = (uint32_t)(i / B), v = (uint32_t)(i % B);
     // shared rows receive every contribution through a staging slot: Y is written, not accumulated
-    double s = 0.0;
-    for (uint32_t e = off[r]; e < off[r + 1]; ++e)
-      s += stage[(size_t)slots[e] * B + v];
-    Y[(size_t)rows[r] * B + v] = s;
+    Y[(size_t)rows[r] * B + v] = ordered_slot_sum<true>(stage, slots, off[r], off[r + 1], B, v);
   }
   // rows shared by very many cells (an enrichment function spans every cell inside its cutoff): two-stage
   // fixed-order reduction - chunks of SH_CHUNK consecutive slots are summed in parallel, then the chunk partials
@@ -477,27 +561,25 @@ namespace hx
   shared_reduce_chunks_kernel(const double *stage, const uint32_t *chBegin, const uint32_t *chEnd, const uint32_t *slots,
                               double *partial, uint32_t nChunks, uint32_t B)
   {
+    pdl_wait();
+    pdl_launch();
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (size_t)nChunks * B)
       return;
     const uint32_t k = (uint32_t)(i / B), v = (uint32_t)(i % B);
-    double         s = 0.0;
-    for (uint32_t e = chBegin[k]; e < chEnd[k]; ++e)
-      s += stage[(size_t)slots[e] * B + v];
-    partial[i] = s;
+    partial[i] = ordered_slot_sum<true>(stage, slots, chBegin[k], chEnd[k], B, v);
   }
   __global__ void
   shared_reduce_final_kernel(double *Y, const double *partial, const uint32_t *rows, const uint32_t *chOff, uint32_t nrows,
                              uint32_t B)
   {
+    pdl_wait();
+    pdl_launch();
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (size_t)nrows * B)
       return;
     const uint32_t r = (uint32_t)(i / B), v = (uint32_t)(i % B);
-    double         s = 0.0;
-    for (uint32_t k = chOff[r]; k < chOff[r + 1]; ++k)
-      s += partial[(size_t)k * B + v];
-    Y[(size_t)rows[r] * B + v] = s;
+    Y[(size_t)rows[r] * B + v] = ordered_slot_sum<false>(partial, nullptr, chOff[r], chOff[r + 1], B, v);
   }
 
   int
@@ -507,19 +589,16 @@ namespace hx
       return HX_OK;
     if (p->n_sh_chunks)
       {
-        shared_reduce_chunks_kernel<<<nblk((size_t)p->n_sh_chunks * B), 256, 0, p->stream>>>(
-          p->d_stage.p, p->d_sh_ch_begin.p, p->d_sh_ch_end.p, p->d_sh_slots.p, p->d_sh_partial.p, p->n_sh_chunks, B);
-        shared_reduce_final_kernel<<<nblk((size_t)p->n_shared * B), 256, 0, p->stream>>>(
-          Y, p->d_sh_partial.p, p->d_sh_rows.p, p->d_sh_ch_off.p, p->n_shared, B);
+        HX_CUDA(launch_pdl(shared_reduce_chunks_kernel, nblk((size_t)p->n_sh_chunks * B), 256, 0, p->stream, p->d_stage.p,
+                           p->d_sh_ch_begin.p, p->d_sh_ch_end.p, p->d_sh_slots.p, p->d_sh_partial.p, p->n_sh_chunks, B));
+        HX_CUDA(launch_pdl(shared_reduce_final_kernel, nblk((size_t)p->n_shared * B), 256, 0, p->stream, Y, p->d_sh_partial.p,
+                           p->d_sh_rows.p, p->d_sh_ch_off.p, p->n_shared, B));
         p->launches += 2;
-        HX_CUDA(cudaGetLastError());
         return HX_OK;
       }
-    shared_reduce_kernel<<<nblk((size_t)p->n_shared * B), 256, 0, p->stream>>>(Y, p->d_stage.p, p->d_sh_rows.p,
-                                                                               p->d_sh_off.p, p->d_sh_slots.p,
-                                                                               p->n_shared, B);
+    HX_CUDA(launch_pdl(shared_reduce_kernel, nblk((size_t)p->n_shared * B), 256, 0, p->stream, Y, p->d_stage.p, p->d_sh_rows.p,
+                       p->d_sh_off.p, p->d_sh_slots.p, p->n_shared, B));
     p->launches++;
-    HX_CUDA(cudaGetLastError());
     return HX_OK;
   }
 
@@ -560,6 +639,8 @@ namespace hx
                     const double *blk, uint32_t ncl, uint32_t nE, uint32_t nRows, uint32_t B, double a, double b,
                     double c, const uint32_t *rows)
   {
+    pdl_wait();
+    pdl_launch();
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (size_t)nRows * B)
       return;
@@ -586,11 +667,31 @@ namespace hx
         else
           t = dinv[r] * s1[i];
         if (info != 0xFFFFFFFFu)
-          for (uint32_t e = parOff[info]; e < parOff[info + 1]; ++e)
-            {
-              const uint32_t ch = parChild[e];
-              t += parW[e] * (dinv[ch] * s1[(size_t)ch * B + v]);
-            }
+          {
+            const uint32_t end = parOff[info + 1];
+            for (uint32_t e0 = parOff[info]; e0 < end; e0 += ILP)
+              {
+                uint32_t ch[ILP];
+                double   w[ILP], dv[ILP], sv[ILP];
+#pragma unroll
+                for (int u = 0; u < ILP; ++u)
+                  {
+                    const uint32_t e = min(e0 + u, end - 1);
+                    ch[u]            = parChild[e];
+                    w[u]             = parW[e];
+                  }
+#pragma unroll
+                for (int u = 0; u < ILP; ++u)
+                  {
+                    dv[u] = dinv[ch[u]];
+                    sv[u] = s1[(size_t)ch[u] * B + v];
+                  }
+#pragma unroll
+                for (int u = 0; u < ILP; ++u)
+                  if (e0 + u < end)
+                    t += w[u] * (dv[u] * sv[u]);
+              }
+          }
       }
     out[i] = cheb_combine(a, t, b, xcur[i], c, c != 0.0 ? xprev[i] : 0.0);
   }
@@ -608,13 +709,10 @@ namespace hx
     const size_t   tot = (size_t)nr * B;
     if (tot == 0)
       return HX_OK;
-    cheb_fused_kernel<<<nblk(tot), 256, 0, p->stream>>>(s1, xcur, xprev ? xprev : xcur, out, binv->d_diag.p,
-                                                        p->d_rowinfo.p, p->d_par_off.p, p->d_par_child.p,
-                                                        p->d_par_w.p, binv->d_enr_block.p, p->n_owned_classical,
-                                                        binv->variant == HX_DIAG_CFE ? 0u : binv->nE, nr, B, a, b,
-                                                        xprev ? c : 0.0, rows);
+    HX_CUDA(launch_pdl(cheb_fused_kernel, nblk(tot), 256, 0, p->stream, s1, xcur, xprev ? xprev : xcur, out, binv->d_diag.p,
+                       p->d_rowinfo.p, p->d_par_off.p, p->d_par_child.p, p->d_par_w.p, binv->d_enr_block.p,
+                       p->n_owned_classical, binv->variant == HX_DIAG_CFE ? 0u : binv->nE, nr, B, a, b, xprev ? c : 0.0, rows));
     p->launches++;
-    HX_CUDA(cudaGetLastError());
     return HX_OK;
   }
 } // namespace hx

@@ -343,6 +343,10 @@ int hx_plan_enable_kernel_timing(hx_plan *plan, int on);
  * nl-halo, cell-kernel, shared+c2p, y-halo, cheb-rest) and clears the trace. */
 int hx_plan_trace(hx_plan *plan, int on);
 int hx_plan_trace_report(hx_plan *plan, char *buf, size_t buf_bytes);
+/* 1 when the short kernels of an apply / filter degree are launched with programmatic dependent launch (the launch of
+ * kernel k+1 overlaps the tail of kernel k; results are bitwise those of serialised launches).  Environment
+ * HXB200_PDL=0 / 1 selects it, read at every launch.  No reference counterpart (the reference launches nothing). */
+int hx_programmatic_launch_enabled(void);
 /* FP64 DMMA / DFMA / copy microbenchmarks used for the roofline denominators. */
 int hx_microbench(double *dmma_tflops, double *dfma_tflops, double *copy_gbs);
 

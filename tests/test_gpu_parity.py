@@ -377,6 +377,44 @@ def test_chebyshev_epilogue_fusion_is_bitwise_the_unfused_recurrence(capi, prob_
     assert rel_l2_per_vector(res[0], F[:p.n_owned]) < 1e-11
 
 
+@pytest.mark.parametrize("B", [1, 8, 40])
+@pytest.mark.parametrize("mesh", ["full", "plain"])
+def test_programmatic_dependent_launch_is_bitwise_the_serialised_launches(capi, prob_full, prob_plain, mesh, B):
+    """Programmatic dependent launch (HXB200_PDL) only overlaps the launch of kernel k+1 with the tail of kernel k:
+    every kernel waits for its predecessor's completion before touching memory, so an apply and a filter (many short
+    kernels back to back, repeated to give an ordering bug a chance to show) must give the same bits either way."""
+    import os
+    p = prob_full if mesh == "full" else prob_plain
+    deg = 12
+    a0, a, b = -3.0, 1.0, 60.0
+    plan = capi.Plan(p, max_block=B)
+    H = capi.CellOp(plan)
+    minv = capi.DiagOp(plan, p.diag_inv, p.enr_block_inv, capi.DIAG_OEFE_ATOMBLOCK)
+    X = synth.make_block(p, B)
+    old = os.environ.get("HXB200_PDL")
+    res = {}
+    try:
+        for mode in ("0", "1"):
+            os.environ["HXB200_PDL"] = mode
+            out = []
+            for _ in range(6):
+                dX, dY = plan.block(B, X), plan.block(B)
+                H.apply(dX, dY, True, False)
+                out.append(dY.download())
+                dX, dY = plan.block(B, X), plan.block(B)
+                capi.chebyshev_filter(H, minv, dX, dY, deg, a0, a, b)
+                out.append(dY.download()[:p.n_owned])
+            res[mode] = out
+    finally:
+        if old is None:
+            os.environ.pop("HXB200_PDL", None)
+        else:
+            os.environ["HXB200_PDL"] = old
+    for k, (u, v) in enumerate(zip(res["0"], res["1"])):
+        assert np.array_equal(u, v), f"result {k} differs between serialised and programmatic dependent launch"
+        assert np.array_equal(u, res["0"][k % 2]), f"result {k} is not reproducible"
+
+
 def test_chebyshev_filter_host_entry(capi, prob_full):
     """hx_chebyshev_filter_host (HOST buffers in/out) == the device entry point, bit for bit."""
     p = prob_full
