@@ -213,6 +213,7 @@ namespace hx
         HX_CHECK(rowinfo[m->row_ids[i]] == 0xFFFFFFFFu, HX_ERR_INVALID, "duplicate constraint row %u", m->row_ids[i]);
         rowinfo[m->row_ids[i]] = 0xFFFFFFFEu;
         p->nnz                 = std::max(p->nnz, m->row_offsets[i] + m->row_sizes[i]);
+        p->max_row             = std::max(p->max_row, m->row_sizes[i]);
       }
     std::map<uint32_t, std::vector<std::pair<uint32_t, double>>> par;
     for (uint32_t i = 0; i < p->nR; ++i)
@@ -241,6 +242,7 @@ namespace hx
             p->h_par_w.push_back(e.second);
           }
         p->h_par_off.push_back((uint32_t)p->h_par_child.size());
+        p->max_child = std::max(p->max_child, (uint32_t)kv.second.size());
       }
     p->nPar = (uint32_t)p->h_par_ids.size();
     p->h_row_ids.assign(m->row_ids, m->row_ids + p->nR);
@@ -664,7 +666,7 @@ hx_plan::constraint_view(uint32_t set) const
   if (set > 0 && set <= extra_constraints.size())
     return extra_constraints[set - 1]->view();
   hx::ConstraintView v;
-  v.nR = nR, v.nPar = nPar;
+  v.nR = nR, v.nPar = nPar, v.max_row = max_row, v.max_child = max_child;
   v.row_ids = d_row_ids.p, v.row_sizes = d_row_sizes.p, v.row_offsets = d_row_offsets.p, v.col_ids = d_col_ids.p;
   v.col_vals = d_col_vals.p, v.inhom = d_inhom.p;
   v.par_ids = d_par_ids.p, v.par_off = d_par_off.p, v.par_child = d_par_child.p, v.par_w = d_par_w.p;
@@ -1046,6 +1048,7 @@ extern "C"
         HX_CHECK(!constrained[row_ids[i]], HX_ERR_INVALID, "duplicate constraint row %u", row_ids[i]);
         constrained[row_ids[i]] = 1;
         c->nnz                  = std::max(c->nnz, row_offsets[i] + row_sizes[i]);
+        c->max_row              = std::max(c->max_row, row_sizes[i]);
       }
     std::map<uint32_t, std::vector<std::pair<uint32_t, double>>> par;
     for (uint32_t i = 0; i < n_rows; ++i)
@@ -1068,6 +1071,7 @@ extern "C"
             par_w.push_back(e.second);
           }
         par_off.push_back((uint32_t)par_child.size());
+        c->max_child = std::max(c->max_child, (uint32_t)kv.second.size());
       }
     c->nPar = (uint32_t)par_ids.size();
     HX_TRY(c->d_row_ids.upload(row_ids, n_rows));

@@ -195,6 +195,7 @@ namespace hx
   struct ConstraintView
   {
     uint32_t        nR = 0, nPar = 0;
+    uint32_t        max_row = 0, max_child = 0; // longest constraint row / longest child list of a parent
     const uint32_t *row_ids = nullptr, *row_sizes = nullptr, *row_offsets = nullptr, *col_ids = nullptr;
     const double *  col_vals = nullptr, *inhom = nullptr;
     const uint32_t *par_ids = nullptr, *par_off = nullptr, *par_child = nullptr;
@@ -202,14 +203,14 @@ namespace hx
   };
   struct ConstraintSet
   {
-    uint32_t         nR = 0, nnz = 0, nPar = 0;
+    uint32_t         nR = 0, nnz = 0, nPar = 0, max_row = 0, max_child = 0;
     DevBuf<uint32_t> d_row_ids, d_row_sizes, d_row_offsets, d_col_ids, d_par_ids, d_par_off, d_par_child;
     DevBuf<double>   d_col_vals, d_inhom, d_par_w;
     ConstraintView
     view() const
     {
       ConstraintView v;
-      v.nR = nR, v.nPar = nPar;
+      v.nR = nR, v.nPar = nPar, v.max_row = max_row, v.max_child = max_child;
       v.row_ids = d_row_ids.p, v.row_sizes = d_row_sizes.p, v.row_offsets = d_row_offsets.p, v.col_ids = d_col_ids.p;
       v.col_vals = d_col_vals.p, v.inhom = d_inhom.p;
       v.par_ids = d_par_ids.p, v.par_off = d_par_off.p, v.par_child = d_par_child.p, v.par_w = d_par_w.p;
@@ -279,7 +280,7 @@ struct hx_plan
   uint32_t              nR = 0, nnz = 0;
   hx::DevBuf<uint32_t>  d_row_ids, d_row_sizes, d_row_offsets, d_col_ids;
   hx::DevBuf<double>    d_col_vals, d_inhom;
-  uint32_t              nPar = 0;
+  uint32_t              nPar = 0, max_row = 0, max_child = 0; // longest constraint row / child list (chain depth of the row kernels)
   std::vector<uint32_t> h_par_ids, h_par_off, h_par_child;
   std::vector<double>   h_par_w;
   hx::DevBuf<uint32_t>  d_par_ids, d_par_off, d_par_child;

@@ -12,97 +12,195 @@ namespace hx
     return (unsigned)((n + t - 1) / t);
   }
 
+  // ---- shared machinery of the row kernels -----------------------------------------------------------
+  // A thread owns VEC consecutive columns of one row (VEC = 2: 16-byte accesses, B even and 16-B aligned blocks), so a
+  // row of B doubles is moved by B / VEC lanes with whole 32-byte sectors.  Each column is computed exactly as in the
+  // scalar form, so VEC does not change a single bit of the result.
+  template <int VEC>
+  struct VD
+  {
+    double v[VEC];
+  };
+  template <int VEC>
+  __device__ __forceinline__ VD<VEC>
+  ldv(const double *p)
+  {
+    VD<VEC> r;
+    if constexpr (VEC == 2)
+      {
+        const double2 t = *reinterpret_cast<const double2 *>(p);
+        r.v[0] = t.x, r.v[1] = t.y;
+      }
+    else
+      r.v[0] = *p;
+    return r;
+  }
+  template <int VEC>
+  __device__ __forceinline__ void
+  stv(double *p, const VD<VEC> &x)
+  {
+    if constexpr (VEC == 2)
+      *reinterpret_cast<double2 *>(p) = make_double2(x.v[0], x.v[1]);
+    else
+      *p = x.v[0];
+  }
+  static inline bool
+  aligned16(const void *a, const void *b = nullptr, const void *c = nullptr, const void *d = nullptr)
+  {
+    return ((((uintptr_t)a) | ((uintptr_t)b) | ((uintptr_t)c) | ((uintptr_t)d)) & 15) == 0;
+  }
+
   // The fixed-order sums below (constraint rows, parent-side transposes, shared-row slots) are chains of
-  // index -> value loads.  Only the additions have to be serial: the loads of ILP consecutive terms are issued
-  // together, so a chain of m terms costs m / ILP memory latencies instead of m (summation order unchanged).
-  constexpr int ILP    = 8;
-  constexpr int ILP_SH = 16;
+  // index -> value loads.  Only the additions have to be serial: the index loads of U consecutive terms are issued
+  // together, then their value loads, so a chain of m terms costs about 2 m / U memory latencies instead of 2 m; the
+  // summation order is the sequential one.  Indices beyond the end
+  // are clamped to the last entry (every load unconditional and in range), their terms are not accumulated.
+  template <int U, typename I, typename V, typename FI, typename FV, typename FA>
+  __device__ __forceinline__ void
+  ordered_chain(uint32_t begin, uint32_t end, FI load_idx, FV load_val, FA accumulate)
+  {
+    if (begin >= end)
+      return;
+    I idx[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      idx[u] = load_idx(min(begin + (uint32_t)u, end - 1));
+    for (uint32_t e0 = begin; e0 < end; e0 += U)
+      {
+        V val[U];
+        I cur[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          {
+            cur[u] = idx[u];
+            val[u] = load_val(cur[u]);
+          }
+        // (kept conditional on purpose: written unconditionally ptxas interleaves the value loads with the additions
+        // that wait for them; in this form all U value loads are issued back to back)
+        if (e0 + U < end)
+          {
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+              idx[u] = load_idx(min(e0 + U + (uint32_t)u, end - 1));
+          }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          if (e0 + u < end)
+            accumulate(cur[u], val[u]);
+      }
+  }
+  // chain depth by the longest chain of the data (known at plan creation): short chains keep the register count low
+  static inline int
+  chain_depth(uint32_t longest)
+  {
+    return longest <= 1 ? 1 : (longest <= 32 ? 8 : 16);
+  }
+  struct WeightedRow
+  {
+    uint32_t row;
+    double   w;
+  };
 
   // ---- constraints -------------------------------------------------------------------------------
   // distributeParentToChild (src/basis/ConstraintsInternal.cpp:35-108): X[r,:] = inh_r + sum_j w_rj X[col_rj,:].
   // Rows are independent once the constraints are closed (checked at plan creation), so one thread per
-  // (row, vector); the j-order of the reference is kept.
+  // (row, VEC columns); the j-order of the reference is kept.
+  template <int VEC, int U>
   __global__ void
   p2c_kernel(double *X, uint32_t B, uint32_t nR, const uint32_t *rowIds, const uint32_t *rowSizes,
              const uint32_t *rowOffsets, const uint32_t *colIds, const double *colVals, const double *inhom)
   {
     pdl_wait();
     pdl_launch();
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (size_t)nR * B)
+    const uint32_t bv = B / VEC;
+    const size_t   i  = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)nR * bv)
       return;
-    const uint32_t r = (uint32_t)(i / B), v = (uint32_t)(i % B);
-    double         s = inhom[r];
+    const uint32_t r = (uint32_t)(i / bv), v = (uint32_t)(i % bv) * VEC;
+    VD<VEC>        s;
+#pragma unroll
+    for (int k = 0; k < VEC; ++k)
+      s.v[k] = inhom[r];
     const uint32_t o = rowOffsets[r], m = rowSizes[r];
-    for (uint32_t j0 = 0; j0 < m; j0 += ILP)
-      {
-        uint32_t cid[ILP];
-        double   w[ILP], x[ILP];
+    ordered_chain<U, WeightedRow, VD<VEC>>(
+      o, o + m, [&](uint32_t e) { return WeightedRow{colIds[e], colVals[e]}; },
+      [&](const WeightedRow &q) { return ldv<VEC>(X + (size_t)q.row * B + v); },
+      [&](const WeightedRow &q, const VD<VEC> &x) {
 #pragma unroll
-        for (int u = 0; u < ILP; ++u)
-          {
-            const uint32_t j = min(j0 + u, m - 1); // clamped: every load is unconditional and in range
-            cid[u]           = colIds[o + j];
-            w[u]             = colVals[o + j];
-          }
-#pragma unroll
-        for (int u = 0; u < ILP; ++u)
-          x[u] = X[(size_t)cid[u] * B + v];
-#pragma unroll
-        for (int u = 0; u < ILP; ++u)
-          if (j0 + u < m)
-            s += w[u] * x[u];
-      }
-    X[(size_t)rowIds[r] * B + v] = s;
+        for (int k = 0; k < VEC; ++k)
+          s.v[k] += q.w * x.v[k];
+      });
+    stv<VEC>(X + (size_t)rowIds[r] * B + v, s);
   }
 
   // distributeChildToParent (src/basis/ConstraintsInternal.cpp:110-170) without atomics: one thread per
-  // (parent, vector) walks the parent-side transpose in the reference's (row, entry) order.
+  // (parent, VEC columns) walks the parent-side transpose in the reference's (row, entry) order.
+  template <int VEC, int U>
   __global__ void
   c2p_kernel(double *Y, uint32_t B, uint32_t nPar, const uint32_t *parIds, const uint32_t *parOff,
              const uint32_t *parChild, const double *parW)
   {
     pdl_wait();
     pdl_launch();
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (size_t)nPar * B)
+    const uint32_t bv = B / VEC;
+    const size_t   i  = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)nPar * bv)
       return;
-    const uint32_t q = (uint32_t)(i / B), v = (uint32_t)(i % B);
+    const uint32_t q = (uint32_t)(i / bv), v = (uint32_t)(i % bv) * VEC;
     double *       y = Y + (size_t)parIds[q] * B + v;
-    double         s = *y;
-    const uint32_t end = parOff[q + 1];
-    for (uint32_t e0 = parOff[q]; e0 < end; e0 += ILP)
-      {
-        uint32_t ch[ILP];
-        double   w[ILP], x[ILP];
+    VD<VEC>        s = ldv<VEC>(y);
+    ordered_chain<U, WeightedRow, VD<VEC>>(
+      parOff[q], parOff[q + 1], [&](uint32_t e) { return WeightedRow{parChild[e], parW[e]}; },
+      [&](const WeightedRow &c) { return ldv<VEC>(Y + (size_t)c.row * B + v); },
+      [&](const WeightedRow &c, const VD<VEC> &x) {
 #pragma unroll
-        for (int u = 0; u < ILP; ++u)
-          {
-            const uint32_t e = min(e0 + u, end - 1);
-            ch[u]            = parChild[e];
-            w[u]             = parW[e];
-          }
-#pragma unroll
-        for (int u = 0; u < ILP; ++u)
-          x[u] = Y[(size_t)ch[u] * B + v];
-#pragma unroll
-        for (int u = 0; u < ILP; ++u)
-          if (e0 + u < end)
-            s += w[u] * x[u];
-      }
-    *y = s;
+        for (int k = 0; k < VEC; ++k)
+          s.v[k] += c.w * x.v[k];
+      });
+    stv<VEC>(y, s);
   }
 
+  template <int VEC>
   __global__ void
   zero_rows_kernel(double *Y, uint32_t B, uint32_t nR, const uint32_t *rowIds)
   {
     pdl_wait();
     pdl_launch();
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (size_t)nR * B)
+    const uint32_t bv = B / VEC;
+    const size_t   i  = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)nR * bv)
       return;
-    Y[(size_t)rowIds[i / B] * B + (i % B)] = 0.0;
+    VD<VEC> z;
+#pragma unroll
+    for (int k = 0; k < VEC; ++k)
+      z.v[k] = 0.0;
+    stv<VEC>(Y + (size_t)rowIds[i / bv] * B + (i % bv) * VEC, z);
   }
+
+// picks the <VEC, U> instantiation: vec_ (bool) and depth_ (1 / 8 / 16) are run-time values
+#define HX_VEC_DEPTH_DISPATCH(vec_, depth_, CALL) \
+  do                                              \
+    {                                             \
+      if (vec_)                                   \
+        {                                         \
+          if ((depth_) == 1)                      \
+            CALL(2, 1);                           \
+          else if ((depth_) == 8)                 \
+            CALL(2, 8);                           \
+          else                                    \
+            CALL(2, 16);                          \
+        }                                         \
+      else                                        \
+        {                                         \
+          if ((depth_) == 1)                      \
+            CALL(1, 1);                           \
+          else if ((depth_) == 8)                 \
+            CALL(1, 8);                           \
+          else                                    \
+            CALL(1, 16);                          \
+        }                                         \
+    }                                             \
+  while (0)
 
   int
   launch_p2c(hx_plan *p, double *X, uint32_t B, uint32_t set)
@@ -110,19 +208,14 @@ namespace hx
     const ConstraintView c = p->constraint_view(set);
     if (c.nR == 0)
       return HX_OK;
-    HX_CUDA(launch_pdl(p2c_kernel, nblk((size_t)c.nR * B), 256, 0, p->stream, X, B, c.nR, c.row_ids, c.row_sizes, c.row_offsets,
-                       c.col_ids, c.col_vals, c.inhom));
-    p->launches++;
-    return HX_OK;
-  }
-
-  int
-  launch_zero_constrained(hx_plan *p, double *Y, uint32_t B, uint32_t set)
-  {
-    const ConstraintView c = p->constraint_view(set);
-    if (c.nR == 0)
-      return HX_OK;
-    HX_CUDA(launch_pdl(zero_rows_kernel, nblk((size_t)c.nR * B), 256, 0, p->stream, Y, B, c.nR, c.row_ids));
+    const bool vec = (B % 2 == 0) && aligned16(X);
+    const int  dep = chain_depth(c.max_row);
+    const unsigned nb = nblk((size_t)c.nR * (B / (vec ? 2 : 1)));
+#define HX_CALL(V_, U_)                                                                                               \
+  HX_CUDA(launch_pdl(p2c_kernel<V_, U_>, nb, 256, 0, p->stream, X, B, c.nR, c.row_ids, c.row_sizes, c.row_offsets, \
+                     c.col_ids, c.col_vals, c.inhom))
+    HX_VEC_DEPTH_DISPATCH(vec, dep, HX_CALL);
+#undef HX_CALL
     p->launches++;
     return HX_OK;
   }
@@ -132,9 +225,19 @@ namespace hx
   {
     if (n == 0)
       return HX_OK;
-    HX_CUDA(launch_pdl(zero_rows_kernel, nblk((size_t)n * B), 256, 0, p->stream, Y, B, n, rows));
+    if ((B % 2 == 0) && aligned16(Y))
+      HX_CUDA(launch_pdl(zero_rows_kernel<2>, nblk((size_t)n * (B / 2)), 256, 0, p->stream, Y, B, n, rows));
+    else
+      HX_CUDA(launch_pdl(zero_rows_kernel<1>, nblk((size_t)n * B), 256, 0, p->stream, Y, B, n, rows));
     p->launches++;
     return HX_OK;
+  }
+
+  int
+  launch_zero_constrained(hx_plan *p, double *Y, uint32_t B, uint32_t set)
+  {
+    const ConstraintView c = p->constraint_view(set);
+    return launch_zero_rows(p, Y, B, c.row_ids, c.nR);
   }
 
   int
@@ -145,11 +248,15 @@ namespace hx
       return HX_OK;
     if (c.nPar)
       {
-        HX_CUDA(launch_pdl(c2p_kernel, nblk((size_t)c.nPar * B), 256, 0, p->stream, Y, B, c.nPar, c.par_ids, c.par_off,
-                           c.par_child, c.par_w));
+        const bool     vec = (B % 2 == 0) && aligned16(Y);
+        const int      dep = chain_depth(c.max_child);
+        const unsigned nb  = nblk((size_t)c.nPar * (B / (vec ? 2 : 1)));
+#define HX_CALL(V_, U_) \
+  HX_CUDA(launch_pdl(c2p_kernel<V_, U_>, nb, 256, 0, p->stream, Y, B, c.nPar, c.par_ids, c.par_off, c.par_child, c.par_w))
+        HX_VEC_DEPTH_DISPATCH(vec, dep, HX_CALL);
+#undef HX_CALL
         p->launches++;
       }
-    HX_CUDA(cudaGetLastError());
     return launch_zero_constrained(p, Y, B, set);
   }
 
@@ -182,22 +289,9 @@ namespace hx
     const uint32_t r = (uint32_t)(i / B), v = (uint32_t)(i % B);
     double *       d = x + (size_t)rows[r] * B + v;
     double         s = *d;
-    const uint32_t end = off[r + 1];
-    for (uint32_t e0 = off[r]; e0 < end; e0 += ILP)
-      {
-        uint32_t ps[ILP];
-        double   t[ILP];
-#pragma unroll
-        for (int u = 0; u < ILP; ++u)
-          ps[u] = pos[min(e0 + u, end - 1)];
-#pragma unroll
-        for (int u = 0; u < ILP; ++u)
-          t[u] = buf[(size_t)ps[u] * B + v];
-#pragma unroll
-        for (int u = 0; u < ILP; ++u)
-          if (e0 + u < end)
-            s += t[u];
-      }
+    ordered_chain<8, uint32_t, double>(
+      off[r], off[r + 1], [&](uint32_t e) { return pos[e]; }, [&](uint32_t ps) { return buf[(size_t)ps * B + v]; },
+      [&](uint32_t, double t) { s += t; });
     *d = s;
   }
 
@@ -514,92 +608,100 @@ namespace hx
     return HX_OK;
   }
 
-  // ---- shared-row (enrichment) reduction after the coloured scatter --------------------------------
-  // s = sum over e in [begin, end), ascending, of src[slot(e) * B + v]
-  template <bool INDIRECT>
-  __device__ __forceinline__ double
+  // ---- shared-row (enrichment) reduction after the cell kernel's scatter -----------------------------
+  // s = sum over e in [begin, end), ascending, of src[slot(e) * B + v .. v + VEC)
+  template <int VEC, bool INDIRECT>
+  __device__ __forceinline__ VD<VEC>
   ordered_slot_sum(const double *src, const uint32_t *slots, uint32_t begin, uint32_t end, uint32_t B, uint32_t v)
   {
-    double s = 0.0;
-    for (uint32_t e0 = begin; e0 < end; e0 += ILP_SH)
-      {
-        uint32_t sl[ILP_SH];
-        double   t[ILP_SH];
+    VD<VEC> s;
 #pragma unroll
-        for (int u = 0; u < ILP_SH; ++u)
-          {
-            const uint32_t e = min(e0 + u, end - 1); // clamped: every load is unconditional and in range
-            sl[u]            = INDIRECT ? slots[e] : e;
-          }
+    for (int k = 0; k < VEC; ++k)
+      s.v[k] = 0.0;
+    ordered_chain<16, uint32_t, VD<VEC>>(
+      begin, end, [&](uint32_t e) { return INDIRECT ? slots[e] : e; },
+      [&](uint32_t sl) { return ldv<VEC>(src + (size_t)sl * B + v); },
+      [&](uint32_t, const VD<VEC> &t) {
 #pragma unroll
-        for (int u = 0; u < ILP_SH; ++u)
-          t[u] = src[(size_t)sl[u] * B + v];
-#pragma unroll
-        for (int u = 0; u < ILP_SH; ++u)
-          if (e0 + u < end)
-            s += t[u];
-      }
+        for (int k = 0; k < VEC; ++k)
+          s.v[k] += t.v[k];
+      });
     return s;
   }
+  template <int VEC>
   __global__ void
   shared_reduce_kernel(double *Y, const double *stage, const uint32_t *rows, const uint32_t *off,
                        const uint32_t *slots, uint32_t nrows, uint32_t B)
   {
     pdl_wait();
     pdl_launch();
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (size_t)nrows * B)
+    const uint32_t bv = B / VEC;
+    const size_t   i  = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)nrows * bv)
       return;
-    const uint32_t r = (uint32_t)(i / B), v = (uint32_t)(i % B);
+    const uint32_t r = (uint32_t)(i / bv), v = (uint32_t)(i % bv) * VEC;
     // shared rows receive every contribution through a staging slot: Y is written, not accumulated
-    Y[(size_t)rows[r] * B + v] = ordered_slot_sum<true>(stage, slots, off[r], off[r + 1], B, v);
+    stv<VEC>(Y + (size_t)rows[r] * B + v, ordered_slot_sum<VEC, true>(stage, slots, off[r], off[r + 1], B, v));
   }
   // rows shared by very many cells (an enrichment function spans every cell inside its cutoff): two-stage
   // fixed-order reduction - chunks of SH_CHUNK consecutive slots are summed in parallel, then the chunk partials
   // of a row in chunk order.  Deterministic; the grouping differs from the plain ascending sum only in rounding.
+  template <int VEC>
   __global__ void
   shared_reduce_chunks_kernel(const double *stage, const uint32_t *chBegin, const uint32_t *chEnd, const uint32_t *slots,
                               double *partial, uint32_t nChunks, uint32_t B)
   {
     pdl_wait();
     pdl_launch();
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (size_t)nChunks * B)
+    const uint32_t bv = B / VEC;
+    const size_t   i  = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)nChunks * bv)
       return;
-    const uint32_t k = (uint32_t)(i / B), v = (uint32_t)(i % B);
-    partial[i] = ordered_slot_sum<true>(stage, slots, chBegin[k], chEnd[k], B, v);
+    const uint32_t k = (uint32_t)(i / bv), v = (uint32_t)(i % bv) * VEC;
+    stv<VEC>(partial + (size_t)k * B + v, ordered_slot_sum<VEC, true>(stage, slots, chBegin[k], chEnd[k], B, v));
   }
+  template <int VEC>
   __global__ void
   shared_reduce_final_kernel(double *Y, const double *partial, const uint32_t *rows, const uint32_t *chOff, uint32_t nrows,
                              uint32_t B)
   {
     pdl_wait();
     pdl_launch();
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (size_t)nrows * B)
+    const uint32_t bv = B / VEC;
+    const size_t   i  = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)nrows * bv)
       return;
-    const uint32_t r = (uint32_t)(i / B), v = (uint32_t)(i % B);
-    Y[(size_t)rows[r] * B + v] = ordered_slot_sum<false>(partial, nullptr, chOff[r], chOff[r + 1], B, v);
+    const uint32_t r = (uint32_t)(i / bv), v = (uint32_t)(i % bv) * VEC;
+    stv<VEC>(Y + (size_t)rows[r] * B + v, ordered_slot_sum<VEC, false>(partial, nullptr, chOff[r], chOff[r + 1], B, v));
   }
 
+  template <int VEC>
+  static int
+  launch_shared_reduce_v(hx_plan *p, double *Y, uint32_t B)
+  {
+    const uint32_t bv = B / VEC;
+    if (p->n_sh_chunks)
+      {
+        HX_CUDA(launch_pdl(shared_reduce_chunks_kernel<VEC>, nblk((size_t)p->n_sh_chunks * bv), 256, 0, p->stream, p->d_stage.p,
+                           p->d_sh_ch_begin.p, p->d_sh_ch_end.p, p->d_sh_slots.p, p->d_sh_partial.p, p->n_sh_chunks, B));
+        HX_CUDA(launch_pdl(shared_reduce_final_kernel<VEC>, nblk((size_t)p->n_shared * bv), 256, 0, p->stream, Y,
+                           p->d_sh_partial.p, p->d_sh_rows.p, p->d_sh_ch_off.p, p->n_shared, B));
+        p->launches += 2;
+        return HX_OK;
+      }
+    HX_CUDA(launch_pdl(shared_reduce_kernel<VEC>, nblk((size_t)p->n_shared * bv), 256, 0, p->stream, Y, p->d_stage.p,
+                       p->d_sh_rows.p, p->d_sh_off.p, p->d_sh_slots.p, p->n_shared, B));
+    p->launches++;
+    return HX_OK;
+  }
   int
   launch_shared_reduce(hx_plan *p, double *Y, uint32_t B)
   {
     if (p->n_shared == 0)
       return HX_OK;
-    if (p->n_sh_chunks)
-      {
-        HX_CUDA(launch_pdl(shared_reduce_chunks_kernel, nblk((size_t)p->n_sh_chunks * B), 256, 0, p->stream, p->d_stage.p,
-                           p->d_sh_ch_begin.p, p->d_sh_ch_end.p, p->d_sh_slots.p, p->d_sh_partial.p, p->n_sh_chunks, B));
-        HX_CUDA(launch_pdl(shared_reduce_final_kernel, nblk((size_t)p->n_shared * B), 256, 0, p->stream, Y, p->d_sh_partial.p,
-                           p->d_sh_rows.p, p->d_sh_ch_off.p, p->n_shared, B));
-        p->launches += 2;
-        return HX_OK;
-      }
-    HX_CUDA(launch_pdl(shared_reduce_kernel, nblk((size_t)p->n_shared * B), 256, 0, p->stream, Y, p->d_stage.p, p->d_sh_rows.p,
-                       p->d_sh_off.p, p->d_sh_slots.p, p->n_shared, B));
-    p->launches++;
-    return HX_OK;
+    if ((B % 2 == 0) && aligned16(Y, p->d_stage.p, p->d_sh_partial.p))
+      return launch_shared_reduce_v<2>(p, Y, B);
+    return launch_shared_reduce_v<1>(p, Y, B);
   }
 
   // ---- atom-block enrichment matrix: Yenr (B x nE) = Xenr (B x nE) * blk (nE x nE), col-major ----------
@@ -633,6 +735,13 @@ namespace hx
   //   out    = a*t + b*xcur + c*xprev                           (the two axpby of ChebyshevFilter.t.cpp:105-124)
   // s1 must already have its constrained rows filled (p2c launched before).  rowinfo[i]: 0xFFFFFFFF = free row
   // without children, 0xFFFFFFFE = constrained row (-> t = 0), else index into the parent-side CSR.
+  template <int VEC>
+  struct ChildVal
+  {
+    double  dinv;
+    VD<VEC> s;
+  };
+  template <int VEC, int U>
   __global__ void
   cheb_fused_kernel(const double *s1, const double *xcur, const double *xprev, double *out, const double *dinv,
                     const uint32_t *rowinfo, const uint32_t *parOff, const uint32_t *parChild, const double *parW,
@@ -641,59 +750,75 @@ namespace hx
   {
     pdl_wait();
     pdl_launch();
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (size_t)nRows * B)
+    const uint32_t bv = B / VEC;
+    const size_t   g  = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= (size_t)nRows * bv)
       return;
-    uint32_t r = (uint32_t)(i / B);
-    const uint32_t v = (uint32_t)(i % B);
+    uint32_t       r = (uint32_t)(g / bv);
+    const uint32_t v = (uint32_t)(g % bv) * VEC;
     if (rows)
+      r = rows[r];
+    const size_t   i = (size_t)r * B + v;
+    // the recurrence operands do not depend on the M^-1 part: their loads go first (out may alias xprev - the same
+    // thread reads before it writes)
+    const VD<VEC> xc = ldv<VEC>(xcur + i);
+    VD<VEC>       xp;
+    if (c != 0.0)
+      xp = ldv<VEC>(xprev + i);
+    else
       {
-        r = rows[r];
-        i = (size_t)r * B + v;
+#pragma unroll
+        for (int k = 0; k < VEC; ++k)
+          xp.v[k] = 0.0;
       }
-    double         t;
+    VD<VEC>        t;
     const uint32_t info = rowinfo[r];
     if (info == 0xFFFFFFFEu)
-      t = 0.0;
+      {
+#pragma unroll
+        for (int k = 0; k < VEC; ++k)
+          t.v[k] = 0.0;
+      }
     else
       {
         if (r >= ncl && nE > 0)
           {
-            t = 0.0;
+#pragma unroll
+            for (int k = 0; k < VEC; ++k)
+              t.v[k] = 0.0;
             const uint32_t j = r - ncl;
-            for (uint32_t k = 0; k < nE; ++k)
-              t += s1[(size_t)(ncl + k) * B + v] * blk[(size_t)k + (size_t)j * nE];
-          }
-        else
-          t = dinv[r] * s1[i];
-        if (info != 0xFFFFFFFFu)
-          {
-            const uint32_t end = parOff[info + 1];
-            for (uint32_t e0 = parOff[info]; e0 < end; e0 += ILP)
+            for (uint32_t e = 0; e < nE; ++e)
               {
-                uint32_t ch[ILP];
-                double   w[ILP], dv[ILP], sv[ILP];
+                const VD<VEC> sv = ldv<VEC>(s1 + (size_t)(ncl + e) * B + v);
+                const double  m  = blk[(size_t)e + (size_t)j * nE];
 #pragma unroll
-                for (int u = 0; u < ILP; ++u)
-                  {
-                    const uint32_t e = min(e0 + u, end - 1);
-                    ch[u]            = parChild[e];
-                    w[u]             = parW[e];
-                  }
-#pragma unroll
-                for (int u = 0; u < ILP; ++u)
-                  {
-                    dv[u] = dinv[ch[u]];
-                    sv[u] = s1[(size_t)ch[u] * B + v];
-                  }
-#pragma unroll
-                for (int u = 0; u < ILP; ++u)
-                  if (e0 + u < end)
-                    t += w[u] * (dv[u] * sv[u]);
+                for (int k = 0; k < VEC; ++k)
+                  t.v[k] += sv.v[k] * m;
               }
           }
+        else
+          {
+            const double  d  = dinv[r];
+            const VD<VEC> sv = ldv<VEC>(s1 + i);
+#pragma unroll
+            for (int k = 0; k < VEC; ++k)
+              t.v[k] = d * sv.v[k];
+          }
+        if (info != 0xFFFFFFFFu)
+          ordered_chain<U, WeightedRow, ChildVal<VEC>>(
+            parOff[info], parOff[info + 1], [&](uint32_t e) { return WeightedRow{parChild[e], parW[e]}; },
+            [&](const WeightedRow &q) { return ChildVal<VEC>{dinv[q.row], ldv<VEC>(s1 + (size_t)q.row * B + v)}; },
+            [&](const WeightedRow &q, const ChildVal<VEC> &ch) {
+#pragma unroll
+              for (int k = 0; k < VEC; ++k)
+                t.v[k] += q.w * (ch.dinv * ch.s.v[k]);
+            });
       }
-    out[i] = cheb_combine(a, t, b, xcur[i], c, c != 0.0 ? xprev[i] : 0.0);
+    VD<VEC> o;
+#pragma unroll
+    for (int k = 0; k < VEC; ++k)
+      o.v[k] = cheb_combine(a, t.v[k], b, xc.v[k], c, xp.v[k]);
+    stv<VEC>(out + i, o);
   }
 } // namespace hx
 
@@ -709,9 +834,31 @@ namespace hx
     const size_t   tot = (size_t)nr * B;
     if (tot == 0)
       return HX_OK;
-    HX_CUDA(launch_pdl(cheb_fused_kernel, nblk(tot), 256, 0, p->stream, s1, xcur, xprev ? xprev : xcur, out, binv->d_diag.p,
-                       p->d_rowinfo.p, p->d_par_off.p, p->d_par_child.p, p->d_par_w.p, binv->d_enr_block.p,
-                       p->n_owned_classical, binv->variant == HX_DIAG_CFE ? 0u : binv->nE, nr, B, a, b, xprev ? c : 0.0, rows));
+    const double * xp  = xprev ? xprev : xcur;
+    const bool     vec = (B % 2 == 0) && aligned16(s1, xcur, xp, out);
+    // this kernel is also the full-vector pass of the unfused filter (a bandwidth kernel over all owned rows): the chain
+    // depth stops at 8 so that two 256-thread blocks stay resident per SM
+    const bool     deep = p->max_child > 1;
+    const unsigned nb   = nblk((size_t)nr * (B / (vec ? 2 : 1)));
+#define HX_CALL(V_, U_)                                                                                                  \
+  HX_CUDA(launch_pdl(cheb_fused_kernel<V_, U_>, nb, 256, 0, p->stream, s1, xcur, xp, out, binv->d_diag.p, p->d_rowinfo.p, \
+                     p->d_par_off.p, p->d_par_child.p, p->d_par_w.p, binv->d_enr_block.p, p->n_owned_classical,          \
+                     binv->variant == HX_DIAG_CFE ? 0u : binv->nE, nr, B, a, b, xprev ? c : 0.0, rows))
+    if (vec)
+      {
+        if (deep)
+          HX_CALL(2, 8);
+        else
+          HX_CALL(2, 1);
+      }
+    else
+      {
+        if (deep)
+          HX_CALL(1, 8);
+        else
+          HX_CALL(1, 1);
+      }
+#undef HX_CALL
     p->launches++;
     return HX_OK;
   }
