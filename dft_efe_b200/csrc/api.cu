@@ -22,13 +22,13 @@ namespace hx
     va_end(ap);
   }
 
-  // HXB200_PDL=1 switches programmatic dependent launch on for the small kernels of an apply (read per launch so a
-  // test can toggle it)
+  // programmatic dependent launch of the kernels of an apply is on unless HXB200_PDL=0 (read per launch so a test can
+  // toggle it)
   bool
   pdl_enabled()
   {
     const char *e = getenv("HXB200_PDL");
-    return e && e[0] == '1';
+    return !(e && e[0] == '0');
   }
 
   int

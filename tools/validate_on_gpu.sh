@@ -46,6 +46,9 @@ HXB200_PDL=1 timeout 240 compute-sanitizer --tool memcheck --error-exitcode 3 \
 echo "memcheck rc=$?"; tail -4 gpurun_out/memcheck_smoke.log
 lap "memcheck"
 
-HXB200_PDL=1 timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv \
+HXB200_PDL=1 timeout 150 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv \
   --log-file gpurun_out/launches_filter_step.csv python bench.py --steps 2 --warmup 1 --quick > gpurun_out/ncu_bench.log 2>&1
-lap "ncu launch list rc=$?"
+lap "ncu launch list c2 rc=$?"
+HXB200_PDL=1 timeout 120 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv \
+  --log-file gpurun_out/launches_filter_step_c1.csv python bench.py --workload c1 --steps 2 --warmup 1 --quick > gpurun_out/ncu_bench_c1.log 2>&1
+lap "ncu launch list c1 rc=$?"
