@@ -245,6 +245,12 @@ namespace hx
         p->max_child = std::max(p->max_child, (uint32_t)kv.second.size());
       }
     p->nPar = (uint32_t)p->h_par_ids.size();
+    // M^-1 of the fused Chebyshev step reads its input at the row itself, at the constrained children of a parent row and
+    // at the owned enrichment rows: without parents and without constrained enrichment rows no constrained row is read
+    p->cheb_fill_dead = (p->nPar == 0);
+    for (uint32_t i = 0; i < p->nR; ++i)
+      if (m->row_ids[i] >= p->n_owned_classical && m->row_ids[i] < p->n_owned)
+        p->cheb_fill_dead = false;
     p->h_row_ids.assign(m->row_ids, m->row_ids + p->nR);
     HX_TRY(p->d_row_ids.upload(m->row_ids, p->nR));
     HX_TRY(p->d_row_sizes.upload(m->row_sizes, p->nR));
@@ -553,7 +559,7 @@ namespace hx
   // ---------------------------------------------------------------------------------------------
   static int
   cellop_apply(hx_op *op, double *X, double *Y, uint32_t B, int ugx, int ugy, const FuseArgs *fuse = nullptr,
-               bool *fused_applied = nullptr)
+               bool *fused_applied = nullptr, bool y_constrained_rows_dead = false)
   {
     hx_plan *p = op->plan;
     p->mark("apply:begin");
@@ -582,7 +588,9 @@ namespace hx
     HX_TRY(launch_cell_apply(op, X, Y, B, fuse, fused_applied));
     p->mark("cell-kernel");
     HX_TRY(launch_shared_reduce(p, Y, B));
-    HX_TRY(launch_c2p(p, Y, B, op->y_set));
+    // (a caller that never reads the constrained rows of Y - the fused filter's scratch on a single rank, where no halo
+    // accumulation follows - saves their zeroing)
+    HX_TRY(launch_c2p(p, Y, B, op->y_set, !(y_constrained_rows_dead && p->nranks == 1)));
     p->mark("shared+c2p");
     HX_TRY(halo_accumulate(p, p->halo, Y, B));
     if (ugy)
@@ -1460,11 +1468,13 @@ extern "C"
           FuseArgs f;
           f.dinv = BInv->d_diag.p, f.xprev = xp, f.out = out, f.a = ca, f.b = cb, f.c = xp ? cc : 0.0;
           HX_CHECK(xc != s1 && out != xc, HX_ERR_INVALID, "aliasing in the fused Chebyshev step");
-          HX_TRY(cellop_apply(A, xc, s1, B, 1, 0, &f, &applied));
+          // s1 is scratch: its constrained rows are either refilled by the hanging-node fill below or never read
+          HX_TRY(cellop_apply(A, xc, s1, B, 1, 0, &f, &applied, true));
         }
       else
         HX_TRY(op_apply(A, xc, s1, B, 1, 0));
-      HX_TRY(launch_p2c(p, s1, B));
+      if (!p->cheb_fill_dead)
+        HX_TRY(launch_p2c(p, s1, B));
       int r = applied ? launch_cheb_fused(p, BInv, s1, xc, xp, out, B, ca, cb, cc, true, p->d_nonfuse_rows.p, p->n_nonfuse) :
                         launch_cheb_fused(p, BInv, s1, xc, xp, out, B, ca, cb, cc);
       p->mark("cheb-rest");

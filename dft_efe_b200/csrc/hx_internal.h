@@ -318,6 +318,9 @@ struct hx_plan
   // Chebyshev epilogue fusion: owned rows NOT updated inside the cell kernel (row-list pass afterwards)
   uint32_t              n_nonfuse = 0, n_fusable = 0;
   hx::DevBuf<uint32_t>  d_nonfuse_rows;
+  bool                  cheb_fill_dead = false;        // no row of the M^-1 step reads a constrained row of its input
+                                                       // (no parents, no constrained enrichment row): the fused filter
+                                                       // skips the hanging-node fill of its scratch H.X
   bool                  cheb_fusable_multirank = true; // no constrained ghost row has parents (see api.cu)
   bool                  cheb_fusable_agreed    = false; // ... on every rank (AND-ed across the communicator once)
   int                   sm_count = 0;
@@ -405,7 +408,8 @@ namespace hx
 {
   // kernels.cu / cell_kernel.cu entry points (host launchers)
   int launch_p2c(hx_plan *p, double *X, uint32_t B, uint32_t set = 0);
-  int launch_c2p(hx_plan *p, double *Y, uint32_t B, uint32_t set = 0);
+  // zero_rows = false leaves the constrained rows of Y as they are (for a scratch Y whose constrained rows nobody reads)
+  int launch_c2p(hx_plan *p, double *Y, uint32_t B, uint32_t set = 0, bool zero_rows = true);
   int launch_coldot(hx_plan *p, const double *x, const double *y, uint32_t B, size_t nrows, double *out_dev);
   int launch_col_divide(hx_plan *p, const double *num, const double *den, double *out, double *out_neg, uint32_t B);
   int launch_cg_dots2(hx_plan *p, const double *z, const double *r, const double *pd, const double *w, uint32_t B,

@@ -241,7 +241,7 @@ namespace hx
   }
 
   int
-  launch_c2p(hx_plan *p, double *Y, uint32_t B, uint32_t set)
+  launch_c2p(hx_plan *p, double *Y, uint32_t B, uint32_t set, bool zero_rows)
   {
     const ConstraintView c = p->constraint_view(set);
     if (c.nR == 0)
@@ -257,7 +257,7 @@ namespace hx
 #undef HX_CALL
         p->launches++;
       }
-    return launch_zero_constrained(p, Y, B, set);
+    return zero_rows ? launch_zero_constrained(p, Y, B, set) : HX_OK;
   }
 
   // ---- halo pack / unpack / accumulate (src/utils/DiscontiguousDataOperations.cpp:36-92) ------------
@@ -839,6 +839,7 @@ namespace hx
     // this kernel is also the full-vector pass of the unfused filter (a bandwidth kernel over all owned rows): the chain
     // depth stops at 8 so that two 256-thread blocks stay resident per SM
     const bool     deep = p->max_child > 1;
+    const bool     deep16 = use_row_list && p->max_child > 32; // a short row list with long child lists: latency-bound
     const unsigned nb   = nblk((size_t)nr * (B / (vec ? 2 : 1)));
 #define HX_CALL(V_, U_)                                                                                                  \
   HX_CUDA(launch_pdl(cheb_fused_kernel<V_, U_>, nb, 256, 0, p->stream, s1, xcur, xp, out, binv->d_diag.p, p->d_rowinfo.p, \
@@ -846,14 +847,18 @@ namespace hx
                      binv->variant == HX_DIAG_CFE ? 0u : binv->nE, nr, B, a, b, xprev ? c : 0.0, rows))
     if (vec)
       {
-        if (deep)
+        if (deep16)
+          HX_CALL(2, 16);
+        else if (deep)
           HX_CALL(2, 8);
         else
           HX_CALL(2, 1);
       }
     else
       {
-        if (deep)
+        if (deep16)
+          HX_CALL(1, 16);
+        else if (deep)
           HX_CALL(1, 8);
         else
           HX_CALL(1, 1);
