@@ -41,20 +41,34 @@ def main():
             if h in WANT:
                 print(f"  {h:84s} {u:16s} {v}")
     src = page(rep, "source")
-    print("==", src[0][1] if src and len(src[0]) > 1 else "")
-    h = src[1]
-    ix = {x: i for i, x in enumerate(h)}
-    data = src[2:]
-    tot = sum(int(r[ix['# Samples']]) for r in data)
-    print(f"warp-stall samples: {tot}")
-    agg = {s: sum(int(r[ix[s]]) for r in data) for s in STALLS}
-    for s, v in sorted(agg.items(), key=lambda kv: -kv[1]):
-        if v:
-            print(f"  {s:26s} {v:8d}  {100.0 * v / max(tot, 1):5.1f}%")
-    print(f"hottest {nhot} SASS instructions (samples, executed, instruction, stall reasons):")
-    for r in sorted(data, key=lambda r: -int(r[ix['# Samples']]))[:nhot]:
-        st = {s.replace('stall_', ''): int(r[ix[s]]) for s in STALLS if int(r[ix[s]]) > 0}
-        print(f"  {r[ix['# Samples']]:>7s} {r[ix['Instructions Executed']]:>10s}  {r[ix['Source']][:64]:64s} {st}")
+    # the source page holds one block per profiled kernel: a title row, a header row, then one row per instruction
+    blocks, cur, prev = [], None, []
+    for r in src:
+        if '# Samples' in r:
+            cur = {"title": blocks_title, "hdr": r, "rows": []} if (blocks_title := (prev[1] if len(prev) > 1 else "")) is not None else None
+            blocks.append(cur)
+        elif cur is not None and len(r) == len(cur["hdr"]):
+            cur["rows"].append(r)
+        prev = r
+    seen = set()
+    for b in blocks:
+        key = (b["title"], len(b["rows"]))
+        if key in seen:  # ncu repeats the block when the same kernel source serves several results
+            continue
+        seen.add(key)
+        print("==", b["title"])
+        ix = {x: i for i, x in enumerate(b["hdr"])}
+        data = b["rows"]
+        tot = sum(int(r[ix['# Samples']]) for r in data)
+        print(f"warp-stall samples: {tot}")
+        agg = {s: sum(int(r[ix[s]]) for r in data) for s in STALLS if s in ix}
+        for s, v in sorted(agg.items(), key=lambda kv: -kv[1]):
+            if v:
+                print(f"  {s:26s} {v:8d}  {100.0 * v / max(tot, 1):5.1f}%")
+        print(f"hottest {nhot} SASS instructions (samples, executed, instruction, stall reasons):")
+        for r in sorted(data, key=lambda r: -int(r[ix['# Samples']]))[:nhot]:
+            st = {s.replace('stall_', ''): int(r[ix[s]]) for s in STALLS if s in ix and int(r[ix[s]]) > 0}
+            print(f"  {r[ix['# Samples']]:>7s} {r[ix['Instructions Executed']]:>10s}  {r[ix['Source']][:64]:64s} {st}")
 
 
 if __name__ == "__main__":
