@@ -22,13 +22,20 @@ namespace hx
     va_end(ap);
   }
 
-  // programmatic dependent launch of the kernels of an apply is on unless HXB200_PDL=0 (read per launch so a test can
-  // toggle it)
+  // Programmatic dependent launch of the kernels of an apply (read per launch so a test can toggle it): HXB200_PDL=1 /
+  // 0 forces it on / off; unset, it is on for single-rank plans and off once a multi-rank plan exists in the process -
+  // the combination with the spin-waiting peer-memory halo kernels has not been run on N >= 2 GPUs yet, so multi-rank
+  // runs keep the serialised launches they were validated with.
+  static bool g_multirank_plan = false;
   bool
   pdl_enabled()
   {
     const char *e = getenv("HXB200_PDL");
-    return !(e && e[0] == '0');
+    if (e && e[0] == '0')
+      return false;
+    if (e && e[0] == '1')
+      return true;
+    return !g_multirank_plan;
   }
 
   int
@@ -182,6 +189,8 @@ namespace hx
     p->max_block         = m->max_block ? m->max_block : 1;
     HX_CHECK(p->n_owned_classical <= p->n_owned, HX_ERR_INVALID, "n_owned_classical > n_owned");
     HX_CHECK(p->nranks >= 1 && p->rank >= 0 && p->rank < p->nranks, HX_ERR_INVALID, "bad rank/nranks");
+    if (p->nranks > 1)
+      g_multirank_plan = true;
     HX_CHECK(p->n_local < 0x1fffffffu, HX_ERR_INVALID, "too many local rows");
 
     p->h_ncd.assign(m->num_cell_dofs, m->num_cell_dofs + p->C);
@@ -1473,7 +1482,7 @@ extern "C"
         }
       else
         HX_TRY(op_apply(A, xc, s1, B, 1, 0));
-      if (!p->cheb_fill_dead)
+      if (!(p->cheb_fill_dead && p->nranks == 1))
         HX_TRY(launch_p2c(p, s1, B));
       int r = applied ? launch_cheb_fused(p, BInv, s1, xc, xp, out, B, ca, cb, cc, true, p->d_nonfuse_rows.p, p->n_nonfuse) :
                         launch_cheb_fused(p, BInv, s1, xc, xp, out, B, ca, cb, cc);

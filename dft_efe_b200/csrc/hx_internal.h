@@ -51,7 +51,7 @@ namespace hx
     }                     \
   while (0)
 
-  // Programmatic dependent launch (default; HXB200_PDL=0 switches it off): the kernels of one H.X apply / filter degree are launched with
+  // Programmatic dependent launch (default for single-rank plans; HXB200_PDL=0 / 1 forces it off / on): the kernels of one H.X apply / filter degree are launched with
   // cudaLaunchAttributeProgrammaticStreamSerialization, so the launch and block scheduling of kernel k+1 overlap the
   // tail of kernel k.  Every such kernel executes pdl_wait() before its first global-memory access (it returns once
   // the preceding grid has completed and its writes are visible: the stream-order semantics are unchanged) and

@@ -344,8 +344,9 @@ int hx_plan_enable_kernel_timing(hx_plan *plan, int on);
 int hx_plan_trace(hx_plan *plan, int on);
 int hx_plan_trace_report(hx_plan *plan, char *buf, size_t buf_bytes);
 /* 1 when the short kernels of an apply / filter degree are launched with programmatic dependent launch (the launch of
- * kernel k+1 overlaps the tail of kernel k; results are bitwise those of serialised launches).  On by default;
- * environment HXB200_PDL=0 switches it off (read at every launch).  No reference counterpart (the reference launches nothing). */
+ * kernel k+1 overlaps the tail of kernel k; results are bitwise those of serialised launches).  Default: on for
+ * single-rank plans, off once a multi-rank plan exists in the process; environment HXB200_PDL=0 / 1 forces it off / on
+ * (read at every launch).  No reference counterpart (the reference launches nothing). */
 int hx_programmatic_launch_enabled(void);
 /* FP64 DMMA / DFMA / copy microbenchmarks used for the roofline denominators. */
 int hx_microbench(double *dmma_tflops, double *dfma_tflops, double *copy_gbs);
