@@ -163,9 +163,9 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     spec, B = workload_spec(args.workload, 1)
     # bounded sample: each step = one filter call over `cores` partitions of 8^3 cells
+    # W warm-up and exactly K timed steps, as on the GPU arm (a step is 1.5-4 s on 8-64 cores)
     res = cpu_filter_throughput(sample_cells=(8, 8, 8), p=spec.p, B=B, threads=cores, seconds=1e9,
-                                warm=max(1, min(args.warmup, 2)), max_steps=max(1, min(args.steps, 20)),
-                                workload=args.workload)
+                                warm=max(0, args.warmup), max_steps=max(1, args.steps), workload=args.workload)
     line = {"metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
