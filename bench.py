@@ -156,16 +156,118 @@ def cpu_filter_throughput(sample_cells=(10, 10, 10), p=4, B=32, threads=1, secon
             "ms_per_step": dt * 1e3}
 
 
+def _scipy_dgemm_pointer():
+    import ctypes as ct
+    import scipy.linalg.cython_blas as cb
+    cap = cb.__pyx_capi__["dgemm"]
+    ct.pythonapi.PyCapsule_GetName.restype = ct.c_char_p
+    ct.pythonapi.PyCapsule_GetName.argtypes = [ct.py_object]
+    ct.pythonapi.PyCapsule_GetPointer.restype = ct.c_void_p
+    ct.pythonapi.PyCapsule_GetPointer.argtypes = [ct.py_object, ct.c_char_p]
+    return ct.pythonapi.PyCapsule_GetPointer(cap, ct.pythonapi.PyCapsule_GetName(cap))
+
+
+def cpu_filter_throughput_ref(sample_cells=(8, 8, 8), p=4, B=32, threads=1, warm=1, steps=1, degree=DEGREE, workload=None):
+    """The reference's OWN code on the host cores (oracle/_ref = its sources compiled where they lie): its ChebyshevFilter
+    template (linearAlgebra/ChebyshevFilter.t.cpp:39-134) drives KohnShamOperatorContextFE::apply assembled from its
+    compiled gather / gemmStridedVarBatched / scaleStridedVarBatched / scatter-add / constraint routines with the
+    reference's default CELL_BATCH_SIZE = 1 (ksdft/Defaults.cpp:84; ref_hx_apply_serial) - the one piece that cannot be
+    compiled here, the mass-lumped M^-1 apply (deal.II-dependent class), is the oracle port.  dgemm_ is SciPy's OpenBLAS,
+    the stand-in for the MKL/BLIS a site links.  One independent single-rank problem per thread (no halo traffic at all:
+    this favours the reference over an MPI run of the same cells)."""
+    import copy
+    import ctypes as ct
+    from concurrent.futures import ThreadPoolExecutor
+    os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
+    from dft_efe_b200 import synth
+    from oracle import oracle as orc, ref
+    assert ref.available(), "oracle/_ref/libdftefe_ref.so not built"
+    orc.use_scipy_dgemm(True)
+    L = ref.lib()
+    L.ref_set_dgemm.argtypes = [ct.c_void_p]
+    L.ref_set_dgemm(_scipy_dgemm_pointer())
+    if workload == "c1":
+        spec, B = workload_spec("c1", 1)
+        nc, p = spec.ncell, spec.p
+    else:
+        nc = tuple(sample_cells)
+        rng = np.random.default_rng(7)
+        Lbox = np.array(nc) * 0.8
+        atoms = (0.25 + 0.5 * rng.uniform(size=(2, 3))) * Lbox[None, :]
+        spec = synth.MeshSpec(ncell=nc, p=p, h=0.8, atoms=atoms, n_enr_per_atom=4, enr_cutoff=1.28,
+                              n_proj_per_atom=4, proj_cutoff=1.04, nranks=1, boundary="dirichlet")
+    base = synth.build_problem(spec)[0]
+    probs = []
+    for _ in range(threads):  # same cells, private copies of the big arrays (no cache sharing between the "ranks")
+        q = copy.copy(base)
+        q.h_cell = base.h_cell.copy()
+        if getattr(base, "cell_c", None) is not None:
+            q.cell_c = base.cell_c.copy()
+        probs.append(q)
+    worlds = [orc.OracleWorld([q]) for q in probs]
+    X0 = synth.make_block(base, B)
+    a0, a_, b_ = FILTER_BOUNDS
+
+    def make_cb(q, W):
+        def cb(_user, op_id, xp, yp, n_, B_, ugx, ugy):
+            X = np.ctypeslib.as_array(xp, shape=(n_, B_))
+            Y = np.ctypeslib.as_array(yp, shape=(n_, B_))
+            if op_id == 0:
+                ref.hx_apply_serial(q, X, cell_block=1, out=Y)  # the C call releases the GIL; no Python-side copy
+            else:
+                W.minv_apply([X], [Y], bool(ugx), bool(ugy))
+        return ref.APPLY_CB(cb)
+
+    cbs = [make_cb(q, W) for q, W in zip(probs, worlds)]
+
+    def one(i):
+        x, y = X0.copy(), np.zeros_like(X0)
+        L.ref_chebyshev_filter(cbs[i], None, orc._f64(x), orc._f64(y), ct.c_uint32(base.n_local), ct.c_uint32(B),
+                               ct.c_uint32(degree), ct.c_double(a0), ct.c_double(a_), ct.c_double(b_))
+        return float(np.abs(y).max())
+
+    pool = ThreadPoolExecutor(max_workers=threads)
+
+    def step():
+        return list(pool.map(one, range(threads)))
+
+    for _ in range(warm):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        chk = step()
+    dt = (time.perf_counter() - t0) / steps
+    assert all(np.isfinite(chk)), "reference filter produced non-finite values"
+    N = base.n_owned * threads
+    return {"value": degree * N * B / dt / 1e9, "unit": UNIT, "cores": threads, "kind": "reference",
+            "sample": f"ChebyshevFilter degree {degree} through oracle/_ref (the reference's compiled ChebyshevFilter template + "
+                      f"H.X apply assembled from its compiled gather / gemmStridedVarBatched / scatter / constraint routines, "
+                      f"CELL_BATCH_SIZE=1; M^-1 apply = oracle port) on {threads} independent single-rank problem(s) of "
+                      f"{nc[0]}x{nc[1]}x{nc[2]} cells order {p} ({base.n_owned} DoFs each) B={B}, one per thread, {steps} "
+                      f"filter call(s) per problem, dgemm_ = SciPy OpenBLAS",
+            "ms_per_step": dt * 1e3}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
     spec, B = workload_spec(args.workload, 1)
-    # bounded sample: each step = one filter call over `cores` partitions of 8^3 cells
-    # W warm-up and exactly K timed steps, as on the GPU arm (a step is 1.5-4 s on 8-64 cores)
-    res = cpu_filter_throughput(sample_cells=(8, 8, 8), p=spec.p, B=B, threads=cores, seconds=1e9,
-                                warm=max(0, args.warmup), max_steps=max(1, args.steps), workload=args.workload)
+    # bounded sample: each step = one filter call over `cores` problems / partitions of 8^3 cells; W warm-up and exactly
+    # K timed steps, as on the GPU arm (a step is 1.5-4 s on 8-64 cores)
+    res = None
+    try:
+        from oracle import ref as _ref
+        if _ref.available() and not os.environ.get("HXB200_BENCH_REFERENCE_PORT"):
+            res = cpu_filter_throughput_ref(sample_cells=(8, 8, 8), p=spec.p, B=B, threads=cores, warm=max(0, args.warmup),
+                                            steps=max(1, args.steps), workload=args.workload)
+    except Exception as e:  # noqa: BLE001 - the reference-compiled arm must not take the baseline down with it
+        sys.stderr.write(f"[bench] oracle/_ref arm failed ({e}); timing the oracle port instead\n")
+        res = None
+    if res is None:
+        res = cpu_filter_throughput(sample_cells=(8, 8, 8), p=spec.p, B=B, threads=cores, seconds=1e9,
+                                    warm=max(0, args.warmup), max_steps=max(1, args.steps), workload=args.workload)
     line = {"metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",

@@ -127,12 +127,14 @@ def scatter_add(ycell, prob, Y):
     lib().ref_scatter_add(f64(ycell), C.c_uint32(B), ip, np_, C.c_uint32(len(ncd)), f64(Y))
 
 
-def hx_apply_serial(prob, X, cell_block=3, use_nonlocal=True):
+def hx_apply_serial(prob, X, cell_block=3, use_nonlocal=True, out=None):
     """KohnShamOperatorContextFE::apply on one rank assembled from reference-compiled routines only
-    (ref_shim_cellwise.cpp: ref_hx_apply_serial).  X is modified in place like the reference; returns Y."""
+    (ref_shim_cellwise.cpp: ref_hx_apply_serial).  X is modified in place like the reference; returns Y (`out` when
+    given: the routine overwrites it, as the reference's apply does with its Y)."""
     assert prob.nranks == 1
     B = X.shape[1]
-    Y = np.zeros_like(X)
+    Y = np.zeros_like(X) if out is None else out
+    assert Y.shape == X.shape and Y.dtype == np.float64 and Y.flags["C_CONTIGUOUS"]
     ids, ip = u32(prob.cell_local_ids); ncd, ncdp = u32(prob.num_cell_dofs)
     r, rp = u32(prob.row_ids); s, sp = u32(prob.row_sizes); o, op = u32(prob.row_offsets); c, cp = u32(prob.col_ids)
     v = np.ascontiguousarray(prob.col_vals); ih = np.ascontiguousarray(prob.inhom)

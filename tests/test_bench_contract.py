@@ -16,8 +16,7 @@ def run_bench(*argv, env=None):
                           env=e, timeout=600)
 
 
-def test_reference_arm_prints_one_contract_line():
-    r = run_bench("--impl", "reference", "--steps", "2", "--warmup", "1", "--workload", "small")
+def _check_reference_line(r, kind):
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if l.strip()]
     assert len(lines) == 1, lines
@@ -25,11 +24,27 @@ def test_reference_arm_prints_one_contract_line():
     assert d["impl"] == "reference" and d["metric"] == "hx_throughput_fp64" and d["unit"] == "GDoF*vec/s"
     assert d["higher_is_better"] is True and d["dtype"] == "f64" and d["data"] == "synthetic"
     assert d["steps"] == 2 and d["warmup"] == 1 and d["n_gpus"] == 1 and d["vs_baseline"] is None
-    assert "workload" in d["config"] and "2 filter calls" in d["config"]["sample"]
+    assert "workload" in d["config"] and "2 filter call" in d["config"]["sample"]
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] == (os.cpu_count() or 1) and cb["value"] == d["value"] > 0
+    assert cb["kind"] == kind and cb["cores"] == (os.cpu_count() or 1) and cb["value"] == d["value"] > 0
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["gpu_launches"] == 0
+    return d
+
+
+def test_reference_arm_prints_one_contract_line():
+    """With oracle/_ref built (the reference's own sources compiled) the arm times THAT code: kind "reference"."""
+    from oracle import ref
+    r = run_bench("--impl", "reference", "--steps", "2", "--warmup", "1", "--workload", "small")
+    d = _check_reference_line(r, "reference" if ref.available() else "port")
+    if ref.available():
+        assert "oracle/_ref" in d["config"]["sample"] and "CELL_BATCH_SIZE=1" in d["config"]["sample"]
+
+
+def test_reference_arm_falls_back_to_the_oracle_port():
+    r = run_bench("--impl", "reference", "--steps", "2", "--warmup", "1", "--workload", "small",
+                  env={"HXB200_BENCH_REFERENCE_PORT": "1"})
+    _check_reference_line(r, "port")
 
 
 def test_reference_arm_nonzero_ranks_exit_without_work():
