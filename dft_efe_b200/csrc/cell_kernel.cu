@@ -241,7 +241,15 @@ namespace hx
   // =================================================================================================
   // Ordered persistent kernel
   // =================================================================================================
-  template <int NT, int MTW, bool VEC, int MINB, bool FUSE>
+  // PADDR (experiment, HXB200_PRODUCER_ADDR=1, 32-column vectorised kernels only, NOT yet run on a GPU): the producer
+  // warp computes the 64-bit source address of a gathered row once per row, lane-parallel (lane l owns row 32j + l of
+  // the current block of 32 rows), and each copy instruction fetches it with a 64-bit shuffle - about 9 instead of 33
+  // instructions per 16-byte copy instruction.  Why: in the default form the producer warp issues ~320 instructions per
+  // pipeline stage (SASS of <4,2,1,2,1>: 0x5520..0x6900), the same order as the time the DMMA warps take to consume a
+  // stage, and ncu shows those warps waiting on the `full` barrier for 20 % of all samples while DRAM is at 55 %
+  // (DESIGN.md section 11, item 1).  The default instantiations are byte-identical to the kernel validated in round 1:
+  // the experimental loop is a separate `if constexpr` branch.
+  template <int NT, int MTW, bool VEC, int MINB, bool FUSE, bool PADDR = false>
   __global__ void __launch_bounds__(V2_THREADS, MINB) cell_apply_ordered_kernel(const CellArgs a)
   {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -359,52 +367,112 @@ namespace hx
             const uint32_t col   = b0 + (VEC ? cc * 2 : cc);
             const bool     colok = col < a.B;
             const double * srcA  = a.packed + d.h_off;
-            for (int mc = 0; mc < nMt; mc += MPC)
+            if constexpr (PADDR)
               {
-                const int      mtc   = min(MPC, nMt - mc);
-                const uint32_t bytes = (uint32_t)mtc * KC * 256u;
-                // row codes: lane l holds row 32*j + l of the current / next block of 32 rows
-                uint32_t code = row_code(lane), code_next = row_code(32 + lane);
-                for (int kc = 0; kc < nKC; ++kc)
+                static_assert(!PADDR || VEC, "PADDR exists for the vectorised kernels");
+                for (int mc = 0; mc < nMt; mc += MPC)
                   {
-                    constexpr int SPB = 32 / KROWS; // stages per 32-row block
-                    if (kc && (kc % SPB) == 0)
+                    const int      mtc   = min(MPC, nMt - mc);
+                    const uint32_t bytes = (uint32_t)mtc * KC * 256u;
+                    // row codes: lane l holds row 32*j + l of the current / next block of 32 rows
+                    uint32_t code = row_code(lane), code_next = row_code(32 + lane);
+                    // start address of this lane's row (0 = zero row)
+                    auto row_addr = [&](uint32_t c) -> unsigned long long {
+                      if (c == 0xffffffffu)
+                        return 0ull;
+                      return (unsigned long long)((c & 0x80000000u) ? a.VCX + (size_t)(c & 0x7fffffffu) * a.B :
+                                                                      a.X + (size_t)c * a.B);
+                    };
+                    unsigned long long raddr = row_addr(code);
+                    for (int kc = 0; kc < nKC; ++kc)
                       {
-                        code      = code_next;
-                        code_next = row_code((kc / SPB + 1) * 32 + lane);
+                        constexpr int SPB = 32 / KROWS; // stages per 32-row block
+                        if (kc && (kc % SPB) == 0)
+                          {
+                            code      = code_next;
+                            code_next = row_code((kc / SPB + 1) * 32 + lane);
+                            raddr     = row_addr(code);
+                          }
+                        mbar_wait(sbase + SM_EMPTY + 8 * stage, ph ^ 1u);
+                        const uint32_t st_addr = sbase + SM_HEADER + stage * S_BYTES;
+                        const uint32_t full    = sbase + SM_FULL + 8 * stage;
+                        if (lane == 0)
+                          {
+                            mbar_arrive_expect_tx(full, bytes);
+                            if (once)
+                              bulk_g2s_hint(st_addr, srcA, bytes, full, evict_first);
+                            else
+                              bulk_g2s(st_addr, srcA, bytes, full);
+                          }
+                        srcA += bytes / 8;
+                        const uint32_t xs = st_addr + A_BYTES;
+    #pragma unroll
+                        for (int r = 0; r < KROWS; r += RPI)
+                          {
+                            const unsigned long long rp = __shfl_sync(0xffffffffu, raddr, (kc % SPB) * KROWS + r + rr);
+                            const bool               ok = (rp != 0ull) && colok;
+                            const double *           src = ok ? reinterpret_cast<const double *>(rp) + col : a.X;
+                            const uint32_t           dst = xs + ((uint32_t)(r + rr) * LDX + cc * 2) * 8u;
+                            cp_async_zfill16(dst, src, ok ? 16u : 0u);
+                          }
+                        cp_async_mbar_arrive_noinc(full);
+                        if (++stage == NS)
+                          {
+                            stage = 0;
+                            ph ^= 1u;
+                          }
                       }
-                    mbar_wait(sbase + SM_EMPTY + 8 * stage, ph ^ 1u);
-                    const uint32_t st_addr = sbase + SM_HEADER + stage * S_BYTES;
-                    const uint32_t full    = sbase + SM_FULL + 8 * stage;
-                    if (lane == 0)
+                  }
+              }
+            else
+              {
+                for (int mc = 0; mc < nMt; mc += MPC)
+                  {
+                    const int      mtc   = min(MPC, nMt - mc);
+                    const uint32_t bytes = (uint32_t)mtc * KC * 256u;
+                    // row codes: lane l holds row 32*j + l of the current / next block of 32 rows
+                    uint32_t code = row_code(lane), code_next = row_code(32 + lane);
+                    for (int kc = 0; kc < nKC; ++kc)
                       {
-                        mbar_arrive_expect_tx(full, bytes);
-                        if (once)
-                          bulk_g2s_hint(st_addr, srcA, bytes, full, evict_first);
-                        else
-                          bulk_g2s(st_addr, srcA, bytes, full);
-                      }
-                    srcA += bytes / 8;
-                    const uint32_t xs = st_addr + A_BYTES;
-#pragma unroll
-                    for (int r = 0; r < KROWS; r += RPI)
-                      {
-                        const uint32_t c   = __shfl_sync(0xffffffffu, code, (kc % SPB) * KROWS + r + rr);
-                        const bool     ok  = (c != 0xffffffffu) && colok;
-                        const double * src = a.X;
-                        if (ok)
-                          src = ((c & 0x80000000u) ? a.VCX + (size_t)(c & 0x7fffffffu) * a.B : a.X + (size_t)c * a.B) + col;
-                        const uint32_t dst = xs + ((uint32_t)(r + rr) * LDX + (VEC ? cc * 2 : cc)) * 8u;
-                        if (VEC)
-                          cp_async_zfill16(dst, src, ok ? 16u : 0u);
-                        else
-                          cp_async_zfill8(dst, src, ok ? 8u : 0u);
-                      }
-                    cp_async_mbar_arrive_noinc(full);
-                    if (++stage == NS)
-                      {
-                        stage = 0;
-                        ph ^= 1u;
+                        constexpr int SPB = 32 / KROWS; // stages per 32-row block
+                        if (kc && (kc % SPB) == 0)
+                          {
+                            code      = code_next;
+                            code_next = row_code((kc / SPB + 1) * 32 + lane);
+                          }
+                        mbar_wait(sbase + SM_EMPTY + 8 * stage, ph ^ 1u);
+                        const uint32_t st_addr = sbase + SM_HEADER + stage * S_BYTES;
+                        const uint32_t full    = sbase + SM_FULL + 8 * stage;
+                        if (lane == 0)
+                          {
+                            mbar_arrive_expect_tx(full, bytes);
+                            if (once)
+                              bulk_g2s_hint(st_addr, srcA, bytes, full, evict_first);
+                            else
+                              bulk_g2s(st_addr, srcA, bytes, full);
+                          }
+                        srcA += bytes / 8;
+                        const uint32_t xs = st_addr + A_BYTES;
+    #pragma unroll
+                        for (int r = 0; r < KROWS; r += RPI)
+                          {
+                            const uint32_t c   = __shfl_sync(0xffffffffu, code, (kc % SPB) * KROWS + r + rr);
+                            const bool     ok  = (c != 0xffffffffu) && colok;
+                            const double * src = a.X;
+                            if (ok)
+                              src = ((c & 0x80000000u) ? a.VCX + (size_t)(c & 0x7fffffffu) * a.B : a.X + (size_t)c * a.B) + col;
+                            const uint32_t dst = xs + ((uint32_t)(r + rr) * LDX + (VEC ? cc * 2 : cc)) * 8u;
+                            if (VEC)
+                              cp_async_zfill16(dst, src, ok ? 16u : 0u);
+                            else
+                              cp_async_zfill8(dst, src, ok ? 8u : 0u);
+                          }
+                        cp_async_mbar_arrive_noinc(full);
+                        if (++stage == NS)
+                          {
+                            stage = 0;
+                            ph ^= 1u;
+                          }
                       }
                   }
               }
@@ -1184,12 +1252,12 @@ namespace hx
     return HX_OK;
   }
 
-  template <int NT, int MTW, bool VEC, int MINB, bool FUSE>
+  template <int NT, int MTW, bool VEC, int MINB, bool FUSE, bool PADDR = false>
   static int
   launch_ordered(hx_op *op, CellArgs a)
   {
     hx_plan *    p      = op->plan;
-    auto         k      = cell_apply_ordered_kernel<NT, MTW, VEC, MINB, FUSE>;
+    auto         k      = cell_apply_ordered_kernel<NT, MTW, VEC, MINB, FUSE, PADDR>;
     const size_t budget = 225 * 1024 / MINB - 1024; // per CTA (1 KB reserved by the runtime per CTA)
     size_t       ns     = (budget - SM_HEADER) / (size_t)stage_bytes(NT, MTW);
     if (ns > MAX_STAGES)
@@ -1272,9 +1340,15 @@ namespace hx
             if (fused_applied)
               *fused_applied = true;
           }
+        // experimental producer-side addressing (see PADDR above): 32-column tiles, two CTAs per SM
+        const char *pa_env = getenv("HXB200_PRODUCER_ADDR");
+        const bool  paddr  = pa_env && pa_env[0] == '1' && vec && nt == 4 && minb == 2;
 #define HX_ORD(NT_, MTW_, MINB_)                                                                       \
-  (fz ? launch_ordered<NT_, MTW_, true, MINB_, true>(op, a) :                                          \
-        (vec ? launch_ordered<NT_, MTW_, true, MINB_, false>(op, a) : launch_ordered<NT_, MTW_, false, MINB_, false>(op, a)))
+  (fz ? ((paddr && NT_ == 4 && MINB_ == 2) ? launch_ordered<4, MTW_, true, 2, true, true>(op, a) :     \
+                                             launch_ordered<NT_, MTW_, true, MINB_, true>(op, a)) :    \
+        (vec ? ((paddr && NT_ == 4 && MINB_ == 2) ? launch_ordered<4, MTW_, true, 2, false, true>(op, a) : \
+                                                    launch_ordered<NT_, MTW_, true, MINB_, false>(op, a)) : \
+               launch_ordered<NT_, MTW_, false, MINB_, false>(op, a)))
 #define HX_ORD_M(NT_, MTW_) (minb == 2 ? HX_ORD(NT_, MTW_, 2) : HX_ORD(NT_, MTW_, 1))
         if (op->mtw == 1)
           switch (nt)

@@ -415,6 +415,42 @@ def test_programmatic_dependent_launch_is_bitwise_the_serialised_launches(capi, 
         assert np.array_equal(u, res["0"][k % 2]), f"result {k} is not reproducible"
 
 
+@pytest.mark.skipif(__import__("os").environ.get("HXB200_EXPERIMENTS") != "1",
+                    reason="experimental kernel variants (not yet run on a GPU): set HXB200_EXPERIMENTS=1")
+@pytest.mark.parametrize("B", [32, 40, 64])
+@pytest.mark.parametrize("mesh", ["full", "plain"])
+def test_experimental_producer_addressing_is_bitwise_the_default(capi, prob_full, prob_plain, mesh, B):
+    """HXB200_PRODUCER_ADDR=1 (cell_apply_ordered_kernel<..., PADDR>): the gather addresses are computed lane-parallel
+    and shuffled; what is gathered is the same, so apply and fused filter must not change by a bit."""
+    import os
+    p = prob_full if mesh == "full" else prob_plain
+    deg = 6
+    a0, a, b = -3.0, 1.0, 60.0
+    plan = capi.Plan(p, max_block=B)
+    H = capi.CellOp(plan)
+    minv = capi.DiagOp(plan, p.diag_inv, p.enr_block_inv, capi.DIAG_OEFE_ATOMBLOCK)
+    X = synth.make_block(p, B)
+    res = {}
+    try:
+        for mode in ("0", "1"):
+            os.environ["HXB200_PRODUCER_ADDR"] = mode
+            dX, dY = plan.block(B, X), plan.block(B)
+            H.apply(dX, dY, True, False)
+            out = [dY.download()]
+            dX, dY = plan.block(B, X), plan.block(B)
+            capi.chebyshev_filter(H, minv, dX, dY, deg, a0, a, b)
+            out.append(dY.download()[:p.n_owned])
+            res[mode] = out
+    finally:
+        os.environ.pop("HXB200_PRODUCER_ADDR", None)
+    for u, v in zip(res["0"], res["1"]):
+        assert np.array_equal(u, v)
+    W = orc.OracleWorld([p])
+    Xo, Yo = X.copy(), np.zeros_like(X)
+    W.hx_apply([Xo], [Yo], True, False)
+    assert rel_l2_per_vector(res["1"][0], Yo) < RTOL_HX
+
+
 def test_chebyshev_filter_host_entry(capi, prob_full):
     """hx_chebyshev_filter_host (HOST buffers in/out) == the device entry point, bit for bit."""
     p = prob_full
