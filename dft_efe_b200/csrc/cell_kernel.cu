@@ -68,6 +68,7 @@ namespace hx
     double          f_a, f_b, f_c;
     uint32_t        f_discard; // Y tiles are whole 128-B lines (B % 16 == 0, aligned): dead partial sums are discarded
     uint32_t        shared_a;  // many cells stream the same packed matrix (hx_cellop_set_matrix_sharing): keep it in L2
+    const double *  zero_row;  // PROD == 2 only: 32 zero doubles, the source of the rows beyond a cell's K extent
   };
 
   __device__ __forceinline__ void
@@ -241,15 +242,21 @@ namespace hx
   // =================================================================================================
   // Ordered persistent kernel
   // =================================================================================================
-  // PADDR (experiment, HXB200_PRODUCER_ADDR=1, 32-column vectorised kernels only, NOT yet run on a GPU): the producer
-  // warp computes the 64-bit source address of a gathered row once per row, lane-parallel (lane l owns row 32j + l of
-  // the current block of 32 rows), and each copy instruction fetches it with a 64-bit shuffle - about 9 instead of 33
-  // instructions per 16-byte copy instruction.  Why: in the default form the producer warp issues ~320 instructions per
-  // pipeline stage (SASS of <4,2,1,2,1>: 0x5520..0x6900), the same order as the time the DMMA warps take to consume a
-  // stage, and ncu shows those warps waiting on the `full` barrier for 20 % of all samples while DRAM is at 55 %
-  // (DESIGN.md section 11, item 1).  The default instantiations are byte-identical to the kernel validated in round 1:
-  // the experimental loop is a separate `if constexpr` branch.
-  template <int NT, int MTW, bool VEC, int MINB, bool FUSE, bool PADDR = false>
+  // PROD (experiments on the producer warp, HXB200_PRODUCER_ADDR=1 / 2, 32-column vectorised kernels with two CTAs per SM
+  // only, NOT yet run on a GPU; 0 = the validated default).  Why: in the default form the producer warp issues ~320
+  // instructions per pipeline stage (SASS of <4,2,1,2,1>: 0x5520..0x6900; 33 per 16-byte copy instruction), the same
+  // order as the time the DMMA warps take to consume a stage, and ncu shows those warps waiting on the `full` barrier
+  // for 20 % of all samples while DRAM is at 55 %.
+  //   1: the 64-bit source address of a gathered row is computed once per row, lane-parallel (lane l owns row 32j + l
+  //      of the current block of 32 rows), and each copy instruction fetches it with a 64-bit shuffle: 137 instructions
+  //      per stage.
+  //   2: a gathered row of a 32-column tile is 256 contiguous bytes: lanes 0..15 issue ONE cp.async.bulk (TMA) each per
+  //      stage instead of the warp issuing 8 cp.async instructions of 32 x 16 bytes; rows beyond the cell's K extent
+  //      are copied from a zero line; everything completes on the `full` mbarrier through its transaction count (one
+  //      arrival instead of 33).  Columns of the tile beyond B are not written (their accumulators are never stored).
+  // The default instantiations are byte-identical to the kernels validated in round 1: each experiment is a separate
+  // `if constexpr` branch.
+  template <int NT, int MTW, bool VEC, int MINB, bool FUSE, int PROD = 0>
   __global__ void __launch_bounds__(V2_THREADS, MINB) cell_apply_ordered_kernel(const CellArgs a)
   {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -267,7 +274,7 @@ namespace hx
       {
         for (uint32_t s = 0; s < NS; ++s)
           {
-            mbar_init(sbase + SM_FULL + 8 * s, 33); // lane 0's arrive.expect_tx (A) + 32 gather lanes (X)
+            mbar_init(sbase + SM_FULL + 8 * s, PROD == 2 ? 1 : 33); // lane 0's arrive.expect_tx (A) + 32 gather lanes (X)
             mbar_init(sbase + SM_EMPTY + 8 * s, CWARPS);
           }
         for (int b = 0; b < 2; ++b)
@@ -367,9 +374,61 @@ namespace hx
             const uint32_t col   = b0 + (VEC ? cc * 2 : cc);
             const bool     colok = col < a.B;
             const double * srcA  = a.packed + d.h_off;
-            if constexpr (PADDR)
+            if constexpr (PROD == 2)
               {
-                static_assert(!PADDR || VEC, "PADDR exists for the vectorised kernels");
+                static_assert(PROD != 2 || (VEC && KROWS <= 32), "bulk row copies: vectorised kernels");
+                const uint32_t rowbytes = min((uint32_t)BT, a.B - b0) * 8u; // multiple of 16: B even, b0 a multiple of BT
+                for (int mc = 0; mc < nMt; mc += MPC)
+                  {
+                    const int      mtc   = min(MPC, nMt - mc);
+                    const uint32_t bytes = (uint32_t)mtc * KC * 256u;
+                    uint32_t       code = row_code(lane), code_next = row_code(32 + lane);
+                    auto           row_addr = [&](uint32_t c) -> unsigned long long {
+                      if (c == 0xffffffffu)
+                        return 0ull;
+                      return (unsigned long long)((c & 0x80000000u) ? a.VCX + (size_t)(c & 0x7fffffffu) * a.B :
+                                                                      a.X + (size_t)c * a.B);
+                    };
+                    unsigned long long raddr = row_addr(code);
+                    for (int kc = 0; kc < nKC; ++kc)
+                      {
+                        constexpr int SPB = 32 / KROWS; // stages per 32-row block
+                        if (kc && (kc % SPB) == 0)
+                          {
+                            code      = code_next;
+                            code_next = row_code((kc / SPB + 1) * 32 + lane);
+                            raddr     = row_addr(code);
+                          }
+                        mbar_wait(sbase + SM_EMPTY + 8 * stage, ph ^ 1u);
+                        const uint32_t st_addr = sbase + SM_HEADER + stage * S_BYTES;
+                        const uint32_t full    = sbase + SM_FULL + 8 * stage;
+                        if (lane == 0)
+                          {
+                            mbar_arrive_expect_tx(full, bytes + (uint32_t)KROWS * rowbytes);
+                            if (once)
+                              bulk_g2s_hint(st_addr, srcA, bytes, full, evict_first);
+                            else
+                              bulk_g2s(st_addr, srcA, bytes, full);
+                          }
+                        srcA += bytes / 8;
+                        const unsigned long long rp = __shfl_sync(0xffffffffu, raddr, (kc % SPB) * KROWS + (lane % KROWS));
+                        if (lane < KROWS)
+                          {
+                            const double *src = rp ? reinterpret_cast<const double *>(rp) + b0 : a.zero_row;
+                            bulk_g2s(st_addr + A_BYTES + (uint32_t)lane * (LDX * 8u), src, rowbytes, full);
+                          }
+                        __syncwarp();
+                        if (++stage == NS)
+                          {
+                            stage = 0;
+                            ph ^= 1u;
+                          }
+                      }
+                  }
+              }
+            else if constexpr (PROD == 1)
+              {
+                static_assert(PROD != 1 || VEC, "shuffled row addresses: vectorised kernels");
                 for (int mc = 0; mc < nMt; mc += MPC)
                   {
                     const int      mtc   = min(MPC, nMt - mc);
@@ -1252,12 +1311,12 @@ namespace hx
     return HX_OK;
   }
 
-  template <int NT, int MTW, bool VEC, int MINB, bool FUSE, bool PADDR = false>
+  template <int NT, int MTW, bool VEC, int MINB, bool FUSE, int PROD = 0>
   static int
   launch_ordered(hx_op *op, CellArgs a)
   {
     hx_plan *    p      = op->plan;
-    auto         k      = cell_apply_ordered_kernel<NT, MTW, VEC, MINB, FUSE, PADDR>;
+    auto         k      = cell_apply_ordered_kernel<NT, MTW, VEC, MINB, FUSE, PROD>;
     const size_t budget = 225 * 1024 / MINB - 1024; // per CTA (1 KB reserved by the runtime per CTA)
     size_t       ns     = (budget - SM_HEADER) / (size_t)stage_bytes(NT, MTW);
     if (ns > MAX_STAGES)
@@ -1340,14 +1399,25 @@ namespace hx
             if (fused_applied)
               *fused_applied = true;
           }
-        // experimental producer-side addressing (see PADDR above): 32-column tiles, two CTAs per SM
+        // experiments on the producer warp (see PROD above): 32-column tiles, two CTAs per SM
         const char *pa_env = getenv("HXB200_PRODUCER_ADDR");
-        const bool  paddr  = pa_env && pa_env[0] == '1' && vec && nt == 4 && minb == 2;
+        const int   prod   = (pa_env && vec && nt == 4 && minb == 2) ? (pa_env[0] == '1' ? 1 : (pa_env[0] == '2' ? 2 : 0)) : 0;
+        if (prod == 2)
+          {
+            if (!p->d_zero_row.p)
+              {
+                HX_TRY(p->d_zero_row.alloc(32));
+                HX_CUDA(cudaMemsetAsync(p->d_zero_row.p, 0, 32 * sizeof(double), p->stream));
+              }
+            a.zero_row = p->d_zero_row.p;
+          }
+#define HX_ORD_X(MTW_, FUSE_) \
+  (prod == 2 ? launch_ordered<4, MTW_, true, 2, FUSE_, 2>(op, a) : launch_ordered<4, MTW_, true, 2, FUSE_, 1>(op, a))
 #define HX_ORD(NT_, MTW_, MINB_)                                                                       \
-  (fz ? ((paddr && NT_ == 4 && MINB_ == 2) ? launch_ordered<4, MTW_, true, 2, true, true>(op, a) :     \
-                                             launch_ordered<NT_, MTW_, true, MINB_, true>(op, a)) :    \
-        (vec ? ((paddr && NT_ == 4 && MINB_ == 2) ? launch_ordered<4, MTW_, true, 2, false, true>(op, a) : \
-                                                    launch_ordered<NT_, MTW_, true, MINB_, false>(op, a)) : \
+  (fz ? ((prod && NT_ == 4 && MINB_ == 2) ? HX_ORD_X(MTW_, true) :                                     \
+                                            launch_ordered<NT_, MTW_, true, MINB_, true>(op, a)) :     \
+        (vec ? ((prod && NT_ == 4 && MINB_ == 2) ? HX_ORD_X(MTW_, false) :                             \
+                                                   launch_ordered<NT_, MTW_, true, MINB_, false>(op, a)) : \
                launch_ordered<NT_, MTW_, false, MINB_, false>(op, a)))
 #define HX_ORD_M(NT_, MTW_) (minb == 2 ? HX_ORD(NT_, MTW_, 2) : HX_ORD(NT_, MTW_, 1))
         if (op->mtw == 1)
@@ -1371,6 +1441,7 @@ namespace hx
           }
 #undef HX_ORD_M
 #undef HX_ORD
+#undef HX_ORD_X
       }
     while (nt > 1 && xtile_of(nt) > 200 * 1024)
       nt >>= 1;

@@ -312,6 +312,7 @@ struct hx_plan
   hx::DevBuf<uint32_t>  d_order, d_wait_off, d_wait_list;
   hx::DevBuf<uint32_t>  d_flags;    // [C * ceil(max_block/8)] epoch stamps
   hx::DevBuf<uint32_t>  d_counters; // [0] work counter, [1] finished CTAs
+  hx::DevBuf<double>    d_zero_row; // 32 zero doubles (experimental bulk-copy gather of the cell kernel), allocated on use
   uint32_t              epoch = 0;
   uint32_t              n_untouched = 0;
   hx::DevBuf<uint32_t>  d_untouched; // rows no cell writes (zeroed explicitly each apply)

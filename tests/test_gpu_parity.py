@@ -420,8 +420,9 @@ def test_programmatic_dependent_launch_is_bitwise_the_serialised_launches(capi, 
 @pytest.mark.parametrize("B", [32, 40, 64])
 @pytest.mark.parametrize("mesh", ["full", "plain"])
 def test_experimental_producer_addressing_is_bitwise_the_default(capi, prob_full, prob_plain, mesh, B):
-    """HXB200_PRODUCER_ADDR=1 (cell_apply_ordered_kernel<..., PADDR>): the gather addresses are computed lane-parallel
-    and shuffled; what is gathered is the same, so apply and fused filter must not change by a bit."""
+    """HXB200_PRODUCER_ADDR=1 / 2 (cell_apply_ordered_kernel<..., PROD>): 1 = gather addresses computed lane-parallel and
+    shuffled, 2 = one TMA bulk copy per gathered row; what is gathered is the same, so apply and fused filter must not
+    change by a bit."""
     import os
     p = prob_full if mesh == "full" else prob_plain
     deg = 6
@@ -432,7 +433,7 @@ def test_experimental_producer_addressing_is_bitwise_the_default(capi, prob_full
     X = synth.make_block(p, B)
     res = {}
     try:
-        for mode in ("0", "1"):
+        for mode in ("0", "1", "2"):
             os.environ["HXB200_PRODUCER_ADDR"] = mode
             dX, dY = plan.block(B, X), plan.block(B)
             H.apply(dX, dY, True, False)
@@ -443,8 +444,9 @@ def test_experimental_producer_addressing_is_bitwise_the_default(capi, prob_full
             res[mode] = out
     finally:
         os.environ.pop("HXB200_PRODUCER_ADDR", None)
-    for u, v in zip(res["0"], res["1"]):
-        assert np.array_equal(u, v)
+    for mode in ("1", "2"):
+        for u, v in zip(res["0"], res[mode]):
+            assert np.array_equal(u, v), f"producer variant {mode} changes the result"
     W = orc.OracleWorld([p])
     Xo, Yo = X.copy(), np.zeros_like(X)
     W.hx_apply([Xo], [Yo], True, False)
