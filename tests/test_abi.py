@@ -53,3 +53,10 @@ def test_no_cpu_fallback(hxlib):
         capi.Plan(prob, max_block=4)
     with pytest.raises(capi.HxError):
         capi.microbench()
+
+
+def test_every_exported_symbol_is_documented_for_the_integrator(hxlib):
+    """INTEGRATION.md tells a dft-efe maintainer what each entry point replaces: no exported symbol may be missing."""
+    txt = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    missing = [n for n in declared_symbols() if n not in txt]
+    assert not missing, missing
