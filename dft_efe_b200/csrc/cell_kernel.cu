@@ -1420,6 +1420,11 @@ namespace hx
                                                    launch_ordered<NT_, MTW_, true, MINB_, false>(op, a)) : \
                launch_ordered<NT_, MTW_, false, MINB_, false>(op, a)))
 #define HX_ORD_M(NT_, MTW_) (minb == 2 ? HX_ORD(NT_, MTW_, 2) : HX_ORD(NT_, MTW_, 1))
+        // experiment (HXB200_CELL_MINB=3, NOT yet run on a GPU): three CTAs per SM for blocks of at most 8 columns, where an
+        // item is a few hundred DMMAs and its fixed latencies (claim, descriptor, predecessor wait, scatter round trip)
+        // dominate - the C1 shape.  The 8-column kernels need 60-70 registers, so three 320-thread CTAs fit an SM.
+        const char *mb_env = getenv("HXB200_CELL_MINB");
+        const bool  minb3  = mb_env && mb_env[0] == '3' && nt == 1;
         if (op->mtw == 1)
           switch (nt)
             {
@@ -1428,7 +1433,7 @@ namespace hx
               case 2:
                 return HX_ORD_M(2, 1);
               default:
-                return HX_ORD_M(1, 1);
+                return minb3 ? HX_ORD(1, 1, 3) : HX_ORD_M(1, 1);
             }
         switch (nt)
           {
@@ -1437,7 +1442,7 @@ namespace hx
             case 2:
               return HX_ORD_M(2, 2);
             default:
-              return HX_ORD_M(1, 2);
+              return minb3 ? HX_ORD(1, 2, 3) : HX_ORD_M(1, 2);
           }
 #undef HX_ORD_M
 #undef HX_ORD

@@ -453,6 +453,39 @@ def test_experimental_producer_addressing_is_bitwise_the_default(capi, prob_full
     assert rel_l2_per_vector(res["1"][0], Yo) < RTOL_HX
 
 
+@pytest.mark.skipif(__import__("os").environ.get("HXB200_EXPERIMENTS") != "1",
+                    reason="experimental kernel variants (not yet run on a GPU): set HXB200_EXPERIMENTS=1")
+@pytest.mark.parametrize("B", [1, 2, 8])
+@pytest.mark.parametrize("mesh", ["full", "plain"])
+def test_experimental_three_ctas_per_sm_is_bitwise_the_default(capi, prob_full, prob_plain, mesh, B):
+    """HXB200_CELL_MINB=3: the 8-column kernels with three CTAs per SM.  Same items, same order, same arithmetic."""
+    import os
+    p = prob_full if mesh == "full" else prob_plain
+    deg = 6
+    a0, a, b = -3.0, 1.0, 60.0
+    plan = capi.Plan(p, max_block=B)
+    H = capi.CellOp(plan)
+    minv = capi.DiagOp(plan, p.diag_inv, p.enr_block_inv, capi.DIAG_OEFE_ATOMBLOCK)
+    X = synth.make_block(p, B)
+    res = {}
+    try:
+        for mode in ("2", "3"):
+            os.environ["HXB200_CELL_MINB"] = mode
+            out = []
+            for _ in range(3):
+                dX, dY = plan.block(B, X), plan.block(B)
+                H.apply(dX, dY, True, False)
+                out.append(dY.download())
+                dX, dY = plan.block(B, X), plan.block(B)
+                capi.chebyshev_filter(H, minv, dX, dY, deg, a0, a, b)
+                out.append(dY.download()[:p.n_owned])
+            res[mode] = out
+    finally:
+        os.environ.pop("HXB200_CELL_MINB", None)
+    for u, v in zip(res["2"], res["3"]):
+        assert np.array_equal(u, v)
+
+
 def test_chebyshev_filter_host_entry(capi, prob_full):
     """hx_chebyshev_filter_host (HOST buffers in/out) == the device entry point, bit for bit."""
     p = prob_full
