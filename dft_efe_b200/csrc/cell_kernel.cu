@@ -1180,6 +1180,16 @@ namespace hx
     hx_plan *p = op->plan;
     // m-tiles per warp: small cells (n <= 64) keep all 8 DMMA warps busy with one m-tile each
     op->mtw       = (p->max_n <= 64) ? 1 : 2;
+    // experiment (HXB200_CELL_MTW=1 / 2 overrides the choice; not yet run on a GPU for cells above 64 DoFs with one
+    // m-tile per warp): a mesh of 64-DoF cells with a few enriched 65-66-DoF cells (C1) is better served by one m-tile per
+    // warp - all eight DMMA warps busy on the common cell, a second one-tile chunk for the enriched ones
+    if (const char *e = getenv("HXB200_CELL_MTW"))
+      {
+        if (e[0] == '1')
+          op->mtw = 1;
+        else if (e[0] == '2')
+          op->mtw = 2;
+      }
     const int mpc = CWARPS * op->mtw;
     size_t    tot = 0;
     op->h_meta.resize(p->C);

@@ -486,6 +486,34 @@ def test_experimental_three_ctas_per_sm_is_bitwise_the_default(capi, prob_full, 
         assert np.array_equal(u, v)
 
 
+@pytest.mark.skipif(__import__("os").environ.get("HXB200_EXPERIMENTS") != "1",
+                    reason="experimental kernel variants (not yet run on a GPU): set HXB200_EXPERIMENTS=1")
+@pytest.mark.parametrize("B", [3, 8, 32])
+def test_experimental_one_m_tile_per_warp_for_enriched_small_cells(capi, prob_full, B):
+    """HXB200_CELL_MTW=1 on a mesh whose enriched cells exceed 64 DoFs (order 3 + enrichment: 64..67 DoFs per cell): the
+    layout choice only regroups m-tiles into chunks, every output row keeps its k order, so the result must not change by
+    a bit against the default two-m-tiles-per-warp layout - and must match the oracle."""
+    import os
+    p = prob_full
+    assert p.num_cell_dofs.max() > 64 and p.num_cell_dofs.min() <= 64
+    X = synth.make_block(p, B)
+    res = {}
+    try:
+        for mode in ("2", "1"):
+            os.environ["HXB200_CELL_MTW"] = mode   # read when the cell matrices are packed
+            plan = capi.Plan(p, max_block=B)
+            H = capi.CellOp(plan)
+            dX, dY = plan.block(B, X), plan.block(B)
+            H.apply(dX, dY, True, False)
+            res[mode] = dY.download()
+    finally:
+        os.environ.pop("HXB200_CELL_MTW", None)
+    assert np.array_equal(res["1"], res["2"])
+    Xo, Yo = X.copy(), np.zeros_like(X)
+    orc.OracleWorld([p]).hx_apply([Xo], [Yo], True, False)
+    assert rel_l2_per_vector(res["1"], Yo) < RTOL_HX
+
+
 def test_chebyshev_filter_host_entry(capi, prob_full):
     """hx_chebyshev_filter_host (HOST buffers in/out) == the device entry point, bit for bit."""
     p = prob_full
