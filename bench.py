@@ -51,6 +51,18 @@ def workload_spec(name: str, nranks: int):
         # into nranks z-slabs (strong scaling; 31 GB of cell matrices in total, meant for 4 or 8 GPUs)
         nc, p, B, h = (32, 32, 32), 6, 128, 0.8
         n_atoms = 24
+    elif name == "c2a":
+        # C2 on an ADAPTIVE mesh (dft-efe meshes are refined around the atoms): 24^3 cells of which the ones within 2.5 h
+        # of an atom are split 2:1 -> ~15.9 k cells, ~1.0 M DoFs, ~30 k hanging-node rows, parents with a few hundred
+        # children.  Exercises the constraint kernels and the row-list recurrence at the size of C2.
+        nc, p, B, h = (24, 24, 24 * nranks), 4, 32, 0.8
+        rng = np.random.default_rng(7)
+        L = np.array(nc) * h
+        atoms = (0.25 + 0.5 * rng.uniform(size=(5 * nranks, 3))) * L[None, :]
+        spec = synth.MeshSpec(ncell=nc, p=p, h=h, refine_mask=synth.refine_ball(nc, h, atoms, 2.5 * h), atoms=atoms,
+                              n_enr_per_atom=4, enr_cutoff=1.6 * h, n_proj_per_atom=4, proj_cutoff=1.3 * h, nranks=nranks,
+                              boundary="dirichlet")
+        return spec, B
     elif name == "c1":
         # BASELINE configs[0]: H2 all-electron classical EFE on a small adaptive mesh, block of 8 wavefunctions (the
         # reference's own CPU-runnable test/ksdft case: 15^3 cells refined around the two nuclei, FE order 3, one
@@ -637,7 +649,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c2", "small", "c3", "c1"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "small", "c3", "c1", "c2a"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--quick", action="store_true",
                     help="only the step, its phase trace, the bare apply and e2e (skips the subspace / ChFSI pass / SCF-neighbour / "
