@@ -89,11 +89,17 @@ namespace hx
             accumulate(cur[u], val[u]);
       }
   }
-  // chain depth by the longest chain of the data (known at plan creation): short chains keep the register count low
+  // Chain depth by the longest chain of the data (known at plan creation) and by the size of the launch.  Depth 16 costs
+  // 130-190 registers, i.e. ONE 256-thread block per SM: worth it only while the whole launch is a wave or two (the C1
+  // mesh: 1352 parents, 18.7 k row-list rows at 8 columns); a large launch (an adaptive mesh of C2's size: 1.8 M
+  // row-list threads, 46 waves at one block per SM) is better off with depth 8 and two to three blocks per SM.
   static inline int
-  chain_depth(uint32_t longest)
+  chain_depth(uint32_t longest, size_t threads, int sm_count)
   {
-    return longest <= 1 ? 1 : (longest <= 32 ? 8 : 16);
+    if (longest <= 1)
+      return 1;
+    const size_t two_waves = (size_t)2 * 256 * (size_t)(sm_count > 0 ? sm_count : 148);
+    return (longest > 32 && threads <= two_waves) ? 16 : 8;
   }
   struct WeightedRow
   {
@@ -209,8 +215,9 @@ namespace hx
     if (c.nR == 0)
       return HX_OK;
     const bool vec = (B % 2 == 0) && aligned16(X);
-    const int  dep = chain_depth(c.max_row);
-    const unsigned nb = nblk((size_t)c.nR * (B / (vec ? 2 : 1)));
+    const size_t nthr = (size_t)c.nR * (B / (vec ? 2 : 1));
+    const int  dep = chain_depth(c.max_row, nthr, p->sm_count);
+    const unsigned nb = nblk(nthr);
 #define HX_CALL(V_, U_)                                                                                               \
   HX_CUDA(launch_pdl(p2c_kernel<V_, U_>, nb, 256, 0, p->stream, X, B, c.nR, c.row_ids, c.row_sizes, c.row_offsets, \
                      c.col_ids, c.col_vals, c.inhom))
@@ -249,8 +256,9 @@ namespace hx
     if (c.nPar)
       {
         const bool     vec = (B % 2 == 0) && aligned16(Y);
-        const int      dep = chain_depth(c.max_child);
-        const unsigned nb  = nblk((size_t)c.nPar * (B / (vec ? 2 : 1)));
+        const size_t   nthr = (size_t)c.nPar * (B / (vec ? 2 : 1));
+        const int      dep  = chain_depth(c.max_child, nthr, p->sm_count);
+        const unsigned nb   = nblk(nthr);
 #define HX_CALL(V_, U_) \
   HX_CUDA(launch_pdl(c2p_kernel<V_, U_>, nb, 256, 0, p->stream, Y, B, c.nPar, c.par_ids, c.par_off, c.par_child, c.par_w))
         HX_VEC_DEPTH_DISPATCH(vec, dep, HX_CALL);
@@ -838,9 +846,11 @@ namespace hx
     const bool     vec = (B % 2 == 0) && aligned16(s1, xcur, xp, out);
     // this kernel is also the full-vector pass of the unfused filter (a bandwidth kernel over all owned rows): the chain
     // depth stops at 8 so that two 256-thread blocks stay resident per SM
+    const size_t   nthr = (size_t)nr * (B / (vec ? 2 : 1));
     const bool     deep = p->max_child > 1;
-    const bool     deep16 = use_row_list && p->max_child > 32; // a short row list with long child lists: latency-bound
-    const unsigned nb   = nblk((size_t)nr * (B / (vec ? 2 : 1)));
+    // a short row list with long child lists is latency-bound: depth 16; anything longer than two waves keeps depth 8
+    const bool     deep16 = use_row_list && chain_depth(p->max_child, nthr, p->sm_count) == 16;
+    const unsigned nb   = nblk(nthr);
 #define HX_CALL(V_, U_)                                                                                                  \
   HX_CUDA(launch_pdl(cheb_fused_kernel<V_, U_>, nb, 256, 0, p->stream, s1, xcur, xp, out, binv->d_diag.p, p->d_rowinfo.p, \
                      p->d_par_off.p, p->d_par_child.p, p->d_par_w.p, binv->d_enr_block.p, p->n_owned_classical,          \
