@@ -529,6 +529,18 @@ namespace hx
           }
         p->n_nonfuse = (uint32_t)nonfuse.size();
         HX_TRY(p->d_nonfuse_rows.upload(nonfuse));
+        {
+          std::vector<uint32_t> split;
+          split.reserve(nonfuse.size());
+          for (uint32_t r : nonfuse)
+            if (rowinfo[r] >= 0xFFFFFFFEu) // free row without children, or constrained row
+              split.push_back(r);
+          p->n_nonfuse_plain = (uint32_t)split.size();
+          for (uint32_t r : nonfuse)
+            if (rowinfo[r] < 0xFFFFFFFEu) // parent row: index into the parent-side CSR
+              split.push_back(r);
+          HX_TRY(p->d_nonfuse_split.upload(split));
+        }
         // the fused M^-1 skips the ghost update between its row scaling and its child->parent pass: exact unless a
         // constrained GHOST row has parents (its scaled value would come from the owner)
         p->cheb_fusable_multirank = true;
@@ -1484,8 +1496,20 @@ extern "C"
         HX_TRY(op_apply(A, xc, s1, B, 1, 0));
       if (!(p->cheb_fill_dead && p->nranks == 1))
         HX_TRY(launch_p2c(p, s1, B));
-      int r = applied ? launch_cheb_fused(p, BInv, s1, xc, xp, out, B, ca, cb, cc, true, p->d_nonfuse_rows.p, p->n_nonfuse) :
-                        launch_cheb_fused(p, BInv, s1, xc, xp, out, B, ca, cb, cc);
+      int r;
+      const char *split_env = getenv("HXB200_SPLIT_ROWLIST");
+      if (applied && split_env && split_env[0] == '1' && p->n_nonfuse_plain < p->n_nonfuse)
+        {
+          // experiment (not yet run on a GPU): the rows without a child list in one launch (no chain, 40 registers), the
+          // parent rows in a second one that alone pays for the deep-chain variant.  Same kernels, same per-row work.
+          r = launch_cheb_fused(p, BInv, s1, xc, xp, out, B, ca, cb, cc, true, p->d_nonfuse_split.p, p->n_nonfuse_plain, 1);
+          if (r == HX_OK)
+            r = launch_cheb_fused(p, BInv, s1, xc, xp, out, B, ca, cb, cc, true, p->d_nonfuse_split.p + p->n_nonfuse_plain,
+                                  p->n_nonfuse - p->n_nonfuse_plain);
+        }
+      else
+        r = applied ? launch_cheb_fused(p, BInv, s1, xc, xp, out, B, ca, cb, cc, true, p->d_nonfuse_rows.p, p->n_nonfuse) :
+                      launch_cheb_fused(p, BInv, s1, xc, xp, out, B, ca, cb, cc);
       p->mark("cheb-rest");
       return r;
     };

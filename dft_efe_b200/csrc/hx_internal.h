@@ -319,6 +319,10 @@ struct hx_plan
   // Chebyshev epilogue fusion: owned rows NOT updated inside the cell kernel (row-list pass afterwards)
   uint32_t              n_nonfuse = 0, n_fusable = 0;
   hx::DevBuf<uint32_t>  d_nonfuse_rows;
+  // the same rows split by kind (experiment HXB200_SPLIT_ROWLIST=1): [0, n_nonfuse_plain) rows without a child list,
+  // then the parent rows - so that only the parents pay for the deep-chain kernel variant
+  uint32_t              n_nonfuse_plain = 0;
+  hx::DevBuf<uint32_t>  d_nonfuse_split;
   bool                  cheb_fill_dead = false;        // no row of the M^-1 step reads a constrained row of its input
                                                        // (no parents, no constrained enrichment row): the fused filter
                                                        // skips the hanging-node fill of its scratch H.X
@@ -436,9 +440,10 @@ namespace hx
   int launch_nl_phase_a(hx_op *op, const double *X, uint32_t B);
   int pack_cell_matrices(hx_op *op, const double *raw_dev_or_host, int on_device); // raw == nullptr: structure only
   // use_row_list false: all owned rows; true: only the n_rows listed rows
+  // force_depth: 0 = by the plan's longest child list and the launch size, 1 = the rows are known to have no child list
   int launch_cheb_fused(hx_plan *p, hx_op *binv, const double *s1, const double *xcur, const double *xprev,
                         double *out, uint32_t B, double a, double b, double c, bool use_row_list = false,
-                        const uint32_t *rows = nullptr, uint32_t n_rows = 0);
+                        const uint32_t *rows = nullptr, uint32_t n_rows = 0, int force_depth = 0);
   int gram_block(hx_plan *p, const double *X, uint32_t B, uint32_t j0, const double *OpXb, uint32_t b,
                  size_t nOwned, double *S_dev);
   int rotate(hx_plan *p, double *X, uint32_t B, size_t nOwned, const double *Q_dev, int transpose, int lowerTri,

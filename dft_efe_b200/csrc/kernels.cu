@@ -834,7 +834,8 @@ namespace hx
 {
   int
   launch_cheb_fused(hx_plan *p, hx_op *binv, const double *s1, const double *xcur, const double *xprev, double *out,
-                    uint32_t B, double a, double b, double c, bool use_row_list, const uint32_t *rows, uint32_t n_rows)
+                    uint32_t B, double a, double b, double c, bool use_row_list, const uint32_t *rows, uint32_t n_rows,
+                    int force_depth)
   {
     if (!use_row_list)
       rows = nullptr;
@@ -847,9 +848,9 @@ namespace hx
     // this kernel is also the full-vector pass of the unfused filter (a bandwidth kernel over all owned rows): the chain
     // depth stops at 8 so that two 256-thread blocks stay resident per SM
     const size_t   nthr = (size_t)nr * (B / (vec ? 2 : 1));
-    const bool     deep = p->max_child > 1;
+    const bool     deep = p->max_child > 1 && force_depth != 1;
     // a short row list with long child lists is latency-bound: depth 16; anything longer than two waves keeps depth 8
-    const bool     deep16 = use_row_list && chain_depth(p->max_child, nthr, p->sm_count) == 16;
+    const bool     deep16 = deep && use_row_list && chain_depth(p->max_child, nthr, p->sm_count) == 16;
     const unsigned nb   = nblk(nthr);
 #define HX_CALL(V_, U_)                                                                                                  \
   HX_CUDA(launch_pdl(cheb_fused_kernel<V_, U_>, nb, 256, 0, p->stream, s1, xcur, xp, out, binv->d_diag.p, p->d_rowinfo.p, \

@@ -514,6 +514,32 @@ def test_experimental_one_m_tile_per_warp_for_enriched_small_cells(capi, prob_fu
     assert rel_l2_per_vector(res["1"], Yo) < RTOL_HX
 
 
+@pytest.mark.skipif(__import__("os").environ.get("HXB200_EXPERIMENTS") != "1",
+                    reason="experimental kernel variants (not yet run on a GPU): set HXB200_EXPERIMENTS=1")
+@pytest.mark.parametrize("B", [2, 8, 32])
+def test_experimental_split_row_list_is_bitwise_the_default(capi, prob_full, B):
+    """HXB200_SPLIT_ROWLIST=1: the row-list pass of the fused filter as two launches (rows without a child list, parent
+    rows).  Same kernels, same work per row."""
+    import os
+    p = prob_full
+    deg = 7
+    a0, a, b = -3.0, 1.0, 60.0
+    plan = capi.Plan(p, max_block=B)
+    H = capi.CellOp(plan)
+    minv = capi.DiagOp(plan, p.diag_inv, p.enr_block_inv, capi.DIAG_OEFE_ATOMBLOCK)
+    X = synth.make_block(p, B)
+    res = {}
+    try:
+        for mode in ("0", "1"):
+            os.environ["HXB200_SPLIT_ROWLIST"] = mode
+            dX, dY = plan.block(B, X), plan.block(B)
+            capi.chebyshev_filter(H, minv, dX, dY, deg, a0, a, b)
+            res[mode] = dY.download()[:p.n_owned]
+    finally:
+        os.environ.pop("HXB200_SPLIT_ROWLIST", None)
+    assert np.array_equal(res["0"], res["1"])
+
+
 def test_chebyshev_filter_host_entry(capi, prob_full):
     """hx_chebyshev_filter_host (HOST buffers in/out) == the device entry point, bit for bit."""
     p = prob_full
