@@ -754,3 +754,21 @@ def test_properties_at_bench_scale(capi):
         d8, dh8 = plan.block(8, np.ascontiguousarray(X[:, j0:j0 + 8])), plan.block(8)
         H.apply(d8, dh8)
         assert rel_l2_per_vector(dh8.download(), HX[:, j0:j0 + 8]) < 1e-13
+
+
+def test_chebyshev_filter_against_reference_golden_fixture(capi):
+    """tests/golden/ref_filter_small.npz = the reference's own compiled ChebyshevFilter template driving
+    KohnShamOperatorContextFE::apply assembled from its compiled routines (tests/golden/make_golden.py): the CUDA filter
+    (epilogue-fused recurrence, dependent launches and all) must match it within the filter tolerance."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_filter_small.npz"))
+    p = synth.build_problem(spec_full(p=int(g["p"]), nc=tuple(int(v) for v in g["nc"])))[0]
+    B = int(g["B"])
+    a0, a, b = (float(v) for v in g["bounds"])
+    plan = capi.Plan(p, max_block=B)
+    H = capi.CellOp(plan)
+    minv = capi.DiagOp(plan, p.diag_inv, p.enr_block_inv, capi.DIAG_OEFE_ATOMBLOCK)
+    dX, dY = plan.block(B, np.ascontiguousarray(g["X"])), plan.block(B)
+    capi.chebyshev_filter(H, minv, dX, dY, int(g["degree"]), a0, a, b)
+    assert rel_l2_per_vector(dY.download()[:p.n_owned], g["F"]) < 1e-11
+

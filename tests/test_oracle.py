@@ -174,6 +174,19 @@ def test_hx_golden_fixture_from_reference_assembled_apply(probs):
     assert err.max() < 1e-14, err
 
 
+def test_filter_golden_fixture_from_reference_chebyshev_filter(probs):
+    """tests/golden/ref_filter_small.npz = the reference's own compiled ChebyshevFilter template over the
+    reference-assembled apply (tests/golden/make_golden.py): the oracle's filter must reproduce it."""
+    g = np.load(os.path.join(HERE, "golden", "ref_filter_small.npz"))
+    p = synth.build_problem(small_spec(1, p=int(g["p"]), nc=tuple(int(v) for v in g["nc"])))[0]
+    X = synth.make_block(p, int(g["B"]))
+    assert np.array_equal(X, g["X"])
+    a0, a, b = (float(v) for v in g["bounds"])
+    F = orc.OracleWorld([p]).chebyshev_filter([X.copy()], int(g["degree"]), a0, a, b)[0][:p.n_owned]
+    err = np.linalg.norm(F - g["F"], axis=0) / np.linalg.norm(g["F"], axis=0)
+    assert err.max() < 1e-13, err
+
+
 def _poisson_setup(p, B, seed=5):
     """right-hand side with zero constrained rows and an initial guess (ghost rows arbitrary)"""
     rng = np.random.default_rng(seed)
