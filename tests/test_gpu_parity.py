@@ -772,3 +772,28 @@ def test_chebyshev_filter_against_reference_golden_fixture(capi):
     capi.chebyshev_filter(H, minv, dX, dY, int(g["degree"]), a0, a, b)
     assert rel_l2_per_vector(dY.download()[:p.n_owned], g["F"]) < 1e-11
 
+
+@pytest.mark.skipif(__import__("os").environ.get("HXB200_EXPERIMENTS") != "1",
+                    reason="written without GPU access at the end of round 1: run once with HXB200_EXPERIMENTS=1, then un-gate")
+@pytest.mark.parametrize("B", [1, 4, 32])
+def test_hx_and_filter_periodic_wrap(capi, B):
+    """BASELINE configs[3] is periodic: the wrap as one-entry constraint rows (slave -> master, weight 1; corner masters
+    with 7 slaves), cf. tests/test_oracle.py::test_periodic_wrap_constraints."""
+    p = synth.build_problem(spec_full(p=3, nc=(4, 4, 4), refine=False, enr=2, proj=2, boundary="periodic"))[0]
+    plan = capi.Plan(p, max_block=B)
+    H = capi.CellOp(plan)
+    W = orc.OracleWorld([p])
+    X = synth.make_block(p, B)
+    dX, dY = plan.block(B, X), plan.block(B)
+    H.apply(dX, dY, True, False)
+    Xo, Yo = X.copy(), np.zeros_like(X)
+    W.hx_apply([Xo], [Yo], True, False)
+    assert rel_l2_per_vector(dY.download(), Yo) < RTOL_HX
+    assert rel_l2_per_vector(dX.download(), Xo) < 1e-14
+    assert np.all(dY.download()[p.row_ids.astype(np.int64)] == 0.0)
+    minv = capi.DiagOp(plan, p.diag_inv, p.enr_block_inv, capi.DIAG_OEFE_ATOMBLOCK)
+    dX, dY = plan.block(B, X), plan.block(B)
+    capi.chebyshev_filter(H, minv, dX, dY, 7, -3.0, 1.0, 60.0)
+    F = W.chebyshev_filter([X.copy()], 7, -3.0, 1.0, 60.0)[0]
+    assert rel_l2_per_vector(dY.download()[:p.n_owned], F[:p.n_owned]) < 1e-11
+

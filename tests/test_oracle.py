@@ -187,6 +187,44 @@ def test_filter_golden_fixture_from_reference_chebyshev_filter(probs):
     assert err.max() < 1e-13, err
 
 
+def test_periodic_wrap_constraints(ref_lib):
+    """BASELINE configs[3] is periodic; the reference has no periodic support, so the wrap is expressed the
+    way its constraint machinery would carry it: one-entry rows (slave -> master, weight 1; a corner master has 7
+    slaves).  The oracle's apply equals the reference-assembled apply on such constraints, is independent of the
+    partitioning and symmetric; a periodic function is reproduced on the slave rows by the hanging-node fill."""
+    kw = dict(p=3, nc=(4, 4, 4), refine=False, enr=2, proj=2, boundary="periodic")
+    B = 4
+    nat = {}
+    for n in (1, 2, 4):
+        ps = synth.build_problem(small_spec(n, **kw))
+        assert all(int(q.row_sizes.max()) == 1 for q in ps)
+        Xs = [synth.make_block(q, B) for q in ps]
+        Ys = [np.zeros_like(x) for x in Xs]
+        orc.OracleWorld(ps).hx_apply(Xs, Ys, True, False)
+        nat[n] = to_natural(ps, Ys)
+    for n in (2, 4):
+        assert np.abs(nat[n] - nat[1]).max() <= 1e-14 * np.abs(nat[1]).max()
+    p = synth.build_problem(small_spec(1, **kw))[0]
+    assert np.bincount(p.col_ids.astype(np.int64)).max() == 7
+    X = synth.make_block(p, B)
+    Yr = ref_lib.hx_apply_serial(p, X.copy(), cell_block=1)
+    W = orc.OracleWorld([p])
+    Xo, Yo = X.copy(), np.zeros_like(X)
+    W.hx_apply([Xo], [Yo], True, False)
+    assert np.abs(Yo - Yr).max() <= 1e-14 * np.abs(Yr).max()
+    rows = p.row_ids.astype(np.int64)
+    assert np.array_equal(Xo[rows], Xo[p.col_ids.astype(np.int64)[p.row_offsets.astype(np.int64)]])  # slave = master
+    assert np.all(Yo[rows] == 0.0)
+    Z = synth.make_block(p, B) * 0.7 + 0.1
+    Zo, HZ = Z.copy(), np.zeros_like(Z)
+    W.hx_apply([Zo], [HZ], True, False)
+    free = np.ones(p.n_local, bool)
+    free[rows] = False
+    a = np.einsum("ij,ij->j", Yo[free], Zo[free])
+    b = np.einsum("ij,ij->j", Xo[free], HZ[free])
+    assert np.abs(a - b).max() <= 1e-12 * np.abs(a).max()
+
+
 def _poisson_setup(p, B, seed=5):
     """right-hand side with zero constrained rows and an initial guess (ghost rows arbitrary)"""
     rng = np.random.default_rng(seed)
