@@ -529,18 +529,6 @@ namespace hx
           }
         p->n_nonfuse = (uint32_t)nonfuse.size();
         HX_TRY(p->d_nonfuse_rows.upload(nonfuse));
-        {
-          std::vector<uint32_t> split;
-          split.reserve(nonfuse.size());
-          for (uint32_t r : nonfuse)
-            if (rowinfo[r] >= 0xFFFFFFFEu) // free row without children, or constrained row
-              split.push_back(r);
-          p->n_nonfuse_plain = (uint32_t)split.size();
-          for (uint32_t r : nonfuse)
-            if (rowinfo[r] < 0xFFFFFFFEu) // parent row: index into the parent-side CSR
-              split.push_back(r);
-          HX_TRY(p->d_nonfuse_split.upload(split));
-        }
         // the fused M^-1 skips the ghost update between its row scaling and its child->parent pass: exact unless a
         // constrained GHOST row has parents (its scaled value would come from the owner)
         p->cheb_fusable_multirank = true;
@@ -1441,6 +1429,28 @@ extern "C"
   }
 
   // ------------------------------------------------------------------------------- filters ----
+  // experiment HXB200_SPLIT_ROWLIST=1 (built on first use, so that plan creation is untouched): the rows of the fused
+  // filter's row list reordered as [rows without a child list | parent rows]
+  static int
+  build_split_row_list(hx_plan *p)
+  {
+    if (p->d_nonfuse_split.p || p->n_nonfuse == 0)
+      return HX_OK;
+    std::vector<uint32_t> rows(p->n_nonfuse), info(p->n_local), split;
+    HX_CUDA(cudaStreamSynchronize(p->stream));
+    HX_CUDA(cudaMemcpy(rows.data(), p->d_nonfuse_rows.p, rows.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    HX_CUDA(cudaMemcpy(info.data(), p->d_rowinfo.p, info.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    split.reserve(rows.size());
+    for (uint32_t r : rows)
+      if (info[r] >= 0xFFFFFFFEu) // free row without children, or constrained row
+        split.push_back(r);
+    p->n_nonfuse_plain = (uint32_t)split.size();
+    for (uint32_t r : rows)
+      if (info[r] < 0xFFFFFFFEu) // parent row: index into the parent-side CSR
+        split.push_back(r);
+    return p->d_nonfuse_split.upload(split);
+  }
+
   int
   hx_chebyshev_filter(hx_op *A, hx_op *BInv, double *X, double *Y, uint32_t B, uint32_t degree, double a0, double a,
                       double b)
@@ -1498,7 +1508,10 @@ extern "C"
         HX_TRY(launch_p2c(p, s1, B));
       int r;
       const char *split_env = getenv("HXB200_SPLIT_ROWLIST");
-      if (applied && split_env && split_env[0] == '1' && p->n_nonfuse_plain < p->n_nonfuse)
+      const bool  split    = applied && split_env && split_env[0] == '1';
+      if (split)
+        HX_TRY(build_split_row_list(p));
+      if (split && p->d_nonfuse_split.p && p->n_nonfuse_plain < p->n_nonfuse)
         {
           // experiment (not yet run on a GPU): the rows without a child list in one launch (no chain, 40 registers), the
           // parent rows in a second one that alone pays for the deep-chain variant.  Same kernels, same per-row work.
