@@ -386,6 +386,7 @@ def run_ours(args):
         ms_per_step = timed(step, args.steps)
         launches = plan.launch_count() - l0
         cell_ms, cell_launches = plan.cell_kernel_time_ms()
+        cell_clock_mhz = plan.cell_kernel_sm_clock_mhz()
         plan.enable_kernel_timing(False)
 
         # ---- phase breakdown of one filter call (untimed pass with CUDA events at the phase boundaries) ----
@@ -611,6 +612,7 @@ def run_ours(args):
                                    "update of %d of %d owned rows is applied in its scatter epilogue)" % (n_fus, n_fus + n_other),
                          "algorithmic_bytes_bare_apply": alg_apply,
                          "kernel_ms_per_launch": cell_ms_per_launch, "kernel_launches_timed": int(cell_launches),
+                         "kernel_sm_clock_mhz": round(cell_clock_mhz, 1),
                          "kernel_share_of_step": cell_ms / args.steps / ms_per_step,
                          "algorithmic_bytes_per_launch": alg_bytes, "flops_per_launch": flops,
                          "tensor": {"achieved_tflops": flops / (cell_ms_per_launch * 1e-3) / 1e12,

@@ -26,7 +26,7 @@ EXPORTS = [
     "hx_distribute_child_to_parent_set", "hx_cellop_set_constraint_sets", "hx_cg_solve", "hx_cellop_create", "hx_cellop_set_matrices", "hx_cellop_set_nonlocal",
     "hx_diagop_create", "hx_op_destroy", "hx_op_apply", "hx_op_apply_host", "hx_chebyshev_filter", "hx_chebyshev_filter_host",
     "hx_residual_chebyshev_filter", "hx_xtopx", "hx_subspace_rotation", "hx_l2_norms", "hx_axpby",
-    "hx_axpby_blocked", "hx_plan_launch_count", "hx_plan_cell_kernel_time_ms", "hx_plan_enable_kernel_timing", "hx_plan_trace", "hx_plan_trace_report",
+    "hx_axpby_blocked", "hx_plan_launch_count", "hx_plan_cell_kernel_time_ms", "hx_plan_cell_kernel_sm_clock_mhz", "hx_plan_enable_kernel_timing", "hx_plan_trace", "hx_plan_trace_report",
     "hx_microbench", "hx_programmatic_launch_enabled",
     "hx_xtopx_device", "hx_subspace_rotation_device", "hx_dense_cholesky_inverse", "hx_dense_sym_eig",
     "hx_cholesky_gram_schmidt", "hx_rayleigh_ritz", "hx_chfsi_solve", "hx_eigen_residual_norms", "hx_lanczos_extreme",
@@ -304,6 +304,11 @@ class Plan:
         n = C.c_uint64()
         check(lib().hx_plan_cell_kernel_time_ms(self.h, C.byref(ms), C.byref(n)))
         return ms.value, n.value
+
+    def cell_kernel_sm_clock_mhz(self) -> float:
+        mhz = C.c_double()
+        check(lib().hx_plan_cell_kernel_sm_clock_mhz(self.h, C.byref(mhz)))
+        return mhz.value
 
 
 class Op:

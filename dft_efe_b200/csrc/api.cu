@@ -550,6 +550,8 @@ namespace hx
       HX_CUDA(cudaMemset(p->d_flags.p, 0, nflags * sizeof(uint32_t)));
       HX_TRY(p->d_counters.alloc(2));
       HX_CUDA(cudaMemset(p->d_counters.p, 0, 2 * sizeof(uint32_t)));
+      HX_TRY(p->d_clk.alloc(2));
+      HX_CUDA(cudaMemset(p->d_clk.p, 0, 2 * sizeof(unsigned long long)));
       p->epoch = 0;
       int dev = 0;
       HX_CUDA(cudaGetDevice(&dev));
@@ -1429,8 +1431,7 @@ extern "C"
   }
 
   // ------------------------------------------------------------------------------- filters ----
-  // experiment HXB200_SPLIT_ROWLIST=1 (built on first use, so that plan creation is untouched): the rows of the fused
-  // filter's row list reordered as [rows without a child list | parent rows]
+  // the rows of the fused filter's row list reordered as [rows without a child list | parent rows] (built on first use)
   static int
   build_split_row_list(hx_plan *p)
   {
@@ -1458,6 +1459,7 @@ extern "C"
     HX_CHECK(A && BInv && X && Y, HX_ERR_INVALID, "null argument");
     HX_CHECK(A->plan == BInv->plan, HX_ERR_INVALID, "operators belong to different plans");
     HX_CHECK(degree >= 1, HX_ERR_INVALID, "polynomial degree must be >= 1");
+    HX_CHECK(X != Y, HX_ERR_INVALID, "X and Y must not alias (the recurrence ping-pongs between them)");
     hx_plan *p = A->plan;
     HX_CHECK_B(p, B);
     // ChebyshevFilter.t.cpp:62-70
@@ -1508,13 +1510,13 @@ extern "C"
         HX_TRY(launch_p2c(p, s1, B));
       int r;
       const char *split_env = getenv("HXB200_SPLIT_ROWLIST");
-      const bool  split    = applied && split_env && split_env[0] == '1';
+      const bool  split    = applied && !(split_env && split_env[0] == '0');
       if (split)
         HX_TRY(build_split_row_list(p));
       if (split && p->d_nonfuse_split.p && p->n_nonfuse_plain < p->n_nonfuse)
         {
-          // experiment (not yet run on a GPU): the rows without a child list in one launch (no chain, 40 registers), the
-          // parent rows in a second one that alone pays for the deep-chain variant.  Same kernels, same per-row work.
+          // the rows without a child list in one launch (no chain, 40 registers), the parent rows in a second one that
+          // alone pays for the deep-chain variant.  Same kernels, same per-row work (HXB200_SPLIT_ROWLIST=0: one launch).
           r = launch_cheb_fused(p, BInv, s1, xc, xp, out, B, ca, cb, cc, true, p->d_nonfuse_split.p, p->n_nonfuse_plain, 1);
           if (r == HX_OK)
             r = launch_cheb_fused(p, BInv, s1, xc, xp, out, B, ca, cb, cc, true, p->d_nonfuse_split.p + p->n_nonfuse_plain,
@@ -1581,6 +1583,7 @@ extern "C"
     HX_CHECK(A && Bop && BInv && eigenvalues && X && Y, HX_ERR_INVALID, "null argument");
     hx_plan *p = A->plan;
     HX_CHECK(p == Bop->plan && p == BInv->plan, HX_ERR_INVALID, "operators belong to different plans");
+    HX_CHECK(X != Y, HX_ERR_INVALID, "X and Y must not alias (the recurrence ping-pongs between them)");
     HX_CHECK_B(p, B);
     const double e      = 0.5 * (b - a);
     const double c      = 0.5 * (b + a);
@@ -1817,6 +1820,18 @@ extern "C"
     *ms                 = tot;
     *launches           = plan->cell_launches;
     plan->cell_launches = 0;
+    return HX_OK;
+  }
+
+  int
+  hx_plan_cell_kernel_sm_clock_mhz(hx_plan *plan, double *mhz)
+  {
+    HX_CHECK(plan && mhz, HX_ERR_INVALID, "null argument");
+    HX_CUDA(cudaStreamSynchronize(plan->stream));
+    unsigned long long c[2] = {0, 0};
+    HX_CUDA(cudaMemcpy(c, plan->d_clk.p, sizeof(c), cudaMemcpyDeviceToHost));
+    HX_CUDA(cudaMemset(plan->d_clk.p, 0, sizeof(c)));
+    *mhz = c[1] ? 1e3 * (double)c[0] / (double)c[1] : 0.0;
     return HX_OK;
   }
 }

@@ -99,7 +99,7 @@ namespace hx
   template <bool PACKED>
   __global__ void __launch_bounds__(256, 4)
   fe_matrices_kernel(const hx_fe_basis::Cell *cells, const double *basis, const double *w, const double *add_to, double *out,
-                     uint32_t tilesPerCell, const CellMeta *meta, int mpc)
+                     uint32_t tilesPerCell, const CellMeta *meta, int mpc, int KCv)
   {
     __shared__ __align__(16) double As[2][FKC * FLD];
     __shared__ __align__(16) double Bs[2][FKC * FLD];
@@ -194,14 +194,14 @@ namespace hx
       {
         const CellMeta cm = meta[blockIdx.x / tilesPerCell];
         o                 = out + cm.h_off;
-        nKC               = ((int)cm.n + (int)cm.nproj + 4 * KC - 1) / (4 * KC);
+        nKC               = ((int)cm.n + (int)cm.nproj + 4 * KCv - 1) / (4 * KCv);
         nMt               = ((int)cm.n + 7) >> 3;
-        per_chunk         = (size_t)mpc * nKC * KC * 32;
+        per_chunk         = (size_t)mpc * nKC * KCv * 32;
       }
     auto pidx = [&](uint32_t r, uint32_t c) -> size_t {
       const int mt = (int)(r >> 3), ch = mt / mpc, mc = ch * mpc, mtc = min(mpc, nMt - mc), mtl = mt - mc;
-      const int kc = (int)(c >> 4), ks = (int)((c >> 2) & 3);
-      return (size_t)ch * per_chunk + (size_t)kc * mtc * KC * 32 + (size_t)(mtl * KC + ks) * 32 + (r & 7) * 4 + (c & 3);
+      const int kc = (int)(c >> 2) / KCv, ks = (int)(c >> 2) % KCv;
+      return (size_t)ch * per_chunk + (size_t)kc * mtc * KCv * 32 + (size_t)(mtl * KCv + ks) * 32 + (r & 7) * 4 + (c & 3);
     };
 #pragma unroll
     for (int j = 0; j < 2; ++j)
@@ -516,10 +516,10 @@ extern "C"
     if (packed_op)
       fe_matrices_kernel<true><<<b->C * tiles, 256, 0, p->stream>>>(b->d_cells.p, b->d_basis.p, b->d_w.p, add_to_dev,
                                                                    packed_op->d_packed.p, tiles, packed_op->d_meta.p,
-                                                                   CWARPS * packed_op->mtw);
+                                                                   CWARPS * packed_op->mtw, packed_op->kc);
     else
       fe_matrices_kernel<false><<<b->C * tiles, 256, 0, p->stream>>>(b->d_cells.p, b->d_basis.p, b->d_w.p, add_to_dev,
-                                                                    cell_matrices_dev, tiles, nullptr, 0);
+                                                                    cell_matrices_dev, tiles, nullptr, 0, 4);
     p->mark("fe-matrices");
     p->launches += 2;
     HX_CUDA(cudaGetLastError());

@@ -15,9 +15,12 @@
 //     linear stream of "stages"; stage (chunk, kc) holds, for the <= 8*MTW m-tiles of the chunk and KC k-steps, the
 //     32-double DMMA A-fragments.  One cp.async.bulk (TMA, 1-D) per stage moves it into a shared-memory ring
 //     guarded by full/empty mbarriers; compute warps read their fragments with conflict-free 256-B LDS.
-//   * Persistent CTAs (grid = SMs x CTAs/SM), warp-specialised: 8 DMMA warps, 1 A-stream warp (claims work
-//     items from a global counter and issues the bulk copies, running ahead across items), 1 gather warp
-//     (cp.async 16-B zero-filling gathers of the cell's rows of X / VCX into a padded shared tile).
+//   * Persistent CTAs (two per SM), warp-specialised into four warpgroups whose register budgets are re-split with
+//     setmaxnreg: 4 DMMA warps (k loop only), 8 scatter warps (everything with global-memory latency), one A-stream
+//     warp (claims work items from a global counter and issues the bulk copies, running ahead across items) and one
+//     gather warp (cp.async 16-B zero-filling gathers of the cell's rows of X / VCX into a padded shared tile).  The
+//     accumulators of a finished m-chunk change hands through a swizzled shared-memory tile, so the DMMA warps never
+//     wait for a global load (cell_apply_pipe_kernel below).
 //   * Deterministic scatter without colour launches: work items are claimed in processing order; a cell adds
 //     its rows into Y only after the immediately preceding toucher of each row has published an epoch stamp
 //     (release/acquire through L2).  Per row the summation order is therefore ascending cell order - the
@@ -32,9 +35,7 @@
 
 namespace hx
 {
-  // KC (k-steps of 4 per stage) and CWARPS (DMMA warps) live in hx_internal.h: they define the packed layout
-  constexpr int CTHREADS      = CWARPS * 32;
-  constexpr int V2_THREADS    = CTHREADS + 64;   // + A-stream warp + gather warp
+  // CWARPS (m-tiles of a chunk / mtw) lives in hx_internal.h; with op->kc (k-steps of 4 per stage) it defines the packed layout
   constexpr int QD            = 16;              // item queue depth (A-stream warp -> gather / DMMA warps)
   constexpr int MAX_STAGES    = 8;
   constexpr uint32_t ITEM_END = 0xffffffffu;
@@ -66,9 +67,11 @@ namespace hx
     const double *  f_xprev;
     double *        f_out;
     double          f_a, f_b, f_c;
+    uint32_t        f_has_c;   // c != 0 (the first degree has no Xprev term)
     uint32_t        f_discard; // Y tiles are whole 128-B lines (B % 16 == 0, aligned): dead partial sums are discarded
     uint32_t        shared_a;  // many cells stream the same packed matrix (hx_cellop_set_matrix_sharing): keep it in L2
-    const double *  zero_row;  // PROD == 2 only: 32 zero doubles, the source of the rows beyond a cell's K extent
+    unsigned long long *clk;   // [4 x nSamples ring]: clock64 / globaltimer at the start and end of CTA 0 (SM clock under load)
+    uint32_t        kc;        // k-steps per stage of the packed stream (layout parameter, see pack_kernel)
   };
 
   __device__ __forceinline__ void
@@ -114,12 +117,12 @@ namespace hx
     asm volatile("{\n"
                  ".reg .pred p;\n"
                  "WAIT_%=:\n"
-                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
                  "@p bra DONE_%=;\n"
                  "bra WAIT_%=;\n"
                  "DONE_%=:\n"
                  "}" ::"r"(bar),
-                 "r"(parity)
+                 "r"(parity), "r"(0x989680u) // suspend-time hint: the warp sleeps in hardware until the phase completes
                  : "memory");
   }
   __device__ __forceinline__ void
@@ -176,248 +179,206 @@ namespace hx
   {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
   }
-  __device__ __forceinline__ void
-  bar_compute()
-  {
-    asm volatile("bar.sync 1, %0;" ::"n"(CTHREADS) : "memory");
-  }
-
   // offset (doubles, relative to the cell's packed base) of stage (chunk starting at m-tile mc, k-chunk kc)
   __device__ __host__ __forceinline__ size_t
-  stage_offset(int mc, int mtc, int kc, int nKC)
+  stage_offset(int mc, int mtc, int kc, int nKC, int kcv)
   {
-    return ((size_t)mc * nKC + (size_t)mtc * kc) * (KC * 32);
+    return ((size_t)mc * nKC + (size_t)mtc * kc) * (kcv * 32);
   }
 
-  // shared-memory header of the ordered kernel (bytes from the dynamic smem base, 128-B aligned)
-  constexpr int SM_FULL   = 0;               // MAX_STAGES x 8
-  constexpr int SM_EMPTY  = 64;              // MAX_STAGES x 8
-  constexpr int SM_PRED   = 128;             // 2 x 8: predecessors of item (it & 1) have scattered
-  constexpr int SM_DONE   = 144;             // 2 x 8: all DMMA warps have scattered item (it & 1)
-  constexpr int SM_Q      = 256;             // QD x 32: item queue, producer warp -> DMMA warps + sync warp
-  constexpr int SM_HEADER = SM_Q + QD * 32;  // 768
+  // =================================================================================================
+  // Pipelined ordered kernel (default): the contraction and the scatter of a work item run in DIFFERENT warps.
+  // =================================================================================================
+  // In the round-1 kernel the DMMA warps also performed the scatter epilogue of every item - destination codes,
+  // the wait for the predecessors, Y / X / Xprev loads, stores - four serialised memory round trips per item during
+  // which the CTA feeds no DMMA (ncu: tensor pipe 65 % active).  Here a CTA (two per SM) has four roles in four
+  // warpgroups, with the register file re-split between them by setmaxnreg:
+  //   * warps 0-3, DMMA: k loop only, 4 m-tiles x 4 n-tiles per warp (16 independent accumulators; 128 bytes of
+  //     shared-memory fragments per DMMA instead of 192 with 2 m-tiles).  At the end of an m-chunk they park the
+  //     accumulators in a shared-memory tile (swizzled, conflict-free for both sides) and start the next chunk / item.
+  //   * warps 4-11, scatter: everything with global-memory latency.  Per chunk, threads 0-127 own one row each
+  //     (destination code -> record {byte offset, flags}, dinv, L2 prefetch of Xprev) and threads 128-255 one
+  //     predecessor each (ld.acquire.gpu on its stamp); all of that index data is requested one chunk ahead.  Then the
+  //     256 threads read-modify-write the rows (16 bytes of a row per thread, straight-line predicated code over the
+  //     records), and thread 0 publishes the item's stamp (st.release.gpu).
+  //   * warp 12, A stream: claims items from the global counter (two ahead), fetches their descriptors, queues them
+  //     for the other roles and issues one cp.async.bulk (TMA) per pipeline stage.
+  //   * warp 13, gather: zero-filling cp.async of the stage's rows of X (or of V C^H X) into the padded B tile; the
+  //     64-bit source address of a row is computed once, lane-parallel, and fetched with a shuffle.
+  //   (warps 14-15 only complete the fourth warpgroup: they give their registers away and exit.)
+  // Ordering / determinism: exactly the scheme above (one chain per row in processing order, first toucher stores,
+  // last toucher of a fusable row applies the recurrence), so results are bit-identical to it.
+  // Memory-model chain of a stamp: scatter threads st.cg -> bar.sync(scatter warps) -> thread 0 st.release.gpu;
+  // consumer: scatter threads ld.acquire.gpu -> bar.sync -> ld.cg.
+  constexpr int DWARPS       = 4;                // DMMA warps: 4 (or 2) m-tiles x 4 n-tiles each, 16 independent accumulators
+  constexpr int DTHREADS     = DWARPS * 32;
+  constexpr int SWARPS       = 8;
+  constexpr int STHREADS     = SWARPS * 32;
+  constexpr int SROWS        = 128;              // rows of the largest chunk (16 m-tiles)
+  constexpr int PIPE_THREADS = (DWARPS + SWARPS + 4) * 32; // 512: launched with 64 registers per thread
+  constexpr int REG_DMMA     = 144;              // 128 x 144 + 256 x 40 + 128 x 32 = 512 x 64
+  constexpr int REG_SCATTER  = 40;
+  constexpr int REG_PRODUCER = 32;
+  constexpr int SMP_FULL     = 0;                // MAX_STAGES x 8
+  constexpr int SMP_EMPTY    = 64;               // MAX_STAGES x 8
+  constexpr int SMP_ACCFULL  = 128;              // (+16 per tile) accumulators of a chunk are in the shared tile
+  constexpr int SMP_ACCFREE  = 136;              // (+16 per tile) the scatter warps have read them
+  constexpr int SMP_Q        = 256;              // QD x 32 item queue
+  constexpr int SMP_REC      = SMP_Q + QD * 32;  // 2 x SROWS x (16 + 8): row records {byte offset, flags} + dinv, current / next chunk
+  constexpr int SMP_HEADER   = SMP_REC + 2 * SROWS * 24; // 6912
 
-  // queue entry: what the DMMA warps and the sync warp need to know about a work item
-  struct ItemInfo
+  __host__ __device__ constexpr int
+  pipe_stage_bytes(int nt, int mtw, int kc)
   {
-    uint32_t tag; // item index + 1; 0 = slot empty; ITEM_END = no more work
-    uint32_t ids_off, n, nproj, wait_off, nwait;
+    return CWARPS * mtw * kc * 256 + 4 * kc * (nt * 8 + 4) * 8;
+  }
+  __host__ __device__ constexpr int
+  pipe_acc_bytes(int nt, int mtw)
+  {
+    return CWARPS * mtw * 8 * nt * 8 * 8;
+  }
+  __device__ __forceinline__ void
+  bar_scatter()
+  {
+    asm volatile("bar.sync 1, %0;" ::"n"(STHREADS) : "memory");
+  }
+  template <int R>
+  __device__ __forceinline__ void
+  reg_inc()
+  {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R));
+  }
+  template <int R>
+  __device__ __forceinline__ void
+  reg_dec()
+  {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R));
+  }
+  // queue entry of the pipelined kernel: 8 words
+  struct PItem
+  {
+    uint32_t tag, ids_off, n, nproj, wait_off, nwait, proj_off;
   };
   __device__ __forceinline__ void
-  item_store(uint32_t addr, const ItemInfo &it)
-  {
-    asm volatile("st.volatile.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr + 16), "r"(it.wait_off), "r"(it.nwait),
-                 "r"(0u), "r"(0u)
-                 : "memory");
-    asm volatile("st.volatile.shared.v2.u32 [%0], {%1,%2};" ::"r"(addr + 8), "r"(it.n), "r"(it.nproj) : "memory");
-    st_volatile_shared(addr + 4, it.ids_off);
-    __threadfence_block();
-    st_volatile_shared(addr, it.tag);
-  }
-  __device__ __forceinline__ void
-  item_load_payload(uint32_t addr, ItemInfo &it)
+  pitem_load(uint32_t addr, PItem &it)
   {
     __threadfence_block();
-    uint32_t d0, d1;
-    it.ids_off = ld_volatile_shared(addr + 4);
-    asm volatile("ld.volatile.shared.v2.u32 {%0,%1}, [%2];" : "=r"(it.n), "=r"(it.nproj) : "r"(addr + 8) : "memory");
+    uint32_t pad;
     asm volatile("ld.volatile.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(it.wait_off), "=r"(it.nwait), "=r"(d0), "=r"(d1)
+                 : "=r"(pad), "=r"(it.ids_off), "=r"(it.n), "=r"(it.nproj)
+                 : "r"(addr)
+                 : "memory");
+    asm volatile("ld.volatile.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(it.wait_off), "=r"(it.nwait), "=r"(it.proj_off), "=r"(pad)
                  : "r"(addr + 16)
                  : "memory");
   }
 
-  // bytes of one pipeline stage: the A fragments of one (m-chunk, k-chunk) + the 4*KC gathered rows of X
-  __host__ __device__ constexpr int
-  stage_a_bytes(int mtw)
-  {
-    return CWARPS * mtw * KC * 256;
-  }
-  __host__ __device__ constexpr int
-  stage_bytes(int nt, int mtw)
-  {
-    return stage_a_bytes(mtw) + 4 * KC * (nt * 8 + 4) * 8;
-  }
-
-  // =================================================================================================
-  // Ordered persistent kernel
-  // =================================================================================================
-  // PROD (experiments on the producer warp, HXB200_PRODUCER_ADDR=1 / 2, 32-column vectorised kernels with two CTAs per SM
-  // only, NOT yet run on a GPU; 0 = the validated default).  Why: in the default form the producer warp issues ~320
-  // instructions per pipeline stage (SASS of <4,2,1,2,1>: 0x5520..0x6900; 33 per 16-byte copy instruction), the same
-  // order as the time the DMMA warps take to consume a stage, and ncu shows those warps waiting on the `full` barrier
-  // for 20 % of all samples while DRAM is at 55 %.
-  //   1: the 64-bit source address of a gathered row is computed once per row, lane-parallel (lane l owns row 32j + l
-  //      of the current block of 32 rows), and each copy instruction fetches it with a 64-bit shuffle: 137 instructions
-  //      per stage.
-  //   2: a gathered row of a 32-column tile is 256 contiguous bytes: lanes 0..15 issue ONE cp.async.bulk (TMA) each per
-  //      stage instead of the warp issuing 8 cp.async instructions of 32 x 16 bytes; rows beyond the cell's K extent
-  //      are copied from a zero line; everything completes on the `full` mbarrier through its transaction count (one
-  //      arrival instead of 33).  Columns of the tile beyond B are not written (their accumulators are never stored).
-  // The default instantiations are byte-identical to the kernels validated in round 1: each experiment is a separate
-  // `if constexpr` branch.
-  template <int NT, int MTW, bool VEC, int MINB, bool FUSE, int PROD = 0>
-  __global__ void __launch_bounds__(V2_THREADS, MINB) cell_apply_ordered_kernel(const CellArgs a)
+  template <int NT, int MTW, int KCT, bool VEC, int MINB, bool FUSE, int RB, int NACC = 1, int REGD = REG_DMMA, int REGS = REG_SCATTER>
+  __global__ void __launch_bounds__(PIPE_THREADS, MINB) cell_apply_pipe_kernel(const CellArgs a)
   {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int  BT      = NT * 8;
     constexpr int  LDX     = BT + 4;
-    constexpr int  MPC     = CWARPS * MTW; // m-tiles per chunk
-    constexpr int  KROWS   = 4 * KC;       // rows of X per stage
-    constexpr int  A_BYTES = stage_a_bytes(MTW);
-    constexpr int  S_BYTES = stage_bytes(NT, MTW);
+    constexpr int  MPC     = CWARPS * MTW; // m-tiles per chunk (the packed layout's)
+    constexpr int  MPW     = MPC / DWARPS; // m-tiles per DMMA warp
+    constexpr int  KROWS   = 4 * KCT;      // rows of X per stage
+    constexpr int  A_BYTES = CWARPS * MTW * KCT * 256;
+    constexpr int  S_BYTES = pipe_stage_bytes(NT, MTW, KCT);
+    constexpr int  ACC_B   = pipe_acc_bytes(NT, MTW);
+    constexpr int  ROW_B   = BT * 8; // bytes of one row of the accumulator tile
     const int      tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t sbase = smem_u32(smem_raw);
+    const uint32_t accb  = sbase + SMP_HEADER;
+    const uint32_t stgb  = accb + NACC * ACC_B;
     const uint32_t NS    = a.nStages;
 
     if (tid == 0)
       {
         for (uint32_t s = 0; s < NS; ++s)
           {
-            mbar_init(sbase + SM_FULL + 8 * s, PROD == 2 ? 1 : 33); // lane 0's arrive.expect_tx (A) + 32 gather lanes (X)
-            mbar_init(sbase + SM_EMPTY + 8 * s, CWARPS);
+            mbar_init(sbase + SMP_FULL + 8 * s, 33); // the A warp's arrive.expect_tx + 32 gather lanes (X)
+            mbar_init(sbase + SMP_EMPTY + 8 * s, DWARPS);
           }
-        for (int b = 0; b < 2; ++b)
+        for (int b = 0; b < NACC; ++b)
           {
-            mbar_init(sbase + SM_PRED + 8 * b, 1);
-            mbar_init(sbase + SM_DONE + 8 * b, CWARPS);
+            mbar_init(sbase + SMP_ACCFULL + 16 * b, DWARPS);
+            mbar_init(sbase + SMP_ACCFREE + 16 * b, SWARPS);
           }
         for (int q = 0; q < QD; ++q)
-          st_volatile_shared(sbase + SM_Q + 32 * q, 0u);
+          st_volatile_shared(sbase + SMP_Q + 32 * q, 0u);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
       }
-    // programmatic dependent launch: the barrier setup above overlaps the tail of the preceding kernel; nothing in
-    // global memory is touched before the preceding grid has completed
     pdl_wait();
     pdl_launch();
     __syncthreads();
 
-    if (warp == CWARPS)
+    if (warp >= DWARPS + SWARPS)
       {
-        // ---------------- producer warp: claims items, streams A (TMA bulk), gathers X (cp.async) ----------------
-        constexpr int CPR = VEC ? BT / 2 : BT; // copies per row (<= 32)
-        constexpr int RPI = 32 / CPR;          // rows per warp instruction
-        const int     cc  = lane % CPR;
-        const int     rr  = lane / CPR;
-        uint32_t      stage = 0, ph = 0;
-        // a cell matrix is read once per apply when one column tile covers B: keep it from evicting
-        // the X / Y lines that neighbouring cells are about to reuse
-        uint64_t evict_first;
-        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(evict_first));
-        const bool once = (a.nBt == 1) && !a.shared_a;
-        // claims run two items ahead, descriptors one item ahead (all lanes hold the same values)
-        auto claim = [&]() -> uint32_t {
-          uint32_t v = 0;
-          if (lane == 0)
-            v = atomicAdd(a.counters, 1u);
-          return __shfl_sync(0xffffffffu, v, 0);
-        };
-        auto fetch = [&](uint32_t w_) -> ItemDesc {
-          ItemDesc d;
-          d.n = 0;
-          if (w_ < a.nItems)
-            {
-              const uint4 *q  = reinterpret_cast<const uint4 *>(a.items + w_ / a.nBt);
-              const uint4  lo = __ldg(q), hi = __ldg(q + 1);
-              d.h_off    = ((unsigned long long)lo.y << 32) | lo.x;
-              d.ids_off  = lo.z;
-              d.n        = lo.w;
-              d.nproj    = hi.x;
-              d.proj_off = hi.y;
-              d.wait_off = hi.z;
-              d.nwait    = hi.w;
-            }
-          return d;
-        };
-        uint32_t w_cur  = claim();
-        ItemDesc d_cur  = fetch(w_cur);
-        uint32_t w_next = claim();
-        for (uint32_t it = 0;; ++it)
+        reg_dec<REG_PRODUCER>();
+        if (warp == DWARPS + SWARPS)
           {
-            const uint32_t slot = sbase + SM_Q + 32 * (it % QD);
-            if (lane == 0)
-              while (ld_volatile_shared(slot) != 0u)
+            // ---------------- A-stream warp (one lane): claims, descriptors, queue, one bulk copy per stage ----------------
+            if (lane != 0)
+              return;
+            uint32_t stage = 0, ph = 0;
+            uint64_t evict_first;
+            asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(evict_first));
+            const bool once  = (a.nBt == 1) && !a.shared_a;
+            auto       fetch = [&](uint32_t w_, uint4 &lo, uint4 &hi) {
+              lo = hi = make_uint4(0u, 0u, 0u, 0u);
+              if (w_ < a.nItems)
                 {
+                  const uint4 *q = reinterpret_cast<const uint4 *>(a.items + w_ / a.nBt);
+                  lo = __ldg(q), hi = __ldg(q + 1);
                 }
-            __syncwarp();
-            if (w_cur >= a.nItems)
-              {
-                if (lane == 0)
-                  st_volatile_shared(slot, ITEM_END);
-                break;
-              }
-            const ItemDesc d = d_cur;
-            const uint32_t w = w_cur;
-            if (lane == 0)
-              {
-                ItemInfo info;
-                info.tag = w + 1u, info.ids_off = d.ids_off, info.n = d.n, info.nproj = d.nproj;
-                info.wait_off = d.wait_off, info.nwait = d.nwait;
-                item_store(slot, info);
-              }
-            // prefetch: next descriptor (its index was claimed one item ago), and one more claim
-            w_cur  = w_next;
-            d_cur  = fetch(w_cur);
-            w_next = claim();
-
-            const int n = (int)d.n, ktot = n + (int)d.nproj;
-            auto      row_code = [&](int k) -> uint32_t {
-              if (k >= ktot)
-                return 0xffffffffu; // zero row
-              if (k < n)
-                return __ldg(a.ids + d.ids_off + k);
-              return 0x80000000u | __ldg(a.pids + d.proj_off + (k - n));
             };
-            const uint32_t b0    = (w % a.nBt) * BT;
-            const int      nKC   = (ktot + KROWS - 1) / KROWS;
-            const int      nMt   = (n + 7) >> 3;
-            const uint32_t col   = b0 + (VEC ? cc * 2 : cc);
-            const bool     colok = col < a.B;
-            const double * srcA  = a.packed + d.h_off;
-            if constexpr (PROD == 2)
+            uint32_t w_cur = atomicAdd(a.counters, 1u);
+            uint4    lo_cur, hi_cur;
+            fetch(w_cur, lo_cur, hi_cur);
+            uint32_t w_next = atomicAdd(a.counters, 1u);
+            for (uint32_t it = 0;; ++it)
               {
-                static_assert(PROD != 2 || (VEC && KROWS <= 32), "bulk row copies: vectorised kernels");
-                const uint32_t rowbytes = min((uint32_t)BT, a.B - b0) * 8u; // multiple of 16: B even, b0 a multiple of BT
+                const uint32_t slot = sbase + SMP_Q + 32 * (it % QD);
+                while (ld_volatile_shared(slot) != 0u)
+                  {
+                  }
+                if (w_cur >= a.nItems)
+                  {
+                    st_volatile_shared(slot, ITEM_END);
+                    break;
+                  }
+                // ItemDesc: lo = {h_off lo, h_off hi, ids_off, n}, hi = {nproj, proj_off, wait_off, nwait}
+                const uint4    lo = lo_cur, hi = hi_cur;
+                const uint32_t w  = w_cur;
+                asm volatile("st.volatile.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(slot + 16), "r"(hi.z), "r"(hi.w), "r"(hi.y),
+                             "r"(0u)
+                             : "memory");
+                asm volatile("st.volatile.shared.v2.u32 [%0], {%1,%2};" ::"r"(slot + 8), "r"(lo.w), "r"(hi.x) : "memory");
+                st_volatile_shared(slot + 4, lo.z);
+                __threadfence_block();
+                st_volatile_shared(slot, w + 1u);
+                w_cur = w_next;
+                fetch(w_cur, lo_cur, hi_cur);
+                w_next = atomicAdd(a.counters, 1u);
+
+                const int     n = (int)lo.w, ktot = n + (int)hi.x;
+                const int     nKC  = (ktot + KROWS - 1) / KROWS;
+                const int     nMt  = (n + 7) >> 3;
+                const double *srcA = a.packed + (((unsigned long long)lo.y << 32) | lo.x);
                 for (int mc = 0; mc < nMt; mc += MPC)
                   {
-                    const int      mtc   = min(MPC, nMt - mc);
-                    const uint32_t bytes = (uint32_t)mtc * KC * 256u;
-                    uint32_t       code = row_code(lane), code_next = row_code(32 + lane);
-                    auto           row_addr = [&](uint32_t c) -> unsigned long long {
-                      if (c == 0xffffffffu)
-                        return 0ull;
-                      return (unsigned long long)((c & 0x80000000u) ? a.VCX + (size_t)(c & 0x7fffffffu) * a.B :
-                                                                      a.X + (size_t)c * a.B);
-                    };
-                    unsigned long long raddr = row_addr(code);
+                    const uint32_t bytes = (uint32_t)min(MPC, nMt - mc) * KCT * 256u;
                     for (int kc = 0; kc < nKC; ++kc)
                       {
-                        constexpr int SPB = 32 / KROWS; // stages per 32-row block
-                        if (kc && (kc % SPB) == 0)
-                          {
-                            code      = code_next;
-                            code_next = row_code((kc / SPB + 1) * 32 + lane);
-                            raddr     = row_addr(code);
-                          }
-                        mbar_wait(sbase + SM_EMPTY + 8 * stage, ph ^ 1u);
-                        const uint32_t st_addr = sbase + SM_HEADER + stage * S_BYTES;
-                        const uint32_t full    = sbase + SM_FULL + 8 * stage;
-                        if (lane == 0)
-                          {
-                            mbar_arrive_expect_tx(full, bytes + (uint32_t)KROWS * rowbytes);
-                            if (once)
-                              bulk_g2s_hint(st_addr, srcA, bytes, full, evict_first);
-                            else
-                              bulk_g2s(st_addr, srcA, bytes, full);
-                          }
+                        mbar_wait(sbase + SMP_EMPTY + 8 * stage, ph ^ 1u);
+                        const uint32_t full = sbase + SMP_FULL + 8 * stage;
+                        mbar_arrive_expect_tx(full, bytes);
+                        if (once)
+                          bulk_g2s_hint(stgb + stage * S_BYTES, srcA, bytes, full, evict_first);
+                        else
+                          bulk_g2s(stgb + stage * S_BYTES, srcA, bytes, full);
                         srcA += bytes / 8;
-                        const unsigned long long rp = __shfl_sync(0xffffffffu, raddr, (kc % SPB) * KROWS + (lane % KROWS));
-                        if (lane < KROWS)
-                          {
-                            const double *src = rp ? reinterpret_cast<const double *>(rp) + b0 : a.zero_row;
-                            bulk_g2s(st_addr + A_BYTES + (uint32_t)lane * (LDX * 8u), src, rowbytes, full);
-                          }
-                        __syncwarp();
                         if (++stage == NS)
                           {
                             stage = 0;
@@ -426,107 +387,68 @@ namespace hx
                       }
                   }
               }
-            else if constexpr (PROD == 1)
+          }
+        else if (warp == DWARPS + SWARPS + 1)
+          {
+            // ---------------- gather warp: rows of X (and of V C^H X) into the B tile of every stage ----------------
+            constexpr int CPR = VEC ? BT / 2 : BT; // copies per row (<= 32)
+            constexpr int RPI = 32 / CPR;          // rows per warp instruction
+            constexpr int SPB = 32 / KROWS;        // stages per block of 32 gathered rows
+            static_assert(KROWS <= 32 && 32 % KROWS == 0 && KROWS % RPI == 0, "stage rows");
+            const int cc = lane % CPR;
+            const int rr = lane / CPR;
+            uint32_t  stage = 0, ph = 0;
+            for (uint32_t it = 0;; ++it)
               {
-                static_assert(PROD != 1 || VEC, "shuffled row addresses: vectorised kernels");
+                const uint32_t slot = sbase + SMP_Q + 32 * (it % QD);
+                uint32_t       tag;
+                while ((tag = ld_volatile_shared(slot)) == 0u)
+                  {
+                  }
+                if (tag == ITEM_END)
+                  break;
+                PItem d;
+                pitem_load(slot, d);
+                const uint32_t w = tag - 1u;
+                const int      n = (int)d.n, ktot = n + (int)d.nproj;
+                // start address of row k of the B operand (0 = zero row): X rows of the cell, then its rows of V C^H X
+                auto row_addr = [&](int k) -> unsigned long long {
+                  if (k >= ktot)
+                    return 0ull;
+                  if (k < n)
+                    return (unsigned long long)(a.X + (size_t)__ldg(a.ids + d.ids_off + k) * a.B);
+                  return (unsigned long long)(a.VCX + (size_t)__ldg(a.pids + d.proj_off + (k - n)) * a.B);
+                };
+                const uint32_t b0    = (w % a.nBt) * BT;
+                const int      nKC   = (ktot + KROWS - 1) / KROWS;
+                const int      nMt   = (n + 7) >> 3;
+                const uint32_t col   = b0 + (VEC ? cc * 2 : cc);
+                const bool     colok = col < a.B;
                 for (int mc = 0; mc < nMt; mc += MPC)
                   {
-                    const int      mtc   = min(MPC, nMt - mc);
-                    const uint32_t bytes = (uint32_t)mtc * KC * 256u;
-                    // row codes: lane l holds row 32*j + l of the current / next block of 32 rows
-                    uint32_t code = row_code(lane), code_next = row_code(32 + lane);
-                    // start address of this lane's row (0 = zero row)
-                    auto row_addr = [&](uint32_t c) -> unsigned long long {
-                      if (c == 0xffffffffu)
-                        return 0ull;
-                      return (unsigned long long)((c & 0x80000000u) ? a.VCX + (size_t)(c & 0x7fffffffu) * a.B :
-                                                                      a.X + (size_t)c * a.B);
-                    };
-                    unsigned long long raddr = row_addr(code);
+                    unsigned long long raddr = row_addr(lane), raddr_next = row_addr(32 + lane);
                     for (int kc = 0; kc < nKC; ++kc)
                       {
-                        constexpr int SPB = 32 / KROWS; // stages per 32-row block
                         if (kc && (kc % SPB) == 0)
                           {
-                            code      = code_next;
-                            code_next = row_code((kc / SPB + 1) * 32 + lane);
-                            raddr     = row_addr(code);
+                            raddr      = raddr_next;
+                            raddr_next = row_addr((kc / SPB + 1) * 32 + lane);
                           }
-                        mbar_wait(sbase + SM_EMPTY + 8 * stage, ph ^ 1u);
-                        const uint32_t st_addr = sbase + SM_HEADER + stage * S_BYTES;
-                        const uint32_t full    = sbase + SM_FULL + 8 * stage;
-                        if (lane == 0)
-                          {
-                            mbar_arrive_expect_tx(full, bytes);
-                            if (once)
-                              bulk_g2s_hint(st_addr, srcA, bytes, full, evict_first);
-                            else
-                              bulk_g2s(st_addr, srcA, bytes, full);
-                          }
-                        srcA += bytes / 8;
-                        const uint32_t xs = st_addr + A_BYTES;
-    #pragma unroll
+                        mbar_wait(sbase + SMP_EMPTY + 8 * stage, ph ^ 1u);
+                        const uint32_t xs = stgb + stage * S_BYTES + A_BYTES;
+#pragma unroll
                         for (int r = 0; r < KROWS; r += RPI)
                           {
                             const unsigned long long rp = __shfl_sync(0xffffffffu, raddr, (kc % SPB) * KROWS + r + rr);
                             const bool               ok = (rp != 0ull) && colok;
                             const double *           src = ok ? reinterpret_cast<const double *>(rp) + col : a.X;
-                            const uint32_t           dst = xs + ((uint32_t)(r + rr) * LDX + cc * 2) * 8u;
-                            cp_async_zfill16(dst, src, ok ? 16u : 0u);
-                          }
-                        cp_async_mbar_arrive_noinc(full);
-                        if (++stage == NS)
-                          {
-                            stage = 0;
-                            ph ^= 1u;
-                          }
-                      }
-                  }
-              }
-            else
-              {
-                for (int mc = 0; mc < nMt; mc += MPC)
-                  {
-                    const int      mtc   = min(MPC, nMt - mc);
-                    const uint32_t bytes = (uint32_t)mtc * KC * 256u;
-                    // row codes: lane l holds row 32*j + l of the current / next block of 32 rows
-                    uint32_t code = row_code(lane), code_next = row_code(32 + lane);
-                    for (int kc = 0; kc < nKC; ++kc)
-                      {
-                        constexpr int SPB = 32 / KROWS; // stages per 32-row block
-                        if (kc && (kc % SPB) == 0)
-                          {
-                            code      = code_next;
-                            code_next = row_code((kc / SPB + 1) * 32 + lane);
-                          }
-                        mbar_wait(sbase + SM_EMPTY + 8 * stage, ph ^ 1u);
-                        const uint32_t st_addr = sbase + SM_HEADER + stage * S_BYTES;
-                        const uint32_t full    = sbase + SM_FULL + 8 * stage;
-                        if (lane == 0)
-                          {
-                            mbar_arrive_expect_tx(full, bytes);
-                            if (once)
-                              bulk_g2s_hint(st_addr, srcA, bytes, full, evict_first);
-                            else
-                              bulk_g2s(st_addr, srcA, bytes, full);
-                          }
-                        srcA += bytes / 8;
-                        const uint32_t xs = st_addr + A_BYTES;
-    #pragma unroll
-                        for (int r = 0; r < KROWS; r += RPI)
-                          {
-                            const uint32_t c   = __shfl_sync(0xffffffffu, code, (kc % SPB) * KROWS + r + rr);
-                            const bool     ok  = (c != 0xffffffffu) && colok;
-                            const double * src = a.X;
-                            if (ok)
-                              src = ((c & 0x80000000u) ? a.VCX + (size_t)(c & 0x7fffffffu) * a.B : a.X + (size_t)c * a.B) + col;
-                            const uint32_t dst = xs + ((uint32_t)(r + rr) * LDX + (VEC ? cc * 2 : cc)) * 8u;
+                            const uint32_t           dst = xs + ((uint32_t)(r + rr) * LDX + (VEC ? cc * 2 : cc)) * 8u;
                             if (VEC)
                               cp_async_zfill16(dst, src, ok ? 16u : 0u);
                             else
                               cp_async_zfill8(dst, src, ok ? 8u : 0u);
                           }
-                        cp_async_mbar_arrive_noinc(full);
+                        cp_async_mbar_arrive_noinc(sbase + SMP_FULL + 8 * stage);
                         if (++stage == NS)
                           {
                             stage = 0;
@@ -536,118 +458,309 @@ namespace hx
                   }
               }
           }
+        return;
       }
-    else if (warp == CWARPS + 1)
+    else if (warp >= DWARPS)
       {
-        // ---------------- sync warp: waits for the predecessors' stamps, publishes this item's stamp ----------------
+        reg_dec<REGS>();
+        // ---------------- scatter warps ----------------
+        constexpr int TPR   = BT / 2;         // threads per row (16 bytes each)
+        constexpr int RPP   = STHREADS / TPR; // rows per pass of the 256 threads
+        constexpr int NPASS = (MPC * 8 + RPP - 1) / RPP;
+        constexpr int LPR   = (BT * 8 + 127) / 128; // 128-byte lines per row of a tile
+        constexpr int RBE   = RB < NPASS ? RB : NPASS; // rows per batch
+        static_assert(NPASS % RBE == 0, "rows per batch");
+        static_assert(MPC * 8 <= SROWS, "one scatter thread per row of a chunk");
+        const int      st   = tid - DTHREADS;
+        const int      q    = st % TPR;
+        const int      rrow = st / TPR;
+        const uint32_t B    = a.B;
+        const bool     fc   = FUSE && (a.f_has_c != 0u);
+        uint32_t       g    = 0; // chunk counter (phase of the accumulator hand-over, record buffer)
+        // Index data of a chunk - thread st < 128: destination code of row st; thread st >= 128: entry st - 128 of the
+        // item's predecessor list - is requested one chunk ahead, while the rows of the current chunk are being
+        // read-modify-written, so a chunk starts with it in a register.
+        bool     have_next = false;
+        uint32_t idx_next  = 0xffffffffu;
         for (uint32_t it = 0;; ++it)
           {
-            const uint32_t slot = sbase + SM_Q + 32 * (it % QD);
-            ItemInfo       info;
-            while ((info.tag = ld_volatile_shared(slot)) == 0u)
+            const uint32_t slot = sbase + SMP_Q + 32 * (it % QD);
+            uint32_t       tag;
+            while ((tag = ld_volatile_shared(slot)) == 0u)
               {
               }
-            if (info.tag == ITEM_END)
+            if (tag == ITEM_END)
               break;
-            item_load_payload(slot, info);
-            const uint32_t w = info.tag - 1u, bt = w % a.nBt;
-            // the acquire loads order the DMMA warps' read-modify-writes (released to them through the
-            // mbarrier) after the predecessors' stores
-            for (uint32_t i = lane; i < info.nwait; i += 32)
+            PItem info;
+            pitem_load(slot, info);
+            const uint32_t w   = tag - 1u, bt = w % a.nBt;
+            const int      n   = (int)info.n;
+            const int      nMt = (n + 7) >> 3;
+            const uint32_t b0  = bt * BT;
+            const uint32_t col = b0 + q * 2;
+            const bool     c0ok = col < B, c1ok = col + 1 < B;
+            for (int mc = 0; mc < nMt; mc += MPC, ++g)
               {
-                const uint32_t *f = a.flags + (size_t)__ldg(a.wait_list + info.wait_off + i) * a.nBt + bt;
-                while (ld_acquire_gpu(f) != a.epoch)
+                const int      rbase = mc * 8;
+                const int      nrows = min(MPC * 8, n - rbase);
+                const uint32_t rbuf  = sbase + SMP_REC + (g & 1u) * (SROWS * 24);
+                uint32_t       idx;
+                if (have_next)
+                  idx = idx_next;
+                else if (st < SROWS)
+                  idx = (st < nrows) ? __ldg(a.dest + info.ids_off + rbase + st) : 0xffffffffu;
+                else
+                  idx = (mc == 0 && (uint32_t)(st - SROWS) < info.nwait) ? __ldg(a.wait_list + info.wait_off + (st - SROWS)) : 0xffffffffu;
+                have_next = false;
+                double dinv_r = 0.0;
+                if (st < SROWS)
                   {
+                    if (FUSE && idx != 0xffffffffu && (idx & (HX_DEST_LASTF | HX_DEST_STAGED)) == HX_DEST_LASTF)
+                      {
+                        dinv_r = __dmul_rn(a.f_a, __ldg(a.f_dinv + HX_DEST_ROW(idx))); // s = a*dinv of the row
+                        if (fc)
+                          {
+                            // this row's last toucher will read xprev[row, tile]: pull the lines into L2 now
+                            const double *xp = a.f_xprev + (size_t)HX_DEST_ROW(idx) * B + b0;
+#pragma unroll
+                            for (int l = 0; l < LPR; ++l)
+                              if (b0 + l * 16 < B)
+                                asm volatile("prefetch.global.L2 [%0];" ::"l"(xp + l * 16));
+                          }
+                      }
                   }
+                // request the index data of the next chunk (same item, or the next item if it is queued already)
+                if (mc + MPC < nMt)
+                  {
+                    if (st < SROWS)
+                      idx_next = (st < n - rbase - MPC * 8) ? __ldg(a.dest + info.ids_off + rbase + MPC * 8 + st) : 0xffffffffu;
+                    else
+                      idx_next = 0xffffffffu;
+                    have_next = true;
+                  }
+                else
+                  {
+                    const uint32_t nslot = sbase + SMP_Q + 32 * ((it + 1) % QD);
+                    const uint32_t ntag  = ld_volatile_shared(nslot);
+                    if (ntag != 0u && ntag != ITEM_END)
+                      {
+                        PItem ni;
+                        pitem_load(nslot, ni);
+                        if (st < SROWS)
+                          idx_next = ((uint32_t)st < ni.n) ? __ldg(a.dest + ni.ids_off + st) : 0xffffffffu;
+                        else
+                          idx_next = ((uint32_t)(st - SROWS) < ni.nwait) ? __ldg(a.wait_list + ni.wait_off + (st - SROWS)) : 0xffffffffu;
+                        have_next = true;
+                      }
+                  }
+                if (st >= SROWS)
+                  {
+                    // the immediately preceding toucher of every row of this cell must have stored (acquire)
+                    if (mc == 0)
+                      {
+                        if (idx != 0xffffffffu)
+                          {
+                            const uint32_t *f = a.flags + (size_t)idx * a.nBt + bt;
+                            while (ld_acquire_gpu(f) != a.epoch)
+                              {
+                              }
+                          }
+                        for (uint32_t i = (uint32_t)st; i < info.nwait; i += SROWS)
+                          {
+                            const uint32_t *f = a.flags + (size_t)__ldg(a.wait_list + info.wait_off + i) * a.nBt + bt;
+                            while (ld_acquire_gpu(f) != a.epoch)
+                              {
+                              }
+                          }
+                      }
+                  }
+                else
+                  {
+                    // record of this thread's row: flags bit 0 valid, 1 add (read the partial sum first), 2 last toucher of
+                    // a fusable row, 3 staged
+                    const bool valid  = idx != 0xffffffffu;
+                    const bool staged = valid && (idx & HX_DEST_STAGED);
+                    const bool lastf  = FUSE && valid && (idx & (HX_DEST_LASTF | HX_DEST_STAGED)) == HX_DEST_LASTF;
+                    const uint32_t fl = !valid ? 0u :
+                                                 (1u | ((!staged && !(idx & HX_DEST_FIRST)) ? 2u : 0u) | (lastf ? 4u : 0u) | (staged ? 8u : 0u));
+                    const unsigned long long ro =
+                      (unsigned long long)(staged ? (idx & 0x7fffffffu) : HX_DEST_ROW(idx)) * B * 8ull;
+                    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(rbuf + 16 * st), "r"((uint32_t)ro),
+                                 "r"((uint32_t)(ro >> 32)), "r"(fl), "r"(0u)
+                                 : "memory");
+                    if (FUSE)
+                      asm volatile("st.shared.f64 [%0], %1;" ::"r"(rbuf + SROWS * 16 + 8 * st), "d"(dinv_r) : "memory");
+                  }
+                bar_scatter(); // records of the chunk are in shared memory; the predecessors have stored
+                const uint32_t ab = (NACC == 2) ? (g & 1u) : 0u, aph = (NACC == 2) ? ((g >> 1) & 1u) : (g & 1u);
+                mbar_wait(sbase + SMP_ACCFULL + 16 * ab, aph);
+                const uint32_t acct = accb + ab * ACC_B;
+                const unsigned long long colb = (unsigned long long)col * 8ull;
+#pragma unroll 1
+                for (int p0 = 0; p0 < NPASS; p0 += RBE)
+                  {
+                    uint32_t           fl[RBE];
+                    unsigned long long t[RBE];
+                    double2            y[RBE], xc[RBE], xp[RBE], av[RBE];
+#pragma unroll
+                    for (int u = 0; u < RBE; ++u)
+                      {
+                        const int r = (p0 + u) * RPP + rrow;
+                        uint32_t  lo, hi, pad;
+                        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                                     : "=r"(lo), "=r"(hi), "=r"(fl[u]), "=r"(pad)
+                                     : "r"(rbuf + 16 * r)
+                                     : "memory");
+                        t[u] = (((unsigned long long)hi << 32) | lo) + colb;
+                        if (!c0ok || (MPC * 8 % RPP != 0 && r >= MPC * 8))
+                          fl[u] = 0u;
+                      }
+#pragma unroll
+                    for (int u = 0; u < RBE; ++u)
+                      {
+                        y[u] = xc[u] = xp[u] = make_double2(0.0, 0.0);
+                        if (fl[u] & 2u)
+                          {
+                            if (VEC)
+                              y[u] = __ldcg(reinterpret_cast<const double2 *>(reinterpret_cast<const char *>(a.Y) + t[u]));
+                            else
+                              {
+                                y[u].x = __ldcg(reinterpret_cast<const double *>(reinterpret_cast<const char *>(a.Y) + t[u]));
+                                if (c1ok)
+                                  y[u].y = __ldcg(reinterpret_cast<const double *>(reinterpret_cast<const char *>(a.Y) + t[u]) + 1);
+                              }
+                          }
+                        if (FUSE && (fl[u] & 4u))
+                          {
+                            xc[u] = __ldcg(reinterpret_cast<const double2 *>(reinterpret_cast<const char *>(a.X) + t[u]));
+                            if (fc)
+                              xp[u] = __ldcg(reinterpret_cast<const double2 *>(reinterpret_cast<const char *>(a.f_xprev) + t[u]));
+                          }
+                      }
+                    // accumulators of these rows (swizzled tile, see the DMMA warps)
+#pragma unroll
+                    for (int u = 0; u < RBE; ++u)
+                      {
+                        const int      r    = (p0 + u) * RPP + rrow;
+                        const uint32_t addr = acct + (uint32_t)r * ROW_B + (uint32_t)(((q >> 2) ^ (r & (NT - 1))) * 64 + (q & 3) * 16);
+                        asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(av[u].x), "=d"(av[u].y) : "r"(addr) : "memory");
+                      }
+#pragma unroll
+                    for (int u = 0; u < RBE; ++u)
+                      {
+                        double2 v;
+                        v.x = y[u].x + av[u].x;
+                        v.y = y[u].y + av[u].y;
+                        char *ptr = reinterpret_cast<char *>((fl[u] & 8u) ? a.stage : a.Y) + t[u];
+                        if (FUSE)
+                          {
+                            if (fl[u] & 4u)
+                              {
+                                // last toucher of a fusable row: the final (H X)[row, tile] is here,
+                                // out = (a*dinv)*(H X) + (b*X + c*Xprev)   [cheb_combine_diag]
+                                const int r = (p0 + u) * RPP + rrow;
+                                double    dv;
+                                asm volatile("ld.shared.f64 %0, [%1];" : "=d"(dv) : "r"(rbuf + SROWS * 16 + 8 * r) : "memory");
+                                double2 z;
+                                z.x = __dmul_rn(a.f_b, xc[u].x), z.y = __dmul_rn(a.f_b, xc[u].y);
+                                if (fc) // cheb_z
+                                  z.x = __fma_rn(a.f_c, xp[u].x, z.x), z.y = __fma_rn(a.f_c, xp[u].y, z.y);
+                                // the partial sums of this row are dead: drop their dirty L2 lines (whole 128-B lines only)
+                                if ((fl[u] & 2u) && a.f_discard && (q & 7) == 0)
+                                  asm volatile("discard.global.L2 [%0], 128;" ::"l"(ptr) : "memory");
+                                v.x = __fma_rn(dv, v.x, z.x);
+                                v.y = __fma_rn(dv, v.y, z.y);
+                                ptr = reinterpret_cast<char *>(a.f_out) + t[u];
+                              }
+                          }
+                        if (fl[u] & 1u)
+                          {
+                            if (VEC)
+                              __stcg(reinterpret_cast<double2 *>(ptr), v);
+                            else
+                              {
+                                __stcg(reinterpret_cast<double *>(ptr), v.x);
+                                if (c1ok)
+                                  __stcg(reinterpret_cast<double *>(ptr) + 1, v.y);
+                              }
+                          }
+                      }
+                  }
+                // the tile may be overwritten by the next chunk
+                __syncwarp();
+                if (lane == 0)
+                  mbar_arrive(sbase + SMP_ACCFREE + 16 * ab);
               }
-            __syncwarp();
-            if (lane == 0)
-              mbar_arrive(sbase + SM_PRED + 8 * (it & 1u));
-            // all DMMA warps have stored their rows of this item: publish (release, cumulative at gpu scope)
-            mbar_wait(sbase + SM_DONE + 8 * (it & 1u), (it >> 1) & 1u);
-            if (lane == 0)
+            // every row of the item is stored: publish its stamp (release, cumulative at gpu scope)
+            bar_scatter();
+            if (st == 0)
               {
                 st_release_gpu(a.flags + w, a.epoch);
                 st_volatile_shared(slot, 0u); // queue slot free again
               }
-            __syncwarp();
           }
       }
     else
       {
-        // ------------------------------------ DMMA warps ------------------------------------
-        uint32_t stage = 0, ph = 0;
+        reg_inc<REGD>();
+        // ---------------- DMMA warps ----------------
+        unsigned long long c0 = 0, t0 = 0;
+        if (tid == 0 && blockIdx.x == 0 && a.clk)
+          {
+            c0 = clock64();
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+          }
+        uint32_t stage = 0, ph = 0, g = 0;
         for (uint32_t it = 0;; ++it)
           {
-            const uint32_t slot = sbase + SM_Q + 32 * (it % QD);
-            ItemInfo       info;
-            while ((info.tag = ld_volatile_shared(slot)) == 0u)
+            const uint32_t slot = sbase + SMP_Q + 32 * (it % QD);
+            uint32_t       tag;
+            while ((tag = ld_volatile_shared(slot)) == 0u)
               {
               }
-            if (info.tag == ITEM_END)
+            if (tag == ITEM_END)
               break;
-            item_load_payload(slot, info);
-            const uint32_t w    = info.tag - 1u;
-            const int      n    = (int)info.n;
-            const int      nKC  = (n + (int)info.nproj + KROWS - 1) / KROWS;
-            const int      nMt  = (n + 7) >> 3;
-            const uint32_t B    = a.B;
-            const uint32_t b0   = (w % a.nBt) * BT;
-            const int      xoff = A_BYTES / 8 + (lane & 3) * LDX + (lane >> 2); // B fragment inside a stage
-
-            for (int mc = 0; mc < nMt; mc += MPC)
+            __threadfence_block();
+            uint32_t n_, np_;
+            asm volatile("ld.volatile.shared.v2.u32 {%0,%1}, [%2];" : "=r"(n_), "=r"(np_) : "r"(slot + 8) : "memory");
+            const int n    = (int)n_;
+            const int nKC  = (n + (int)np_ + KROWS - 1) / KROWS;
+            const int nMt  = (n + 7) >> 3;
+            const int xoff = A_BYTES / 8 + (lane & 3) * LDX + (lane >> 2); // B fragment inside a stage
+            for (int mc = 0; mc < nMt; mc += MPC, ++g)
               {
                 const int  mtc    = min(MPC, nMt - mc);
-                const int  mtl0   = warp * MTW; // first local m-tile of this warp
+                const int  mtl0   = warp * MPW;
                 const bool active = mtl0 < mtc;
-                // destinations of this thread's rows (latency hidden behind the k loop)
-                uint32_t dst_code[MTW];
+                int        aoff[MPW];
 #pragma unroll
-                for (int j = 0; j < MTW; ++j)
-                  {
-                    const int r = (mc + mtl0 + j) * 8 + (lane >> 2);
-                    dst_code[j] = (r < n) ? __ldg(a.dest + info.ids_off + r) : 0xffffffffu;
-                    if (FUSE)
-                      {
-                        // the last toucher will need xprev[row, tile]: pull its lines into L2 behind the k loop
-                        const uint32_t d  = dst_code[j];
-                        const uint32_t pc = b0 + (lane & 3) * 16;
-                        if (d != 0xffffffffu && (d & (HX_DEST_LASTF | HX_DEST_STAGED)) == HX_DEST_LASTF && a.f_c != 0.0 &&
-                            (lane & 3) * 16 < BT && pc < B)
-                          asm volatile("prefetch.global.L2 [%0];" ::"l"(a.f_xprev + (size_t)HX_DEST_ROW(d) * B + pc));
-                      }
-                  }
-                int aoff[MTW];
+                for (int j = 0; j < MPW; ++j)
+                  aoff[j] = min(mtl0 + j, mtc - 1) * (KCT * 32) + lane;
+                double acc[MPW][NT][2];
 #pragma unroll
-                for (int j = 0; j < MTW; ++j)
-                  aoff[j] = min(mtl0 + j, mtc - 1) * (KC * 32) + lane;
-
-                double acc[MTW][NT][2];
-#pragma unroll
-                for (int j = 0; j < MTW; ++j)
+                for (int j = 0; j < MPW; ++j)
 #pragma unroll
                   for (int t = 0; t < NT; ++t)
                     acc[j][t][0] = acc[j][t][1] = 0.0;
-
                 for (int kc = 0; kc < nKC; ++kc)
                   {
-                    mbar_wait(sbase + SM_FULL + 8 * stage, ph);
+                    mbar_wait(sbase + SMP_FULL + 8 * stage, ph);
                     if (active)
                       {
-                        const double *St = reinterpret_cast<const double *>(smem_raw + SM_HEADER + (size_t)stage * S_BYTES);
+                        const double *St = reinterpret_cast<const double *>(smem_raw + SMP_HEADER + NACC * ACC_B + (size_t)stage * S_BYTES);
                         const double *xr = St + xoff;
 #pragma unroll
-                        for (int ks = 0; ks < KC; ++ks)
+                        for (int ks = 0; ks < KCT; ++ks)
                           {
-                            double af[MTW], bf[NT];
+                            double af[MPW], bf[NT];
 #pragma unroll
-                            for (int j = 0; j < MTW; ++j)
+                            for (int j = 0; j < MPW; ++j)
                               af[j] = St[aoff[j] + ks * 32];
 #pragma unroll
                             for (int t = 0; t < NT; ++t)
                               bf[t] = xr[ks * 4 * LDX + t * 8];
 #pragma unroll
-                            for (int j = 0; j < MTW; ++j)
+                            for (int j = 0; j < MPW; ++j)
 #pragma unroll
                               for (int t = 0; t < NT; ++t)
                                 dmma884(acc[j][t][0], acc[j][t][1], af[j], bf[t]);
@@ -655,139 +768,42 @@ namespace hx
                       }
                     __syncwarp();
                     if (lane == 0)
-                      mbar_arrive(sbase + SM_EMPTY + 8 * stage);
+                      mbar_arrive(sbase + SMP_EMPTY + 8 * stage);
                     if (++stage == NS)
                       {
                         stage = 0;
                         ph ^= 1u;
                       }
                   }
-                // Chebyshev epilogue, part 1: z = b*X[row] + c*Xprev[row] for the rows this thread finishes.  It does not
-                // depend on the predecessors, so for the first m-tile it is issued before waiting for them; the other
-                // m-tiles load it together with their Y rows (registers).
-                auto load_z = [&](int j, double2(&z)[NT], double &dv) {
-                  const uint32_t d  = dst_code[j];
-                  const size_t   ro = (size_t)HX_DEST_ROW(d) * B;
-                  dv                = __ldg(a.f_dinv + HX_DEST_ROW(d));
-                  double2 xc[NT], xp[NT];
-#pragma unroll
-                  for (int t = 0; t < NT; ++t)
-                    {
-                      const uint32_t col = b0 + t * 8 + (lane & 3) * 2;
-                      xc[t] = xp[t] = make_double2(0.0, 0.0);
-                      if (col < B)
-                        {
-                          xc[t] = __ldcg(reinterpret_cast<const double2 *>(a.X + ro + col));
-                          if (a.f_c != 0.0)
-                            xp[t] = __ldcg(reinterpret_cast<const double2 *>(a.f_xprev + ro + col));
-                        }
-                    }
-#pragma unroll
-                  for (int t = 0; t < NT; ++t)
-                    {
-                      z[t].x = cheb_z(a.f_b, xc[t].x, a.f_c, xp[t].x);
-                      z[t].y = cheb_z(a.f_b, xc[t].y, a.f_c, xp[t].y);
-                    }
-                };
-                auto is_lastf = [&](int j) {
-                  return dst_code[j] != 0xffffffffu && (dst_code[j] & (HX_DEST_LASTF | HX_DEST_STAGED)) == HX_DEST_LASTF;
-                };
-                double2 z0[NT];
-                double  dv0 = 0.0;
-                if (FUSE && active && is_lastf(0))
-                  load_z(0, z0, dv0);
-                if (mc == 0) // the preceding toucher of every row of this cell has scattered (sync warp)
-                  mbar_wait(sbase + SM_PRED + 8 * (it & 1u), (it >> 1) & 1u);
-                // ---- scatter-add (ordered: plain RMW through L2; shared rows: staging slot) ----
+                // park the accumulators for the scatter warps (they have released the tile of the previous chunk)
+                const uint32_t ab = (NACC == 2) ? (g & 1u) : 0u, aph = (NACC == 2) ? ((g >> 1) & 1u) : (g & 1u);
+                mbar_wait(sbase + SMP_ACCFREE + 16 * ab, aph ^ 1u);
                 if (active)
                   {
 #pragma unroll
-                    for (int j = 0; j < MTW; ++j)
-                      {
-                        const uint32_t d = dst_code[j];
-                        if (d != 0xffffffffu)
-                          {
-                            const bool staged = (d & HX_DEST_STAGED) != 0;
-                            const bool add    = !staged && !(d & HX_DEST_FIRST);
-                            double *   dst    = staged ? a.stage + (size_t)(d & 0x7fffffffu) * B : a.Y + (size_t)HX_DEST_ROW(d) * B;
-                            if (VEC)
-                              {
-                                double2 y[NT];
+                    for (int j = 0; j < MPW; ++j)
+                      if (mtl0 + j < mtc)
+                        {
+                          const int r = (mtl0 + j) * 8 + (lane >> 2);
 #pragma unroll
-                                for (int t = 0; t < NT; ++t)
-                                  {
-                                    const uint32_t col = b0 + t * 8 + (lane & 3) * 2;
-                                    y[t]               = make_double2(0.0, 0.0);
-                                    if (add && col < B)
-                                      y[t] = __ldcg(reinterpret_cast<const double2 *>(dst + col));
-                                  }
-                                if (FUSE && !staged && (d & HX_DEST_LASTF))
-                                  {
-                                    // part 2: the final (H X)[row, tile] is in registers: out = a*dinv*(H X) + z
-                                    const size_t ro = (size_t)HX_DEST_ROW(d) * B;
-                                    double2      z[NT];
-                                    double       dv;
-                                    if (j == 0)
-                                      {
-                                        dv = dv0;
-#pragma unroll
-                                        for (int t = 0; t < NT; ++t)
-                                          z[t] = z0[t];
-                                      }
-                                    else
-                                      load_z(j, z, dv);
-#pragma unroll
-                                    for (int t = 0; t < NT; ++t)
-                                      {
-                                        const uint32_t col = b0 + t * 8 + (lane & 3) * 2;
-                                        if (col < B)
-                                          {
-                                            double2 o;
-                                            o.x = __fma_rn(a.f_a, __dmul_rn(dv, y[t].x + acc[j][t][0]), z[t].x);
-                                            o.y = __fma_rn(a.f_a, __dmul_rn(dv, y[t].y + acc[j][t][1]), z[t].y);
-                                            __stcg(reinterpret_cast<double2 *>(a.f_out + ro + col), o);
-                                          }
-                                      }
-                                    // the partial sums of this row are dead now: drop their (dirty) L2 lines instead of
-                                    // letting them be written back to HBM.  Only when the tile covers whole 128-B lines.
-                                    if (add && a.f_discard && (lane & 3) * 16 < BT)
-                                      asm volatile("discard.global.L2 [%0], 128;" ::"l"(dst + b0 + (lane & 3) * 16) : "memory");
-                                  }
-                                else
-                                  {
-#pragma unroll
-                                    for (int t = 0; t < NT; ++t)
-                                      {
-                                        const uint32_t col = b0 + t * 8 + (lane & 3) * 2;
-                                        if (col < B)
-                                          {
-                                            y[t].x += acc[j][t][0];
-                                            y[t].y += acc[j][t][1];
-                                            __stcg(reinterpret_cast<double2 *>(dst + col), y[t]);
-                                          }
-                                      }
-                                  }
-                              }
-                            else
-                              {
-#pragma unroll
-                                for (int t = 0; t < NT; ++t)
-                                  {
-                                    const uint32_t col = b0 + t * 8 + (lane & 3) * 2;
-                                    if (col < B)
-                                      __stcg(dst + col, (add ? __ldcg(dst + col) : 0.0) + acc[j][t][0]);
-                                    if (col + 1 < B)
-                                      __stcg(dst + col + 1, (add ? __ldcg(dst + col + 1) : 0.0) + acc[j][t][1]);
-                                  }
-                              }
-                          }
-                      }
+                          for (int t = 0; t < NT; ++t)
+                            {
+                              const uint32_t addr = accb + ab * ACC_B + (uint32_t)r * ROW_B + (uint32_t)((t ^ (r & (NT - 1))) * 64 + (lane & 3) * 16);
+                              asm volatile("st.shared.v2.f64 [%0], {%1,%2};" ::"r"(addr), "d"(acc[j][t][0]), "d"(acc[j][t][1]) : "memory");
+                            }
+                        }
                   }
+                __syncwarp();
+                if (lane == 0)
+                  mbar_arrive(sbase + SMP_ACCFULL + 16 * ab);
               }
-            // this warp's rows of the item are stored (the arrive releases them to the sync warp)
-            __syncwarp();
-            if (lane == 0)
-              mbar_arrive(sbase + SM_DONE + 8 * (it & 1u));
+          }
+        if (tid == 0 && blockIdx.x == 0 && a.clk)
+          {
+            unsigned long long t1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            a.clk[0] += clock64() - c0; // SM cycles and nanoseconds CTA 0 spent in the kernel, summed over launches
+            a.clk[1] += t1 - t0;
           }
         // last CTA out resets the work counters for the next launch
         if (tid == 0)
@@ -827,8 +843,9 @@ namespace hx
     const CellMeta cm   = a.meta[cell];
     const int      n    = (int)cm.n;
     const int      ktot = n + (int)cm.nproj;
-    const int      nKC  = (ktot + 4 * KC - 1) / (4 * KC);
-    const int      Kp   = nKC * 4 * KC;
+    const int      KCv  = (int)a.kc;
+    const int      nKC  = (ktot + 4 * KCv - 1) / (4 * KCv);
+    const int      Kp   = nKC * 4 * KCv;
     const int      nK   = Kp >> 2;
     const int      nMt  = (n + 7) >> 3;
     const uint32_t B    = a.B;
@@ -899,9 +916,9 @@ namespace hx
         const double *Ap[MTW];
 #pragma unroll
         for (int j = 0; j < MTW; ++j)
-          Ap[j] = Abase + stage_offset(mc, mtc, 0, nKC) + (size_t)min(mtl0 + j, mtc - 1) * (KC * 32);
-        const size_t kc_stride = (size_t)mtc * (KC * 32);
-        auto         frag      = [&](int j, int k) { return Ap[j] + (size_t)(k / KC) * kc_stride + (size_t)(k % KC) * 32; };
+          Ap[j] = Abase + stage_offset(mc, mtc, 0, nKC, KCv) + (size_t)min(mtl0 + j, mtc - 1) * (KCv * 32);
+        const size_t kc_stride = (size_t)mtc * (KCv * 32);
+        auto         frag      = [&](int j, int k) { return Ap[j] + (size_t)(k / KCv) * kc_stride + (size_t)(k % KCv) * 32; };
 
         double acc[MTW][NT][2];
 #pragma unroll
@@ -993,6 +1010,7 @@ namespace hx
   // pack: raw row-major n x n cell matrices (+ column-major nProj x n projector matrices) -> the stage stream.
   // For chunk mc (mtc m-tiles), k-chunk kc, local m-tile mtl, k-step ks, lane:
   //   packed[stage_offset(mc,mtc,kc) + ((mtl*KC + ks)*32 + lane)] = A[(mc+mtl)*8 + lane/4][(kc*KC + ks)*4 + lane%4]
+  // with KC = op->kc k-steps per stage (2 or 4, chosen per operator in pack_cell_matrices)
   __global__ void
   pack_kernel(const double *            raw,
               unsigned long long        raw_base,
@@ -1002,30 +1020,31 @@ namespace hx
               const CellMeta *          meta,
               double *                  packed,
               uint32_t                  cell_begin,
-              int                       mpc)
+              int                       mpc,
+              int                       KCv)
   {
     const uint32_t cell = cell_begin + blockIdx.x;
     const CellMeta cm   = meta[cell];
     const int      n = (int)cm.n, np = (int)cm.nproj;
-    const int      nKC = (n + np + 4 * KC - 1) / (4 * KC), nMt = (n + 7) >> 3;
+    const int      nKC = (n + np + 4 * KCv - 1) / (4 * KCv), nMt = (n + 7) >> 3;
     const double * H   = raw ? raw + (raw_off[cell] - raw_base) : nullptr; // null: structure only (H part zero)
     const double * Cc  = (np > 0) ? cellC + c_off[cell] : nullptr;
     double *       out = packed + cm.h_off;
-    const size_t   tot = (size_t)nMt * nKC * KC * 32;
+    const size_t   tot = (size_t)nMt * nKC * KCv * 32;
     for (size_t idx = threadIdx.x; idx < tot; idx += blockDim.x)
       {
         // decode idx in stream order
-        const size_t per_chunk = (size_t)mpc * nKC * KC * 32;
+        const size_t per_chunk = (size_t)mpc * nKC * KCv * 32;
         const int    ch        = (int)(idx / per_chunk);
         const int    mc        = ch * mpc;
         const int    mtc       = min(mpc, nMt - mc);
         size_t       rem       = idx - (size_t)ch * per_chunk;
-        const int    kc        = (int)(rem / ((size_t)mtc * KC * 32));
-        rem -= (size_t)kc * mtc * KC * 32;
-        const int mtl  = (int)(rem / (KC * 32));
-        const int ks   = (int)((rem / 32) % KC);
+        const int    kc        = (int)(rem / ((size_t)mtc * KCv * 32));
+        rem -= (size_t)kc * mtc * KCv * 32;
+        const int mtl  = (int)(rem / (KCv * 32));
+        const int ks   = (int)((rem / 32) % KCv);
         const int lane = (int)(rem & 31);
-        const int r = (mc + mtl) * 8 + (lane >> 2), k = (kc * KC + ks) * 4 + (lane & 3);
+        const int r = (mc + mtl) * 8 + (lane >> 2), k = (kc * KCv + ks) * 4 + (lane & 3);
         double    v = 0.0;
         if (r < n)
           {
@@ -1098,7 +1117,8 @@ namespace hx
     for (uint32_t c = 0; c < p->C; ++c)
       {
         const CellMeta &m  = op->h_meta[c];
-        const uint32_t  Kp = (m.n + m.nproj + 4 * KC - 1) / (4 * KC) * (4 * KC), Mp = (m.n + 7) & ~7u;
+        const uint32_t  kr = 4u * (uint32_t)op->kc;
+        const uint32_t  Kp = (m.n + m.nproj + kr - 1) / kr * kr, Mp = (m.n + 7) & ~7u;
         len[c]             = (unsigned long long)Kp * Mp;
       }
     DevBuf<unsigned long long> d_len, d_hash;
@@ -1180,16 +1200,9 @@ namespace hx
     hx_plan *p = op->plan;
     // m-tiles per warp: small cells (n <= 64) keep all 8 DMMA warps busy with one m-tile each
     op->mtw       = (p->max_n <= 64) ? 1 : 2;
-    // experiment (HXB200_CELL_MTW=1 / 2 overrides the choice; not yet run on a GPU for cells above 64 DoFs with one
-    // m-tile per warp): a mesh of 64-DoF cells with a few enriched 65-66-DoF cells (C1) is better served by one m-tile per
-    // warp - all eight DMMA warps busy on the common cell, a second one-tile chunk for the enriched ones
-    if (const char *e = getenv("HXB200_CELL_MTW"))
-      {
-        if (e[0] == '1')
-          op->mtw = 1;
-        else if (e[0] == '2')
-          op->mtw = 2;
-      }
+    // k-steps per pipeline stage: seven stages either way (8 KB of A + 8 rows of X with 16 m-tiles per chunk, 8 KB + 16
+    // rows with 8)
+    op->kc = (op->mtw == 2) ? 2 : 4;
     const int mpc = CWARPS * op->mtw;
     size_t    tot = 0;
     op->h_meta.resize(p->C);
@@ -1203,7 +1216,8 @@ namespace hx
         m.nproj     = op->has_nl ? op->h_ncp[c] : 0;
         m.proj_off  = poff;
         poff += m.nproj;
-        const uint32_t Kp = (m.n + m.nproj + 4 * KC - 1) / (4 * KC) * (4 * KC), Mp = (m.n + 7) & ~7u;
+        const uint32_t kr = 4u * (uint32_t)op->kc;
+        const uint32_t Kp = (m.n + m.nproj + kr - 1) / kr * kr, Mp = (m.n + 7) & ~7u;
         m.h_off = tot;
         tot += (size_t)Kp * Mp;
         op->max_kp = Kp > op->max_kp ? Kp : op->max_kp;
@@ -1239,7 +1253,7 @@ namespace hx
         if (p->C)
           {
             pack_kernel<<<p->C, 256, 0, p->stream>>>(raw, 0ull, d_raw_off.p, op->d_cell_c.p, op->d_c_off.p,
-                                                     op->d_meta.p, op->d_packed.p, 0, mpc);
+                                                     op->d_meta.p, op->d_packed.p, 0, mpc, op->kc);
             p->launches++;
           }
         HX_CUDA(cudaGetLastError());
@@ -1261,7 +1275,7 @@ namespace hx
               HX_TRY(tmp.alloc(cnt));
             HX_CUDA(cudaMemcpyAsync(tmp.p, raw + raw_off[c0], cnt * sizeof(double), cudaMemcpyHostToDevice, p->stream));
             pack_kernel<<<c1 - c0, 256, 0, p->stream>>>(tmp.p, raw_off[c0], d_raw_off.p, op->d_cell_c.p,
-                                                        op->d_c_off.p, op->d_meta.p, op->d_packed.p, c0, mpc);
+                                                        op->d_c_off.p, op->d_meta.p, op->d_packed.p, c0, mpc, op->kc);
             p->launches++;
             HX_CUDA(cudaGetLastError());
             HX_CUDA(cudaStreamSynchronize(p->stream));
@@ -1321,28 +1335,29 @@ namespace hx
     return HX_OK;
   }
 
-  template <int NT, int MTW, bool VEC, int MINB, bool FUSE, int PROD = 0>
+  template <int NT, int MTW, int KCT, bool VEC, int MINB, bool FUSE, int RB, int NACC = 1, int REGD = REG_DMMA, int REGS = REG_SCATTER>
   static int
-  launch_ordered(hx_op *op, CellArgs a)
+  launch_pipe(hx_op *op, CellArgs a)
   {
     hx_plan *    p      = op->plan;
-    auto         k      = cell_apply_ordered_kernel<NT, MTW, VEC, MINB, FUSE, PROD>;
-    const size_t budget = 225 * 1024 / MINB - 1024; // per CTA (1 KB reserved by the runtime per CTA)
-    size_t       ns     = (budget - SM_HEADER) / (size_t)stage_bytes(NT, MTW);
+    auto         k      = cell_apply_pipe_kernel<NT, MTW, KCT, VEC, MINB, FUSE, RB, NACC, REGD, REGS>;
+    const size_t budget = 227 * 1024 / MINB - 1024; // per CTA (228 KB per SM, 1 KB reserved by the runtime per CTA)
+    const size_t fixed  = SMP_HEADER + (size_t)NACC * pipe_acc_bytes(NT, MTW);
+    size_t       ns     = (budget - fixed) / (size_t)pipe_stage_bytes(NT, MTW, KCT);
     if (ns > MAX_STAGES)
       ns = MAX_STAGES;
-    const size_t smem = SM_HEADER + ns * (size_t)stage_bytes(NT, MTW);
+    const size_t smem = fixed + ns * (size_t)pipe_stage_bytes(NT, MTW, KCT);
     a.nStages         = (uint32_t)ns;
     HX_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
-    HX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, V2_THREADS, smem));
-    HX_CHECK(occ >= 1, HX_ERR_UNSUPPORTED, "ordered cell kernel does not fit on an SM (smem %zu)", smem);
+    HX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, PIPE_THREADS, smem));
+    HX_CHECK(occ >= 1, HX_ERR_UNSUPPORTED, "pipelined cell kernel does not fit on an SM (smem %zu)", smem);
     uint32_t grid = (uint32_t)(p->sm_count * std::min(occ, MINB));
     if (grid > a.nItems)
       grid = a.nItems;
     cudaEvent_t e1;
     HX_TRY(timing_begin(p, &e1));
-    HX_CUDA(launch_pdl(k, grid, V2_THREADS, smem, p->stream, a));
+    HX_CUDA(launch_pdl(k, grid, PIPE_THREADS, smem, p->stream, a));
     p->launches++;
     p->cell_launches++;
     if (e1)
@@ -1378,6 +1393,8 @@ namespace hx
     a.counters  = p->d_counters.p;
     a.B         = B;
     a.shared_a  = (op->n_unique * 2u < p->C) ? 1u : 0u;
+    a.kc        = (uint32_t)op->kc;
+    a.clk       = p->timing ? p->d_clk.p : nullptr;
     // column tile: widest of {8,16,32} columns that B needs and shared memory allows
     int  nt      = B > 16 ? 4 : (B > 8 ? 2 : 1);
     auto xtile_of = [&](int nt_) { return (size_t)op->max_kp * (nt_ * 8 + 4) * sizeof(double); };
@@ -1385,8 +1402,6 @@ namespace hx
     const bool ordered = (p->scatter_mode == 0);
     if (ordered)
       {
-        // two CTAs per SM: one scatters / waits for predecessors while the other contracts
-        const int minb = 2;
         a.nBt    = (B + nt * 8 - 1) / (nt * 8);
         a.nItems = p->C * a.nBt;
         a.epoch  = ++p->epoch;
@@ -1405,58 +1420,22 @@ namespace hx
           {
             a.f_dinv = fuse->dinv, a.f_xprev = fuse->xprev ? fuse->xprev : fuse->out, a.f_out = fuse->out;
             a.f_a = fuse->a, a.f_b = fuse->b, a.f_c = fuse->c;
-            a.f_discard = (B % (uint32_t)(nt * 8) == 0 && nt >= 2 && (((uintptr_t)Y) & 127) == 0 && !getenv("HXB200_NO_DISCARD")) ? 1u : 0u;
+            a.f_has_c = (fuse->c != 0.0) ? 1u : 0u;
+            a.f_discard = (B % (uint32_t)(nt * 8) == 0 && nt >= 2 && (((uintptr_t)Y) & 127) == 0) ? 1u : 0u;
             if (fused_applied)
               *fused_applied = true;
           }
-        // experiments on the producer warp (see PROD above): 32-column tiles, two CTAs per SM
-        const char *pa_env = getenv("HXB200_PRODUCER_ADDR");
-        const int   prod   = (pa_env && vec && nt == 4 && minb == 2) ? (pa_env[0] == '1' ? 1 : (pa_env[0] == '2' ? 2 : 0)) : 0;
-        if (prod == 2)
-          {
-            if (!p->d_zero_row.p)
-              {
-                HX_TRY(p->d_zero_row.alloc(32));
-                HX_CUDA(cudaMemsetAsync(p->d_zero_row.p, 0, 32 * sizeof(double), p->stream));
-              }
-            a.zero_row = p->d_zero_row.p;
-          }
-#define HX_ORD_X(MTW_, FUSE_) \
-  (prod == 2 ? launch_ordered<4, MTW_, true, 2, FUSE_, 2>(op, a) : launch_ordered<4, MTW_, true, 2, FUSE_, 1>(op, a))
-#define HX_ORD(NT_, MTW_, MINB_)                                                                       \
-  (fz ? ((prod && NT_ == 4 && MINB_ == 2) ? HX_ORD_X(MTW_, true) :                                     \
-                                            launch_ordered<NT_, MTW_, true, MINB_, true>(op, a)) :     \
-        (vec ? ((prod && NT_ == 4 && MINB_ == 2) ? HX_ORD_X(MTW_, false) :                             \
-                                                   launch_ordered<NT_, MTW_, true, MINB_, false>(op, a)) : \
-               launch_ordered<NT_, MTW_, false, MINB_, false>(op, a)))
-#define HX_ORD_M(NT_, MTW_) (minb == 2 ? HX_ORD(NT_, MTW_, 2) : HX_ORD(NT_, MTW_, 1))
-        // experiment (HXB200_CELL_MINB=3, NOT yet run on a GPU): three CTAs per SM for blocks of at most 8 columns, where an
-        // item is a few hundred DMMAs and its fixed latencies (claim, descriptor, predecessor wait, scatter round trip)
-        // dominate - the C1 shape.  The 8-column kernels need 60-70 registers, so three 320-thread CTAs fit an SM.
-        const char *mb_env = getenv("HXB200_CELL_MINB");
-        const bool  minb3  = mb_env && mb_env[0] == '3' && nt == 1;
+        // rows per scatter batch (loads in flight per thread): what the 40 registers of a scatter thread hold
+        constexpr int RBF = 1, RBP = 2;
+#define HX_PIPE(NT_, MTW_, KC_)                                                                     \
+  (fz ? launch_pipe<NT_, MTW_, KC_, true, 2, true, RBF>(op, a) :                                    \
+        (vec ? launch_pipe<NT_, MTW_, KC_, true, 2, false, RBP>(op, a) : launch_pipe<NT_, MTW_, KC_, false, 2, false, RBP>(op, a)))
+#define HX_PIPE_NT(MTW_, KC_) (nt == 4 ? HX_PIPE(4, MTW_, KC_) : (nt == 2 ? HX_PIPE(2, MTW_, KC_) : HX_PIPE(1, MTW_, KC_)))
         if (op->mtw == 1)
-          switch (nt)
-            {
-              case 4:
-                return HX_ORD_M(4, 1);
-              case 2:
-                return HX_ORD_M(2, 1);
-              default:
-                return minb3 ? HX_ORD(1, 1, 3) : HX_ORD_M(1, 1);
-            }
-        switch (nt)
-          {
-            case 4:
-              return HX_ORD_M(4, 2);
-            case 2:
-              return HX_ORD_M(2, 2);
-            default:
-              return minb3 ? HX_ORD(1, 2, 3) : HX_ORD_M(1, 2);
-          }
-#undef HX_ORD_M
-#undef HX_ORD
-#undef HX_ORD_X
+          return HX_PIPE_NT(1, 4);
+        return HX_PIPE_NT(2, 2);
+#undef HX_PIPE_NT
+#undef HX_PIPE
       }
     while (nt > 1 && xtile_of(nt) > 200 * 1024)
       nt >>= 1;

@@ -221,9 +221,8 @@ namespace hx
 
 namespace hx
 {
-  // the packed (fragment-major) cell-matrix stream of the cell kernel: stages of KC k-steps (4 columns each) for the
+  // the packed (fragment-major) cell-matrix stream of the cell kernel: stages of op->kc k-steps (4 columns each) for the
   // CWARPS * mtw m-tiles (8 rows each) of a chunk; see pack_kernel in cell_kernel.cu
-  constexpr int KC     = 4;
   constexpr int CWARPS = 8;
 } // namespace hx
 
@@ -260,6 +259,12 @@ namespace hx
   cheb_combine(double a, double t, double b, double xc, double c, double xp)
   {
     return __fma_rn(a, t, cheb_z(b, xc, c, xp));
+  }
+  // free row of a diagonal M^-1 (t = dinv * hx): the scale s = a*dinv is formed once per row, out = s*hx + z
+  __device__ __forceinline__ double
+  cheb_combine_diag(double a, double dinv, double hx, double b, double xc, double c, double xp)
+  {
+    return __fma_rn(__dmul_rn(a, dinv), hx, cheb_z(b, xc, c, xp));
   }
 #endif
 } // namespace hx
@@ -312,7 +317,7 @@ struct hx_plan
   hx::DevBuf<uint32_t>  d_order, d_wait_off, d_wait_list;
   hx::DevBuf<uint32_t>  d_flags;    // [C * ceil(max_block/8)] epoch stamps
   hx::DevBuf<uint32_t>  d_counters; // [0] work counter, [1] finished CTAs
-  hx::DevBuf<double>    d_zero_row; // 32 zero doubles (experimental bulk-copy gather of the cell kernel), allocated on use
+  hx::DevBuf<unsigned long long> d_clk; // [0] SM cycles, [1] ns that CTA 0 of the cell kernel ran (while kernel timing is on)
   uint32_t              epoch = 0;
   uint32_t              n_untouched = 0;
   hx::DevBuf<uint32_t>  d_untouched; // rows no cell writes (zeroed explicitly each apply)
@@ -390,6 +395,7 @@ struct hx_op
   bool                      have_matrices  = false;
   uint32_t                  max_kp = 0, max_mp = 0;
   int                       mtw = 2; // m-tiles (8 rows) per compute warp per chunk: packed layout depends on it
+  int                       kc  = 4; // k-steps (4 columns) per pipeline stage: packed layout depends on it
   // nonlocal
   bool                      has_nl = false;
   hx::Halo                  phalo;

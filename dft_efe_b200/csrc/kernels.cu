@@ -781,6 +781,18 @@ namespace hx
       }
     VD<VEC>        t;
     const uint32_t info = rowinfo[r];
+    if (info == 0xFFFFFFFFu && !(r >= ncl && nE > 0))
+      {
+        // free row of the diagonal M^-1 without hanging-node children: the form the cell kernel's epilogue uses
+        const double  d  = dinv[r];
+        const VD<VEC> sv = ldv<VEC>(s1 + i);
+        VD<VEC>       o;
+#pragma unroll
+        for (int k = 0; k < VEC; ++k)
+          o.v[k] = cheb_combine_diag(a, d, sv.v[k], b, xc.v[k], c, xp.v[k]);
+        stv<VEC>(out + i, o);
+        return;
+      }
     if (info == 0xFFFFFFFEu)
       {
 #pragma unroll

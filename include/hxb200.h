@@ -338,6 +338,9 @@ int hx_chebyshev_polynomial_degree(double unWantedSpectrumUpperBound, uint32_t *
 int hx_plan_launch_count(hx_plan *plan, uint64_t *n);
 int hx_plan_cell_kernel_time_ms(hx_plan *plan, double *ms, uint64_t *launches);
 int hx_plan_enable_kernel_timing(hx_plan *plan, int on);
+/* SM clock the cell kernel actually ran at while kernel timing was on: clock64 cycles / globaltimer nanoseconds of its
+ * CTA 0, summed over the launches (reset on read).  Shows power-cap throttling that a 1 Hz nvidia-smi sample misses. */
+int hx_plan_cell_kernel_sm_clock_mhz(hx_plan *plan, double *mhz);
 /* Phase trace: CUDA events at the phase boundaries of every apply / filter degree issued while tracing is on;
  * the report is a JSON object {"phase": {"ms": total, "n": count}, ...} (phases: x-halo, p2c+zero, nl-phase-a,
  * nl-halo, cell-kernel, shared+c2p, y-halo, cheb-rest) and clears the trace. */

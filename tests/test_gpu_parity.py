@@ -415,111 +415,10 @@ def test_programmatic_dependent_launch_is_bitwise_the_serialised_launches(capi, 
         assert np.array_equal(u, res["0"][k % 2]), f"result {k} is not reproducible"
 
 
-@pytest.mark.skipif(__import__("os").environ.get("HXB200_EXPERIMENTS") != "1",
-                    reason="experimental kernel variants (not yet run on a GPU): set HXB200_EXPERIMENTS=1")
-@pytest.mark.parametrize("B", [32, 40, 64])
-@pytest.mark.parametrize("mesh", ["full", "plain"])
-def test_experimental_producer_addressing_is_bitwise_the_default(capi, prob_full, prob_plain, mesh, B):
-    """HXB200_PRODUCER_ADDR=1 / 2 (cell_apply_ordered_kernel<..., PROD>): 1 = gather addresses computed lane-parallel and
-    shuffled, 2 = one TMA bulk copy per gathered row; what is gathered is the same, so apply and fused filter must not
-    change by a bit."""
-    import os
-    p = prob_full if mesh == "full" else prob_plain
-    deg = 6
-    a0, a, b = -3.0, 1.0, 60.0
-    plan = capi.Plan(p, max_block=B)
-    H = capi.CellOp(plan)
-    minv = capi.DiagOp(plan, p.diag_inv, p.enr_block_inv, capi.DIAG_OEFE_ATOMBLOCK)
-    X = synth.make_block(p, B)
-    res = {}
-    try:
-        for mode in ("0", "1", "2"):
-            os.environ["HXB200_PRODUCER_ADDR"] = mode
-            dX, dY = plan.block(B, X), plan.block(B)
-            H.apply(dX, dY, True, False)
-            out = [dY.download()]
-            dX, dY = plan.block(B, X), plan.block(B)
-            capi.chebyshev_filter(H, minv, dX, dY, deg, a0, a, b)
-            out.append(dY.download()[:p.n_owned])
-            res[mode] = out
-    finally:
-        os.environ.pop("HXB200_PRODUCER_ADDR", None)
-    for mode in ("1", "2"):
-        for u, v in zip(res["0"], res[mode]):
-            assert np.array_equal(u, v), f"producer variant {mode} changes the result"
-    W = orc.OracleWorld([p])
-    Xo, Yo = X.copy(), np.zeros_like(X)
-    W.hx_apply([Xo], [Yo], True, False)
-    assert rel_l2_per_vector(res["1"][0], Yo) < RTOL_HX
-
-
-@pytest.mark.skipif(__import__("os").environ.get("HXB200_EXPERIMENTS") != "1",
-                    reason="experimental kernel variants (not yet run on a GPU): set HXB200_EXPERIMENTS=1")
-@pytest.mark.parametrize("B", [1, 2, 8])
-@pytest.mark.parametrize("mesh", ["full", "plain"])
-def test_experimental_three_ctas_per_sm_is_bitwise_the_default(capi, prob_full, prob_plain, mesh, B):
-    """HXB200_CELL_MINB=3: the 8-column kernels with three CTAs per SM.  Same items, same order, same arithmetic."""
-    import os
-    p = prob_full if mesh == "full" else prob_plain
-    deg = 6
-    a0, a, b = -3.0, 1.0, 60.0
-    plan = capi.Plan(p, max_block=B)
-    H = capi.CellOp(plan)
-    minv = capi.DiagOp(plan, p.diag_inv, p.enr_block_inv, capi.DIAG_OEFE_ATOMBLOCK)
-    X = synth.make_block(p, B)
-    res = {}
-    try:
-        for mode in ("2", "3"):
-            os.environ["HXB200_CELL_MINB"] = mode
-            out = []
-            for _ in range(3):
-                dX, dY = plan.block(B, X), plan.block(B)
-                H.apply(dX, dY, True, False)
-                out.append(dY.download())
-                dX, dY = plan.block(B, X), plan.block(B)
-                capi.chebyshev_filter(H, minv, dX, dY, deg, a0, a, b)
-                out.append(dY.download()[:p.n_owned])
-            res[mode] = out
-    finally:
-        os.environ.pop("HXB200_CELL_MINB", None)
-    for u, v in zip(res["2"], res["3"]):
-        assert np.array_equal(u, v)
-
-
-@pytest.mark.skipif(__import__("os").environ.get("HXB200_EXPERIMENTS") != "1",
-                    reason="experimental kernel variants (not yet run on a GPU): set HXB200_EXPERIMENTS=1")
-@pytest.mark.parametrize("B", [3, 8, 32])
-def test_experimental_one_m_tile_per_warp_for_enriched_small_cells(capi, prob_full, B):
-    """HXB200_CELL_MTW=1 on a mesh whose enriched cells exceed 64 DoFs (order 3 + enrichment: 64..67 DoFs per cell): the
-    layout choice only regroups m-tiles into chunks, every output row keeps its k order, so the result must not change by
-    a bit against the default two-m-tiles-per-warp layout - and must match the oracle."""
-    import os
-    p = prob_full
-    assert p.num_cell_dofs.max() > 64 and p.num_cell_dofs.min() <= 64
-    X = synth.make_block(p, B)
-    res = {}
-    try:
-        for mode in ("2", "1"):
-            os.environ["HXB200_CELL_MTW"] = mode   # read when the cell matrices are packed
-            plan = capi.Plan(p, max_block=B)
-            H = capi.CellOp(plan)
-            dX, dY = plan.block(B, X), plan.block(B)
-            H.apply(dX, dY, True, False)
-            res[mode] = dY.download()
-    finally:
-        os.environ.pop("HXB200_CELL_MTW", None)
-    assert np.array_equal(res["1"], res["2"])
-    Xo, Yo = X.copy(), np.zeros_like(X)
-    orc.OracleWorld([p]).hx_apply([Xo], [Yo], True, False)
-    assert rel_l2_per_vector(res["1"], Yo) < RTOL_HX
-
-
-@pytest.mark.skipif(__import__("os").environ.get("HXB200_EXPERIMENTS") != "1",
-                    reason="experimental kernel variants (not yet run on a GPU): set HXB200_EXPERIMENTS=1")
 @pytest.mark.parametrize("B", [2, 8, 32])
-def test_experimental_split_row_list_is_bitwise_the_default(capi, prob_full, B):
-    """HXB200_SPLIT_ROWLIST=1: the row-list pass of the fused filter as two launches (rows without a child list, parent
-    rows).  Same kernels, same work per row."""
+def test_split_row_list_is_bitwise_the_single_launch(capi, prob_full, B):
+    """The row-list pass of the fused filter runs as two launches (rows without a child list, parent rows; first run on a
+    B200 in round 2); HXB200_SPLIT_ROWLIST=0 keeps the single launch.  Same kernels, same work per row."""
     import os
     p = prob_full
     deg = 7
@@ -773,8 +672,6 @@ def test_chebyshev_filter_against_reference_golden_fixture(capi):
     assert rel_l2_per_vector(dY.download()[:p.n_owned], g["F"]) < 1e-11
 
 
-@pytest.mark.skipif(__import__("os").environ.get("HXB200_EXPERIMENTS") != "1",
-                    reason="written without GPU access at the end of round 1: run once with HXB200_EXPERIMENTS=1, then un-gate")
 @pytest.mark.parametrize("B", [1, 4, 32])
 def test_hx_and_filter_periodic_wrap(capi, B):
     """BASELINE configs[3] is periodic: the wrap as one-entry constraint rows (slave -> master, weight 1; corner masters

@@ -123,6 +123,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "sweep.json"))
+    ap.add_argument("--points", default="", help="comma-separated p:B[:enr[:proj]] points instead of the full grid")
     args = ap.parse_args()
     import torch
     from dft_efe_b200 import capi, synth
@@ -137,7 +138,12 @@ def main():
     except Exception:
         pass
     points = []
-    if args.quick:
+    if args.points:
+        grid = []
+        for tok in args.points.split(","):
+            f = [int(x) for x in tok.split(":")]
+            grid.append((f[0], f[1], f[2] if len(f) > 2 else 0, f[3] if len(f) > 3 else 0))
+    elif args.quick:
         grid = [(4, 32, 0, 0), (6, 128, 0, 0), (2, 16, 0, 0), (4, 32, 16, 4)]
     else:
         grid = [(p, B, 0, 0) for p in (2, 3, 4, 5, 6, 7, 8) for B in (16, 32, 128, 512, 2048)]
@@ -152,7 +158,7 @@ def main():
         print(json.dumps(r), flush=True)
         json.dump(out, open(args.out, "w"), indent=1)
     # per-GPU shapes of the multi-GPU configs (one of 8 slabs), single GPU
-    if not args.quick:
+    if not args.quick and not args.points:
         for label, p, B, e, hg, vg in (("C3/8: benzene-dimer-like slab, order 6, B=128", 6, 128, 8, 4.5, 1.1),
                                        ("C4/8 column batch: order 5, B=256 of 1024", 5, 256, 0, 6.0, 4.0)):
             try:
