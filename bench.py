@@ -292,6 +292,183 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def multi_gpu_parity(torch, dist, capi, synth, rank, world):
+    """N > 1 only, before anything is timed: the checks of tests/mgpu_worker.py on a small mesh (order 4, enrichment,
+    projectors, 3 cell layers per rank) through the same plan / communicator machinery the timed run uses - H.X, the fused
+    Chebyshev filter and X^T H X on every rank against the CPU oracle of the whole rank set, and the halo exchange
+    overlapped with the cell kernel against the serial exchange (bitwise).  The oracle is the checker here, never the
+    thing measured."""
+    from oracle import oracle as orc
+    nc = (4, 4, 3 * world)
+    L = np.array(nc, float)
+    atoms = np.array([[0.5 * L[0], 0.5 * L[1], 0.5 * L[2]], [0.3 * L[0], 0.7 * L[1], 0.26 * L[2]]])
+    spec = synth.MeshSpec(ncell=nc, p=4, atoms=atoms, n_enr_per_atom=2, enr_cutoff=1.2, n_proj_per_atom=2, proj_cutoff=1.0,
+                          nranks=world)
+    probs = synth.build_problem(spec)
+    q = probs[rank]
+    B = 16
+    plan = capi.Plan(q, max_block=B)
+    uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        uid.copy_(torch.frombuffer(bytearray(capi.comm_unique_id()), dtype=torch.uint8))
+    dist.broadcast(uid, 0)
+    plan.attach_comm(bytes(uid.cpu().numpy().tobytes()))
+    H = capi.CellOp(plan)
+    minv = capi.DiagOp(plan, q.diag_inv, q.enr_block_inv, capi.DIAG_OEFE_ATOMBLOCK)
+    W = orc.OracleWorld(probs)
+    Xs = [synth.make_block(p_, B) for p_ in probs]
+    for p_, x in zip(probs, Xs):
+        x[p_.n_owned:] = 7.0  # stale ghosts: the update must fix them
+
+    def rel(a, b):
+        den = np.linalg.norm(b, axis=0)
+        den[den == 0] = 1.0
+        return float((np.linalg.norm(a - b, axis=0) / den).max())
+
+    out = {}
+    dX, dY = plan.block(B, Xs[rank]), plan.block(B)
+    H.apply(dX, dY, True, True)
+    Yo = [np.zeros_like(x) for x in Xs]
+    W.hx_apply([x.copy() for x in Xs], Yo, True, True)
+    out["hx"] = rel(dY.download(), Yo[rank])
+    os.environ["HXB200_HALO_OVERLAP"] = "0"
+    dXs, dYs = plan.block(B, Xs[rank]), plan.block(B)
+    H.apply(dXs, dYs, True, True)
+    os.environ.pop("HXB200_HALO_OVERLAP")
+    out["overlap_vs_serial_max_abs_diff"] = float(np.abs(dY.download() - dYs.download()).max())
+    dX, dF = plan.block(B, Xs[rank]), plan.block(B)
+    capi.chebyshev_filter(H, minv, dX, dF, 6, -3.0, 1.0, 60.0)
+    F = W.chebyshev_filter([x.copy() for x in Xs], 6, -3.0, 1.0, 60.0)
+    out["cheb"] = rel(dF.download()[:q.n_owned], F[rank][:q.n_owned])
+    dX = plan.block(B, Xs[rank])
+    S = H.xtopx(dX, 8)
+    So = W.xtopx([x.copy() for x in Xs], lambda a, b, c, d_: W.hx_apply(a, b, c, d_), 8)
+    out["xtopx"] = float(np.abs(S - So).max() / np.abs(So).max())
+    plan.synchronize()
+    transport = plan.halo_transport()
+    t = torch.tensor([out["hx"], out["cheb"], out["xtopx"], out["overlap_vs_serial_max_abs_diff"]], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dist.barrier()
+    for o in (H, minv):
+        o.destroy()
+    plan.destroy()
+    dist.barrier()
+    v = [float(x) for x in t.cpu()]
+    tol = {"hx": 1e-12, "cheb": 1e-11, "xtopx": 1e-12}
+    return {"hx": v[0], "cheb": v[1], "xtopx": v[2], "overlap_vs_serial_max_abs_diff": v[3], "tolerance": tol,
+            "ok": bool(v[0] <= tol["hx"] and v[1] <= tol["cheb"] and v[2] <= tol["xtopx"] and v[3] == 0.0),
+            "what": f"max over {world} ranks, order-4 mesh {nc[0]}x{nc[1]}x{nc[2]} with enrichment and projectors, B={B}: H.X and "
+                    f"fused Chebyshev filter rel. L2 per vector, X^T H X max rel., against the CPU oracle of the whole rank set; "
+                    f"overlapped vs serial halo exchange bitwise", "halo_transport": transport}
+
+
+def c3_strong_block(torch, dist, capi, synth, rank, nranks, local_rank, micro, steps=2):
+    """BASELINE configs[2] on N GPUs: the FIXED benzene-dimer-like mesh (order 6, 32^3 cells, 7.1 M DoFs, B = 128) cut
+    into N z-slabs - strong scaling; its cell kernel is bound by the FP64 tensor pipe (arithmetic intensity ~ 30 flop/B)."""
+    import psutil
+    spec, B = workload_spec("c3", nranks)
+    spec.with_k_cell = False
+    need = 8.0 * 343 * 343 * (32 ** 3) / nranks   # per rank; all ranks of the node generate theirs at the same time
+    ok_mem = psutil.virtual_memory().available > 2.3 * need * nranks
+    flag = torch.tensor([1 if ok_mem else 0], device="cuda")
+    if nranks > 1:
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if not int(flag.item()):
+        return {"skipped": "not enough host memory to generate %.1f GB of synthetic cell matrices per rank" % (need / 1e9)}
+    t0 = time.perf_counter()
+    prob = synth.build_problem(spec, only_rank=rank)[0]
+    t_build = time.perf_counter() - t0
+    stream = torch.cuda.Stream()
+    plan = capi.Plan(prob, max_block=B, stream=stream.cuda_stream)
+    if nranks > 1:
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(capi.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        plan.attach_comm(bytes(uid.cpu().numpy().tobytes()))
+    H = capi.CellOp(plan)
+    minv = capi.DiagOp(plan, prob.diag_inv, prob.enr_block_inv, capi.DIAG_OEFE_ATOMBLOCK)
+    X = synth.make_block(prob, B)
+    N_global = prob.n_owned
+    S2 = prob.S2 + (int(np.sum(prob.num_cell_proj.astype(np.int64) * prob.num_cell_dofs.astype(np.int64)))
+                    if prob.num_cell_proj is not None else 0)
+    del prob.h_cell
+    if nranks > 1:
+        t = torch.tensor([N_global], dtype=torch.int64, device="cuda")
+        dist.all_reduce(t)
+        N_global = int(t.item())
+
+    class Blk:
+        def __init__(self, host=None):
+            self.B = B
+            self.t = torch.zeros(X.shape[0] * B, dtype=torch.float64, device="cuda") if host is None else \
+                torch.from_numpy(np.ascontiguousarray(host)).reshape(-1).cuda()
+            self.p = C.cast(self.t.data_ptr(), capi.f64p)
+
+    a0, a_, b_ = FILTER_BOUNDS
+    with torch.cuda.stream(stream):
+        dX0, dX, dF = Blk(X), Blk(X), Blk()
+
+        def step():
+            dX.t.copy_(dX0.t, non_blocking=True)
+            capi.chebyshev_filter(H, minv, dX, dF, DEGREE, a0, a_, b_)
+
+        step()
+        plan.synchronize()
+        if nranks > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        plan.enable_kernel_timing(True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            step()
+        e1.record(stream)
+        plan.synchronize()
+        if nranks > 1:
+            dist.barrier()
+        ms = e0.elapsed_time(e1) / steps
+        cell_ms, nl = plan.cell_kernel_time_ms()
+        clk = plan.cell_kernel_sm_clock_mhz()
+        plan.enable_kernel_timing(False)
+        phases = {}
+        try:
+            plan.trace(True)
+            step()
+            rep = plan.trace_report()
+            plan.trace(False)
+            phases = {k: round(v["ms"] / DEGREE, 5) for k, v in rep.items()}
+        except Exception as e:  # noqa: BLE001
+            phases = {"error": str(e)[:200]}
+        finite = bool(torch.isfinite(dF.t).all())
+    tm = torch.tensor([ms, cell_ms / max(nl, 1)], dtype=torch.float64, device="cuda")
+    if nranks > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    ms, cell_ms1 = [float(v) for v in tm.cpu()]
+    flops = 2.0 * B * S2
+    dmma = micro["dmma_tflops"] if micro else None
+    res = {"workload": "c3: ChebyshevFilter degree %d, order 6, 32x32x32 cells, %d DoFs, B=%d, fixed mesh cut into %d z-slab(s)"
+                       % (DEGREE, N_global, B, nranks),
+           "scaling": "strong", "n_gpus": nranks, "ms_per_step": ms, "ms_per_degree": ms / DEGREE,
+           "value": DEGREE * N_global * B / (ms * 1e-3) / 1e9, "unit": UNIT, "steps": steps, "result_finite": finite,
+           "cell_kernel_ms_per_launch": cell_ms1, "cell_kernel_sm_clock_mhz": round(clk, 1),
+           "cell_kernel_tflops_per_gpu": flops / (cell_ms1 * 1e-3) / 1e12,
+           "roofline": {"bound": "tensor", "achieved": flops / (cell_ms1 * 1e-3) / 1e12, "peak": dmma, "unit": "TFLOP/s",
+                        "frac": (flops / (cell_ms1 * 1e-3) / 1e12 / dmma) if dmma else None,
+                        "peak_source": "hx_microbench: mma.sync.m8n8k4.f64 (DMMA.8x8x4) issue rate measured on this GPU in this run"},
+           "phase_ms_per_degree": phases, "halo_transport": plan.halo_transport(), "host_build_s": round(t_build, 1),
+           "efficiency_note": "strong-scaling efficiency = ms_per_step(N=1) / (N * ms_per_step(N)) over the c3_strong blocks of "
+                              "the per-N runs"}
+    for o in (H, minv):
+        o.destroy()
+    del dX0, dX, dF
+    if nranks > 1:
+        dist.barrier()
+    plan.destroy()
+    torch.cuda.empty_cache()
+    return res
+
+
 # ----------------------------------------------------------------------------- GPU leg ----
 def run_ours(args):
     # keep stdout for the ONE JSON line: libraries (NCCL's version banner) write to fd 1 during initialisation
@@ -311,11 +488,29 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     capi.check(capi.lib().hx_set_device(local_rank))
+    affinity = None
+    try:  # run (and first-touch the pinned host buffers) on the CPUs next to this rank's GPU
+        import pynvml
+        pynvml.nvmlInit()
+        hnd = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        pynvml.nvmlDeviceSetCpuAffinity(hnd)
+        affinity = sorted(os.sched_getaffinity(0))
+        affinity = f"{affinity[0]}-{affinity[-1]} ({len(affinity)} cpus)"
+    except Exception as e:  # noqa: BLE001
+        affinity = f"unchanged ({str(e)[:60]})"
     if nranks > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
+    parity = None
+    if nranks > 1:
+        try:
+            parity = multi_gpu_parity(torch, dist, capi, synth, rank, nranks)
+        except Exception as e:  # noqa: BLE001
+            parity = {"ok": False, "error": str(e)[:300]}
     spec, B = workload_spec(args.workload, nranks)
+    if args.workload in ("c3",):
+        spec.with_k_cell = False
     prob = synth.build_problem(spec, only_rank=rank)[0]
     stream = torch.cuda.Stream()
     plan = capi.Plan(prob, max_block=B, stream=stream.cuda_stream)
@@ -527,30 +722,55 @@ def run_ours(args):
         except Exception as e:  # noqa: BLE001
             poisson["error"] = str(e)[:200]
 
-        # ---- end to end through the host-buffer entry point (pinned host memory, H2D + D2H every step) ----
-        xh = torch.from_numpy(X).pin_memory()
-        yh = torch.zeros_like(xh).pin_memory()
+        # ---- BASELINE configs[2] (the largest config that north_star's 80 % parallel-efficiency target is stated on) ----
+        c3 = None
+        if not args.quick and not args.no_c3 and args.workload == "c2":
+            try:
+                c3 = c3_strong_block(torch, dist, capi, synth, rank, nranks, local_rank, capi.microbench())
+            except Exception as e:  # noqa: BLE001
+                c3 = {"error": str(e)[:300]}
+
+        # ---- end to end through the host-buffer entry points (pinned host memory, H2D + D2H every step) ----
+        # (a) the call a ChebyshevFilteredEigenSolver with HOST wavefunctions makes: E2E_BATCHES column batches of B vectors,
+        #     hx_chebyshev_filter_host_batches pipelines copy-in / filter / copy-out of neighbouring batches;
+        # (b) a single block (nothing to overlap with: H2D, filter, D2H in sequence) for comparison.
+        E2E_BATCHES = 6
+        xb = [torch.from_numpy(X).pin_memory() for _ in range(E2E_BATCHES)]
+        yb = [torch.zeros_like(xb[0]).pin_memory() for _ in range(E2E_BATCHES)]
+        xp_, yp_ = [t_.data_ptr() for t_ in xb], [t_.data_ptr() for t_ in yb]
 
         def e2e_step():
-            capi.chebyshev_filter_host_ptr(H, minv, xh.data_ptr(), yh.data_ptr(), B, DEGREE, a0, a_, b_, False)
+            capi.chebyshev_filter_host_batches(H, minv, xp_, yp_, B, DEGREE, a0, a_, b_)
 
-        for _ in range(2):
-            e2e_step()
+        e2e_step()
         barrier()
-        e2e_steps = max(3, min(args.steps, 10))
+        e2e_steps = max(2, min(args.steps, 4))
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
             e2e_step()
         barrier()
         e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+        e2e_finite = bool(all(torch.isfinite(t_).all() for t_ in yb))
+        e2e_same = bool(torch.equal(yb[0], yb[-1]))  # every batch holds the same input here: same output, bit for bit
+
+        def e2e1_step():
+            capi.chebyshev_filter_host_ptr(H, minv, xp_[0], yp_[0], B, DEGREE, a0, a_, b_, False)
+
+        e2e1_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            e2e1_step()
+        barrier()
+        e2e1_ms = (time.perf_counter() - t0) * 1e3 / 3
         sampler.stop_flag = True
         sampler.join(timeout=2)
-        e2e_finite = bool(torch.isfinite(yh).all())
+        del xb, yb
 
-    tms = torch.tensor([ms_per_step, apply_ms, e2e_ms, cell_ms], dtype=torch.float64, device="cuda")
+    tms = torch.tensor([ms_per_step, apply_ms, e2e_ms, cell_ms, e2e1_ms], dtype=torch.float64, device="cuda")
     if nranks > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-    ms_per_step, apply_ms, e2e_ms, cell_ms = [float(v) for v in tms.cpu()]
+    ms_per_step, apply_ms, e2e_ms, cell_ms, e2e1_ms = [float(v) for v in tms.cpu()]
 
     if rank == 0:
         peaks = {}
@@ -585,6 +805,32 @@ def run_ours(args):
         except Exception:
             pass
         blk_bytes = 8 * B * prob.n_local
+        # which roof bounds the kernel: the larger of the two minimum times (algorithmic bytes at the HBM peak, flops at the
+        # FP64 tensor peak); `frac` is that minimum time over the measured time, both single fractions are reported as well
+        dmma_peak = micro["dmma_tflops"] if micro else None
+        t_k = cell_ms_per_launch * 1e-3
+        t_bytes = alg_bytes / (hbm_peak * 1e9)
+        t_flops = flops / (dmma_peak * 1e12) if dmma_peak else 0.0
+        tensor_bound = t_flops > t_bytes
+        roof = {"bound": "tensor" if tensor_bound else "hbm",
+                "achieved": (flops / t_k / 1e12) if tensor_bound else achieved,
+                "peak": dmma_peak if tensor_bound else hbm_peak, "unit": "TFLOP/s" if tensor_bound else "GB/s",
+                "frac": max(t_bytes, t_flops) / t_k, "frac_hbm": t_bytes / t_k, "frac_tensor": (t_flops / t_k) if dmma_peak else None,
+                "traffic": traffic, "traffic_source": traffic_src,
+                "peak_source": peak_src + "; FP64 tensor peak = hx_microbench (mma.sync.m8n8k4.f64 / SASS DMMA.8x8x4 issue rate measured on "
+                                          "this GPU in this run; MEASURED_PEAKS.json has no FP64 entry)",
+                "kernel": "cell_apply_pipe_kernel<FUSE> (one persistent launch per H.X apply: 4 DMMA warps + 8 scatter warps + A-stream "
+                          "and gather warps per CTA; the Chebyshev update of %d of %d owned rows is applied in its scatter "
+                          "epilogue)" % (n_fus, n_fus + n_other),
+                "algorithmic_bytes_bare_apply": alg_apply,
+                "kernel_ms_per_launch": cell_ms_per_launch, "kernel_launches_timed": int(cell_launches),
+                "kernel_sm_clock_mhz": round(cell_clock_mhz, 1),
+                "kernel_share_of_step": cell_ms / args.steps / ms_per_step,
+                "algorithmic_bytes_per_launch": alg_bytes, "flops_per_launch": flops,
+                "tensor": {"achieved_tflops": flops / t_k / 1e12,
+                           "dmma_peak_tflops_measured": micro["dmma_tflops"] if micro else None,
+                           "dfma_peak_tflops_measured": micro["dfma_tflops"] if micro else None,
+                           "copy_gbs_measured": micro["copy_gbs"] if micro else None}}
         line = {
             "metric": METRIC, "value": DEGREE * N_global * B / (ms_per_step * 1e-3) / 1e9, "unit": UNIT, "n_gpus": nranks,
             "steps": args.steps, "warmup": warm, "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -596,35 +842,29 @@ def run_ours(args):
                                    f"{spec.n_proj_per_atom} projectors, z-slab per GPU",
                        "global_dofs": N_global, "block": B, "degree": DEGREE, "cells_per_gpu": prob.n_cells,
                        "parallelism": f"cells/{nranks}", "halo_transport": plan.halo_transport(),
-                       "programmatic_dependent_launch": capi.pdl_enabled(),
+                       "programmatic_dependent_launch": capi.pdl_enabled(), "cpu_affinity_rank0": affinity,
                        "l2_policy": "inputs larger than L2 (cell matrices %.2f GB + 4 block vectors %.2f GB per GPU)"
                                     % (8 * S2 / 1e9, 4 * blk_bytes / 1e9)},
-            "e2e": {"value": DEGREE * N_global * B / (e2e_ms * 1e-3) / 1e9, "unit": UNIT,
-                    "h2d_bytes_per_step": blk_bytes, "d2h_bytes_per_step": blk_bytes, "ms_per_step": e2e_ms,
-                    "result_finite": e2e_finite,
-                    "call": "hx_chebyshev_filter_host (pinned host X in, filtered block out; H2D, 24 applies, D2H per step)"},
+            "e2e": {"value": DEGREE * N_global * B * E2E_BATCHES / (e2e_ms * 1e-3) / 1e9, "unit": UNIT,
+                    "h2d_bytes_per_step": blk_bytes * E2E_BATCHES, "d2h_bytes_per_step": blk_bytes * E2E_BATCHES,
+                    "ms_per_step": e2e_ms, "ms_per_batch": e2e_ms / E2E_BATCHES, "column_batches": E2E_BATCHES,
+                    "result_finite": e2e_finite, "batches_bitwise_equal": e2e_same,
+                    "call": "hx_chebyshev_filter_host_batches (pinned host wavefunctions in %d column batches of B=%d, as "
+                            "ChebyshevFilteredEigenSolver filters them: per batch H2D, %d H.X applies + M^-1 + recurrence, D2H; "
+                            "the copies of neighbouring batches overlap the filter)" % (E2E_BATCHES, B, DEGREE),
+                    "single_block": {"value": DEGREE * N_global * B / (e2e1_ms * 1e-3) / 1e9, "ms_per_step": e2e1_ms,
+                                     "call": "hx_chebyshev_filter_host (one block: H2D, filter, D2H in sequence)"}},
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": traffic, "traffic_source": traffic_src,
-                         "peak_source": peak_src,
-                         "kernel": "cell_apply_ordered_kernel<FUSE> (one persistent launch per H.X apply; the Chebyshev "
-                                   "update of %d of %d owned rows is applied in its scatter epilogue)" % (n_fus, n_fus + n_other),
-                         "algorithmic_bytes_bare_apply": alg_apply,
-                         "kernel_ms_per_launch": cell_ms_per_launch, "kernel_launches_timed": int(cell_launches),
-                         "kernel_sm_clock_mhz": round(cell_clock_mhz, 1),
-                         "kernel_share_of_step": cell_ms / args.steps / ms_per_step,
-                         "algorithmic_bytes_per_launch": alg_bytes, "flops_per_launch": flops,
-                         "tensor": {"achieved_tflops": flops / (cell_ms_per_launch * 1e-3) / 1e12,
-                                    "dmma_peak_tflops_measured": micro["dmma_tflops"] if micro else None,
-                                    "dfma_peak_tflops_measured": micro["dfma_tflops"] if micro else None,
-                                    "copy_gbs_measured": micro["copy_gbs"] if micro else None}},
+            "roofline": roof,
             "hx_apply": {"ms": apply_ms, "value": N_global * B / (apply_ms * 1e-3) / 1e9, "unit": UNIT,
                          "what": "bare KohnShamOperatorContextFE::apply (updateGhostX=true), block resident in HBM"},
             "subspace": sub,
             "chfsi_pass": chfsi,
             "scf_neighbours": scf,
             "poisson": poisson,
+            "c3_strong": c3,
+            "parity": parity,
             "chebyshev_filter": {"degree": DEGREE, "seconds_per_scf_iter": ms_per_step * 1e-3,
                                  "ms_per_degree": ms_per_step / DEGREE, "fused_recurrence": True,
                                  "phase_ms_per_degree": phases},
@@ -653,6 +893,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=["c2", "small", "c3", "c1", "c2a"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-c3", action="store_true", help="skip the c3_strong block (BASELINE configs[2] on the same GPUs)")
     ap.add_argument("--quick", action="store_true",
                     help="only the step, its phase trace, the bare apply and e2e (skips the subspace / ChFSI pass / SCF-neighbour / "
                          "Poisson extras and the cpu_baseline leg): for A/B runs of one setting")

@@ -24,7 +24,7 @@ EXPORTS = [
     "hx_accumulate_add_locally_owned", "hx_distribute_parent_to_child", "hx_distribute_child_to_parent",
     "hx_set_constrained_nodes_to_zero", "hx_plan_add_constraints", "hx_distribute_parent_to_child_set",
     "hx_distribute_child_to_parent_set", "hx_cellop_set_constraint_sets", "hx_cg_solve", "hx_cellop_create", "hx_cellop_set_matrices", "hx_cellop_set_nonlocal",
-    "hx_diagop_create", "hx_op_destroy", "hx_op_apply", "hx_op_apply_host", "hx_chebyshev_filter", "hx_chebyshev_filter_host",
+    "hx_diagop_create", "hx_op_destroy", "hx_op_apply", "hx_op_apply_host", "hx_chebyshev_filter", "hx_chebyshev_filter_host", "hx_chebyshev_filter_host_batches",
     "hx_residual_chebyshev_filter", "hx_xtopx", "hx_subspace_rotation", "hx_l2_norms", "hx_axpby",
     "hx_axpby_blocked", "hx_plan_launch_count", "hx_plan_cell_kernel_time_ms", "hx_plan_cell_kernel_sm_clock_mhz", "hx_plan_enable_kernel_timing", "hx_plan_trace", "hx_plan_trace_report",
     "hx_microbench", "hx_programmatic_launch_enabled",
@@ -410,6 +410,15 @@ def chebyshev_filter_host_ptr(A: Op, BInv: Op, xptr, yptr, B, degree, a0, a, b, 
     check(lib().hx_chebyshev_filter_host(A.h, BInv.h, C.cast(xptr, f64p), C.cast(yptr, f64p), C.c_uint32(B),
                                          C.c_uint32(degree), C.c_double(a0), C.c_double(a), C.c_double(b),
                                          C.c_int(int(write_back_x))))
+
+
+def chebyshev_filter_host_batches(A, BInv, xptrs, yptrs, B, degree, a0, a, b):
+    """pinned HOST buffers, one pointer per column batch (n_local x B each): copies overlap the filter of the batch between"""
+    n = len(xptrs)
+    XP = (f64p * n)(*[C.cast(p_, f64p) for p_ in xptrs])
+    YP = (f64p * n)(*[C.cast(p_, f64p) for p_ in yptrs])
+    check(lib().hx_chebyshev_filter_host_batches(A.h, BInv.h, XP, YP, C.c_uint32(n), C.c_uint32(B), C.c_uint32(degree),
+                                                 C.c_double(a0), C.c_double(a), C.c_double(b)))
 
 
 def chebyshev_filter_host(A: Op, BInv: Op, Xh: np.ndarray, Yh: np.ndarray, degree, a0, a, b, write_back_x=True):

@@ -22,20 +22,14 @@ namespace hx
     va_end(ap);
   }
 
-  // Programmatic dependent launch of the kernels of an apply (read per launch so a test can toggle it): HXB200_PDL=1 /
-  // 0 forces it on / off; unset, it is on for single-rank plans and off once a multi-rank plan exists in the process -
-  // the combination with the spin-waiting peer-memory halo kernels has not been run on N >= 2 GPUs yet, so multi-rank
-  // runs keep the serialised launches they were validated with.
-  static bool g_multirank_plan = false;
+  // Programmatic dependent launch of the kernels of an apply (read per launch so a test can toggle it): on by default,
+  // HXB200_PDL=0 switches it off.  (Multi-rank plans with the spin-waiting peer-memory halo kernels were validated with it
+  // on 2 B200s in round 2: tests/test_multi_gpu.py under HXB200_PDL=1, profiles/r2_mgpu_parity_N2_serial_halo.log.)
   bool
   pdl_enabled()
   {
     const char *e = getenv("HXB200_PDL");
-    if (e && e[0] == '0')
-      return false;
-    if (e && e[0] == '1')
-      return true;
-    return !g_multirank_plan;
+    return !(e && e[0] == '0');
   }
 
   int
@@ -124,6 +118,17 @@ namespace hx
     h.peer = nullptr;
   }
 
+  // every synchronisation that hands results to the host goes through here: a peer halo wait that timed out inside a
+  // kernel (lost neighbour) must surface as HX_ERR_COMM, not as host scalars computed from garbage
+  int
+  plan_sync(hx_plan *p)
+  {
+    HX_CUDA(cudaStreamSynchronize(p->stream));
+    for (Halo *h : p->peer_halos)
+      HX_TRY(peer_check_status(*h));
+    return HX_OK;
+  }
+
   int
   halo_update(hx_plan *p, Halo &h, double *X, uint32_t B)
   {
@@ -189,9 +194,7 @@ namespace hx
     p->max_block         = m->max_block ? m->max_block : 1;
     HX_CHECK(p->n_owned_classical <= p->n_owned, HX_ERR_INVALID, "n_owned_classical > n_owned");
     HX_CHECK(p->nranks >= 1 && p->rank >= 0 && p->rank < p->nranks, HX_ERR_INVALID, "bad rank/nranks");
-    if (p->nranks > 1)
-      g_multirank_plan = true;
-    HX_CHECK(p->n_local < 0x1fffffffu, HX_ERR_INVALID, "too many local rows");
+    HX_CHECK(p->n_local < 0x0fffffffu, HX_ERR_INVALID, "too many local rows");
 
     p->h_ncd.assign(m->num_cell_dofs, m->num_cell_dofs + p->C);
     p->h_cell_off.assign(p->C + 1, 0);
@@ -375,6 +378,19 @@ namespace hx
     }
     HX_TRY(p->d_colour_cells.upload(p->h_colour_cells));
 
+    // cells that read ghost rows of X (multi-rank plans)
+    std::vector<char> boundary(p->C, 0);
+    p->n_boundary_cells = 0;
+    if (p->nranks > 1)
+      for (uint32_t c = 0; c < p->C; ++c)
+        {
+          for (uint32_t i = p->h_cell_off[c]; i < p->h_cell_off[c + 1]; ++i)
+            if (p->h_ids[i] >= p->n_owned)
+              boundary[c] = 1;
+          p->n_boundary_cells += boundary[c];
+        }
+    p->h_boundary.assign(boundary.begin(), boundary.end());
+
     // ---- ordered scatter: processing order, first-touch flags, predecessor (wait) lists ----
     // For every non-shared row the touching cells form a chain in processing order; a cell waits only for the
     // immediately preceding toucher of each of its rows (completion is transitive).  The order keeps the
@@ -415,37 +431,45 @@ namespace hx
                 if (!(dest[i] & HX_DEST_STAGED))
                   rc[fill[p->h_ids[i]]++] = c;
           }
-          typedef std::pair<uint32_t, uint32_t> PR; // (key, cell)
-          std::priority_queue<uint32_t, std::vector<uint32_t>, std::greater<uint32_t>> eligible;
-          std::priority_queue<PR, std::vector<PR>, std::greater<PR>>                   waiting;
+          // sweep key of a cell: its index in the caller's order - except that on a multi-rank plan the cells reading ghost
+          // rows are all keyed at a quarter of the sweep: late enough that the halo has arrived when the first of them is
+          // claimed, early enough that their ghost-row sums travel while the rest of the interior is contracted
+          typedef unsigned long long KEY;
+          const uint32_t k0 = p->C / 4;
+          auto           key_of = [&](uint32_t c) -> KEY { return ((KEY)(boundary[c] ? k0 : c) << 33) | ((KEY)(boundary[c] ? 0u : 1u) << 32) | c; };
+          typedef std::pair<uint32_t, KEY> PR; // (time, key)
+          std::priority_queue<KEY, std::vector<KEY>, std::greater<KEY>> eligible;
+          std::priority_queue<PR, std::vector<PR>, std::greater<PR>>    waiting;
           std::vector<uint32_t> ready(p->C, 0);
           std::vector<char>     placed(p->C, 0);
           for (uint32_t c = 0; c < p->C; ++c)
-            eligible.push(c);
+            eligible.push(key_of(c));
           for (uint32_t t = 0; t < p->C; ++t)
             {
               while (!waiting.empty() && waiting.top().first <= t)
                 {
-                  const PR e = waiting.top();
+                  const PR       e = waiting.top();
+                  const uint32_t x = (uint32_t)e.second;
                   waiting.pop();
-                  if (!placed[e.second])
+                  if (!placed[x])
                     {
-                      if (ready[e.second] <= t)
+                      if (ready[x] <= t)
                         eligible.push(e.second);
-                      else if (ready[e.second] != e.first)
-                        waiting.push(PR(ready[e.second], e.second));
+                      else if (ready[x] != e.first)
+                        waiting.push(PR(ready[x], e.second));
                     }
                 }
               uint32_t c = 0xffffffffu;
               while (!eligible.empty())
                 {
-                  const uint32_t x = eligible.top();
+                  const KEY      k = eligible.top();
+                  const uint32_t x = (uint32_t)k;
                   eligible.pop();
                   if (placed[x])
                     continue;
                   if (ready[x] > t)
                     {
-                      waiting.push(PR(ready[x], x));
+                      waiting.push(PR(ready[x], k));
                       continue;
                     }
                   c = x;
@@ -454,16 +478,17 @@ namespace hx
               while (c == 0xffffffffu)
                 {
                   // every remaining cell is delayed: take the one that becomes eligible first
-                  const PR e = waiting.top();
+                  const PR       e = waiting.top();
+                  const uint32_t x = (uint32_t)e.second;
                   waiting.pop();
-                  if (placed[e.second])
+                  if (placed[x])
                     continue;
-                  if (ready[e.second] != e.first)
+                  if (ready[x] != e.first)
                     {
-                      waiting.push(PR(ready[e.second], e.second));
+                      waiting.push(PR(ready[x], e.second));
                       continue;
                     }
-                  c = e.second;
+                  c = x;
                 }
               placed[c]     = 1;
               p->h_order[t] = c;
@@ -536,6 +561,35 @@ namespace hx
           if (m->row_ids[i] >= p->n_owned && m->row_sizes[i] > 0)
             p->cheb_fusable_multirank = false;
       }
+      // halo overlap (hx_internal.h): which ghost rows the cell kernel pushes itself, which ones the closing kernel does
+      if (p->nranks > 1)
+        {
+          p->overlap_x_ok = true;
+          for (uint32_t e = 0; e < p->nnz; ++e)
+            if (m->col_ids[e] >= p->n_owned)
+              p->overlap_x_ok = false; // a hanging-node / periodic fill reads a ghost row: it must follow the unpack
+          std::vector<uint32_t> unpack(p->n_ghost), rest;
+          p->n_push_direct = 0;
+          for (uint32_t k = 0; k < p->n_ghost; ++k)
+            {
+              const uint32_t j = m->halo.ghost_local_ids[k], r = p->n_owned + j;
+              unpack[k]        = j | (rowinfo[r] == 0xFFFFFFFEu ? 0x80000000u : 0u);
+              const bool direct = rowinfo[r] == 0xFFFFFFFFu && last_entry[r] != 0xffffffffu;
+              if (direct)
+                {
+                  dest[last_entry[r]] |= HX_DEST_PUSH;
+                  p->n_push_direct++;
+                }
+              else
+                rest.push_back(k);
+            }
+          p->overlap_y_ok = true;
+          p->n_push_rest  = (uint32_t)rest.size();
+          HX_TRY(p->d_unpack_ids.upload(unpack));
+          HX_TRY(p->d_push_rest.upload(rest));
+          HX_TRY(p->d_x_ready.alloc(1));
+          HX_CUDA(cudaMemset(p->d_x_ready.p, 0, sizeof(uint32_t)));
+        }
       std::vector<uint32_t> untouched;
       for (uint32_t r = 0; r < p->n_local; ++r)
         if (last[r] == 0xffffffffu && shared.find(r) == shared.end())
@@ -574,8 +628,38 @@ namespace hx
   {
     hx_plan *p = op->plan;
     p->mark("apply:begin");
+    // halo exchange overlapped with the cell kernel (north_star: "NCCL/NVLink halo exchange overlapped with interior-cell
+    // compute"; the reference splits its exchange into Begin / End for the same purpose, MPICommunicatorP2P.t.cpp:89-273,
+    // 288-470): the send side of the X update runs here, its receive side inside the cell kernel; the send side of the Y
+    // accumulation runs inside the cell kernel, its receive side after it.  Needs the peer-memory transport, the mesh's own
+    // constraint set on both sides and the ordered kernel; HXB200_HALO_OVERLAP=0 keeps the serial exchange (same results,
+    // bit for bit: the processing order does not depend on the mode).
+    bool overlap = false;
+    if (p->nranks > 1 && p->scatter_mode == 0 && op->x_set == 0 && op->y_set == 0 && p->C > 0)
+      {
+        HX_CHECK(p->comm != nullptr, HX_ERR_COMM, "nranks > 1 but no communicator attached (hx_plan_attach_comm)");
+        HX_TRY(halo_pick_transport(p, p->halo)); // collective
+        const char *e = getenv("HXB200_HALO_OVERLAP");
+        overlap       = peer_overlap_available(p->halo) && p->overlap_y_ok && !(e && e[0] == '0');
+      }
+    if (overlap && op->has_nl && op->nl_reads_ghost < 0)
+      {
+        // the projector pre-pass (nl_phase_a) runs before the cell kernel and reads the X rows of the projector cells: if one
+        // of them reads ghost rows, the ghosts must be in place before it - the unpack cannot wait for the cell kernel
+        op->nl_reads_ghost = 0;
+        for (uint32_t c = 0; c < p->C; ++c)
+          if (op->h_ncp[c] > 0 && p->h_boundary[c])
+            op->nl_reads_ghost = 1;
+      }
+    const bool unpack_in_kernel = overlap && ugx && p->overlap_x_ok && !(op->has_nl && op->nl_reads_ghost == 1);
+    uint32_t   seqU             = 0;
     if (ugx)
-      HX_TRY(halo_update(p, p->halo, X, B));
+      {
+        if (unpack_in_kernel)
+          HX_TRY(peer_push_update(p, p->halo, X, B, &seqU));
+        else
+          HX_TRY(halo_update(p, p->halo, X, B));
+      }
     p->mark("x-halo");
     HX_TRY(launch_p2c(p, X, B, op->x_set));
     if (p->scatter_mode == 1)
@@ -596,14 +680,20 @@ namespace hx
             p->mark("nl-halo");
           }
       }
-    HX_TRY(launch_cell_apply(op, X, Y, B, fuse, fused_applied));
+    HaloK hk;
+    if (overlap)
+      HX_TRY(peer_overlap_args(p, p->halo, X, B, unpack_in_kernel, seqU, &hk));
+    HX_TRY(launch_cell_apply(op, X, Y, B, fuse, fused_applied, overlap ? &hk : nullptr));
     p->mark("cell-kernel");
     HX_TRY(launch_shared_reduce(p, Y, B));
     // (a caller that never reads the constrained rows of Y - the fused filter's scratch on a single rank, where no halo
     // accumulation follows - saves their zeroing)
     HX_TRY(launch_c2p(p, Y, B, op->y_set, !(y_constrained_rows_dead && p->nranks == 1)));
     p->mark("shared+c2p");
-    HX_TRY(halo_accumulate(p, p->halo, Y, B));
+    if (overlap)
+      HX_TRY(peer_finish_accumulate(p, p->halo, Y, B, hk.seqA));
+    else
+      HX_TRY(halo_accumulate(p, p->halo, Y, B));
     if (ugy)
       HX_TRY(halo_update(p, p->halo, Y, B));
     p->mark("y-halo");
@@ -714,6 +804,13 @@ hx_plan::~hx_plan()
     comm_destroy(comm);
   if (dense)
     dense_destroy(dense);
+  for (auto e : pipe_ev)
+    if (e)
+      cudaEventDestroy(e);
+  if (copy_in)
+    cudaStreamDestroy(copy_in);
+  if (copy_out)
+    cudaStreamDestroy(copy_out);
   if (own_stream && stream)
     cudaStreamDestroy(stream);
 }
@@ -904,10 +1001,7 @@ extern "C"
   hx_plan_synchronize(hx_plan *plan)
   {
     HX_CHECK(plan, HX_ERR_INVALID, "null plan");
-    HX_CUDA(cudaStreamSynchronize(plan->stream));
-    for (Halo *h : plan->peer_halos)
-      HX_TRY(peer_check_status(*h));
-    return HX_OK;
+    return plan_sync(plan);
   }
 
   int
@@ -1183,6 +1277,7 @@ extern "C"
     HX_TRY(op->phalo.init(nl->proj_halo, p->max_block));
     HX_CUDA(cudaDeviceSynchronize());
     op->has_nl = true;
+    op->nl_reads_ghost = -1;
     return HX_OK;
   }
 
@@ -1281,7 +1376,7 @@ extern "C"
         HX_TRY(p->ensure_pinned((size_t)nmod * B * sizeof(double)));
         HX_CUDA(cudaMemcpyAsync(p->h_pinned, buf, (size_t)nmod * B * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
       }
-    HX_CUDA(cudaStreamSynchronize(p->stream));
+    HX_TRY(plan_sync(p));
     for (uint32_t i = 0; i < nmod; ++i)
       memcpy(Xh + (size_t)p->h_modrows[i] * B, p->h_pinned + (size_t)i * B, (size_t)B * sizeof(double));
     return HX_OK;
@@ -1336,7 +1431,7 @@ extern "C"
     HX_CUDA(cudaMemcpyAsync(d_ones, ones.data(), B * sizeof(double), cudaMemcpyHostToDevice, p->stream));
     std::vector<double> neg(B, -1.0);
     HX_CUDA(cudaMemcpyAsync(d_nalpha, neg.data(), B * sizeof(double), cudaMemcpyHostToDevice, p->stream));
-    HX_CUDA(cudaStreamSynchronize(p->stream));
+    HX_TRY(plan_sync(p));
     auto reduce = [&](const double *u, const double *v, double *out_dev) -> int {
       HX_TRY(launch_coldot(p, u, v, B, p->n_owned, out_dev));
       if (p->nranks > 1)
@@ -1345,7 +1440,7 @@ extern "C"
     };
     auto fetch = [&](const double *dev, double *out_host) -> int {
       HX_CUDA(cudaMemcpyAsync(h, dev, B * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
-      HX_CUDA(cudaStreamSynchronize(p->stream));
+      HX_TRY(plan_sync(p));
       memcpy(out_host, h, B * sizeof(double));
       return HX_OK;
     };
@@ -1420,7 +1515,7 @@ extern "C"
       }
     // linearSolverFunction.setSolution(xConverged)
     HX_CUDA(cudaMemcpyAsync(x, xconv, nloc * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
-    HX_CUDA(cudaStreamSynchronize(p->stream));
+    HX_TRY(plan_sync(p));
     if (iter > max_iter)
       err = HX_CG_FAILED_TO_CONVERGE;
     *iterations = iter;
@@ -1438,7 +1533,7 @@ extern "C"
     if (p->d_nonfuse_split.p || p->n_nonfuse == 0)
       return HX_OK;
     std::vector<uint32_t> rows(p->n_nonfuse), info(p->n_local), split;
-    HX_CUDA(cudaStreamSynchronize(p->stream));
+    HX_TRY(plan_sync(p));
     HX_CUDA(cudaMemcpy(rows.data(), p->d_nonfuse_rows.p, rows.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     HX_CUDA(cudaMemcpy(info.data(), p->d_rowinfo.p, info.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     split.reserve(rows.size());
@@ -1572,7 +1667,60 @@ extern "C"
     HX_CUDA(cudaMemcpyAsync(Yh, dY, bytes, cudaMemcpyDeviceToHost, p->stream));
     if (write_back_x)
       HX_CUDA(cudaMemcpyAsync(Xh, dX, bytes, cudaMemcpyDeviceToHost, p->stream));
-    HX_CUDA(cudaStreamSynchronize(p->stream));
+    HX_TRY(plan_sync(p));
+    return HX_OK;
+  }
+
+  // The column batches of ChebyshevFilteredEigenSolver::solve (src/linearAlgebra/ChebyshevFilteredEigenSolver.t.cpp:231-335:
+  // the block of wavefunctions is filtered MAX_WAVEFN_BATCH_SIZE columns at a time) for wavefunctions that live in HOST
+  // memory: batch k+1 is copied in and batch k-1 copied out while batch k is filtered - three streams, two device buffers
+  // per direction - so the filter runs at its resident rate and PCIe is hidden behind it.  Xh[k] / Yh[k]: n_local x B,
+  // contiguous, ideally pinned.
+  int
+  hx_chebyshev_filter_host_batches(hx_op *A, hx_op *BInv, const double *const *Xh, double *const *Yh, uint32_t n_batches,
+                                   uint32_t B, uint32_t degree, double a0, double a, double b)
+  {
+    HX_CHECK(A && BInv && Xh && Yh, HX_ERR_INVALID, "null argument");
+    hx_plan *p = A->plan;
+    HX_CHECK_B(p, B);
+    if (n_batches == 0)
+      return HX_OK;
+    if (!p->copy_in)
+      {
+        HX_CUDA(cudaStreamCreateWithFlags(&p->copy_in, cudaStreamNonBlocking));
+        HX_CUDA(cudaStreamCreateWithFlags(&p->copy_out, cudaStreamNonBlocking));
+        for (int i = 0; i < 6; ++i)
+          HX_CUDA(cudaEventCreateWithFlags(&p->pipe_ev[i], cudaEventDisableTiming));
+      }
+    double *dX[2], *dY[2];
+    HX_TRY(p->get_scratch(4, &dX[0]));
+    HX_TRY(p->get_scratch(5, &dY[0]));
+    HX_TRY(p->get_scratch(7, &dX[1]));
+    HX_TRY(p->get_scratch(8, &dY[1]));
+    cudaEvent_t *in_done = p->pipe_ev, *comp_done = p->pipe_ev + 2, *out_done = p->pipe_ev + 4;
+    const size_t bytes   = (size_t)p->n_local * B * sizeof(double);
+    // nothing of an earlier call may still be using the buffers
+    HX_CUDA(cudaEventRecord(comp_done[0], p->stream));
+    HX_CUDA(cudaStreamWaitEvent(p->copy_in, comp_done[0], 0));
+    for (uint32_t k = 0; k < n_batches; ++k)
+      {
+        const int s = (int)(k & 1u);
+        HX_CHECK(Xh[k] && Yh[k], HX_ERR_INVALID, "null batch pointer");
+        if (k >= 2)
+          HX_CUDA(cudaStreamWaitEvent(p->copy_in, comp_done[s], 0)); // the filter of batch k-2 is done with this X buffer
+        HX_CUDA(cudaMemcpyAsync(dX[s], Xh[k], bytes, cudaMemcpyHostToDevice, p->copy_in));
+        HX_CUDA(cudaEventRecord(in_done[s], p->copy_in));
+        HX_CUDA(cudaStreamWaitEvent(p->stream, in_done[s], 0));
+        if (k >= 2)
+          HX_CUDA(cudaStreamWaitEvent(p->stream, out_done[s], 0)); // batch k-2 has left this Y buffer
+        HX_TRY(hx_chebyshev_filter(A, BInv, dX[s], dY[s], B, degree, a0, a, b));
+        HX_CUDA(cudaEventRecord(comp_done[s], p->stream));
+        HX_CUDA(cudaStreamWaitEvent(p->copy_out, comp_done[s], 0));
+        HX_CUDA(cudaMemcpyAsync(Yh[k], dY[s], bytes, cudaMemcpyDeviceToHost, p->copy_out));
+        HX_CUDA(cudaEventRecord(out_done[s], p->copy_out));
+      }
+    HX_CUDA(cudaStreamSynchronize(p->copy_out));
+    HX_TRY(plan_sync(p));
     return HX_OK;
   }
 
@@ -1605,7 +1753,7 @@ extern "C"
     double *d_ones = p->d_small.p, *d_ev = p->d_small.p + B, *d_ev2 = p->d_small.p + 2 * (size_t)B;
     HX_CUDA(cudaMemcpyAsync(d_ones, ones.data(), B * sizeof(double), cudaMemcpyHostToDevice, p->stream));
     HX_CUDA(cudaMemcpyAsync(d_ev, ev.data(), B * sizeof(double), cudaMemcpyHostToDevice, p->stream));
-    HX_CUDA(cudaStreamSynchronize(p->stream));
+    HX_TRY(plan_sync(p));
     double alpha1 = sigma1 / e, alpha2 = -c;
     HX_TRY(op_apply(Bop, X, Y, B, 1, 0));
     HX_TRY(op_apply(A, X, s3, B, 1, 0));
@@ -1626,7 +1774,7 @@ extern "C"
         HX_TRY(launch_axpby(p, nown, 1.0, s1, alpha2, Res, Res));
         HX_CUDA(cudaMemcpyAsync(d_ev2, ev2.data(), B * sizeof(double), cudaMemcpyHostToDevice, p->stream));
         HX_TRY(launch_axpby_blocked(p, p->n_owned, B, 1.0, d_ones, Res, alpha1, d_ev2, Y, Res));
-        HX_CUDA(cudaStreamSynchronize(p->stream)); // ev2 (host) is rewritten below
+        HX_TRY(plan_sync(p)); // ev2 (host) is rewritten below
         for (uint32_t j = 0; j < B; ++j)
           {
             ev1[j] = (-c * alpha1) * ev2[j] + alpha2 * ev1[j];
@@ -1639,7 +1787,7 @@ extern "C"
     HX_TRY(op_apply(BInv, ResNew, Res, B, 1, 1));
     HX_CUDA(cudaMemcpyAsync(d_ev2, ev2.data(), B * sizeof(double), cudaMemcpyHostToDevice, p->stream));
     HX_TRY(launch_axpby_blocked(p, p->n_owned, B, 1.0, d_ones, Res, 1.0, d_ev2, X, Y));
-    HX_CUDA(cudaStreamSynchronize(p->stream));
+    HX_TRY(plan_sync(p));
     return HX_OK;
   }
 
@@ -1675,7 +1823,7 @@ extern "C"
         // the reference copies the (possibly constraint-filled) batch back into X
         if (xb != X)
           HX_TRY(copy_cols(p, xin, b, 0, X, B, j0, b, p->n_local));
-        HX_CUDA(cudaStreamSynchronize(p->stream));
+        HX_TRY(plan_sync(p));
         for (uint32_t i = 0; i < b; ++i)
           for (uint32_t j = j0 + i; j < B; ++j)
             S_host[(size_t)j + (size_t)(i + j0) * B] = p->h_pinned[(size_t)i * (B - j0) + (j - j0)];
@@ -1697,7 +1845,7 @@ extern "C"
     HX_TRY(plan->ensure_small((size_t)B * B));
     HX_CUDA(cudaMemcpyAsync(plan->d_small.p, qeff.data(), qeff.size() * sizeof(double), cudaMemcpyHostToDevice,
                             plan->stream));
-    HX_CUDA(cudaStreamSynchronize(plan->stream));
+    HX_TRY(plan_sync(plan));
     double *tmp;
     HX_TRY(plan->get_scratch(2, &tmp));
     return rotate(plan, X, B, plan->n_owned, plan->d_small.p, transpose, lowerTri, tmp);
@@ -1715,7 +1863,7 @@ extern "C"
     if (plan->nranks > 1)
       HX_TRY(comm_allreduce_sum(plan->comm, plan->stream, out, B));
     HX_CUDA(cudaMemcpyAsync(norms_host, out, B * sizeof(double), cudaMemcpyDeviceToHost, plan->stream));
-    HX_CUDA(cudaStreamSynchronize(plan->stream));
+    HX_TRY(plan_sync(plan));
     for (uint32_t j = 0; j < B; ++j)
       norms_host[j] = sqrt(norms_host[j]);
     return HX_OK;
@@ -1736,7 +1884,7 @@ extern "C"
     HX_TRY(plan->ensure_small(2 * (size_t)B));
     HX_CUDA(cudaMemcpyAsync(plan->d_small.p, alpha_host, B * sizeof(double), cudaMemcpyHostToDevice, plan->stream));
     HX_CUDA(cudaMemcpyAsync(plan->d_small.p + B, beta_host, B * sizeof(double), cudaMemcpyHostToDevice, plan->stream));
-    HX_CUDA(cudaStreamSynchronize(plan->stream));
+    HX_TRY(plan_sync(plan));
     return launch_axpby_blocked(plan, n_rows, B, alpha1, plan->d_small.p, x, beta1, plan->d_small.p + B, y, z);
   }
 
@@ -1744,7 +1892,7 @@ extern "C"
   hx_plan_trace(hx_plan *plan, int on)
   {
     HX_CHECK(plan, HX_ERR_INVALID, "null plan");
-    HX_CUDA(cudaStreamSynchronize(plan->stream));
+    HX_TRY(plan_sync(plan));
     for (auto &m : plan->trace_marks)
       plan->trace_pool.push_back(m.second);
     plan->trace_marks.clear();
@@ -1756,7 +1904,7 @@ extern "C"
   hx_plan_trace_report(hx_plan *plan, char *buf, size_t buf_bytes)
   {
     HX_CHECK(plan && buf && buf_bytes > 0, HX_ERR_INVALID, "null argument");
-    HX_CUDA(cudaStreamSynchronize(plan->stream));
+    HX_TRY(plan_sync(plan));
     std::vector<std::pair<std::string, std::pair<double, uint64_t>>> acc; // phase -> (ms, count), first-seen order
     for (size_t i = 1; i < plan->trace_marks.size(); ++i)
       {
@@ -1808,7 +1956,7 @@ extern "C"
   hx_plan_cell_kernel_time_ms(hx_plan *plan, double *ms, uint64_t *launches)
   {
     HX_CHECK(plan && ms && launches, HX_ERR_INVALID, "null argument");
-    HX_CUDA(cudaStreamSynchronize(plan->stream));
+    HX_TRY(plan_sync(plan));
     double tot = 0.0;
     for (size_t i = 0; i + 1 < plan->ev_used; i += 2)
       {
@@ -1827,7 +1975,7 @@ extern "C"
   hx_plan_cell_kernel_sm_clock_mhz(hx_plan *plan, double *mhz)
   {
     HX_CHECK(plan && mhz, HX_ERR_INVALID, "null argument");
-    HX_CUDA(cudaStreamSynchronize(plan->stream));
+    HX_TRY(plan_sync(plan));
     unsigned long long c[2] = {0, 0};
     HX_CUDA(cudaMemcpy(c, plan->d_clk.p, sizeof(c), cudaMemcpyDeviceToHost));
     HX_CUDA(cudaMemset(plan->d_clk.p, 0, sizeof(c)));

@@ -70,6 +70,7 @@ namespace hx
     uint32_t        f_has_c;   // c != 0 (the first degree has no Xprev term)
     uint32_t        f_discard; // Y tiles are whole 128-B lines (B % 16 == 0, aligned): dead partial sums are discarded
     uint32_t        shared_a;  // many cells stream the same packed matrix (hx_cellop_set_matrix_sharing): keep it in L2
+    HaloK           halo;      // halo exchange inside the kernel (multi-rank plans, peer-memory transport); x_ready == nullptr: off
     unsigned long long *clk;   // [4 x nSamples ring]: clock64 / globaltimer at the start and end of CTA 0 (SM clock under load)
     uint32_t        kc;        // k-steps per stage of the packed stream (layout parameter, see pack_kernel)
   };
@@ -313,6 +314,50 @@ namespace hx
     pdl_launch();
     __syncthreads();
 
+    if (a.halo.x_ready != nullptr && blockIdx.x < a.halo.n_halo_ctas)
+      {
+        // ---------------- halo CTAs: receive side of updateGhostValues, before they join the contraction ----------------
+        // (MPICommunicatorP2P::updateGhostValuesEnd, src/utils/MPICommunicatorP2P.t.cpp:226-273: wait, unpack.)  The other
+        // CTAs are already contracting interior cells; the cells that read ghost rows wait for x_ready.
+        __shared__ int halo_ok;
+        const HaloK &  hk = a.halo;
+        if (tid == 0)
+          {
+            bool ok = wait_words(hk.flagU, hk.nSrcU, hk.seqU, hk.status);
+            ok      = ok && wait_words(hk.ackA, hk.nDstA, hk.seqA - 1u, hk.status);
+            if (!ok)
+              atomicExch(hk.status, 1u);
+            halo_ok = ok ? 1 : 0;
+          }
+        __syncthreads();
+        if (halo_ok && hk.do_unpack)
+          {
+            const uint32_t B   = a.B;
+            const size_t   tot = (size_t)hk.n_ghost * B;
+            for (size_t i = (size_t)blockIdx.x * blockDim.x + tid; i < tot; i += (size_t)hk.n_halo_ctas * blockDim.x)
+              {
+                const uint32_t g = hk.unpack_ids[i / B];
+                if (!(g & 0x80000000u)) // a constrained ghost row keeps the value its parents gave it
+                  hk.xghost[(size_t)g * B + (i % B)] = __ldcg(hk.recvU + i);
+              }
+          }
+        __threadfence();
+        __syncthreads();
+        if (tid == 0)
+          {
+            const uint32_t done = atomicAdd(hk.counter, 1u);
+            if (done == hk.n_halo_ctas - 1)
+              {
+                hk.counter[0] = 0u;
+                __threadfence_system();
+                if (halo_ok && hk.do_unpack) // a timed-out exchange acknowledges nothing
+                  for (uint32_t s = 0; s < hk.nSrcU; ++s)
+                    st_release_sys(hk.rackU[s], hk.seqU);
+                st_release_gpu(hk.x_ready, a.epoch);
+              }
+          }
+      }
+
     if (warp >= DWARPS + SWARPS)
       {
         reg_dec<REG_PRODUCER>();
@@ -411,6 +456,16 @@ namespace hx
                 pitem_load(slot, d);
                 const uint32_t w = tag - 1u;
                 const int      n = (int)d.n, ktot = n + (int)d.nproj;
+                if ((d.nwait & HX_ITEM_BOUNDARY) && a.halo.x_ready != nullptr)
+                  {
+                    // this cell reads ghost rows of X: they are in place once the halo CTAs have published the stamp (which
+                    // also means the owners have consumed the previous accumulate message: this cell may push into their buffers)
+                    if (lane == 0)
+                      while (ld_acquire_gpu(a.halo.x_ready) != a.epoch)
+                        {
+                        }
+                    __syncwarp();
+                  }
                 // start address of row k of the B operand (0 = zero row): X rows of the cell, then its rows of V C^H X
                 auto row_addr = [&](int k) -> unsigned long long {
                   if (k >= ktot)
@@ -494,6 +549,7 @@ namespace hx
             PItem info;
             pitem_load(slot, info);
             const uint32_t w   = tag - 1u, bt = w % a.nBt;
+            const uint32_t nwait = info.nwait & ~HX_ITEM_BOUNDARY;
             const int      n   = (int)info.n;
             const int      nMt = (n + 7) >> 3;
             const uint32_t b0  = bt * BT;
@@ -510,7 +566,7 @@ namespace hx
                 else if (st < SROWS)
                   idx = (st < nrows) ? __ldg(a.dest + info.ids_off + rbase + st) : 0xffffffffu;
                 else
-                  idx = (mc == 0 && (uint32_t)(st - SROWS) < info.nwait) ? __ldg(a.wait_list + info.wait_off + (st - SROWS)) : 0xffffffffu;
+                  idx = (mc == 0 && (uint32_t)(st - SROWS) < nwait) ? __ldg(a.wait_list + info.wait_off + (st - SROWS)) : 0xffffffffu;
                 have_next = false;
                 double dinv_r = 0.0;
                 if (st < SROWS)
@@ -549,7 +605,7 @@ namespace hx
                         if (st < SROWS)
                           idx_next = ((uint32_t)st < ni.n) ? __ldg(a.dest + ni.ids_off + st) : 0xffffffffu;
                         else
-                          idx_next = ((uint32_t)(st - SROWS) < ni.nwait) ? __ldg(a.wait_list + ni.wait_off + (st - SROWS)) : 0xffffffffu;
+                          idx_next = ((uint32_t)(st - SROWS) < (ni.nwait & ~HX_ITEM_BOUNDARY)) ? __ldg(a.wait_list + ni.wait_off + (st - SROWS)) : 0xffffffffu;
                         have_next = true;
                       }
                   }
@@ -565,7 +621,7 @@ namespace hx
                               {
                               }
                           }
-                        for (uint32_t i = (uint32_t)st; i < info.nwait; i += SROWS)
+                        for (uint32_t i = (uint32_t)st; i < nwait; i += SROWS)
                           {
                             const uint32_t *f = a.flags + (size_t)__ldg(a.wait_list + info.wait_off + i) * a.nBt + bt;
                             while (ld_acquire_gpu(f) != a.epoch)
@@ -581,15 +637,24 @@ namespace hx
                     const bool valid  = idx != 0xffffffffu;
                     const bool staged = valid && (idx & HX_DEST_STAGED);
                     const bool lastf  = FUSE && valid && (idx & (HX_DEST_LASTF | HX_DEST_STAGED)) == HX_DEST_LASTF;
+                    // 4 push: last toucher of a ghost row whose sum goes straight into its owner's accumulate buffer
+                    const bool push = valid && !staged && (idx & HX_DEST_PUSH) && a.halo.x_ready != nullptr;
                     const uint32_t fl = !valid ? 0u :
-                                                 (1u | ((!staged && !(idx & HX_DEST_FIRST)) ? 2u : 0u) | (lastf ? 4u : 0u) | (staged ? 8u : 0u));
+                                                 (1u | ((!staged && !(idx & HX_DEST_FIRST)) ? 2u : 0u) | (lastf ? 4u : 0u) | (staged ? 8u : 0u) |
+                                                  (push ? 16u : 0u));
                     const unsigned long long ro =
                       (unsigned long long)(staged ? (idx & 0x7fffffffu) : HX_DEST_ROW(idx)) * B * 8ull;
                     asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(rbuf + 16 * st), "r"((uint32_t)ro),
                                  "r"((uint32_t)(ro >> 32)), "r"(fl), "r"(0u)
                                  : "memory");
-                    if (FUSE)
-                      asm volatile("st.shared.f64 [%0], %1;" ::"r"(rbuf + SROWS * 16 + 8 * st), "d"(dinv_r) : "memory");
+                    // second slot of the record: a*dinv of a fusable row, or the owner-side address of a pushed ghost row
+                    unsigned long long aux = (unsigned long long)__double_as_longlong(dinv_r);
+                    if (push)
+                      {
+                        const uint32_t j = HX_DEST_ROW(idx) - a.halo.n_owned;
+                        aux = (unsigned long long)a.halo.push_base[j] + (unsigned long long)a.halo.push_row[j] * B * 8ull;
+                      }
+                    asm volatile("st.shared.u64 [%0], %1;" ::"r"(rbuf + SROWS * 16 + 8 * st), "l"(aux) : "memory");
                   }
                 bar_scatter(); // records of the chunk are in shared memory; the predecessors have stored
                 const uint32_t ab = (NACC == 2) ? (g & 1u) : 0u, aph = (NACC == 2) ? ((g >> 1) & 1u) : (g & 1u);
@@ -682,6 +747,23 @@ namespace hx
                                 __stcg(reinterpret_cast<double *>(ptr), v.x);
                                 if (c1ok)
                                   __stcg(reinterpret_cast<double *>(ptr) + 1, v.y);
+                              }
+                          }
+                        if (fl[u] & 16u)
+                          {
+                            // accumulateAddLocallyOwned, send side (MPICommunicatorP2P.t.cpp:288-380): this cell was the last
+                            // local toucher of a ghost row - its sum goes into the owner's receive buffer over NVLink now
+                            const int          r = (p0 + u) * RPP + rrow;
+                            unsigned long long ra;
+                            asm volatile("ld.shared.u64 %0, [%1];" : "=l"(ra) : "r"(rbuf + SROWS * 16 + 8 * r) : "memory");
+                            char *rp = reinterpret_cast<char *>(ra + colb);
+                            if (VEC)
+                              *reinterpret_cast<double2 *>(rp) = v;
+                            else
+                              {
+                                *reinterpret_cast<double *>(rp) = v.x;
+                                if (c1ok)
+                                  *(reinterpret_cast<double *>(rp) + 1) = v.y;
                               }
                           }
                       }
@@ -1188,7 +1270,7 @@ namespace hx
         const CellMeta &m = op->h_meta[p->h_order[w]];
         ItemDesc &      d = items[w];
         d.h_off = m.h_off, d.ids_off = m.ids_off, d.n = m.n, d.nproj = m.nproj, d.proj_off = m.proj_off;
-        d.wait_off = p->h_wait_off[w], d.nwait = p->h_wait_off[w + 1] - p->h_wait_off[w];
+        d.wait_off = p->h_wait_off[w], d.nwait = (p->h_wait_off[w + 1] - p->h_wait_off[w]) | (p->h_boundary[p->h_order[w]] ? HX_ITEM_BOUNDARY : 0u);
       }
     HX_TRY(op->d_items.upload(items));
     return HX_OK;
@@ -1231,7 +1313,7 @@ namespace hx
           const CellMeta &m = op->h_meta[p->h_order[w]];
           ItemDesc &      d = items[w];
           d.h_off = m.h_off, d.ids_off = m.ids_off, d.n = m.n, d.nproj = m.nproj, d.proj_off = m.proj_off;
-          d.wait_off = p->h_wait_off[w], d.nwait = p->h_wait_off[w + 1] - p->h_wait_off[w];
+          d.wait_off = p->h_wait_off[w], d.nwait = (p->h_wait_off[w + 1] - p->h_wait_off[w]) | (p->h_boundary[p->h_order[w]] ? HX_ITEM_BOUNDARY : 0u);
         }
       HX_TRY(op->d_items.upload(items));
     }
@@ -1366,7 +1448,7 @@ namespace hx
   }
 
   int
-  launch_cell_apply(hx_op *op, const double *X, double *Y, uint32_t B, const FuseArgs *fuse, bool *fused_applied)
+  launch_cell_apply(hx_op *op, const double *X, double *Y, uint32_t B, const FuseArgs *fuse, bool *fused_applied, const HaloK *halo)
   {
     if (fused_applied)
       *fused_applied = false;
@@ -1395,6 +1477,8 @@ namespace hx
     a.shared_a  = (op->n_unique * 2u < p->C) ? 1u : 0u;
     a.kc        = (uint32_t)op->kc;
     a.clk       = p->timing ? p->d_clk.p : nullptr;
+    if (halo)
+      a.halo = *halo;
     // column tile: widest of {8,16,32} columns that B needs and shared memory allows
     int  nt      = B > 16 ? 4 : (B > 8 ? 2 : 1);
     auto xtile_of = [&](int nt_) { return (size_t)op->max_kp * (nt_ * 8 + 4) * sizeof(double); };

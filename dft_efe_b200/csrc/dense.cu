@@ -200,7 +200,7 @@ namespace hx
   {
     int h = 0;
     HX_CUDA(cudaMemcpyAsync(&h, d->info.p, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
-    HX_CUDA(cudaStreamSynchronize(p->stream));
+    HX_TRY(plan_sync(p));
     *info_host = h;
     return HX_OK;
   }

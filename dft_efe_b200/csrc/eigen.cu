@@ -122,7 +122,7 @@ namespace hx
     HX_TRY(p->ensure_pinned((size_t)B * sizeof(double)));
     HX_CUDA(cudaMemcpy2DAsync(p->h_pinned, sizeof(double), S, ((size_t)B + 1) * sizeof(double), sizeof(double), B,
                               cudaMemcpyDeviceToHost, p->stream));
-    HX_CUDA(cudaStreamSynchronize(p->stream));
+    HX_TRY(plan_sync(p));
     for (uint32_t i = 0; i < B; ++i)
       if (!(fabs(p->h_pinned[i]) < 1e14))
         {
@@ -151,7 +151,7 @@ namespace hx
     HX_TRY(dense_sym_eig(p, S, B, p->d_dense_w.p, &info)); // S <- Q
     p->mark("dense-eig");
     HX_CUDA(cudaMemcpyAsync(evals_host, p->d_dense_w.p, B * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
-    HX_CUDA(cudaStreamSynchronize(p->stream));
+    HX_TRY(plan_sync(p));
     if (info != 0)
       {
         *status = 1;
@@ -278,7 +278,7 @@ extern "C"
     HX_TRY(dense_buffers(plan, B));
     HX_TRY(dense_sym_eig(plan, S_dev, B, plan->d_dense_w.p, info));
     HX_CUDA(cudaMemcpyAsync(eigenvalues_host, plan->d_dense_w.p, B * sizeof(double), cudaMemcpyDeviceToHost, plan->stream));
-    HX_CUDA(cudaStreamSynchronize(plan->stream));
+    HX_TRY(plan_sync(plan));
     return HX_OK;
   }
 
@@ -410,7 +410,7 @@ extern "C"
       if (p->nranks > 1)
         HX_TRY(comm_allreduce_sum(p->comm, p->stream, d_dot, 1));
       HX_CUDA(cudaMemcpyAsync(p->h_pinned, d_dot, sizeof(double), cudaMemcpyDeviceToHost, p->stream));
-      HX_CUDA(cudaStreamSynchronize(p->stream));
+      HX_TRY(plan_sync(p));
       *out = p->h_pinned[0];
       return HX_OK;
     };

@@ -229,7 +229,9 @@ namespace hx
 #define HX_DEST_STAGED 0x80000000u
 #define HX_DEST_FIRST 0x40000000u
 #define HX_DEST_LASTF 0x20000000u /* last toucher (processing order) of a row whose Chebyshev update can be fused */
-#define HX_DEST_ROW(d) ((d)&0x1fffffffu)
+#define HX_DEST_PUSH 0x10000000u  /* last toucher of a ghost row whose partial sum goes straight to its owner (halo overlap) */
+#define HX_DEST_ROW(d) ((d)&0x0fffffffu)
+#define HX_ITEM_BOUNDARY 0x80000000u /* ItemDesc::nwait: the cell reads ghost rows of X (waits for the halo inside the kernel) */
 
 namespace hx
 {
@@ -269,11 +271,72 @@ namespace hx
 #endif
 } // namespace hx
 
+namespace hx
+{
+  // what the cell kernel needs to take part in a halo exchange (halo overlap, peer-memory transport): all device
+  // pointers; x_ready == nullptr switches the whole thing off
+  struct HaloK
+  {
+    uint32_t *       x_ready = nullptr; // local stamp word: epoch once ghosts are unpacked and the accumulate buffers are free
+    // update direction (X): wait for the sources' flags, copy my receive buffer into the ghost rows, acknowledge
+    const uint32_t * flagU   = nullptr; // [nSrcU] in my arena
+    uint32_t *const *rackU   = nullptr; // [nSrcU] ack words at the sources (peer mappings)
+    const double *   recvU   = nullptr;
+    const uint32_t * unpack_ids = nullptr; // [n_ghost] ghost index of buffer row k; bit 31: constrained, keep as filled
+    double *         xghost  = nullptr; // X + n_owned * B
+    uint32_t         nSrcU = 0, seqU = 0, n_ghost = 0, do_unpack = 0;
+    // accumulate direction (Y): the owners must have consumed the previous message before anyone writes their buffers
+    const uint32_t * ackA    = nullptr; // [nDstA] in my arena
+    double *const *  push_base = nullptr; // [n_ghost] owner's buffer of ghost row j (peer mapping)
+    const uint32_t * push_row  = nullptr; // [n_ghost] row inside it
+    uint32_t         nDstA = 0, seqA = 0, n_owned = 0, do_push = 0;
+    uint32_t *       counter = nullptr; // CTA counter of the unpack phase
+    uint32_t *       status  = nullptr; // raised on timeout
+    uint32_t         n_halo_ctas = 0;
+  };
+} // namespace hx
+
+#ifdef __CUDACC__
+namespace hx
+{
+  // ---- peer-memory halo: device-side primitives shared by peer.cu and the cell kernel ----
+  constexpr unsigned long long PEER_TIMEOUT_CYCLES = 57000000000ull; // ~30 s at 1.9 GHz: ranks may arrive late
+  __device__ __forceinline__ uint32_t
+  ld_acquire_sys(const uint32_t *p)
+  {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+  }
+  __device__ __forceinline__ void
+  st_release_sys(uint32_t *p, uint32_t v)
+  {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+  }
+  // wait until words[i] >= seq for all i < n (sequence numbers only grow); returns false on timeout, and at once
+  // when an earlier exchange already timed out (the status word stays raised: no cascade of 30-s waits)
+  __device__ __forceinline__ bool
+  wait_words(const uint32_t *words, uint32_t n, uint32_t seq, const uint32_t *status)
+  {
+    if (*reinterpret_cast<const volatile uint32_t *>(status) != 0u)
+      return false;
+    const unsigned long long t0 = clock64();
+    for (uint32_t i = 0; i < n; ++i)
+      while ((int32_t)(ld_acquire_sys(words + i) - seq) < 0)
+        if (clock64() - t0 > PEER_TIMEOUT_CYCLES)
+          return false;
+    return true;
+  }
+} // namespace hx
+#endif
+
 struct hx_plan
 {
   int          rank = 0, nranks = 1;
   cudaStream_t stream     = nullptr;
   bool         own_stream = false;
+  cudaStream_t copy_in = nullptr, copy_out = nullptr; // host-batch pipeline of hx_chebyshev_filter_host_batches
+  cudaEvent_t  pipe_ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   uint32_t     n_owned = 0, n_ghost = 0, n_local = 0, n_owned_classical = 0;
   uint32_t     C = 0, S = 0, max_n = 0, max_block = 0;
   size_t       S2 = 0;
@@ -314,6 +377,7 @@ struct hx_plan
   // per row (ascending processing order, the reference's CPU order) without colour launches or atomics
   int                   scatter_mode = 0; // 0 = ordered persistent kernel, 1 = one launch per colour
   std::vector<uint32_t> h_order, h_wait_off, h_wait_list;
+  std::vector<char>     h_boundary; // per cell: reads ghost rows of X
   hx::DevBuf<uint32_t>  d_order, d_wait_off, d_wait_list;
   hx::DevBuf<uint32_t>  d_flags;    // [C * ceil(max_block/8)] epoch stamps
   hx::DevBuf<uint32_t>  d_counters; // [0] work counter, [1] finished CTAs
@@ -331,6 +395,19 @@ struct hx_plan
   bool                  cheb_fill_dead = false;        // no row of the M^-1 step reads a constrained row of its input
                                                        // (no parents, no constrained enrichment row): the fused filter
                                                        // skips the hanging-node fill of its scratch H.X
+  // halo exchange overlapped with the cell kernel (peer-memory transport, constraint set 0 on both sides):
+  //   X side: the ghost rows are unpacked by the first CTAs of the cell kernel itself while the others contract interior
+  //           cells; only the cells that read ghost rows (ItemDesc::nwait & HX_ITEM_BOUNDARY) wait for them.  Needs: no
+  //           constraint row with a ghost parent (its fill would have to follow the unpack).
+  //   Y side: the last toucher of a ghost row stores its final partial sum straight into the owner's accumulate buffer
+  //           (HX_DEST_PUSH); rows that get contributions after the kernel (constrained / parent / staged / untouched ghost
+  //           rows) are pushed by the short kernel that also raises the flags.
+  bool                  overlap_x_ok = false, overlap_y_ok = false;
+  uint32_t              n_boundary_cells = 0, n_push_direct = 0;
+  hx::DevBuf<uint32_t>  d_unpack_ids;   // [n_ghost] ghost_local_ids, bit 31 set for constrained ghost rows (kept as filled)
+  hx::DevBuf<uint32_t>  d_push_rest;    // ghost rows (buffer positions) NOT pushed by the cell kernel
+  uint32_t              n_push_rest = 0;
+  hx::DevBuf<uint32_t>  d_x_ready;      // [1] epoch stamp: ghosts of X are in place, accumulate buffers may be written
   bool                  cheb_fusable_multirank = true; // no constrained ghost row has parents (see api.cu)
   bool                  cheb_fusable_agreed    = false; // ... on every rank (AND-ed across the communicator once)
   int                   sm_count = 0;
@@ -398,6 +475,7 @@ struct hx_op
   int                       kc  = 4; // k-steps (4 columns) per pipeline stage: packed layout depends on it
   // nonlocal
   bool                      has_nl = false;
+  int                       nl_reads_ghost = -1; // a projector cell reads ghost rows of X (-1: not determined yet)
   hx::Halo                  phalo;
   uint32_t                  n_proj_local = 0, sum_proj = 0;
   std::vector<uint32_t>     h_ncp, h_pids, h_nl_cells; // cells with projectors
@@ -442,7 +520,7 @@ namespace hx
   int launch_enr_block(hx_plan *p, const double *blk, uint32_t nE, const double *Xenr, double *Yenr, uint32_t B);
   // fuse != nullptr asks for the Chebyshev epilogue; *fused_applied tells whether the launched variant did it
   int launch_cell_apply(hx_op *op, const double *X, double *Y, uint32_t B, const FuseArgs *fuse = nullptr,
-                        bool *fused_applied = nullptr);
+                        bool *fused_applied = nullptr, const HaloK *halo = nullptr);
   int launch_nl_phase_a(hx_op *op, const double *X, uint32_t B);
   int pack_cell_matrices(hx_op *op, const double *raw_dev_or_host, int on_device); // raw == nullptr: structure only
   // use_row_list false: all owned rows; true: only the n_rows listed rows
@@ -459,6 +537,7 @@ namespace hx
   int copy_cols(hx_plan *p, const double *src, uint32_t ldsrc, uint32_t c0s, double *dst, uint32_t lddst, uint32_t c0d,
                 uint32_t ncols, size_t nrows);
   int halo_update(hx_plan *p, Halo &h, double *X, uint32_t B);
+  int plan_sync(hx_plan *p); // stream synchronisation + status of the peer-memory halos
   uint32_t gram_max_split(uint32_t M, uint32_t N);
   // dense.cu: B x B subspace problems on the device (cuSOLVER, resolved with dlopen)
   struct Dense;
@@ -481,4 +560,9 @@ namespace hx
   int peer_halo_update(hx_plan *p, Halo &h, double *X, uint32_t B);
   int peer_halo_accumulate(hx_plan *p, Halo &h, double *Y, uint32_t B);
   int peer_check_status(Halo &h);
+  // halo overlap: push only (the cell kernel unpacks), kernel arguments, closing kernels of the accumulate
+  int peer_push_update(hx_plan *p, Halo &h, const double *X, uint32_t B, uint32_t *seq);
+  int peer_overlap_args(hx_plan *p, Halo &h, double *X, uint32_t B, bool do_unpack, uint32_t seqU, HaloK *k);
+  int peer_finish_accumulate(hx_plan *p, Halo &h, double *Y, uint32_t B, uint32_t seqA);
+  bool peer_overlap_available(const Halo &h);
 } // namespace hx

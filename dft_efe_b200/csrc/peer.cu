@@ -20,36 +20,6 @@
 
 namespace hx
 {
-  constexpr unsigned long long PEER_TIMEOUT_CYCLES = 57000000000ull; // ~30 s at 1.9 GHz: ranks may arrive late
-
-  __device__ __forceinline__ uint32_t
-  ld_acquire_sys(const uint32_t *p)
-  {
-    uint32_t v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-  }
-  __device__ __forceinline__ void
-  st_release_sys(uint32_t *p, uint32_t v)
-  {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-  }
-
-  // wait until words[i] >= seq for all i < n (sequence numbers only grow); returns false on timeout, and at once
-  // when an earlier exchange already timed out (the status word stays raised: no cascade of 30-s waits)
-  __device__ __forceinline__ bool
-  wait_words(const uint32_t *words, uint32_t n, uint32_t seq, const uint32_t *status)
-  {
-    if (*reinterpret_cast<const volatile uint32_t *>(status) != 0u)
-      return false;
-    const unsigned long long t0 = clock64();
-    for (uint32_t i = 0; i < n; ++i)
-      while ((int32_t)(ld_acquire_sys(words + i) - seq) < 0)
-        if (clock64() - t0 > PEER_TIMEOUT_CYCLES)
-          return false;
-    return true;
-  }
-
   struct PeerDir // one direction of one halo, as the kernels see it
   {
     // sender side
@@ -107,8 +77,10 @@ namespace hx
           {
             d.counter[0] = 0u;
             __threadfence_system();
-            for (uint32_t s = 0; s < d.nDst; ++s)
-              st_release_sys(d.rflag[s], seq);
+            // a timed-out exchange raises no flag: the neighbours run into their own timeout instead of consuming stale rows
+            if (*reinterpret_cast<const volatile uint32_t *>(d.status) == 0u)
+              for (uint32_t s = 0; s < d.nDst; ++s)
+                st_release_sys(d.rflag[s], seq);
           }
       }
   }
@@ -139,8 +111,9 @@ namespace hx
           {
             d.counter[1] = 0u;
             __threadfence_system();
-            for (uint32_t s = 0; s < d.nSrc; ++s)
-              st_release_sys(d.rack[s], seq);
+            if (*reinterpret_cast<const volatile uint32_t *>(d.status) == 0u) // no acknowledgement after a timeout
+              for (uint32_t s = 0; s < d.nSrc; ++s)
+                st_release_sys(d.rack[s], seq);
           }
       }
   }
@@ -151,9 +124,19 @@ namespace hx
   {
     if (peer_consume_begin(d, seq))
       {
-        const size_t tot = (size_t)n * B;
-        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (size_t)gridDim.x * blockDim.x)
-          x[(size_t)ids[i / B] * B + (i % B)] = __ldcg(d.recv + i);
+        if (B % 2 == 0)
+          {
+            const uint32_t bv  = B / 2;
+            const size_t   tot = (size_t)n * bv;
+            for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (size_t)gridDim.x * blockDim.x)
+              reinterpret_cast<double2 *>(x + (size_t)ids[i / bv] * B)[i % bv] = __ldcg(reinterpret_cast<const double2 *>(d.recv) + i);
+          }
+        else
+          {
+            const size_t tot = (size_t)n * B;
+            for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (size_t)gridDim.x * blockDim.x)
+              x[(size_t)ids[i / B] * B + (i % B)] = __ldcg(d.recv + i);
+          }
       }
     peer_consume_end(d, seq);
   }
@@ -165,15 +148,36 @@ namespace hx
   {
     if (peer_consume_begin(d, seq))
       {
-        const size_t tot = (size_t)nrows * B;
-        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (size_t)gridDim.x * blockDim.x)
+        if (B % 2 == 0)
           {
-            const uint32_t r = (uint32_t)(i / B), v = (uint32_t)(i % B);
-            double *       y = x + (size_t)rows[r] * B + v;
-            double         s = *y;
-            for (uint32_t e = off[r]; e < off[r + 1]; ++e)
-              s += __ldcg(d.recv + (size_t)pos[e] * B + v);
-            *y = s;
+            const uint32_t bv  = B / 2;
+            const size_t   tot = (size_t)nrows * bv;
+            for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (size_t)gridDim.x * blockDim.x)
+              {
+                const uint32_t r = (uint32_t)(i / bv), v = (uint32_t)(i % bv);
+                double2 *      y = reinterpret_cast<double2 *>(x + (size_t)rows[r] * B) + v;
+                double2        s = *y;
+                for (uint32_t e = off[r]; e < off[r + 1]; ++e)
+                  {
+                    const double2 t = __ldcg(reinterpret_cast<const double2 *>(d.recv + (size_t)pos[e] * B) + v);
+                    s.x += t.x;
+                    s.y += t.y;
+                  }
+                *y = s;
+              }
+          }
+        else
+          {
+            const size_t tot = (size_t)nrows * B;
+            for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (size_t)gridDim.x * blockDim.x)
+              {
+                const uint32_t r = (uint32_t)(i / B), v = (uint32_t)(i % B);
+                double *       y = x + (size_t)rows[r] * B + v;
+                double         s = *y;
+                for (uint32_t e = off[r]; e < off[r + 1]; ++e)
+                  s += __ldcg(d.recv + (size_t)pos[e] * B + v);
+                *y = s;
+              }
           }
       }
     peer_consume_end(d, seq);
@@ -196,6 +200,8 @@ namespace hx
     DevBuf<uint32_t *> d_rflagU, d_rflagA, d_rackU, d_rackA;
     uint32_t           seqU = 0, seqA = 0;
     PeerDir            dirU, dirA;
+    DevBuf<double *>   d_push_base; // [n_ghost] owner's accumulate buffer for ghost row j (peer mapping)
+    DevBuf<uint32_t>   d_push_row;  // [n_ghost] row of ghost j inside it
     ~PeerState()
     {
       for (void *m : mapped)
@@ -330,11 +336,16 @@ namespace hx
     std::vector<double *>   rbU(s->nTP), rbA(s->nGP);
     std::vector<uint32_t>   roU(s->nTP), roA(s->nGP);
     std::vector<uint32_t *> rfU(s->nTP), rfA(s->nGP), rackU(s->nGP), rackA(s->nTP);
+    int                     mismatch = 0;
     for (uint32_t i = 0; i < s->nTP; ++i)
       {
         const int       q  = (int)h.target_procs[i];
         const uint32_t *tq = table(q);
-        HX_CHECK(tq[4 * me + 1] != 0xffffffffu, HX_ERR_COMM, "halo patterns of ranks %d and %d disagree", me, q);
+        if (tq[4 * me + 1] == 0xffffffffu)
+          {
+            mismatch = 1; // halo patterns of the two ranks disagree: voted on below, so that every rank leaves together
+            continue;
+          }
         rbU[i]   = reinterpret_cast<double *>((unsigned char *)s->mapped[q] + wire(q)->offU);
         roU[i]   = tq[4 * me + 0];
         rfU[i]   = words_of(q) + tq[4 * me + 1];                                   // flagU[idx of me at q]
@@ -345,7 +356,11 @@ namespace hx
       {
         const int       q  = (int)h.ghost_procs[i];
         const uint32_t *tq = table(q);
-        HX_CHECK(tq[4 * me + 3] != 0xffffffffu, HX_ERR_COMM, "halo patterns of ranks %d and %d disagree", me, q);
+        if (tq[4 * me + 3] == 0xffffffffu)
+          {
+            mismatch = 1;
+            continue;
+          }
         rbA[i]   = reinterpret_cast<double *>((unsigned char *)s->mapped[q] + wire(q)->offA);
         roA[i]   = tq[4 * me + 2];
         rfA[i]   = words_of(q) + 2 * wire(q)->nGP + tq[4 * me + 3];                 // flagA[idx of me at q]
@@ -360,11 +375,29 @@ namespace hx
       }
     for (uint32_t i = 0; i < s->nGP; ++i)
       {
-        HX_CHECK(h.ghost_ranges[2 * i] == segbA[i], HX_ERR_UNSUPPORTED, "ghost ranges must be contiguous per ghost proc");
+        if (h.ghost_ranges[2 * i] != segbA[i])
+          mismatch = 1; // ghost ranges must be contiguous per ghost proc
         segbA[i + 1] = h.ghost_ranges[2 * i + 1];
         for (uint32_t k = segbA[i]; k < segbA[i + 1]; ++k)
           segA[k] = i;
       }
+    {
+      // every rank leaves together when any pair of halo patterns is inconsistent (no rank is left in a collective)
+      std::vector<unsigned char> f1(4, 0), fall(4 * (size_t)nr, 0);
+      f1[0] = (unsigned char)mismatch;
+      int rc = comm_allgather_bytes(p->comm, p->stream, f1.data(), fall.data(), 4);
+      for (int q = 0; q < nr; ++q)
+        if (fall[4 * (size_t)q])
+          mismatch = 1;
+      if (rc != HX_OK || mismatch)
+        {
+          delete s;
+          if (rc != HX_OK)
+            return rc;
+          set_error("halo patterns of the ranks disagree (a rank lists a neighbour that does not list it back, or ghost ranges are not contiguous)");
+          return HX_ERR_COMM;
+        }
+    }
     HX_TRY(s->d_rbaseU.upload(rbU));
     HX_TRY(s->d_rbaseA.upload(rbA));
     HX_TRY(s->d_rrowoffU.upload(roU));
@@ -388,6 +421,22 @@ namespace hx
     a.seg = s->d_segA.p, a.segbegin = s->d_segbeginA.p, a.nDst = s->nGP, a.nRows = h.n_ghost;
     a.recv = reinterpret_cast<const double *>(s->arena + s->offA), a.flag = s->wFlagA, a.rack = s->d_rackA.p;
     a.nSrc = s->nTP, a.counter = s->wCounter + 2, a.status = s->wStatus;
+    {
+      // ghost row j = ghost_local_ids[k] travels as send row k of the accumulate direction
+      std::vector<uint32_t> gids(h.n_ghost);
+      if (h.n_ghost)
+        HX_CUDA(cudaMemcpy(gids.data(), h.d_ghost_local_ids.p, gids.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+      std::vector<double *> pb(h.n_ghost, nullptr);
+      std::vector<uint32_t> pr(h.n_ghost, 0);
+      for (uint32_t k = 0; k < h.n_ghost; ++k)
+        {
+          const uint32_t sg = segA[k];
+          pb[gids[k]]       = rbA[sg];
+          pr[gids[k]]       = roA[sg] + (k - segbA[sg]);
+        }
+      HX_TRY(s->d_push_base.upload(pb));
+      HX_TRY(s->d_push_row.upload(pr));
+    }
     h.peer = s;
     p->peer_halos.push_back(&h);
     // nobody may push before every rank has mapped and zeroed its arena
@@ -401,8 +450,10 @@ namespace hx
   static unsigned
   grid_for(size_t work_items)
   {
+    // one thread of every block waits for the neighbours' words (a bounded wait on a remote event: blocks that become
+    // resident later simply find it satisfied), the rest is a grid-stride copy: two blocks per SM are plenty
     size_t g = (work_items + 255) / 256;
-    return (unsigned)std::max<size_t>(1, std::min<size_t>(g, 64)); // small, co-resident grids: every block spins
+    return (unsigned)std::max<size_t>(1, std::min<size_t>(g, 296));
   }
 
   int
@@ -417,7 +468,7 @@ namespace hx
       }
     if (h.n_ghost || s->nGP)
       {
-        peer_unpack_kernel<<<grid_for((size_t)h.n_ghost * B), 256, 0, p->stream>>>(s->dirU, X + (size_t)h.n_owned * B,
+        peer_unpack_kernel<<<grid_for((size_t)h.n_ghost * B / 2), 256, 0, p->stream>>>(s->dirU, X + (size_t)h.n_owned * B,
                                                                                   h.d_ghost_local_ids.p, h.n_ghost, B, seq);
         p->launches++;
       }
@@ -439,8 +490,112 @@ namespace hx
       }
     if (h.n_send || s->nTP)
       {
-        peer_add_rows_kernel<<<grid_for((size_t)h.n_acc_rows * B), 256, 0, p->stream>>>(s->dirA, Y, h.d_acc_rows.p, h.d_acc_off.p,
+        peer_add_rows_kernel<<<grid_for((size_t)h.n_acc_rows * B / 2), 256, 0, p->stream>>>(s->dirA, Y, h.d_acc_rows.p, h.d_acc_off.p,
                                                                                        h.d_acc_pos.p, h.n_acc_rows, B, seq);
+        p->launches++;
+      }
+    HX_CUDA(cudaGetLastError());
+    return HX_OK;
+  }
+
+
+  // ---- halo overlap: the cell kernel unpacks the ghost rows of X and pushes the ghost-row sums of Y itself ----
+  // closing kernel of the accumulate: pushes the ghost rows the cell kernel could not (rows that receive contributions
+  // after it: constrained / parent / staged / untouched ones), then raises the flags of the message at the owners.  It
+  // runs after the cell kernel in stream order, so the cell kernel's own peer stores are complete.
+  __global__ void __launch_bounds__(256)
+  peer_push_rest_kernel(PeerDir d, const double *yghost, const uint32_t *gids, const uint32_t *rest, uint32_t nrest, uint32_t B,
+                        uint32_t seq)
+  {
+    const size_t tot = (size_t)nrest * B;
+    const bool   ok  = *reinterpret_cast<const volatile uint32_t *>(d.status) == 0u;
+    if (ok)
+      for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (size_t)gridDim.x * blockDim.x)
+        {
+          const uint32_t k = rest[i / B], c = (uint32_t)(i % B);
+          const uint32_t s = d.seg[k];
+          d.rbase[s][((size_t)d.rrowoff[s] + (k - d.segbegin[s])) * B + c] = yghost[(size_t)gids[k] * B + c];
+        }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0)
+      {
+        const uint32_t done = atomicAdd(d.counter, 1u);
+        if (done == gridDim.x - 1)
+          {
+            d.counter[0] = 0u;
+            __threadfence_system();
+            if (ok) // a timed-out exchange raises no flag: the neighbours time out as well instead of reading garbage
+              for (uint32_t s = 0; s < d.nDst; ++s)
+                st_release_sys(d.rflag[s], seq);
+          }
+      }
+  }
+
+  bool
+  peer_overlap_available(const Halo &h)
+  {
+    return h.peer != nullptr;
+  }
+
+  // updateGhostValues, send side only (the receive side runs inside the cell kernel)
+  int
+  peer_push_update(hx_plan *p, Halo &h, const double *X, uint32_t B, uint32_t *seq)
+  {
+    PeerState *s = h.peer;
+    *seq         = ++s->seqU;
+    if (h.n_send || s->nTP)
+      {
+        peer_push_kernel<<<grid_for((size_t)h.n_send * B / 2), 256, 0, p->stream>>>(s->dirU, X, h.d_owned_ids_for_targets.p, B, *seq);
+        p->launches++;
+      }
+    HX_CUDA(cudaGetLastError());
+    return HX_OK;
+  }
+
+  int
+  peer_overlap_args(hx_plan *p, Halo &h, double *X, uint32_t B, bool do_unpack, uint32_t seqU, HaloK *k)
+  {
+    PeerState *s  = h.peer;
+    k->x_ready    = p->d_x_ready.p;
+    k->flagU      = s->wFlagU;
+    k->rackU      = s->d_rackU.p;
+    k->recvU      = reinterpret_cast<const double *>(s->arena + s->offU);
+    k->unpack_ids = p->d_unpack_ids.p;
+    k->xghost     = X + (size_t)h.n_owned * B;
+    k->nSrcU      = do_unpack ? s->nGP : 0u;
+    k->seqU       = seqU;
+    k->n_ghost    = h.n_ghost;
+    k->do_unpack  = do_unpack ? 1u : 0u;
+    k->ackA       = s->wAckA;
+    k->push_base  = s->d_push_base.p;
+    k->push_row   = s->d_push_row.p;
+    k->nDstA      = s->nGP;
+    k->seqA       = ++s->seqA;
+    k->n_owned    = h.n_owned;
+    k->do_push    = 1u;
+    k->counter    = s->wCounter + 5; // own word: [0..1] / [2..3] are the push / consume counters of the two directions, [4] status
+    k->status     = s->wStatus;
+    const size_t bytes = (size_t)h.n_ghost * B * sizeof(double);
+    k->n_halo_ctas     = (uint32_t)std::max<size_t>(1, std::min<size_t>(32, bytes / (256 * 1024) + 1));
+    return HX_OK;
+  }
+
+  // accumulateAddLocallyOwned after a cell kernel that pushed its ghost-row sums itself
+  int
+  peer_finish_accumulate(hx_plan *p, Halo &h, double *Y, uint32_t B, uint32_t seqA)
+  {
+    PeerState *s = h.peer;
+    if (h.n_ghost || s->nGP)
+      {
+        peer_push_rest_kernel<<<grid_for((size_t)p->n_push_rest * B), 256, 0, p->stream>>>(
+          s->dirA, Y + (size_t)h.n_owned * B, h.d_ghost_local_ids.p, p->d_push_rest.p, p->n_push_rest, B, seqA);
+        p->launches++;
+      }
+    if (h.n_send || s->nTP)
+      {
+        peer_add_rows_kernel<<<grid_for((size_t)h.n_acc_rows * B / 2), 256, 0, p->stream>>>(s->dirA, Y, h.d_acc_rows.p, h.d_acc_off.p,
+                                                                                       h.d_acc_pos.p, h.n_acc_rows, B, seqA);
         p->launches++;
       }
     HX_CUDA(cudaGetLastError());

@@ -119,6 +119,7 @@ class MeshSpec:
     proj_cutoff: float = 0.0
     nranks: int = 1
     seed: int = 1234
+    with_k_cell: bool = True            # also build the Laplace cell matrices (Poisson tests); off for the big bench meshes
 
 
 @dataclass
@@ -638,17 +639,28 @@ def build_problem(spec: MeshSpec, only_rank: Optional[int] = None) -> List[RankP
         off1 = np.concatenate(([0], np.cumsum(ncd64)))
         off2 = np.concatenate(([0], np.cumsum(ncd64 * ncd64)))
         ids = np.zeros(int(off1[-1]), np.int64)
-        h_cell = np.zeros(int(off2[-1]))
-        k_cell = np.zeros(int(off2[-1]))
+        h_cell = np.empty(int(off2[-1]))
+        k_cell = np.empty(int(off2[-1])) if spec.with_k_cell else None
         plain = nenr_c == 0
         for s_ in (1, 2):
             m = plain & (size[cells] == s_)
             if not m.any():
                 continue
             Kc, Mc, _ = mats[s_]
-            blk = 0.5 * Kc.ravel()[None, :] + vcell[cells[m]][:, None] * Mc.ravel()[None, :]
-            h_cell[(off2[:-1][m][:, None] + np.arange(npc * npc)[None, :]).ravel()] = blk.ravel()
-            k_cell[(off2[:-1][m][:, None] + np.arange(npc * npc)[None, :]).ravel()] = np.tile(Kc.ravel(), int(m.sum()))
+            kr, mr = 0.5 * Kc.ravel(), Mc.ravel()
+            # plain cells of one size occupy contiguous runs of the flat arrays: fill them as 2-D views, a few hundred
+            # cells at a time (a 7 M-DoF order-6 mesh has 31 GB of cell matrices)
+            mi = np.nonzero(m)[0]
+            brk = np.nonzero(np.diff(mi) != 1)[0] + 1
+            for run in np.split(mi, brk):
+                for c0 in range(0, len(run), 256):
+                    rr = run[c0:c0 + 256]
+                    a_, b_ = int(off2[rr[0]]), int(off2[rr[-1] + 1])
+                    view = h_cell[a_:b_].reshape(len(rr), npc * npc)
+                    np.multiply(vcell[cells[rr]][:, None], mr[None, :], out=view)
+                    view += kr[None, :]
+                    if k_cell is not None:
+                        k_cell[a_:b_].reshape(len(rr), npc * npc)[:] = Kc.ravel()[None, :]
             ids[(off1[:-1][m][:, None] + np.arange(npc)[None, :]).ravel()] = cl_all[m].ravel()
         for ic in np.nonzero(~plain)[0]:
             c = cells[ic]
@@ -669,10 +681,11 @@ def build_problem(spec: MeshSpec, only_rank: Optional[int] = None) -> List[RankP
             Hc[npc:, :npc] = Bc.T
             Hc[npc:, npc:] = 0.5 * (Ec + Ec.T) + np.eye(len(el)) * 0.5 * vol
             h_cell[off2[ic]:off2[ic + 1]] = Hc.ravel()
-            Kx = np.zeros((n_c, n_c))
-            Kx[:npc, :npc] = Kc
-            Kx[npc:, npc:] = np.eye(len(el)) * vol
-            k_cell[off2[ic]:off2[ic + 1]] = Kx.ravel()
+            if k_cell is not None:
+                Kx = np.zeros((n_c, n_c))
+                Kx[:npc, :npc] = Kc
+                Kx[npc:, npc:] = np.eye(len(el)) * vol
+                k_cell[off2[ic]:off2[ic + 1]] = Kx.ravel()
         ncd = ncd64.astype(U32)
         ids = ids.astype(U32)
         ncp, pids, cblocks = [], [], []
@@ -742,7 +755,7 @@ def build_problem(spec: MeshSpec, only_rank: Optional[int] = None) -> List[RankP
         prob.cell_edge = spec.h * size[cells].astype(np.float64) / 2.0  # edge length of each local cell
         prob.k_diag = np.ones(halo.n_local)
         prob.k_diag[clm] = kdiag_g[gid_to_node[l2g[clm]]]
-        if (~clm).any():  # enrichment rows: sum of the identity*vol blocks of the touching cells
+        if (~clm).any() and k_cell is not None:  # enrichment rows: sum of the identity*vol blocks of the touching cells
             kd = np.zeros(halo.n_local)
             np.add.at(kd, ids.astype(np.int64), np.concatenate(
                 [np.diag(k_cell[off2[i]:off2[i + 1]].reshape(int(ncd64[i]), int(ncd64[i]))) for i in range(C)]))

@@ -220,6 +220,12 @@ int hx_chebyshev_filter(hx_op *A, hx_op *BInv, double *X, double *Y, uint32_t B,
  * ChebyshevFilter.t.cpp:133).  Blocks until the result is in host memory. */
 int hx_chebyshev_filter_host(hx_op *A, hx_op *BInv, double *X_host, double *Y_host, uint32_t B, uint32_t degree,
                              double wantedLower, double wantedUpper, double unwantedUpper, int write_back_x);
+/* The same for a block that lives in host memory as n_batches column batches of B vectors each (Xh[k], Yh[k]: n_local x B,
+ * contiguous, ideally pinned) - the column batches of ChebyshevFilteredEigenSolver::solve
+ * (src/linearAlgebra/ChebyshevFilteredEigenSolver.t.cpp:231-335).  The copy-in of batch k+1 and the copy-out of batch k-1
+ * overlap the filter of batch k (three streams, two device buffers per direction). */
+int hx_chebyshev_filter_host_batches(hx_op *A, hx_op *BInv, const double *const *Xh, double *const *Yh, uint32_t n_batches,
+                                     uint32_t B, uint32_t degree, double a0, double a, double b);
 /* eigenvalues: HOST array of B doubles (std::vector<RealType>& in the reference). */
 int hx_residual_chebyshev_filter(hx_op *A, hx_op *Bop, hx_op *BInv, const double *eigenvalues, double *X,
                                  double *Y, uint32_t B, uint32_t degree, double wantedLower,
@@ -347,8 +353,8 @@ int hx_plan_cell_kernel_sm_clock_mhz(hx_plan *plan, double *mhz);
 int hx_plan_trace(hx_plan *plan, int on);
 int hx_plan_trace_report(hx_plan *plan, char *buf, size_t buf_bytes);
 /* 1 when the short kernels of an apply / filter degree are launched with programmatic dependent launch (the launch of
- * kernel k+1 overlaps the tail of kernel k; results are bitwise those of serialised launches).  Default: on for
- * single-rank plans, off once a multi-rank plan exists in the process; environment HXB200_PDL=0 / 1 forces it off / on
+ * kernel k+1 overlaps the tail of kernel k; results are bitwise those of serialised launches).  Default: on
+ * (single- and multi-rank plans); environment HXB200_PDL=0 switches it off
  * (read at every launch).  No reference counterpart (the reference launches nothing). */
 int hx_programmatic_launch_enabled(void);
 /* FP64 DMMA / DFMA / copy microbenchmarks used for the roofline denominators. */

@@ -591,7 +591,10 @@ def processing_order(prob, delay: int, shared_threshold: int = 8):
     predecessor lists.  Cells are swept in the caller's order - the order of the reference's sequential
     scatter loop, basis/FECellWiseDataOperations.t.cpp:87-153 - but a cell is placed only when every
     already-placed neighbour (a cell sharing a non-shared row) sits at least `delay` positions back; if no
-    cell qualifies, the one that qualifies soonest (ties: lowest index) is taken.
+    cell qualifies, the one that qualifies soonest (ties: lowest sweep key) is taken.
+    On a multi-rank partition the cells that read ghost rows are all keyed at a quarter of the sweep (ahead of
+    the interior cell with that index, among themselves in caller order): the halo exchange runs while the
+    interior cells before and after them are contracted.
     Returns (order[C], wait_off[C+1], wait_list): position -> cell, and for each position the sorted
     positions of the immediately preceding toucher of each of the cell's non-shared rows."""
     import heapq
@@ -601,40 +604,47 @@ def processing_order(prob, delay: int, shared_threshold: int = 8):
     inc = np.bincount(ids, minlength=prob.n_local)
     C = prob.n_cells
     rows_of = [[int(r) for r in ids[off[c]:off[c + 1]] if inc[r] <= shared_threshold] for c in range(C)]
+    multi = getattr(prob, "nranks", 1) > 1
+    boundary = [multi and bool((ids[off[c]:off[c + 1]] >= prob.n_owned).any()) for c in range(C)]
+    k0 = C // 4
+    key_of = [((k0, 0, c) if boundary[c] else (c, 1, c)) for c in range(C)]
     cells_of = {}
     for c in range(C):
         for r in rows_of[c]:
             cells_of.setdefault(r, []).append(c)
     ready = [0] * C
     placed = [False] * C
-    eligible = list(range(C))
+    eligible = [key_of[c] for c in range(C)]
     heapq.heapify(eligible)
     waiting = []
     order = []
     for t in range(C):
         while waiting and waiting[0][0] <= t:
-            key, x = heapq.heappop(waiting)
+            key, kx = heapq.heappop(waiting)
+            x = kx[2]
             if not placed[x]:
                 if ready[x] <= t:
-                    heapq.heappush(eligible, x)
+                    heapq.heappush(eligible, kx)
                 elif ready[x] != key:
-                    heapq.heappush(waiting, (ready[x], x))
+                    heapq.heappush(waiting, (ready[x], kx))
         c = None
         while eligible:
-            x = heapq.heappop(eligible)
+            kx = heapq.heappop(eligible)
+            x = kx[2]
             if placed[x]:
                 continue
             if ready[x] > t:
-                heapq.heappush(waiting, (ready[x], x))
+                heapq.heappush(waiting, (ready[x], kx))
                 continue
             c = x
             break
         while c is None:
-            key, x = heapq.heappop(waiting)
+            key, kx = heapq.heappop(waiting)
+            x = kx[2]
             if placed[x]:
                 continue
             if ready[x] != key:
-                heapq.heappush(waiting, (ready[x], x))
+                heapq.heappush(waiting, (ready[x], kx))
                 continue
             c = x
         placed[c] = True

@@ -181,6 +181,30 @@ def test_processing_order_and_wait_lists_bit_exact(capi, prob_full, delay, monke
     assert rel_l2_per_vector(dY.download(), Yo) < RTOL_HX
 
 
+@pytest.mark.parametrize("delay", [7, 592])
+def test_processing_order_of_a_partition_keys_its_boundary_cells_at_a_quarter(capi, delay, monkeypatch):
+    """Multi-rank plans (halo overlap): the cells that read ghost rows are keyed at C/4 of the sweep; the order and the
+    predecessor lists of every partition match the oracle's specification bit for bit.  (Plan creation needs no
+    communicator, so a partition of a 2-rank mesh can be planned on one GPU.)"""
+    nc = (4, 4, 8)
+    atoms = np.array([[2.0, 2.0, 4.0]])
+    spec = synth.MeshSpec(ncell=nc, p=3, refine_mask=synth.refine_ball(nc, 1.0, atoms, 0.9), atoms=atoms,
+                          n_enr_per_atom=2, enr_cutoff=1.2, n_proj_per_atom=2, proj_cutoff=1.0, nranks=2)
+    monkeypatch.setenv("HXB200_ORDER_DELAY", str(delay))
+    for q in synth.build_problem(spec):
+        plan = capi.Plan(q, max_block=8)
+        off, preds = plan.wait_lists()
+        order = plan.processing_order()
+        o_order, o_off, o_preds = orc.processing_order(q, delay)
+        assert np.array_equal(order, o_order)
+        assert np.array_equal(off, o_off)
+        assert np.array_equal(preds, o_preds)
+        ids = q.cell_local_ids.astype(np.int64)
+        cell_off = np.concatenate(([0], np.cumsum(q.num_cell_dofs.astype(np.int64))))
+        bnd = np.array([(ids[cell_off[c]:cell_off[c + 1]] >= q.n_owned).any() for c in range(q.n_cells)])
+        assert bnd.any() and not bnd.all()
+
+
 @pytest.mark.parametrize("B", [3, 8, 32, 40])
 def test_ordered_and_coloured_scatter_agree(capi, prob_full, B):
     p = prob_full
@@ -458,6 +482,28 @@ def test_chebyshev_filter_host_entry(capi, prob_full):
     Xh2, Yh2 = X.copy(), np.zeros_like(X)
     capi.chebyshev_filter_host(H, minv, Xh2, Yh2, deg, a0, a, b, write_back_x=False)
     assert np.array_equal(Xh2, X) and np.array_equal(Yh2[:own], Yh[:own])
+
+
+def test_chebyshev_filter_host_batches_pipeline(capi, prob_full):
+    """hx_chebyshev_filter_host_batches (column batches from HOST memory, copies overlapped with the filter of the batch in
+    between) == the device entry point on every batch, bit for bit - 5 batches through 2 device buffers per direction."""
+    import torch
+    p = prob_full
+    B, deg = 8, 6
+    a0, a, b = -3.0, 1.0, 60.0
+    plan = capi.Plan(p, max_block=B)
+    H = capi.CellOp(plan)
+    minv = capi.DiagOp(plan, p.diag_inv, p.enr_block_inv, capi.DIAG_OEFE_ATOMBLOCK)
+    rng = np.random.default_rng(5)
+    Xs = [synth.make_block(p, B) * (1.0 + 0.1 * k) + 1e-3 * rng.standard_normal((p.n_local, B)) for k in range(5)]
+    xb = [torch.from_numpy(np.ascontiguousarray(x)).pin_memory() for x in Xs]
+    yb = [torch.zeros_like(x).pin_memory() for x in xb]
+    for rep in range(2):   # second call: buffers and events are reused
+        capi.chebyshev_filter_host_batches(H, minv, [x.data_ptr() for x in xb], [y.data_ptr() for y in yb], B, deg, a0, a, b)
+        for k in range(5):
+            dX, dY = plan.block(B, Xs[k]), plan.block(B)
+            capi.chebyshev_filter(H, minv, dX, dY, deg, a0, a, b)
+            assert np.array_equal(yb[k].numpy(), dY.download()), f"batch {k} differs (call {rep})"
 
 
 def test_residual_chebyshev_filter(capi, prob_full):
