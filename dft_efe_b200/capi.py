@@ -24,7 +24,7 @@ EXPORTS = [
     "hx_accumulate_add_locally_owned", "hx_distribute_parent_to_child", "hx_distribute_child_to_parent",
     "hx_set_constrained_nodes_to_zero", "hx_plan_add_constraints", "hx_distribute_parent_to_child_set",
     "hx_distribute_child_to_parent_set", "hx_cellop_set_constraint_sets", "hx_cg_solve", "hx_cellop_create", "hx_cellop_set_matrices", "hx_cellop_set_nonlocal",
-    "hx_diagop_create", "hx_op_destroy", "hx_op_apply", "hx_op_apply_host", "hx_chebyshev_filter", "hx_chebyshev_filter_host", "hx_chebyshev_filter_host_batches",
+    "hx_diagop_create", "hx_diagop_create_global_enrichment", "hx_op_destroy", "hx_op_apply", "hx_op_apply_host", "hx_chebyshev_filter", "hx_chebyshev_filter_host", "hx_chebyshev_filter_host_batches", "hx_multipass_cgs", "hx_chfsi_solve_ortho", "hx_plan_global_size",
     "hx_residual_chebyshev_filter", "hx_xtopx", "hx_subspace_rotation", "hx_l2_norms", "hx_axpby",
     "hx_axpby_blocked", "hx_plan_launch_count", "hx_plan_cell_kernel_time_ms", "hx_plan_cell_kernel_sm_clock_mhz", "hx_plan_enable_kernel_timing", "hx_plan_trace", "hx_plan_trace_report",
     "hx_microbench", "hx_programmatic_launch_enabled",
@@ -305,6 +305,11 @@ class Plan:
         check(lib().hx_plan_cell_kernel_time_ms(self.h, C.byref(ms), C.byref(n)))
         return ms.value, n.value
 
+    def global_size(self) -> int:
+        n = C.c_uint64()
+        check(lib().hx_plan_global_size(self.h, C.byref(n)))
+        return n.value
+
     def cell_kernel_sm_clock_mhz(self) -> float:
         mhz = C.c_double()
         check(lib().hx_plan_cell_kernel_sm_clock_mhz(self.h, C.byref(mhz)))
@@ -401,6 +406,18 @@ class DiagOp(Op):
         check(lib().hx_diagop_create(plan.h, p, ep, C.c_int(variant), C.byref(self.h)))
 
 
+class DiagOpGlobalEnrichment(Op):
+    """OrthoEFEOverlapInverseOpContextGLL: diag_inv + one dense block (column-major nEg x nEg) over all enrichment functions"""
+
+    def __init__(self, plan: Plan, diag_inv: np.ndarray, block_global: np.ndarray, n_enr_global: int, owned_offset: int):
+        super().__init__(plan)
+        a, p = _f64(diag_inv)
+        assert a.size == plan.n_local
+        e, ep = _f64(np.asarray(block_global).ravel()) if n_enr_global else (None, None)
+        check(lib().hx_diagop_create_global_enrichment(plan.h, p, ep, C.c_uint32(n_enr_global), C.c_uint32(owned_offset),
+                                                       C.byref(self.h)))
+
+
 def chebyshev_filter(A: Op, BInv: Op, X: DeviceBlock, Y: DeviceBlock, degree, a0, a, b):
     check(lib().hx_chebyshev_filter(A.h, BInv.h, X.p, Y.p, C.c_uint32(X.B), C.c_uint32(degree), C.c_double(a0),
                                     C.c_double(a), C.c_double(b)))
@@ -486,6 +503,14 @@ def cholesky_gram_schmidt(Bop: Op, X: DeviceBlock, ortho: DeviceBlock, batch: in
     return st.value
 
 
+def multipass_cgs(Bop: Op, X: DeviceBlock, ortho: DeviceBlock, batch: int, max_pass=50, shift_tol=1e-12, identity_tol=1e-12):
+    """OrthonormalizationFunctions::MultipassCGS: returns (OrthonormalizationErrorCode, Cholesky passes performed)."""
+    st, np_ = C.c_int(), C.c_uint32()
+    check(lib().hx_multipass_cgs(Bop.h, X.p, ortho.p, C.c_uint32(X.B), C.c_uint32(batch), C.c_uint32(max_pass),
+                                 C.c_double(shift_tol), C.c_double(identity_tol), C.byref(st), C.byref(np_)))
+    return st.value, np_.value
+
+
 def rayleigh_ritz(A: Op, X: DeviceBlock, vecs: DeviceBlock, batch: int, compute_vectors=True):
     st = C.c_int()
     w = np.zeros(X.B)
@@ -495,14 +520,14 @@ def rayleigh_ritz(A: Op, X: DeviceBlock, vecs: DeviceBlock, batch: int, compute_
 
 
 def chfsi_solve(A: Op, Bop: Op, BInv: Op, guess: DeviceBlock, vecs: DeviceBlock, batch, degree, a0, a, b,
-                eigenvalues=None, residual_filter=False, compute_vectors=True):
+                eigenvalues=None, residual_filter=False, compute_vectors=True, multipass_cgs=False):
     """ChebyshevFilteredEigenSolver::solve: returns (Ritz values, EigenSolverErrorCode)."""
     st = C.c_int()
     w = np.zeros(guess.B) if eigenvalues is None else np.ascontiguousarray(eigenvalues, dtype=np.float64).copy()
-    check(lib().hx_chfsi_solve(A.h, Bop.h, BInv.h, guess.p, vecs.p, C.c_uint32(guess.B), C.c_uint32(batch),
-                               C.c_uint32(degree), C.c_double(a0), C.c_double(a), C.c_double(b),
-                               C.c_int(int(residual_filter)), w.ctypes.data_as(f64p), C.c_int(int(compute_vectors)),
-                               C.byref(st)))
+    check(lib().hx_chfsi_solve_ortho(A.h, Bop.h, BInv.h, guess.p, vecs.p, C.c_uint32(guess.B), C.c_uint32(batch),
+                                     C.c_uint32(degree), C.c_double(a0), C.c_double(a), C.c_double(b),
+                                     C.c_int(int(residual_filter)), w.ctypes.data_as(f64p), C.c_int(int(compute_vectors)),
+                                     C.c_int(1 if multipass_cgs else 0), C.byref(st)))
     return w, st.value
 
 

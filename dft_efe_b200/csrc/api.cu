@@ -714,6 +714,38 @@ namespace hx
           HX_TRY(halo_update(p, p->halo, Y, B));
         return HX_OK;
       }
+    if (op->variant == HX_DIAG_OEFE_GLOBAL)
+      {
+        // OrthoEFEOverlapInverseOpContextGLL::apply (src/basis/OrthoEFEOverlapInverseOpContextGLL.t.cpp:1182-1282): diagonal
+        // part on every local row, then the dense block over ALL enrichment functions of the system: every rank places its
+        // owned enrichment rows at their global offset, the vector is summed over the ranks (the reference's MPI_Allreduce
+        // of nE_global x B, :1228-1234; ncclAllReduce here), and each rank takes its own rows of block . Xenr
+        if (ugx)
+          HX_TRY(halo_update(p, p->halo, X, B));
+        HX_TRY(launch_p2c(p, X, B));
+        HX_TRY(launch_row_scale(p, op->d_diag.p, X, Y, B, p->n_local));
+        if (op->nE_global)
+          {
+            HX_TRY(p->ensure_small((size_t)op->nE_global * B));
+            double *xg = p->d_small.p;
+            HX_CUDA(cudaMemsetAsync(xg, 0, (size_t)op->nE_global * B * sizeof(double), p->stream));
+            if (op->nE)
+              HX_CUDA(cudaMemcpyAsync(xg + (size_t)op->enr_offset * B, X + (size_t)p->n_owned_classical * B,
+                                      (size_t)op->nE * B * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
+            if (p->nranks > 1)
+              {
+                HX_CHECK(p->comm != nullptr, HX_ERR_COMM, "nranks > 1 but no communicator attached (hx_plan_attach_comm)");
+                HX_TRY(comm_allreduce_sum(p->comm, p->stream, xg, (size_t)op->nE_global * B));
+              }
+            HX_TRY(launch_enr_block_global(p, op->d_enr_block.p, op->nE_global, op->enr_offset, op->nE, xg,
+                                           Y + (size_t)p->n_owned_classical * B, B));
+          }
+        HX_TRY(halo_update(p, p->halo, Y, B));
+        HX_TRY(launch_c2p(p, Y, B));
+        if (ugy)
+          HX_TRY(halo_update(p, p->halo, Y, B));
+        return HX_OK;
+      }
     if (op->variant == HX_DIAG_OEFE_MASS)
       ugx = ugy = 0;
     if (ugx)
@@ -1002,6 +1034,29 @@ extern "C"
   {
     HX_CHECK(plan, HX_ERR_INVALID, "null plan");
     return plan_sync(plan);
+  }
+
+  // MultiVector::globalSize(): the number of locally owned rows summed over the ranks of the plan's communicator
+  int
+  hx_plan_global_size(hx_plan *plan, uint64_t *n)
+  {
+    HX_CHECK(plan && n, HX_ERR_INVALID, "null argument");
+    if (plan->n_global == 0)
+      {
+        double v = (double)plan->n_owned;
+        if (plan->nranks > 1)
+          {
+            HX_CHECK(plan->comm != nullptr, HX_ERR_COMM, "nranks > 1 but no communicator attached (hx_plan_attach_comm)");
+            HX_TRY(plan->ensure_small(1));
+            HX_CUDA(cudaMemcpyAsync(plan->d_small.p, &v, sizeof(double), cudaMemcpyHostToDevice, plan->stream));
+            HX_TRY(comm_allreduce_sum(plan->comm, plan->stream, plan->d_small.p, 1));
+            HX_CUDA(cudaMemcpyAsync(&v, plan->d_small.p, sizeof(double), cudaMemcpyDeviceToHost, plan->stream));
+            HX_TRY(plan_sync(plan));
+          }
+        plan->n_global = (uint64_t)(v + 0.5);
+      }
+    *n = plan->n_global;
+    return HX_OK;
   }
 
   int
@@ -1325,6 +1380,41 @@ extern "C"
   }
 
   int
+  hx_diagop_create_global_enrichment(hx_plan *plan, const double *diag_inv, const double *enr_block_global, uint32_t nE_global,
+                                     uint32_t owned_enr_offset, hx_op **op)
+  {
+    HX_CHECK(plan && diag_inv && op, HX_ERR_INVALID, "null argument");
+    const uint32_t nE = plan->n_owned - plan->n_owned_classical;
+    HX_CHECK((uint64_t)owned_enr_offset + nE <= nE_global, HX_ERR_INVALID,
+             "owned enrichment rows [%u, %u) outside the global enrichment range [0, %u)", owned_enr_offset, owned_enr_offset + nE,
+             nE_global);
+    HX_CHECK(nE_global == 0 || enr_block_global, HX_ERR_INVALID, "enrichment block required");
+    hx_op *o = new (std::nothrow) hx_op();
+    HX_CHECK(o, HX_ERR_NOMEM, "out of host memory");
+    o->plan       = plan;
+    o->kind       = HX_OP_DIAG;
+    o->variant    = HX_DIAG_OEFE_GLOBAL;
+    o->nE         = nE;
+    o->nE_global  = nE_global;
+    o->enr_offset = owned_enr_offset;
+    int r         = o->d_diag.upload(diag_inv, plan->n_local);
+    if (r == HX_OK && nE_global)
+      r = o->d_enr_block.upload(enr_block_global, (size_t)nE_global * nE_global);
+    if (r == HX_OK && cudaDeviceSynchronize() != cudaSuccess)
+      {
+        set_error("cudaDeviceSynchronize failed after operator upload");
+        r = HX_ERR_CUDA;
+      }
+    if (r != HX_OK)
+      {
+        delete o;
+        return r;
+      }
+    *op = o;
+    return HX_OK;
+  }
+
+  int
   hx_op_destroy(hx_op *op)
   {
     if (op)
@@ -1577,7 +1667,7 @@ extern "C"
             p->cheb_fusable_multirank = false;
         p->cheb_fusable_agreed = true;
       }
-    const bool   fused  = BInv->kind == HX_OP_DIAG && X != Y &&
+    const bool   fused  = BInv->kind == HX_OP_DIAG && X != Y && BInv->variant != HX_DIAG_OEFE_GLOBAL &&
                        (BInv->variant == HX_DIAG_CFE || p->nranks == 1 || p->cheb_fusable_multirank);
     double *     s1, *s2 = nullptr;
     HX_TRY(p->get_scratch(0, &s1));

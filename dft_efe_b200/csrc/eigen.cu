@@ -98,6 +98,7 @@ namespace hx
     ORTHO_SUCCESS           = 0,
     ORTHO_LAPACK_ERROR      = 1,
     ORTHO_NON_ORTHONORMALIZABLE = 2,
+    ORTHO_MAX_PASS_EXCEEDED     = 3,
   };
 
   static int
@@ -135,6 +136,116 @@ namespace hx
     if (orthoX != X)
       HX_CUDA(cudaMemcpyAsync(orthoX, X, (size_t)p->n_local * B * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
     *status = ORTHO_SUCCESS;
+    return HX_OK;
+  }
+
+  // OrthonormalizationFunctions::MultipassCGS (src/linearAlgebra/OrthonormalizationFunctions.t.cpp:440-785): Cholesky-
+  // Gram-Schmidt passes on S = X^T B X, each preceded by the smallest eigenvalue of S: while it is below shiftTolerance
+  // the diagonal is shifted up to it before the factorisation, and the pass that finds it above is the last one.  The
+  // reference's estimate of ||S - I||_F is restated as written (:541-578: every entry squared, the diagonal entries once
+  // more as (s_ii - 1)^2), its early exit included.  The dense steps are cuSOLVER calls like the reference's ELPA /
+  // ScaLAPACK ones; the B x B matrix makes one trip to the host per pass for the two scalar tests, as in the reference.
+  static int
+  multipass_cgs(hx_op *Bop, double *X, double *orthoX, uint32_t B, uint32_t batch, uint32_t maxPass, double shiftTol,
+                double identityTol, int *status, uint32_t *passes)
+  {
+    hx_plan *p = Bop->plan;
+    HX_TRY(dense_buffers(p, B));
+    double *            S = p->d_dense_s.p;
+    std::vector<double> Sh((size_t)B * B), w(B);
+    // X.globalSize() < numVec: NON_ORTHONORMALIZABLE_MULTIVECTOR (:478-481)
+    {
+      double nglob = (double)p->n_owned;
+      if (p->nranks > 1)
+        {
+          HX_TRY(p->ensure_small(1));
+          HX_CUDA(cudaMemcpyAsync(p->d_small.p, &nglob, sizeof(double), cudaMemcpyHostToDevice, p->stream));
+          HX_TRY(comm_allreduce_sum(p->comm, p->stream, p->d_small.p, 1));
+          HX_CUDA(cudaMemcpyAsync(&nglob, p->d_small.p, sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+          HX_TRY(plan_sync(p));
+        }
+      if (nglob < (double)B)
+        {
+          *status = ORTHO_NON_ORTHONORMALIZABLE;
+          set_error("MultipassCGS: fewer rows than vectors");
+          return HX_OK;
+        }
+    }
+    uint32_t iPass = 1;
+    bool     ok    = true;
+    while (iPass <= maxPass)
+      {
+        HX_TRY(xtopx_device(Bop, X, B, batch, S)); // lower triangle, strict upper triangle zero
+        HX_CUDA(cudaMemcpyAsync(Sh.data(), S, Sh.size() * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+        HX_TRY(plan_sync(p));
+        double err2 = 0.0;
+        for (uint32_t j = 0; j < B; ++j)
+          for (uint32_t i = j; i < B; ++i)
+            {
+              const double v = Sh[(size_t)i + (size_t)j * B];
+              if (i == j)
+                err2 += (v - 1.0) * (v - 1.0) + v * v;
+              else
+                err2 += 2.0 * v * v; // both halves of the symmetrised matrix
+            }
+        if (sqrt(err2) < identityTol * sqrt((double)B))
+          break;
+        // smallest eigenvalue of S (the eigenvalue-only ELPA / MRRR call of :580-612) on a copy
+        HX_CUDA(cudaMemcpyAsync(p->d_dense_q.p, S, Sh.size() * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
+        int info = 0;
+        p->mark("dense:begin");
+        HX_TRY(dense_sym_eig(p, p->d_dense_q.p, B, p->d_dense_w.p, &info));
+        p->mark("dense-eig");
+        HX_CUDA(cudaMemcpyAsync(w.data(), p->d_dense_w.p, B * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+        HX_TRY(plan_sync(p));
+        if (info != 0)
+          {
+            ok = false;
+            break;
+          }
+        const double evMin    = w[0];
+        bool         lastPass = false;
+        double       shift    = 0.0;
+        if (evMin > shiftTol)
+          lastPass = true;
+        else
+          shift = shiftTol - evMin;
+        if (shift != 0.0)
+          {
+            for (uint32_t i = 0; i < B; ++i)
+              w[i] = Sh[(size_t)i * (B + 1)] + shift;
+            HX_CUDA(cudaMemcpy2DAsync(S, ((size_t)B + 1) * sizeof(double), w.data(), sizeof(double), sizeof(double), B,
+                                      cudaMemcpyHostToDevice, p->stream));
+          }
+        p->mark("dense:begin");
+        HX_TRY(dense_cholesky_inverse(p, S, B, &info)); // S <- L^-1
+        p->mark("dense-cholesky");
+        if (info != 0)
+          {
+            ok = false;
+            break;
+          }
+        HX_TRY(rotation_device(p, X, B, S, 0, 1));
+        if (lastPass)
+          break;
+        ++iPass;
+      }
+    if (passes)
+      *passes = std::min(iPass, maxPass);
+    if (orthoX != X)
+      HX_CUDA(cudaMemcpyAsync(orthoX, X, (size_t)p->n_local * B * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
+    if (iPass > maxPass)
+      {
+        *status = ORTHO_MAX_PASS_EXCEEDED;
+        set_error("MultipassCGS: maximum number of passes exceeded");
+      }
+    else if (!ok)
+      {
+        *status = ORTHO_LAPACK_ERROR;
+        set_error("MultipassCGS: dense eigenvalue / Cholesky step failed");
+      }
+    else
+      *status = ORTHO_SUCCESS;
     return HX_OK;
   }
 
@@ -303,10 +414,32 @@ extern "C"
   }
 
   int
+  hx_multipass_cgs(hx_op *Bop, double *X, double *orthogonalizedX, uint32_t B, uint32_t batch, uint32_t maxPass,
+                   double shiftTolerance, double identityTolerance, int *status, uint32_t *passes)
+  {
+    HX_CHECK(Bop && X && orthogonalizedX && status, HX_ERR_INVALID, "null argument");
+    HX_CHECK_B(Bop->plan, B);
+    HX_CHECK(batch >= 1 && maxPass >= 1, HX_ERR_INVALID, "batch and maxPass must be >= 1");
+    return multipass_cgs(Bop, X, orthogonalizedX, B, batch, maxPass, shiftTolerance, identityTolerance, status, passes);
+  }
+
+  int
   hx_chfsi_solve(hx_op *A, hx_op *Bop, hx_op *BInv, double *eigenSubspaceGuess, double *eigenVectors, uint32_t B,
                  uint32_t batch, uint32_t degree, double wantedLower, double wantedUpper, double unwantedUpper,
                  int residualFilter, double *eigenvalues_host, int computeEigenVectors, int *status)
   {
+    return hx_chfsi_solve_ortho(A, Bop, BInv, eigenSubspaceGuess, eigenVectors, B, batch, degree, wantedLower, wantedUpper,
+                                unwantedUpper, residualFilter, eigenvalues_host, computeEigenVectors, HX_ORTHO_CHOLESKY_GRAMSCHMIDT,
+                                status);
+  }
+
+  int
+  hx_chfsi_solve_ortho(hx_op *A, hx_op *Bop, hx_op *BInv, double *eigenSubspaceGuess, double *eigenVectors, uint32_t B,
+                       uint32_t batch, uint32_t degree, double wantedLower, double wantedUpper, double unwantedUpper,
+                       int residualFilter, double *eigenvalues_host, int computeEigenVectors, int orthoType, int *status)
+  {
+    HX_CHECK(orthoType == HX_ORTHO_CHOLESKY_GRAMSCHMIDT || orthoType == HX_ORTHO_MULTIPASS_CGS, HX_ERR_INVALID,
+             "Orthogonalization type not present");
     HX_CHECK(A && Bop && BInv && eigenSubspaceGuess && eigenVectors && eigenvalues_host && status, HX_ERR_INVALID,
              "null argument");
     hx_plan *p = A->plan;
@@ -338,9 +471,13 @@ extern "C"
             HX_TRY(copy_cols(p, in, b, 0, eigenSubspaceGuess, B, j0, b, p->n_local));
           }
       }
-    // [O] X -> X_O, M-orthonormal (CHOLESKY_GRAMSCHMIDT branch, :352-358)
+    // [O] X -> X_O, M-orthonormal (:350-371): CHOLESKY_GRAMSCHMIDT, or MULTIPASS_CGS with MultiPassOrthoDefaults
+    // (MAX_PASS 50, SHIFT_TOL 1e-12, IDENTITY_TOL 1e-12: src/linearAlgebra/Defaults.cpp:41-43)
     int ostat = 0;
-    HX_TRY(cholesky_gram_schmidt(Bop, eigenVectors, eigenSubspaceGuess, B, batch, &ostat));
+    if (orthoType == HX_ORTHO_MULTIPASS_CGS)
+      HX_TRY(multipass_cgs(Bop, eigenVectors, eigenSubspaceGuess, B, batch, 50, 1e-12, 1e-12, &ostat, nullptr));
+    else
+      HX_TRY(cholesky_gram_schmidt(Bop, eigenVectors, eigenSubspaceGuess, B, batch, &ostat));
     if (ostat != ORTHO_SUCCESS)
       {
         *status = 4; // EigenSolverErrorCode::CHFSI_ORTHONORMALIZATION_ERROR

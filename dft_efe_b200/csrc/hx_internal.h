@@ -338,6 +338,7 @@ struct hx_plan
   cudaStream_t copy_in = nullptr, copy_out = nullptr; // host-batch pipeline of hx_chebyshev_filter_host_batches
   cudaEvent_t  pipe_ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   uint32_t     n_owned = 0, n_ghost = 0, n_local = 0, n_owned_classical = 0;
+  uint64_t     n_global = 0; // sum of n_owned over the ranks (hx_plan_global_size, computed on first use)
   uint32_t     C = 0, S = 0, max_n = 0, max_block = 0;
   size_t       S2 = 0;
 
@@ -491,6 +492,7 @@ struct hx_op
   int                variant = 0;
   hx::DevBuf<double> d_diag, d_enr_block;
   uint32_t           nE = 0;
+  uint32_t           nE_global = 0, enr_offset = 0; // HX_DIAG_OEFE_GLOBAL: all enrichment functions of the system, first owned one
 };
 
 namespace hx
@@ -518,6 +520,8 @@ namespace hx
   int launch_shared_reduce(hx_plan *p, double *Y, uint32_t B);
   int launch_zero_rows(hx_plan *p, double *Y, uint32_t B, const uint32_t *rows, uint32_t n);
   int launch_enr_block(hx_plan *p, const double *blk, uint32_t nE, const double *Xenr, double *Yenr, uint32_t B);
+  int launch_enr_block_global(hx_plan *p, const double *blk, uint32_t nEg, uint32_t off, uint32_t nE, const double *Xg, double *Yenr,
+                              uint32_t B);
   // fuse != nullptr asks for the Chebyshev epilogue; *fused_applied tells whether the launched variant did it
   int launch_cell_apply(hx_op *op, const double *X, double *Y, uint32_t B, const FuseArgs *fuse = nullptr,
                         bool *fused_applied = nullptr, const HaloK *halo = nullptr);

@@ -737,6 +737,32 @@ namespace hx
     return HX_OK;
   }
 
+  // ---- global enrichment block: Yenr_owned (nE x B) = block[off .. off+nE, :] (nEg x nEg, column-major) . Xg (nEg x B) ----
+  // (gemm('N','T', B, nEg, nEg, Xg, block) of src/basis/OrthoEFEOverlapInverseOpContextGLL.t.cpp:1246-1262, owned rows only)
+  __global__ void
+  enr_block_global_kernel(const double *blk, uint32_t nEg, uint32_t off, uint32_t nE, const double *Xg, double *Yenr, uint32_t B)
+  {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)nE * B)
+      return;
+    const uint32_t j = (uint32_t)(i / B), v = (uint32_t)(i % B);
+    double         s = 0.0;
+    for (uint32_t k = 0; k < nEg; ++k)
+      s += Xg[(size_t)k * B + v] * blk[(size_t)(off + j) + (size_t)k * nEg];
+    Yenr[i] = s;
+  }
+  int
+  launch_enr_block_global(hx_plan *p, const double *blk, uint32_t nEg, uint32_t off, uint32_t nE, const double *Xg, double *Yenr,
+                          uint32_t B)
+  {
+    if (nE == 0)
+      return HX_OK;
+    enr_block_global_kernel<<<nblk((size_t)nE * B), 256, 0, p->stream>>>(blk, nEg, off, nE, Xg, Yenr, B);
+    p->launches++;
+    HX_CUDA(cudaGetLastError());
+    return HX_OK;
+  }
+
   // ---- fused Chebyshev recurrence step ---------------------------------------------------------------
   // One pass over the owned rows does, for the diagonal (mass-lumped) M^-1 of the reference,
   //   t      = C2P( dinv .* P2C(s1) ) [+ atom-block rows]      (M^-1 apply, a11)

@@ -960,19 +960,20 @@ namespace dftefe
       solve(const DeviceOperatorContext &A, std::vector<double> &eigenValues, DeviceMultiVector &eigenVectors,
             bool computeEigenVectors, const DeviceOperatorContext &B, const DeviceOperatorContext &BInv)
       {
-        utils::throwException(d_orthoType == OrthogonalizationType::CHOLESKY_GRAMSCHMIDT,
-                              "Orthogonalization type not present");
         const size_type nVec = eigenVectors.getNumberComponents();
         utils::throwException(d_eigenSubspaceGuess->getNumberComponents() == nVec, "guess and eigenVectors differ in width");
         eigenValues.resize(nVec, 0.0);
         int st = 0;
-        utils::hxCheck(hx_chfsi_solve(asNative(A, "ChebyshevFilteredEigenSolver").handle(),
+        utils::hxCheck(hx_chfsi_solve_ortho(asNative(A, "ChebyshevFilteredEigenSolver").handle(),
                                       asNative(B, "ChebyshevFilteredEigenSolver").handle(),
                                       asNative(BInv, "ChebyshevFilteredEigenSolver").handle(), d_eigenSubspaceGuess->data(),
                                       eigenVectors.data(), nVec, d_eigenVecBatchSize ? d_eigenVecBatchSize : nVec,
                                       (size_type)d_polynomialDegree, d_wantedSpectrumLowerBound, d_wantedSpectrumUpperBound,
                                       d_unWantedSpectrumUpperBound, d_isResidualChebyFilter, eigenValues.data(),
-                                      computeEigenVectors, &st));
+                                      computeEigenVectors,
+                                      d_orthoType == OrthogonalizationType::MULTIPASS_CGS ? HX_ORTHO_MULTIPASS_CGS :
+                                                                                            HX_ORTHO_CHOLESKY_GRAMSCHMIDT,
+                                      &st));
         EigenSolverError e = EigenSolverErrorMsg::isSuccessAndMsg(static_cast<EigenSolverErrorCode>(st));
         if (st != 0)
           e.msg += hx_last_error();
@@ -1267,7 +1268,10 @@ namespace dftefe
               d_wantedSpectrumUpperBound = (d_unWantedSpectrumUpperBound + eigenValuesLanczos[0]) * 0.5;
           }
         if (!d_setChebyPolDegExternally)
-          d_chebyshevPolynomialDegree = getChebyPolynomialDegree((size_type)d_unWantedSpectrumUpperBound);
+          {
+            d_chebyshevPolynomialDegree = getChebyPolynomialDegree((size_type)d_unWantedSpectrumUpperBound);
+            d_chebyshevPolynomialDegree = (size_type)(d_chebyshevPolynomialDegree * d_chebyPolyScalingFactor); // :305-306
+          }
         ChebyshevFilteredEigenSolver chfsi(d_wantedSpectrumLowerBound, d_wantedSpectrumUpperBound,
                                            d_unWantedSpectrumUpperBound, (double)d_chebyshevPolynomialDegree,
                                            LinearEigenSolverDefaults::ILL_COND_TOL, *d_waveFunctionSubspaceGuess,
@@ -1324,6 +1328,7 @@ namespace dftefe
             r = EigenSolverErrorMsg::isSuccessAndMsg(EigenSolverErrorCode::SUCCESS);
             r.msg += "Number of CHFSI passes required are " + std::to_string(iPass + 1) + ".";
           }
+        d_chebyPolyScalingFactor = 1.0; // :533
         return r;
       }
       double
@@ -1354,7 +1359,15 @@ namespace dftefe
       {
         return d_numPasses;
       }
-      // the global number of DoFs (MultiVector::globalSize); set by the caller for multi-rank runs
+      // KohnShamEigenSolver::setChebyPolyScalingFactor (src/ksdft/KohnShamEigenSolver.t.cpp:178-186): the degree from the
+      // lookup table is multiplied by it in the next solve (1.34 on the first pseudopotential SCF step), then it resets to 1
+      void
+      setChebyPolyScalingFactor(double scalingFactor)
+      {
+        d_chebyPolyScalingFactor = scalingFactor;
+      }
+      // the global number of DoFs is MultiVector::globalSize() (all-reduced over the plan's communicator); an override is
+      // kept for callers that know it
       void
       setGlobalSize(size_t n)
       {
@@ -1365,7 +1378,11 @@ namespace dftefe
       size_t
       d_globalSize(const linearAlgebra::DeviceMultiVector &X) const
       {
-        return d_globalSizeOverride ? d_globalSizeOverride : X.locallyOwnedSize();
+        if (d_globalSizeOverride)
+          return d_globalSizeOverride;
+        uint64_t n = 0;
+        utils::hxCheck(hx_plan_global_size(X.getDeviceContext()->plan(), &n));
+        return (size_t)n;
       }
       bool
       solveFermiEnergy(const std::vector<double> &eps)
@@ -1404,6 +1421,7 @@ namespace dftefe
       double              d_wantedSpectrumLowerBound = 0, d_wantedSpectrumUpperBound = 0, d_unWantedSpectrumUpperBound = 0;
       double              d_fermiEnergy = 0;
       size_t              d_globalSizeOverride = 0;
+      double              d_chebyPolyScalingFactor = 1.0;
       linearAlgebra::DeviceMultiVector *d_waveFunctionSubspaceGuess, *d_lanczosGuess;
       const OpContext *                 d_MLanczos, *d_MInvLanczos;
     };

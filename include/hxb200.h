@@ -90,6 +90,9 @@ typedef enum hx_diag_variant {
   HX_DIAG_OEFE_ATOMBLOCK = 1, /* OEFEAtomBlockOverlapInvOpContextGLL::apply (src/basis/OEFEAtomBlockOverlapInvOpContextGLL.t.cpp:953-1108) */
   HX_DIAG_OEFE_MASS      = 2, /* OrthoEFEOverlapOperatorContext::apply, mass-lumped atom-block branch: as ATOMBLOCK
                                  but both ghost flags are forced to false (src/basis/OrthoEFEOverlapOperatorContext.t.cpp:2093-2235) */
+  HX_DIAG_OEFE_GLOBAL    = 4, /* OrthoEFEOverlapInverseOpContextGLL::apply (src/basis/OrthoEFEOverlapInverseOpContextGLL.t.cpp:1182-1282):
+                               diagonal + ONE dense block over all enrichment functions of the system; created with
+                               hx_diagop_create_global_enrichment */
   HX_DIAG_JACOBI         = 3  /* linearAlgebra::PreconditionerJacobi::apply: Y = diag .* X over local rows, ghost flags
                                  honoured, no constraints (src/linearAlgebra/PreconditionerJacobi.t.cpp:52-82); pass the
                                  RECIPROCAL diagonal (the reference inverts it in the constructor, :40-45) */
@@ -130,6 +133,10 @@ int hx_plan_synchronize(hx_plan *plan);
  * MPIPatternP2P (src/utils/MPIPatternP2P.h:489).  Ranks of the halo descriptors are communicator ranks. */
 int hx_comm_unique_id(char id[128]);
 int hx_plan_attach_comm(hx_plan *plan, const char id[128]);
+/* MultiVector::globalSize() (src/linearAlgebra/MultiVector.h): locally owned rows summed over the ranks of the plan's
+ * communicator (collective on first use, cached).  KohnShamEigenSolver scales wantedSpectrumUpperBound with it
+ * (src/ksdft/KohnShamEigenSolver.t.cpp:270-283). */
+int hx_plan_global_size(hx_plan *plan, uint64_t *n);
 /* Transport the ghost communicator settled on at its first exchange: 0 = none yet / single rank, 1 = NCCL send/recv,
  * 2 = NVLink peer memory (the pack kernel stores straight into the neighbour's receive buffer and raises a flag; the
  * unpack / ordered-add kernel waits for it).  HXB200_HALO=nccl forces 1; 2 needs CUDA IPC between the ranks. */
@@ -195,6 +202,13 @@ int hx_cellop_set_constraint_sets(hx_op *op, uint32_t x_set, uint32_t y_set);
 /* Mass-lumped M / M^-1 style operator: diagonal over local rows + atom-block enrichment matrix
  * (nE_owned x nE_owned, column-major; may be NULL when nE_owned == 0). Host pointers. */
 int hx_diagop_create(hx_plan *plan, const double *diag, const double *enr_block, int variant, hx_op **op);
+/* OrthoEFEOverlapInverseOpContextGLL (src/basis/OrthoEFEOverlapInverseOpContextGLL.t.cpp:1182-1282): M^-1 = diag_inv on
+ * every local row + enr_block_global (nE_global x nE_global, column-major) on the enrichment rows of the WHOLE system.
+ * apply(): every rank places its owned enrichment rows (global enrichment indices owned_enr_offset ..) into an
+ * nE_global x B vector, the vector is all-reduced over the plan's communicator (the reference's MPI_Allreduce, :1228-1234),
+ * and each rank keeps its own rows of block . Xenr; then ghost update, child->parent condensation. */
+int hx_diagop_create_global_enrichment(hx_plan *plan, const double *diag_inv, const double *enr_block_global, uint32_t nE_global,
+                                       uint32_t owned_enr_offset, hx_op **op);
 int hx_op_destroy(hx_op *op);
 /* OperatorContext::apply(X, Y, updateGhostX, updateGhostY): X may be modified (ghost update + hanging-node
  * fill, OperatorContext.h:98-101); Y fully overwritten; Y's owned rows final, ghost rows hold the rank's
@@ -280,6 +294,19 @@ int hx_rayleigh_ritz(hx_op *A, double *X, double *eigenVectors, uint32_t B, uint
 int hx_chfsi_solve(hx_op *A, hx_op *Bop, hx_op *BInv, double *eigenSubspaceGuess, double *eigenVectors, uint32_t B,
                    uint32_t batch, uint32_t degree, double wantedLower, double wantedUpper, double unwantedUpper,
                    int residualFilter, double *eigenvalues_host, int computeEigenVectors, int *status);
+/* The same with the orthogonalisation of the reference's constructor argument (ChebyshevFilteredEigenSolver.t.cpp:350-371):
+ * HX_ORTHO_CHOLESKY_GRAMSCHMIDT (hx_chfsi_solve) or HX_ORTHO_MULTIPASS_CGS with MultiPassOrthoDefaults. */
+#define HX_ORTHO_CHOLESKY_GRAMSCHMIDT 0
+#define HX_ORTHO_MULTIPASS_CGS 1
+int hx_chfsi_solve_ortho(hx_op *A, hx_op *Bop, hx_op *BInv, double *eigenSubspaceGuess, double *eigenVectors, uint32_t B,
+                         uint32_t batch, uint32_t degree, double wantedLower, double wantedUpper, double unwantedUpper,
+                         int residualFilter, double *eigenvalues_host, int computeEigenVectors, int orthoType, int *status);
+/* OrthonormalizationFunctions::MultipassCGS (src/linearAlgebra/OrthonormalizationFunctions.t.cpp:440-785): repeated
+ * Cholesky-Gram-Schmidt passes with the diagonal of X^T B X shifted while its smallest eigenvalue is below shiftTolerance.
+ * status: OrthonormalizationErrorCode (0 SUCCESS, 1 LAPACK_ERROR, 2 NON_ORTHONORMALIZABLE_MULTIVECTOR, 3 MAX_PASS_EXCEEDED);
+ * passes (optional): Cholesky passes performed. */
+int hx_multipass_cgs(hx_op *Bop, double *X, double *orthogonalizedX, uint32_t B, uint32_t batch, uint32_t maxPass,
+                     double shiftTolerance, double identityTolerance, int *status, uint32_t *passes);
 /* KohnShamEigenSolver::getLinearEigenSolveResidual (src/ksdft/KohnShamEigenSolver.t.cpp:574-682):
  * norms[j] = || H x_j - lambda_j M x_j ||_2 over owned rows, in column batches. */
 int hx_eigen_residual_norms(hx_op *A, hx_op *Mop, const double *X, uint32_t B, uint32_t batch,

@@ -144,6 +144,37 @@ def cholesky_gram_schmidt(W, Xs, apply_M, batch):
     return 0, Linv
 
 
+def multipass_cgs(W, Xs, apply_M, batch, max_pass=50, shift_tol=1e-12, identity_tol=1e-12):
+    """OrthonormalizationFunctions::MultipassCGS (linearAlgebra/OrthonormalizationFunctions.t.cpp:440-785), in place.
+    Returns (status, passes): 0 SUCCESS, 1 LAPACK error, 2 non-orthonormalizable, 3 MAX_PASS_EXCEEDED."""
+    B = Xs[0].shape[1]
+    if sum(W.n_owned) < B:
+        return 2, 0
+    i_pass = 1
+    while i_pass <= max_pass:
+        S = W.xtopx(Xs, apply_M, batch)                       # lower triangle
+        full = S + S.T - np.diag(np.diag(S))                  # overlapMatPar + its transpose, diagonal halved (:531-552)
+        d = np.diag(full)
+        err = np.sqrt(np.sum(full * full) + np.sum((d - 1.0) ** 2))  # the reference's estimate as written (:541-578)
+        if err < identity_tol * np.sqrt(B):
+            break
+        ev_min = sla.eigvalsh(full)[0]
+        last = ev_min > shift_tol
+        shift = 0.0 if last else shift_tol - ev_min
+        try:
+            L = sla.cholesky(full + shift * np.eye(B), lower=True)
+        except sla.LinAlgError:
+            return 1, i_pass
+        Linv = np.tril(sla.lapack.dtrtri(L, lower=1)[0])
+        W.subspace_rotation(Xs, Linv, False, True)
+        if last:
+            break
+        i_pass += 1
+    if i_pass > max_pass:
+        return 3, max_pass
+    return 0, i_pass
+
+
 def rayleigh_ritz(W, Xs, apply_A, batch, compute_vectors=True):
     S = W.xtopx(Xs, apply_A, batch)
     full = S + S.T - np.diag(np.diag(S))  # projHam + projHam^T, diagonal halved

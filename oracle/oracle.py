@@ -382,6 +382,38 @@ class OracleWorld:
         if update_ghost_y:
             self.update_ghost_values(Ys)
 
+    def minv_apply_global_enrichment(self, Xs, Ys, block_global, update_ghost_x=False, update_ghost_y=False):
+        """OrthoEFEOverlapInverseOpContextGLL::apply (basis/OrthoEFEOverlapInverseOpContextGLL.t.cpp:1182-1282): diag_inv on
+        every local row, then one dense block over ALL enrichment functions of the system - the owned enrichment rows of every
+        rank placed at their global offset, summed over the ranks (MPI_Allreduce, :1228-1234), times block^T (gemm 'N','T'),
+        own rows kept; ghost update, child->parent."""
+        B = Xs[0].shape[1]
+        nEs = [r.n_owned - r.p.n_owned_classical for r in self.ranks]
+        offs = np.concatenate(([0], np.cumsum(nEs)))
+        nEg = int(offs[-1])
+        blk = np.asarray(block_global, dtype=np.float64).reshape(nEg, nEg, order="F")   # column-major like the reference
+        if update_ghost_x:
+            self.update_ghost_values(Xs)
+        xg = np.zeros((nEg, B))
+        for i, r in enumerate(self.ranks):
+            r.p2c(Xs[i])
+            Ys[i][...] = 0.0
+            d = np.ascontiguousarray(r.p.diag_inv, dtype=np.float64)
+            lib().orc_row_scale(_f64(d), _f64(Xs[i]), _f64(Ys[i]), C.c_uint32(B), C.c_size_t(r.n_local))
+            ncl = r.p.n_owned_classical
+            xg[offs[i]:offs[i + 1]] += Xs[i][ncl:ncl + nEs[i]]          # the all-reduce
+        for i, r in enumerate(self.ranks):
+            ncl = r.p.n_owned_classical
+            for j in range(nEs[i]):                                    # Y[j,v] = sum_k block[j,k] X[k,v], k ascending
+                acc = np.zeros(B)
+                for k in range(nEg):
+                    acc += xg[k] * blk[offs[i] + j, k]
+                Ys[i][ncl + j] = acc
+        self.update_ghost_values(Ys)
+        self._each_rank(lambda i: self.ranks[i].c2p(Ys[i]))
+        if update_ghost_y:
+            self.update_ghost_values(Ys)
+
     def minv_apply(self, Xs, Ys, update_ghost_x=False, update_ghost_y=False, variant="oefe_atomblock"):
         self.diag_apply(Xs, Ys, [p.diag_inv for p in self.problems], [p.enr_block_inv for p in self.problems],
                         update_ghost_x, update_ghost_y, variant)

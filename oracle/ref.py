@@ -154,6 +154,70 @@ def hx_apply_serial(prob, X, cell_block=3, use_nonlocal=True, out=None):
     return Y
 
 
+class PartitionedApply:
+    """KohnShamOperatorContextFE::apply over a PARTITIONED mesh with every rank-local routine the reference's own
+    (ref_hx_phase_a / ref_hx_phase_b of ref_shim_cellwise.cpp) and the exchanges of an oracle.OracleWorld (the in-process
+    stand-in for MPI): ghost update, phase A on every rank, projector all-reduce + V scaling, phase B, accumulate.  Used by
+    `bench.py --impl reference` (one partition per host core, rank-local phases on a thread pool: the C routines release the
+    GIL) and pinned against the oracle's hx_apply in tests/test_oracle.py."""
+
+    def __init__(self, world, cell_block=1):
+        self.W = world
+        self.cell_block = cell_block
+        self.args = []
+        for q in world.problems:
+            ids, ip = u32(q.cell_local_ids); ncd, ncdp = u32(q.num_cell_dofs)
+            r, rp = u32(q.row_ids); s_, sp = u32(q.row_sizes); o, op = u32(q.row_offsets); c, cp = u32(q.col_ids)
+            v = np.ascontiguousarray(q.col_vals); ih = np.ascontiguousarray(q.inhom)
+            h = np.ascontiguousarray(q.h_cell)
+            nl = q.num_cell_proj is not None
+            d = dict(ids=(ids, ip), ncd=(ncd, ncdp), rows=(r, rp), sizes=(s_, sp), offs=(o, op), cols=(c, cp), v=v, ih=ih, h=h, nl=nl,
+                     n=q.n_local, C=len(ncd), S=int(np.sum(q.num_cell_dofs.astype(np.int64))))
+            if nl:
+                d["ncp"] = u32(q.num_cell_proj); d["pids"] = u32(q.cell_proj_local_ids)
+                d["cc"] = np.ascontiguousarray(q.cell_c); d["V"] = np.ascontiguousarray(q.proj_v); d["nproj"] = q.proj_halo.n_local
+            self.args.append(d)
+        self.xcell = None
+
+    def __call__(self, Xs, Ys, update_ghost_x=False, update_ghost_y=False):
+        from . import oracle as orc
+        W, B = self.W, Xs[0].shape[1]
+        if self.xcell is None or self.xcell[0].shape[0] != self.args[0]["S"] * B:
+            self.xcell = [np.empty(d["S"] * B) for d in self.args]
+            self.cx = [np.zeros((d.get("nproj", 0), B)) for d in self.args]
+        if update_ghost_x:
+            W.update_ghost_values(Xs)
+        L = lib()
+
+        def a(i):
+            d = self.args[i]
+            L.ref_hx_phase_a(f64(Xs[i]), f64(Ys[i]), C.c_uint32(d["n"]), C.c_uint32(B), C.c_uint32(d["C"]), d["ncd"][1], d["ids"][1],
+                             C.c_uint32(len(d["rows"][0])), d["rows"][1], d["sizes"][1], d["offs"][1], d["cols"][1],
+                             C.c_uint32(len(d["cols"][0])), f64(d["v"]), f64(d["ih"]),
+                             d["ncp"][1] if d["nl"] else None, d["pids"][1] if d["nl"] else None, f64(d["cc"]) if d["nl"] else None,
+                             C.c_uint32(d.get("nproj", 0)), C.c_uint32(self.cell_block), f64(self.xcell[i]),
+                             f64(self.cx[i]) if d["nl"] else None)
+        W._each_rank(a)
+        if W.has_nonlocal:
+            if W.nr > 1:
+                orc._exchange_accumulate(W.phalos, self.cx, W.np_owned)
+                orc._exchange_update(W.phalos, self.cx, W.np_owned)
+            for d, cx in zip(self.args, self.cx):
+                L.ref_scale_rows_strided(f64(d["V"]), f64(cx), C.c_uint32(B), C.c_uint32(d["nproj"]))
+
+        def b(i):
+            d = self.args[i]
+            L.ref_hx_phase_b(f64(Ys[i]), C.c_uint32(d["n"]), C.c_uint32(B), C.c_uint32(d["C"]), d["ncd"][1], d["ids"][1], f64(d["h"]),
+                             C.c_uint32(len(d["rows"][0])), d["rows"][1], d["sizes"][1], d["offs"][1], d["cols"][1],
+                             C.c_uint32(len(d["cols"][0])), f64(d["v"]),
+                             d["ncp"][1] if d["nl"] else None, d["pids"][1] if d["nl"] else None, f64(d["cc"]) if d["nl"] else None,
+                             C.c_uint32(self.cell_block), f64(self.xcell[i]), f64(self.cx[i]) if d["nl"] else None)
+        W._each_rank(b)
+        W.accumulate_add_locally_owned(Ys)
+        if update_ghost_y:
+            W.update_ghost_values(Ys)
+
+
 def cg_solve(apply_A, apply_PC, b, x0, max_iter, abs_tol, rel_tol, div_tol):
     """The reference's own CGLinearSolver::solve (linearAlgebra/CGLinearSolver.t.cpp) on one rank over Python
     operators: apply_X(X, Y, update_ghost_x, update_ghost_y) with [n, B] arrays.  Returns (x, isSuccess)."""

@@ -172,4 +172,87 @@ extern "C"
       }
     ref_c2p(Y, nLocal, B, nR, rowIds, rowSizes, rowOffsets, colIds, nnz, colVals); // :1424-1425
   }
+
+  // The same apply split at its collective point, for a rank of a PARTITIONED run (the caller performs the ghost update
+  // before phase A, applyAllReduceOnCconjtransX between the phases and accumulateAddLocallyOwned after phase B, as
+  // KohnShamOperatorContextFE::apply does through MPI, :1340-1443).  xCell (S*B doubles) carries the gathered cell data
+  // from phase A to phase B like d_XCellWise does in the reference; CX: nProjLocal*B partial sums out of phase A, the
+  // reduced and V-scaled coefficients into phase B.
+  void
+  ref_hx_phase_a(double *X, double *Y, unsigned nLocal, unsigned B, unsigned C, const unsigned *ncd, const unsigned *ids,
+                 unsigned nR, const unsigned *rowIds, const unsigned *rowSizes, const unsigned *rowOffsets,
+                 const unsigned *colIds, unsigned nnz, const double *colVals, const double *inhom, const unsigned *ncp,
+                 const unsigned *pids, const double *cellC, unsigned nProjLocal, unsigned cellBlockSize, double *xCell, double *CX)
+  {
+    ref_p2c(X, nLocal, B, nR, rowIds, rowSizes, rowOffsets, colIds, nnz, colVals, inhom);
+    std::memset(Y, 0, sizeof(double) * (size_t)nLocal * B);
+    const bool nl = ncp != nullptr;
+    unsigned   maxProj = 0;
+    if (nl)
+      {
+        std::memset(CX, 0, sizeof(double) * (size_t)nProjLocal * B);
+        for (unsigned c = 0; c < C; ++c)
+          maxProj = std::max(maxProj, ncp[c]);
+      }
+    std::vector<double> CXCell((size_t)cellBlockSize * B * std::max(maxProj, 1u));
+    size_t              idsOff = 0, pOff = 0, cOff = 0;
+    for (unsigned c0 = 0; c0 < C; c0 += cellBlockSize)
+      {
+        const unsigned nb = std::min(cellBlockSize, C - c0);
+        CellOps::copyFieldToCellWiseData(X, B, ids + idsOff, sizes(ncd + c0, nb), xCell + idsOff * B);
+        if (nl)
+          {
+            cell_gemm(nb, B, ncd + c0, ncp + c0, true, 0.0, xCell + idsOff * B, cellC + cOff, CXCell.data());
+            CellOps::addCellWiseDataToFieldData(CXCell.data(), B, pids + pOff, sizes(ncp + c0, nb), CX);
+          }
+        for (unsigned i = 0; i < nb; ++i)
+          {
+            idsOff += ncd[c0 + i];
+            if (nl)
+              {
+                pOff += ncp[c0 + i];
+                cOff += (size_t)ncp[c0 + i] * ncd[c0 + i];
+              }
+          }
+      }
+  }
+  void
+  ref_hx_phase_b(double *Y, unsigned nLocal, unsigned B, unsigned C, const unsigned *ncd, const unsigned *ids,
+                 const double *hcell, unsigned nR, const unsigned *rowIds, const unsigned *rowSizes,
+                 const unsigned *rowOffsets, const unsigned *colIds, unsigned nnz, const double *colVals, const unsigned *ncp,
+                 const unsigned *pids, const double *cellC, unsigned cellBlockSize, const double *xCell, const double *CX)
+  {
+    const bool nl = ncp != nullptr;
+    unsigned   maxDof = 0, maxProj = 0;
+    for (unsigned c = 0; c < C; ++c)
+      {
+        maxDof = std::max(maxDof, ncd[c]);
+        if (nl)
+          maxProj = std::max(maxProj, ncp[c]);
+      }
+    std::vector<double> yCell((size_t)cellBlockSize * B * maxDof), CXCell((size_t)cellBlockSize * B * std::max(maxProj, 1u));
+    size_t              idsOff = 0, pOff = 0, cOff = 0, hOff = 0;
+    for (unsigned c0 = 0; c0 < C; c0 += cellBlockSize)
+      {
+        const unsigned nb = std::min(cellBlockSize, C - c0);
+        cell_gemm(nb, B, ncd + c0, ncd + c0, false, 0.0, xCell + idsOff * B, hcell + hOff, yCell.data());
+        if (nl)
+          {
+            CellOps::copyFieldToCellWiseData(CX, B, pids + pOff, sizes(ncp + c0, nb), CXCell.data());
+            cell_gemm(nb, B, ncp + c0, ncd + c0, false, 1.0, CXCell.data(), cellC + cOff, yCell.data());
+          }
+        CellOps::addCellWiseDataToFieldData(yCell.data(), B, ids + idsOff, sizes(ncd + c0, nb), Y);
+        for (unsigned i = 0; i < nb; ++i)
+          {
+            idsOff += ncd[c0 + i];
+            hOff += (size_t)ncd[c0 + i] * ncd[c0 + i];
+            if (nl)
+              {
+                pOff += ncp[c0 + i];
+                cOff += (size_t)ncp[c0 + i] * ncd[c0 + i];
+              }
+          }
+      }
+    ref_c2p(Y, nLocal, B, nR, rowIds, rowSizes, rowOffsets, colIds, nnz, colVals);
+  }
 }

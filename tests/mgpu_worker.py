@@ -102,6 +102,24 @@ def main():
     F = W.chebyshev_filter([x.copy() for x in Xs], 6, -3.0, 1.0, 60.0)
     errs["cheb"] = rel(dF.download()[:mine.n_owned], F[rank][:mine.n_owned])
 
+    # ---- OrthoEFEOverlapInverseOpContextGLL: one dense block over the enrichment functions of ALL ranks (all-reduce) ----
+    nEs = [q.n_owned - q.n_owned_classical for q in probs]
+    nEg = int(sum(nEs))
+    if nEg:
+        rng = np.random.default_rng(23)
+        Rm = rng.standard_normal((nEg, nEg))
+        blk = np.asfortranarray(Rm @ Rm.T / nEg + np.eye(nEg) + 0.05 * rng.standard_normal((nEg, nEg)))
+        MIg = capi.DiagOpGlobalEnrichment(plan, mine.diag_inv, blk.ravel(order="F"), nEg, int(sum(nEs[:rank])))
+        dX, dY = plan.block(B, Xs[rank]), plan.block(B)
+        MIg.apply(dX, dY, True, True)
+        Xo = [x.copy() for x in Xs]
+        Yo = [np.zeros_like(x) for x in Xs]
+        W.minv_apply_global_enrichment(Xo, Yo, blk.ravel(order="F"), True, True)
+        errs["minv_global_enrichment"] = rel(dY.download(), Yo[rank])
+        MIg.destroy()
+    else:
+        errs["minv_global_enrichment"] = 0.0
+
     # ---- X^T H X (NCCL all-reduce of the Gram blocks) and column norms ----
     dX = plan.block(B, Xs[rank])
     S = H.xtopx(dX, 8)
@@ -163,7 +181,7 @@ def main():
     if want:
         assert plan.halo_transport() == want and plan2.halo_transport() == want, (plan.halo_transport(), want)
 
-    tol = {"overlap_vs_serial": 0.0, "update_ghost": 0.0, "cheb_fused": 1e-11, "accumulate_add": 1e-14, "hx": 1e-12, "hx_x_modified": 1e-14, "cheb": 1e-11,
+    tol = {"minv_global_enrichment": 1e-13, "overlap_vs_serial": 0.0, "update_ghost": 0.0, "cheb_fused": 1e-11, "accumulate_add": 1e-14, "hx": 1e-12, "hx_x_modified": 1e-14, "cheb": 1e-11,
            "xtopx": 1e-12, "l2": 1e-13, "lanczos": 1e-10, "chfsi_ritz": 1e-9, "eig_residuals": 1e-6}
     bad = {k: v for k, v in errs.items() if not v <= tol[k]}
     print(f"[rank {rank}/{world}] halo transport {plan.halo_transport()} " + " ".join(f"{k}={v:.2e}" for k, v in errs.items()), flush=True)

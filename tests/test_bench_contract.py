@@ -24,7 +24,11 @@ def _check_reference_line(r, kind):
     assert d["impl"] == "reference" and d["metric"] == "hx_throughput_fp64" and d["unit"] == "GDoF*vec/s"
     assert d["higher_is_better"] is True and d["dtype"] == "f64" and d["data"] == "synthetic"
     assert d["steps"] == 2 and d["warmup"] == 1 and d["n_gpus"] == 1 and d["vs_baseline"] is None
-    assert "workload" in d["config"] and "2 filter call" in d["config"]["sample"]
+    assert "workload" in d["config"] and "2 filter call" in d["reference_run"]["sample"]
+    # both arms print the same `config` object (it depends on the workload and N only)
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["config"] == bench.shared_config("small", 1)
     cb = d["cpu_baseline"]
     assert cb["kind"] == kind and cb["cores"] == (os.cpu_count() or 1) and cb["value"] == d["value"] > 0
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
@@ -38,7 +42,8 @@ def test_reference_arm_prints_one_contract_line():
     r = run_bench("--impl", "reference", "--steps", "2", "--warmup", "1", "--workload", "small")
     d = _check_reference_line(r, "reference" if ref.available() else "port")
     if ref.available():
-        assert "oracle/_ref" in d["config"]["sample"] and "CELL_BATCH_SIZE=1" in d["config"]["sample"]
+        assert "oracle/_ref" in d["reference_run"]["sample"] and "CELL_BATCH_SIZE=1" in d["reference_run"]["sample"]
+        assert "the whole workload" in d["reference_run"]["sample"]  # the same mesh the GPU arm times, cut into one partition per core
 
 
 def test_reference_arm_falls_back_to_the_oracle_port():

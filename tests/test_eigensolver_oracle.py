@@ -143,3 +143,27 @@ def test_cheby_degree_lookup_and_fermi():
     assert ok and -0.5 < mu < -0.2
     occ = sum(2 * es.fermi_dirac(e, mu, es.BOLTZMANN_CONST_HARTREE, 1000.0) for e in ev)
     assert abs(occ - 4) < 1e-9
+
+
+def test_multipass_cgs_orthonormalises_a_nearly_dependent_block():
+    """oracle.eigensolver.multipass_cgs (OrthonormalizationFunctions.t.cpp:440-785): one pass for a well conditioned block,
+    a shifted first pass + more passes for a block with two nearly parallel columns; the result is M-orthonormal."""
+    from dft_efe_b200 import synth
+    from oracle import eigensolver as es, oracle as orc
+    nc = (3, 3, 3)
+    atoms = np.array([[1.5, 1.5, 1.5]])
+    spec = synth.MeshSpec(ncell=nc, p=2, atoms=atoms, n_enr_per_atom=1, enr_cutoff=1.2)
+    p = synth.build_problem(spec)[0]
+    W = orc.OracleWorld([p])
+    Mop = lambda a, b, gx, gy: W.m_apply(a, b, gx, gy)  # noqa: E731
+    B = 6
+    X = synth.make_block(p, B)
+    Xb = X.copy()
+    Xb[:, 1] = Xb[:, 0] * (1.0 + 1e-9) + 1e-7 * X[:, 1]
+    for blk, min_passes in ((X, 1), (Xb, 2)):
+        Xs = [blk.copy()]
+        st, passes = es.multipass_cgs(W, Xs, Mop, B)
+        assert st == 0 and passes >= min_passes
+        S = W.xtopx([Xs[0].copy()], Mop, B)
+        S = S + S.T - np.diag(np.diag(S))
+        assert np.abs(S - np.eye(B)).max() < 1e-10

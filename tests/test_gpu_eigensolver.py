@@ -104,6 +104,41 @@ def test_cholesky_gram_schmidt_and_rayleigh_ritz(capi, setup, B, batch):
     assert capi.cholesky_gram_schmidt(M, plan.block(B, Xd), plan.block(B), batch) != 0
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,batch", [(8, 3), (24, 24)])
+def test_multipass_cgs_matches_oracle(capi, setup, B, batch):
+    """OrthonormalizationFunctions::MultipassCGS (OrthonormalizationFunctions.t.cpp:440-785): a well conditioned block
+    needs one pass; a block with nearly dependent columns is shifted and re-orthonormalised in further passes.  Same pass
+    count and same block as the oracle; the result is M-orthonormal to 1e-10; a ChFSI pass with MULTIPASS_CGS gives the
+    Ritz values of the CholGS pass."""
+    p, W, plan, H, M, MInv = setup
+    Mop = lambda a, b, gx, gy: W.m_apply(a, b, gx, gy)  # noqa: E731
+    n = p.n_owned
+    X = synth.make_block(p, B)
+    Xbad = X.copy()
+    Xbad[:, 1] = Xbad[:, 0] * (1.0 + 1e-9) + 1e-7 * X[:, 1]   # kappa(X^T M X) ~ 1e14: CholGS alone loses orthogonality
+    for blk, min_passes in ((X, 1), (Xbad, 2)):
+        dX, dO = plan.block(B, blk), plan.block(B)
+        st, passes = capi.multipass_cgs(M, dX, dO, batch)
+        Xo = [blk.copy()]
+        sto, passes_o = es.multipass_cgs(W, Xo, Mop, batch)
+        assert st == 0 and sto == 0 and passes == passes_o and passes >= min_passes, (st, sto, passes, passes_o)
+        got = dO.download()
+        assert np.array_equal(dX.download(), got)
+        if min_passes == 1:
+            assert np.abs(got[:n] - Xo[0][:n]).max() < 1e-9 * np.abs(Xo[0][:n]).max()
+        G = [got.copy()]
+        S = W.xtopx(G, Mop, batch)
+        S = S + S.T - np.diag(np.diag(S))
+        assert np.abs(S - np.eye(B)).max() < 1e-10
+    dG, dV = plan.block(B, X), plan.block(B)
+    w1, st1 = capi.chfsi_solve(H, M, MInv, dG, dV, batch, 12, -1.0, 6.0, 2500.0, None, False, True, multipass_cgs=True)
+    dG, dV = plan.block(B, X), plan.block(B)
+    w0, st0 = capi.chfsi_solve(H, M, MInv, dG, dV, batch, 12, -1.0, 6.0, 2500.0, None, False, True)
+    assert st0 == 0 and st1 == 0 and np.abs(w1 - w0).max() < 1e-9 * np.abs(w0).max()
+    assert plan.global_size() == p.n_owned
+
+
 @pytest.mark.parametrize("residual_filter", [False, True])
 def test_chfsi_pass_matches_oracle(capi, setup, residual_filter):
     p, W, plan, H, M, MInv = setup

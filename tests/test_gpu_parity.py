@@ -254,6 +254,32 @@ def test_hx_host_entry_point(capi, prob_full):
     assert rel_l2_per_vector(Xh, Xo) < 1e-14
 
 
+@pytest.mark.parametrize("p_order,B", [(6, 128), (4, 256), (5, 256), (7, 32), (8, 16)])
+def test_hx_and_filter_at_the_baseline_block_widths(capi, p_order, B):
+    """The shapes of BASELINE configs[2] (order 6, B = 128) and of a configs[3] column batch (order 5, B = 256), wide blocks at
+    order 4 and the large cells of the sweep at narrow B: H.X within 1e-12 and the fused Chebyshev filter within 1e-11 of the
+    oracle, on a mesh with hanging nodes, enrichment and projectors (several column tiles, several m-chunks per cell)."""
+    nc = (3, 3, 3)
+    atoms = np.array([[1.5, 1.5, 1.5]])
+    spec = synth.MeshSpec(ncell=nc, p=p_order, refine_mask=synth.refine_ball(nc, 1.0, atoms, 0.9), atoms=atoms,
+                          n_enr_per_atom=2, enr_cutoff=1.2, n_proj_per_atom=2, proj_cutoff=1.0)
+    p = synth.build_problem(spec)[0]
+    plan = capi.Plan(p, max_block=B)
+    H = capi.CellOp(plan)
+    minv = capi.DiagOp(plan, p.diag_inv, p.enr_block_inv, capi.DIAG_OEFE_ATOMBLOCK)
+    X = synth.make_block(p, B)
+    dX, dY = plan.block(B, X), plan.block(B)
+    H.apply(dX, dY, True, False)
+    W = orc.OracleWorld([p])
+    Xo, Yo = X.copy(), np.zeros_like(X)
+    W.hx_apply([Xo], [Yo], True, False)
+    assert rel_l2_per_vector(dY.download(), Yo) < RTOL_HX
+    dX, dF = plan.block(B, X), plan.block(B)
+    capi.chebyshev_filter(H, minv, dX, dF, 4, -3.0, 1.0, 60.0)
+    F = W.chebyshev_filter([X.copy()], 4, -3.0, 1.0, 60.0)[0]
+    assert rel_l2_per_vector(dF.download()[:p.n_owned], F[:p.n_owned]) < 1e-11
+
+
 @pytest.mark.parametrize("p_order", [1, 2, 5, 6])
 def test_hx_other_orders(capi, p_order):
     nc = (3, 3, 3) if p_order >= 5 else (4, 4, 4)
@@ -314,6 +340,33 @@ def test_diag_ops(capi, prob_full, variant):
     Xo, Yo = X.copy(), np.zeros_like(X)
     W.m_apply([Xo], [Yo], True, True)
     assert rel_l2_per_vector(dY.download(), Yo) < 1e-14
+
+
+@pytest.mark.parametrize("B", [1, 8, 32])
+def test_global_enrichment_overlap_inverse(capi, prob_full, B):
+    """HX_DIAG_OEFE_GLOBAL = OrthoEFEOverlapInverseOpContextGLL::apply (OrthoEFEOverlapInverseOpContextGLL.t.cpp:1182-1282):
+    diagonal + one dense block over all enrichment functions; also as the M^-1 of the (then unfused) Chebyshev filter."""
+    p = prob_full
+    nE = p.n_owned - p.n_owned_classical
+    assert nE > 0
+    rng = np.random.default_rng(17)
+    Rm = rng.standard_normal((nE, nE))
+    blk = np.asfortranarray(Rm @ Rm.T / nE + np.eye(nE) + 0.05 * rng.standard_normal((nE, nE)))  # not symmetric: order matters
+    plan = capi.Plan(p, max_block=B)
+    MI = capi.DiagOpGlobalEnrichment(plan, p.diag_inv, blk.ravel(order="F"), nE, 0)
+    X = synth.make_block(p, B)
+    dX, dY = plan.block(B, X), plan.block(B)
+    MI.apply(dX, dY, True, True)
+    W = orc.OracleWorld([p])
+    Xo, Yo = X.copy(), np.zeros_like(X)
+    W.minv_apply_global_enrichment([Xo], [Yo], blk.ravel(order="F"), True, True)
+    assert rel_l2_per_vector(dY.download(), Yo) < 1e-13
+    assert np.array_equal(dX.download(), Xo)
+    if B % 2 == 0:
+        H = capi.CellOp(plan)
+        dX, dF = plan.block(B, X), plan.block(B)
+        capi.chebyshev_filter(H, MI, dX, dF, 4, -3.0, 1.0, 60.0)
+        assert np.isfinite(dF.download()).all()
 
 
 def test_hx_against_reference_golden_fixture(capi):

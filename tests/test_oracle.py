@@ -488,3 +488,32 @@ def test_xtopx_and_rotation(probs):
     W.subspace_rotation(Xr, Ql, transpose=False, lower_tri=True, dof_block=100, vec_block=4)
     for p, xr, x in zip(ps, Xr, Xs):
         assert np.abs(xr[:p.n_owned] - x[:p.n_owned] @ Ql.T).max() < 1e-12
+
+
+def test_partitioned_reference_apply_matches_the_oracle_world():
+    """ref.PartitionedApply (bench.py --impl reference): KohnShamOperatorContextFE::apply over a partitioned mesh with the
+    rank-local phases through the reference's compiled routines and the exchanges of the oracle world == the oracle's
+    hx_apply, bit for bit (same arithmetic routines underneath), X side effects included."""
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref not built")
+    nc = (4, 4, 6)
+    atoms = np.array([[2.0, 2.0, 3.0], [1.2, 2.8, 1.6]])
+    spec = synth.MeshSpec(ncell=nc, p=3, refine_mask=synth.refine_ball(nc, 1.0, [atoms[0]], 0.9), atoms=atoms, n_enr_per_atom=3,
+                          enr_cutoff=1.2, n_proj_per_atom=2, proj_cutoff=1.0, nranks=3)
+    probs = synth.build_problem(spec)
+    W = orc.OracleWorld(probs)
+    B = 5
+    Xs = [synth.make_block(q, B) for q in probs]
+    for q, x in zip(probs, Xs):
+        x[q.n_owned:] = 7.0
+    Xo, Yo = [x.copy() for x in Xs], [np.zeros_like(x) for x in Xs]
+    W.hx_apply(Xo, Yo, True, True)
+    for cb in (1, 3):
+        PA = ref.PartitionedApply(W, cell_block=cb)
+        Xr, Yr = [x.copy() for x in Xs], [np.full_like(x, 3.0) for x in Xs]
+        PA(Xr, Yr, True, True)
+        for a, b in zip(Yr, Yo):
+            assert np.allclose(a, b, rtol=0, atol=1e-13 * np.abs(b).max())
+        for a, b in zip(Xr, Xo):
+            assert np.array_equal(a, b)

@@ -23,7 +23,7 @@ for pdl in (0, 1):
     try:
         d = json.loads(open(f"gpurun_out/r2m1/bench_c2_n{n}_pdl{pdl}.json").read().strip().splitlines()[-1])
         print(f"N={n} PDL={pdl}: value %.2f  ms/step %.3f  cell ms %.4f" % (d["value"], d["ms_per_step"], d["roofline"]["kernel_ms_per_launch"]),
-              d["chebyshev_filter"]["phase_ms_per_degree"], d["config"]["halo_transport"])
+              d["chebyshev_filter"]["phase_ms_per_degree"], d["run"]["halo_transport"])
     except Exception as e:
         print(f"N={n} PDL={pdl}: unreadable: {e}")
 PY

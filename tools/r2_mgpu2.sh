@@ -23,7 +23,7 @@ for ov in (1, 0):
     try:
         d = json.loads(open(f"gpurun_out/r2m2/bench_c2_n{n}_ov{ov}.json").read().strip().splitlines()[-1])
         print(f"N={n} overlap={ov}: value %.2f  ms/step %.3f  cell ms %.4f" % (d["value"], d["ms_per_step"], d["roofline"]["kernel_ms_per_launch"]),
-              d["chebyshev_filter"]["phase_ms_per_degree"], d["config"]["halo_transport"])
+              d["chebyshev_filter"]["phase_ms_per_degree"], d["run"]["halo_transport"])
     except Exception as e:
         print(f"N={n} overlap={ov}: unreadable: {e}")
 PY
