@@ -355,7 +355,8 @@ class Op:
 class CellOp(Op):
     """KohnShamOperatorContextFE-shaped operator (cell matrices + optional nonlocal projectors)."""
 
-    def __init__(self, plan: Plan, h_cell=None, with_nonlocal=True, share_identical=False):
+    def __init__(self, plan: Plan, h_cell=None, with_nonlocal=True, share_identical=False, matrices=True):
+        """matrices=False: no cell matrices yet (they are assembled on the device: FeBasis.assemble_into)"""
         super().__init__(plan)
         check(lib().hx_cellop_create(plan.h, C.byref(self.h)))
         if share_identical:
@@ -371,7 +372,8 @@ class CellOp(Op):
             a, d.cell_c = _f64(prob.cell_c); keep.append(a)
             a, d.v = _f64(prob.proj_v); keep.append(a)
             check(lib().hx_cellop_set_nonlocal(self.h, C.byref(d)))
-        self.set_matrices(prob.h_cell if h_cell is None else h_cell)
+        if matrices:
+            self.set_matrices(prob.h_cell if h_cell is None else h_cell)
 
     def set_matrices(self, h_cell: np.ndarray):
         a, p = _f64(h_cell)

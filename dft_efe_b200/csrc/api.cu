@@ -77,9 +77,7 @@ namespace hx
     HX_TRY(d_acc_rows.upload(rows));
     HX_TRY(d_acc_off.upload(off));
     HX_TRY(d_acc_pos.upload(pos));
-    const size_t m = (size_t)std::max(n_send, n_ghost) * max_block;
-    HX_TRY(d_send.alloc(m));
-    HX_TRY(d_recv.alloc(m));
+    buf_doubles = (size_t)std::max(n_send, n_ghost) * max_block; // staging buffers of the NCCL transport: allocated on its first use
     return HX_OK;
   }
 
@@ -140,6 +138,7 @@ namespace hx
       return HX_OK;
     if (h.peer)
       return peer_halo_update(p, h, X, B);
+    HX_TRY(h.ensure_staging());
     HX_TRY(launch_pack(p, X, B, h.d_owned_ids_for_targets.p, h.n_send, h.d_send.p));
     std::vector<size_t> sc(h.target_counts.size()), rc(h.ghost_procs.size());
     for (size_t i = 0; i < sc.size(); ++i)
@@ -161,6 +160,7 @@ namespace hx
       return HX_OK;
     if (h.peer)
       return peer_halo_accumulate(p, h, Y, B);
+    HX_TRY(h.ensure_staging());
     HX_TRY(launch_pack(p, Y + (size_t)h.n_owned * B, B, h.d_ghost_local_ids.p, h.n_ghost, h.d_send.p));
     std::vector<size_t> sc(h.ghost_procs.size()), rc(h.target_counts.size());
     for (size_t i = 0; i < sc.size(); ++i)
@@ -848,11 +848,13 @@ hx_plan::~hx_plan()
 }
 
 int
-hx_plan::get_scratch(size_t idx, double **out)
+hx_plan::get_scratch(size_t idx, double **out, uint32_t cols)
 {
+  // n_local x cols doubles (cols = 0: max_block), grow-only: a 60 M-DoF plan with max_block = 1024 filters 64 columns at
+  // a time and must not pay 60 GB per scratch block
   while (scratch.size() <= idx)
     scratch.push_back(new DevBuf<double>());
-  const size_t need = (size_t)n_local * max_block;
+  const size_t need = (size_t)n_local * (cols ? cols : max_block);
   if (scratch[idx]->n < need)
     HX_TRY(scratch[idx]->alloc(need));
   *out = scratch[idx]->p;
@@ -1293,6 +1295,9 @@ extern "C"
     hx_plan *p       = op->plan;
     op->have_matrices = false; // the packed layout carries the projector columns: matrices must be (re)set
     op->h_ncp.assign(nl->num_cell_proj, nl->num_cell_proj + p->C);
+    for (uint32_t c = 0; c < p->C; ++c)
+      HX_CHECK(op->h_ncp[c] <= 64, HX_ERR_UNSUPPORTED, "cell %u couples to %u projectors (the projector pre-pass holds at most 64 per cell)", c,
+               op->h_ncp[c]);
     op->sum_proj = 0;
     op->h_c_off.assign(p->C + 1, 0);
     op->h_nl_cells.clear();
@@ -1670,9 +1675,9 @@ extern "C"
     const bool   fused  = BInv->kind == HX_OP_DIAG && X != Y && BInv->variant != HX_DIAG_OEFE_GLOBAL &&
                        (BInv->variant == HX_DIAG_CFE || p->nranks == 1 || p->cheb_fusable_multirank);
     double *     s1, *s2 = nullptr;
-    HX_TRY(p->get_scratch(0, &s1));
+    HX_TRY(p->get_scratch(0, &s1, B));
     if (!fused)
-      HX_TRY(p->get_scratch(1, &s2));
+      HX_TRY(p->get_scratch(1, &s2, B));
     double *cur = X, *oth = Y; // cur = "eigenSubspaceGuess", oth = "filteredSubspace"
     // one degree of the mass-lumped path: s1 = A xc (updateGhostX), then out = ca*M^-1 s1 + cb*xc + cc*xp.  The
     // update of most rows happens inside the cell kernel's scatter (FuseArgs); the remaining owned rows (and all
@@ -1749,8 +1754,8 @@ extern "C"
     hx_plan *p = A->plan;
     HX_CHECK_B(p, B);
     double *dX, *dY;
-    HX_TRY(p->get_scratch(4, &dX));
-    HX_TRY(p->get_scratch(5, &dY));
+    HX_TRY(p->get_scratch(4, &dX, B));
+    HX_TRY(p->get_scratch(5, &dY, B));
     const size_t bytes = (size_t)p->n_local * B * sizeof(double);
     HX_CUDA(cudaMemcpyAsync(dX, Xh, bytes, cudaMemcpyHostToDevice, p->stream));
     HX_TRY(hx_chebyshev_filter(A, BInv, dX, dY, B, degree, a0, a, b));
@@ -1783,10 +1788,10 @@ extern "C"
           HX_CUDA(cudaEventCreateWithFlags(&p->pipe_ev[i], cudaEventDisableTiming));
       }
     double *dX[2], *dY[2];
-    HX_TRY(p->get_scratch(4, &dX[0]));
-    HX_TRY(p->get_scratch(5, &dY[0]));
-    HX_TRY(p->get_scratch(7, &dX[1]));
-    HX_TRY(p->get_scratch(8, &dY[1]));
+    HX_TRY(p->get_scratch(4, &dX[0], B));
+    HX_TRY(p->get_scratch(5, &dY[0], B));
+    HX_TRY(p->get_scratch(7, &dX[1], B));
+    HX_TRY(p->get_scratch(8, &dY[1], B));
     cudaEvent_t *in_done = p->pipe_ev, *comp_done = p->pipe_ev + 2, *out_done = p->pipe_ev + 4;
     const size_t bytes   = (size_t)p->n_local * B * sizeof(double);
     // nothing of an earlier call may still be using the buffers
@@ -1893,7 +1898,7 @@ extern "C"
     double *xin, *xout;
     HX_TRY(p->get_scratch(2, &xin));
     HX_TRY(p->get_scratch(3, &xout));
-    HX_TRY(p->ensure_small((size_t)B * batch + (size_t)1300 * 4096)); // S block + split-K partials (gram_block)
+    HX_TRY(p->ensure_small(gram_workspace_doubles(p, B, batch, p->n_owned))); // S block + split-K partials (gram_block)
     HX_TRY(p->ensure_pinned((size_t)B * batch * sizeof(double)));
     for (size_t i = 0; i < (size_t)B * B; ++i)
       S_host[i] = 0.0;

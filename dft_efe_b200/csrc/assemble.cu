@@ -463,12 +463,8 @@ extern "C"
       max_nq = std::max(max_nq, q);
     const uint32_t qt = (max_nq + RQ - 1) / RQ;
     HX_CHECK(qt <= 65535, HX_ERR_UNSUPPORTED, "more than 16M quadrature points per cell are not supported");
-    static bool attr_set = false;
-    if (!attr_set)
-      {
-        HX_CUDA(cudaFuncSetAttribute(rho_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RHO_SMEM));
-        attr_set = true;
-      }
+    // per launch (cheap): a second device in the same process needs the opt-in as well
+    HX_CUDA(cudaFuncSetAttribute(rho_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RHO_SMEM));
     p->mark("rho:begin");
     dim3 grid(b->C, qt);
     rho_kernel<<<grid, 256, RHO_SMEM, p->stream>>>(b->d_cells.p, b->d_basis.p, p->d_ids.p, X_dev, B, b->d_occ.p, out);

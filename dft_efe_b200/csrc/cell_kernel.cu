@@ -1554,11 +1554,13 @@ namespace hx
   // Nonlocal phase A: per projector cell, CXcell[p,v] = sum_k C_c[p + k*nP] x_c[k,v]
   // (AtomCenterNonLocalOpContextFE::applyCconjtransOnX, src/basis/AtomCenterNonLocalOpContextFE.t.cpp:889-942),
   // written to a per-(cell,projector) staging row; reduced per projector row in ascending cell order afterwards.
+  constexpr int NLA_KCH  = 256; // rows of the cell gathered per pass
+  constexpr int NLA_MAXS = 8;   // projector groups of 8 per cell held in registers: nProj_c <= 64
   __global__ void __launch_bounds__(256)
   nl_phase_a_kernel(const double *X, const uint32_t *ids, const uint32_t *nl_cells, const CellMeta *meta,
                     const double *cellC, const unsigned long long *c_off, double *cx_stage, uint32_t B)
   {
-    extern __shared__ __align__(16) double xs[]; // [n][32]
+    extern __shared__ __align__(16) double xs[]; // [NLA_KCH][32] rows of X, then [8][NLA_KCH] projector coefficients
     pdl_wait();
     pdl_launch();
     const uint32_t cell = nl_cells[blockIdx.x];
@@ -1567,47 +1569,64 @@ namespace hx
     const int      n = (int)cm.n, np = (int)cm.nproj;
     const int      lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t col  = b0 + lane;
-    // gather: 4 rows per warp in flight (row id -> row is a dependent pair of loads)
-    for (int k0 = warp; k0 < n; k0 += 32)
+    const double * Cc   = cellC + c_off[cell];
+    double *       cs   = xs + (size_t)NLA_KCH * 32;
+    double         acc[NLA_MAXS];
+#pragma unroll
+    for (int g = 0; g < NLA_MAXS; ++g)
+      acc[g] = 0.0;
+    // the rows of the cell pass through shared memory NLA_KCH at a time (any cell size fits); every projector's sum runs
+    // over k in ascending order across the passes, so the result does not depend on the chunking
+    for (int k0 = 0; k0 < n; k0 += NLA_KCH)
       {
-        uint32_t r[4];
-        double   v[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-          r[u] = (k0 + 8 * u < n) ? __ldg(ids + cm.ids_off + k0 + 8 * u) : 0u;
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-          v[u] = (k0 + 8 * u < n && col < B) ? __ldg(X + (size_t)r[u] * B + col) : 0.0;
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-          if (k0 + 8 * u < n)
-            xs[(k0 + 8 * u) * 32 + lane] = v[u];
-      }
-    __syncthreads();
-    // C_c (np x n, projector index fastest) is staged through shared memory 8 projectors at a time, so the dot
-    // products read it as broadcasts instead of a chain of dependent global loads
-    const double *Cc = cellC + c_off[cell];
-    double *      cs = xs + (size_t)n * 32; // [8][n]
-    for (int p0 = 0; p0 < np; p0 += 8)
-      {
-        const int pc = min(8, np - p0);
+        const int kc = min(NLA_KCH, n - k0);
         __syncthreads();
-        for (int i = threadIdx.x; i < pc * n; i += blockDim.x)
+        // gather: 4 rows per warp in flight (row id -> row is a dependent pair of loads)
+        for (int kk = warp; kk < kc; kk += 32)
           {
-            const int k = i / pc, q = i % pc;
-            cs[q * n + k] = __ldg(Cc + (size_t)(p0 + q) + (size_t)k * np);
+            uint32_t r[4];
+            double   v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              r[u] = (kk + 8 * u < kc) ? __ldg(ids + cm.ids_off + k0 + kk + 8 * u) : 0u;
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              v[u] = (kk + 8 * u < kc && col < B) ? __ldg(X + (size_t)r[u] * B + col) : 0.0;
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (kk + 8 * u < kc)
+                xs[(kk + 8 * u) * 32 + lane] = v[u];
           }
-        __syncthreads();
-        if (warp < pc)
+        // C_c (np x n, projector index fastest) is staged 8 projectors at a time, so the dot products read it as
+        // broadcasts instead of a chain of dependent global loads
+#pragma unroll
+        for (int g = 0; g < NLA_MAXS; ++g)
           {
-            const double *cr = cs + warp * n;
-            double        s  = 0.0;
-            for (int k = 0; k < n; ++k)
-              s += cr[k] * xs[k * 32 + lane];
-            if (col < B)
-              cx_stage[(size_t)(cm.proj_off + p0 + warp) * B + col] = s;
+            const int p0 = g * 8;
+            if (p0 >= np)
+              break;
+            const int pc = min(8, np - p0);
+            __syncthreads();
+            for (int i = threadIdx.x; i < pc * kc; i += blockDim.x)
+              {
+                const int k = i / pc, q = i % pc;
+                cs[q * NLA_KCH + k] = __ldg(Cc + (size_t)(p0 + q) + (size_t)(k0 + k) * np);
+              }
+            __syncthreads();
+            if (warp < pc)
+              {
+                const double *cr = cs + warp * NLA_KCH;
+                double        s_ = acc[g];
+                for (int k = 0; k < kc; ++k)
+                  s_ += cr[k] * xs[k * 32 + lane];
+                acc[g] = s_;
+              }
           }
       }
+#pragma unroll
+    for (int g = 0; g < NLA_MAXS; ++g)
+      if (g * 8 + warp < np && col < B)
+        cx_stage[(size_t)(cm.proj_off + g * 8 + warp) * B + col] = acc[g];
   }
 
   // CX[row,:] = V[row] * sum over the row's staging slots (fixed order)   [reduce + (single rank) V scale]
@@ -1652,7 +1671,7 @@ namespace hx
     const uint32_t ncell = (uint32_t)op->h_nl_cells.size();
     if (ncell)
       {
-        const size_t smem = (size_t)p->max_n * (32 + 8) * sizeof(double);
+        const size_t smem = (size_t)NLA_KCH * (32 + 8) * sizeof(double);
         HX_CUDA(cudaFuncSetAttribute(nl_phase_a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         dim3 grid(ncell, (B + 31) / 32);
         HX_CUDA(launch_pdl(nl_phase_a_kernel, grid, 256, smem, p->stream, X, p->d_ids.p, op->d_nl_cells.p, op->d_meta.p,

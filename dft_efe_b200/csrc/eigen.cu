@@ -43,9 +43,9 @@ namespace hx
     hx_plan *p = op->plan;
     batch      = std::max(1u, std::min(batch, B));
     double *xin, *xout;
-    HX_TRY(p->get_scratch(2, &xin));
-    HX_TRY(p->get_scratch(3, &xout));
-    HX_TRY(p->ensure_small((size_t)B * batch + (size_t)1300 * 4096)); // S block + split-K partials (gram_block)
+    HX_TRY(p->get_scratch(2, &xin, batch));
+    HX_TRY(p->get_scratch(3, &xout, batch));
+    HX_TRY(p->ensure_small(gram_workspace_doubles(p, B, batch, p->n_owned))); // S block + split-K partials (gram_block)
     for (uint32_t j0 = 0; j0 < B; j0 += batch)
       {
         const uint32_t b = std::min(batch, B - j0);
@@ -76,8 +76,12 @@ namespace hx
   static int
   rotation_device(hx_plan *p, double *X, uint32_t B, const double *Q_dev, int transpose, int lowerTri)
   {
-    double *tmp;
-    HX_TRY(p->get_scratch(2, &tmp));
+    // the rotation runs over row slabs whose image fits the scratch block (the reference rotates SUBSPACE_ROT_DOF_BATCH rows
+    // at a time, ElpaScalapackOperations.t.cpp:303-330): about 1 GB, never the whole block
+    const size_t   slab_rows = std::max<size_t>(64, std::min<size_t>(p->n_owned, ((size_t)1 << 27) / std::max(B, 1u)) / 64 * 64);
+    const uint32_t tmp_cols  = (uint32_t)std::max<size_t>(1, (slab_rows * B + p->n_local - 1) / std::max<size_t>(p->n_local, 1));
+    double *       tmp;
+    HX_TRY(p->get_scratch(2, &tmp, tmp_cols));
     const double *qeff = Q_dev; // row-major Qeff[i*B+j] = Q(j,i): the column-major storage of Q itself
     if (transpose)
       {
@@ -88,7 +92,7 @@ namespace hx
         qeff = p->d_dense_q.p;
       }
     p->mark("rotate:begin");
-    HX_TRY(rotate(p, X, B, p->n_owned, qeff, transpose, lowerTri, tmp));
+    HX_TRY(rotate(p, X, B, p->n_owned, qeff, transpose, lowerTri, tmp, slab_rows));
     p->mark(lowerTri ? "rotate-lower" : "rotate");
     return HX_OK;
   }
@@ -447,9 +451,9 @@ extern "C"
     HX_CHECK_B(p, B);
     HX_CHECK(batch >= 1 && eigenSubspaceGuess != eigenVectors, HX_ERR_INVALID, "bad batch / aliasing blocks");
     batch = std::min(batch, B);
-    double *xin, *xout;
-    HX_TRY(p->get_scratch(4, &xin));
-    HX_TRY(p->get_scratch(5, &xout));
+    double *xin, *xout; // (blocks 0-3 and 6 belong to the filters, 2-3 to the Gram / rotation steps)
+    HX_TRY(p->get_scratch(4, &xin, batch));
+    HX_TRY(p->get_scratch(5, &xout, batch));
     // [CF] column-batched filter (ChebyshevFilteredEigenSolver.t.cpp:231-335): the batch is copied out of the guess,
     // filtered, and copied into BOTH blocks
     for (uint32_t j0 = 0; j0 < B; j0 += batch)

@@ -306,12 +306,24 @@ namespace hx
     return HX_OK;
   }
 
-  // upper bound of the split count gram_block will choose (for workspace sizing)
-  uint32_t
-  gram_max_split(uint32_t M, uint32_t N)
+  // doubles gram_block needs behind S_dev for an M x N block over nOwned rows: the block itself + one partial per K split
+  // (the same split counts gram_block chooses)
+  size_t
+  gram_workspace_doubles(const hx_plan *p, uint32_t M, uint32_t N, size_t nOwned)
   {
-    const uint32_t tiles = ((M + GT - 1) / GT) * ((N + GT - 1) / GT);
-    return std::max(1u, (592 + tiles - 1) / tiles) + 1;
+    uint32_t nSplit;
+    if (M <= 32 && N <= 32)
+      nSplit = 2u * (uint32_t)std::max(p->sm_count, 1);
+    else
+      {
+        const uint32_t tilesM = (M + GT - 1) / GT, tilesN = (N + GT - 1) / GT;
+        uint32_t       active = 0;
+        for (uint32_t tn = 0; tn < tilesN; ++tn)
+          active += tilesM > tn ? tilesM - tn : 0;
+        nSplit = std::max(1u, 4u * (uint32_t)std::max(p->sm_count, 1) / std::max(active, 1u));
+      }
+    nSplit = (uint32_t)std::max<size_t>(1, std::min<size_t>(nSplit, (nOwned + 255) / 256)) + 1; // + 1: slab rounding
+    return (size_t)M * N * (1 + (size_t)nSplit);
   }
 
   // ---------------------------------------------------------------------------------------------------
@@ -488,7 +500,7 @@ namespace hx
 
   int
   rotate(hx_plan *p, double *X, uint32_t B, size_t nOwned, const double *Q_dev, int transpose, int lowerTri,
-         double *tmp)
+         double *tmp, size_t tmp_rows)
   {
     if (nOwned == 0)
       return HX_OK;
@@ -501,14 +513,21 @@ namespace hx
         HX_CUDA(cudaGetLastError());
         return HX_OK;
       }
+    // a row's image depends on that row only: slabs of tmp_rows rows (a multiple of the tile height) are rotated into the
+    // scratch block and copied back in place
     const uint32_t tilesN  = (B + GT - 1) / GT;
-    const size_t   tilesM  = (nOwned + GT - 1) / GT;
     const int      aligned = (B % 2 == 0) && (((uintptr_t)X & 15) == 0) && (((uintptr_t)Q_dev & 15) == 0);
-    rotate_kernel<<<(unsigned)(tilesM * tilesN), 256, 0, p->stream>>>(X, B, nOwned, Q_dev, tmp, lowerTri, transpose,
-                                                                      aligned);
-    p->launches++;
-    HX_CUDA(cudaGetLastError());
-    HX_CUDA(cudaMemcpyAsync(X, tmp, nOwned * B * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
+    const size_t   slab    = tmp_rows ? std::max<size_t>(GT, tmp_rows / GT * GT) : nOwned;
+    for (size_t r0 = 0; r0 < nOwned; r0 += slab)
+      {
+        const size_t rows   = std::min(slab, nOwned - r0);
+        const size_t tilesM = (rows + GT - 1) / GT;
+        double *     Xs     = X + r0 * B;
+        rotate_kernel<<<(unsigned)(tilesM * tilesN), 256, 0, p->stream>>>(Xs, B, rows, Q_dev, tmp, lowerTri, transpose, aligned);
+        p->launches++;
+        HX_CUDA(cudaGetLastError());
+        HX_CUDA(cudaMemcpyAsync(Xs, tmp, rows * B * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
+      }
     return HX_OK;
   }
 } // namespace hx

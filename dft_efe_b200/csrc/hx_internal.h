@@ -163,7 +163,17 @@ namespace hx
     // accumulate side: unique owned rows receiving halo contributions -> ordered buffer positions
     uint32_t              n_acc_rows = 0;
     DevBuf<uint32_t>      d_acc_rows, d_acc_off, d_acc_pos;
-    DevBuf<double>        d_send, d_recv; // sized for max_block
+    DevBuf<double>        d_send, d_recv; // NCCL transport only; sized for max_block on first use
+    size_t                buf_doubles = 0;
+    int
+    ensure_staging()
+    {
+      if (d_send.n < buf_doubles)
+        HX_TRY(d_send.alloc(buf_doubles));
+      if (d_recv.n < buf_doubles)
+        HX_TRY(d_recv.alloc(buf_doubles));
+      return HX_OK;
+    }
     int
     init(const hx_halo_desc &h, uint32_t max_block);
   };
@@ -447,7 +457,7 @@ struct hx_plan
 
   ~hx_plan();
   int
-  get_scratch(size_t idx, double **p); // n_local * max_block doubles
+  get_scratch(size_t idx, double **p, uint32_t cols = 0); // n_local * cols doubles (0: max_block), grow-only
   int
   ensure_small(size_t doubles);
   int
@@ -535,14 +545,14 @@ namespace hx
   int gram_block(hx_plan *p, const double *X, uint32_t B, uint32_t j0, const double *OpXb, uint32_t b,
                  size_t nOwned, double *S_dev);
   int rotate(hx_plan *p, double *X, uint32_t B, size_t nOwned, const double *Q_dev, int transpose, int lowerTri,
-             double *tmp);
+             double *tmp, size_t tmp_rows = 0); // tmp holds tmp_rows x B doubles (0: nOwned rows)
   // api.cu helpers shared with eigen.cu
   int op_apply(hx_op *op, double *X, double *Y, uint32_t B, int ugx, int ugy);
   int copy_cols(hx_plan *p, const double *src, uint32_t ldsrc, uint32_t c0s, double *dst, uint32_t lddst, uint32_t c0d,
                 uint32_t ncols, size_t nrows);
   int halo_update(hx_plan *p, Halo &h, double *X, uint32_t B);
   int plan_sync(hx_plan *p); // stream synchronisation + status of the peer-memory halos
-  uint32_t gram_max_split(uint32_t M, uint32_t N);
+  size_t gram_workspace_doubles(const hx_plan *p, uint32_t M, uint32_t N, size_t nOwned);
   // dense.cu: B x B subspace problems on the device (cuSOLVER, resolved with dlopen)
   struct Dense;
   void dense_destroy(Dense *d);

@@ -120,6 +120,7 @@ class MeshSpec:
     nranks: int = 1
     seed: int = 1234
     with_k_cell: bool = True            # also build the Laplace cell matrices (Poisson tests); off for the big bench meshes
+    with_h_cell: bool = True            # build the Hamiltonian cell matrices on the host (off: they are assembled on the device)
 
 
 @dataclass
@@ -639,8 +640,8 @@ def build_problem(spec: MeshSpec, only_rank: Optional[int] = None) -> List[RankP
         off1 = np.concatenate(([0], np.cumsum(ncd64)))
         off2 = np.concatenate(([0], np.cumsum(ncd64 * ncd64)))
         ids = np.zeros(int(off1[-1]), np.int64)
-        h_cell = np.empty(int(off2[-1]))
-        k_cell = np.empty(int(off2[-1])) if spec.with_k_cell else None
+        h_cell = np.empty(int(off2[-1])) if spec.with_h_cell else None
+        k_cell = np.empty(int(off2[-1])) if (spec.with_k_cell and spec.with_h_cell) else None
         plain = nenr_c == 0
         for s_ in (1, 2):
             m = plain & (size[cells] == s_)
@@ -652,7 +653,7 @@ def build_problem(spec: MeshSpec, only_rank: Optional[int] = None) -> List[RankP
             # cells at a time (a 7 M-DoF order-6 mesh has 31 GB of cell matrices)
             mi = np.nonzero(m)[0]
             brk = np.nonzero(np.diff(mi) != 1)[0] + 1
-            for run in np.split(mi, brk):
+            for run in (np.split(mi, brk) if h_cell is not None else []):
                 for c0 in range(0, len(run), 256):
                     rr = run[c0:c0 + 256]
                     a_, b_ = int(off2[rr[0]]), int(off2[rr[-1] + 1])
