@@ -309,21 +309,30 @@ namespace hx
   // doubles gram_block needs behind S_dev for an M x N block over nOwned rows: the block itself + one partial per K split
   // (the same split counts gram_block chooses)
   size_t
-  gram_workspace_doubles(const hx_plan *p, uint32_t M, uint32_t N, size_t nOwned)
+  gram_workspace_doubles(const hx_plan *p, uint32_t B, uint32_t batch, size_t nOwned)
   {
-    uint32_t nSplit;
-    if (M <= 32 && N <= 32)
-      nSplit = 2u * (uint32_t)std::max(p->sm_count, 1);
-    else
+    // the column batches of computeXTransOpX: block j0 is (B - j0) x b; the later (smaller) blocks have fewer active tiles
+    // and are split further, so the maximum is taken over all of them
+    batch        = std::max(1u, std::min(batch, B));
+    size_t worst = 0;
+    for (uint32_t j0 = 0; j0 < B; j0 += batch)
       {
-        const uint32_t tilesM = (M + GT - 1) / GT, tilesN = (N + GT - 1) / GT;
-        uint32_t       active = 0;
-        for (uint32_t tn = 0; tn < tilesN; ++tn)
-          active += tilesM > tn ? tilesM - tn : 0;
-        nSplit = std::max(1u, 4u * (uint32_t)std::max(p->sm_count, 1) / std::max(active, 1u));
+        const uint32_t M = B - j0, N = std::min(batch, B - j0);
+        uint32_t       nSplit;
+        if (M <= 32 && N <= 32)
+          nSplit = 2u * (uint32_t)std::max(p->sm_count, 1);
+        else
+          {
+            const uint32_t tilesM = (M + GT - 1) / GT, tilesN = (N + GT - 1) / GT;
+            uint32_t       active = 0;
+            for (uint32_t tn = 0; tn < tilesN; ++tn)
+              active += tilesM > tn ? tilesM - tn : 0;
+            nSplit = std::max(1u, 4u * (uint32_t)std::max(p->sm_count, 1) / std::max(active, 1u));
+          }
+        nSplit = (uint32_t)std::max<size_t>(1, std::min<size_t>(nSplit, (nOwned + 255) / 256)) + 1; // + 1: slab rounding
+        worst  = std::max(worst, (size_t)M * N * (1 + (size_t)nSplit));
       }
-    nSplit = (uint32_t)std::max<size_t>(1, std::min<size_t>(nSplit, (nOwned + 255) / 256)) + 1; // + 1: slab rounding
-    return (size_t)M * N * (1 + (size_t)nSplit);
+    return worst;
   }
 
   // ---------------------------------------------------------------------------------------------------

@@ -552,7 +552,7 @@ namespace hx
                 uint32_t ncols, size_t nrows);
   int halo_update(hx_plan *p, Halo &h, double *X, uint32_t B);
   int plan_sync(hx_plan *p); // stream synchronisation + status of the peer-memory halos
-  size_t gram_workspace_doubles(const hx_plan *p, uint32_t M, uint32_t N, size_t nOwned);
+  size_t gram_workspace_doubles(const hx_plan *p, uint32_t B, uint32_t batch, size_t nOwned); // all column batches of a B-wide block
   // dense.cu: B x B subspace problems on the device (cuSOLVER, resolved with dlopen)
   struct Dense;
   void dense_destroy(Dense *d);

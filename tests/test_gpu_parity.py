@@ -361,7 +361,7 @@ def test_global_enrichment_overlap_inverse(capi, prob_full, B):
     Xo, Yo = X.copy(), np.zeros_like(X)
     W.minv_apply_global_enrichment([Xo], [Yo], blk.ravel(order="F"), True, True)
     assert rel_l2_per_vector(dY.download(), Yo) < 1e-13
-    assert np.array_equal(dX.download(), Xo)
+    assert rel_l2_per_vector(dX.download(), Xo) < 1e-14   # X is filled through the constraints, like the reference's apply
     if B % 2 == 0:
         H = capi.CellOp(plan)
         dX, dF = plan.block(B, X), plan.block(B)
