@@ -11,7 +11,7 @@ from typing import Optional
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libhxb200.so")
+LIB_PATH = os.environ.get("HXB200_LIB") or os.path.join(_HERE, "lib", "libhxb200.so")  # HXB200_LIB: A/B build (tools/build_variants.py)
 
 u32p = C.POINTER(C.c_uint32)
 f64p = C.POINTER(C.c_double)
