@@ -126,6 +126,28 @@ namespace hx
                  "r"(parity), "r"(0x989680u) // suspend-time hint: the warp sleeps in hardware until the phase completes
                  : "memory");
   }
+  // long waits: a warp suspended in try_wait is woken by every mbarrier event of the CTA (hundreds per work item) and
+  // re-checks each time; polling with a timed sleep issues an order of magnitude fewer instructions
+  template <int NS_>
+  __device__ __forceinline__ void
+  mbar_wait_sleep(uint32_t bar, uint32_t parity)
+  {
+    uint32_t done;
+    for (;;)
+      {
+        asm volatile("{\n"
+                     ".reg .pred p;\n"
+                     "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+                     "selp.u32 %0, 1, 0, p;\n"
+                     "}"
+                     : "=r"(done)
+                     : "r"(bar), "r"(parity)
+                     : "memory");
+        if (done)
+          break;
+        asm volatile("nanosleep.u32 %0;" ::"n"(NS_));
+      }
+  }
   __device__ __forceinline__ void
   bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
   {
@@ -217,8 +239,11 @@ namespace hx
   constexpr int STHREADS     = SWARPS * 32;
   constexpr int SROWS        = 128;              // rows of the largest chunk (16 m-tiles)
   constexpr int PIPE_THREADS = (DWARPS + SWARPS + 4) * 32; // 512: launched with 64 registers per thread
-  constexpr int REG_DMMA     = 144;              // 128 x 144 + 256 x 40 + 128 x 32 = 512 x 64
-  constexpr int REG_SCATTER  = 40;
+  // register split (setmaxnreg): 128 x 112 + 256 x 56 + 128 x 32 = 512 x 64.  The k loop needs ~100 registers (16 accumulator
+  // pairs + fragments); 56 per scatter thread hold two rows of Y / X / Xprev in flight without spilling (with 144 / 40 and one
+  // row per batch the DMMA warps spent 20 % of their time waiting for the accumulator tile: 0.71 -> 0.63 ms at C2)
+  constexpr int REG_DMMA     = 112;
+  constexpr int REG_SCATTER  = 56;
   constexpr int REG_PRODUCER = 32;
   // build-time tuning knobs of the pipelined kernel (tools/build_variants.py compiles A/B libraries with other values)
 #ifndef HX_PIPE_REGD
@@ -228,26 +253,21 @@ namespace hx
 #define HX_PIPE_REGS REG_SCATTER
 #endif
 #ifndef HX_PIPE_RBF
-#define HX_PIPE_RBF 1 // rows per scatter batch (loads in flight per thread), Chebyshev-epilogue kernels
+#define HX_PIPE_RBF 2 // rows per scatter batch (loads in flight per thread), Chebyshev-epilogue kernels
 #endif
 #ifndef HX_PIPE_RBP
 #define HX_PIPE_RBP 2 // same, plain apply
 #endif
+#ifndef HX_PIPE_SLEEP_NS
+#define HX_PIPE_SLEEP_NS 0 // > 0: the scatter warps wait for the accumulators with test_wait + nanosleep instead of try_wait
+#endif
 #ifndef HX_PIPE_NACC
 #define HX_PIPE_NACC 1 // accumulator tiles between the DMMA and the scatter warps
-#endif
-#ifndef HX_PIPE_HELPER
-#define HX_PIPE_HELPER 0 // 1: a publisher warp stores the item's stamp (the fence leaves the scatter warps' critical path)
-#endif
-#ifndef HX_PIPE_DINVPF
-#define HX_PIPE_DINVPF 0 // 1: a*dinv of the next chunk's rows is requested while the current chunk is being stored
 #endif
   constexpr int SMP_FULL     = 0;                // MAX_STAGES x 8
   constexpr int SMP_EMPTY    = 64;               // MAX_STAGES x 8
   constexpr int SMP_ACCFULL  = 128;              // (+16 per tile) accumulators of a chunk are in the shared tile
   constexpr int SMP_ACCFREE  = 136;              // (+16 per tile) the scatter warps have read them
-  constexpr int SMP_ITEMDONE = 160;              // (+16 per parity of the item counter) the scatter warps have stored the item's rows
-  constexpr int SMP_PUBLISHED = 168;             // (+16 per parity) the publisher warp has stored the item's stamp
   constexpr int SMP_Q        = 256;              // QD x 32 item queue
   constexpr int SMP_REC      = SMP_Q + QD * 32;  // 2 x SROWS x (16 + 8): row records {byte offset, flags} + dinv, current / next chunk
   constexpr int SMP_HEADER   = SMP_REC + 2 * SROWS * 24; // 6912
@@ -329,11 +349,6 @@ namespace hx
           {
             mbar_init(sbase + SMP_ACCFULL + 16 * b, DWARPS);
             mbar_init(sbase + SMP_ACCFREE + 16 * b, SWARPS);
-          }
-        for (int b = 0; b < 2; ++b)
-          {
-            mbar_init(sbase + SMP_ITEMDONE + 16 * b, SWARPS);
-            mbar_init(sbase + SMP_PUBLISHED + 16 * b, 1);
           }
         for (int q = 0; q < QD; ++q)
           st_volatile_shared(sbase + SMP_Q + 32 * q, 0u);
@@ -542,31 +557,6 @@ namespace hx
                   }
               }
           }
-#if HX_PIPE_HELPER
-        else if (warp == DWARPS + SWARPS + 2)
-          {
-            // ---------------- publisher warp (one lane): the item's stamp, once the scatter warps have stored its rows ----------------
-            // chain of a stamp: scatter threads st.cg -> __syncwarp -> lane 0 mbarrier.arrive (release.cta) -> this thread's
-            // mbarrier.try_wait (acquire.cta) -> st.release.gpu
-            if (lane != 0)
-              return;
-            for (uint32_t it = 0;; ++it)
-              {
-                const uint32_t slot = sbase + SMP_Q + 32 * (it % QD);
-                uint32_t       tag;
-                while ((tag = ld_volatile_shared(slot)) == 0u)
-                  {
-                  }
-                if (tag == ITEM_END)
-                  break;
-                const uint32_t b = it & 1u, ph = (it >> 1) & 1u;
-                mbar_wait(sbase + SMP_ITEMDONE + 16 * b, ph);
-                st_release_gpu(a.flags + (tag - 1u), a.epoch);
-                st_volatile_shared(slot, 0u); // queue slot free again
-                mbar_arrive(sbase + SMP_PUBLISHED + 16 * b);
-              }
-          }
-#endif
         return;
       }
     else if (warp >= DWARPS)
@@ -591,10 +581,6 @@ namespace hx
         // read-modify-written, so a chunk starts with it in a register.
         bool     have_next = false;
         uint32_t idx_next  = 0xffffffffu;
-#if HX_PIPE_DINVPF
-        bool   have_dinv = false;
-        double dinv_next = 0.0;
-#endif
         for (uint32_t it = 0;; ++it)
           {
             const uint32_t slot = sbase + SMP_Q + 32 * (it % QD);
@@ -631,11 +617,7 @@ namespace hx
                   {
                     if (FUSE && idx != 0xffffffffu && (idx & (HX_DEST_LASTF | HX_DEST_STAGED)) == HX_DEST_LASTF)
                       {
-#if HX_PIPE_DINVPF
-                        dinv_r = __dmul_rn(a.f_a, have_dinv ? dinv_next : __ldg(a.f_dinv + HX_DEST_ROW(idx))); // s = a*dinv of the row
-#else
                         dinv_r = __dmul_rn(a.f_a, __ldg(a.f_dinv + HX_DEST_ROW(idx))); // s = a*dinv of the row
-#endif
                         if (fc)
                           {
                             // this row's last toucher will read xprev[row, tile]: pull the lines into L2 now
@@ -720,7 +702,11 @@ namespace hx
                   }
                 bar_scatter(); // records of the chunk are in shared memory; the predecessors have stored
                 const uint32_t ab = (NACC == 2) ? (g & 1u) : 0u, aph = (NACC == 2) ? ((g >> 1) & 1u) : (g & 1u);
+#if HX_PIPE_SLEEP_NS > 0
+                mbar_wait_sleep<HX_PIPE_SLEEP_NS>(sbase + SMP_ACCFULL + 16 * ab, aph);
+#else
                 mbar_wait(sbase + SMP_ACCFULL + 16 * ab, aph);
+#endif
                 const uint32_t acct = accb + ab * ACC_B;
                 const unsigned long long colb = (unsigned long long)col * 8ull;
 #pragma unroll 1
@@ -834,23 +820,7 @@ namespace hx
                 __syncwarp();
                 if (lane == 0)
                   mbar_arrive(sbase + SMP_ACCFREE + 16 * ab);
-#if HX_PIPE_DINVPF
-                // the next chunk's destination codes have arrived long ago: request a*dinv of its fusable rows now
-                have_dinv = have_next;
-                if (FUSE && have_next && st < SROWS && idx_next != 0xffffffffu && (idx_next & (HX_DEST_LASTF | HX_DEST_STAGED)) == HX_DEST_LASTF)
-                  dinv_next = __ldg(a.f_dinv + HX_DEST_ROW(idx_next));
-#endif
               }
-#if HX_PIPE_HELPER
-            // every row this warp owns is stored: tell the publisher warp (which has finished with this barrier's previous item)
-            __syncwarp();
-            if (lane == 0)
-              {
-                const uint32_t b = it & 1u, ph = (it >> 1) & 1u;
-                mbar_wait(sbase + SMP_PUBLISHED + 16 * b, ph ^ 1u);
-                mbar_arrive(sbase + SMP_ITEMDONE + 16 * b);
-              }
-#else
             // every row of the item is stored: publish its stamp (release, cumulative at gpu scope)
             bar_scatter();
             if (st == 0)
@@ -858,7 +828,6 @@ namespace hx
                 st_release_gpu(a.flags + w, a.epoch);
                 st_volatile_shared(slot, 0u); // queue slot free again
               }
-#endif
           }
       }
     else
@@ -1588,7 +1557,7 @@ namespace hx
             if (fused_applied)
               *fused_applied = true;
           }
-        // rows per scatter batch (loads in flight per thread): what the 40 registers of a scatter thread hold
+        // rows per scatter batch (loads in flight per thread): what the registers of a scatter thread hold
         constexpr int RBF = HX_PIPE_RBF, RBP = HX_PIPE_RBP;
 #define HX_PIPE(NT_, MTW_, KC_)                                                                     \
   (fz ? launch_pipe<NT_, MTW_, KC_, true, 2, true, RBF, HX_PIPE_NACC, HX_PIPE_REGD, HX_PIPE_REGS>(op, a) :                 \
