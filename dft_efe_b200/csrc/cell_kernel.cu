@@ -126,28 +126,6 @@ namespace hx
                  "r"(parity), "r"(0x989680u) // suspend-time hint: the warp sleeps in hardware until the phase completes
                  : "memory");
   }
-  // long waits: a warp suspended in try_wait is woken by every mbarrier event of the CTA (hundreds per work item) and
-  // re-checks each time; polling with a timed sleep issues an order of magnitude fewer instructions
-  template <int NS_>
-  __device__ __forceinline__ void
-  mbar_wait_sleep(uint32_t bar, uint32_t parity)
-  {
-    uint32_t done;
-    for (;;)
-      {
-        asm volatile("{\n"
-                     ".reg .pred p;\n"
-                     "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-                     "selp.u32 %0, 1, 0, p;\n"
-                     "}"
-                     : "=r"(done)
-                     : "r"(bar), "r"(parity)
-                     : "memory");
-        if (done)
-          break;
-        asm volatile("nanosleep.u32 %0;" ::"n"(NS_));
-      }
-  }
   __device__ __forceinline__ void
   bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
   {
@@ -257,9 +235,6 @@ namespace hx
 #endif
 #ifndef HX_PIPE_RBP
 #define HX_PIPE_RBP 2 // same, plain apply
-#endif
-#ifndef HX_PIPE_SLEEP_NS
-#define HX_PIPE_SLEEP_NS 0 // > 0: the scatter warps wait for the accumulators with test_wait + nanosleep instead of try_wait
 #endif
 #ifndef HX_PIPE_NACC
 #define HX_PIPE_NACC 1 // accumulator tiles between the DMMA and the scatter warps
@@ -702,11 +677,7 @@ namespace hx
                   }
                 bar_scatter(); // records of the chunk are in shared memory; the predecessors have stored
                 const uint32_t ab = (NACC == 2) ? (g & 1u) : 0u, aph = (NACC == 2) ? ((g >> 1) & 1u) : (g & 1u);
-#if HX_PIPE_SLEEP_NS > 0
-                mbar_wait_sleep<HX_PIPE_SLEEP_NS>(sbase + SMP_ACCFULL + 16 * ab, aph);
-#else
                 mbar_wait(sbase + SMP_ACCFULL + 16 * ab, aph);
-#endif
                 const uint32_t acct = accb + ab * ACC_B;
                 const unsigned long long colb = (unsigned long long)col * 8ull;
 #pragma unroll 1
