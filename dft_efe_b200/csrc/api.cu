@@ -171,6 +171,24 @@ namespace hx
     return launch_add_rows(p, h.d_recv.p, B, h.d_acc_rows.p, h.d_acc_off.p, h.d_acc_pos.p, h.n_acc_rows, Y);
   }
 
+  // accumulateAddLocallyOwned + updateGhostValues of the same vector (a sum over the sharing ranks that everybody needs):
+  // one single-block kernel when the halo is small and the peer transport is up (HXB200_NL_FUSED=0: the two exchanges)
+  static int
+  halo_accumulate_update(hx_plan *p, Halo &h, double *X, uint32_t B)
+  {
+    if (p->nranks == 1)
+      return HX_OK;
+    HX_CHECK(p->comm != nullptr, HX_ERR_COMM, "nranks > 1 but no communicator attached (hx_plan_attach_comm)");
+    HX_TRY(halo_pick_transport(p, h));
+    if (h.n_ghost == 0 && h.n_send == 0)
+      return HX_OK;
+    static const bool fused_ok = !(getenv("HXB200_NL_FUSED") && getenv("HXB200_NL_FUSED")[0] == '0');
+    if (fused_ok && peer_acc_update_is_small(h, B))
+      return peer_halo_accumulate_update_small(p, h, X, B);
+    HX_TRY(halo_accumulate(p, h, X, B));
+    return halo_update(p, h, X, B);
+  }
+
   // ---------------------------------------------------------------------------------------------
   static int
   sm_count_for_order()
@@ -674,8 +692,7 @@ namespace hx
         if (p->nranks > 1)
           {
             // applyAllReduceOnCconjtransX + applyVOnCconjtransX
-            HX_TRY(halo_accumulate(p, op->phalo, op->d_cx.p, B));
-            HX_TRY(halo_update(p, op->phalo, op->d_cx.p, B));
+            HX_TRY(halo_accumulate_update(p, op->phalo, op->d_cx.p, B));
             HX_TRY(launch_row_scale(p, op->d_v.p, op->d_cx.p, op->d_cx.p, B, op->n_proj_local));
             p->mark("nl-halo");
           }

@@ -573,6 +573,8 @@ namespace hx
   int peer_setup(hx_plan *p, Halo &h);
   int peer_halo_update(hx_plan *p, Halo &h, double *X, uint32_t B);
   int peer_halo_accumulate(hx_plan *p, Halo &h, double *Y, uint32_t B);
+  bool peer_acc_update_is_small(const Halo &h, uint32_t B);
+  int peer_halo_accumulate_update_small(hx_plan *p, Halo &h, double *X, uint32_t B);
   int peer_check_status(Halo &h);
   // halo overlap: push only (the cell kernel unpacks), kernel arguments, closing kernels of the accumulate
   int peer_push_update(hx_plan *p, Halo &h, const double *X, uint32_t B, uint32_t *seq);

@@ -602,6 +602,119 @@ namespace hx
     return HX_OK;
   }
 
+  // ---- accumulateAddLocallyOwned followed by updateGhostValues on the same small vector, in ONE single-block kernel ----
+  // (the projector coefficients C^H X of an apply: AtomCenterNonLocalOpContextFE::applyCconjtransOnX's all-reduce over the
+  // ranks sharing an atom, src/basis/AtomCenterNonLocalOpContextFE.t.cpp:943-997 - a few rows per rank.)  The two exchanges
+  // cost four launches with a grid-wide last-block hand-over and a system fence each; here one block walks the same wire
+  // protocol (same buffers, flags, acknowledgements, same summation order at the owner), so a neighbour may run either form.
+  __global__ void __launch_bounds__(1024)
+  peer_acc_update_small_kernel(PeerDir da, PeerDir du, double *x, uint32_t n_owned, const uint32_t *gids, uint32_t n_ghost,
+                               const uint32_t *send_rows, const uint32_t *acc_rows, const uint32_t *acc_off, const uint32_t *acc_pos,
+                               uint32_t n_acc_rows, uint32_t B, uint32_t seqA, uint32_t seqU)
+  {
+    __shared__ int ok;
+    double *       xg = x + (size_t)n_owned * B;
+    if (threadIdx.x == 0)
+      {
+        // flow control of both directions: the previous messages have been consumed
+        bool o = wait_words(da.ack, da.nDst, seqA - 1u, da.status);
+        o      = o && wait_words(du.ack, du.nDst, seqU - 1u, du.status);
+        if (!o)
+          atomicExch(da.status, 1u);
+        ok = o ? 1 : 0;
+      }
+    __syncthreads();
+    // (1) accumulate, send side: my ghost rows go into their owners' buffers
+    if (ok)
+      for (size_t i = threadIdx.x; i < (size_t)da.nRows * B; i += blockDim.x)
+        {
+          const uint32_t k = (uint32_t)(i / B), c = (uint32_t)(i % B);
+          const uint32_t s = da.seg[k];
+          da.rbase[s][((size_t)da.rrowoff[s] + (k - da.segbegin[s])) * B + c] = xg[(size_t)gids[k] * B + c];
+        }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0)
+      {
+        if (ok)
+          for (uint32_t s = 0; s < da.nDst; ++s)
+            st_release_sys(da.rflag[s], seqA);
+        // (2) accumulate, receive side: owned rows += buffer rows in buffer order
+        const bool o = ok && wait_words(da.flag, da.nSrc, seqA, da.status);
+        if (ok && !o)
+          atomicExch(da.status, 1u);
+        ok = o ? 1 : 0;
+      }
+    __syncthreads();
+    if (ok)
+      for (size_t i = threadIdx.x; i < (size_t)n_acc_rows * B; i += blockDim.x)
+        {
+          const uint32_t r = (uint32_t)(i / B), v = (uint32_t)(i % B);
+          double *       y = x + (size_t)acc_rows[r] * B + v;
+          double         t = *y;
+          for (uint32_t e = acc_off[r]; e < acc_off[r + 1]; ++e)
+            t += __ldcg(da.recv + (size_t)acc_pos[e] * B + v);
+          *y = t;
+        }
+    __syncthreads();
+    // (3) update, send side: my owned rows (now complete) go into the sharers' buffers
+    if (ok)
+      for (size_t i = threadIdx.x; i < (size_t)du.nRows * B; i += blockDim.x)
+        {
+          const uint32_t k = (uint32_t)(i / B), c = (uint32_t)(i % B);
+          const uint32_t s = du.seg[k];
+          du.rbase[s][((size_t)du.rrowoff[s] + (k - du.segbegin[s])) * B + c] = x[(size_t)send_rows[k] * B + c];
+        }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0)
+      {
+        if (ok)
+          {
+            for (uint32_t s = 0; s < da.nSrc; ++s)
+              st_release_sys(da.rack[s], seqA); // the accumulate buffers have been read
+            for (uint32_t s = 0; s < du.nDst; ++s)
+              st_release_sys(du.rflag[s], seqU);
+          }
+        // (4) update, receive side
+        const bool o = ok && wait_words(du.flag, du.nSrc, seqU, du.status);
+        if (ok && !o)
+          atomicExch(du.status, 1u);
+        ok = o ? 1 : 0;
+      }
+    __syncthreads();
+    if (ok)
+      for (size_t i = threadIdx.x; i < (size_t)n_ghost * B; i += blockDim.x)
+        xg[(size_t)gids[i / B] * B + (i % B)] = __ldcg(du.recv + i);
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0 && ok)
+      for (uint32_t s = 0; s < du.nSrc; ++s)
+        st_release_sys(du.rack[s], seqU);
+  }
+
+  // at most this many doubles through one block (more: the multi-block kernels of the separate exchanges)
+  constexpr size_t PEER_SMALL_DOUBLES = 96 * 1024;
+
+  bool
+  peer_acc_update_is_small(const Halo &h, uint32_t B)
+  {
+    return h.peer != nullptr && ((size_t)h.n_ghost + h.n_send + h.n_acc_rows) * B <= PEER_SMALL_DOUBLES;
+  }
+
+  int
+  peer_halo_accumulate_update_small(hx_plan *p, Halo &h, double *X, uint32_t B)
+  {
+    PeerState *    s    = h.peer;
+    const uint32_t seqA = ++s->seqA, seqU = ++s->seqU;
+    peer_acc_update_small_kernel<<<1, 1024, 0, p->stream>>>(s->dirA, s->dirU, X, h.n_owned, h.d_ghost_local_ids.p, h.n_ghost,
+                                                         h.d_owned_ids_for_targets.p, h.d_acc_rows.p, h.d_acc_off.p, h.d_acc_pos.p,
+                                                         h.n_acc_rows, B, seqA, seqU);
+    p->launches++;
+    HX_CUDA(cudaGetLastError());
+    return HX_OK;
+  }
+
   // raised by a kernel whose wait timed out
   int
   peer_check_status(Halo &h)
