@@ -236,6 +236,12 @@ namespace hx
 #ifndef HX_PIPE_RBP
 #define HX_PIPE_RBP 2 // same, plain apply
 #endif
+#ifndef HX_PIPE_NG_SMALL
+#define HX_PIPE_NG_SMALL 3 // gather warps (1..3) of the one-m-tile-per-warp kernels (cells of <= 64 DoFs), see launch_cell_apply
+#endif
+#ifndef HX_PIPE_NG_LARGE
+#define HX_PIPE_NG_LARGE 1 // ... of the two-m-tile kernels
+#endif
 #ifndef HX_PIPE_NACC
 #define HX_PIPE_NACC 1 // accumulator tiles between the DMMA and the scatter warps
 #endif
@@ -294,7 +300,7 @@ namespace hx
                  : "memory");
   }
 
-  template <int NT, int MTW, int KCT, bool VEC, int MINB, bool FUSE, int RB, int NACC = 1, int REGD = REG_DMMA, int REGS = REG_SCATTER>
+  template <int NT, int MTW, int KCT, bool VEC, int MINB, bool FUSE, int RB, int NACC = 1, int REGD = REG_DMMA, int REGS = REG_SCATTER, int NG = 1>
   __global__ void __launch_bounds__(PIPE_THREADS, MINB) cell_apply_pipe_kernel(const CellArgs a)
   {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -317,7 +323,7 @@ namespace hx
       {
         for (uint32_t s = 0; s < NS; ++s)
           {
-            mbar_init(sbase + SMP_FULL + 8 * s, 33); // the A warp's arrive.expect_tx + 32 gather lanes (X)
+            mbar_init(sbase + SMP_FULL + 8 * s, 1 + 32 * NG); // the A warp's arrive.expect_tx + the gather lanes (X)
             mbar_init(sbase + SMP_EMPTY + 8 * s, DWARPS);
           }
         for (int b = 0; b < NACC; ++b)
@@ -452,8 +458,9 @@ namespace hx
                   }
               }
           }
-        else if (warp == DWARPS + SWARPS + 1)
+        else if (warp <= DWARPS + SWARPS + NG)
           {
+            const int gw = warp - (DWARPS + SWARPS + 1); // gather warp gw issues every NG-th row instruction of a stage
             // ---------------- gather warp: rows of X (and of V C^H X) into the B tile of every stage ----------------
             constexpr int CPR = VEC ? BT / 2 : BT; // copies per row (<= 32)
             constexpr int RPI = 32 / CPR;          // rows per warp instruction
@@ -513,6 +520,8 @@ namespace hx
 #pragma unroll
                         for (int r = 0; r < KROWS; r += RPI)
                           {
+                            if (NG > 1 && (r / RPI) % NG != gw)
+                              continue;
                             const unsigned long long rp = __shfl_sync(0xffffffffu, raddr, (kc % SPB) * KROWS + r + rr);
                             const bool               ok = (rp != 0ull) && colok;
                             const double *           src = ok ? reinterpret_cast<const double *>(rp) + col : a.X;
@@ -1436,12 +1445,12 @@ namespace hx
     return HX_OK;
   }
 
-  template <int NT, int MTW, int KCT, bool VEC, int MINB, bool FUSE, int RB, int NACC = 1, int REGD = REG_DMMA, int REGS = REG_SCATTER>
+  template <int NT, int MTW, int KCT, bool VEC, int MINB, bool FUSE, int RB, int NACC = 1, int REGD = REG_DMMA, int REGS = REG_SCATTER, int NG = 1>
   static int
   launch_pipe(hx_op *op, CellArgs a)
   {
     hx_plan *    p      = op->plan;
-    auto         k      = cell_apply_pipe_kernel<NT, MTW, KCT, VEC, MINB, FUSE, RB, NACC, REGD, REGS>;
+    auto         k      = cell_apply_pipe_kernel<NT, MTW, KCT, VEC, MINB, FUSE, RB, NACC, REGD, REGS, NG>;
     const size_t budget = 227 * 1024 / MINB - 1024; // per CTA (228 KB per SM, 1 KB reserved by the runtime per CTA)
     const size_t fixed  = SMP_HEADER + (size_t)NACC * pipe_acc_bytes(NT, MTW);
     size_t       ns     = (budget - fixed) / (size_t)pipe_stage_bytes(NT, MTW, KCT);
@@ -1530,16 +1539,20 @@ namespace hx
           }
         // rows per scatter batch (loads in flight per thread): what the registers of a scatter thread hold
         constexpr int RBF = HX_PIPE_RBF, RBP = HX_PIPE_RBP;
+ // small cells (<= 64 DoFs: 4 stages of 16 rows per item) are paced by the gather warp's cp.async issue rate: three gather warps
+        // share the rows of a stage there (order 3, B = 32: 0.505 -> 0.539 of the roofline); with 125-DoF cells one is enough
+#define HX_NG(MTW_) ((MTW_) == 1 ? HX_PIPE_NG_SMALL : HX_PIPE_NG_LARGE)
 #define HX_PIPE(NT_, MTW_, KC_)                                                                     \
-  (fz ? launch_pipe<NT_, MTW_, KC_, true, 2, true, RBF, HX_PIPE_NACC, HX_PIPE_REGD, HX_PIPE_REGS>(op, a) :                 \
-        (vec ? launch_pipe<NT_, MTW_, KC_, true, 2, false, RBP, HX_PIPE_NACC, HX_PIPE_REGD, HX_PIPE_REGS>(op, a) :         \
-               launch_pipe<NT_, MTW_, KC_, false, 2, false, RBP, HX_PIPE_NACC, HX_PIPE_REGD, HX_PIPE_REGS>(op, a)))
+  (fz ? launch_pipe<NT_, MTW_, KC_, true, 2, true, RBF, HX_PIPE_NACC, HX_PIPE_REGD, HX_PIPE_REGS, HX_NG(MTW_)>(op, a) :                 \
+        (vec ? launch_pipe<NT_, MTW_, KC_, true, 2, false, RBP, HX_PIPE_NACC, HX_PIPE_REGD, HX_PIPE_REGS, HX_NG(MTW_)>(op, a) :         \
+               launch_pipe<NT_, MTW_, KC_, false, 2, false, RBP, HX_PIPE_NACC, HX_PIPE_REGD, HX_PIPE_REGS, HX_NG(MTW_)>(op, a)))
 #define HX_PIPE_NT(MTW_, KC_) (nt == 4 ? HX_PIPE(4, MTW_, KC_) : (nt == 2 ? HX_PIPE(2, MTW_, KC_) : HX_PIPE(1, MTW_, KC_)))
         if (op->mtw == 1)
           return HX_PIPE_NT(1, 4);
         return HX_PIPE_NT(2, 2);
 #undef HX_PIPE_NT
 #undef HX_PIPE
+#undef HX_NG
       }
     while (nt > 1 && xtile_of(nt) > 200 * 1024)
       nt >>= 1;

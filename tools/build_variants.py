@@ -14,12 +14,13 @@ sys.path.insert(0, ROOT)
 from dft_efe_b200 import build as b  # noqa: E402
 
 
-def build_variant(name: str, defines: list[str], source: str = "cell_kernel.cu") -> str:
+def build_variant(name: str, defines: list[str], source: str = "cell_kernel.cu", alt_path: str | None = None) -> str:
+    """alt_path: another revision of `source` (e.g. `git show <rev>:dft_efe_b200/csrc/cell_kernel.cu > /tmp/x.cu`)"""
     b.build()
     exp = os.path.join(b.LIBDIR, "exp")
     os.makedirs(exp, exist_ok=True)
     obj = os.path.join(exp, f"{source[:-3]}_{name}.o")
-    cmd = [b._nvcc()] + b.NVCC_FLAGS + [f"-D{d}" for d in defines] + ["-c", os.path.join(b.CSRC, source), "-o", obj]
+    cmd = [b._nvcc()] + b.NVCC_FLAGS + [f"-D{d}" for d in defines] + ["-I", b.CSRC, "-c", alt_path or os.path.join(b.CSRC, source), "-o", obj]
     out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     open(obj + ".ptxas.log", "w").write(out.stdout)
     if out.returncode != 0:
@@ -35,4 +36,7 @@ if __name__ == "__main__":
     procs = []
     for spec in sys.argv[1:]:
         name, _, defs = spec.partition(":")
-        print(build_variant(name, [d for d in defs.split(",") if d]))
+        alt = None
+        if "@" in defs:  # name:DEF=1,DEF2=2@/path/to/other_revision_of_cell_kernel.cu
+            defs, _, alt = defs.partition("@")
+        print(build_variant(name, [d for d in defs.split(",") if d], alt_path=alt))
