@@ -754,6 +754,66 @@ def test_properties_at_bench_scale(capi):
         assert rel_l2_per_vector(dh8.download(), HX[:, j0:j0 + 8]) < 1e-13
 
 
+def owned_rows_by_natural_id(whole, part):
+    """Rows of the single-partition problem `whole` that hold the owned DoFs of partition `part` (RankProblem.natural_ids
+    is the partition-independent DoF id the generator keys its values on)."""
+    nat = whole.natural_ids[:whole.n_owned].astype(np.int64)
+    order = np.argsort(nat, kind="stable")
+    want = part.natural_ids[:part.n_owned].astype(np.int64)
+    pos = np.searchsorted(nat[order], want)
+    assert np.array_equal(nat[order][pos], want)
+    return order[pos]
+
+
+def test_c2_size_hx_and_filter_against_the_partitioned_oracle(capi):
+    """BASELINE configs[1] at FULL size (25^3 cells, order 4, 1 030 321 DoFs, 32 vectors, 5 atoms x 4 enrichment functions
+    + 4 projectors - the problem bench.py times) against the oracle itself, not only through properties: the oracle runs the
+    same mesh cut into one partition per host core (its result is partition independent, tests/test_oracle.py), rows are
+    matched through the partition-independent DoF ids.  One H.X apply and one fused degree-6 Chebyshev filter."""
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+    os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
+    nt = max(2, min(16, os.cpu_count() or 2))
+    B, h, nc = 32, 0.8, (25, 25, 25)
+    atoms = (0.25 + 0.5 * np.random.default_rng(7).uniform(size=(5, 3))) * (np.array(nc) * h)[None, :]
+
+    def spec(nranks):
+        return synth.MeshSpec(ncell=nc, p=4, h=h, atoms=atoms, n_enr_per_atom=4, enr_cutoff=1.6 * h, n_proj_per_atom=4,
+                              proj_cutoff=1.3 * h, nranks=nranks, boundary="dirichlet", with_k_cell=False)
+
+    whole = synth.build_problem(spec(1))[0]
+    parts = synth.build_problem(spec(nt))
+    assert whole.n_owned == 1030321 == sum(q.n_owned for q in parts)
+    deg, a0, a, b = 6, -3.0, 1.0, 400.0
+    # ---- GPU, through the C ABI ----
+    plan = capi.Plan(whole, max_block=B)
+    H = capi.CellOp(plan)
+    minv = capi.DiagOp(plan, whole.diag_inv, whole.enr_block_inv, capi.DIAG_OEFE_ATOMBLOCK)
+    X = synth.make_block(whole, B)
+    dX, dY = plan.block(B, X), plan.block(B)
+    H.apply(dX, dY, True, False)
+    Y = dY.download()
+    dX = plan.block(B, X)
+    capi.chebyshev_filter(H, minv, dX, dY, deg, a0, a, b)
+    F = dY.download()
+    del plan, H, minv, dX, dY
+    # ---- oracle, one partition per thread ----
+    orc.use_scipy_dgemm(True)
+    W = orc.OracleWorld(parts)
+    W.pool = ThreadPoolExecutor(max_workers=nt)
+    Xs = [synth.make_block(q, B) for q in parts]
+    Ys = [np.zeros_like(x) for x in Xs]
+    W.hx_apply([x.copy() for x in Xs], Ys, True, False)
+    Fs = W.chebyshev_filter([x.copy() for x in Xs], deg, a0, a, b)
+    Yo, Fo = np.zeros((whole.n_owned, B)), np.zeros((whole.n_owned, B))
+    for q, y, f in zip(parts, Ys, Fs):
+        rows = owned_rows_by_natural_id(whole, q)
+        Yo[rows] = y[:q.n_owned]
+        Fo[rows] = f[:q.n_owned]
+    assert rel_l2_per_vector(Y[:whole.n_owned], Yo) < RTOL_HX
+    assert rel_l2_per_vector(F[:whole.n_owned], Fo) < 1e-11
+
+
 def test_chebyshev_filter_against_reference_golden_fixture(capi):
     """tests/golden/ref_filter_small.npz = the reference's own compiled ChebyshevFilter template driving
     KohnShamOperatorContextFE::apply assembled from its compiled routines (tests/golden/make_golden.py): the CUDA filter
