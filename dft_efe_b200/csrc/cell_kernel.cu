@@ -204,9 +204,9 @@ namespace hx
   //     records), and thread 0 publishes the item's stamp (st.release.gpu).
   //   * warp 12, A stream: claims items from the global counter (two ahead), fetches their descriptors, queues them
   //     for the other roles and issues one cp.async.bulk (TMA) per pipeline stage.
-  //   * warp 13, gather: zero-filling cp.async of the stage's rows of X (or of V C^H X) into the padded B tile; the
+  //   * warp 13 (and 14, 15 in the kernels for cells of <= 64 DoFs), gather: zero-filling cp.async of the stage's rows of X (or of V C^H X) into the padded B tile; the
   //     64-bit source address of a row is computed once, lane-parallel, and fetched with a shuffle.
-  //   (warps 14-15 only complete the fourth warpgroup: they give their registers away and exit.)
+  //   (warps of the fourth warpgroup without a role only complete it: they give their registers away and exit.)
   // Ordering / determinism: exactly the scheme above (one chain per row in processing order, first toucher stores,
   // last toucher of a fusable row applies the recurrence), so results are bit-identical to it.
   // Memory-model chain of a stamp: scatter threads st.cg -> bar.sync(scatter warps) -> thread 0 st.release.gpu;
