@@ -177,11 +177,42 @@ def main():
     os.environ.pop("HXB200_HALO_OVERLAP")
     errs["overlap_vs_serial"] += float(np.abs(dF.download()[:probs2[rank].n_owned] - dFs.download()[:probs2[rank].n_owned]).max())
     plan2.synchronize()
+
+    # ---- small cells (order 2, no enrichment): the one-m-tile-per-warp kernels with three gather warps, each of which
+    # waits for the in-kernel ghost unpack on its own; H.X and the fused filter, overlapped against serial exchange ----
+    spec3 = synth.MeshSpec(ncell=(5, 4, 3 * world), p=2, nranks=world)
+    probs3 = synth.build_problem(spec3)
+    plan3 = capi.Plan(probs3[rank], max_block=B)
+    uid3 = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        uid3.copy_(torch.frombuffer(bytearray(capi.comm_unique_id()), dtype=torch.uint8))
+    dist.broadcast(uid3, 0)
+    plan3.attach_comm(bytes(uid3.cpu().numpy().tobytes()))
+    H3 = capi.CellOp(plan3)
+    minv3 = capi.DiagOp(plan3, probs3[rank].diag_inv, probs3[rank].enr_block_inv, capi.DIAG_CFE)
+    X3 = [synth.make_block(q, B) for q in probs3]
+    W3 = orc.OracleWorld(probs3)
+    n3 = probs3[rank].n_owned
+    dX, dY3 = plan3.block(B, X3[rank]), plan3.block(B)
+    H3.apply(dX, dY3, True, False)
+    Y3 = [np.zeros_like(x) for x in X3]
+    W3.hx_apply([x.copy() for x in X3], Y3, True, False)
+    errs["hx_small_cells"] = rel(dY3.download()[:n3], Y3[rank][:n3])
+    dX, dF3 = plan3.block(B, X3[rank]), plan3.block(B)
+    capi.chebyshev_filter(H3, minv3, dX, dF3, 5, -3.0, 1.0, 60.0)
+    F3 = W3.chebyshev_filter([x.copy() for x in X3], 5, -3.0, 1.0, 60.0, minv_variant="cfe")
+    errs["cheb_small_cells"] = rel(dF3.download()[:n3], F3[rank][:n3])
+    os.environ["HXB200_HALO_OVERLAP"] = "0"
+    dXs, dFs = plan3.block(B, X3[rank]), plan3.block(B)
+    capi.chebyshev_filter(H3, minv3, dXs, dFs, 5, -3.0, 1.0, 60.0)
+    os.environ.pop("HXB200_HALO_OVERLAP")
+    errs["overlap_vs_serial"] += float(np.abs(dF3.download()[:n3] - dFs.download()[:n3]).max())
+    plan3.synchronize()
     want = os.environ.get("HXB200_EXPECT_TRANSPORT")
     if want:
         assert plan.halo_transport() == want and plan2.halo_transport() == want, (plan.halo_transport(), want)
 
-    tol = {"minv_global_enrichment": 1e-13, "overlap_vs_serial": 0.0, "update_ghost": 0.0, "cheb_fused": 1e-11, "accumulate_add": 1e-14, "hx": 1e-12, "hx_x_modified": 1e-14, "cheb": 1e-11,
+    tol = {"hx_small_cells": 1e-12, "cheb_small_cells": 1e-11, "minv_global_enrichment": 1e-13, "overlap_vs_serial": 0.0, "update_ghost": 0.0, "cheb_fused": 1e-11, "accumulate_add": 1e-14, "hx": 1e-12, "hx_x_modified": 1e-14, "cheb": 1e-11,
            "xtopx": 1e-12, "l2": 1e-13, "lanczos": 1e-10, "chfsi_ritz": 1e-9, "eig_residuals": 1e-6}
     bad = {k: v for k, v in errs.items() if not v <= tol[k]}
     print(f"[rank {rank}/{world}] halo transport {plan.halo_transport()} " + " ".join(f"{k}={v:.2e}" for k, v in errs.items()), flush=True)
@@ -189,10 +220,11 @@ def main():
     dist.all_reduce(t)
     dist.barrier()
     # collective teardown (peer transports synchronise across ranks): operators first, then plans
-    for o in (H, minv, H2, minv2):
+    for o in (H, minv, H2, minv2, H3, minv3):
         o.destroy()
     plan.destroy()
     plan2.destroy()
+    plan3.destroy()
     dist.barrier()
     dist.destroy_process_group()
     if int(t.item()):
