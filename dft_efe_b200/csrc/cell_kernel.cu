@@ -204,8 +204,9 @@ namespace hx
   //     records), and thread 0 publishes the item's stamp (st.release.gpu).
   //   * warp 12, A stream: claims items from the global counter (two ahead), fetches their descriptors, queues them
   //     for the other roles and issues one cp.async.bulk (TMA) per pipeline stage.
-  //   * warp 13 (and 14, 15 in the kernels for cells of <= 64 DoFs), gather: zero-filling cp.async of the stage's rows of X (or of V C^H X) into the padded B tile; the
-  //     64-bit source address of a row is computed once, lane-parallel, and fetched with a shuffle.
+  //   * warp 13 (and 14, 15 in the kernels for cells of <= 64 DoFs, where the gather paces the pipeline), gather:
+  //     zero-filling cp.async of the stage's rows of X (or of V C^H X) into the padded B tile; the 64-bit source address
+  //     of a row is computed once, lane-parallel, and fetched with a shuffle.
   //   (warps of the fourth warpgroup without a role only complete it: they give their registers away and exit.)
   // Ordering / determinism: exactly the scheme above (one chain per row in processing order, first toucher stores,
   // last toucher of a fusable row applies the recurrence), so results are bit-identical to it.
@@ -1539,8 +1540,9 @@ namespace hx
           }
         // rows per scatter batch (loads in flight per thread): what the registers of a scatter thread hold
         constexpr int RBF = HX_PIPE_RBF, RBP = HX_PIPE_RBP;
- // small cells (<= 64 DoFs: 4 stages of 16 rows per item) are paced by the gather warp's cp.async issue rate: three gather warps
-        // share the rows of a stage there (order 3, B = 32: 0.505 -> 0.539 of the roofline); with 125-DoF cells one is enough
+        // small cells (<= 64 DoFs: 4 stages of 16 rows per item) are paced by the gather warp's cp.async issue rate: three
+        // gather warps share the rows of a stage there (order 3, B = 32: 0.505 -> 0.539 of the roofline); with 125-DoF
+        // cells one is enough
 #define HX_NG(MTW_) ((MTW_) == 1 ? HX_PIPE_NG_SMALL : HX_PIPE_NG_LARGE)
 #define HX_PIPE(NT_, MTW_, KC_)                                                                     \
   (fz ? launch_pipe<NT_, MTW_, KC_, true, 2, true, RBF, HX_PIPE_NACC, HX_PIPE_REGD, HX_PIPE_REGS, HX_NG(MTW_)>(op, a) :                 \
